@@ -1,0 +1,344 @@
+// Index builder on the device: fm_index:make_index/4 (fm_index.erl:127-141) -> bwt:fm/1 (bwt.erl:84-98).
+//
+// dsa:dsa/1 (dsa.erl:15-48) sorts the suffixes of Seq++"$" under byte order with '$' below ACGT; every correct
+// suffix array of that string is the same array, so the construction is free:
+//   round 0 : radix sort of all suffixes by their first 21 symbols (3 bits each, '$' = 0 so that suffixes that
+//             reach the end are ordered exactly)                                     -- cub::DeviceRadixSort
+//   round k : prefix doubling restricted to the still-tied groups: sort (group, rank[i+h]) and split
+// CUB's radix sort is the only library primitive used, and only here in the offline builder.
+// Then L[e] = Seq[SA[e]-1] ('$' for SA[e] = 0), pointers from the symbol counts (fmi.erl:66-84).
+#include <cub/device/device_radix_sort.cuh>
+
+#include "common.cuh"
+
+namespace {
+
+__device__ __forceinline__ uint64_t sym3(uint8_t c) { return c == 'A' ? 1 : c == 'C' ? 2 : c == 'G' ? 3 : 4; }
+
+// key of suffix i: 21 symbols, 3 bits each, most significant first; past the end ('$' and beyond) = 0
+__global__ void key0_kernel(const uint8_t *__restrict__ text, uint64_t len, uint64_t n, uint64_t *__restrict__ keys,
+                            uint32_t *__restrict__ idx) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint64_t k = 0;
+#pragma unroll
+    for (int t = 0; t < 21; t++) {
+        uint64_t p = i + t;
+        k = (k << 3) | (p < len ? sym3(text[p]) : 0ull);
+    }
+    keys[i] = k;
+    idx[i] = (uint32_t)i;
+}
+
+// after a sort: head flag of every run of equal keys, within [0,m)
+__global__ void heads_kernel(const uint64_t *__restrict__ keys, uint64_t m, uint32_t *__restrict__ head) {
+    uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= m) return;
+    head[p] = (p == 0 || keys[p] != keys[p - 1]) ? 1u : 0u;
+}
+
+// group head position of every slot = running maximum of (head ? p : 0): done per block with a serial fix-up
+// table of block-leading heads (simple two-level scheme)
+__global__ void block_last_head_kernel(const uint32_t *__restrict__ head, uint64_t m, uint32_t *__restrict__ blk_last) {
+    // one thread per 1024-slot block: position of the last head inside the block, or 0xFFFFFFFF
+    uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint64_t lo = b * 1024;
+    if (lo >= m) return;
+    uint64_t hi = lo + 1024 < m ? lo + 1024 : m;
+    uint32_t last = 0xFFFFFFFFu;
+    for (uint64_t p = lo; p < hi; p++) if (head[p]) last = (uint32_t)p;
+    blk_last[b] = last;
+}
+
+__global__ void carry_heads_kernel(uint32_t *blk_last, uint64_t nb) {
+    // single thread: turn "last head inside block" into "last head at or before the end of the block"
+    if (blockIdx.x || threadIdx.x) return;
+    uint32_t cur = 0;
+    for (uint64_t b = 0; b < nb; b++) {
+        if (blk_last[b] != 0xFFFFFFFFu) cur = blk_last[b];
+        blk_last[b] = cur;
+    }
+}
+
+// grp[p] = position of the head of p's group; flags slots of groups with more than one member
+__global__ void groups_kernel(const uint32_t *__restrict__ head, uint64_t m, const uint32_t *__restrict__ blk_last,
+                              uint32_t *__restrict__ grp, uint32_t *__restrict__ tied) {
+    uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint64_t lo = b * 1024;
+    if (lo >= m) return;
+    uint64_t hi = lo + 1024 < m ? lo + 1024 : m;
+    uint32_t cur = b ? blk_last[b - 1] : 0u;
+    for (uint64_t p = lo; p < hi; p++) {
+        if (head[p]) cur = (uint32_t)p;
+        grp[p] = cur;
+        bool single = head[p] && (p + 1 == m || head[p + 1]);
+        tied[p] = single ? 0u : 1u;
+    }
+}
+
+// round 0 bookkeeping: sa[p] = idx[p]; rank[idx[p]] = grp[p]
+__global__ void commit0_kernel(const uint32_t *__restrict__ idx, const uint32_t *__restrict__ grp, uint64_t n,
+                               uint32_t *__restrict__ sa, uint32_t *__restrict__ rank) {
+    uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    uint32_t i = idx[p];
+    sa[p] = i;
+    rank[i] = grp[p];
+}
+
+// compaction of the tied slots: pos[k] = k-th tied slot (ascending)
+__global__ void scatter_tied_kernel(const uint32_t *__restrict__ tied, const uint32_t *__restrict__ off, uint64_t m,
+                                    const uint32_t *__restrict__ src_pos, uint32_t *__restrict__ pos) {
+    uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= m) return;
+    if (tied[p]) pos[off[p]] = src_pos ? src_pos[p] : (uint32_t)p;
+}
+
+// keys of a doubling round over the tied slots: (group head, rank[i+h]+1 or 0 past the end)
+__global__ void keyh_kernel(const uint32_t *__restrict__ pos, uint64_t m, const uint32_t *__restrict__ sa,
+                            const uint32_t *__restrict__ rank, uint64_t n, uint64_t h, uint64_t *__restrict__ keys,
+                            uint32_t *__restrict__ idx) {
+    uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= m) return;
+    uint32_t i = sa[pos[k]];
+    uint64_t j = (uint64_t)i + h;
+    uint64_t second = j < n ? (uint64_t)rank[j] + 1 : 0ull;
+    keys[k] = ((uint64_t)rank[i] << 32) | second;
+    idx[k] = i;
+}
+
+// after sorting a doubling round: slot pos[k] receives idx[k]; its new group head is pos[grp_local[k]]
+__global__ void commith_kernel(const uint32_t *__restrict__ pos, const uint32_t *__restrict__ idx,
+                               const uint32_t *__restrict__ grp_local, uint64_t m, uint32_t *__restrict__ sa,
+                               uint32_t *__restrict__ rank) {
+    uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= m) return;
+    uint32_t i = idx[k];
+    sa[pos[k]] = i;
+    rank[i] = pos[grp_local[k]];
+}
+
+__global__ void bwt_kernel(const uint8_t *__restrict__ text, const uint32_t *__restrict__ sa, uint64_t n,
+                           uint8_t *__restrict__ L) {
+    uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    uint32_t i = sa[p];
+    L[p] = i ? text[i - 1] : (uint8_t)'$';
+}
+
+__global__ void count_kernel(const uint8_t *__restrict__ text, uint64_t len, unsigned long long *__restrict__ cnt) {
+    __shared__ unsigned int s[4];
+    if (threadIdx.x < 4) s[threadIdx.x] = 0;
+    __syncthreads();
+    unsigned int c[4] = {0, 0, 0, 0};
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += (uint64_t)gridDim.x * blockDim.x) {
+        int k = bwt_code(text[i]);
+        if (k >= 0) c[k]++;
+    }
+    for (int k = 0; k < 4; k++) atomicAdd(&s[k], c[k]);
+    __syncthreads();
+    if (threadIdx.x < 4) atomicAdd(&cnt[threadIdx.x], (unsigned long long)s[threadIdx.x]);
+}
+
+// IUPAC -> ACGT as fm_index.erl:131-135; flags 'N' and unknown symbols
+__global__ void map_acgt_kernel(const uint8_t *__restrict__ in, uint64_t len, uint8_t *__restrict__ out,
+                                uint32_t *__restrict__ flags) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= len) return;
+    uint8_t c = in[i], o;
+    switch (c) {
+    case 'A': case 'R': case 'M': case 'W': case 'V': o = 'A'; break;
+    case 'C': case 'B': case 'Y': case 'S': o = 'C'; break;
+    case 'G': case 'D': o = 'G'; break;
+    case 'T': case 'K': o = 'T'; break;
+    case 'N': o = 'A'; atomicAdd(flags, 1u); break;
+    default: o = 'A'; atomicAdd(flags + 1, 1u); break;
+    }
+    out[i] = o;
+}
+
+__global__ void synth_kernel(uint8_t *__restrict__ out, uint64_t len, uint64_t seed) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= len) return;
+    uint64_t z = seed + 0x9E3779B97F4A7C15ull * (i / 32 + 1);        // splitmix64 of the 32-base word index
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z ^= z >> 31;
+    out[i] = (uint8_t)"ACGT"[(z >> (2 * (i & 31))) & 3];
+}
+
+struct DevBuf {
+    void *p = nullptr;
+    ~DevBuf() { release(); }
+    void release() { if (p) cudaFree(p); p = nullptr; }
+    int alloc(size_t bytes) {
+        if (cudaMalloc(&p, bytes ? bytes : 16) != cudaSuccess) {
+            cudaGetLastError();
+            p = nullptr;
+            bwt_set_error("builder: device allocation of %zu bytes failed", bytes);
+            return BWT_ERR_NOMEM;
+        }
+        return BWT_OK;
+    }
+    template <typename T> T *as() { return reinterpret_cast<T *>(p); }
+};
+
+unsigned blocks_for(uint64_t n, unsigned t = 256) { return (unsigned)div_up_u64(n, t); }
+
+// group structure of a sorted key array of m slots -> grp (head position per slot), tied flags
+int compute_groups(const uint64_t *keys, uint64_t m, uint32_t *head, uint32_t *grp, uint32_t *tied, uint32_t *blk) {
+    uint64_t nb = div_up_u64(m, 1024);
+    heads_kernel<<<blocks_for(m), 256>>>(keys, m, head);
+    block_last_head_kernel<<<blocks_for(nb), 256>>>(head, m, blk);
+    carry_heads_kernel<<<1, 1>>>(blk, nb);
+    groups_kernel<<<blocks_for(nb), 256>>>(head, m, blk, grp, tied);
+    CU_TRY(cudaGetLastError());
+    return BWT_OK;
+}
+
+}  // namespace
+
+int build_sa_device(const uint8_t *d_text, uint64_t len, uint32_t **d_sa_out, uint8_t **d_L_out, uint32_t pointers[4]) {
+    const uint64_t n = len + 1;
+    if (len < 4 || n >= 0xFFFFFFFFull - (1u << 20)) { bwt_set_error("builder: %llu bases outside the supported range", (unsigned long long)len); return BWT_ERR_LIMIT; }
+    // symbol counts -> pointers (first 1-based row whose F is C / G / T; fmi.erl:66-84)
+    DevBuf cntb;
+    BWT_TRY(cntb.alloc(4 * sizeof(unsigned long long)));
+    CU_TRY(cudaMemset(cntb.p, 0, 4 * sizeof(unsigned long long)));
+    count_kernel<<<148 * 8, 256>>>(d_text, len, cntb.as<unsigned long long>());
+    unsigned long long cnt[4];
+    CU_TRY(cudaMemcpy(cnt, cntb.p, sizeof cnt, cudaMemcpyDeviceToHost));
+    if (cnt[0] + cnt[1] + cnt[2] + cnt[3] != len) { bwt_set_error("builder: text must be ACGT only"); return BWT_ERR_FORMAT; }
+    if (!cnt[0] || !cnt[1] || !cnt[2] || !cnt[3]) {
+        bwt_set_error("builder: every one of A,C,G,T must occur (fmi:get_index_pointers/1 walks off the index otherwise)");
+        return BWT_ERR_FORMAT;
+    }
+    pointers[0] = (uint32_t)(2 + cnt[0]);
+    pointers[1] = (uint32_t)(pointers[0] + cnt[1]);
+    pointers[2] = (uint32_t)(pointers[1] + cnt[2]);
+    pointers[3] = (uint32_t)n;
+
+    // head / tied / grp alias the sort inputs (keys_a, idx_a), which are dead once a sort has produced keys_b / idx_b
+    DevBuf keys_a, keys_b, idx_a, idx_b, rank, blk, tmp, scan_tmp, posa, posb;
+    uint32_t *d_sa = nullptr;
+    if (cudaMalloc(&d_sa, n * sizeof(uint32_t)) != cudaSuccess) { cudaGetLastError(); bwt_set_error("builder: SA allocation failed"); return BWT_ERR_NOMEM; }
+    int st = BWT_OK;
+    do {
+        if ((st = keys_a.alloc(n * 8)) || (st = keys_b.alloc(n * 8)) || (st = idx_a.alloc(n * 4)) || (st = idx_b.alloc(n * 4)) ||
+            (st = rank.alloc(n * 4)) ||
+            (st = blk.alloc((div_up_u64(n, 1024) + 1) * 4)) || (st = scan_tmp.alloc(scan_tmp_words(n) * 4)))
+            break;
+        uint32_t *const a_head = keys_a.as<uint32_t>(), *const a_tied = keys_a.as<uint32_t>() + n, *const a_grp = idx_a.as<uint32_t>();
+        key0_kernel<<<blocks_for(n), 256>>>(d_text, len, n, keys_a.as<uint64_t>(), idx_a.as<uint32_t>());
+        size_t tmp_bytes = 0;
+        cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys_a.as<uint64_t>(), keys_b.as<uint64_t>(), idx_a.as<uint32_t>(),
+                                        idx_b.as<uint32_t>(), (uint64_t)n, 0, 63);
+        if ((st = tmp.alloc(tmp_bytes))) break;
+        cudaError_t e = cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, keys_a.as<uint64_t>(), keys_b.as<uint64_t>(),
+                                                        idx_a.as<uint32_t>(), idx_b.as<uint32_t>(), (uint64_t)n, 0, 63);
+        if (e != cudaSuccess) { bwt_set_error("builder: radix sort failed: %s", cudaGetErrorString(e)); st = BWT_ERR_CUDA; break; }
+        if ((st = compute_groups(keys_b.as<uint64_t>(), n, a_head, a_grp, a_tied, blk.as<uint32_t>()))) break;
+        commit0_kernel<<<blocks_for(n), 256>>>(idx_b.as<uint32_t>(), a_grp, n, d_sa, rank.as<uint32_t>());
+        // tied slots of round 0
+        uint32_t m32 = 0;
+        DevBuf totb;
+        if ((st = totb.alloc(4))) break;
+        // `tied` doubles as the scan input; keep the flags in `head` (no longer needed)
+        cudaMemcpy(a_head, a_tied, n * 4, cudaMemcpyDeviceToDevice);
+        if ((st = exclusive_scan_u32(a_tied, n, scan_tmp.as<uint32_t>(), totb.as<uint32_t>(), 0, nullptr))) break;
+        cudaMemcpy(&m32, totb.p, 4, cudaMemcpyDeviceToHost);
+        uint64_t m = m32;
+        if (m) {
+            if ((st = posa.alloc(m * 4)) || (st = posb.alloc(m * 4))) break;
+            scatter_tied_kernel<<<blocks_for(n), 256>>>(a_head, a_tied, n, nullptr, posa.as<uint32_t>());
+        }
+        uint64_t h = 21;
+        uint32_t *pos = posa.as<uint32_t>(), *pos_next = posb.as<uint32_t>();
+        while (m > 0) {
+            keyh_kernel<<<blocks_for(m), 256>>>(pos, m, d_sa, rank.as<uint32_t>(), n, h, keys_a.as<uint64_t>(), idx_a.as<uint32_t>());
+            size_t need = 0;
+            cub::DeviceRadixSort::SortPairs(nullptr, need, keys_a.as<uint64_t>(), keys_b.as<uint64_t>(), idx_a.as<uint32_t>(),
+                                            idx_b.as<uint32_t>(), (uint64_t)m, 0, 64);
+            if (need > tmp_bytes) { bwt_set_error("builder: radix temp grew"); st = BWT_ERR_NOMEM; break; }
+            e = cub::DeviceRadixSort::SortPairs(tmp.p, need, keys_a.as<uint64_t>(), keys_b.as<uint64_t>(), idx_a.as<uint32_t>(),
+                                                idx_b.as<uint32_t>(), (uint64_t)m, 0, 64);
+            if (e != cudaSuccess) { bwt_set_error("builder: radix sort failed: %s", cudaGetErrorString(e)); st = BWT_ERR_CUDA; break; }
+            if ((st = compute_groups(keys_b.as<uint64_t>(), m, a_head, a_grp, a_tied, blk.as<uint32_t>()))) break;
+            commith_kernel<<<blocks_for(m), 256>>>(pos, idx_b.as<uint32_t>(), a_grp, m, d_sa, rank.as<uint32_t>());
+            cudaMemcpy(a_head, a_tied, m * 4, cudaMemcpyDeviceToDevice);
+            if ((st = exclusive_scan_u32(a_tied, m, scan_tmp.as<uint32_t>(), totb.as<uint32_t>(), 0, nullptr))) break;
+            cudaMemcpy(&m32, totb.p, 4, cudaMemcpyDeviceToHost);
+            if (m32) scatter_tied_kernel<<<blocks_for(m), 256>>>(a_head, a_tied, m, pos, pos_next);
+            std::swap(pos, pos_next);
+            m = m32;
+            h *= 2;
+            if (h > 4 * n + 64) { bwt_set_error("builder: prefix doubling did not converge"); st = BWT_ERR_CUDA; break; }
+        }
+        if (st != BWT_OK) break;
+        e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) { bwt_set_error("builder: %s", cudaGetErrorString(e)); st = BWT_ERR_CUDA; break; }
+    } while (0);
+    if (st != BWT_OK) { cudaFree(d_sa); return st; }
+    // free the big temporaries before allocating L
+    keys_a.release();
+    keys_b.release();
+    uint8_t *d_L = nullptr;
+    if (cudaMalloc(&d_L, n) != cudaSuccess) { cudaGetLastError(); cudaFree(d_sa); bwt_set_error("builder: L allocation failed"); return BWT_ERR_NOMEM; }
+    bwt_kernel<<<blocks_for(n), 256>>>(d_text, d_sa, n, d_L);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { cudaFree(d_sa); cudaFree(d_L); bwt_set_error("builder: %s", cudaGetErrorString(e)); return BWT_ERR_CUDA; }
+    *d_sa_out = d_sa;
+    *d_L_out = d_L;
+    return BWT_OK;
+}
+
+static int build_from_device_chunk(uint8_t *d_chunk, uint64_t len, int64_t shift, int device, bool already_acgt,
+                                   bwt_index **out) {
+    // d_chunk: the .ref bytes on the device (kept as the window source); text = its ACGT mapping
+    uint8_t *d_text = d_chunk;
+    DevBuf mapped, flags;
+    if (!already_acgt) {
+        BWT_TRY(mapped.alloc(len));
+        BWT_TRY(flags.alloc(8));
+        CU_TRY(cudaMemset(flags.p, 0, 8));
+        map_acgt_kernel<<<blocks_for(len), 256>>>(d_chunk, len, mapped.as<uint8_t>(), flags.as<uint32_t>());
+        uint32_t f[2];
+        CU_TRY(cudaMemcpy(f, flags.p, 8, cudaMemcpyDeviceToHost));
+        if (f[1]) { bwt_set_error("builder: %u symbols outside ACGT/IUPAC (fm_index.erl:136 raises)", f[1]); return BWT_ERR_FORMAT; }
+        if (f[0]) { bwt_set_error("builder: %u 'N' in the chunk; the reference substitutes random:uniform(4), which is not reproducible", f[0]); return BWT_ERR_FORMAT; }
+        d_text = mapped.as<uint8_t>();
+    }
+    uint32_t *d_sa = nullptr;
+    uint8_t *d_L = nullptr;
+    uint32_t pointers[4];
+    BWT_TRY(build_sa_device(d_text, len, &d_sa, &d_L, pointers));
+    uint8_t *d_ref = nullptr;
+    int st = index_upload_ref_device(d_chunk, len, &d_ref);
+    if (st != BWT_OK) { cudaFree(d_sa); cudaFree(d_L); return st; }
+    bwt_index *h = new bwt_index();
+    h->device = device;
+    st = index_finish_from_device(h, d_L, len + 1, d_sa, d_ref, len, pointers, shift);
+    cudaFree(d_L);
+    if (st != BWT_OK) { cudaFree(d_sa); cudaFree(d_ref); delete h; return st; }
+    *out = h;
+    return BWT_OK;
+}
+
+extern "C" int bwt_build(const uint8_t *chunk, uint64_t len, int64_t shift, int device, bwt_index **out) {
+    if (!chunk || !out) { bwt_set_error("bwt_build: null argument"); return BWT_ERR_ARG; }
+    BWT_TRY(index_select_device(device));
+    DevBuf d;
+    BWT_TRY(d.alloc(len));
+    CU_TRY(cudaMemcpy(d.p, chunk, len, cudaMemcpyHostToDevice));
+    return build_from_device_chunk(d.as<uint8_t>(), len, shift, device, false, out);
+}
+
+extern "C" int bwt_build_synthetic(uint64_t len, uint64_t seed, int64_t shift, int device, bwt_index **out) {
+    if (!out) { bwt_set_error("bwt_build_synthetic: null argument"); return BWT_ERR_ARG; }
+    BWT_TRY(index_select_device(device));
+    DevBuf d;
+    BWT_TRY(d.alloc(len));
+    synth_kernel<<<blocks_for(len), 256>>>(d.as<uint8_t>(), len, seed);
+    CU_TRY(cudaGetLastError());
+    return build_from_device_chunk(d.as<uint8_t>(), len, shift, device, true, out);
+}

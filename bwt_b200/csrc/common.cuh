@@ -1,0 +1,91 @@
+// Shared declarations of libbwt_b200: error plumbing, the device-side index view, small utilities.
+// sm_100a only; no fallbacks.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+
+#include "../../include/bwt_b200.h"
+
+// ---- reference constants (include/bwt.hrl:1-20, worker_bwt.erl:16-17) ----------------------------
+#define BWT_TOLERANCE 20
+#define BWT_MIN_LEN 8
+#define BWT_MAX_RANGE 45
+#define BWT_MAX_LEN 15
+#define BWT_REF_EXT 200
+
+// ---- error plumbing -----------------------------------------------------------------------------
+void bwt_set_error(const char *fmt, ...);
+
+#define CU_TRY(expr)                                                                                  \
+    do {                                                                                              \
+        cudaError_t _e = (expr);                                                                      \
+        if (_e != cudaSuccess) {                                                                      \
+            bwt_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e));      \
+            return BWT_ERR_CUDA;                                                                      \
+        }                                                                                             \
+    } while (0)
+
+#define BWT_TRY(expr)                 \
+    do {                              \
+        int _s = (expr);              \
+        if (_s != BWT_OK) return _s;  \
+    } while (0)
+
+// ---- device view of one index partition ---------------------------------------------------------
+// Occ layout: one 32-byte block (= one DRAM sector) per 64 rows of L:
+//   uint4 #0 : occurrences of A,C,G,T in rows before the block   (checkpoint)
+//   uint4 #1 : bit planes of the 64 symbols: lo[0],lo[1],hi[0],hi[1]   (code = hi<<1 | lo, A0 C1 G2 T3;
+//              the '$' row is stored as A and corrected with dollar_row)
+// so that one LF bound = one aligned 32-byte fetch (two LDG.128 to the same sector).
+struct DevIndex {
+    const uint4 *occ;
+    const uint32_t *sa;        // full suffix array, SA[e-1] for 1-based row e (fmi.erl:89-100 reads it un-sampled)
+    const uint2 *kmer;         // 4^8 entries: (Sp,Ep) after the first 8 characters, or (0, steps) if the search stopped
+    const uint8_t *ref;        // .ref padded with 200 'N' on both sides (worker_bwt.erl:53-55)
+    uint64_t ref_len_padded;
+    uint32_t n;                // rows
+    uint32_t P[4];             // 1-based first row whose F is A (=2), C, G, T
+    uint32_t last;
+    uint32_t dollar;           // 1-based row whose L is '$'
+    int64_t shift;
+};
+
+struct bwt_index {
+    DevIndex dv{};
+    int device = 0;
+    uint64_t n = 0;
+    uint64_t ref_len = 0;      // unpadded
+    uint32_t pointers[4] = {0, 0, 0, 0};
+    int64_t shift = 0;
+    uint64_t device_bytes = 0;
+    void *d_occ = nullptr, *d_sa = nullptr, *d_kmer = nullptr, *d_ref = nullptr;
+};
+
+// ASCII -> index code (A0 C1 G2 T3), -1 otherwise
+__host__ __device__ __forceinline__ int bwt_code(uint8_t c) {
+    return c == 'A' ? 0 : c == 'C' ? 1 : c == 'G' ? 2 : c == 'T' ? 3 : -1;
+}
+
+static inline uint64_t div_up_u64(uint64_t a, uint64_t b) { return (a + b - 1) / b; }
+
+// ---- device scan (scan.cu) ----------------------------------------------------------------------
+// In-place exclusive prefix sum of n uint32 on `stream`; d_total (device, may be null) receives the sum.
+// tmp must hold scan_tmp_words(n) uint32.
+size_t scan_tmp_words(size_t n);
+int exclusive_scan_u32(uint32_t *d_data, size_t n, uint32_t *d_tmp, uint32_t *d_total, cudaStream_t stream,
+                       uint32_t *launches);
+
+// ---- index construction helpers (index.cu) ------------------------------------------------------
+// Build occ blocks + k-mer table from device-resident ASCII L (n bytes) and SA; takes ownership of d_sa and d_ref_padded.
+int index_finish_from_device(bwt_index *h, const uint8_t *d_L, uint64_t n, uint32_t *d_sa, uint8_t *d_ref_padded,
+                             uint64_t ref_len, const uint32_t pointers[4], int64_t shift);
+int index_select_device(int device);
+int index_upload_ref_device(const uint8_t *d_ref, uint64_t len, uint8_t **d_out);
+
+// ---- builder (build.cu) -------------------------------------------------------------------------
+int build_sa_device(const uint8_t *d_text_acgt, uint64_t len, uint32_t **d_sa_out, uint8_t **d_L_out,
+                    uint32_t pointers[4]);

@@ -1,0 +1,317 @@
+// Index lifetime: parse / upload / device layout (Occ blocks, 8-mer interval table), save, export.
+//
+// Replaces fm_index:get_index/2 (fm_index.erl:154-156) and the .ref load + 'N' padding of
+// worker_bwt.erl:48-55.  HBM layout per partition (n rows, ref_len bases):
+//   occ   : ceil(n/64) x 32 B   checkpoint counts + bit planes of L      (0.5 B / row)
+//   sa    : n x 4 B             full suffix array, as the reference keeps it (fmi.erl:89-100)
+//   kmer  : 65536 x 8 B         interval after the first 8 characters (L2-resident)
+//   ref   : ref_len + 400 B     ASCII .ref padded with 200 'N' each side
+#include <stdarg.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "common.cuh"
+#include "etf.hpp"
+#include "search.cuh"
+
+// ---- thread-local error text ----------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+
+void bwt_set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+}
+
+extern "C" const char *bwt_last_error(void) { return g_err; }
+extern "C" int bwt_abi_version(void) { return BWT_B200_ABI_VERSION; }
+
+extern "C" int bwt_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int index_select_device(int device) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        bwt_set_error("no CUDA device available (%s): libbwt_b200 has no CPU path",
+                      e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+        return BWT_ERR_NODEVICE;
+    }
+    if (device < 0 || device >= n) { bwt_set_error("device %d out of range (0..%d)", device, n - 1); return BWT_ERR_ARG; }
+    CU_TRY(cudaSetDevice(device));
+    return BWT_OK;
+}
+
+// ---- layout kernels -------------------------------------------------------------------------------
+namespace {
+
+// one thread per 64-row block: bit planes + per-block symbol counts ('$' is stored and counted as A)
+__global__ void planes_kernel(const uint8_t *__restrict__ L, uint64_t n, uint4 *__restrict__ occ,
+                              uint32_t *__restrict__ cA, uint32_t *__restrict__ cC, uint32_t *__restrict__ cG,
+                              uint32_t *__restrict__ cT, uint32_t *__restrict__ dollar, uint32_t *__restrict__ bad) {
+    uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint64_t nb = (n + 63) / 64;
+    if (b >= nb) return;
+    uint32_t lo[2] = {0, 0}, hi[2] = {0, 0}, cnt[4] = {0, 0, 0, 0};
+    uint64_t base = b * 64;
+    for (int k = 0; k < 64; k++) {
+        uint64_t row = base + k;
+        if (row >= n) break;
+        uint8_t ch = L[row];
+        int c = bwt_code(ch);
+        if (c < 0) {
+            if (ch == '$') { atomicMin(dollar, (uint32_t)(row + 1)); atomicAdd(dollar + 1, 1u); }
+            else atomicAdd(bad, 1u);
+            c = 0;
+        }
+        cnt[c]++;
+        lo[k >> 5] |= (uint32_t)(c & 1) << (k & 31);
+        hi[k >> 5] |= (uint32_t)(c >> 1) << (k & 31);
+    }
+    occ[2 * b + 1] = make_uint4(lo[0], lo[1], hi[0], hi[1]);
+    cA[b] = cnt[0]; cC[b] = cnt[1]; cG[b] = cnt[2]; cT[b] = cnt[3];
+}
+
+__global__ void counts_kernel(uint4 *__restrict__ occ, uint64_t nb, const uint32_t *__restrict__ cA,
+                              const uint32_t *__restrict__ cC, const uint32_t *__restrict__ cG,
+                              const uint32_t *__restrict__ cT) {
+    uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < nb) occ[2 * b] = make_uint4(cA[b], cC[b], cG[b], cT[b]);
+}
+
+// 4^8 threads: the first eight characters of bwa:find_seeds/6 for every ACGT 8-mer
+__global__ void kmer_kernel(DevIndex ix, uint2 *__restrict__ tab) {
+    uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= 65536u) return;
+    const char sym[4] = {'A', 'C', 'G', 'T'};
+    uint8_t q[8];
+    for (int t = 0; t < 8; t++) q[7 - t] = (uint8_t)sym[(idx >> (2 * t)) & 3];   // q[7] is the last character
+    uint32_t sp, ep;
+    first_interval(ix, (int)(idx & 3), sp, ep);
+    int n = 1;
+    for (int k = 6; k >= 0; k--) {
+        if (!lf_step(ix, sp, ep, bwt_code(q[k]))) break;
+        n++;
+    }
+    tab[idx] = (n == 8) ? make_uint2(sp, ep) : make_uint2(0u, (uint32_t)n);
+}
+
+__global__ void pad_fill_kernel(uint8_t *p, uint64_t n, uint8_t v) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+}  // namespace
+
+int index_finish_from_device(bwt_index *h, const uint8_t *d_L, uint64_t n, uint32_t *d_sa, uint8_t *d_ref_padded,
+                             uint64_t ref_len, const uint32_t pointers[4], int64_t shift) {
+    if (n < 2 || n >= 0xFFFFFFFFull - (1u << 20)) {
+        bwt_set_error("index of %llu rows is outside the supported range (2 .. 2^32-2^20)", (unsigned long long)n);
+        return BWT_ERR_LIMIT;
+    }
+    if (!(pointers[0] >= 2 && pointers[0] < pointers[1] && pointers[1] < pointers[2] && pointers[2] <= pointers[3] &&
+          pointers[3] == n)) {
+        bwt_set_error("inconsistent pointers {%u,%u,%u,%u} for %llu rows", pointers[0], pointers[1], pointers[2],
+                      pointers[3], (unsigned long long)n);
+        return BWT_ERR_FORMAT;
+    }
+    uint64_t nb = (n + 63) / 64;
+    uint4 *d_occ = nullptr;
+    uint32_t *d_cnt = nullptr, *d_tmp = nullptr, *d_flags = nullptr;
+    uint2 *d_kmer = nullptr;
+    CU_TRY(cudaMalloc(&d_occ, nb * 32));
+    CU_TRY(cudaMalloc(&d_cnt, nb * 4 * sizeof(uint32_t)));
+    CU_TRY(cudaMalloc(&d_tmp, scan_tmp_words(nb) * sizeof(uint32_t)));
+    CU_TRY(cudaMalloc(&d_flags, 4 * sizeof(uint32_t)));
+    CU_TRY(cudaMalloc(&d_kmer, 65536 * sizeof(uint2)));
+    uint32_t init[4] = {0xFFFFFFFFu, 0, 0, 0};   // dollar row (min), #dollars, #bad symbols
+    CU_TRY(cudaMemcpy(d_flags, init, sizeof init, cudaMemcpyHostToDevice));
+    uint32_t *cA = d_cnt, *cC = d_cnt + nb, *cG = d_cnt + 2 * nb, *cT = d_cnt + 3 * nb;
+    planes_kernel<<<(unsigned)div_up_u64(nb, 256), 256>>>(d_L, n, d_occ, cA, cC, cG, cT, d_flags, d_flags + 2);
+    CU_TRY(cudaGetLastError());
+    for (int c = 0; c < 4; c++) BWT_TRY(exclusive_scan_u32(d_cnt + c * nb, nb, d_tmp, nullptr, 0, nullptr));
+    counts_kernel<<<(unsigned)div_up_u64(nb, 256), 256>>>(d_occ, nb, cA, cC, cG, cT);
+    CU_TRY(cudaGetLastError());
+    uint32_t flags[4];
+    CU_TRY(cudaMemcpy(flags, d_flags, sizeof flags, cudaMemcpyDeviceToHost));
+    cudaFree(d_cnt); cudaFree(d_tmp); cudaFree(d_flags);
+    if (flags[2] != 0 || flags[1] != 1) {
+        cudaFree(d_occ); cudaFree(d_kmer);
+        bwt_set_error("L column must hold exactly one '$' and otherwise only ACGT (%u '$', %u other symbols)", flags[1], flags[2]);
+        return BWT_ERR_FORMAT;
+    }
+    h->n = n;
+    h->ref_len = ref_len;
+    h->shift = shift;
+    memcpy(h->pointers, pointers, sizeof h->pointers);
+    h->d_occ = d_occ; h->d_sa = d_sa; h->d_kmer = d_kmer; h->d_ref = d_ref_padded;
+    DevIndex &dv = h->dv;
+    dv.occ = d_occ; dv.sa = d_sa; dv.kmer = d_kmer; dv.ref = d_ref_padded;
+    dv.ref_len_padded = ref_len + 2 * BWT_REF_EXT;
+    dv.n = (uint32_t)n;
+    dv.P[0] = 2; dv.P[1] = pointers[0]; dv.P[2] = pointers[1]; dv.P[3] = pointers[2];
+    dv.last = pointers[3];
+    dv.dollar = flags[0];
+    dv.shift = shift;
+    kmer_kernel<<<256, 256>>>(dv, d_kmer);
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaDeviceSynchronize());
+    h->device_bytes = nb * 32 + n * 4 + 65536 * 8 + dv.ref_len_padded;
+    return BWT_OK;
+}
+
+// pad: d_out[0..200) = 'N', [200..200+len) = ref, tail = 'N'   (worker_bwt.erl:53-55)
+static int upload_padded_ref(const uint8_t *ref, uint64_t len, bool on_device, uint8_t **d_out) {
+    uint8_t *d = nullptr;
+    uint64_t tot = len + 2 * BWT_REF_EXT;
+    CU_TRY(cudaMalloc(&d, tot));
+    pad_fill_kernel<<<1, 256>>>(d, BWT_REF_EXT, 'N');
+    pad_fill_kernel<<<1, 256>>>(d + BWT_REF_EXT + len, BWT_REF_EXT, 'N');
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaMemcpy(d + BWT_REF_EXT, ref, len, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice));
+    *d_out = d;
+    return BWT_OK;
+}
+
+int index_upload_ref_device(const uint8_t *d_ref, uint64_t len, uint8_t **d_out) {
+    return upload_padded_ref(d_ref, len, true, d_out);
+}
+
+extern "C" int bwt_open_arrays(const uint8_t *L, uint64_t n, const uint32_t *SA, const uint32_t pointers[4],
+                               int64_t shift, const uint8_t *ref, uint64_t ref_len, int device, bwt_index **out) {
+    if (!L || !SA || !pointers || !ref || !out) { bwt_set_error("bwt_open_arrays: null argument"); return BWT_ERR_ARG; }
+    BWT_TRY(index_select_device(device));
+    bwt_index *h = new bwt_index();
+    h->device = device;
+    uint8_t *d_L = nullptr, *d_ref = nullptr;
+    uint32_t *d_sa = nullptr;
+    int st = BWT_OK;
+    do {
+        if (cudaMalloc(&d_L, n) != cudaSuccess || cudaMalloc(&d_sa, n * sizeof(uint32_t)) != cudaSuccess) {
+            bwt_set_error("device allocation of %llu index rows failed: %s", (unsigned long long)n,
+                          cudaGetErrorString(cudaGetLastError()));
+            st = BWT_ERR_NOMEM; break;
+        }
+        if (cudaMemcpy(d_L, L, n, cudaMemcpyHostToDevice) != cudaSuccess ||
+            cudaMemcpy(d_sa, SA, n * sizeof(uint32_t), cudaMemcpyHostToDevice) != cudaSuccess) {
+            bwt_set_error("index upload failed: %s", cudaGetErrorString(cudaGetLastError()));
+            st = BWT_ERR_CUDA; break;
+        }
+        st = upload_padded_ref(ref, ref_len, false, &d_ref);
+        if (st != BWT_OK) break;
+        st = index_finish_from_device(h, d_L, n, d_sa, d_ref, ref_len, pointers, shift);
+    } while (0);
+    if (d_L) cudaFree(d_L);
+    if (st != BWT_OK) {
+        if (d_sa) cudaFree(d_sa);
+        if (d_ref) cudaFree(d_ref);
+        delete h;
+        return st;
+    }
+    *out = h;
+    return BWT_OK;
+}
+
+static int read_file(const char *path, std::vector<uint8_t> &buf) {
+    FILE *f = fopen(path, "rb");
+    if (!f) { bwt_set_error("cannot open %s", path); return BWT_ERR_IO; }
+    fseek(f, 0, SEEK_END);
+    long sz = ftell(f);
+    fseek(f, 0, SEEK_SET);
+    buf.resize((size_t)sz);
+    size_t got = sz ? fread(buf.data(), 1, (size_t)sz, f) : 0;
+    fclose(f);
+    if (got != (size_t)sz) { bwt_set_error("short read on %s", path); return BWT_ERR_IO; }
+    return BWT_OK;
+}
+
+extern "C" int bwt_open(const char *fm_path, const char *ref_path, int device, bwt_index **out) {
+    if (!fm_path || !ref_path || !out) { bwt_set_error("bwt_open: null argument"); return BWT_ERR_ARG; }
+    BWT_TRY(index_select_device(device));   // fail before any file work when there is no GPU
+    std::vector<uint8_t> fm, ref;
+    BWT_TRY(read_file(fm_path, fm));
+    BWT_TRY(read_file(ref_path, ref));
+    EtfIndex ix;
+    std::string err;
+    if (!etf_parse_fm(fm.data(), fm.size(), ix, err)) {
+        bwt_set_error("%s: %s", fm_path, err.c_str());
+        return BWT_ERR_FORMAT;
+    }
+    fm.clear(); fm.shrink_to_fit();
+    if (ix.L.size() != ref.size() + 1) {
+        bwt_set_error("%s has %zu rows but %s holds %zu bases (expected rows = bases + 1)", fm_path, ix.L.size(),
+                      ref_path, ref.size());
+        return BWT_ERR_FORMAT;
+    }
+    return bwt_open_arrays(ix.L.data(), ix.L.size(), ix.SA.data(), ix.pointers, ix.shift, ref.data(), ref.size(), device, out);
+}
+
+extern "C" int bwt_close(bwt_index *h) {
+    if (!h) return BWT_OK;
+    cudaSetDevice(h->device);
+    cudaFree(h->d_occ); cudaFree(h->d_sa); cudaFree(h->d_kmer); cudaFree(h->d_ref);
+    delete h;
+    return BWT_OK;
+}
+
+extern "C" int bwt_info(const bwt_index *h, bwt_index_info *info) {
+    if (!h || !info) { bwt_set_error("bwt_info: null argument"); return BWT_ERR_ARG; }
+    info->n_rows = h->n;
+    memcpy(info->pointers, h->pointers, sizeof info->pointers);
+    info->shift = h->shift;
+    info->ref_len = h->ref_len;
+    info->dollar_row = h->dv.dollar;
+    info->device_bytes = h->device_bytes;
+    info->device = h->device;
+    info->kmer_k = 8;
+    return BWT_OK;
+}
+
+// ---- export / save ----------------------------------------------------------------------------------
+namespace {
+__global__ void unpack_L_kernel(const uint4 *__restrict__ occ, uint64_t n, uint32_t dollar, uint8_t *__restrict__ L) {
+    uint64_t row = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= n) return;
+    uint4 pl = occ[2 * (row >> 6) + 1];
+    uint32_t k = row & 63;
+    uint32_t lo = ((k < 32 ? pl.x : pl.y) >> (k & 31)) & 1u, hi = ((k < 32 ? pl.z : pl.w) >> (k & 31)) & 1u;
+    const char sym[4] = {'A', 'C', 'G', 'T'};
+    L[row] = (row + 1 == dollar) ? '$' : (uint8_t)sym[hi * 2 + lo];
+}
+}  // namespace
+
+extern "C" int bwt_export(const bwt_index *h, uint8_t *L, uint32_t *SA, uint8_t *ref) {
+    if (!h) { bwt_set_error("bwt_export: null handle"); return BWT_ERR_ARG; }
+    CU_TRY(cudaSetDevice(h->device));
+    if (L) {
+        uint8_t *d_L = nullptr;
+        CU_TRY(cudaMalloc(&d_L, h->n));
+        unpack_L_kernel<<<(unsigned)div_up_u64(h->n, 256), 256>>>(h->dv.occ, h->n, h->dv.dollar, d_L);
+        cudaError_t e = cudaMemcpy(L, d_L, h->n, cudaMemcpyDeviceToHost);
+        cudaFree(d_L);
+        CU_TRY(e);
+    }
+    if (SA) CU_TRY(cudaMemcpy(SA, h->d_sa, h->n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    if (ref) CU_TRY(cudaMemcpy(ref, (const uint8_t *)h->d_ref + BWT_REF_EXT, h->ref_len, cudaMemcpyDeviceToHost));
+    return BWT_OK;
+}
+
+extern "C" int bwt_save(const bwt_index *h, const char *fm_path, const char *ref_path) {
+    if (!h || !fm_path || !ref_path) { bwt_set_error("bwt_save: null argument"); return BWT_ERR_ARG; }
+    std::vector<uint8_t> L(h->n), ref(h->ref_len), out;
+    std::vector<uint32_t> SA(h->n);
+    BWT_TRY(bwt_export(h, L.data(), SA.data(), ref.data()));
+    etf_write_fm(L.data(), SA.data(), h->n, h->pointers, h->shift, out);
+    FILE *f = fopen(fm_path, "wb");
+    if (!f || fwrite(out.data(), 1, out.size(), f) != out.size()) { if (f) fclose(f); bwt_set_error("cannot write %s", fm_path); return BWT_ERR_IO; }
+    fclose(f);
+    f = fopen(ref_path, "wb");
+    if (!f || fwrite(ref.data(), 1, ref.size(), f) != ref.size()) { if (f) fclose(f); bwt_set_error("cannot write %s", ref_path); return BWT_ERR_IO; }
+    fclose(f);
+    return BWT_OK;
+}

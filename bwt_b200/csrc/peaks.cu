@@ -1,0 +1,104 @@
+// Roofline denominators measured on the device at hand (SURVEY.md 8d asks for both; nothing is assumed):
+//   * random 32-byte-sector gather bandwidth: the ceiling of Occ-block fetches (two LDG.128 per sector,
+//     exactly what occ_at() issues), addresses from a per-thread LCG over a buffer far larger than L2
+//   * DPX issue rate: independent chains of VIADDMNMX (__viaddmax_s32), the instruction the SW cell is made of
+#include "common.cuh"
+
+namespace {
+
+__global__ void __launch_bounds__(256) gather_kernel(const uint4 *__restrict__ buf, uint64_t n_sectors, int iters,
+                                                     uint32_t *__restrict__ sink) {
+    uint64_t x = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    x = x * 0x9E3779B97F4A7C15ull + 0x1234567ull;
+    uint32_t acc = 0;
+    for (int it = 0; it < iters; it += 4) {
+        uint4 a[4], b[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {                  // four independent sectors in flight per thread
+            x = x * 6364136223846793005ull + 1442695040888963407ull;
+            uint64_t s = (x >> 20) % n_sectors;
+            a[u] = __ldg(buf + 2 * s);
+            b[u] = __ldg(buf + 2 * s + 1);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) acc += a[u].x ^ b[u].w;
+    }
+    if (acc == 0x9999999u) sink[0] = acc;
+}
+
+__global__ void __launch_bounds__(256) dpx_kernel(int iters, int seed, int *__restrict__ sink) {
+    int a[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) a[k] = seed + k + threadIdx.x;
+    const int b = seed | 1, c = seed - 7;
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int k = 0; k < 8; k++) a[k] = __viaddmax_s32(a[k], b, c + k);
+#pragma unroll
+        for (int k = 0; k < 8; k++) a[k] = __viaddmax_s32(a[k], -b, c - k);
+    }
+    int s = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) s ^= a[k];
+    if (s == 0x7FFFFFF1) sink[0] = s;
+}
+
+}  // namespace
+
+extern "C" int bwt_peak_gather_gbs(int device, uint64_t bytes, double *gbs) {
+    if (!gbs || bytes < (1ull << 20)) { bwt_set_error("bwt_peak_gather_gbs: bad argument"); return BWT_ERR_ARG; }
+    BWT_TRY(index_select_device(device));
+    uint4 *buf = nullptr;
+    uint32_t *sink = nullptr;
+    uint64_t n_sectors = bytes / 32;
+    CU_TRY(cudaMalloc(&buf, n_sectors * 32));
+    CU_TRY(cudaMalloc(&sink, 4));
+    CU_TRY(cudaMemset(buf, 1, n_sectors * 32));
+    cudaEvent_t e0, e1;
+    CU_TRY(cudaEventCreate(&e0));
+    CU_TRY(cudaEventCreate(&e1));
+    const int iters = 64, blocks = 148 * 32;
+    gather_kernel<<<blocks, 256>>>(buf, n_sectors, iters, sink);        // warm-up
+    double best = 0;
+    for (int rep = 0; rep < 5; rep++) {
+        CU_TRY(cudaEventRecord(e0));
+        gather_kernel<<<blocks, 256>>>(buf, n_sectors, iters, sink);
+        CU_TRY(cudaEventRecord(e1));
+        CU_TRY(cudaEventSynchronize(e1));
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        double g = (double)blocks * 256 * iters * 32.0 / (ms * 1e-3) / 1e9;
+        if (g > best) best = g;
+    }
+    *gbs = best;
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(buf); cudaFree(sink);
+    return BWT_OK;
+}
+
+extern "C" int bwt_peak_dpx_gops(int device, double *gops) {
+    if (!gops) { bwt_set_error("bwt_peak_dpx_gops: bad argument"); return BWT_ERR_ARG; }
+    BWT_TRY(index_select_device(device));
+    int *sink = nullptr;
+    CU_TRY(cudaMalloc(&sink, 4));
+    cudaEvent_t e0, e1;
+    CU_TRY(cudaEventCreate(&e0));
+    CU_TRY(cudaEventCreate(&e1));
+    const int iters = 4096, blocks = 148 * 8;
+    dpx_kernel<<<blocks, 256>>>(iters, 3, sink);
+    double best = 0;
+    for (int rep = 0; rep < 5; rep++) {
+        CU_TRY(cudaEventRecord(e0));
+        dpx_kernel<<<blocks, 256>>>(iters, 3 + rep, sink);
+        CU_TRY(cudaEventRecord(e1));
+        CU_TRY(cudaEventSynchronize(e1));
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        double g = (double)blocks * 256 * iters * 16.0 / (ms * 1e-3) / 1e9;
+        if (g > best) best = g;
+    }
+    *gops = best;
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(sink);
+    return BWT_OK;
+}

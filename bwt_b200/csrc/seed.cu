@@ -1,0 +1,385 @@
+// Seeding kernels (see seed.cuh).  Reference semantics: sga.erl:17-76, bwa.erl:12-45, fmi.erl:25-39,89-100.
+#include <cooperative_groups.h>
+
+#include "search.cuh"
+#include "seed.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace {
+
+constexpr int SGA_BLOCK = 128;
+
+enum { CTR_SEARCHES = 0, CTR_LF, CTR_HBM_LF, CTR_LOCATED, CTR_CLUSTERS, CTR_N };
+
+__device__ __forceinline__ void flush_counters(unsigned long long *s_ctr, SeedCounters *ctr) {
+    __syncthreads();
+    if (threadIdx.x < CTR_N && s_ctr[threadIdx.x]) {
+        unsigned long long *dst = threadIdx.x == CTR_SEARCHES ? &ctr->searches
+                                  : threadIdx.x == CTR_LF     ? &ctr->lf_steps
+                                  : threadIdx.x == CTR_HBM_LF ? &ctr->hbm_lf_steps
+                                  : threadIdx.x == CTR_LOCATED ? &ctr->located
+                                                               : &ctr->clusters;
+        atomicAdd(dst, s_ctr[threadIdx.x]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// bwa:find_seeds/6 for a batch of independent subsequences: one thread per search.
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) search_kernel(DevIndex ix, const uint8_t *__restrict__ subs,
+                                                     const int64_t *__restrict__ offs, int64_t n, int32_t fixed_len,
+                                                     int32_t *__restrict__ status, uint32_t *__restrict__ sp,
+                                                     uint32_t *__restrict__ ep, int32_t *__restrict__ nm,
+                                                     SeedCounters *ctr) {
+    __shared__ unsigned long long s_ctr[CTR_N];
+    if (threadIdx.x < CTR_N) s_ctr[threadIdx.x] = 0;
+    __syncthreads();
+    unsigned long long lf = 0, hbm = 0, cnt = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const uint8_t *q;
+        int len;
+        if (fixed_len > 0) { q = subs + i * fixed_len; len = fixed_len; }
+        else { q = subs + offs[i]; len = (int)(offs[i + 1] - offs[i]); }
+        SearchRes r;
+        if (len <= 0) { r.sp = r.ep = 0; r.n = 0; r.status = BWT_SEARCH_CRASH; r.table = 0; }   // hd([]) badmatch
+        else r = search_sub(ix, q, len, true);
+        if (status) status[i] = r.status;
+        if (sp) sp[i] = r.sp;
+        if (ep) ep[i] = r.ep;
+        if (nm) nm[i] = r.n;
+        cnt++;
+        int steps = r.n > 0 ? r.n - 1 : 0;
+        lf += steps;
+        hbm += r.table ? (r.n > BWT_MIN_LEN ? r.n - BWT_MIN_LEN : 0) : steps;
+    }
+    // warp-reduce, then one shared atomic per warp
+    for (int d = 16; d > 0; d >>= 1) {
+        lf += __shfl_down_sync(0xFFFFFFFFu, lf, d);
+        hbm += __shfl_down_sync(0xFFFFFFFFu, hbm, d);
+        cnt += __shfl_down_sync(0xFFFFFFFFu, cnt, d);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(&s_ctr[CTR_SEARCHES], cnt);
+        atomicAdd(&s_ctr[CTR_LF], lf);
+        atomicAdd(&s_ctr[CTR_HBM_LF], hbm);
+    }
+    if (ctr) flush_counters(s_ctr, ctr);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// sga:skip_Ns/1 (sga.erl:69-76): -1 = no_more_subseqs, else Skipped (the new length is len - Skipped).
+// The 'N' that ends a skipped stretch is itself counted as the first of the next eight.
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int skip_ns(const uint8_t *q, int len) {
+    if (len < BWT_MIN_LEN) return -1;
+    int j = 0, skipped = 0, k = len - 1;
+    for (;;) {
+        if (j == BWT_MIN_LEN) return skipped;
+        if (k < 0) return -1;
+        if (q[k] == 'N') { skipped += j; j = 1; } else j++;
+        k--;
+    }
+}
+
+struct GroupShared {        // per-group scratch for the task list of one read
+    uint16_t *t_end;        // subsequence end (exclusive) inside the read
+    uint16_t *t_shift;      // Shift+Skip added to its seed ends (sga.erl:32-33,37-39)
+    uint2 *t_res;           // {Sp, count<<4 | N}
+    uint32_t *t_pos;        // first slot of its seed ends
+};
+
+enum { SGA_DONE = 0, SGA_DEFER = 1 };
+
+// One read, one group of G lanes.  `seeds` holds `cap` uint32 (a power of two) in shared or global memory.
+template <int G, int MAXT, bool SLOW, typename Tile>
+__device__ __forceinline__ int sga_read(const Tile &tile, const DevIndex &ix, const uint8_t *__restrict__ q, int lq,
+                                        uint32_t read, uint32_t *seeds, uint32_t cap, const GroupShared &gs,
+                                        int32_t *read_status, uint32_t *ncl, uint32_t *cl_base, Cluster *clusters,
+                                        uint32_t cl_cap, SlowRead *slow, uint32_t slow_cap, SeedCounters *ctr,
+                                        unsigned long long *s_ctr) {
+    const int lane = tile.thread_rank();
+    if (lq > BWT_MAX_READ_LEN) {
+        if (lane == 0) { read_status[read] = BWT_READ_LIMIT; ncl[read] = 0; cl_base[read] = 0; }
+        return SGA_DONE;
+    }
+    // -- task list: where each subsequence ends and what is added to its seed ends
+    bool has_n = false;
+    for (int i = lane; i < lq; i += G) has_n |= (q[i] == 'N');
+    has_n = tile.any(has_n);
+    int nt;
+    if (!has_n) {
+        nt = lq >= BWT_MIN_LEN ? (lq - BWT_MIN_LEN) / BWT_MIN_LEN + 1 : 0;
+    } else {
+        nt = 0;
+        if (lane == 0) {                                       // sga.erl:18-34, the search-independent part
+            int len = lq, shift = 0;
+            for (;;) {
+                int skip = skip_ns(q, len);
+                if (skip < 0) break;
+                len -= skip;
+                gs.t_end[nt] = (uint16_t)len;
+                gs.t_shift[nt] = (uint16_t)(shift + skip);
+                nt++;
+                len -= BWT_MIN_LEN;
+                shift += BWT_MIN_LEN + skip;
+            }
+        }
+        nt = tile.shfl(nt, 0);
+        tile.sync();
+    }
+    // -- searches: lane k takes subsequences k, k+G, ...
+    bool crash = false;
+    unsigned long long lf = 0, hbm = 0;
+    for (int k = lane; k < nt; k += G) {
+        int end = has_n ? (int)gs.t_end[k] : lq - BWT_MIN_LEN * k;
+        SearchRes r = search_sub(ix, q, end, true);
+        crash |= (r.status == BWT_SEARCH_CRASH);
+        uint32_t cnt = (r.status == BWT_SEEDS) ? (r.ep - r.sp + 1) : 0u;
+        if (cnt > BWT_MAX_SEEDS_PER_READ) cnt = BWT_MAX_SEEDS_PER_READ + 1;     // flagged below
+        gs.t_res[k] = make_uint2(r.sp, (cnt << 4) | (uint32_t)r.n);
+        int steps = r.n > 0 ? r.n - 1 : 0;
+        lf += steps;
+        hbm += r.table ? (r.n > BWT_MIN_LEN ? r.n - BWT_MIN_LEN : 0) : steps;
+    }
+    crash = tile.any(crash);
+    tile.sync();
+    // -- slots: exclusive prefix of the seed counts; Qty = searches that produced a list (sga.erl:30-33)
+    uint32_t total = 0, qty = 0;
+    for (int k0 = 0; k0 < nt; k0 += G) {
+        int k = k0 + lane;
+        uint32_t c = k < nt ? (gs.t_res[k].y >> 4) : 0u;
+        uint32_t inc = c;
+#pragma unroll
+        for (int d = 1; d < G; d <<= 1) {
+            uint32_t t = tile.shfl_up(inc, d);
+            if (lane >= d) inc += t;
+        }
+        if (k < nt) gs.t_pos[k] = total + inc - c;
+        total += tile.shfl(inc, G - 1);
+        qty += __popc(tile.ballot(c > 0));
+    }
+    if (!SLOW && lane == 0) atomicAdd(&s_ctr[CTR_SEARCHES], (unsigned long long)nt);
+    // lane-sum of the LF counters
+#pragma unroll
+    for (int d = G / 2; d > 0; d >>= 1) {
+        lf += tile.shfl_down(lf, d);
+        hbm += tile.shfl_down(hbm, d);
+    }
+    if (!SLOW && lane == 0) {
+        atomicAdd(&s_ctr[CTR_LF], lf);
+        atomicAdd(&s_ctr[CTR_HBM_LF], hbm);
+    }
+    if (crash || total > BWT_MAX_SEEDS_PER_READ) {
+        if (lane == 0) {
+            read_status[read] = crash ? BWT_READ_CRASH : BWT_READ_LIMIT;
+            ncl[read] = 0; cl_base[read] = 0;
+        }
+        return SGA_DONE;
+    }
+    if (lane == 0) read_status[read] = BWT_READ_OK;
+    if (qty < 2) {                                             // get_similar(0|1,_) -> []  (sga.erl:42-43)
+        if (lane == 0) { ncl[read] = 0; cl_base[read] = 0; }
+        if (!SLOW && lane == 0) atomicAdd(&s_ctr[CTR_LOCATED], (unsigned long long)total);
+        return SGA_DONE;
+    }
+    if (total > cap) {                                         // does not fit on chip: hand to the slow kernel
+        if (lane == 0) {
+            uint32_t slot = atomicAdd(&ctr->n_slow, 1u);
+            if (slot < slow_cap) { slow[slot].read = read; slow[slot].seeds = total; }
+        }
+        return SGA_DEFER;
+    }
+    if (lane == 0) {
+        if (SLOW) atomicAdd(&ctr->located, (unsigned long long)total);
+        else atomicAdd(&s_ctr[CTR_LOCATED], (unsigned long long)total);
+    }
+    // -- locate: SA of every row of every interval, plus N and the subsequence's shift (fmi.erl:89-100, sga.erl:37-39)
+    uint32_t P = 1;
+    while (P < total) P <<= 1;
+    if (SLOW) {
+        for (int k = 0; k < nt; k++) {
+            uint2 tr = gs.t_res[k];
+            uint32_t cnt = tr.y >> 4, add = (tr.y & 15u) + (has_n ? (uint32_t)gs.t_shift[k] : (uint32_t)(BWT_MIN_LEN * k));
+            uint32_t pos = gs.t_pos[k];
+            for (uint32_t t = lane; t < cnt; t += G) seeds[pos + t] = __ldg(ix.sa + (tr.x - 1) + t) + add;
+        }
+    } else {
+        for (int k = lane; k < nt; k += G) {
+            uint2 tr = gs.t_res[k];
+            uint32_t cnt = tr.y >> 4, add = (tr.y & 15u) + (has_n ? (uint32_t)gs.t_shift[k] : (uint32_t)(BWT_MIN_LEN * k));
+            uint32_t pos = gs.t_pos[k];
+            for (uint32_t t = 0; t < cnt; t++) seeds[pos + t] = __ldg(ix.sa + (tr.x - 1) + t) + add;
+        }
+    }
+    for (uint32_t i = total + lane; i < P; i += G) seeds[i] = 0xFFFFFFFFu;
+    tile.sync();
+    // -- lists:sort/1 (sga.erl:45): bitonic network over P slots
+    for (uint32_t k = 2; k <= P; k <<= 1) {
+        for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+            for (uint32_t i = lane; i < P; i += G) {
+                uint32_t x = i ^ j;
+                if (x > i) {
+                    uint32_t a = seeds[i], b = seeds[x];
+                    bool asc = (i & k) == 0;
+                    if ((a > b) == asc) { seeds[i] = b; seeds[x] = a; }
+                }
+            }
+            tile.sync();
+        }
+    }
+    // -- get_similar/7 (sga.erl:46-64): chains with gaps <= TOLERANCE; keep those with >= 2 + Qty div 7
+    //    members as {last position, sum of gaps}; the reference's list is descending by position.
+    const uint32_t need = 2 + qty / 7;
+    uint32_t base_out = 0, emitted = 0;
+    for (int pass = 0; pass < 2; pass++) {
+        emitted = 0;
+        for (uint32_t b0 = 0; b0 < total; b0 += G) {
+            int64_t i = (int64_t)total - 1 - (int64_t)(b0 + lane);
+            bool em = false;
+            uint32_t S = 0, D = 0;
+            if (i >= 0) {
+                uint32_t si = seeds[i];
+                bool is_end = (i == (int64_t)total - 1) || (seeds[i + 1] - si > BWT_TOLERANCE);
+                if (is_end) {
+                    int64_t k = i;
+                    while (k > 0 && seeds[k] - seeds[k - 1] <= BWT_TOLERANCE) k--;
+                    if ((uint32_t)(i - k + 1) >= need) { em = true; S = si; D = si - seeds[k]; }
+                }
+            }
+            uint32_t bal = tile.ballot(em);
+            if (pass == 1 && em) {
+                uint32_t rank = emitted + __popc(bal & ((1u << lane) - 1u));
+                if ((uint64_t)base_out + rank < cl_cap) {      // on overflow the host retries with the needed capacity
+                    Cluster c;
+                    c.read = read; c.s = S; c.d = (int32_t)D; c.rank = rank;
+                    clusters[base_out + rank] = c;
+                }
+            }
+            emitted += __popc(bal);
+        }
+        if (pass == 0) {
+            if (emitted == 0) break;
+            if (lane == 0) {
+                base_out = atomicAdd(&ctr->n_clusters, emitted);
+                if ((uint64_t)base_out + emitted > cl_cap) atomicExch(&ctr->cluster_overflow, 1u);
+            }
+            base_out = tile.shfl(base_out, 0);
+        }
+    }
+    if (lane == 0) {
+        ncl[read] = emitted;
+        cl_base[read] = base_out;
+        if (!SLOW) atomicAdd(&s_ctr[CTR_CLUSTERS], (unsigned long long)emitted);
+        else atomicAdd(&ctr->clusters, (unsigned long long)emitted);
+    }
+    tile.sync();
+    return SGA_DONE;
+}
+
+template <int G, int MAXT>
+__global__ void __launch_bounds__(SGA_BLOCK) sga_kernel(DevIndex ix, const uint8_t *__restrict__ reads,
+                                                        const int64_t *__restrict__ offs, int64_t n_reads,
+                                                        int32_t *read_status, uint32_t *ncl, uint32_t *cl_base,
+                                                        Cluster *clusters, uint32_t cl_cap, SlowRead *slow,
+                                                        uint32_t slow_cap, SeedCounters *ctr) {
+    constexpr int GPB = SGA_BLOCK / G;
+    constexpr int CAP = 32 * G;
+    __shared__ uint32_t s_seeds[GPB][CAP];
+    __shared__ uint16_t s_end[GPB][MAXT], s_shift[GPB][MAXT];
+    __shared__ uint2 s_res[GPB][MAXT];
+    __shared__ uint32_t s_pos[GPB][MAXT];
+    __shared__ unsigned long long s_ctr[CTR_N];
+    if (threadIdx.x < CTR_N) s_ctr[threadIdx.x] = 0;
+    __syncthreads();
+    auto tile = cg::tiled_partition<G>(cg::this_thread_block());
+    const int g = threadIdx.x / G;
+    GroupShared gs{s_end[g], s_shift[g], s_res[g], s_pos[g]};
+    for (int64_t read = (int64_t)blockIdx.x * GPB + g; read < n_reads; read += (int64_t)gridDim.x * GPB) {
+        const uint8_t *q = reads + offs[read];
+        int lq = (int)(offs[read + 1] - offs[read]);
+        // a read with more subsequences than MAXT cannot run in this instantiation: the launcher picks
+        // G/MAXT from the longest read of the batch, so this only guards against misuse
+        if (lq > BWT_MIN_LEN * (MAXT - 1) + BWT_MAX_LEN && MAXT < SGA_MAX_TASKS) {
+            if (tile.thread_rank() == 0) { read_status[read] = BWT_READ_LIMIT; ncl[read] = 0; cl_base[read] = 0; }
+            continue;
+        }
+        sga_read<G, MAXT, false>(tile, ix, q, lq, (uint32_t)read, s_seeds[g], CAP, gs, read_status, ncl, cl_base,
+                                 clusters, cl_cap, slow, slow_cap, ctr, s_ctr);
+        tile.sync();
+    }
+    flush_counters(s_ctr, ctr);
+}
+
+// reads whose seed ends overflow the shared-memory budget: one warp per read, seeds in HBM scratch
+__global__ void __launch_bounds__(SGA_BLOCK) sga_slow_kernel(DevIndex ix, const uint8_t *__restrict__ reads,
+                                                             const int64_t *__restrict__ offs,
+                                                             const SlowRead *__restrict__ slow,
+                                                             const uint64_t *__restrict__ slow_off, uint32_t n_slow,
+                                                             uint32_t *scratch, int32_t *read_status, uint32_t *ncl,
+                                                             uint32_t *cl_base, Cluster *clusters, uint32_t cl_cap,
+                                                             SeedCounters *ctr) {
+    constexpr int G = 32, GPB = SGA_BLOCK / G, MAXT = SGA_MAX_TASKS;
+    __shared__ uint16_t s_end[GPB][MAXT], s_shift[GPB][MAXT];
+    __shared__ uint2 s_res[GPB][MAXT];
+    __shared__ uint32_t s_pos[GPB][MAXT];
+    auto tile = cg::tiled_partition<G>(cg::this_thread_block());
+    const int g = threadIdx.x / G;
+    GroupShared gs{s_end[g], s_shift[g], s_res[g], s_pos[g]};
+    for (uint32_t w = blockIdx.x * GPB + g; w < n_slow; w += gridDim.x * GPB) {
+        uint32_t read = slow[w].read;
+        const uint8_t *q = reads + offs[read];
+        int lq = (int)(offs[read + 1] - offs[read]);
+        uint64_t cap = slow_off[w + 1] - slow_off[w];
+        sga_read<G, MAXT, true>(tile, ix, q, lq, read, scratch + slow_off[w], (uint32_t)cap, gs, read_status, ncl,
+                                cl_base, clusters, cl_cap, nullptr, 0, ctr, nullptr);
+        tile.sync();
+    }
+}
+
+}  // namespace
+
+int launch_search(const DevIndex &ix, const uint8_t *d_subs, const int64_t *d_offs, int64_t n, int32_t fixed_len,
+                  int32_t *d_status, uint32_t *d_sp, uint32_t *d_ep, int32_t *d_n, SeedCounters *d_ctr,
+                  cudaStream_t stream) {
+    if (n <= 0) return BWT_OK;
+    int64_t blocks = (n + 255) / 256;
+    if (blocks > 148 * 64) blocks = 148 * 64;         // grid-stride beyond 64 CTAs per SM
+    search_kernel<<<(unsigned)blocks, 256, 0, stream>>>(ix, d_subs, d_offs, n, fixed_len, d_status, d_sp, d_ep, d_n, d_ctr);
+    CU_TRY(cudaGetLastError());
+    return BWT_OK;
+}
+
+int launch_sga(const DevIndex &ix, const uint8_t *d_reads, const int64_t *d_offs, int64_t n_reads, int max_read_len,
+               int32_t *d_read_status, uint32_t *d_ncl, uint32_t *d_cl_base, Cluster *d_clusters, uint32_t cl_cap,
+               SlowRead *d_slow, uint32_t slow_cap, SeedCounters *d_ctr, cudaStream_t stream) {
+    if (n_reads <= 0) return BWT_OK;
+    // 16 lanes per read while every read has at most 16 subsequences (<= 135 bases), else a full warp
+    if (max_read_len <= BWT_MIN_LEN * 15 + BWT_MAX_LEN) {
+        int64_t blocks = (n_reads + 7) / 8;
+        if (blocks > 148 * 256) blocks = 148 * 256;
+        sga_kernel<16, 16><<<(unsigned)blocks, SGA_BLOCK, 0, stream>>>(ix, d_reads, d_offs, n_reads, d_read_status, d_ncl,
+                                                                     d_cl_base, d_clusters, cl_cap, d_slow, slow_cap, d_ctr);
+    } else {
+        int64_t blocks = (n_reads + 3) / 4;
+        if (blocks > 148 * 256) blocks = 148 * 256;
+        sga_kernel<32, SGA_MAX_TASKS><<<(unsigned)blocks, SGA_BLOCK, 0, stream>>>(ix, d_reads, d_offs, n_reads, d_read_status,
+                                                                               d_ncl, d_cl_base, d_clusters, cl_cap, d_slow,
+                                                                               slow_cap, d_ctr);
+    }
+    CU_TRY(cudaGetLastError());
+    return BWT_OK;
+}
+
+int launch_sga_slow(const DevIndex &ix, const uint8_t *d_reads, const int64_t *d_offs, const SlowRead *d_slow,
+                    const uint64_t *d_slow_off, uint32_t n_slow, uint32_t *d_scratch, int32_t *d_read_status,
+                    uint32_t *d_ncl, uint32_t *d_cl_base, Cluster *d_clusters, uint32_t cl_cap, SeedCounters *d_ctr,
+                    cudaStream_t stream) {
+    if (n_slow == 0) return BWT_OK;
+    unsigned blocks = (n_slow + 3) / 4;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    sga_slow_kernel<<<blocks, SGA_BLOCK, 0, stream>>>(ix, d_reads, d_offs, d_slow, d_slow_off, n_slow, d_scratch,
+                                                      d_read_status, d_ncl, d_cl_base, d_clusters, cl_cap, d_ctr);
+    CU_TRY(cudaGetLastError());
+    return BWT_OK;
+}

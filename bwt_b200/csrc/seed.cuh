@@ -1,0 +1,37 @@
+// Seeding kernels: batched backward search, and the fused per-read
+//   skip_Ns -> find_seeds -> locate -> sort -> vote        (sga:sga/6, sga.erl:17-76)
+// with one cooperative group of G lanes per read.  Seed ends never leave the SM: they are located into
+// shared memory, sorted there (bitonic) and voted into {S,D} clusters; only clusters go to HBM.
+#pragma once
+#include "common.cuh"
+
+struct Cluster {        // one element of sga's result list, 16 B
+    uint32_t read;      // read index inside the batch
+    uint32_t s;         // S: 0-based end (exclusive) of the read in the chunk
+    int32_t d;          // D: sum of gaps of the voting chain
+    uint32_t rank;      // position in the reference's (descending) result list
+};
+
+struct SeedCounters {   // device-side counters of one run
+    unsigned long long searches, lf_steps, hbm_lf_steps, located, clusters;
+    uint32_t n_clusters;      // append cursor of the cluster list
+    uint32_t n_slow;          // reads whose seed ends did not fit the shared-memory budget
+    uint32_t cluster_overflow;
+    uint32_t pad;
+};
+
+struct SlowRead { uint32_t read; uint32_t seeds; };
+
+constexpr int SGA_MAX_TASKS = 128;    // subsequences per read => BWT_MAX_READ_LEN = 8*127 + 15
+
+// launchers (seed.cu)
+int launch_search(const DevIndex &ix, const uint8_t *d_subs, const int64_t *d_offs, int64_t n, int32_t fixed_len,
+                  int32_t *d_status, uint32_t *d_sp, uint32_t *d_ep, int32_t *d_n, SeedCounters *d_ctr,
+                  cudaStream_t stream);
+int launch_sga(const DevIndex &ix, const uint8_t *d_reads, const int64_t *d_offs, int64_t n_reads, int max_read_len,
+               int32_t *d_read_status, uint32_t *d_ncl, uint32_t *d_cl_base, Cluster *d_clusters, uint32_t cl_cap,
+               SlowRead *d_slow, uint32_t slow_cap, SeedCounters *d_ctr, cudaStream_t stream);
+int launch_sga_slow(const DevIndex &ix, const uint8_t *d_reads, const int64_t *d_offs, const SlowRead *d_slow,
+                    const uint64_t *d_slow_off, uint32_t n_slow, uint32_t *d_scratch, int32_t *d_read_status,
+                    uint32_t *d_ncl, uint32_t *d_cl_base, Cluster *d_clusters, uint32_t cl_cap, SeedCounters *d_ctr,
+                    cudaStream_t stream);

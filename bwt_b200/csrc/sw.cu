@@ -1,0 +1,486 @@
+// Candidate extension kernels: sw:sw/2 of the reference (sw.erl:47-160), bit-exact.
+//
+// The recurrence is NOT Gotoh: one matrix of (V, dir) cells; a gap costs -1 when the neighbour's *chosen*
+// direction already is that gap and -2 otherwise; ties resolve up_left > up > left (Erlang term order of
+// {V,Atom} under lists:max/1, sw.erl:90-94); the query is global, the window is free at both ends; a row
+// whose maximum falls below -2*(Lq div 2) + 2*i ends the alignment with no_match (sw.erl:62,69-71).
+//
+// Fast path (both strings plain ACGT, the common case):  one THREAD per pair, no inter-thread traffic.
+//   * a cell is one 32-bit key  K = 8*V + code,  code: left=1, up=2, up_left=4.  max over the three
+//     candidate keys reproduces value-then-direction ordering in one integer max, and the direction
+//     dependent gap cost is  m + 8*[code bit]  with m = K & ~7:
+//        diag = m(i-1,j-1) + (8*sigma+4)      up = m(i-1,j) + 4*(K&2) - 14      left = m(i,j-1) + 8*(K&1) - 15
+//     so a cell is 2 x VIADDMNMX (DPX, __viaddmax_s32) + 1 x VIMNMX for the row maximum + LOP3/IMAD.
+//   * the thread sweeps the matrix in strips of SW_R = 10 rows held in registers; only the strip's bottom
+//     row (int16 keys) and the 2-bit packed window live in shared memory, laid out [column][thread] so
+//     that a warp's accesses are conflict free.
+//   * the ten 3-bit direction codes of one column of a strip are one 32-bit word, written to a per-thread
+//     slice of an HBM/L2 scratch ([word][thread], coalesced) and read back by the traceback.
+//   * sigma comes from a per-row 4-byte profile selected with one PRMT (__byte_perm) by the window base.
+// General path (any byte, e.g. 'N' = 1.6 or IUPAC codes in the window, or sizes beyond the fast tier):
+//   IEEE doubles added in the reference's order, one thread per pair, rows in HBM scratch.
+#include "sw.cuh"
+
+namespace {
+
+__device__ __forceinline__ bool is_acgt(uint8_t c) { return c == 'A' || c == 'C' || c == 'G' || c == 'T'; }
+
+// ---------------------------------------------------------------------------------------------------
+// classification: fast list / general list / immediate no_match
+// ---------------------------------------------------------------------------------------------------
+__global__ void sw_classify_kernel(const SwDesc *__restrict__ desc, SwOut *__restrict__ out, uint32_t n,
+                                   int cap_cols, uint32_t *__restrict__ list_fast, uint32_t *__restrict__ list_gen,
+                                   SwCounters *ctr) {
+    uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    if (out[k].status == BWT_HIT_WINDOW_OOR) return;
+    SwDesc d = desc[k];
+    if (d.lq <= 0 || d.lr <= 0) {                   // sw(_,_) -> no_match for empty strings (sw.erl:54)
+        SwOut o; o.score = 0; o.status = BWT_HIT_NO_MATCH; o.cigar_len = 0; o.cigar_off = 0;
+        out[k] = o;
+        return;
+    }
+    if (d.lq <= SW_FAST_MAX_LQ && d.lr + 1 <= cap_cols) list_fast[atomicAdd(&ctr->n_fast, 1u)] = k;
+    else list_gen[atomicAdd(&ctr->n_general, 1u)] = k;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// fast path
+// ---------------------------------------------------------------------------------------------------
+struct SwFastParams {
+    const uint8_t *qbase, *rbase;
+    const SwDesc *desc;
+    const uint32_t *list;
+    SwOut *out;
+    uint32_t *list_gen;
+    SwCounters *ctr;
+    char *cig;
+    uint32_t cig_cap;
+    uint32_t *dirs;
+    int cap_cols;      // columns (Lr+1) the shared row can hold; multiple of 16
+    int max_strips;
+};
+
+template <bool MASKED>
+__device__ __forceinline__ void sw_strip(int16_t *__restrict__ row, const uint32_t *__restrict__ refw,
+                                         uint32_t *__restrict__ dstrip, const int lr, const int i0,
+                                         const uint32_t (&prof)[SW_R], int (&mx)[SW_R]) {
+    constexpr int B = SW_BLOCK;
+    int mleft[SW_R], lfv[SW_R];
+    const int rmin = 1 - i0;                        // first real row of a masked strip (rows i <= 0 are row 0)
+#pragma unroll
+    for (int r = 0; r < SW_R; r++) {
+        int i = i0 + r;
+        int k0 = -8 * (i + 1) + 2;                  // column 0: V = -(i+1), dir = up   (sw.erl:72-77)
+        if (MASKED && r < rmin) k0 = 0;
+        mleft[r] = k0 & ~7;
+        lfv[r] = mleft[r];
+        mx[r] = k0;
+    }
+    int mD_top = (int)row[0] & ~7;                  // K(i0-1, 0)
+    row[0] = (int16_t)(-8 * (i0 + SW_R) + 2);       // K(last row of the strip, 0)
+    uint32_t rw = 0;
+    for (int j = 1; j <= lr; j++) {
+        const int kt = row[j * B];
+        const int mT = kt & ~7;
+        int uup = mT + ((kt & 2) << 2);
+        if (((j - 1) & 15) == 0) rw = refw[((j - 1) >> 4) * B];
+        const uint32_t sel = (rw & 3u) * 0x1111u + 0x8880u;   // PRMT selector: byte b, sign-extended
+        rw >>= 2;
+        int mdiag = mD_top;
+        uint32_t dw = 0;
+        int K = 0;
+#pragma unroll
+        for (int r = 0; r < SW_R; r++) {
+            const int s = (int)__byte_perm(prof[r], 0u, sel);          // 8*sigma + 4
+            const int x = __viaddmax_s32(lfv[r], -15, mdiag + s);      // max(left, diag)
+            K = __viaddmax_s32(uup, -14, x);                           // max(up, .)
+            if (MASKED) K = (r >= rmin) ? K : 0;
+            mdiag = mleft[r];
+            const int m = K & ~7;
+            mleft[r] = m;
+            lfv[r] = m + ((K & 1) << 3);
+            uup = m + ((K & 2) << 2);
+            mx[r] = max(mx[r], K);
+            dw |= (uint32_t)(K & 7) << (3 * r);
+        }
+        mD_top = mT;
+        row[j * B] = (int16_t)K;
+        dstrip[j * B] = dw;
+    }
+}
+
+__global__ void __launch_bounds__(SW_BLOCK) sw_fast_kernel(SwFastParams p) {
+    extern __shared__ uint32_t smem[];
+    constexpr int B = SW_BLOCK;
+    constexpr int R = SW_R;
+    const int tid = threadIdx.x;
+    int16_t *row = reinterpret_cast<int16_t *>(smem) + tid;                              // row[j*B]
+    uint32_t *refw = smem + (p.cap_cols * B) / 2 + tid;                                  // refw[w*B]
+    uint32_t *dirs = p.dirs + (size_t)blockIdx.x * p.max_strips * p.cap_cols * B + tid;  // dirs[(s*cap+j)*B]
+    const uint32_t n_list = p.ctr->n_fast;
+    unsigned long long calls = 0, cells = 0;
+
+    for (uint32_t it = blockIdx.x * B + tid; it < n_list; it += gridDim.x * B) {
+        const uint32_t cand = p.list[it];
+        const SwDesc d = p.desc[cand];
+        const uint8_t *q = p.qbase + d.q_off;
+        const uint8_t *w = p.rbase + d.r_off;
+        const int lq = d.lq, lr = d.lr;
+        // stage the window as 2-bit codes ((c>>1)&3: A0 C1 T2 G3) and validate both strings
+        bool plain = true;
+        for (int j0 = 0; j0 < lr; j0 += 16) {
+            uint32_t word = 0;
+            for (int t = 0; t < 16 && j0 + t < lr; t++) {
+                uint8_t c = w[j0 + t];
+                plain &= is_acgt(c);
+                word |= (uint32_t)((c >> 1) & 3) << (2 * t);
+            }
+            refw[(j0 >> 4) * B] = word;
+        }
+        for (int i = 0; i < lq; i++) plain &= is_acgt(q[i]);
+        if (!plain) {                                // 'N' / IUPAC: the double-precision kernel takes it
+            p.list_gen[atomicAdd(&p.ctr->n_general, 1u)] = cand;
+            continue;
+        }
+        for (int j = 0; j <= lr; j++) row[j * B] = 0;            // row 0: {0,undef}  (sw.erl:61)
+        const int nstr = (lq + R - 1) / R;
+        const int i_first = lq - nstr * R + 1;                    // row number of strip 0, r = 0 (<= 1)
+        const int thr0 = -2 * (lq / 2);                           // sw.erl:62
+        int rows_done = lq;
+        bool failed = false;
+        int mx[R];
+        for (int s = 0; s < nstr; s++) {
+            const int i0 = i_first + s * R;
+            uint32_t prof[R];
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                int i = i0 + r;
+                uint32_t qc = (i >= 1) ? ((q[i - 1] >> 1) & 3u) : 0u;
+                prof[r] = 0xFCFCFCFCu ^ (0xE8u << (8 * qc));      // byte qc = 20 (match), others = -4 (mismatch)
+            }
+            uint32_t *dstrip = dirs + (size_t)s * p.cap_cols * B;
+            if (i0 < 1) sw_strip<true>(row, refw, dstrip, lr, i0, prof, mx);
+            else sw_strip<false>(row, refw, dstrip, lr, i0, prof, mx);
+            // row threshold (sw.erl:69-71): Vmax of row i must reach thr0 + 2*i
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                int i = i0 + r;
+                if (i >= 1 && !failed && (mx[r] >> 3) < thr0 + 2 * i) { failed = true; rows_done = i; }
+            }
+            if (failed) break;
+        }
+        calls++;
+        cells += (unsigned long long)rows_done * (unsigned)lr;
+        SwOut o;
+        o.score = 0; o.status = BWT_HIT_NO_MATCH; o.cigar_len = 0; o.cigar_off = 0;
+        if (failed) { p.out[cand] = o; continue; }
+        const int vmax = mx[R - 1] >> 3;
+        int j = 0;
+        while ((row[j * B] >> 3) != vmax) j++;                    // leftmost maximum of the last row (sw.erl:110-112)
+        // traceback (sw.erl:116-160); runs are pushed newest-first into the (now free) shared row
+        uint16_t *runs = reinterpret_cast<uint16_t *>(row);
+        int i = lq, nr = 0, cur = -1, len = 0;
+        bool ovf = false;
+        while (i > 0) {
+            int op;                                               // 0 = M (up_left), 1 = D (left), 2 = I (up)
+            if (j == 0) op = 2;
+            else {
+                int t = i - i_first, s = t / R, r = t - s * R;
+                uint32_t code = (dirs[((size_t)s * p.cap_cols + j) * B] >> (3 * r)) & 7u;
+                op = code == 4u ? 0 : code == 2u ? 2 : 1;
+            }
+            if (op == cur) len++;
+            else {
+                if (cur >= 0) { if (nr < p.cap_cols) runs[nr * B] = (uint16_t)((len << 2) | cur); else ovf = true; nr++; }
+                cur = op; len = 1;
+            }
+            if (op == 0) { i--; j--; } else if (op == 2) i--; else j--;
+        }
+        if (nr < p.cap_cols) runs[nr * B] = (uint16_t)((len << 2) | cur); else ovf = true;
+        nr++;
+        if (ovf) { p.list_gen[atomicAdd(&p.ctr->n_general, 1u)] = cand; calls--; cells -= (unsigned long long)rows_done * (unsigned)lr; continue; }
+        int clen = 0;
+        for (int k = 0; k < nr; k++) {
+            int l = runs[k * B] >> 2;
+            clen += 2 + (l >= 10) + (l >= 100) + (l >= 1000) + (l >= 10000);
+        }
+        uint32_t off = atomicAdd(&p.ctr->cig_used, (uint32_t)clen);
+        if ((uint64_t)off + clen <= p.cig_cap) {
+            char *c = p.cig + off;
+            for (int k = nr - 1; k >= 0; k--) {
+                int v = runs[k * B];
+                int l = v >> 2, op = v & 3;
+                int nd = 1 + (l >= 10) + (l >= 100) + (l >= 1000) + (l >= 10000);
+                for (int t = nd - 1; t >= 0; t--) { c[t] = (char)('0' + l % 10); l /= 10; }
+                c[nd] = op == 0 ? 'M' : op == 1 ? 'D' : 'I';
+                c += nd + 1;
+            }
+        } else atomicExch(&p.ctr->cig_overflow, 1u);
+        o.score = vmax; o.status = BWT_HIT_MATCH; o.cigar_len = clen; o.cigar_off = off;
+        p.out[cand] = o;
+    }
+    for (int dlt = 16; dlt > 0; dlt >>= 1) {
+        calls += __shfl_down_sync(0xFFFFFFFFu, calls, dlt);
+        cells += __shfl_down_sync(0xFFFFFFFFu, cells, dlt);
+    }
+    if ((tid & 31) == 0 && calls) { atomicAdd(&p.ctr->sw_calls, calls); atomicAdd(&p.ctr->cells, cells); }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// general path: doubles, any alphabet, any size
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double sigma_ref(uint8_t q, uint8_t r) {      // sw.erl:164-202, first clause wins
+    if (q == 'N' && r == 'N') return 1.6;
+    if (q == r) return 2.0;
+    if (q == 'N' || r == 'N') return 1.6;
+    switch (r) {
+    case 'R': return (q == 'A' || q == 'G') ? 2.0 : -1.0;
+    case 'Y': return (q == 'C' || q == 'T') ? 2.0 : -1.0;
+    case 'B': return (q == 'A') ? -1.0 : 2.0;
+    case 'D': return (q == 'C') ? -1.0 : 2.0;
+    case 'K': return (q == 'G' || q == 'T') ? 2.0 : -1.0;
+    case 'M': return (q == 'A' || q == 'C') ? 2.0 : -1.0;
+    case 'S': return (q == 'G' || q == 'C') ? 2.0 : -1.0;
+    case 'W': return (q == 'A' || q == 'T') ? 2.0 : -1.0;
+    case 'V': return (q == 'T') ? -1.0 : 2.0;
+    default: return -1.0;
+    }
+}
+
+__global__ void sw_dims_kernel(const SwDesc *__restrict__ desc, const uint32_t *__restrict__ list, uint32_t n,
+                               int2 *__restrict__ dims) {
+    uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n) { SwDesc d = desc[list[k]]; dims[k] = make_int2(d.lq, d.lr); }
+}
+
+__host__ __device__ inline uint64_t sw_general_scratch_bytes(int lq, int lr) {
+    uint64_t W = (uint64_t)lr + 1;
+    uint64_t b = 2 * W * 8 + ((uint64_t)lq + 1) * W + 4 * ((uint64_t)lq + lr + 2);
+    return (b + 15) & ~15ull;
+}
+
+__global__ void __launch_bounds__(64) sw_general_kernel(const uint8_t *__restrict__ qbase, const uint8_t *__restrict__ rbase,
+                                                        const SwDesc *__restrict__ desc, const uint32_t *__restrict__ list,
+                                                        uint32_t first, uint32_t count, const uint64_t *__restrict__ off,
+                                                        uint8_t *scratch, SwOut *out, SwCounters *ctr, char *cig,
+                                                        uint32_t cig_cap) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= count) return;
+    const uint32_t cand = list[first + t];
+    const SwDesc d = desc[cand];
+    const uint8_t *q = qbase + d.q_off, *w = rbase + d.r_off;
+    const int lq = d.lq, lr = d.lr, W = lr + 1;
+    uint8_t *base = scratch + (off[first + t] - off[first]);
+    double *pv = reinterpret_cast<double *>(base), *cv = pv + W;
+    uint8_t *dirs = reinterpret_cast<uint8_t *>(cv + W);                 // (lq+1) x W, codes 0 left 1 up 2 up_left 3 undef
+    uint32_t *runs = reinterpret_cast<uint32_t *>(base + ((2 * (uint64_t)W * 8 + ((uint64_t)lq + 1) * W + 3) & ~3ull));
+    for (int j = 0; j < W; j++) { pv[j] = 0.0; dirs[j] = 3; }
+    double thr = (double)(-2 * (lq / 2));
+    double vmax = 0.0;
+    bool failed = false;
+    int rows_done = lq;
+    for (int i = 1; i <= lq; i++) {
+        if (vmax < thr) { failed = true; rows_done = i - 1; break; }      // sw.erl:69-71
+        uint8_t *cd = dirs + (size_t)i * W, *pd = cd - W;
+        cv[0] = pv[0] + (i == 1 ? -2.0 : -1.0);                           // sw.erl:72-77
+        cd[0] = 1;
+        double rowmax = cv[0];
+        const uint8_t qc = q[i - 1];
+        for (int j = 1; j < W; j++) {                                     // sw.erl:88-98
+            double bv = __dadd_rn(pv[j - 1], sigma_ref(qc, w[j - 1]));
+            int bd = 2;
+            double c = __dadd_rn(cv[j - 1], cd[j - 1] == 0 ? -1.0 : -2.0);
+            if (c > bv) { bv = c; bd = 0; }
+            c = __dadd_rn(pv[j], pd[j] == 1 ? -1.0 : -2.0);
+            if (c > bv || (c == bv && bd == 0)) { bv = c; bd = 1; }
+            cv[j] = bv; cd[j] = (uint8_t)bd;
+            if (bv > rowmax) rowmax = bv;
+        }
+        double *tp = pv; pv = cv; cv = tp;
+        vmax = rowmax;
+        thr += 2.0;
+    }
+    if (!failed && vmax < thr) failed = true;
+    atomicAdd(&ctr->sw_calls, 1ull);
+    atomicAdd(&ctr->cells, (unsigned long long)rows_done * (unsigned)lr);
+    atomicAdd(&ctr->general_done, 1u);
+    SwOut o;
+    o.score = 0; o.status = BWT_HIT_NO_MATCH; o.cigar_len = 0; o.cigar_off = 0;
+    if (failed) { out[cand] = o; return; }
+    int j = 0;
+    while (pv[j] != vmax) j++;
+    int i = lq, nr = 0, cur = -1, len = 0;
+    while (i > 0) {
+        uint8_t dc = dirs[(size_t)i * W + j];
+        int op = dc == 2 ? 0 : dc == 1 ? 2 : 1;
+        if (op == cur) len++;
+        else { if (cur >= 0) runs[nr++] = ((uint32_t)len << 2) | (uint32_t)cur; cur = op; len = 1; }
+        if (op == 0) { i--; j--; } else if (op == 2) i--; else j--;
+    }
+    runs[nr++] = ((uint32_t)len << 2) | (uint32_t)cur;
+    int clen = 0;
+    for (int k = 0; k < nr; k++) {
+        uint32_t l = runs[k] >> 2;
+        int nd = 1;
+        while (l >= 10) { nd++; l /= 10; }
+        clen += nd + 1;
+    }
+    uint32_t offc = atomicAdd(&ctr->cig_used, (uint32_t)clen);
+    if ((uint64_t)offc + clen <= cig_cap) {
+        char *c = cig + offc;
+        for (int k = nr - 1; k >= 0; k--) {
+            uint32_t l = runs[k] >> 2;
+            int op = runs[k] & 3, nd = 1;
+            for (uint32_t x = l; x >= 10; x /= 10) nd++;
+            for (int tt = nd - 1; tt >= 0; tt--) { c[tt] = (char)('0' + l % 10); l /= 10; }
+            c[nd] = op == 0 ? 'M' : op == 1 ? 'D' : 'I';
+            c += nd + 1;
+        }
+    } else atomicExch(&ctr->cig_overflow, 1u);
+    o.score = (int32_t)(long long)vmax;                                    // trunc/1 (sw.erl:123)
+    o.status = BWT_HIT_MATCH; o.cigar_len = clen; o.cigar_off = offc;
+    out[cand] = o;
+}
+
+template <typename T>
+int grow(T *&p, size_t &cap_items, size_t need_items) {
+    if (need_items <= cap_items && p) return BWT_OK;
+    if (p) cudaFree(p);
+    p = nullptr;
+    size_t want = need_items + need_items / 4 + 16;
+    if (cudaMalloc(&p, want * sizeof(T)) != cudaSuccess) {
+        cudaGetLastError();
+        cap_items = 0;
+        bwt_set_error("device allocation of %zu bytes failed", want * sizeof(T));
+        return BWT_ERR_NOMEM;
+    }
+    cap_items = want;
+    return BWT_OK;
+}
+
+}  // namespace
+
+int sw_stage_reserve(SwStage &st, uint32_t pairs) {
+    if (pairs <= st.cap && st.d_desc) return BWT_OK;
+    uint32_t want = pairs + pairs / 4 + 1024;
+    if (st.d_desc) { cudaFree(st.d_desc); cudaFree(st.d_out); cudaFree(st.d_list_fast); cudaFree(st.d_list_gen); }
+    st.d_desc = nullptr; st.d_out = nullptr; st.d_list_fast = nullptr; st.d_list_gen = nullptr;
+    st.cap = 0;
+    CU_TRY(cudaMalloc(&st.d_desc, (size_t)want * sizeof(SwDesc)));
+    CU_TRY(cudaMalloc(&st.d_out, (size_t)want * sizeof(SwOut)));
+    CU_TRY(cudaMalloc(&st.d_list_fast, (size_t)want * sizeof(uint32_t)));
+    CU_TRY(cudaMalloc(&st.d_list_gen, (size_t)want * sizeof(uint32_t)));
+    if (!st.d_ctr) {
+        CU_TRY(cudaMalloc(&st.d_ctr, sizeof(SwCounters)));
+        CU_TRY(cudaMallocHost(&st.h_ctr, sizeof(SwCounters)));
+    }
+    st.cap = want;
+    if (st.cig_cap < 32u * want) {
+        if (st.d_cig_tmp) cudaFree(st.d_cig_tmp);
+        st.d_cig_tmp = nullptr;
+        st.cig_cap = 32u * want;
+        CU_TRY(cudaMalloc(&st.d_cig_tmp, st.cig_cap));
+    }
+    return BWT_OK;
+}
+
+void sw_stage_free(SwStage &st) {
+    cudaFree(st.d_desc); cudaFree(st.d_out); cudaFree(st.d_list_fast); cudaFree(st.d_list_gen);
+    cudaFree(st.d_ctr); if (st.h_ctr) cudaFreeHost(st.h_ctr);
+    cudaFree(st.d_cig_tmp); cudaFree(st.d_dirs); cudaFree(st.d_gen_scratch); cudaFree(st.d_gen_off); cudaFree(st.d_gen_dims);
+    st = SwStage();
+}
+
+int sw_stage_run(SwStage &st, const uint8_t *d_qbase, const uint8_t *d_rbase, uint32_t n, int max_lq,
+                 cudaStream_t stream) {
+    st.sw_calls = st.cells = st.n_general = 0;
+    if (n == 0) return BWT_OK;
+    if (n > st.cap) { bwt_set_error("sw_stage_run: %u pairs exceed the reserved %u", n, st.cap); return BWT_ERR_ARG; }
+    // shared-memory tier: columns = longest query + 1 + 64 slack, multiple of 16, capped by the 227 KB CTA limit
+    int cap_cols = ((max_lq + 1 + 64) + 15) & ~15;
+    const int cap_limit = 688;
+    if (cap_cols > cap_limit) cap_cols = cap_limit;
+    int max_strips = (std::min(max_lq, SW_FAST_MAX_LQ) + SW_R - 1) / SW_R;
+    if (max_strips < 1) max_strips = 1;
+    size_t smem = (size_t)SW_BLOCK * (cap_cols * 2 + (cap_cols / 16) * 4);
+    CU_TRY(cudaFuncSetAttribute(sw_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sw_fast_kernel, SW_BLOCK, smem));
+    if (per_sm < 1) { bwt_set_error("sw_fast_kernel does not fit an SM with %zu B of shared memory", smem); return BWT_ERR_CUDA; }
+    int sms = 0;
+    CU_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, st.device));
+    unsigned grid = (unsigned)std::min<uint64_t>((n + SW_BLOCK - 1) / SW_BLOCK, (uint64_t)sms * per_sm);
+    size_t need_dirs = (size_t)grid * SW_BLOCK * max_strips * cap_cols;
+    BWT_TRY(grow(st.d_dirs, st.dirs_words, need_dirs));
+
+    for (int attempt = 0; attempt < 4; attempt++) {
+        CU_TRY(cudaMemsetAsync(st.d_ctr, 0, sizeof(SwCounters), stream));
+        sw_classify_kernel<<<(n + 255) / 256, 256, 0, stream>>>(st.d_desc, st.d_out, n, cap_cols, st.d_list_fast,
+                                                                st.d_list_gen, st.d_ctr);
+        SwFastParams p;
+        p.qbase = d_qbase; p.rbase = d_rbase; p.desc = st.d_desc; p.list = st.d_list_fast; p.out = st.d_out;
+        p.list_gen = st.d_list_gen; p.ctr = st.d_ctr; p.cig = st.d_cig_tmp; p.cig_cap = st.cig_cap;
+        p.dirs = st.d_dirs; p.cap_cols = cap_cols; p.max_strips = max_strips;
+        sw_fast_kernel<<<grid, SW_BLOCK, smem, stream>>>(p);
+        st.launches += 2;
+        CU_TRY(cudaGetLastError());
+        CU_TRY(cudaMemcpyAsync(st.h_ctr, st.d_ctr, sizeof(SwCounters), cudaMemcpyDeviceToHost, stream));
+        CU_TRY(cudaStreamSynchronize(stream));
+        uint32_t ng = st.h_ctr->n_general;
+        if (ng > 0 && !st.h_ctr->cig_overflow) {
+            // size the per-pair scratch of the general kernel on the host
+            size_t cap_items = st.gen_off_cap;
+            if (ng + 1 > st.gen_off_cap) {
+                if (st.d_gen_off) cudaFree(st.d_gen_off);
+                if (st.d_gen_dims) cudaFree(st.d_gen_dims);
+                st.d_gen_off = nullptr; st.d_gen_dims = nullptr;
+                cap_items = (size_t)ng + ng / 2 + 64;
+                CU_TRY(cudaMalloc(&st.d_gen_off, cap_items * sizeof(uint64_t)));
+                CU_TRY(cudaMalloc(&st.d_gen_dims, cap_items * sizeof(int2)));
+                st.gen_off_cap = cap_items;
+            }
+            sw_dims_kernel<<<(ng + 255) / 256, 256, 0, stream>>>(st.d_desc, st.d_list_gen, ng, st.d_gen_dims);
+            st.launches += 1;
+            std::vector<int2> dims(ng);
+            CU_TRY(cudaMemcpyAsync(dims.data(), st.d_gen_dims, ng * sizeof(int2), cudaMemcpyDeviceToHost, stream));
+            CU_TRY(cudaStreamSynchronize(stream));
+            std::vector<uint64_t> off(ng + 1);
+            off[0] = 0;
+            for (uint32_t k = 0; k < ng; k++) off[k + 1] = off[k] + sw_general_scratch_bytes(dims[k].x, dims[k].y);
+            CU_TRY(cudaMemcpyAsync(st.d_gen_off, off.data(), (ng + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, stream));
+            // rounds of at most ~2 GB of scratch
+            const uint64_t round_bytes = 2ull << 30;
+            uint32_t first = 0;
+            while (first < ng) {
+                uint32_t last = first + 1;
+                while (last < ng && off[last + 1] - off[first] <= round_bytes) last++;
+                uint64_t need = off[last] - off[first];
+                BWT_TRY(grow(st.d_gen_scratch, st.gen_scratch_bytes, (size_t)need));
+                uint32_t cnt = last - first;
+                sw_general_kernel<<<(cnt + 63) / 64, 64, 0, stream>>>(d_qbase, d_rbase, st.d_desc, st.d_list_gen, first, cnt,
+                                                                     st.d_gen_off, st.d_gen_scratch, st.d_out, st.d_ctr,
+                                                                     st.d_cig_tmp, st.cig_cap);
+                st.launches += 1;
+                CU_TRY(cudaGetLastError());
+                CU_TRY(cudaStreamSynchronize(stream));
+                first = last;
+            }
+            CU_TRY(cudaMemcpyAsync(st.h_ctr, st.d_ctr, sizeof(SwCounters), cudaMemcpyDeviceToHost, stream));
+            CU_TRY(cudaStreamSynchronize(stream));
+        }
+        if (!st.h_ctr->cig_overflow) {
+            st.sw_calls = st.h_ctr->sw_calls; st.cells = st.h_ctr->cells; st.n_general = st.h_ctr->n_general;
+            return BWT_OK;
+        }
+        // temporary CIGAR arena too small: grow to what this attempt asked for (and then some) and redo the stage
+        uint64_t want = (uint64_t)st.h_ctr->cig_used * 2 + 4096;
+        if (want > 0xFFFFFFF0ull) { bwt_set_error("CIGAR arena beyond 4 GiB for one batch: use smaller batches"); return BWT_ERR_LIMIT; }
+        cudaFree(st.d_cig_tmp);
+        st.d_cig_tmp = nullptr;
+        st.cig_cap = (uint32_t)want;
+        CU_TRY(cudaMalloc(&st.d_cig_tmp, st.cig_cap));
+    }
+    bwt_set_error("CIGAR arena kept overflowing");
+    return BWT_ERR_NOMEM;
+}

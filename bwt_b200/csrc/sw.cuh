@@ -1,0 +1,56 @@
+// Candidate extension: sw:sw/2 (sw.erl:47-160) for a list of (query, window) pairs.
+#pragma once
+#include "common.cuh"
+
+struct SwDesc {          // one (query, window) pair; offsets are into the q / r base buffers
+    int64_t q_off;
+    int64_t r_off;
+    int32_t lq;
+    int32_t lr;
+};
+
+struct SwOut {           // 16 B per pair
+    int32_t score;       // trunc(Vmax)
+    int32_t status;      // BWT_HIT_*
+    int32_t cigar_len;
+    uint32_t cigar_off;  // into the temporary CIGAR arena
+};
+
+struct SwCounters {
+    unsigned long long sw_calls, cells;
+    uint32_t n_fast, n_general;      // list cursors
+    uint32_t cig_used, cig_overflow; // temporary CIGAR arena
+    uint32_t general_done, pad;
+};
+
+constexpr int SW_R = 10;             // rows per register strip; ten 3-bit direction codes per 32-bit word
+constexpr int SW_BLOCK = 128;
+constexpr int SW_FAST_MAX_LQ = 1000; // int16 keys: |8V+7| <= 8*2*Lq+7 < 32768
+
+// Device-resident state of the extension stage (owned by a batch).
+struct SwStage {
+    int device = 0;
+    uint32_t cap = 0;                // pairs
+    SwDesc *d_desc = nullptr;
+    SwOut *d_out = nullptr;
+    uint32_t *d_list_fast = nullptr, *d_list_gen = nullptr;
+    SwCounters *d_ctr = nullptr, *h_ctr = nullptr;     // h_ctr pinned
+    char *d_cig_tmp = nullptr;
+    uint32_t cig_cap = 0;
+    uint32_t *d_dirs = nullptr;
+    size_t dirs_words = 0;
+    uint8_t *d_gen_scratch = nullptr;
+    size_t gen_scratch_bytes = 0;
+    uint64_t *d_gen_off = nullptr;
+    size_t gen_off_cap = 0;
+    int2 *d_gen_dims = nullptr;
+    uint32_t launches = 0;
+    unsigned long long sw_calls = 0, cells = 0, n_general = 0;
+};
+
+int sw_stage_reserve(SwStage &st, uint32_t pairs);
+void sw_stage_free(SwStage &st);
+// Runs the extension of pairs [0,n): d_desc must be filled, d_out[k].status preset to BWT_HIT_WINDOW_OOR for pairs
+// to skip and anything else for pairs to align.  max_lq = longest query (sizes the shared-memory tier).
+int sw_stage_run(SwStage &st, const uint8_t *d_qbase, const uint8_t *d_rbase, uint32_t n, int max_lq,
+                 cudaStream_t stream);

@@ -1,0 +1,192 @@
+/*
+ * bwt_b200.h -- C ABI of the B200-native read-alignment hot path of cloudozer/BWT.
+ *
+ * This is the drop-in boundary: the Erlang host (worker_bwt) reaches these entry points through the
+ * thin NIF in c_src/bwt_nif.c (INTEGRATION.md shows the binding); tests and bench.py reach the very same
+ * symbols through ctypes.  Plain pointers and sizes only.  Every function returns BWT_OK (0) or a
+ * negative bwt_status; bwt_last_error() gives the message of the calling thread's last failure.
+ * Nothing here aborts the process: what is "let it crash" in the reference (case_clause on a bad read
+ * character, badmatch on an out-of-range window) comes back as a per-read / per-hit status.
+ *
+ * There is no CPU fallback behind any of these calls: they need a CUDA device (sm_100a).
+ *
+ * Citations (file:line) are into the reference tree, cloudozer/BWT.
+ */
+#ifndef BWT_B200_H
+#define BWT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BWT_B200_ABI_VERSION 1
+
+typedef enum bwt_status {
+    BWT_OK = 0,
+    BWT_ERR_ARG = -1,      /* bad argument */
+    BWT_ERR_IO = -2,       /* file could not be read / written */
+    BWT_ERR_FORMAT = -3,   /* not a {Meta,FM} external term as written by fm_index:make_index/4 */
+    BWT_ERR_CUDA = -4,     /* CUDA runtime error (message in bwt_last_error) */
+    BWT_ERR_NOMEM = -5,    /* host or device allocation failed */
+    BWT_ERR_NOSPACE = -6,  /* caller-provided output capacity too small; the needed sizes are reported */
+    BWT_ERR_NODEVICE = -7, /* no usable CUDA device: this library has no CPU path */
+    BWT_ERR_LIMIT = -8     /* input beyond a documented limit (n >= 2^32-2^20 rows, read longer than 1031) */
+} bwt_status;
+
+/* per-search status: the three results of bwa:find_seeds/6 (bwa.erl:12-45) + the crash case */
+enum {
+    BWT_SEEDS = 0,          /* a seed list: rows Sp..Ep, N >= 8 characters matched */
+    BWT_NO_SEEDS = 1,       /* no_seeds  (fmi.erl:89-91) */
+    BWT_TOO_MANY_SEEDS = 2, /* too_many_seeds (bwa.erl:31,33,44) */
+    BWT_SEARCH_CRASH = 3    /* the reference raises (case_clause on the last character, bwa.erl:15-24;
+                               element(0,FM) after stepping through the '$' row) */
+};
+
+/* per-read status of sga / align */
+enum {
+    BWT_READ_OK = 0,
+    BWT_READ_CRASH = 1,     /* some search of this read would crash the reference worker */
+    BWT_READ_LIMIT = 2      /* read longer than BWT_MAX_READ_LEN or more seed ends than BWT_MAX_SEEDS_PER_READ */
+};
+
+/* per-hit status of sw / align */
+enum {
+    BWT_HIT_MATCH = 0,      /* sw:sw/2 returned {Score, Cigar} */
+    BWT_HIT_NO_MATCH = 1,   /* sw:sw/2 returned no_match (row threshold, sw.erl:69-71) */
+    BWT_HIT_WINDOW_OOR = 2  /* window outside the padded reference: badmatch at worker_bwt.erl:89 */
+};
+
+#define BWT_MAX_READ_LEN 1031          /* 128 subsequences of sga:sga/6 */
+#define BWT_MAX_SEEDS_PER_READ (1 << 22)
+
+typedef struct bwt_index bwt_index;   /* opaque: one FM-index partition + its padded .ref, resident in HBM */
+typedef struct bwt_batch bwt_batch;   /* opaque: device/pinned buffers and a stream for one batch in flight */
+
+typedef struct bwt_index_info {
+    uint64_t n_rows;        /* size(FM), including the '$' row */
+    uint32_t pointers[4];   /* {Pc,Pg,Pt,Last}, 1-based (fmi.erl:66-84) */
+    int64_t shift;          /* {shift,S} of the meta proplist (fm_index.erl:139) */
+    uint64_t ref_len;       /* bytes of the .ref chunk (unpadded) */
+    uint64_t dollar_row;    /* 1-based row whose L is '$' */
+    uint64_t device_bytes;  /* HBM held by this handle */
+    int32_t device;
+    int32_t kmer_k;         /* depth of the first-k-mer interval table (8) */
+} bwt_index_info;
+
+/* One candidate of one read: an element of worker_bwt's Cigars fold (worker_bwt.erl:84-97), plus the
+ * clusters whose sw:sw/2 said no_match (status != 0), which the reference drops.  40 bytes. */
+typedef struct bwt_hit {
+    int64_t pos;        /* S - Ref_len + Shift  (worker_bwt.erl:94) */
+    int64_t s;          /* sga's S: 0-based end (exclusive) of the read in the chunk (sga.erl:46-64) */
+    int64_t cigar_off;  /* byte offset of the CIGAR string in the arena (no terminator) */
+    int32_t d;          /* sga's D: window slack; Ref_len = Lq + D */
+    int32_t score;      /* trunc(Vmax) (sw.erl:123) */
+    int32_t status;     /* BWT_HIT_* */
+    int32_t cigar_len;
+} bwt_hit;
+
+typedef struct bwt_stats {   /* work counters of the last run (definitions: DESIGN.md "units") */
+    uint64_t reads, searches, lf_steps, located_rows, clusters, sw_calls, sw_cells, sw_general;
+    float ms_total, ms_seed, ms_sw, ms_emit, ms_h2d, ms_d2h; /* CUDA-event times on the batch's stream */
+    uint32_t launches;       /* kernels of this library launched by the last run */
+    uint32_t reserved;
+} bwt_stats;
+
+const char *bwt_last_error(void);
+int bwt_abi_version(void);
+int bwt_device_count(void);
+
+/* ---- index lifetime -------------------------------------------------------------------------------- */
+
+/* fm_index:get_index(Chrom,J) (fm_index.erl:154-156) + the .ref load and 200-'N' padding of
+ * worker_bwt.erl:48-55: parse <..>_pJ.fm (Erlang external term), upload, build the device layout. */
+int bwt_open(const char *fm_path, const char *ref_path, int device, bwt_index **out);
+
+/* Same, from arrays already in host memory (L: n ASCII bytes over "$ACGT"; SA: n 0-based suffix starts). */
+int bwt_open_arrays(const uint8_t *L, uint64_t n, const uint32_t *SA, const uint32_t pointers[4], int64_t shift,
+                    const uint8_t *ref, uint64_t ref_len, int device, bwt_index **out);
+
+/* fm_index:make_index/4 (fm_index.erl:127-141) on the device: chunk = bytes of the .ref (IUPAC allowed,
+ * mapped as fm_index.erl:131-135; 'N' is rejected because the reference substitutes random:uniform(4)).
+ * Suffix array by radix sort of 2-bit packed prefixes; any correct SA equals dsa:dsa/1's (dsa.erl:15-48). */
+int bwt_build(const uint8_t *chunk, uint64_t len, int64_t shift, int device, bwt_index **out);
+
+/* Synthetic reference for the benchmark configs: len i.i.d. uniform ACGT bases from a counter-based
+ * generator (seed), generated on the device, then indexed like bwt_build. */
+int bwt_build_synthetic(uint64_t len, uint64_t seed, int64_t shift, int device, bwt_index **out);
+
+/* Write <fm_path> = term_to_binary({Meta,FM}) and <ref_path> exactly as fm_index:make_index/4 does. */
+int bwt_save(const bwt_index *h, const char *fm_path, const char *ref_path);
+
+/* Copy the index columns back to the host (any pointer may be NULL): L[n], SA[n], ref[ref_len]. */
+int bwt_export(const bwt_index *h, uint8_t *L, uint32_t *SA, uint8_t *ref);
+
+int bwt_info(const bwt_index *h, bwt_index_info *info);
+int bwt_close(bwt_index *h);
+
+/* ---- one-shot calls with HOST buffers (copies inside) ------------------------------------------------ */
+
+/* bwa:find_seeds/6 (bwa.erl:12-45) for n subsequences: subs = concatenated ASCII, offsets[n+1].
+ * Outputs (each n long, any may be NULL): status (BWT_SEEDS..), final Sp/Ep (1-based rows, as the
+ * reference numbers them) and the number of characters matched.  The seed ends of search k are
+ * SA[Ep]+N, ..., SA[Sp]+N (fmi.erl:89-100): fetch them with bwt_locate. */
+int bwt_search_batch(bwt_index *h, const uint8_t *subs, const int64_t *offsets, int64_t n,
+                     int32_t *status, uint32_t *sp, uint32_t *ep, int32_t *nmatched);
+
+/* fmi:get_seed_ends/4 payload: SA of rows first..first+count-1 (1-based) */
+int bwt_locate(bwt_index *h, uint32_t first_row, uint32_t count, uint32_t *sa_out);
+
+/* sga:sga/6 (sga.erl:17-64) for n reads.  cl_offsets[n+1]; clusters of read r are
+ * S[cl_offsets[r]..cl_offsets[r+1]) / D[..] in the reference's order (descending S).
+ * *total = number of clusters; BWT_ERR_NOSPACE if cap is too small (then *total = needed). */
+int bwt_sga_batch(bwt_index *h, const uint8_t *reads, const int64_t *offsets, int64_t n,
+                  int32_t *read_status, int64_t *cl_offsets, int64_t *S, int32_t *D, int64_t cap, int64_t *total);
+
+/* sw:sw/2 (sw.erl:47-160) for n (query, window) pairs.  status BWT_HIT_MATCH / BWT_HIT_NO_MATCH,
+ * score = trunc(Vmax), CIGAR bytes of pair k at cigars[cigar_off[k] .. +cigar_len[k]). */
+int bwt_sw_batch(int device, const uint8_t *q, const int64_t *q_offsets, const uint8_t *r, const int64_t *r_offsets,
+                 int64_t n, int32_t *status, int32_t *score, int64_t *cigar_off, int32_t *cigar_len,
+                 char *cigars, int64_t cigar_cap, int64_t *cigar_total);
+
+/* The worker's inner loop for one list of reads (worker_bwt.erl:73-108), minus the top-1 pick that
+ * stays in Erlang (worker_bwt.erl:99-106): for read r, hits[hit_offsets[r]..hit_offsets[r+1]) are ALL
+ * sga clusters in ascending position; those with status BWT_HIT_MATCH are exactly the reference's Cigars
+ * list, in its order.  BWT_ERR_NOSPACE (with *n_hits / *cigar_bytes = needed) if a capacity is too small. */
+int bwt_align_batch(bwt_index *h, const uint8_t *reads, const int64_t *offsets, int64_t n,
+                    int32_t *read_status, int64_t *hit_offsets, bwt_hit *hits, int64_t hits_cap, int64_t *n_hits,
+                    char *cigars, int64_t cigar_cap, int64_t *cigar_bytes);
+
+/* ---- resident batches: upload / run / download separately (what bench.py times) --------------------- */
+
+int bwt_batch_create(bwt_index *h, int64_t max_reads, int64_t max_read_bytes, bwt_batch **out);
+int bwt_batch_destroy(bwt_batch *b);
+/* host -> HBM (pinned staging inside when the caller's memory is pageable) */
+int bwt_batch_upload(bwt_batch *b, const uint8_t *reads, const int64_t *offsets, int64_t n);
+/* all kernels of the path on the data resident in HBM; results stay in HBM.  Blocks until done. */
+int bwt_batch_run(bwt_batch *b);
+/* sizes of the last run's result */
+int bwt_batch_result_size(bwt_batch *b, int64_t *n_hits, int64_t *cigar_bytes);
+/* HBM -> host */
+int bwt_batch_download(bwt_batch *b, int32_t *read_status, int64_t *hit_offsets, bwt_hit *hits, int64_t hits_cap,
+                       char *cigars, int64_t cigar_cap);
+int bwt_batch_stats(bwt_batch *b, bwt_stats *out);
+/* device pointers of the last run's result (for an NCCL gather by the host harness; valid until the next run) */
+int bwt_batch_device_result(bwt_batch *b, void **d_hit_offsets, void **d_hits, void **d_cigars);
+
+/* Search-only resident benchmark entry: n fixed-length subsequences already in HBM are searched
+ * `repeats` times; *ms = CUDA-event time of all repeats, *lf_steps = LF steps executed per repeat. */
+int bwt_search_resident(bwt_index *h, const uint8_t *subs, int64_t n, int32_t sub_len, int32_t repeats,
+                        float *ms, uint64_t *lf_steps, uint64_t *hbm_lf_steps);
+
+/* Microbenchmarks that give the roofline denominators measured on the device at hand:
+ * random 32-byte-sector gather bandwidth (GB/s) and DPX (VIADDMNMX/VIMNMX3) issue rate (Gop/s). */
+int bwt_peak_gather_gbs(int device, uint64_t bytes, double *gbs);
+int bwt_peak_dpx_gops(int device, double *gops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BWT_B200_H */

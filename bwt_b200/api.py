@@ -1,0 +1,305 @@
+"""numpy-level face of the C ABI (include/bwt_b200.h): what tests, bench.py and the Erlang-shaped
+mirror modules (fm_index, bwa, sga, sw, worker_bwt) call.  Every method is a thin ctypes call; all
+compute happens in libbwt_b200.so on the GPU.  No fallback of any kind.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from ._lib import BwtError, BwtHit, BwtIndexInfo, BwtStats, NoSpace, check, lib
+
+HIT_DTYPE = np.dtype([("pos", "<i8"), ("s", "<i8"), ("cigar_off", "<i8"), ("d", "<i4"), ("score", "<i4"),
+                      ("status", "<i4"), ("cigar_len", "<i4")])
+assert HIT_DTYPE.itemsize == C.sizeof(BwtHit) == 40
+
+SEEDS, NO_SEEDS, TOO_MANY_SEEDS, SEARCH_CRASH = 0, 1, 2, 3
+READ_OK, READ_CRASH, READ_LIMIT = 0, 1, 2
+HIT_MATCH, HIT_NO_MATCH, HIT_WINDOW_OOR = 0, 1, 2
+
+
+def _u8(a) -> np.ndarray:
+    if isinstance(a, (bytes, bytearray, memoryview)):
+        return np.frombuffer(bytes(a), dtype=np.uint8)
+    return np.ascontiguousarray(a, dtype=np.uint8)
+
+
+def _ptr(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data
+
+
+def pack(seqs: Sequence[bytes]) -> Tuple[np.ndarray, np.ndarray]:
+    """list of byte strings -> (concatenated uint8, int64 offsets[n+1])"""
+    offs = np.zeros(len(seqs) + 1, dtype=np.int64)
+    if seqs:
+        offs[1:] = np.cumsum([len(s) for s in seqs])
+    data = np.frombuffer(b"".join(seqs), dtype=np.uint8) if seqs else np.zeros(0, np.uint8)
+    return np.ascontiguousarray(data), offs
+
+
+def device_count() -> int:
+    return lib().bwt_device_count()
+
+
+class Index:
+    """One FM-index partition + its padded .ref resident in HBM (opaque ``bwt_index``)."""
+
+    def __init__(self, handle):
+        self._h = C.c_void_p(handle)
+
+    # -- constructors ----------------------------------------------------------------------------
+    @classmethod
+    def open(cls, fm_path: str, ref_path: str, device: int = 0) -> "Index":
+        h = C.c_void_p()
+        check(lib().bwt_open(fm_path.encode(), ref_path.encode(), device, C.byref(h)))
+        return cls(h.value)
+
+    @classmethod
+    def from_arrays(cls, L, SA, pointers, shift: int, ref, device: int = 0) -> "Index":
+        L = _u8(L)
+        SA = np.ascontiguousarray(SA, dtype=np.uint32)
+        ptr = np.ascontiguousarray(pointers, dtype=np.uint32)
+        ref = _u8(ref)
+        h = C.c_void_p()
+        check(lib().bwt_open_arrays(L.ctypes.data, len(L), SA.ctypes.data, ptr.ctypes.data, int(shift), ref.ctypes.data,
+                                    len(ref), device, C.byref(h)))
+        return cls(h.value)
+
+    @classmethod
+    def build(cls, chunk, shift: int = 1, device: int = 0) -> "Index":
+        chunk = _u8(chunk)
+        h = C.c_void_p()
+        check(lib().bwt_build(chunk.ctypes.data, len(chunk), int(shift), device, C.byref(h)))
+        return cls(h.value)
+
+    @classmethod
+    def build_synthetic(cls, length: int, seed: int = 42, shift: int = 1, device: int = 0) -> "Index":
+        h = C.c_void_p()
+        check(lib().bwt_build_synthetic(int(length), int(seed), int(shift), device, C.byref(h)))
+        return cls(h.value)
+
+    # -- lifetime ---------------------------------------------------------------------------------
+    def close(self):
+        if self._h:
+            lib().bwt_close(self._h)
+            self._h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def handle(self):
+        return self._h
+
+    def info(self) -> BwtIndexInfo:
+        i = BwtIndexInfo()
+        check(lib().bwt_info(self._h, C.byref(i)))
+        return i
+
+    def export(self, want_L=True, want_SA=True, want_ref=True):
+        i = self.info()
+        L = np.empty(i.n_rows, np.uint8) if want_L else None
+        SA = np.empty(i.n_rows, np.uint32) if want_SA else None
+        ref = np.empty(i.ref_len, np.uint8) if want_ref else None
+        check(lib().bwt_export(self._h, _ptr(L), _ptr(SA), _ptr(ref)))
+        return L, SA, ref
+
+    def save(self, fm_path: str, ref_path: str):
+        check(lib().bwt_save(self._h, fm_path.encode(), ref_path.encode()))
+
+    # -- bwa:find_seeds/6 ---------------------------------------------------------------------------
+    def search(self, subs, offsets=None):
+        """-> (status int32[n], Sp uint32[n], Ep uint32[n], N int32[n])"""
+        if offsets is None:
+            subs, offsets = pack(subs)
+        subs = _u8(subs)
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        n = len(offsets) - 1
+        st = np.zeros(n, np.int32)
+        sp = np.zeros(n, np.uint32)
+        ep = np.zeros(n, np.uint32)
+        nm = np.zeros(n, np.int32)
+        check(lib().bwt_search_batch(self._h, subs.ctypes.data, offsets.ctypes.data, n, st.ctypes.data, sp.ctypes.data,
+                                     ep.ctypes.data, nm.ctypes.data))
+        return st, sp, ep, nm
+
+    def locate(self, first_row: int, count: int) -> np.ndarray:
+        out = np.zeros(count, np.uint32)
+        if count:
+            check(lib().bwt_locate(self._h, int(first_row), int(count), out.ctypes.data))
+        return out
+
+    # -- sga:sga/6 ------------------------------------------------------------------------------------
+    def sga(self, reads, offsets=None):
+        """-> (read_status int32[n], cl_offsets int64[n+1], S int64[total], D int32[total]); reference order."""
+        if offsets is None:
+            reads, offsets = pack(reads)
+        reads = _u8(reads)
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        n = len(offsets) - 1
+        st = np.zeros(n, np.int32)
+        clo = np.zeros(n + 1, np.int64)
+        cap = max(16, 4 * n)
+        total = C.c_int64()
+        while True:
+            S = np.zeros(cap, np.int64)
+            D = np.zeros(cap, np.int32)
+            rc = lib().bwt_sga_batch(self._h, reads.ctypes.data, offsets.ctypes.data, n, st.ctypes.data, clo.ctypes.data,
+                                     S.ctypes.data, D.ctypes.data, cap, C.byref(total))
+            if rc == -6:
+                cap = int(total.value) + 16
+                continue
+            check(rc)
+            return st, clo, S[:total.value].copy(), D[:total.value].copy()
+
+    # -- worker_bwt inner loop ------------------------------------------------------------------------
+    def align(self, reads, offsets=None):
+        """-> (read_status int32[n], hit_offsets int64[n+1], hits HIT_DTYPE[total], cigars bytes)"""
+        if offsets is None:
+            reads, offsets = pack(reads)
+        reads = _u8(reads)
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        n = len(offsets) - 1
+        st = np.zeros(n, np.int32)
+        ho = np.zeros(n + 1, np.int64)
+        hcap, ccap = max(16, 4 * n), max(256, 64 * n)
+        nh, nc = C.c_int64(), C.c_int64()
+        while True:
+            hits = np.zeros(hcap, HIT_DTYPE)
+            cig = np.zeros(ccap, np.uint8)
+            rc = lib().bwt_align_batch(self._h, reads.ctypes.data, offsets.ctypes.data, n, st.ctypes.data, ho.ctypes.data,
+                                       hits.ctypes.data, hcap, C.byref(nh), cig.ctypes.data, ccap, C.byref(nc))
+            if rc == -6:
+                hcap, ccap = int(nh.value) + 16, int(nc.value) + 16
+                continue
+            check(rc)
+            return st, ho, hits[:nh.value].copy(), cig[:nc.value].tobytes()
+
+
+def sw_batch(q, q_offsets, r, r_offsets, device: int = 0):
+    """sw:sw/2 for n pairs -> (status int32[n], score int32[n], [cigar bytes or None per pair])"""
+    q = _u8(q)
+    r = _u8(r)
+    qo = np.ascontiguousarray(q_offsets, dtype=np.int64)
+    ro = np.ascontiguousarray(r_offsets, dtype=np.int64)
+    n = len(qo) - 1
+    st = np.zeros(n, np.int32)
+    sc = np.zeros(n, np.int32)
+    co = np.zeros(n, np.int64)
+    cl = np.zeros(n, np.int32)
+    cap = max(256, 32 * n)
+    tot = C.c_int64()
+    while True:
+        cig = np.zeros(cap, np.uint8)
+        rc = lib().bwt_sw_batch(device, _ptr(q) if len(q) else None, qo.ctypes.data, _ptr(r) if len(r) else None,
+                                ro.ctypes.data, n, st.ctypes.data, sc.ctypes.data, co.ctypes.data, cl.ctypes.data,
+                                cig.ctypes.data, cap, C.byref(tot))
+        if rc == -6:
+            cap = int(tot.value) + 16
+            continue
+        check(rc)
+        raw = cig.tobytes()
+        cigars = [raw[co[k]:co[k] + cl[k]] if st[k] == HIT_MATCH else None for k in range(n)]
+        return st, sc, cigars
+
+
+class Batch:
+    """Resident batch: upload / run / download as separate calls (``bwt_batch``)."""
+
+    def __init__(self, index: Index, max_reads: int, max_read_bytes: int):
+        self.index = index
+        self._b = C.c_void_p()
+        check(lib().bwt_batch_create(index.handle, int(max_reads), int(max_read_bytes), C.byref(self._b)))
+
+    def close(self):
+        if self._b:
+            lib().bwt_batch_destroy(self._b)
+            self._b = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def upload(self, reads: np.ndarray, offsets: np.ndarray):
+        self._n = len(offsets) - 1
+        check(lib().bwt_batch_upload(self._b, reads.ctypes.data, offsets.ctypes.data, self._n))
+
+    def upload_ptr(self, reads_ptr: int, offsets_ptr: int, n: int):
+        self._n = n
+        check(lib().bwt_batch_upload(self._b, reads_ptr, offsets_ptr, n))
+
+    def run(self):
+        check(lib().bwt_batch_run(self._b))
+
+    def result_size(self) -> Tuple[int, int]:
+        a, b = C.c_int64(), C.c_int64()
+        check(lib().bwt_batch_result_size(self._b, C.byref(a), C.byref(b)))
+        return int(a.value), int(b.value)
+
+    def download(self, read_status=None, hit_offsets=None, hits=None, cigars=None):
+        nh, nc = self.result_size()
+        n = self._n
+        if read_status is None:
+            read_status = np.zeros(n, np.int32)
+        if hit_offsets is None:
+            hit_offsets = np.zeros(n + 1, np.int64)
+        if hits is None:
+            hits = np.zeros(max(nh, 1), HIT_DTYPE)
+        if cigars is None:
+            cigars = np.zeros(max(nc, 1), np.uint8)
+        check(lib().bwt_batch_download(self._b, read_status.ctypes.data, hit_offsets.ctypes.data, hits.ctypes.data,
+                                       len(hits), cigars.ctypes.data, len(cigars)))
+        return read_status, hit_offsets, hits[:nh], cigars[:nc]
+
+    def download_ptr(self, status_ptr, offs_ptr, hits_ptr, hits_cap, cig_ptr, cig_cap):
+        check(lib().bwt_batch_download(self._b, status_ptr, offs_ptr, hits_ptr, hits_cap, cig_ptr, cig_cap))
+
+    def stats(self) -> BwtStats:
+        s = BwtStats()
+        check(lib().bwt_batch_stats(self._b, C.byref(s)))
+        return s
+
+    def device_result(self):
+        a, b, c = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        check(lib().bwt_batch_device_result(self._b, C.byref(a), C.byref(b), C.byref(c)))
+        return a.value, b.value, c.value
+
+
+def search_resident(index: Index, subs: np.ndarray, sub_len: int, repeats: int = 1):
+    """-> (ms for all repeats, LF steps per repeat, LF steps per repeat not served by the 8-mer table)"""
+    subs = _u8(subs)
+    n = len(subs) // sub_len
+    ms = C.c_float()
+    lf, hbm = C.c_uint64(), C.c_uint64()
+    check(lib().bwt_search_resident(index.handle, subs.ctypes.data, n, sub_len, repeats, C.byref(ms), C.byref(lf),
+                                    C.byref(hbm)))
+    return float(ms.value), int(lf.value), int(hbm.value)
+
+
+def peak_gather_gbs(device: int = 0, nbytes: int = 8 << 30) -> float:
+    g = C.c_double()
+    check(lib().bwt_peak_gather_gbs(device, int(nbytes), C.byref(g)))
+    return float(g.value)
+
+
+def peak_dpx_gops(device: int = 0) -> float:
+    g = C.c_double()
+    check(lib().bwt_peak_dpx_gops(device, C.byref(g)))
+    return float(g.value)
+
+
+__all__ = ["Index", "Batch", "BwtError", "NoSpace", "pack", "sw_batch", "search_resident", "peak_gather_gbs",
+           "peak_dpx_gops", "device_count", "HIT_DTYPE"]

@@ -371,7 +371,7 @@ static int run_core(bwt_batch *b, bool with_sw) {
             windows_kernel<<<(ncl + 255) / 256, 256, 0, b->stream>>>(b->d_clusters, ncl, b->d_offs, b->ix->dv.ref_len_padded,
                                                                      b->sw.d_desc, b->sw.d_out);
             b->stats.launches += 1;
-            CU_TRY(cudaGetLastError());
+            K_CHECK(b->stream, "windows_kernel");
             BWT_TRY(sw_stage_run(b->sw, b->d_reads, b->ix->dv.ref, ncl, b->max_read_len, b->stream));
         } else {
             memset(b->sw.h_ctr, 0, sizeof(SwCounters));
@@ -668,6 +668,8 @@ extern "C" int bwt_sw_batch(int device, const uint8_t *q, const int64_t *q_offse
         cudaMemcpy(d_qo, qo.data(), (size_t)(n + 1) * 8, cudaMemcpyHostToDevice);
         cudaMemcpy(d_ro, ro.data(), (size_t)(n + 1) * 8, cudaMemcpyHostToDevice);
         desc_from_offsets_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(d_qo, d_ro, (uint32_t)n, sw.d_desc, sw.d_out);
+        { cudaError_t e0 = cudaGetLastError(); if (e0 == cudaSuccess && bwt_debug_sync()) e0 = cudaStreamSynchronize(stream);
+          if (e0 != cudaSuccess) { bwt_set_error("desc_from_offsets_kernel: %s", cudaGetErrorString(e0)); st = BWT_ERR_CUDA; break; } }
         if ((st = sw_stage_run(sw, d_q, d_r, (uint32_t)n, max_lq, stream)) != BWT_OK) break;
         cudaMemsetAsync(d_off + n, 0, 4, stream);
         sw_pairs_emit_count_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(sw.d_out, (uint32_t)n, d_off);

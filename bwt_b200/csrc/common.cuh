@@ -29,6 +29,19 @@ void bwt_set_error(const char *fmt, ...);
         }                                                                                             \
     } while (0)
 
+// After a kernel launch: catches launch errors; with BWT_DEBUG_SYNC=1 in the environment it also waits for the
+// kernel so that a device fault is reported with the name of the kernel that raised it.
+bool bwt_debug_sync();
+#define K_CHECK(stream, name)                                                                         \
+    do {                                                                                              \
+        cudaError_t _e = cudaGetLastError();                                                          \
+        if (_e == cudaSuccess && bwt_debug_sync()) _e = cudaStreamSynchronize(stream);                \
+        if (_e != cudaSuccess) {                                                                      \
+            bwt_set_error("%s:%d: kernel %s -> %s", __FILE__, __LINE__, name, cudaGetErrorString(_e)); \
+            return BWT_ERR_CUDA;                                                                      \
+        }                                                                                             \
+    } while (0)
+
 #define BWT_TRY(expr)                 \
     do {                              \
         int _s = (expr);              \

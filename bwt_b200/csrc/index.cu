@@ -24,6 +24,11 @@ void bwt_set_error(const char *fmt, ...) {
     va_end(ap);
 }
 
+bool bwt_debug_sync() {
+    static const bool on = [] { const char *e = getenv("BWT_DEBUG_SYNC"); return e && *e && *e != '0'; }();
+    return on;
+}
+
 extern "C" const char *bwt_last_error(void) { return g_err; }
 extern "C" int bwt_abi_version(void) { return BWT_B200_ABI_VERSION; }
 

@@ -77,7 +77,10 @@ __device__ __forceinline__ void first_interval(const DevIndex &ix, int c, uint32
 }
 
 // bwa:find_seeds/6 on q[0..len), len >= 1.  use_table: consult the 8-mer table (false while building it).
-__device__ __forceinline__ SearchRes search_sub(const DevIndex &ix, const uint8_t *q, int len, bool use_table) {
+// exact_stop: when the table says the walk stopped before 8 characters (=> no_seeds whatever the interval), redo
+// the walk so that the reported Sp/Ep/N are the reference's too (only the explicit search API needs them).
+__device__ __forceinline__ SearchRes search_sub(const DevIndex &ix, const uint8_t *q, int len, bool use_table,
+                                                bool exact_stop = false) {
     SearchRes R;
     R.table = 0;
     uint8_t h = q[len - 1];
@@ -98,12 +101,15 @@ __device__ __forceinline__ SearchRes search_sub(const DevIndex &ix, const uint8_
         }
         if (ok) {
             uint2 e = __ldg(ix.kmer + idx);
-            R.table = 1;
-            if (e.x == 0) {                       // stopped before 8 characters => no_seeds (fmi.erl:89-91)
+            if (e.x == 0 && !exact_stop) {        // stopped before 8 characters => no_seeds (fmi.erl:89-91)
+                R.table = 1;
                 R.sp = R.ep = 0; R.n = (int)e.y; R.status = BWT_NO_SEEDS; return R;
             }
-            sp = e.x; ep = e.y; n = BWT_MIN_LEN; k = len - 1 - BWT_MIN_LEN;
-            have = true;
+            if (e.x != 0) {
+                R.table = 1;
+                sp = e.x; ep = e.y; n = BWT_MIN_LEN; k = len - 1 - BWT_MIN_LEN;
+                have = true;
+            }
         }
     }
     if (!have) first_interval(ix, c, sp, ep);

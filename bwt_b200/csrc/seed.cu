@@ -43,7 +43,7 @@ __global__ void __launch_bounds__(256) search_kernel(DevIndex ix, const uint8_t 
         else { q = subs + offs[i]; len = (int)(offs[i + 1] - offs[i]); }
         SearchRes r;
         if (len <= 0) { r.sp = r.ep = 0; r.n = 0; r.status = BWT_SEARCH_CRASH; r.table = 0; }   // hd([]) badmatch
-        else r = search_sub(ix, q, len, true);
+        else r = search_sub(ix, q, len, true, true);
         if (status) status[i] = r.status;
         if (sp) sp[i] = r.sp;
         if (ep) ep[i] = r.ep;

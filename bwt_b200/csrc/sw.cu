@@ -16,12 +16,27 @@
 //     that a warp's accesses are conflict free.
 //   * the ten 3-bit direction codes of one column of a strip are one 32-bit word, written to a per-thread
 //     slice of an HBM/L2 scratch ([word][thread], coalesced) and read back by the traceback.
-//   * sigma comes from a per-row 4-byte profile selected with one PRMT (__byte_perm) by the window base.
+//   * sigma comes from a per-row 4-byte profile selected with one PRMT (prmt.b32, sign-replicate mode) by the window base.
 // General path (any byte, e.g. 'N' = 1.6 or IUPAC codes in the window, or sizes beyond the fast tier):
 //   IEEE doubles added in the reference's order, one thread per pair, rows in HBM scratch.
 #include "sw.cuh"
 
+// -DBWT_KDEBUG builds print and bail out on a violated kernel invariant instead of faulting (debug only).
+#ifdef BWT_KDEBUG
+#define KD_CHECK(cond, ...) do { if (!(cond)) { printf("KDEBUG %s:%d " #cond " ", __FILE__, __LINE__); printf(__VA_ARGS__); printf("\n"); return; } } while (0)
+#else
+#define KD_CHECK(cond, ...) do { } while (0)
+#endif
+
 namespace {
+
+// PRMT with the sign-replicate bit of the selector nibbles honoured (the __byte_perm intrinsic masks it off):
+// result = byte (sel & 3) of a, sign-extended to 32 bits, for sel = b * 0x1111 + 0x8880.
+__device__ __forceinline__ int prmt_sext_byte(uint32_t a, uint32_t sel) {
+    int r;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(0u), "r"(sel));
+    return r;
+}
 
 __device__ __forceinline__ bool is_acgt(uint8_t c) { return c == 'A' || c == 'C' || c == 'G' || c == 'T'; }
 
@@ -92,7 +107,7 @@ __device__ __forceinline__ void sw_strip(int16_t *__restrict__ row, const uint32
         int K = 0;
 #pragma unroll
         for (int r = 0; r < SW_R; r++) {
-            const int s = (int)__byte_perm(prof[r], 0u, sel);          // 8*sigma + 4
+            const int s = prmt_sext_byte(prof[r], sel);                  // 8*sigma + 4
             const int x = __viaddmax_s32(lfv[r], -15, mdiag + s);      // max(left, diag)
             K = __viaddmax_s32(uup, -14, x);                           // max(up, .)
             if (MASKED) K = (r >= rmin) ? K : 0;
@@ -120,6 +135,11 @@ __global__ void __launch_bounds__(SW_BLOCK) sw_fast_kernel(SwFastParams p) {
     uint32_t *dirs = p.dirs + (size_t)blockIdx.x * p.max_strips * p.cap_cols * B + tid;  // dirs[(s*cap+j)*B]
     const uint32_t n_list = p.ctr->n_fast;
     unsigned long long calls = 0, cells = 0;
+#ifdef BWT_KDEBUG
+    if (tid == 0 && blockIdx.x == 0)
+        printf("KDEBUG sw_fast: n_list=%u cap_cols=%d max_strips=%d dirs=%p cig=%p cig_cap=%u desc=%p list=%p out=%p q=%p r=%p\n", n_list,
+               p.cap_cols, p.max_strips, p.dirs, p.cig, p.cig_cap, p.desc, p.list, p.out, p.qbase, p.rbase);
+#endif
 
     for (uint32_t it = blockIdx.x * B + tid; it < n_list; it += gridDim.x * B) {
         const uint32_t cand = p.list[it];
@@ -127,6 +147,7 @@ __global__ void __launch_bounds__(SW_BLOCK) sw_fast_kernel(SwFastParams p) {
         const uint8_t *q = p.qbase + d.q_off;
         const uint8_t *w = p.rbase + d.r_off;
         const int lq = d.lq, lr = d.lr;
+        KD_CHECK(lq >= 1 && lr >= 1 && lr + 1 <= p.cap_cols && (lq + R - 1) / R <= p.max_strips, "cand=%u lq=%d lr=%d", cand, lq, lr);
         // stage the window as 2-bit codes ((c>>1)&3: A0 C1 T2 G3) and validate both strings
         bool plain = true;
         for (int j0 = 0; j0 < lr; j0 += 16) {
@@ -177,12 +198,13 @@ __global__ void __launch_bounds__(SW_BLOCK) sw_fast_kernel(SwFastParams p) {
         if (failed) { p.out[cand] = o; continue; }
         const int vmax = mx[R - 1] >> 3;
         int j = 0;
-        while ((row[j * B] >> 3) != vmax) j++;                    // leftmost maximum of the last row (sw.erl:110-112)
+        while ((row[j * B] >> 3) != vmax) { j++; KD_CHECK(j <= lr, "cand=%u vmax=%d lq=%d lr=%d", cand, vmax, lq, lr); }   // leftmost maximum of the last row (sw.erl:110-112)
         // traceback (sw.erl:116-160); runs are pushed newest-first into the (now free) shared row
         uint16_t *runs = reinterpret_cast<uint16_t *>(row);
         int i = lq, nr = 0, cur = -1, len = 0;
         bool ovf = false;
         while (i > 0) {
+            KD_CHECK(j >= 0 && j <= lr && i <= lq, "traceback cand=%u i=%d j=%d", cand, i, j);
             int op;                                               // 0 = M (up_left), 1 = D (left), 2 = I (up)
             if (j == 0) op = 2;
             else {
@@ -418,13 +440,14 @@ int sw_stage_run(SwStage &st, const uint8_t *d_qbase, const uint8_t *d_rbase, ui
         CU_TRY(cudaMemsetAsync(st.d_ctr, 0, sizeof(SwCounters), stream));
         sw_classify_kernel<<<(n + 255) / 256, 256, 0, stream>>>(st.d_desc, st.d_out, n, cap_cols, st.d_list_fast,
                                                                 st.d_list_gen, st.d_ctr);
+        K_CHECK(stream, "sw_classify_kernel");
         SwFastParams p;
         p.qbase = d_qbase; p.rbase = d_rbase; p.desc = st.d_desc; p.list = st.d_list_fast; p.out = st.d_out;
         p.list_gen = st.d_list_gen; p.ctr = st.d_ctr; p.cig = st.d_cig_tmp; p.cig_cap = st.cig_cap;
         p.dirs = st.d_dirs; p.cap_cols = cap_cols; p.max_strips = max_strips;
         sw_fast_kernel<<<grid, SW_BLOCK, smem, stream>>>(p);
         st.launches += 2;
-        CU_TRY(cudaGetLastError());
+        K_CHECK(stream, "sw_fast_kernel");
         CU_TRY(cudaMemcpyAsync(st.h_ctr, st.d_ctr, sizeof(SwCounters), cudaMemcpyDeviceToHost, stream));
         CU_TRY(cudaStreamSynchronize(stream));
         uint32_t ng = st.h_ctr->n_general;
@@ -462,7 +485,7 @@ int sw_stage_run(SwStage &st, const uint8_t *d_qbase, const uint8_t *d_rbase, ui
                                                                      st.d_gen_off, st.d_gen_scratch, st.d_out, st.d_ctr,
                                                                      st.d_cig_tmp, st.cig_cap);
                 st.launches += 1;
-                CU_TRY(cudaGetLastError());
+                K_CHECK(stream, "sw_general_kernel");
                 CU_TRY(cudaStreamSynchronize(stream));
                 first = last;
             }

@@ -1,0 +1,343 @@
+#!/usr/bin/env python
+"""bench.py -- aligned reads/s of the worker_bwt hot path (sga -> windows -> sw -> hit tuples) on B200.
+
+  python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path (one process per GPU under torchrun)
+  python bench.py --impl reference --gpus N --steps K ...  # the CPU port of the reference (oracle/), all host cores
+
+Workload (BASELINE.json configs[2], the largest single-GPU configuration): one un-chunked FM index of
+a 3,137,454,466 bp synthetic reference (the bp total of bwt_files/human_g1k_v37_decoy.fasta.index, i.i.d. ACGT),
+built on the device; 10 M synthetic 100 bp forward-strand reads per GPU with 1 % substitutions.  A step = one pass of
+the whole path over all of the rank's reads.  At N > 1 the index is replicated and every rank gets its own 10 M reads
+(read sharding, no data-path collective): weak scaling.
+
+  value : reads/s with the reads already resident in HBM (bwt_batch_run only), CUDA-event time, max over ranks
+  e2e   : reads/s through the C ABI with HOST buffers: pinned reads -> H2D -> run -> D2H of the hit tuples
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+REF_BP = 3_137_454_466
+METRIC = "aligned reads/sec"
+UNIT = "reads/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--ref-bp", type=int, default=REF_BP)
+    ap.add_argument("--reads", type=int, default=10_000_000, help="reads per GPU per step")
+    ap.add_argument("--read-len", type=int, default=100)
+    ap.add_argument("--sub-rate", type=float, default=0.01)
+    ap.add_argument("--seed", type=int, default=42)
+    ap.add_argument("--cpu-seconds", type=float, default=15.0, help="CPU work of the cpu_baseline leg (0 = skip)")
+    ap.add_argument("--ref-step-reads", type=int, default=200_000, help="reads per step of --impl reference")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def workload_name(a):
+    return ("synthetic %.3f Gbp reference (human_g1k_v37_decoy bp total), un-chunked FM index; %d synthetic %d bp reads "
+            "per GPU, %.1f %% substitutions; sga + sw + hit tuples" % (a.ref_bp / 1e9, a.reads, a.read_len, 100 * a.sub_rate))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (profiling recipe's clocks line)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu):
+        self.gpu = gpu
+        self.rows = []
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                       "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.p = None
+
+    def _read(self):
+        for ln in self.p.stdout:
+            self.rows.append([x.strip() for x in ln.split(",")])
+
+    def stop(self):
+        if not self.p:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.t.join(timeout=2)
+        sm, mx, reasons, pw = [], [], set(), []
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2])); pw.append(float(r[3]))
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (copy bandwidth, of measured)"
+    return 6650.0, "B200_PROFILING.md fallback 6.65 TB/s (of fallback)"
+
+
+def load_traffic(kernel):
+    """per-launch DRAM bytes of the dominant kernel from the committed ncu --set full capture of this same workload"""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            t = json.load(f)
+        e = t.get(kernel)
+        if e:
+            return e
+    return None
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def cpu_port_setup(ix, a):
+    """Index columns back on the host for the CPU port (oracle/bwt_oracle.c, closed-form LF: same results as the literal scan)."""
+    from oracle.c_oracle import COracle
+    t0 = time.time()
+    L, SA, ref = ix.export()
+    info = ix.info()
+    orc = COracle(L, SA, tuple(info.pointers), int(info.shift), ref, mode=1)
+    return orc, time.time() - t0
+
+
+def cpu_port_run(orc, reads, offs, lo, hi, threads):
+    """-> seconds for reads [lo, hi)"""
+    sub_offs = np.ascontiguousarray(offs[lo:hi + 1])
+    t0 = time.perf_counter()
+    ncand, cand, st = orc.align_batch(reads, sub_offs, nthreads=threads, with_sw=True, cap_per_read=16)
+    return time.perf_counter() - t0, st
+
+
+def main():
+    a = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if a.impl == "reference" and rank != 0:
+        return 0
+
+    from bwt_b200 import api          # raises if libbwt_b200.so is missing: no CPU fallback
+
+    import torch
+    dist = None
+    if world > 1 and a.impl == "ours":
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = local if a.impl == "ours" else 0
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # -- setup (untimed): index on the device, reads in pinned host memory
+    t0 = time.time()
+    ix = api.Index.build_synthetic(a.ref_bp, seed=a.seed, shift=1, device=dev)
+    build_s = time.time() - t0
+    n = a.reads
+    reads_t = torch.empty(n * a.read_len, dtype=torch.uint8).pin_memory()
+    reads = reads_t.numpy()
+    api.sample_reads(ix, n, a.read_len, seed=a.seed + 1000 * (rank + 1), sub_rate=a.sub_rate, out=reads)
+    offs_t = (torch.arange(n + 1, dtype=torch.int64) * a.read_len).pin_memory()
+    offs = offs_t.numpy()
+    threads = os.cpu_count() or 1
+
+    if a.impl == "reference":
+        return run_reference(a, ix, reads, offs, threads)
+
+    batch = api.Batch(ix, n, n * a.read_len)
+    batch.upload(reads, offs)
+
+    # -- resident: warm-up, then K timed steps (CUDA events inside the library, on the batch's own stream)
+    for _ in range(max(a.warmup, 0)):
+        batch.run()
+    clocks = ClockSampler(dev)
+    barrier()
+    clocks.start()
+    w0 = time.perf_counter()
+    ev_ms = 0.0
+    agg = dict(lf=0, hbm_lf=0, located=0, searches=0, clusters=0, sw_calls=0, cells=0, general=0, launches=0,
+               ms_sga=0.0, ms_sw=0.0, ms_seed=0.0, ms_swstage=0.0, ms_emit=0.0)
+    for _ in range(a.steps):
+        batch.run()
+        s = batch.stats()
+        ev_ms += s.ms_total
+        agg["lf"] += s.lf_steps; agg["hbm_lf"] += s.hbm_lf_steps; agg["located"] += s.located_rows
+        agg["searches"] += s.searches; agg["clusters"] += s.clusters; agg["sw_calls"] += s.sw_calls
+        agg["cells"] += s.sw_cells; agg["general"] += s.sw_general; agg["launches"] += s.launches
+        agg["ms_sga"] += s.ms_sga_kernel; agg["ms_sw"] += s.ms_sw_kernel
+        agg["ms_seed"] += s.ms_seed; agg["ms_swstage"] += s.ms_sw; agg["ms_emit"] += s.ms_emit
+    barrier()
+    wall_ms = (time.perf_counter() - w0) * 1e3
+    clk = clocks.stop()
+    n_hits, cig_bytes = batch.result_size()
+
+    # -- end to end through the C ABI: pinned host reads -> H2D -> run -> D2H of the hit tuples, every step
+    e2e = None
+    if not a.no_e2e:
+        st_t = torch.empty(n, dtype=torch.int32).pin_memory()
+        ho_t = torch.empty(n + 1, dtype=torch.int64).pin_memory()
+        hits_t = torch.empty((n_hits + n_hits // 8 + 1024) * 40, dtype=torch.uint8).pin_memory()
+        cig_t = torch.empty(cig_bytes + cig_bytes // 8 + 4096, dtype=torch.uint8).pin_memory()
+
+        def e2e_step():
+            batch.upload_ptr(reads_t.data_ptr(), offs_t.data_ptr(), n)
+            batch.run()
+            batch.download_ptr(st_t.data_ptr(), ho_t.data_ptr(), hits_t.data_ptr(), hits_t.numel() // 40, cig_t.data_ptr(),
+                               cig_t.numel())
+        e2e_step()
+        barrier()
+        e0 = time.perf_counter()
+        for _ in range(a.steps):
+            e2e_step()
+        barrier()
+        e2e_s = time.perf_counter() - e0
+        nh, nc = batch.result_size()
+        h2d = n * a.read_len + (n + 1) * 8
+        d2h = n * 4 + (n + 1) * 8 + nh * 40 + nc
+        e2e = [e2e_s, h2d, d2h]
+
+    # -- max over ranks
+    t_ev, t_wall = ev_ms, wall_ms
+    if dist is not None:
+        t = torch.tensor([ev_ms, wall_ms, e2e[0] if e2e else 0.0], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t_ev, t_wall = float(t[0]), float(t[1])
+        if e2e:
+            e2e[0] = float(t[2])
+        cnt = torch.tensor([agg["launches"]], dtype=torch.int64, device="cuda")
+        dist.all_reduce(cnt)
+        total_launches = int(cnt[0])
+    else:
+        total_launches = agg["launches"]
+
+    if rank == 0:
+        K = a.steps
+        value = world * n * K / (t_ev * 1e-3)
+        hbm_peak, peak_src = load_peaks()
+        # dominant kernel and its algorithmic traffic (DESIGN.md "units"): per HBM-served LF step two 32-byte Occ
+        # blocks, per located row 4 bytes of SA, per read its bases once
+        sga_bytes = 64.0 * agg["hbm_lf"] + 4.0 * agg["located"] + float(n * a.read_len * K)
+        sga_gbs = sga_bytes / (agg["ms_sga"] * 1e-3) / 1e9 if agg["ms_sga"] > 0 else 0.0
+        dominant = "sga_kernel" if agg["ms_sga"] >= agg["ms_sw"] else "sw_fast_kernel"
+        tr = load_traffic("sga_kernel")
+        roof = {"kernel": "sga_kernel", "bound": "hbm", "achieved": round(sga_gbs, 1), "peak": hbm_peak, "unit": "GB/s",
+                "frac": round(sga_gbs / hbm_peak, 4), "traffic": tr["dram_bytes_per_launch"] if tr else None,
+                "peak_source": peak_src, "algorithmic_bytes_per_launch": sga_bytes / K,
+                "ms_per_launch": agg["ms_sga"] / K, "dominant_kernel": dominant,
+                "share_of_step": {"sga_kernel": round(agg["ms_sga"] / t_ev, 3), "sw_fast_kernel": round(agg["ms_sw"] / t_ev, 3)}}
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": a.warmup,
+            "ms_per_step": t_ev / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32",
+            "data": "synthetic",
+            "config": {"workload": workload_name(a), "reads_per_gpu_per_step": n, "read_len": a.read_len, "ref_bp": a.ref_bp,
+                       "parallelism": "read sharding, index replicated x%d" % world,
+                       "l2": "inputs larger than L2 (index %.1f GB, reads %.2f GB per step); no flush needed" % (
+                           ix.info().device_bytes / 1e9, n * a.read_len / 1e9),
+                       "index_build_s": round(build_s, 2), "timer": "CUDA events on the batch stream, max over ranks",
+                       "wall_ms_per_step": t_wall / K},
+            "clocks": clk, "gpu_launches": total_launches,
+            "roofline": roof,
+            "work": {"lf_steps_per_s": agg["lf"] / (agg["ms_sga"] * 1e-3) if agg["ms_sga"] else None,
+                     "hbm_lf_steps_per_read": agg["hbm_lf"] / (n * K), "lf_steps_per_read": agg["lf"] / (n * K),
+                     "located_rows_per_read": agg["located"] / (n * K), "clusters_per_read": agg["clusters"] / (n * K),
+                     "sw_calls_per_read": agg["sw_calls"] / (n * K), "cells_per_read": agg["cells"] / (n * K),
+                     "sw_gcups": agg["cells"] / (agg["ms_sw"] * 1e-3) / 1e9 if agg["ms_sw"] else None,
+                     "sw_general_pairs": agg["general"], "hits_per_step": n_hits,
+                     "ms_stage": {"seed": agg["ms_seed"] / K, "sw": agg["ms_swstage"] / K, "emit": agg["ms_emit"] / K}},
+        }
+        if e2e:
+            out["e2e"] = {"value": world * n * K / e2e[0], "unit": UNIT, "h2d_bytes_per_step": e2e[1], "d2h_bytes_per_step": e2e[2],
+                          "timer": "wall clock around upload+run+download, barrier+synchronize both sides, max over ranks"}
+        if world == 1 and a.cpu_seconds > 0:
+            out["cpu_baseline"] = cpu_baseline(a, ix, reads, offs, threads)
+        print(json.dumps(out), flush=True)
+    batch.close()
+    ix.close()
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def cpu_baseline(a, ix, reads, offs, threads):
+    orc, setup_s = cpu_port_setup(ix, a)
+    probe = min(a.reads, 20_000 * threads)
+    t, _ = cpu_port_run(orc, reads, offs, 0, probe, threads)
+    rate = probe / t
+    m = int(min(a.reads, max(probe, rate * a.cpu_seconds)))
+    t, st = cpu_port_run(orc, reads, offs, 0, m, threads)
+    orc.close()
+    return {"value": m / t, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": "first %d of the step's %d reads, same index (exported from the device), %.1f s of CPU work on %d threads; "
+                      "C port of the reference's algorithm (oracle/bwt_oracle.c), not BEAM" % (m, a.reads, t, threads),
+            "lf_steps_per_read": st.lf_steps / m, "cells_per_read": st.cells / m, "setup_s": round(setup_s, 1)}
+
+
+def run_reference(a, ix, reads, offs, threads):
+    """--impl reference: the reference's CPU algorithm (C port in oracle/; the Erlang original needs OTP, absent here) on
+    all host threads; each step = a bounded sample of the same workload."""
+    orc, setup_s = cpu_port_setup(ix, a)
+    ix.close()
+    m = min(a.ref_step_reads, a.reads)
+    pos = 0
+
+    def step():
+        nonlocal pos
+        if pos + m > a.reads:
+            pos = 0
+        t, st = cpu_port_run(orc, reads, offs, pos, pos + m, threads)
+        pos += m
+        return t
+    for _ in range(a.warmup):
+        step()
+    tot = 0.0
+    for _ in range(a.steps):
+        tot += step()
+    v = m * a.steps / tot
+    sample = "each step = %d reads of the %d-read workload, %d threads; C port of the reference (oracle/bwt_oracle.c)" % (m, a.reads, threads)
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
+        "ms_per_step": tot / a.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32",
+        "data": "synthetic", "config": {"workload": workload_name(a), "sample": sample, "index_export_s": round(setup_s, 1)},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}), flush=True)
+    orc.close()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

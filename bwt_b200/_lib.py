@@ -34,11 +34,12 @@ class BwtIndexInfo(C.Structure):
 
 
 class BwtStats(C.Structure):
-    _fields_ = [("reads", C.c_uint64), ("searches", C.c_uint64), ("lf_steps", C.c_uint64),
+    _fields_ = [("reads", C.c_uint64), ("searches", C.c_uint64), ("lf_steps", C.c_uint64), ("hbm_lf_steps", C.c_uint64),
                 ("located_rows", C.c_uint64), ("clusters", C.c_uint64), ("sw_calls", C.c_uint64),
                 ("sw_cells", C.c_uint64), ("sw_general", C.c_uint64),
                 ("ms_total", C.c_float), ("ms_seed", C.c_float), ("ms_sw", C.c_float), ("ms_emit", C.c_float),
-                ("ms_h2d", C.c_float), ("ms_d2h", C.c_float), ("launches", C.c_uint32), ("reserved", C.c_uint32)]
+                ("ms_h2d", C.c_float), ("ms_d2h", C.c_float), ("ms_sga_kernel", C.c_float), ("ms_sw_kernel", C.c_float),
+                ("launches", C.c_uint32), ("reserved", C.c_uint32)]
 
 
 # every symbol include/bwt_b200.h declares: (restype, argtypes)
@@ -71,6 +72,7 @@ SIGNATURES = {
     "bwt_batch_device_result": (C.c_int, [P, C.POINTER(P), C.POINTER(P), C.POINTER(P)]),
     "bwt_search_resident": (C.c_int, [P, P, C.c_int64, C.c_int32, C.c_int32, C.POINTER(C.c_float),
                                       C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    "bwt_sample_reads": (C.c_int, [P, C.c_int64, C.c_int32, C.c_uint64, C.c_double, P, P]),
     "bwt_peak_gather_gbs": (C.c_int, [C.c_int, C.c_uint64, C.POINTER(C.c_double)]),
     "bwt_peak_dpx_gops": (C.c_int, [C.c_int, C.POINTER(C.c_double)]),
 }

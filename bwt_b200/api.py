@@ -278,6 +278,17 @@ class Batch:
         return a.value, b.value, c.value
 
 
+def sample_reads(index: Index, n: int, read_len: int, seed: int = 42, sub_rate: float = 0.01, out: Optional[np.ndarray] = None,
+                 want_starts: bool = False):
+    """Synthetic fixed-length reads sampled on the device from the index's .ref -> (uint8[n*read_len], offsets, starts|None)"""
+    if out is None:
+        out = np.empty(n * read_len, np.uint8)
+    starts = np.empty(n, np.int64) if want_starts else None
+    check(lib().bwt_sample_reads(index.handle, int(n), int(read_len), int(seed), float(sub_rate), out.ctypes.data, _ptr(starts)))
+    offs = np.arange(n + 1, dtype=np.int64) * read_len
+    return out, offs, starts
+
+
 def search_resident(index: Index, subs: np.ndarray, sub_len: int, repeats: int = 1):
     """-> (ms for all repeats, LF steps per repeat, LF steps per repeat not served by the 8-mer table)"""
     subs = _u8(subs)
@@ -301,5 +312,5 @@ def peak_dpx_gops(device: int = 0) -> float:
     return float(g.value)
 
 
-__all__ = ["Index", "Batch", "BwtError", "NoSpace", "pack", "sw_batch", "search_resident", "peak_gather_gbs",
+__all__ = ["Index", "Batch", "sample_reads", "BwtError", "NoSpace", "pack", "sw_batch", "search_resident", "peak_gather_gbs",
            "peak_dpx_gops", "device_count", "HIT_DTYPE"]

@@ -168,7 +168,7 @@ struct bwt_batch {
     size_t cigars_cap = 0;
     int64_t n_hits = 0, cigar_bytes = 0;
     bool has_result = false;
-    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     bwt_stats stats{};
 };
 
@@ -289,12 +289,15 @@ static int run_seed_stage(bwt_batch *b) {
     const DevIndex &ix = b->ix->dv;
     for (int attempt = 0; attempt < 6; attempt++) {
         CU_TRY(cudaMemsetAsync(b->d_ctr, 0, sizeof(SeedCounters), b->stream));
+        CU_TRY(cudaEventRecord(b->ev[6], b->stream));
         BWT_TRY(launch_sga(ix, b->d_reads, b->d_offs, b->n, b->max_read_len, b->d_read_status, b->d_ncl, b->d_cl_base,
                            b->d_clusters, (uint32_t)std::min<size_t>(b->cl_cap, 0xFFFFFFF0u), b->d_slow, b->slow_cap,
                            b->d_ctr, b->stream));
+        CU_TRY(cudaEventRecord(b->ev[7], b->stream));
         b->stats.launches += 1;
         CU_TRY(cudaMemcpyAsync(b->h_ctr, b->d_ctr, sizeof(SeedCounters), cudaMemcpyDeviceToHost, b->stream));
         CU_TRY(cudaStreamSynchronize(b->stream));
+        cudaEventElapsedTime(&b->stats.ms_sga_kernel, b->ev[6], b->ev[7]);
         uint32_t n_slow = b->h_ctr->n_slow;
         if (n_slow > b->slow_cap) {          // cannot happen with slow_cap = max_reads unless capped at 2^20
             cudaFree(b->d_slow); b->d_slow = nullptr;
@@ -390,7 +393,9 @@ static int run_core(bwt_batch *b, bool with_sw) {
     }
     bwt_stats &s = b->stats;
     s.reads = (uint64_t)b->n;
-    s.searches = b->h_ctr->searches; s.lf_steps = b->h_ctr->lf_steps; s.located_rows = b->h_ctr->located;
+    s.searches = b->h_ctr->searches; s.lf_steps = b->h_ctr->lf_steps; s.hbm_lf_steps = b->h_ctr->hbm_lf_steps;
+    s.located_rows = b->h_ctr->located;
+    s.ms_sw_kernel = with_sw ? b->sw.ms_fast_kernel : 0.f;
     s.clusters = ncl;
     s.sw_calls = b->sw.sw_calls; s.sw_cells = b->sw.cells; s.sw_general = b->sw.n_general;
     s.launches += b->sw.launches;

@@ -167,6 +167,32 @@ __global__ void synth_kernel(uint8_t *__restrict__ out, uint64_t len, uint64_t s
     out[i] = (uint8_t)"ACGT"[(z >> (2 * (i & 31))) & 3];
 }
 
+__device__ __forceinline__ uint64_t mix64(uint64_t z) {           // splitmix64 finaliser
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+
+// one thread per base: read r starts at hash(seed, r) mod (ref_len - len + 1); base p of read r is substituted
+// (by one of the three other bases of A,C,G,T) with probability thresh / 2^32
+__global__ void sample_reads_kernel(const uint8_t *__restrict__ ref, uint64_t ref_len, int64_t n, int32_t len,
+                                    uint64_t seed, uint32_t thresh, uint8_t *__restrict__ out,
+                                    int64_t *__restrict__ starts) {
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n * len) return;
+    int64_t r = t / len;
+    int32_t p = (int32_t)(t - r * len);
+    uint64_t start = mix64(seed ^ (0x9E3779B97F4A7C15ull * (uint64_t)(r + 1))) % (ref_len - (uint64_t)len + 1);
+    if (p == 0 && starts) starts[r] = (int64_t)start;
+    uint8_t c = ref[start + p];
+    uint64_t h = mix64((seed + 0x51ED270B1ull) ^ (0xD6E8FEB86659FD93ull * (uint64_t)(t + 1)));
+    if ((uint32_t)h < thresh) {
+        int k = bwt_code(c);
+        if (k >= 0) c = (uint8_t)"ACGT"[(k + 1 + (int)((h >> 32) % 3)) & 3];
+    }
+    out[t] = c;
+}
+
 struct DevBuf {
     void *p = nullptr;
     ~DevBuf() { release(); }
@@ -230,13 +256,20 @@ int build_sa_device(const uint8_t *d_text, uint64_t len, uint32_t **d_sa_out, ui
             break;
         uint32_t *const a_head = keys_a.as<uint32_t>(), *const a_tied = keys_a.as<uint32_t>() + n, *const a_grp = idx_a.as<uint32_t>();
         key0_kernel<<<blocks_for(n), 256>>>(d_text, len, n, keys_a.as<uint64_t>(), idx_a.as<uint32_t>());
+        // DoubleBuffer form: O(1) temporary storage (the pointer form would take another n*12 bytes); the 63-bit
+        // key needs 8 passes, an even number, so the sorted data ends in the "b" halves -- checked, not assumed.
         size_t tmp_bytes = 0;
-        cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys_a.as<uint64_t>(), keys_b.as<uint64_t>(), idx_a.as<uint32_t>(),
-                                        idx_b.as<uint32_t>(), (uint64_t)n, 0, 63);
+        cub::DoubleBuffer<uint64_t> kbuf(keys_a.as<uint64_t>(), keys_b.as<uint64_t>());
+        cub::DoubleBuffer<uint32_t> vbuf(idx_a.as<uint32_t>(), idx_b.as<uint32_t>());
+        cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, kbuf, vbuf, (uint64_t)n, 0, 64);
+        tmp_bytes += 1024;
         if ((st = tmp.alloc(tmp_bytes))) break;
-        cudaError_t e = cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, keys_a.as<uint64_t>(), keys_b.as<uint64_t>(),
-                                                        idx_a.as<uint32_t>(), idx_b.as<uint32_t>(), (uint64_t)n, 0, 63);
+        cudaError_t e = cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, kbuf, vbuf, (uint64_t)n, 0, 63);
         if (e != cudaSuccess) { bwt_set_error("builder: radix sort failed: %s", cudaGetErrorString(e)); st = BWT_ERR_CUDA; break; }
+        if (kbuf.Current() != keys_b.as<uint64_t>()) {      // normalise: sorted keys in keys_b / idx_b
+            CU_TRY(cudaMemcpy(keys_b.p, kbuf.Current(), n * 8, cudaMemcpyDeviceToDevice));
+            CU_TRY(cudaMemcpy(idx_b.p, vbuf.Current(), n * 4, cudaMemcpyDeviceToDevice));
+        }
         if ((st = compute_groups(keys_b.as<uint64_t>(), n, a_head, a_grp, a_tied, blk.as<uint32_t>()))) break;
         commit0_kernel<<<blocks_for(n), 256>>>(idx_b.as<uint32_t>(), a_grp, n, d_sa, rank.as<uint32_t>());
         // tied slots of round 0
@@ -257,12 +290,16 @@ int build_sa_device(const uint8_t *d_text, uint64_t len, uint32_t **d_sa_out, ui
         while (m > 0) {
             keyh_kernel<<<blocks_for(m), 256>>>(pos, m, d_sa, rank.as<uint32_t>(), n, h, keys_a.as<uint64_t>(), idx_a.as<uint32_t>());
             size_t need = 0;
-            cub::DeviceRadixSort::SortPairs(nullptr, need, keys_a.as<uint64_t>(), keys_b.as<uint64_t>(), idx_a.as<uint32_t>(),
-                                            idx_b.as<uint32_t>(), (uint64_t)m, 0, 64);
+            cub::DoubleBuffer<uint64_t> kb(keys_a.as<uint64_t>(), keys_b.as<uint64_t>());
+            cub::DoubleBuffer<uint32_t> vb(idx_a.as<uint32_t>(), idx_b.as<uint32_t>());
+            cub::DeviceRadixSort::SortPairs(nullptr, need, kb, vb, (uint64_t)m, 0, 64);
             if (need > tmp_bytes) { bwt_set_error("builder: radix temp grew"); st = BWT_ERR_NOMEM; break; }
-            e = cub::DeviceRadixSort::SortPairs(tmp.p, need, keys_a.as<uint64_t>(), keys_b.as<uint64_t>(), idx_a.as<uint32_t>(),
-                                                idx_b.as<uint32_t>(), (uint64_t)m, 0, 64);
+            e = cub::DeviceRadixSort::SortPairs(tmp.p, need, kb, vb, (uint64_t)m, 0, 64);
             if (e != cudaSuccess) { bwt_set_error("builder: radix sort failed: %s", cudaGetErrorString(e)); st = BWT_ERR_CUDA; break; }
+            if (kb.Current() != keys_b.as<uint64_t>()) {
+                CU_TRY(cudaMemcpy(keys_b.p, kb.Current(), m * 8, cudaMemcpyDeviceToDevice));
+                CU_TRY(cudaMemcpy(idx_b.p, vb.Current(), m * 4, cudaMemcpyDeviceToDevice));
+            }
             if ((st = compute_groups(keys_b.as<uint64_t>(), m, a_head, a_grp, a_tied, blk.as<uint32_t>()))) break;
             commith_kernel<<<blocks_for(m), 256>>>(pos, idx_b.as<uint32_t>(), a_grp, m, d_sa, rank.as<uint32_t>());
             cudaMemcpy(a_head, a_tied, m * 4, cudaMemcpyDeviceToDevice);
@@ -341,4 +378,26 @@ extern "C" int bwt_build_synthetic(uint64_t len, uint64_t seed, int64_t shift, i
     synth_kernel<<<blocks_for(len), 256>>>(d.as<uint8_t>(), len, seed);
     CU_TRY(cudaGetLastError());
     return build_from_device_chunk(d.as<uint8_t>(), len, shift, device, true, out);
+}
+
+extern "C" int bwt_sample_reads(const bwt_index *h, int64_t n, int32_t read_len, uint64_t seed, double sub_rate,
+                                uint8_t *reads_out, int64_t *starts_out) {
+    if (!h || !reads_out || n < 0 || read_len <= 0 || sub_rate < 0 || sub_rate > 1 || (uint64_t)read_len > h->ref_len) {
+        bwt_set_error("bwt_sample_reads: bad argument");
+        return BWT_ERR_ARG;
+    }
+    if (n == 0) return BWT_OK;
+    BWT_TRY(index_select_device(h->device));
+    DevBuf out, st;
+    BWT_TRY(out.alloc((size_t)n * read_len));
+    if (starts_out) BWT_TRY(st.alloc((size_t)n * sizeof(int64_t)));
+    double t = sub_rate * 4294967296.0;
+    uint32_t thresh = t >= 4294967295.0 ? 0xFFFFFFFFu : (uint32_t)t;
+    sample_reads_kernel<<<blocks_for((uint64_t)n * read_len), 256>>>((const uint8_t *)h->d_ref + BWT_REF_EXT, h->ref_len, n, read_len,
+                                                                    seed, thresh, out.as<uint8_t>(),
+                                                                    starts_out ? st.as<int64_t>() : nullptr);
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaMemcpy(reads_out, out.p, (size_t)n * read_len, cudaMemcpyDeviceToHost));
+    if (starts_out) CU_TRY(cudaMemcpy(starts_out, st.p, (size_t)n * sizeof(int64_t), cudaMemcpyDeviceToHost));
+    return BWT_OK;
 }

@@ -396,6 +396,8 @@ int sw_stage_reserve(SwStage &st, uint32_t pairs) {
     if (!st.d_ctr) {
         CU_TRY(cudaMalloc(&st.d_ctr, sizeof(SwCounters)));
         CU_TRY(cudaMallocHost(&st.h_ctr, sizeof(SwCounters)));
+        CU_TRY(cudaEventCreate(&st.ev_k0));
+        CU_TRY(cudaEventCreate(&st.ev_k1));
     }
     st.cap = want;
     if (st.cig_cap < 32u * want) {
@@ -410,6 +412,8 @@ int sw_stage_reserve(SwStage &st, uint32_t pairs) {
 void sw_stage_free(SwStage &st) {
     cudaFree(st.d_desc); cudaFree(st.d_out); cudaFree(st.d_list_fast); cudaFree(st.d_list_gen);
     cudaFree(st.d_ctr); if (st.h_ctr) cudaFreeHost(st.h_ctr);
+    if (st.ev_k0) cudaEventDestroy(st.ev_k0);
+    if (st.ev_k1) cudaEventDestroy(st.ev_k1);
     cudaFree(st.d_cig_tmp); cudaFree(st.d_dirs); cudaFree(st.d_gen_scratch); cudaFree(st.d_gen_off); cudaFree(st.d_gen_dims);
     st = SwStage();
 }
@@ -417,6 +421,7 @@ void sw_stage_free(SwStage &st) {
 int sw_stage_run(SwStage &st, const uint8_t *d_qbase, const uint8_t *d_rbase, uint32_t n, int max_lq,
                  cudaStream_t stream) {
     st.sw_calls = st.cells = st.n_general = 0;
+    st.ms_fast_kernel = 0;
     if (n == 0) return BWT_OK;
     if (n > st.cap) { bwt_set_error("sw_stage_run: %u pairs exceed the reserved %u", n, st.cap); return BWT_ERR_ARG; }
     // shared-memory tier: columns = longest query + 1 + 64 slack, multiple of 16, capped by the 227 KB CTA limit
@@ -445,7 +450,9 @@ int sw_stage_run(SwStage &st, const uint8_t *d_qbase, const uint8_t *d_rbase, ui
         p.qbase = d_qbase; p.rbase = d_rbase; p.desc = st.d_desc; p.list = st.d_list_fast; p.out = st.d_out;
         p.list_gen = st.d_list_gen; p.ctr = st.d_ctr; p.cig = st.d_cig_tmp; p.cig_cap = st.cig_cap;
         p.dirs = st.d_dirs; p.cap_cols = cap_cols; p.max_strips = max_strips;
+        CU_TRY(cudaEventRecord(st.ev_k0, stream));
         sw_fast_kernel<<<grid, SW_BLOCK, smem, stream>>>(p);
+        CU_TRY(cudaEventRecord(st.ev_k1, stream));
         st.launches += 2;
         K_CHECK(stream, "sw_fast_kernel");
         CU_TRY(cudaMemcpyAsync(st.h_ctr, st.d_ctr, sizeof(SwCounters), cudaMemcpyDeviceToHost, stream));
@@ -493,6 +500,7 @@ int sw_stage_run(SwStage &st, const uint8_t *d_qbase, const uint8_t *d_rbase, ui
             CU_TRY(cudaStreamSynchronize(stream));
         }
         if (!st.h_ctr->cig_overflow) {
+            cudaEventElapsedTime(&st.ms_fast_kernel, st.ev_k0, st.ev_k1);
             st.sw_calls = st.h_ctr->sw_calls; st.cells = st.h_ctr->cells; st.n_general = st.h_ctr->n_general;
             return BWT_OK;
         }

@@ -46,6 +46,8 @@ struct SwStage {
     int2 *d_gen_dims = nullptr;
     uint32_t launches = 0;
     unsigned long long sw_calls = 0, cells = 0, n_general = 0;
+    cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr;   // around sw_fast_kernel
+    float ms_fast_kernel = 0;
 };
 
 int sw_stage_reserve(SwStage &st, uint32_t pairs);

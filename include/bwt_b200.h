@@ -89,8 +89,10 @@ typedef struct bwt_hit {
 } bwt_hit;
 
 typedef struct bwt_stats {   /* work counters of the last run (definitions: DESIGN.md "units") */
-    uint64_t reads, searches, lf_steps, located_rows, clusters, sw_calls, sw_cells, sw_general;
-    float ms_total, ms_seed, ms_sw, ms_emit, ms_h2d, ms_d2h; /* CUDA-event times on the batch's stream */
+    uint64_t reads, searches, lf_steps, hbm_lf_steps, located_rows, clusters, sw_calls, sw_cells, sw_general;
+    float ms_total, ms_seed, ms_sw, ms_emit, ms_h2d, ms_d2h; /* CUDA-event times of the stages on the batch's stream */
+    float ms_sga_kernel;     /* sga_kernel alone: events directly around its launch */
+    float ms_sw_kernel;      /* sw_fast_kernel alone */
     uint32_t launches;       /* kernels of this library launched by the last run */
     uint32_t reserved;
 } bwt_stats;
@@ -180,6 +182,13 @@ int bwt_batch_device_result(bwt_batch *b, void **d_hit_offsets, void **d_hits, v
  * `repeats` times; *ms = CUDA-event time of all repeats, *lf_steps = LF steps executed per repeat. */
 int bwt_search_resident(bwt_index *h, const uint8_t *subs, int64_t n, int32_t sub_len, int32_t repeats,
                         float *ms, uint64_t *lf_steps, uint64_t *hbm_lf_steps);
+
+/* Synthetic reads for the benchmark configs, sampled on the device from the index's own .ref:
+ * read r = read_len bases starting at a uniform position (counter-based generator, seed), each base replaced by a
+ * different base with probability sub_rate (substitutions only, so every read keeps read_len).  Forward strand.
+ * reads_out: host buffer of n*read_len bytes; starts_out (may be NULL): n 0-based chunk positions. */
+int bwt_sample_reads(const bwt_index *h, int64_t n, int32_t read_len, uint64_t seed, double sub_rate,
+                     uint8_t *reads_out, int64_t *starts_out);
 
 /* Microbenchmarks that give the roofline denominators measured on the device at hand:
  * random 32-byte-sector gather bandwidth (GB/s) and DPX (VIADDMNMX/VIMNMX3) issue rate (Gop/s). */

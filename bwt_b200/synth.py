@@ -1,6 +1,6 @@
 """Synthetic inputs for tests and bench.py: references, reads with the 1 % edit model.
 
-Everything is seeded (numpy PCG64) so that the GPU path, the oracle and the fixtures see the same bytes.
+Everything is seeded (numpy PCG64) so that the GPU path, the CPU checker and the fixtures see the same bytes.
 """
 from __future__ import annotations
 

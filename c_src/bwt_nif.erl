@@ -1,0 +1,22 @@
+%% bwt_nif -- Erlang face of libbwt_b200.so (c_src/bwt_nif.c).  Add this file to the reference's src/ and
+%% build c_src/bwt_nif.c into priv/bwt_nif.so (see INTEGRATION.md).  Every function is replaced by its NIF at load.
+-module(bwt_nif).
+-export([open/3, info/1, find_seeds/2, sga/2, sw/2, align/2]).
+-on_load(init/0).
+
+init() ->
+    PrivDir = case code:priv_dir(bwt) of {error, _} -> "priv"; D -> D end,
+    erlang:load_nif(filename:join(PrivDir, "bwt_nif"), 0).
+
+%% open(FmPath, RefPath, Device) -> {ok, Index} | {error, {Code, Msg}}
+open(_FmPath, _RefPath, _Device) -> erlang:nif_error(nif_not_loaded).
+%% info(Index) -> {{Pc,Pg,Pt,Last}, Shift, NRows}
+info(_Index) -> erlang:nif_error(nif_not_loaded).
+%% find_seeds(Index, [Subseq]) -> [{seeds|no_seeds|too_many_seeds|crash, Sp, Ep, N}]
+find_seeds(_Index, _Subseqs) -> erlang:nif_error(nif_not_loaded).
+%% sga(Index, [Qseq]) -> [[{S,D}] | crash]
+sga(_Index, _Qseqs) -> erlang:nif_error(nif_not_loaded).
+%% sw([{Qseq, Ref}], Device) -> [no_match | {Score, Cigar}]
+sw(_Pairs, _Device) -> erlang:nif_error(nif_not_loaded).
+%% align(Index, [Qseq]) -> [crash | [{match|no_match|window_oor, Score, Cigar, Pos, S, D}]]
+align(_Index, _Qseqs) -> erlang:nif_error(nif_not_loaded).

@@ -55,6 +55,7 @@ SIGNATURES = {
     "bwt_save": (C.c_int, [P, C.c_char_p, C.c_char_p]),
     "bwt_export": (C.c_int, [P, P, P, P]),
     "bwt_info": (C.c_int, [P, C.POINTER(BwtIndexInfo)]),
+    "bwt_set_kmer_depth": (C.c_int, [P, C.c_int]),
     "bwt_close": (C.c_int, [P]),
     "bwt_search_batch": (C.c_int, [P, P, P, C.c_int64, P, P, P, P]),
     "bwt_locate": (C.c_int, [P, C.c_uint32, C.c_uint32, P]),

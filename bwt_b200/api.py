@@ -107,6 +107,10 @@ class Index:
         check(lib().bwt_info(self._h, C.byref(i)))
         return i
 
+    def set_kmer_depth(self, k: int):
+        """0/8 = the 4^8 table only; 9..15 = deeper interval table (results never depend on it)."""
+        check(lib().bwt_set_kmer_depth(self._h, int(k)))
+
     def export(self, want_L=True, want_SA=True, want_ref=True):
         i = self.info()
         L = np.empty(i.n_rows, np.uint8) if want_L else None

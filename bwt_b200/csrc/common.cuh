@@ -57,7 +57,9 @@ bool bwt_debug_sync();
 struct DevIndex {
     const uint4 *occ;
     const uint32_t *sa;        // full suffix array, SA[e-1] for 1-based row e (fmi.erl:89-100 reads it un-sampled)
-    const uint2 *kmer;         // 4^8 entries: (Sp,Ep) after the first 8 characters, or (0, steps) if the search stopped
+    const uint2 *kmer;         // 4^8 entries, depth-8 interval table (format: KmerEntry below)
+    const uint2 *kmer_deep;    // 4^deep_k entries, or null
+    int deep_k;                // 9..15, or 0 when there is no deep table
     const uint8_t *ref;        // .ref padded with 200 'N' on both sides (worker_bwt.erl:53-55)
     uint64_t ref_len_padded;
     uint32_t n;                // rows
@@ -67,6 +69,19 @@ struct DevIndex {
     int64_t shift;
 };
 
+// k-mer interval table entry (uint2): the state of bwa:find_seeds/6 after walking the last k characters of a
+// subsequence (all plain ACGT; a trailing 'N' counts as 'A', bwa.erl:21-23):
+//   x = Sp                                   y = (Ep - Sp) | n << 28
+//   n == k : all k characters matched, interval [Sp,Ep]
+//   1 <= n < k : se_down said not_found at character n+1 (bwa.erl:37-38); [Sp,Ep] is the interval at that point
+//   n == 0 : Ep - Sp does not fit 28 bits: the caller walks from the start instead
+constexpr uint32_t KMER_W_MASK = 0x0FFFFFFFu;
+__host__ __device__ __forceinline__ uint2 kmer_pack(uint32_t sp, uint32_t ep, int n) {
+    uint32_t w = ep - sp;
+    if (w >= KMER_W_MASK) return make_uint2(0u, 0u);
+    return make_uint2(sp, w | ((uint32_t)n << 28));
+}
+
 struct bwt_index {
     DevIndex dv{};
     int device = 0;
@@ -75,7 +90,7 @@ struct bwt_index {
     uint32_t pointers[4] = {0, 0, 0, 0};
     int64_t shift = 0;
     uint64_t device_bytes = 0;
-    void *d_occ = nullptr, *d_sa = nullptr, *d_kmer = nullptr, *d_ref = nullptr;
+    void *d_occ = nullptr, *d_sa = nullptr, *d_kmer = nullptr, *d_ref = nullptr, *d_kmer_deep = nullptr;
 };
 
 // ASCII -> index code (A0 C1 G2 T3), -1 otherwise

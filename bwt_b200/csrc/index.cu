@@ -89,21 +89,41 @@ __global__ void counts_kernel(uint4 *__restrict__ occ, uint64_t nb, const uint32
     if (b < nb) occ[2 * b] = make_uint4(cA[b], cC[b], cG[b], cT[b]);
 }
 
-// 4^8 threads: the first eight characters of bwa:find_seeds/6 for every ACGT 8-mer
+// 4^8 threads: the first eight characters of bwa:find_seeds/6 for every ACGT 8-mer; entry format in
+// common.cuh (the interval at a not_found stop is kept, so the explicit search API can report it)
 __global__ void kmer_kernel(DevIndex ix, uint2 *__restrict__ tab) {
     uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= 65536u) return;
-    const char sym[4] = {'A', 'C', 'G', 'T'};
-    uint8_t q[8];
-    for (int t = 0; t < 8; t++) q[7 - t] = (uint8_t)sym[(idx >> (2 * t)) & 3];   // q[7] is the last character
     uint32_t sp, ep;
     first_interval(ix, (int)(idx & 3), sp, ep);
     int n = 1;
-    for (int k = 6; k >= 0; k--) {
-        if (!lf_step(ix, sp, ep, bwt_code(q[k]))) break;
+    for (int t = 1; t < 8; t++) {
+        if (!lf_step(ix, sp, ep, (int)((idx >> (2 * t)) & 3))) break;
         n++;
     }
-    tab[idx] = (n == 8) ? make_uint2(sp, ep) : make_uint2(0u, (uint32_t)n);
+    tab[idx] = kmer_pack(sp, ep, n);
+}
+
+// depth k -> k+1, in place: entry i (the k characters before the end of a subsequence, last character in bits 0-1)
+// has the four children i | c << 2k.  One thread per parent: both Occ sectors are fetched once for the four characters.
+__global__ void kmer_expand_kernel(DevIndex ix, uint2 *__restrict__ tab, int k) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t cnt = 1ull << (2 * k);
+    if (i >= cnt) return;
+    uint2 e = tab[i];
+    int ne = (int)(e.y >> 28);
+    uint2 child[4] = {e, e, e, e};                      // stopped / overflowed parents propagate unchanged
+    if (ne == k) {
+        const uint32_t sp0 = e.x, ep0 = e.x + (e.y & KMER_W_MASK);
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            uint32_t sp = sp0, ep = ep0;
+            child[c] = lf_step(ix, sp, ep, c) ? kmer_pack(sp, ep, k + 1) : e;   // not_found: stays at n = k
+        }
+    }
+#pragma unroll
+    for (int c = 1; c < 4; c++) tab[i + (uint64_t)c * cnt] = child[c];
+    tab[i] = child[0];
 }
 
 __global__ void pad_fill_kernel(uint8_t *p, uint64_t n, uint8_t v) {
@@ -163,10 +183,50 @@ int index_finish_from_device(bwt_index *h, const uint8_t *d_L, uint64_t n, uint3
     dv.last = pointers[3];
     dv.dollar = flags[0];
     dv.shift = shift;
+    dv.kmer_deep = nullptr;
+    dv.deep_k = 0;
     kmer_kernel<<<256, 256>>>(dv, d_kmer);
     CU_TRY(cudaGetLastError());
     CU_TRY(cudaDeviceSynchronize());
     h->device_bytes = nb * 32 + n * 4 + 65536 * 8 + dv.ref_len_padded;
+    // deep table: the largest depth <= 15 whose 4^k entries do not outnumber 4 rows of the index each
+    // (GL000193.1: k = 9; 3.1 Gbp: k = 15 = MAX_LEN, a whole search is one lookup); BWT_KMER_K overrides
+    int k = 8;
+    while (k < BWT_MAX_LEN && (1ull << (2 * (k + 1))) <= 4ull * n) k++;
+    if (const char *e = getenv("BWT_KMER_K")) { int v = atoi(e); if (v == 0 || (v >= 8 && v <= BWT_MAX_LEN)) k = v; }
+    return bwt_set_kmer_depth(h, k);
+}
+
+extern "C" int bwt_set_kmer_depth(bwt_index *h, int k) {
+    if (!h || (k != 0 && (k < 8 || k > BWT_MAX_LEN))) { bwt_set_error("bwt_set_kmer_depth: depth must be 0 or 8..15"); return BWT_ERR_ARG; }
+    CU_TRY(cudaSetDevice(h->device));
+    CU_TRY(cudaDeviceSynchronize());
+    if (h->d_kmer_deep) {
+        h->device_bytes -= (8ull << (2 * h->dv.deep_k));
+        cudaFree(h->d_kmer_deep);
+        h->d_kmer_deep = nullptr;
+    }
+    h->dv.kmer_deep = nullptr;
+    h->dv.deep_k = 0;
+    if (k <= 8) return BWT_OK;                          // the depth-8 table alone
+    uint2 *tab = nullptr;
+    const uint64_t entries = 1ull << (2 * k);
+    if (cudaMalloc(&tab, entries * sizeof(uint2)) != cudaSuccess) {
+        cudaGetLastError();
+        bwt_set_error("k-mer table of depth %d (%llu MB) does not fit", k, (unsigned long long)(entries * 8 >> 20));
+        return BWT_ERR_NOMEM;
+    }
+    CU_TRY(cudaMemcpy(tab, h->d_kmer, 65536 * sizeof(uint2), cudaMemcpyDeviceToDevice));
+    for (int d = 8; d < k; d++) {
+        kmer_expand_kernel<<<(unsigned)div_up_u64(1ull << (2 * d), 256), 256>>>(h->dv, tab, d);
+        CU_TRY(cudaGetLastError());
+    }
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { cudaFree(tab); bwt_set_error("k-mer table build: %s", cudaGetErrorString(e)); return BWT_ERR_CUDA; }
+    h->d_kmer_deep = tab;
+    h->dv.kmer_deep = tab;
+    h->dv.deep_k = k;
+    h->device_bytes += entries * 8;
     return BWT_OK;
 }
 
@@ -259,7 +319,7 @@ extern "C" int bwt_open(const char *fm_path, const char *ref_path, int device, b
 extern "C" int bwt_close(bwt_index *h) {
     if (!h) return BWT_OK;
     cudaSetDevice(h->device);
-    cudaFree(h->d_occ); cudaFree(h->d_sa); cudaFree(h->d_kmer); cudaFree(h->d_ref);
+    cudaFree(h->d_occ); cudaFree(h->d_sa); cudaFree(h->d_kmer); cudaFree(h->d_kmer_deep); cudaFree(h->d_ref);
     delete h;
     return BWT_OK;
 }
@@ -273,7 +333,7 @@ extern "C" int bwt_info(const bwt_index *h, bwt_index_info *info) {
     info->dollar_row = h->dv.dollar;
     info->device_bytes = h->device_bytes;
     info->device = h->device;
-    info->kmer_k = 8;
+    info->kmer_k = h->dv.deep_k ? h->dv.deep_k : 8;
     return BWT_OK;
 }
 

@@ -65,7 +65,7 @@ struct SearchRes {
     uint32_t sp, ep;
     int n;        // characters matched (the reference's N)
     int status;   // BWT_SEEDS / BWT_NO_SEEDS / BWT_TOO_MANY_SEEDS / BWT_SEARCH_CRASH
-    int table;    // 1 when the first 8 characters were served by the k-mer table
+    int table;    // characters matched by a k-mer table lookup (0 = none): their LF steps touched no Occ block
 };
 
 __device__ __forceinline__ void first_interval(const DevIndex &ix, int c, uint32_t &sp, uint32_t &ep) {
@@ -76,45 +76,42 @@ __device__ __forceinline__ void first_interval(const DevIndex &ix, int c, uint32
     else { sp = ix.P[3]; ep = ix.last; }
 }
 
-// bwa:find_seeds/6 on q[0..len), len >= 1.  use_table: consult the 8-mer table (false while building it).
-// exact_stop: when the table says the walk stopped before 8 characters (=> no_seeds whatever the interval), redo
-// the walk so that the reported Sp/Ep/N are the reference's too (only the explicit search API needs them).
-__device__ __forceinline__ SearchRes search_sub(const DevIndex &ix, const uint8_t *q, int len, bool use_table,
-                                                bool exact_stop = false) {
+// bwa:find_seeds/6 on q[0..len), len >= 1.  use_table: consult the k-mer tables (false while building them).
+__device__ __forceinline__ SearchRes search_sub(const DevIndex &ix, const uint8_t *q, int len, bool use_table) {
     SearchRes R;
     R.table = 0;
     uint8_t h = q[len - 1];
     int c = (h == 'N') ? 0 : bwt_code(h);
     if (c < 0) { R.sp = R.ep = 0; R.n = 0; R.status = BWT_SEARCH_CRASH; return R; }   // case_clause
-    uint32_t sp, ep;
+    uint32_t sp = 0, ep = 0;
     int n = 1, k = len - 2;
-    bool have = false;
+    bool have = false, stopped = false;
     if (use_table && len >= BWT_MIN_LEN) {
-        // the next 7 characters must be plain ACGT for the table to apply
+        // the table of depth d applies when the d-1 characters before the last are plain ACGT
+        const int dk = (ix.deep_k > 0 && len >= ix.deep_k) ? ix.deep_k : BWT_MIN_LEN;
         uint32_t idx = (uint32_t)c;
-        bool ok = true;
-#pragma unroll
-        for (int t = 1; t < BWT_MIN_LEN; t++) {
+        int good = 1;                                  // leading characters (from the end) that are ACGT
+        for (int t = 1; t < dk; t++) {
             int ct = bwt_code(q[len - 1 - t]);
-            ok = ok && (ct >= 0);
-            idx |= (uint32_t)(ct & 3) << (2 * t);
+            if (ct < 0) break;
+            idx |= (uint32_t)ct << (2 * t);
+            good++;
         }
-        if (ok) {
-            uint2 e = __ldg(ix.kmer + idx);
-            if (e.x == 0 && !exact_stop) {        // stopped before 8 characters => no_seeds (fmi.erl:89-91)
-                R.table = 1;
-                R.sp = R.ep = 0; R.n = (int)e.y; R.status = BWT_NO_SEEDS; return R;
-            }
-            if (e.x != 0) {
-                R.table = 1;
-                sp = e.x; ep = e.y; n = BWT_MIN_LEN; k = len - 1 - BWT_MIN_LEN;
+        int depth = good >= dk ? dk : (good >= BWT_MIN_LEN ? BWT_MIN_LEN : 0);
+        if (depth) {
+            uint2 e = depth == BWT_MIN_LEN ? __ldg(ix.kmer + (idx & 0xFFFFu)) : __ldg(ix.kmer_deep + idx);
+            int ne = (int)(e.y >> 28);
+            if (ne) {
+                R.table = ne;                          // characters whose steps the table served
+                sp = e.x; ep = e.x + (e.y & KMER_W_MASK); n = ne; k = len - 1 - ne;
                 have = true;
+                stopped = ne < depth;                  // not_found inside the table's reach
             }
         }
     }
     if (!have) first_interval(ix, c, sp, ep);
-    bool checked;
-    for (;;) {
+    bool checked = false;
+    while (!stopped) {
         if (n == BWT_MAX_LEN) { checked = true; break; }             // bwa.erl:31-32
         if (k < 0) { checked = true; break; }                        // bwa.erl:44-45
         uint8_t ch = q[k];

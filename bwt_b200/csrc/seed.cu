@@ -43,7 +43,7 @@ __global__ void __launch_bounds__(256) search_kernel(DevIndex ix, const uint8_t 
         else { q = subs + offs[i]; len = (int)(offs[i + 1] - offs[i]); }
         SearchRes r;
         if (len <= 0) { r.sp = r.ep = 0; r.n = 0; r.status = BWT_SEARCH_CRASH; r.table = 0; }   // hd([]) badmatch
-        else r = search_sub(ix, q, len, true, true);
+        else r = search_sub(ix, q, len, true);
         if (status) status[i] = r.status;
         if (sp) sp[i] = r.sp;
         if (ep) ep[i] = r.ep;
@@ -51,7 +51,7 @@ __global__ void __launch_bounds__(256) search_kernel(DevIndex ix, const uint8_t 
         cnt++;
         int steps = r.n > 0 ? r.n - 1 : 0;
         lf += steps;
-        hbm += r.table ? (r.n > BWT_MIN_LEN ? r.n - BWT_MIN_LEN : 0) : steps;
+        hbm += r.table ? r.n - r.table : steps;
     }
     // warp-reduce, then one shared atomic per warp
     for (int d = 16; d > 0; d >>= 1) {
@@ -140,7 +140,7 @@ __device__ __forceinline__ int sga_read(const Tile &tile, const DevIndex &ix, co
         gs.t_res[k] = make_uint2(r.sp, (cnt << 4) | (uint32_t)r.n);
         int steps = r.n > 0 ? r.n - 1 : 0;
         lf += steps;
-        hbm += r.table ? (r.n > BWT_MIN_LEN ? r.n - BWT_MIN_LEN : 0) : steps;
+        hbm += r.table ? r.n - r.table : steps;
     }
     crash = tile.any(crash);
     tile.sync();

@@ -73,7 +73,7 @@ typedef struct bwt_index_info {
     uint64_t dollar_row;    /* 1-based row whose L is '$' */
     uint64_t device_bytes;  /* HBM held by this handle */
     int32_t device;
-    int32_t kmer_k;         /* depth of the first-k-mer interval table (8) */
+    int32_t kmer_k;         /* depth of the deepest k-mer interval table (8..15) */
 } bwt_index_info;
 
 /* One candidate of one read: an element of worker_bwt's Cigars fold (worker_bwt.erl:84-97), plus the
@@ -127,6 +127,12 @@ int bwt_save(const bwt_index *h, const char *fm_path, const char *ref_path);
 int bwt_export(const bwt_index *h, uint8_t *L, uint32_t *SA, uint8_t *ref);
 
 int bwt_info(const bwt_index *h, bwt_index_info *info);
+
+/* Depth of the k-mer interval table: entry = state of bwa:find_seeds/6 (bwa.erl:12-45) after the last k characters
+ * of a subsequence, so those k-1 LF steps cost one lookup.  0 or 8 = the 4^8 table only; 9..15 adds a 4^k-entry
+ * table (8 bytes each; k = 15 = MAX_LEN makes a whole search one lookup, 8.6 GB).  Chosen automatically at open
+ * (largest k with 4^k <= 4 * rows); results never depend on it.  Not thread-safe against running batches. */
+int bwt_set_kmer_depth(bwt_index *h, int k);
 int bwt_close(bwt_index *h);
 
 /* ---- one-shot calls with HOST buffers (copies inside) ------------------------------------------------ */

@@ -401,3 +401,34 @@ def test_synthetic_index_parity_midsize():
         for ln, cnt in ((100, 20000), (150, 5000)):
             reads, offs, _ = sample_reads_fast(ref, cnt, ln, seed=ln, edit_rate=0.01)
             _check_align(ix, orc, reads, offs, min_hits=cnt // 10)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# k-mer interval table depth never changes a result
+# ---------------------------------------------------------------------------------------------------------
+def test_kmer_table_depths(gl_fm, gl_ref, gl_coracle):
+    rng = np.random.default_rng(77)
+    subs = [_rand_query(rng, gl_ref, 1, 40) for _ in range(20000)]
+    want = [gl_coracle.find_seeds(q) for q in subs]
+    reads, offs, _ = sample_reads(gl_ref, 3000, 100, seed=13, edit_rate=0.02, n_rate=0.003)
+    base = None
+    with api.Index.from_arrays(gl_fm.L, gl_fm.SA, gl_fm.pointers, gl_fm.shift, gl_ref) as ix:
+        assert ix.info().kmer_k == 9                    # 4^9 <= 4 * 189790 < 4^10
+        for depth in (0, 9, 11, 14, 15):
+            ix.set_kmer_depth(depth)
+            assert ix.info().kmer_k == max(depth, 8)
+            st, sp, ep, n = ix.search(subs)
+            for k, w in enumerate(want):
+                if w[0] == 3:
+                    assert st[k] == 3
+                else:
+                    assert (int(st[k]), int(sp[k]), int(ep[k]), int(n[k])) == w, (depth, subs[k])
+            res = ix.align(reads, offs)
+            if base is None:
+                base = res
+                _check_align(ix, gl_coracle, reads, offs, min_hits=500)
+            else:
+                assert (res[0] == base[0]).all() and (res[1] == base[1]).all() and res[3] == base[3]
+                assert (res[2] == base[2]).all()
+        with pytest.raises(api.BwtError):
+            ix.set_kmer_depth(16)

@@ -5,19 +5,22 @@
 // {V,Atom} under lists:max/1, sw.erl:90-94); the query is global, the window is free at both ends; a row
 // whose maximum falls below -2*(Lq div 2) + 2*i ends the alignment with no_match (sw.erl:62,69-71).
 //
-// Fast path (both strings plain ACGT, the common case):  one THREAD per pair, no inter-thread traffic.
-//   * a cell is one 32-bit key  K = 8*V + code,  code: left=1, up=2, up_left=4.  max over the three
-//     candidate keys reproduces value-then-direction ordering in one integer max, and the direction
-//     dependent gap cost is  m + 8*[code bit]  with m = K & ~7:
-//        diag = m(i-1,j-1) + (8*sigma+4)      up = m(i-1,j) + 4*(K&2) - 14      left = m(i,j-1) + 8*(K&1) - 15
-//     so a cell is 2 x VIADDMNMX (DPX, __viaddmax_s32) + 1 x VIMNMX for the row maximum + LOP3/IMAD.
-//   * the thread sweeps the matrix in strips of SW_R = 10 rows held in registers; only the strip's bottom
-//     row (int16 keys) and the 2-bit packed window live in shared memory, laid out [column][thread] so
-//     that a warp's accesses are conflict free.
-//   * the ten 3-bit direction codes of one column of a strip are one 32-bit word, written to a per-thread
-//     slice of an HBM/L2 scratch ([word][thread], coalesced) and read back by the traceback.
-//   * sigma comes from a per-row 4-byte profile selected with one PRMT (prmt.b32, sign-replicate mode) by the window base.
-// General path (any byte, e.g. 'N' = 1.6 or IUPAC codes in the window, or sizes beyond the fast tier):
+// Fast path (both strings plain ACGT, the common case):  one THREAD per TWO pairs, no inter-thread traffic.
+//   * a cell is one 16-bit key  K = 8*V + code,  code: left=1, up=2, up_left=4.  max over the three candidate
+//     keys reproduces value-then-direction ordering in one integer max, and the direction dependent gap cost is
+//     m + 8*[code bit] with m = K & ~7:
+//        diag = m(i-1,j-1) + (8*sigma+4)     up = m(i-1,j) + 8*[K&2] - 14     left = m(i,j-1) + 8*[K&1] - 15
+//   * the keys of two independent pairs (same query length) sit in the two halves of a 32-bit register and every
+//     operation is a Blackwell DPX / packed-16 instruction: 2 x VIADDMNMX.S16x2 per cell pair for the three-way max
+//     with its fused adds, VIADD.16x2 for the left candidate, VIMNMX.S16x2 for the row maximum, one PRMT that
+//     looks up both lanes' substitution scores from per-row byte profiles, LOP3 for the code/value split.
+//   * the thread sweeps the matrix in strips of SW_R = 10 rows held in registers; only the strip's bottom row
+//     (one 32-bit word per column = both pairs) and the 2-bit packed windows live in shared memory, laid out
+//     [column][thread] so that a warp's accesses are conflict free.
+//   * the ten 3-bit direction codes of one column of a strip are 2 x 15 bits per pair: one uint2 per column holds
+//     both pairs' codes, written to a per-thread slice of an HBM/L2 scratch ([column][thread], coalesced) and read
+//     back by the traceback.
+// General path (any byte, e.g. 'N' = 1.6 or IUPAC codes in the window, or sizes beyond the fast tiers):
 //   IEEE doubles added in the reference's order, one thread per pair, rows in HBM scratch.
 #include "sw.cuh"
 
@@ -30,22 +33,24 @@
 
 namespace {
 
-// PRMT with the sign-replicate bit of the selector nibbles honoured (the __byte_perm intrinsic masks it off):
-// result = byte (sel & 3) of a, sign-extended to 32 bits, for sel = b * 0x1111 + 0x8880.
-__device__ __forceinline__ int prmt_sext_byte(uint32_t a, uint32_t sel) {
-    int r;
-    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(0u), "r"(sel));
+// PRMT in its native form (the __byte_perm intrinsic masks the sign-replicate bit of the selector nibbles off):
+// bytes 0-3 come from a, 4-7 from b; a selector nibble with bit 3 set replicates the sign of the chosen byte.
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
+    uint32_t r;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(sel));
     return r;
 }
 
 __device__ __forceinline__ bool is_acgt(uint8_t c) { return c == 'A' || c == 'C' || c == 'G' || c == 'T'; }
+__device__ __forceinline__ int lane16(uint32_t x, int lane) { return lane ? ((int)x >> 16) : ((int)(x << 16) >> 16); }
+__device__ __forceinline__ uint32_t both(int k) { return ((uint32_t)k & 0xFFFFu) * 0x10001u; }
 
 // ---------------------------------------------------------------------------------------------------
-// classification: fast list / general list / immediate no_match
+// classification: narrow list / wide list / general list / immediate no_match
 // ---------------------------------------------------------------------------------------------------
 __global__ void sw_classify_kernel(const SwDesc *__restrict__ desc, SwOut *__restrict__ out, uint32_t n,
-                                   int cap_cols, uint32_t *__restrict__ list_fast, uint32_t *__restrict__ list_gen,
-                                   SwCounters *ctr) {
+                                   int cap_narrow, int cap_wide, uint32_t *__restrict__ list_fast,
+                                   uint32_t *__restrict__ list_wide, uint32_t *__restrict__ list_gen, SwCounters *ctr) {
     uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
     if (out[k].status == BWT_HIT_WINDOW_OOR) return;
@@ -55,7 +60,8 @@ __global__ void sw_classify_kernel(const SwDesc *__restrict__ desc, SwOut *__res
         out[k] = o;
         return;
     }
-    if (d.lq <= SW_FAST_MAX_LQ && d.lr + 1 <= cap_cols) list_fast[atomicAdd(&ctr->n_fast, 1u)] = k;
+    if (d.lq <= SW_FAST_MAX_LQ && d.lr + 1 <= cap_narrow) list_fast[atomicAdd(&ctr->n_fast, 1u)] = k;
+    else if (d.lq <= SW_FAST_MAX_LQ && d.lr + 1 <= cap_wide) list_wide[atomicAdd(&ctr->n_wide, 1u)] = k;
     else list_gen[atomicAdd(&ctr->n_general, 1u)] = k;
 }
 
@@ -66,63 +72,152 @@ struct SwFastParams {
     const uint8_t *qbase, *rbase;
     const SwDesc *desc;
     const uint32_t *list;
+    const uint32_t *n_list;   // device counter: entries of list
     SwOut *out;
     uint32_t *list_gen;
     SwCounters *ctr;
     char *cig;
     uint32_t cig_cap;
-    uint32_t *dirs;
+    uint2 *dirs;
     int cap_cols;      // columns (Lr+1) the shared row can hold; multiple of 16
     int max_strips;
 };
 
-template <bool MASKED>
-__device__ __forceinline__ void sw_strip(int16_t *__restrict__ row, const uint32_t *__restrict__ refw,
-                                         uint32_t *__restrict__ dstrip, const int lr, const int i0,
-                                         const uint32_t (&prof)[SW_R], int (&mx)[SW_R]) {
+struct StripState {
+    uint32_t mleft[SW_R];     // m(i, j-1) of both pairs
+    uint32_t left15[SW_R];    // left candidate key for column j: m(i,j-1) + 8*[left] - 15
+    uint32_t mx[SW_R];        // running row maxima
+};
+
+// columns j_from..j_to of one strip.  CAPPED: a pair whose window ended before this column keeps computing (its lane
+// is garbage from here on) but must not raise its row maxima: its keys are clamped to -32768 for the maximum.
+template <bool MASKED, bool CAPPED>
+__device__ __forceinline__ void sw_cols(uint32_t *__restrict__ row, const uint32_t *__restrict__ refw,
+                                        uint2 *__restrict__ dstrip, const int j_from, const int j_to, const int rmin,
+                                        const uint32_t capv, const uint32_t (&profA)[SW_R], const uint32_t (&profB)[SW_R],
+                                        StripState &S, uint32_t &mD_top) {
     constexpr int B = SW_BLOCK;
-    int mleft[SW_R], lfv[SW_R];
+    if (j_from > j_to) return;
+    uint32_t rwA = refw[(2 * ((j_from - 1) >> 4)) * B] >> (2 * ((j_from - 1) & 15));
+    uint32_t rwB = refw[(2 * ((j_from - 1) >> 4) + 1) * B] >> (2 * ((j_from - 1) & 15));
+    for (int j = j_from; j <= j_to; j++) {
+        if (((j - 1) & 15) == 0) { rwA = refw[(2 * ((j - 1) >> 4)) * B]; rwB = refw[(2 * ((j - 1) >> 4) + 1) * B]; }
+        // PRMT selector: lane A = byte cA of profA sign-extended, lane B = byte cB of profB sign-extended
+        const uint32_t sel = (rwA & 3u) * 0x11u + (rwB & 3u) * 0x1100u + 0xC480u;
+        rwA >>= 2; rwB >>= 2;
+        const uint32_t kt = row[j * B];                                // K(i0-1, j)
+        const uint32_t mT = kt & 0xFFF8FFF8u;
+        uint32_t mup = mT;
+        uint32_t tup = (((kt & 0x00020002u) * 4u)) | 0xFFF2FFF2u;      // 8*[up] - 14 per lane
+        uint32_t mdiag = mD_top;
+        uint32_t acc_lo = 0, acc_hi = 0, K = 0;
+#pragma unroll
+        for (int r = 0; r < SW_R; r++) {
+            const uint32_t s = prmt(profA[r], profB[r], sel);          // 8*sigma + 4, both lanes
+            const uint32_t x = __viaddmax_s16x2(mdiag, s, S.left15[r]);   // max(diag, left)
+            K = __viaddmax_s16x2(mup, tup, x);                          // max(up, .)
+            if (MASKED) K = (r >= rmin) ? K : 0u;
+            mdiag = S.mleft[r];
+            const uint32_t t7 = K & 0x00070007u;
+            const uint32_t m = K & 0xFFF8FFF8u;
+            S.mleft[r] = m;
+            S.left15[r] = __vadd2(m, ((t7 * 8u) & 0x00080008u) | 0xFFF1FFF1u);
+            mup = m;
+            tup = ((t7 * 4u) & 0x00080008u) | 0xFFF2FFF2u;
+            S.mx[r] = __vmaxs2(S.mx[r], CAPPED ? __vmins2(K, capv) : K);
+            if (r < 5) acc_lo += t7 << (3 * r); else acc_hi += t7 << (3 * (r - 5));
+        }
+        mD_top = mT;
+        row[j * B] = K;
+        dstrip[j * B] = make_uint2(acc_lo, acc_hi);
+    }
+}
+
+template <bool MASKED>
+__device__ __forceinline__ void sw_strip(uint32_t *__restrict__ row, const uint32_t *__restrict__ refw,
+                                         uint2 *__restrict__ dstrip, const int lr_min, const int lr_max, const uint32_t capv,
+                                         const int i0, const uint32_t (&profA)[SW_R], const uint32_t (&profB)[SW_R],
+                                         StripState &S) {
     const int rmin = 1 - i0;                        // first real row of a masked strip (rows i <= 0 are row 0)
 #pragma unroll
     for (int r = 0; r < SW_R; r++) {
-        int i = i0 + r;
-        int k0 = -8 * (i + 1) + 2;                  // column 0: V = -(i+1), dir = up   (sw.erl:72-77)
+        int k0 = -8 * (i0 + r + 1) + 2;             // column 0: V = -(i+1), dir = up   (sw.erl:72-77)
         if (MASKED && r < rmin) k0 = 0;
-        mleft[r] = k0 & ~7;
-        lfv[r] = mleft[r];
-        mx[r] = k0;
+        S.mleft[r] = both(k0 & ~7);
+        S.left15[r] = __vadd2(S.mleft[r], 0xFFF1FFF1u);
+        S.mx[r] = both(k0);
     }
-    int mD_top = (int)row[0] & ~7;                  // K(i0-1, 0)
-    row[0] = (int16_t)(-8 * (i0 + SW_R) + 2);       // K(last row of the strip, 0)
-    uint32_t rw = 0;
-    for (int j = 1; j <= lr; j++) {
-        const int kt = row[j * B];
-        const int mT = kt & ~7;
-        int uup = mT + ((kt & 2) << 2);
-        if (((j - 1) & 15) == 0) rw = refw[((j - 1) >> 4) * B];
-        const uint32_t sel = (rw & 3u) * 0x1111u + 0x8880u;   // PRMT selector: byte b, sign-extended
-        rw >>= 2;
-        int mdiag = mD_top;
-        uint32_t dw = 0;
-        int K = 0;
-#pragma unroll
-        for (int r = 0; r < SW_R; r++) {
-            const int s = prmt_sext_byte(prof[r], sel);                  // 8*sigma + 4
-            const int x = __viaddmax_s32(lfv[r], -15, mdiag + s);      // max(left, diag)
-            K = __viaddmax_s32(uup, -14, x);                           // max(up, .)
-            if (MASKED) K = (r >= rmin) ? K : 0;
-            mdiag = mleft[r];
-            const int m = K & ~7;
-            mleft[r] = m;
-            lfv[r] = m + ((K & 1) << 3);
-            uup = m + ((K & 2) << 2);
-            mx[r] = max(mx[r], K);
-            dw |= (uint32_t)(K & 7) << (3 * r);
+    uint32_t mD_top = row[0] & 0xFFF8FFF8u;         // K(i0-1, 0)
+    row[0] = both(-8 * (i0 + SW_R) + 2);            // K(last row of the strip, 0)
+    sw_cols<MASKED, false>(row, refw, dstrip, 1, lr_min, rmin, 0u, profA, profB, S, mD_top);
+    sw_cols<MASKED, true>(row, refw, dstrip, lr_min + 1, lr_max, rmin, capv, profA, profB, S, mD_top);
+}
+
+// traceback of one lane (sw.erl:116-160) + CIGAR text; returns false when the run buffer overflowed
+__device__ __forceinline__ bool sw_traceback(const SwFastParams &p, const uint2 *dirs, uint32_t *runs, int lane, int lq,
+                                             int lr, int i_first, int j, int vmax, uint32_t cand) {
+    constexpr int B = SW_BLOCK;
+    int i = lq, nr = 0, cur = -1, len = 0;
+    bool ovf = false;
+    while (i > 0) {
+        int op;                                               // 0 = M (up_left), 1 = D (left), 2 = I (up)
+        if (j == 0) op = 2;
+        else {
+            int t = i - i_first, s = t / SW_R, r = t - s * SW_R;
+            uint2 w = dirs[((size_t)s * p.cap_cols + j) * B];
+            uint32_t code = ((r < 5 ? w.x >> (3 * r) : w.y >> (3 * (r - 5))) >> (16 * lane)) & 7u;
+            op = code == 4u ? 0 : code == 2u ? 2 : 1;
         }
-        mD_top = mT;
-        row[j * B] = (int16_t)K;
-        dstrip[j * B] = dw;
+        if (op == cur) len++;
+        else {
+            if (cur >= 0) { if (nr < p.cap_cols) runs[nr * B] = (uint32_t)((len << 2) | cur); else ovf = true; nr++; }
+            cur = op; len = 1;
+        }
+        if (op == 0) { i--; j--; } else if (op == 2) i--; else j--;
     }
+    if (nr < p.cap_cols) runs[nr * B] = (uint32_t)((len << 2) | cur); else ovf = true;
+    nr++;
+    if (ovf) return false;
+    int clen = 0;
+    for (int k = 0; k < nr; k++) {
+        int l = (int)(runs[k * B] >> 2);
+        clen += 2 + (l >= 10) + (l >= 100) + (l >= 1000) + (l >= 10000);
+    }
+    uint32_t off = atomicAdd(&p.ctr->cig_used, (uint32_t)clen);
+    if ((uint64_t)off + clen <= p.cig_cap) {
+        char *c = p.cig + off;
+        for (int k = nr - 1; k >= 0; k--) {
+            int v = (int)runs[k * B];
+            int l = v >> 2, op = v & 3;
+            int nd = 1 + (l >= 10) + (l >= 100) + (l >= 1000) + (l >= 10000);
+            for (int t = nd - 1; t >= 0; t--) { c[t] = (char)('0' + l % 10); l /= 10; }
+            c[nd] = op == 0 ? 'M' : op == 1 ? 'D' : 'I';
+            c += nd + 1;
+        }
+    } else atomicExch(&p.ctr->cig_overflow, 1u);
+    SwOut o;
+    o.score = vmax; o.status = BWT_HIT_MATCH; o.cigar_len = clen; o.cigar_off = off;
+    p.out[cand] = o;
+    return true;
+}
+
+// stage a window as 2-bit codes ((c>>1)&3: A0 C1 T2 G3) into slot `lane` of refw; returns false if not plain ACGT
+__device__ __forceinline__ bool sw_stage(const SwFastParams &p, const SwDesc &d, uint32_t *refw, int lane) {
+    constexpr int B = SW_BLOCK;
+    const uint8_t *q = p.qbase + d.q_off;
+    const uint8_t *w = p.rbase + d.r_off;
+    bool plain = true;
+    for (int j0 = 0; j0 < d.lr; j0 += 16) {
+        uint32_t word = 0;
+        for (int t = 0; t < 16 && j0 + t < d.lr; t++) {
+            uint8_t c = w[j0 + t];
+            plain &= is_acgt(c);
+            word |= (uint32_t)((c >> 1) & 3) << (2 * t);
+        }
+        refw[(2 * (j0 >> 4) + lane) * B] = word;
+    }
+    for (int i = 0; i < d.lq; i++) plain &= is_acgt(q[i]);
+    return plain;
 }
 
 __global__ void __launch_bounds__(SW_BLOCK) sw_fast_kernel(SwFastParams p) {
@@ -130,117 +225,92 @@ __global__ void __launch_bounds__(SW_BLOCK) sw_fast_kernel(SwFastParams p) {
     constexpr int B = SW_BLOCK;
     constexpr int R = SW_R;
     const int tid = threadIdx.x;
-    int16_t *row = reinterpret_cast<int16_t *>(smem) + tid;                              // row[j*B]
-    uint32_t *refw = smem + (p.cap_cols * B) / 2 + tid;                                  // refw[w*B]
-    uint32_t *dirs = p.dirs + (size_t)blockIdx.x * p.max_strips * p.cap_cols * B + tid;  // dirs[(s*cap+j)*B]
-    const uint32_t n_list = p.ctr->n_fast;
+    uint32_t *row = smem + tid;                                                         // row[j*B]: both pairs' keys
+    uint32_t *refw = smem + p.cap_cols * B + tid;                                       // refw[(2w+lane)*B]
+    uint2 *dirs = p.dirs + (size_t)blockIdx.x * p.max_strips * p.cap_cols * B + tid;    // dirs[(s*cap+j)*B]
+    const uint32_t n_list = *p.n_list;
+    const uint32_t n_units = (n_list + 1) / 2;
     unsigned long long calls = 0, cells = 0;
-#ifdef BWT_KDEBUG
-    if (tid == 0 && blockIdx.x == 0)
-        printf("KDEBUG sw_fast: n_list=%u cap_cols=%d max_strips=%d dirs=%p cig=%p cig_cap=%u desc=%p list=%p out=%p q=%p r=%p\n", n_list,
-               p.cap_cols, p.max_strips, p.dirs, p.cig, p.cig_cap, p.desc, p.list, p.out, p.qbase, p.rbase);
-#endif
 
-    for (uint32_t it = blockIdx.x * B + tid; it < n_list; it += gridDim.x * B) {
-        const uint32_t cand = p.list[it];
-        const SwDesc d = p.desc[cand];
-        const uint8_t *q = p.qbase + d.q_off;
-        const uint8_t *w = p.rbase + d.r_off;
-        const int lq = d.lq, lr = d.lr;
-        KD_CHECK(lq >= 1 && lr >= 1 && lr + 1 <= p.cap_cols && (lq + R - 1) / R <= p.max_strips, "cand=%u lq=%d lr=%d", cand, lq, lr);
-        // stage the window as 2-bit codes ((c>>1)&3: A0 C1 T2 G3) and validate both strings
-        bool plain = true;
-        for (int j0 = 0; j0 < lr; j0 += 16) {
-            uint32_t word = 0;
-            for (int t = 0; t < 16 && j0 + t < lr; t++) {
-                uint8_t c = w[j0 + t];
-                plain &= is_acgt(c);
-                word |= (uint32_t)((c >> 1) & 3) << (2 * t);
+    for (uint32_t unit = blockIdx.x * B + tid; unit < n_units; unit += gridDim.x * B) {
+        uint32_t c0 = p.list[2 * unit];
+        uint32_t c1 = 2 * unit + 1 < n_list ? p.list[2 * unit + 1] : 0xFFFFFFFFu;
+        // a unit is processed as one packed pass when both pairs have the same query length, else as two passes
+        for (int pass = 0; pass < 2; pass++) {
+            uint32_t candA, candB;
+            if (pass == 0) {
+                candA = c0; candB = c1;
+                if (c1 != 0xFFFFFFFFu && p.desc[c0].lq != p.desc[c1].lq) candB = 0xFFFFFFFFu;
+                else c1 = 0xFFFFFFFFu;                                  // nothing left for the second pass
+            } else {
+                if (c1 == 0xFFFFFFFFu) break;
+                candA = c1; candB = 0xFFFFFFFFu;
             }
-            refw[(j0 >> 4) * B] = word;
-        }
-        for (int i = 0; i < lq; i++) plain &= is_acgt(q[i]);
-        if (!plain) {                                // 'N' / IUPAC: the double-precision kernel takes it
-            p.list_gen[atomicAdd(&p.ctr->n_general, 1u)] = cand;
-            continue;
-        }
-        for (int j = 0; j <= lr; j++) row[j * B] = 0;            // row 0: {0,undef}  (sw.erl:61)
-        const int nstr = (lq + R - 1) / R;
-        const int i_first = lq - nstr * R + 1;                    // row number of strip 0, r = 0 (<= 1)
-        const int thr0 = -2 * (lq / 2);                           // sw.erl:62
-        int rows_done = lq;
-        bool failed = false;
-        int mx[R];
-        for (int s = 0; s < nstr; s++) {
-            const int i0 = i_first + s * R;
-            uint32_t prof[R];
+            SwDesc dA = p.desc[candA], dB = dA;
+            KD_CHECK(dA.lq >= 1 && dA.lr >= 1 && dA.lr + 1 <= p.cap_cols && (dA.lq + R - 1) / R <= p.max_strips, "cand=%u lq=%d lr=%d", candA, dA.lq, dA.lr);
+            if (!sw_stage(p, dA, refw, 0)) { p.list_gen[atomicAdd(&p.ctr->n_general, 1u)] = candA; candA = 0xFFFFFFFFu; }
+            if (candB != 0xFFFFFFFFu) {
+                dB = p.desc[candB];
+                if (!sw_stage(p, dB, refw, 1)) { p.list_gen[atomicAdd(&p.ctr->n_general, 1u)] = candB; candB = 0xFFFFFFFFu; }
+            }
+            if (candA == 0xFFFFFFFFu && candB == 0xFFFFFFFFu) continue;
+            if (candA == 0xFFFFFFFFu) { candA = candB; dA = dB; candB = 0xFFFFFFFFu; sw_stage(p, dA, refw, 0); }
+            if (candB == 0xFFFFFFFFu) { dB = dA; sw_stage(p, dB, refw, 1); }      // single: lane B shadows lane A
+            const uint8_t *qA = p.qbase + dA.q_off, *qB = p.qbase + dB.q_off;
+            const int lq = dA.lq, lrA = dA.lr, lrB = dB.lr;
+            const int lr_min = min(lrA, lrB), lr_max = max(lrA, lrB);
+            const uint32_t capv = (lrA > lr_min ? 0x7FFFu : 0x8000u) | ((lrB > lr_min ? 0x7FFFu : 0x8000u) << 16);
+            for (int j = 0; j <= lr_max; j++) row[j * B] = 0;            // row 0: {0,undef}  (sw.erl:61)
+            const int nstr = (lq + R - 1) / R;
+            const int i_first = lq - nstr * R + 1;                       // row number of strip 0, r = 0 (<= 1)
+            const int thr0 = -2 * (lq / 2);                              // sw.erl:62
+            int rowsA = lq, rowsB = lq;
+            bool failA = false, failB = false;
+            StripState S;
+            for (int s = 0; s < nstr; s++) {
+                const int i0 = i_first + s * R;
+                uint32_t profA[R], profB[R];
 #pragma unroll
-            for (int r = 0; r < R; r++) {
-                int i = i0 + r;
-                uint32_t qc = (i >= 1) ? ((q[i - 1] >> 1) & 3u) : 0u;
-                prof[r] = 0xFCFCFCFCu ^ (0xE8u << (8 * qc));      // byte qc = 20 (match), others = -4 (mismatch)
-            }
-            uint32_t *dstrip = dirs + (size_t)s * p.cap_cols * B;
-            if (i0 < 1) sw_strip<true>(row, refw, dstrip, lr, i0, prof, mx);
-            else sw_strip<false>(row, refw, dstrip, lr, i0, prof, mx);
-            // row threshold (sw.erl:69-71): Vmax of row i must reach thr0 + 2*i
+                for (int r = 0; r < R; r++) {
+                    int i = i0 + r;
+                    uint32_t qa = (i >= 1) ? ((qA[i - 1] >> 1) & 3u) : 0u, qb = (i >= 1) ? ((qB[i - 1] >> 1) & 3u) : 0u;
+                    profA[r] = 0xFCFCFCFCu ^ (0xE8u << (8 * qa));        // byte qa = 20 (match), others = -4 (mismatch)
+                    profB[r] = 0xFCFCFCFCu ^ (0xE8u << (8 * qb));
+                }
+                uint2 *dstrip = dirs + (size_t)s * p.cap_cols * B;
+                if (i0 < 1) sw_strip<true>(row, refw, dstrip, lr_min, lr_max, capv, i0, profA, profB, S);
+                else sw_strip<false>(row, refw, dstrip, lr_min, lr_max, capv, i0, profA, profB, S);
+                // row threshold (sw.erl:69-71): Vmax of row i must reach thr0 + 2*i
 #pragma unroll
-            for (int r = 0; r < R; r++) {
-                int i = i0 + r;
-                if (i >= 1 && !failed && (mx[r] >> 3) < thr0 + 2 * i) { failed = true; rows_done = i; }
+                for (int r = 0; r < R; r++) {
+                    int i = i0 + r;
+                    if (i >= 1) {
+                        if (!failA && (lane16(S.mx[r], 0) >> 3) < thr0 + 2 * i) { failA = true; rowsA = i; }
+                        if (!failB && (lane16(S.mx[r], 1) >> 3) < thr0 + 2 * i) { failB = true; rowsB = i; }
+                    }
+                }
+                if (failA && failB) break;
             }
-            if (failed) break;
+            calls += 1 + (candB != 0xFFFFFFFFu);
+            cells += (unsigned long long)rowsA * (unsigned)lrA + (candB != 0xFFFFFFFFu ? (unsigned long long)rowsB * (unsigned)lrB : 0ull);
+            SwOut o;
+            o.score = 0; o.status = BWT_HIT_NO_MATCH; o.cigar_len = 0; o.cigar_off = 0;
+            // leftmost maximum of the last row (sw.erl:110-112), for both lanes before the row buffer is reused
+            const int vmaxA = lane16(S.mx[R - 1], 0) >> 3, vmaxB = lane16(S.mx[R - 1], 1) >> 3;
+            int jA = 0, jB = 0;
+            if (!failA) while ((lane16(row[jA * B], 0) >> 3) != vmaxA) { jA++; KD_CHECK(jA <= lrA, "cand=%u vmax=%d", candA, vmaxA); }
+            if (!failB && candB != 0xFFFFFFFFu) while ((lane16(row[jB * B], 1) >> 3) != vmaxB) { jB++; KD_CHECK(jB <= lrB, "cand=%u vmax=%d", candB, vmaxB); }
+            if (failA) p.out[candA] = o;
+            else if (!sw_traceback(p, dirs, row, 0, lq, lrA, i_first, jA, vmaxA, candA)) {
+                p.list_gen[atomicAdd(&p.ctr->n_general, 1u)] = candA; calls--; cells -= (unsigned long long)rowsA * (unsigned)lrA;
+            }
+            if (candB != 0xFFFFFFFFu) {
+                if (failB) p.out[candB] = o;
+                else if (!sw_traceback(p, dirs, row, 1, lq, lrB, i_first, jB, vmaxB, candB)) {
+                    p.list_gen[atomicAdd(&p.ctr->n_general, 1u)] = candB; calls--; cells -= (unsigned long long)rowsB * (unsigned)lrB;
+                }
+            }
         }
-        calls++;
-        cells += (unsigned long long)rows_done * (unsigned)lr;
-        SwOut o;
-        o.score = 0; o.status = BWT_HIT_NO_MATCH; o.cigar_len = 0; o.cigar_off = 0;
-        if (failed) { p.out[cand] = o; continue; }
-        const int vmax = mx[R - 1] >> 3;
-        int j = 0;
-        while ((row[j * B] >> 3) != vmax) { j++; KD_CHECK(j <= lr, "cand=%u vmax=%d lq=%d lr=%d", cand, vmax, lq, lr); }   // leftmost maximum of the last row (sw.erl:110-112)
-        // traceback (sw.erl:116-160); runs are pushed newest-first into the (now free) shared row
-        uint16_t *runs = reinterpret_cast<uint16_t *>(row);
-        int i = lq, nr = 0, cur = -1, len = 0;
-        bool ovf = false;
-        while (i > 0) {
-            KD_CHECK(j >= 0 && j <= lr && i <= lq, "traceback cand=%u i=%d j=%d", cand, i, j);
-            int op;                                               // 0 = M (up_left), 1 = D (left), 2 = I (up)
-            if (j == 0) op = 2;
-            else {
-                int t = i - i_first, s = t / R, r = t - s * R;
-                uint32_t code = (dirs[((size_t)s * p.cap_cols + j) * B] >> (3 * r)) & 7u;
-                op = code == 4u ? 0 : code == 2u ? 2 : 1;
-            }
-            if (op == cur) len++;
-            else {
-                if (cur >= 0) { if (nr < p.cap_cols) runs[nr * B] = (uint16_t)((len << 2) | cur); else ovf = true; nr++; }
-                cur = op; len = 1;
-            }
-            if (op == 0) { i--; j--; } else if (op == 2) i--; else j--;
-        }
-        if (nr < p.cap_cols) runs[nr * B] = (uint16_t)((len << 2) | cur); else ovf = true;
-        nr++;
-        if (ovf) { p.list_gen[atomicAdd(&p.ctr->n_general, 1u)] = cand; calls--; cells -= (unsigned long long)rows_done * (unsigned)lr; continue; }
-        int clen = 0;
-        for (int k = 0; k < nr; k++) {
-            int l = runs[k * B] >> 2;
-            clen += 2 + (l >= 10) + (l >= 100) + (l >= 1000) + (l >= 10000);
-        }
-        uint32_t off = atomicAdd(&p.ctr->cig_used, (uint32_t)clen);
-        if ((uint64_t)off + clen <= p.cig_cap) {
-            char *c = p.cig + off;
-            for (int k = nr - 1; k >= 0; k--) {
-                int v = runs[k * B];
-                int l = v >> 2, op = v & 3;
-                int nd = 1 + (l >= 10) + (l >= 100) + (l >= 1000) + (l >= 10000);
-                for (int t = nd - 1; t >= 0; t--) { c[t] = (char)('0' + l % 10); l /= 10; }
-                c[nd] = op == 0 ? 'M' : op == 1 ? 'D' : 'I';
-                c += nd + 1;
-            }
-        } else atomicExch(&p.ctr->cig_overflow, 1u);
-        o.score = vmax; o.status = BWT_HIT_MATCH; o.cigar_len = clen; o.cigar_off = off;
-        p.out[cand] = o;
     }
     for (int dlt = 16; dlt > 0; dlt >>= 1) {
         calls += __shfl_down_sync(0xFFFFFFFFu, calls, dlt);
@@ -386,12 +456,13 @@ int grow(T *&p, size_t &cap_items, size_t need_items) {
 int sw_stage_reserve(SwStage &st, uint32_t pairs) {
     if (pairs <= st.cap && st.d_desc) return BWT_OK;
     uint32_t want = pairs + pairs / 4 + 1024;
-    if (st.d_desc) { cudaFree(st.d_desc); cudaFree(st.d_out); cudaFree(st.d_list_fast); cudaFree(st.d_list_gen); }
-    st.d_desc = nullptr; st.d_out = nullptr; st.d_list_fast = nullptr; st.d_list_gen = nullptr;
+    if (st.d_desc) { cudaFree(st.d_desc); cudaFree(st.d_out); cudaFree(st.d_list_fast); cudaFree(st.d_list_wide); cudaFree(st.d_list_gen); }
+    st.d_desc = nullptr; st.d_out = nullptr; st.d_list_fast = nullptr; st.d_list_wide = nullptr; st.d_list_gen = nullptr;
     st.cap = 0;
     CU_TRY(cudaMalloc(&st.d_desc, (size_t)want * sizeof(SwDesc)));
     CU_TRY(cudaMalloc(&st.d_out, (size_t)want * sizeof(SwOut)));
     CU_TRY(cudaMalloc(&st.d_list_fast, (size_t)want * sizeof(uint32_t)));
+    CU_TRY(cudaMalloc(&st.d_list_wide, (size_t)want * sizeof(uint32_t)));
     CU_TRY(cudaMalloc(&st.d_list_gen, (size_t)want * sizeof(uint32_t)));
     if (!st.d_ctr) {
         CU_TRY(cudaMalloc(&st.d_ctr, sizeof(SwCounters)));
@@ -410,7 +481,7 @@ int sw_stage_reserve(SwStage &st, uint32_t pairs) {
 }
 
 void sw_stage_free(SwStage &st) {
-    cudaFree(st.d_desc); cudaFree(st.d_out); cudaFree(st.d_list_fast); cudaFree(st.d_list_gen);
+    cudaFree(st.d_desc); cudaFree(st.d_out); cudaFree(st.d_list_fast); cudaFree(st.d_list_wide); cudaFree(st.d_list_gen);
     cudaFree(st.d_ctr); if (st.h_ctr) cudaFreeHost(st.h_ctr);
     if (st.ev_k0) cudaEventDestroy(st.ev_k0);
     if (st.ev_k1) cudaEventDestroy(st.ev_k1);
@@ -424,37 +495,51 @@ int sw_stage_run(SwStage &st, const uint8_t *d_qbase, const uint8_t *d_rbase, ui
     st.ms_fast_kernel = 0;
     if (n == 0) return BWT_OK;
     if (n > st.cap) { bwt_set_error("sw_stage_run: %u pairs exceed the reserved %u", n, st.cap); return BWT_ERR_ARG; }
-    // shared-memory tier: columns = longest query + 1 + 64 slack, multiple of 16, capped by the 227 KB CTA limit
-    int cap_cols = ((max_lq + 1 + 64) + 15) & ~15;
-    const int cap_limit = 688;
-    if (cap_cols > cap_limit) cap_cols = cap_limit;
+    // two shared-memory tiers of the fast kernel: "narrow" holds windows up to Lq + 15 columns (almost every
+    // candidate: D is the summed gap of the voting chain), "wide" up to Lq + 64; anything wider takes the general path
+    const int cap_limit = 400;                           // 128 threads x 4.5 B x columns <= 227 KB, multiple of 16
+    int cap_narrow = std::min(cap_limit, ((max_lq + 1 + 15) + 15) & ~15);
+    int cap_wide = std::min(cap_limit, ((max_lq + 1 + 64) + 15) & ~15);
     int max_strips = (std::min(max_lq, SW_FAST_MAX_LQ) + SW_R - 1) / SW_R;
     if (max_strips < 1) max_strips = 1;
-    size_t smem = (size_t)SW_BLOCK * (cap_cols * 2 + (cap_cols / 16) * 4);
-    CU_TRY(cudaFuncSetAttribute(sw_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int per_sm = 0;
-    CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sw_fast_kernel, SW_BLOCK, smem));
-    if (per_sm < 1) { bwt_set_error("sw_fast_kernel does not fit an SM with %zu B of shared memory", smem); return BWT_ERR_CUDA; }
     int sms = 0;
     CU_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, st.device));
-    unsigned grid = (unsigned)std::min<uint64_t>((n + SW_BLOCK - 1) / SW_BLOCK, (uint64_t)sms * per_sm);
-    size_t need_dirs = (size_t)grid * SW_BLOCK * max_strips * cap_cols;
+    auto smem_of = [](int cap) { return (size_t)SW_BLOCK * ((size_t)cap * 4 + (size_t)(cap / 16) * 8); };
+    CU_TRY(cudaFuncSetAttribute(sw_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_of(cap_wide)));
+    unsigned grid[2];
+    const int caps[2] = {cap_narrow, cap_wide};
+    size_t need_dirs = 0;
+    for (int t = 0; t < 2; t++) {
+        int per_sm = 0;
+        CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sw_fast_kernel, SW_BLOCK, smem_of(caps[t])));
+        if (per_sm < 1) { bwt_set_error("sw_fast_kernel does not fit an SM with %zu B of shared memory", smem_of(caps[t])); return BWT_ERR_CUDA; }
+        uint64_t units = ((uint64_t)n + 1) / 2;
+        grid[t] = (unsigned)std::min<uint64_t>((units + SW_BLOCK - 1) / SW_BLOCK, (uint64_t)sms * per_sm);
+        need_dirs = std::max(need_dirs, (size_t)grid[t] * SW_BLOCK * max_strips * caps[t]);
+    }
     BWT_TRY(grow(st.d_dirs, st.dirs_words, need_dirs));
 
     for (int attempt = 0; attempt < 4; attempt++) {
         CU_TRY(cudaMemsetAsync(st.d_ctr, 0, sizeof(SwCounters), stream));
-        sw_classify_kernel<<<(n + 255) / 256, 256, 0, stream>>>(st.d_desc, st.d_out, n, cap_cols, st.d_list_fast,
-                                                                st.d_list_gen, st.d_ctr);
+        sw_classify_kernel<<<(n + 255) / 256, 256, 0, stream>>>(st.d_desc, st.d_out, n, cap_narrow, cap_wide, st.d_list_fast,
+                                                                st.d_list_wide, st.d_list_gen, st.d_ctr);
         K_CHECK(stream, "sw_classify_kernel");
         SwFastParams p;
-        p.qbase = d_qbase; p.rbase = d_rbase; p.desc = st.d_desc; p.list = st.d_list_fast; p.out = st.d_out;
+        p.qbase = d_qbase; p.rbase = d_rbase; p.desc = st.d_desc; p.out = st.d_out;
         p.list_gen = st.d_list_gen; p.ctr = st.d_ctr; p.cig = st.d_cig_tmp; p.cig_cap = st.cig_cap;
-        p.dirs = st.d_dirs; p.cap_cols = cap_cols; p.max_strips = max_strips;
+        p.dirs = st.d_dirs; p.max_strips = max_strips;
         CU_TRY(cudaEventRecord(st.ev_k0, stream));
-        sw_fast_kernel<<<grid, SW_BLOCK, smem, stream>>>(p);
+        p.list = st.d_list_fast; p.n_list = &st.d_ctr->n_fast; p.cap_cols = cap_narrow;
+        sw_fast_kernel<<<grid[0], SW_BLOCK, smem_of(cap_narrow), stream>>>(p);
+        K_CHECK(stream, "sw_fast_kernel (narrow)");
+        if (cap_wide > cap_narrow) {                     // usually finds an empty list and returns at once
+            p.list = st.d_list_wide; p.n_list = &st.d_ctr->n_wide; p.cap_cols = cap_wide;
+            sw_fast_kernel<<<grid[1], SW_BLOCK, smem_of(cap_wide), stream>>>(p);
+            K_CHECK(stream, "sw_fast_kernel (wide)");
+            st.launches += 1;
+        }
         CU_TRY(cudaEventRecord(st.ev_k1, stream));
         st.launches += 2;
-        K_CHECK(stream, "sw_fast_kernel");
         CU_TRY(cudaMemcpyAsync(st.h_ctr, st.d_ctr, sizeof(SwCounters), cudaMemcpyDeviceToHost, stream));
         CU_TRY(cudaStreamSynchronize(stream));
         uint32_t ng = st.h_ctr->n_general;

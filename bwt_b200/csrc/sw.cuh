@@ -18,14 +18,14 @@ struct SwOut {           // 16 B per pair
 
 struct SwCounters {
     unsigned long long sw_calls, cells;
-    uint32_t n_fast, n_general;      // list cursors
+    uint32_t n_fast, n_wide, n_general, pad0;   // list cursors
     uint32_t cig_used, cig_overflow; // temporary CIGAR arena
     uint32_t general_done, pad;
 };
 
 constexpr int SW_R = 10;             // rows per register strip; ten 3-bit direction codes per 32-bit word
 constexpr int SW_BLOCK = 128;
-constexpr int SW_FAST_MAX_LQ = 1000; // int16 keys: |8V+7| <= 8*2*Lq+7 < 32768
+constexpr int SW_FAST_MAX_LQ = 1000; // int16 keys: |8V+7| + 20 <= 8*2*Lq+27 < 32768
 
 // Device-resident state of the extension stage (owned by a batch).
 struct SwStage {
@@ -33,11 +33,11 @@ struct SwStage {
     uint32_t cap = 0;                // pairs
     SwDesc *d_desc = nullptr;
     SwOut *d_out = nullptr;
-    uint32_t *d_list_fast = nullptr, *d_list_gen = nullptr;
+    uint32_t *d_list_fast = nullptr, *d_list_wide = nullptr, *d_list_gen = nullptr;
     SwCounters *d_ctr = nullptr, *h_ctr = nullptr;     // h_ctr pinned
     char *d_cig_tmp = nullptr;
     uint32_t cig_cap = 0;
-    uint32_t *d_dirs = nullptr;
+    uint2 *d_dirs = nullptr;          // direction scratch: one uint2 per (strip, column, thread)
     size_t dirs_words = 0;
     uint8_t *d_gen_scratch = nullptr;
     size_t gen_scratch_bytes = 0;

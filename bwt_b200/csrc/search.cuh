@@ -76,37 +76,27 @@ __device__ __forceinline__ void first_interval(const DevIndex &ix, int c, uint32
     else { sp = ix.P[3]; ep = ix.last; }
 }
 
-// bwa:find_seeds/6 on q[0..len), len >= 1.  use_table: consult the k-mer tables (false while building them).
-__device__ __forceinline__ SearchRes search_sub(const DevIndex &ix, const uint8_t *q, int len, bool use_table) {
+// bwa:find_seeds/6 on q[0..len), len >= 1, once the characters next to the end are known as 2-bit codes:
+// c = code of the last character ('N' counts as 'A'), idx = codes of the last `good` characters (last one in
+// bits 0-1), all of them plain ACGT.  use_table: consult the k-mer tables (false while building them).
+__device__ __forceinline__ SearchRes search_core(const DevIndex &ix, const uint8_t *q, int len, int c, uint32_t idx,
+                                                 int good, bool use_table) {
     SearchRes R;
     R.table = 0;
-    uint8_t h = q[len - 1];
-    int c = (h == 'N') ? 0 : bwt_code(h);
-    if (c < 0) { R.sp = R.ep = 0; R.n = 0; R.status = BWT_SEARCH_CRASH; return R; }   // case_clause
     uint32_t sp = 0, ep = 0;
     int n = 1, k = len - 2;
     bool have = false, stopped = false;
-    if (use_table && len >= BWT_MIN_LEN) {
+    if (use_table && good >= BWT_MIN_LEN) {
         // the table of depth d applies when the d-1 characters before the last are plain ACGT
-        const int dk = (ix.deep_k > 0 && len >= ix.deep_k) ? ix.deep_k : BWT_MIN_LEN;
-        uint32_t idx = (uint32_t)c;
-        int good = 1;                                  // leading characters (from the end) that are ACGT
-        for (int t = 1; t < dk; t++) {
-            int ct = bwt_code(q[len - 1 - t]);
-            if (ct < 0) break;
-            idx |= (uint32_t)ct << (2 * t);
-            good++;
-        }
-        int depth = good >= dk ? dk : (good >= BWT_MIN_LEN ? BWT_MIN_LEN : 0);
-        if (depth) {
-            uint2 e = depth == BWT_MIN_LEN ? __ldg(ix.kmer + (idx & 0xFFFFu)) : __ldg(ix.kmer_deep + idx);
-            int ne = (int)(e.y >> 28);
-            if (ne) {
-                R.table = ne;                          // characters whose steps the table served
-                sp = e.x; ep = e.x + (e.y & KMER_W_MASK); n = ne; k = len - 1 - ne;
-                have = true;
-                stopped = ne < depth;                  // not_found inside the table's reach
-            }
+        const int depth = (ix.deep_k > 0 && good >= ix.deep_k) ? ix.deep_k : BWT_MIN_LEN;
+        uint2 e = depth == BWT_MIN_LEN ? __ldg(ix.kmer + (idx & 0xFFFFu))
+                                       : __ldg(ix.kmer_deep + (idx & ((1u << (2 * depth)) - 1u)));
+        int ne = (int)(e.y >> 28);
+        if (ne) {
+            R.table = ne;                              // characters whose steps the table served
+            sp = e.x; ep = e.x + (e.y & KMER_W_MASK); n = ne; k = len - 1 - ne;
+            have = true;
+            stopped = ne < depth;                      // not_found inside the table's reach
         }
     }
     if (!have) first_interval(ix, c, sp, ep);
@@ -134,4 +124,27 @@ __device__ __forceinline__ SearchRes search_sub(const DevIndex &ix, const uint8_
     if (checked && ep - sp > BWT_MAX_RANGE) R.status = BWT_TOO_MANY_SEEDS;
     else R.status = n >= BWT_MIN_LEN ? BWT_SEEDS : BWT_NO_SEEDS;
     return R;
+}
+
+// bwa:find_seeds/6 on q[0..len), len >= 1, from the ASCII bytes
+__device__ __forceinline__ SearchRes search_sub(const DevIndex &ix, const uint8_t *q, int len, bool use_table) {
+    uint8_t h = q[len - 1];
+    int c = (h == 'N') ? 0 : bwt_code(h);
+    if (c < 0) {                                       // case_clause (bwa.erl:15-24)
+        SearchRes R;
+        R.sp = R.ep = 0; R.n = 0; R.status = BWT_SEARCH_CRASH; R.table = 0;
+        return R;
+    }
+    uint32_t idx = (uint32_t)c;
+    int good = 1;                                      // characters from the end that are plain ACGT
+    if (use_table) {
+        const int want = len < BWT_MAX_LEN ? len : BWT_MAX_LEN;
+        for (int t = 1; t < want; t++) {
+            int ct = bwt_code(q[len - 1 - t]);
+            if (ct < 0) break;
+            idx |= (uint32_t)ct << (2 * t);
+            good++;
+        }
+    }
+    return search_core(ix, q, len, c, idx, good, use_table);
 }

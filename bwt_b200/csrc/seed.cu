@@ -277,6 +277,224 @@ __device__ __forceinline__ int sga_read(const Tile &tile, const DevIndex &ix, co
     return SGA_DONE;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Fast path of sga:sga/6 for the common read: plain ACGT, at most 8*G seed ends.
+//   * the read is packed once into 2-bit codes, REVERSED (base lq-1-i at bits 2i), in shared memory, so the k-mer
+//     table index of the subsequence that ends 8k bases before the read's end is one funnel shift at bit 16k
+//   * seed ends are located into shared memory by all lanes (balanced over the rows of all intervals), then sorted
+//     in REGISTERS (bitonic network, EPL consecutive elements per lane, shuffles across lanes) and voted there with
+//     a segmented scan -- no shared-memory sort, no second voting pass
+// ---------------------------------------------------------------------------------------------------
+enum { SGA_FALLBACK = 2 };
+
+template <int G, int EPL, typename Tile>
+__device__ __forceinline__ void reg_bitonic(const Tile &tile, uint32_t (&v)[EPL], const int lane) {
+    constexpr int P = G * EPL;
+#pragma unroll
+    for (int k = 2; k <= P; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            if (j >= EPL) {                                      // partner in another lane, same register
+                const int lj = j / EPL;
+                const bool up = ((lane * EPL) & k) == 0;
+                const bool keep_min = ((lane & lj) == 0) == up;
+#pragma unroll
+                for (int r = 0; r < EPL; r++) {
+                    const uint32_t o = tile.shfl_xor(v[r], lj);
+                    v[r] = keep_min ? min(v[r], o) : max(v[r], o);
+                }
+            } else {                                             // partner in this lane
+#pragma unroll
+                for (int r = 0; r < EPL; r++) {
+                    if ((r & j) == 0) {
+                        const bool up = (k >= EPL) ? (((lane * EPL) & k) == 0) : ((r & k) == 0);
+                        const uint32_t a = v[r], b = v[r | j];
+                        const uint32_t lo = min(a, b), hi = max(a, b);
+                        v[r] = up ? lo : hi;
+                        v[r | j] = up ? hi : lo;
+                    }
+                }
+            }
+        }
+    }
+}
+
+// sort + get_similar/7 (sga.erl:45-64) on `total` seed ends in shared memory; emits the clusters
+template <int G, int EPL, typename Tile>
+__device__ __forceinline__ void sort_vote_regs(const Tile &tile, const uint32_t *seeds, const uint32_t total,
+                                               const uint32_t need, const uint32_t read, uint32_t *ncl, uint32_t *cl_base,
+                                               Cluster *clusters, const uint32_t cl_cap, SeedCounters *ctr,
+                                               unsigned long long *s_ctr) {
+    const int lane = tile.thread_rank();
+    uint32_t v[EPL];
+#pragma unroll
+    for (int r = 0; r < EPL; r++) {
+        const uint32_t i = (uint32_t)lane * EPL + r;
+        v[r] = i < total ? seeds[i] : 0xFFFFFFFFu;
+    }
+    reg_bitonic<G, EPL>(tile, v, lane);
+    // chain breaks: element i opens a chain when it is the first or lies more than TOLERANCE after its predecessor
+    const uint32_t prev_last = tile.shfl_up(v[EPL - 1], 1);
+    const uint32_t next_first = tile.shfl_down(v[0], 1);
+    bool f = false;                                              // lane summary: start of the chain running at its end
+    uint32_t sv = 0, si = 0;
+    uint32_t brk = 0;
+#pragma unroll
+    for (int r = 0; r < EPL; r++) {
+        const uint32_t i = (uint32_t)lane * EPL + r;
+        const uint32_t pv = r ? v[r - 1] : prev_last;
+        const bool b = (i == 0) || (v[r] - pv > BWT_TOLERANCE);
+        brk |= (uint32_t)b << r;
+        if (b) { f = true; sv = v[r]; si = i; }
+    }
+#pragma unroll
+    for (int d = 1; d < G; d <<= 1) {                            // inclusive scan: nearest chain start at or before the lane's end
+        const bool f2 = tile.shfl_up(f, d);
+        const uint32_t sv2 = tile.shfl_up(sv, d), si2 = tile.shfl_up(si, d);
+        if (lane >= d && !f) { f = f2; sv = sv2; si = si2; }
+    }
+    uint32_t cur_sv = tile.shfl_up(sv, 1), cur_si = tile.shfl_up(si, 1);   // chain running into this lane (lane 0: element 0 breaks)
+    uint32_t em = 0, dist[EPL];
+#pragma unroll
+    for (int r = 0; r < EPL; r++) {
+        const uint32_t i = (uint32_t)lane * EPL + r;
+        if ((brk >> r) & 1u) { cur_sv = v[r]; cur_si = i; }
+        const uint32_t nv = (r + 1 < EPL) ? v[(r + 1) % EPL] : next_first;
+        const bool is_end = i < total && (i + 1 == total || nv - v[r] > BWT_TOLERANCE);
+        dist[r] = v[r] - cur_sv;
+        if (is_end && i - cur_si + 1 >= need) em |= 1u << r;
+    }
+    // the reference's list is descending by position: rank = number of emitted elements with a higher index
+    const uint32_t c = __popc(em);
+    uint32_t inc = c;
+#pragma unroll
+    for (int d = 1; d < G; d <<= 1) {
+        const uint32_t t = tile.shfl_down(inc, d);
+        if (lane + d < G) inc += t;
+    }
+    const uint32_t emitted = tile.shfl(inc, 0);
+    uint32_t base_out = 0;
+    if (emitted) {
+        if (lane == 0) {
+            base_out = atomicAdd(&ctr->n_clusters, emitted);
+            if ((uint64_t)base_out + emitted > cl_cap) atomicExch(&ctr->cluster_overflow, 1u);
+        }
+        base_out = tile.shfl(base_out, 0);
+        uint32_t rank = inc - c;                                 // emitted in higher lanes
+#pragma unroll
+        for (int r = EPL - 1; r >= 0; r--) {
+            if ((em >> r) & 1u) {
+                if ((uint64_t)base_out + rank < cl_cap) {
+                    Cluster cc;
+                    cc.read = read; cc.s = v[r]; cc.d = (int32_t)dist[r]; cc.rank = rank;
+                    clusters[base_out + rank] = cc;
+                }
+                rank++;
+            }
+        }
+    }
+    if (lane == 0) {
+        ncl[read] = emitted;
+        cl_base[read] = base_out;
+        atomicAdd(&s_ctr[CTR_CLUSTERS], (unsigned long long)emitted);
+    }
+}
+
+template <int G, int MAXT, typename Tile>
+__device__ __forceinline__ int sga_fast_read(const Tile &tile, const DevIndex &ix, const uint8_t *__restrict__ q, const int lq,
+                                             const uint32_t read, uint32_t *seeds, uint32_t *pack, const GroupShared &gs,
+                                             int32_t *read_status, uint32_t *ncl, uint32_t *cl_base, Cluster *clusters,
+                                             const uint32_t cl_cap, SeedCounters *ctr, unsigned long long *s_ctr) {
+    const int lane = tile.thread_rank();
+    // -- pack the read, reversed; any byte outside ACGT sends the read to the general path
+    const int nw = (lq + 15) >> 4;
+    bool valid = true;
+    for (int w = lane; w <= nw; w += G) {
+        uint32_t word = 0;
+        if (w < nw) {
+#pragma unroll 4
+            for (int t = 0; t < 16; t++) {
+                const int p = lq - 1 - (16 * w + t);
+                if (p >= 0) {
+                    const uint32_t ch = q[p];
+                    const uint32_t x = (ch >> 1) & 3u;                       // A0 C1 T2 G3
+                    valid &= ((0x47544341u >> (8 * x)) & 0xFFu) == ch;       // "ACTG"[x] == ch
+                    word |= (x ^ (x >> 1)) << (2 * t);                       // A0 C1 G2 T3
+                }
+            }
+        }
+        pack[w] = word;                                                      // pack[nw] = 0: upper word of the last funnel shift
+    }
+    if (tile.any(!valid)) return SGA_FALLBACK;
+    tile.sync();
+    const int nt = lq >= BWT_MIN_LEN ? (lq - BWT_MIN_LEN) / BWT_MIN_LEN + 1 : 0;
+    // -- searches: lane k takes subsequences k, k+G, ...; subsequence k ends 8k bases before the end of the read
+    unsigned long long lf = 0, hbm = 0;
+    for (int k = lane; k < nt; k += G) {
+        const int end = lq - BWT_MIN_LEN * k;
+        const uint32_t idx = __funnelshift_r(pack[k >> 1], pack[(k >> 1) + 1], (k & 1) * 16) & 0x3FFFFFFFu;
+        SearchRes r = search_core(ix, q, end, (int)(idx & 3u), idx, end < BWT_MAX_LEN ? end : BWT_MAX_LEN, true);
+        uint32_t cnt = (r.status == BWT_SEEDS) ? (r.ep - r.sp + 1) : 0u;
+        if (cnt > BWT_MAX_SEEDS_PER_READ) cnt = BWT_MAX_SEEDS_PER_READ + 1;
+        gs.t_res[k] = make_uint2(r.sp, (cnt << 4) | (uint32_t)r.n);
+        int steps = r.n > 0 ? r.n - 1 : 0;
+        lf += steps;
+        hbm += r.table ? r.n - r.table : steps;
+    }
+    tile.sync();
+    // -- slots: exclusive prefix of the seed counts; Qty = searches that produced a list (sga.erl:30-33)
+    uint32_t total = 0, qty = 0;
+    for (int k0 = 0; k0 < nt; k0 += G) {
+        int k = k0 + lane;
+        uint32_t c = k < nt ? (gs.t_res[k].y >> 4) : 0u;
+        uint32_t inc = c;
+#pragma unroll
+        for (int d = 1; d < G; d <<= 1) {
+            uint32_t t = tile.shfl_up(inc, d);
+            if (lane >= d) inc += t;
+        }
+        if (k < nt) gs.t_pos[k] = total + inc - c;
+        total += tile.shfl(inc, G - 1);
+        qty += __popc(tile.ballot(c > 0));
+    }
+#pragma unroll
+    for (int d = G / 2; d > 0; d >>= 1) {
+        lf += tile.shfl_down(lf, d);
+        hbm += tile.shfl_down(hbm, d);
+    }
+    if (total > (uint32_t)(8 * G)) return SGA_FALLBACK;       // the general path redoes (and counts) the searches (rare)
+    if (lane == 0) {
+        atomicAdd(&s_ctr[CTR_SEARCHES], (unsigned long long)nt);
+        atomicAdd(&s_ctr[CTR_LF], lf);
+        atomicAdd(&s_ctr[CTR_HBM_LF], hbm);
+        read_status[read] = BWT_READ_OK;
+        atomicAdd(&s_ctr[CTR_LOCATED], (unsigned long long)total);
+    }
+    if (qty < 2) {                                             // get_similar(0|1,_) -> []  (sga.erl:42-43)
+        if (lane == 0) { ncl[read] = 0; cl_base[read] = 0; }
+        return SGA_DONE;
+    }
+    tile.sync();
+    // -- locate, balanced over all rows: row t belongs to the last task whose first slot is <= t
+    for (uint32_t t = lane; t < total; t += G) {
+        int lo = 0, hi = nt - 1;                               // invariant: t_pos[lo] <= t
+        while (lo < hi) {
+            int mid = (lo + hi + 1) >> 1;
+            if (gs.t_pos[mid] <= t) lo = mid; else hi = mid - 1;
+        }
+        const uint2 tr = gs.t_res[lo];
+        seeds[t] = __ldg(ix.sa + (tr.x - 1) + (t - gs.t_pos[lo])) + (tr.y & 15u) + (uint32_t)(BWT_MIN_LEN * lo);
+    }
+    tile.sync();
+    const uint32_t need = 2 + qty / 7;
+    if (total <= (uint32_t)G) sort_vote_regs<G, 1>(tile, seeds, total, need, read, ncl, cl_base, clusters, cl_cap, ctr, s_ctr);
+    else if (total <= (uint32_t)(2 * G)) sort_vote_regs<G, 2>(tile, seeds, total, need, read, ncl, cl_base, clusters, cl_cap, ctr, s_ctr);
+    else if (total <= (uint32_t)(4 * G)) sort_vote_regs<G, 4>(tile, seeds, total, need, read, ncl, cl_base, clusters, cl_cap, ctr, s_ctr);
+    else sort_vote_regs<G, 8>(tile, seeds, total, need, read, ncl, cl_base, clusters, cl_cap, ctr, s_ctr);
+    tile.sync();
+    return SGA_DONE;
+}
+
 template <int G, int MAXT>
 __global__ void __launch_bounds__(SGA_BLOCK) sga_kernel(DevIndex ix, const uint8_t *__restrict__ reads,
                                                         const int64_t *__restrict__ offs, int64_t n_reads,
@@ -289,6 +507,8 @@ __global__ void __launch_bounds__(SGA_BLOCK) sga_kernel(DevIndex ix, const uint8
     __shared__ uint16_t s_end[GPB][MAXT], s_shift[GPB][MAXT];
     __shared__ uint2 s_res[GPB][MAXT];
     __shared__ uint32_t s_pos[GPB][MAXT];
+    constexpr int MAXW = (BWT_MIN_LEN * (MAXT - 1) + BWT_MAX_LEN + 15) / 16 + 2;     // packed read words
+    __shared__ uint32_t s_pack[GPB][MAXW];
     __shared__ unsigned long long s_ctr[CTR_N];
     if (threadIdx.x < CTR_N) s_ctr[threadIdx.x] = 0;
     __syncthreads();
@@ -304,8 +524,13 @@ __global__ void __launch_bounds__(SGA_BLOCK) sga_kernel(DevIndex ix, const uint8
             if (tile.thread_rank() == 0) { read_status[read] = BWT_READ_LIMIT; ncl[read] = 0; cl_base[read] = 0; }
             continue;
         }
-        sga_read<G, MAXT, false>(tile, ix, q, lq, (uint32_t)read, s_seeds[g], CAP, gs, read_status, ncl, cl_base,
-                                 clusters, cl_cap, slow, slow_cap, ctr, s_ctr);
+        int how = SGA_FALLBACK;
+        if (lq <= BWT_MIN_LEN * (MAXT - 1) + BWT_MAX_LEN)
+            how = sga_fast_read<G, MAXT>(tile, ix, q, lq, (uint32_t)read, s_seeds[g], s_pack[g], gs, read_status, ncl, cl_base,
+                                         clusters, cl_cap, ctr, s_ctr);
+        if (how == SGA_FALLBACK)                                  // 'N' / other bytes, or more seed ends than registers hold
+            sga_read<G, MAXT, false>(tile, ix, q, lq, (uint32_t)read, s_seeds[g], CAP, gs, read_status, ncl, cl_base,
+                                     clusters, cl_cap, slow, slow_cap, ctr, s_ctr);
         tile.sync();
     }
     flush_counters(s_ctr, ctr);

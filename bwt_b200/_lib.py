@@ -71,6 +71,11 @@ SIGNATURES = {
     "bwt_batch_download": (C.c_int, [P, P, P, P, C.c_int64, P, C.c_int64]),
     "bwt_batch_stats": (C.c_int, [P, C.POINTER(BwtStats)]),
     "bwt_batch_device_result": (C.c_int, [P, C.POINTER(P), C.POINTER(P), C.POINTER(P)]),
+    "bwt_aligner_create": (C.c_int, [P, C.c_int64, C.c_int64, C.c_int, C.POINTER(P)]),
+    "bwt_aligner_run": (C.c_int, [P, P, P, C.c_int64, P, P, P, C.c_int64, C.POINTER(C.c_int64), P, C.c_int64,
+                                  C.POINTER(C.c_int64)]),
+    "bwt_aligner_stats": (C.c_int, [P, C.POINTER(BwtStats)]),
+    "bwt_aligner_destroy": (C.c_int, [P]),
     "bwt_search_resident": (C.c_int, [P, P, C.c_int64, C.c_int32, C.c_int32, C.POINTER(C.c_float),
                                       C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "bwt_sample_reads": (C.c_int, [P, C.c_int64, C.c_int32, C.c_uint64, C.c_double, P, P]),

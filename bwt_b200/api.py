@@ -282,6 +282,61 @@ class Batch:
         return a.value, b.value, c.value
 
 
+class Aligner:
+    """Pipelined ``bwt_align_batch``: persistent chunk buffers, copies overlapped with kernels (``bwt_aligner``)."""
+
+    def __init__(self, index: Index, chunk_reads: int = 1 << 20, chunk_bytes: int = 256 << 20, depth: int = 3):
+        self.index = index
+        self._a = C.c_void_p()
+        check(lib().bwt_aligner_create(index.handle, int(chunk_reads), int(chunk_bytes), int(depth), C.byref(self._a)))
+
+    def close(self):
+        if self._a:
+            lib().bwt_aligner_destroy(self._a)
+            self._a = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def run_ptr(self, reads_ptr, offs_ptr, n, status_ptr, hit_offs_ptr, hits_ptr, hits_cap, cig_ptr, cig_cap):
+        """raw-pointer form (pinned buffers of the caller); -> (n_hits, cigar_bytes); raises NoSpace with the needed sizes"""
+        nh, nc = C.c_int64(), C.c_int64()
+        rc = lib().bwt_aligner_run(self._a, reads_ptr, offs_ptr, int(n), status_ptr, hit_offs_ptr, hits_ptr, int(hits_cap),
+                                   C.byref(nh), cig_ptr, int(cig_cap), C.byref(nc))
+        if rc == -6:
+            raise NoSpace(lib().bwt_last_error().decode(), (int(nh.value), int(nc.value)))
+        check(rc)
+        return int(nh.value), int(nc.value)
+
+    def run(self, reads, offsets=None):
+        if offsets is None:
+            reads, offsets = pack(reads)
+        reads = _u8(reads)
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        n = len(offsets) - 1
+        st = np.zeros(n, np.int32)
+        ho = np.zeros(n + 1, np.int64)
+        hcap, ccap = max(16, 4 * n), max(256, 64 * n)
+        while True:
+            hits = np.zeros(hcap, HIT_DTYPE)
+            cig = np.zeros(ccap, np.uint8)
+            try:
+                nh, nc = self.run_ptr(reads.ctypes.data, offsets.ctypes.data, n, st.ctypes.data, ho.ctypes.data,
+                                      hits.ctypes.data, hcap, cig.ctypes.data, ccap)
+            except NoSpace as e:
+                hcap, ccap = e.needed[0] + 16, e.needed[1] + 16
+                continue
+            return st, ho, hits[:nh].copy(), cig[:nc].tobytes()
+
+    def stats(self) -> BwtStats:
+        s = BwtStats()
+        check(lib().bwt_aligner_stats(self._a, C.byref(s)))
+        return s
+
+
 def sample_reads(index: Index, n: int, read_len: int, seed: int = 42, sub_rate: float = 0.01, out: Optional[np.ndarray] = None,
                  want_starts: bool = False):
     """Synthetic fixed-length reads sampled on the device from the index's .ref -> (uint8[n*read_len], offsets, starts|None)"""
@@ -316,5 +371,5 @@ def peak_dpx_gops(device: int = 0) -> float:
     return float(g.value)
 
 
-__all__ = ["Index", "Batch", "sample_reads", "BwtError", "NoSpace", "pack", "sw_batch", "search_resident", "peak_gather_gbs",
+__all__ = ["Index", "Batch", "Aligner", "sample_reads", "BwtError", "NoSpace", "pack", "sw_batch", "search_resident", "peak_gather_gbs",
            "peak_dpx_gops", "device_count", "HIT_DTYPE"]

@@ -6,7 +6,10 @@
 // One bwt_batch owns its stream, device buffers and pinned staging, so several batches can be in flight on one
 // (immutable) index from different host threads.
 #include <algorithm>
+#include <condition_variable>
+#include <mutex>
 #include <string.h>
+#include <thread>
 
 #include "common.cuh"
 #include "seed.cuh"
@@ -28,6 +31,30 @@ int dev_grow(T *&p, size_t &cap, size_t need, bool keep_slack = true) {
     }
     cap = want;
     return BWT_OK;
+}
+
+// offsets arrive as the caller has them: find the longest read and check that they do not decrease (the rebase to
+// 0 is a second kernel, so that nobody reads an element a neighbour has already rewritten)
+__global__ void prep_offsets_kernel(const int64_t *__restrict__ offs, int64_t n, uint32_t *__restrict__ info) {
+    int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t len = k < n ? offs[k + 1] - offs[k] : 0;
+    uint32_t l = len < 0 ? 0u : (len > (1 << 30) ? (1u << 30) : (uint32_t)len);
+    if (len < 0) atomicExch(info + 1, 1u);
+    for (int d = 16; d > 0; d >>= 1) l = max(l, __shfl_down_sync(0xFFFFFFFFu, l, d));
+    if ((threadIdx.x & 31) == 0 && l) atomicMax(info, l);
+}
+
+__global__ void rebase_offsets_kernel(int64_t *__restrict__ offs, int64_t n, int64_t base) {
+    int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k <= n) offs[k] -= base;
+}
+
+// pipelined aligner: results of a chunk move to their place in the caller's arrays
+__global__ void rebase_result_kernel(int64_t *__restrict__ hit_off64, int64_t n, bwt_hit *__restrict__ hits, int64_t n_hits,
+                                     int64_t hit_base, int64_t cig_base) {
+    int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k <= n) hit_off64[k] += hit_base;
+    if (k < n_hits) hits[k].cigar_off += cig_base;
 }
 
 // windows of worker_bwt.erl:84-90: Ref_len = Lq + D, Start = S - Ref_len + 200 into the padded reference
@@ -244,31 +271,29 @@ extern "C" int bwt_batch_upload(bwt_batch *b, const uint8_t *reads, const int64_
     int64_t base = offsets[0], bytes = offsets[n] - base;
     if (bytes < 0 || bytes > b->max_bytes) { bwt_set_error("batch of %lld read bytes exceeds max_read_bytes %lld", (long long)bytes, (long long)b->max_bytes); return BWT_ERR_ARG; }
     CU_TRY(cudaSetDevice(b->ix->device));
-    int maxlen = 0;
-    // offsets are rebased to 0 on the way in; the longest read picks the kernel variants
-    size_t need = (size_t)bytes + (size_t)(n + 1) * sizeof(int64_t);
+    // pageable callers are staged through pinned memory; the offsets are rebased and checked on the device
+    const bool pin_r = bytes == 0 || is_pinned(reads + base), pin_o = is_pinned(offsets);
+    size_t need = (pin_r ? 0 : (size_t)bytes) + (pin_o ? 0 : (size_t)(n + 1) * sizeof(int64_t));
     if (need > b->h_stage_bytes) {
         if (b->h_stage) cudaFreeHost(b->h_stage);
         b->h_stage = nullptr;
         b->h_stage_bytes = need + need / 4 + 4096;
         CU_TRY(cudaMallocHost(&b->h_stage, b->h_stage_bytes));
     }
-    int64_t *so = reinterpret_cast<int64_t *>(b->h_stage);
-    for (int64_t k = 0; k <= n; k++) {
-        int64_t o = offsets[k] - base;
-        so[k] = o;
-        if (k > 0) {
-            int64_t l = o - so[k - 1];
-            if (l < 0) { bwt_set_error("offsets must be non-decreasing (read %lld)", (long long)(k - 1)); return BWT_ERR_ARG; }
-            if (l > maxlen) maxlen = (int)std::min<int64_t>(l, 1 << 30);
-        }
-    }
+    const int64_t *src_o = offsets;
+    if (!pin_o) { memcpy(b->h_stage, offsets, (size_t)(n + 1) * sizeof(int64_t)); src_o = reinterpret_cast<const int64_t *>(b->h_stage); }
     CU_TRY(cudaEventRecord(b->ev[4], b->stream));
-    CU_TRY(cudaMemcpyAsync(b->d_offs, so, (size_t)(n + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, b->stream));
+    CU_TRY(cudaMemcpyAsync(b->d_offs, src_o, (size_t)(n + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, b->stream));
+    CU_TRY(cudaMemsetAsync(b->d_totals, 0, 2 * sizeof(uint32_t), b->stream));
+    unsigned blocks = (unsigned)((n + 1 + 255) / 256);
+    prep_offsets_kernel<<<blocks, 256, 0, b->stream>>>(b->d_offs, n, b->d_totals);
+    rebase_offsets_kernel<<<blocks, 256, 0, b->stream>>>(b->d_offs, n, base);
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaMemcpyAsync(b->h_totals, b->d_totals, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, b->stream));
     if (bytes > 0) {
         const uint8_t *src = reads + base;
-        if (!is_pinned(src)) {
-            uint8_t *sr = b->h_stage + (size_t)(n + 1) * sizeof(int64_t);
+        if (!pin_r) {
+            uint8_t *sr = b->h_stage + (pin_o ? 0 : (size_t)(n + 1) * sizeof(int64_t));
             memcpy(sr, src, (size_t)bytes);
             src = sr;
         }
@@ -276,6 +301,8 @@ extern "C" int bwt_batch_upload(bwt_batch *b, const uint8_t *reads, const int64_
     }
     CU_TRY(cudaEventRecord(b->ev[5], b->stream));
     CU_TRY(cudaStreamSynchronize(b->stream));
+    if (b->h_totals[1]) { bwt_set_error("offsets must be non-decreasing"); return BWT_ERR_ARG; }
+    int maxlen = (int)b->h_totals[0];
     float ms = 0;
     cudaEventElapsedTime(&ms, b->ev[4], b->ev[5]);
     b->stats.ms_h2d = ms;
@@ -458,52 +485,169 @@ static const int64_t CHUNK_READS = 1 << 20;
 static const int64_t CHUNK_BYTES = 256ll << 20;
 
 // splits [0,n) into chunks that respect both limits; returns the end of the chunk starting at lo
-static int64_t chunk_end(const int64_t *offsets, int64_t lo, int64_t n) {
-    int64_t hi = std::min(n, lo + CHUNK_READS);
-    while (hi > lo + 1 && offsets[hi] - offsets[lo] > CHUNK_BYTES) hi = lo + (hi - lo) / 2;
+static int64_t chunk_end_lim(const int64_t *offsets, int64_t lo, int64_t n, int64_t max_reads, int64_t max_bytes) {
+    int64_t hi = std::min(n, lo + max_reads);
+    if (offsets[hi] - offsets[lo] > max_bytes) {           // last index whose prefix still fits
+        const int64_t *e = std::upper_bound(offsets + lo, offsets + hi + 1, offsets[lo] + max_bytes);
+        hi = std::max<int64_t>(lo + 1, (e - offsets) - 1);
+    }
     return hi;
 }
+static int64_t chunk_end(const int64_t *offsets, int64_t lo, int64_t n) { return chunk_end_lim(offsets, lo, n, CHUNK_READS, CHUNK_BYTES); }
 
+// ---- pipelined aligner ------------------------------------------------------------------------------
+// `depth` resident batches, one host thread each; chunk c is uploaded, run and downloaded by thread c mod depth on
+// that batch's own stream, so the H2D of one chunk, the kernels of another and the D2H of a third overlap.  Results
+// land in the caller's arrays at their final place: a chunk learns its bases once every earlier chunk has finished.
+struct bwt_aligner {
+    bwt_index *ix = nullptr;
+    int64_t chunk_reads = 0, chunk_bytes = 0;
+    std::vector<bwt_batch *> batches;
+    bwt_stats stats{};
+};
+
+extern "C" int bwt_aligner_create(bwt_index *h, int64_t chunk_reads, int64_t chunk_bytes, int depth, bwt_aligner **out) {
+    if (!h || !out || chunk_reads <= 0 || chunk_bytes <= 0 || depth < 1 || depth > 16) { bwt_set_error("bwt_aligner_create: bad argument"); return BWT_ERR_ARG; }
+    bwt_aligner *a = new bwt_aligner();
+    a->ix = h; a->chunk_reads = chunk_reads; a->chunk_bytes = chunk_bytes;
+    for (int k = 0; k < depth; k++) {
+        bwt_batch *b = nullptr;
+        int st = bwt_batch_create(h, chunk_reads, chunk_bytes, &b);
+        if (st != BWT_OK) { bwt_aligner_destroy(a); return st; }
+        a->batches.push_back(b);
+    }
+    *out = a;
+    return BWT_OK;
+}
+
+extern "C" int bwt_aligner_destroy(bwt_aligner *a) {
+    if (!a) return BWT_OK;
+    for (bwt_batch *b : a->batches) bwt_batch_destroy(b);
+    delete a;
+    return BWT_OK;
+}
+
+extern "C" int bwt_aligner_stats(bwt_aligner *a, bwt_stats *out) {
+    if (!a || !out) { bwt_set_error("bwt_aligner_stats: null argument"); return BWT_ERR_ARG; }
+    *out = a->stats;
+    return BWT_OK;
+}
+
+namespace {
+struct PipeShared {
+    std::mutex mu;
+    std::condition_variable cv;
+    int64_t next_chunk = 0;          // chunks [0, next_chunk) have published their totals
+    int64_t hit_base = 0, cig_base = 0;
+    bool space = true;
+    int status = BWT_OK;
+    std::string error;
+};
+
+static void stats_add(bwt_stats &t, const bwt_stats &s) {
+    t.reads += s.reads; t.searches += s.searches; t.lf_steps += s.lf_steps; t.hbm_lf_steps += s.hbm_lf_steps;
+    t.located_rows += s.located_rows; t.clusters += s.clusters; t.sw_calls += s.sw_calls; t.sw_cells += s.sw_cells;
+    t.sw_general += s.sw_general; t.ms_total += s.ms_total; t.ms_seed += s.ms_seed; t.ms_sw += s.ms_sw; t.ms_emit += s.ms_emit;
+    t.ms_h2d += s.ms_h2d; t.ms_d2h += s.ms_d2h; t.ms_sga_kernel += s.ms_sga_kernel; t.ms_sw_kernel += s.ms_sw_kernel;
+    t.launches += s.launches;
+}
+}  // namespace
+
+extern "C" int bwt_aligner_run(bwt_aligner *a, const uint8_t *reads, const int64_t *offsets, int64_t n, int32_t *read_status,
+                               int64_t *hit_offsets, bwt_hit *hits, int64_t hits_cap, int64_t *n_hits, char *cigars,
+                               int64_t cigar_cap, int64_t *cigar_bytes) {
+    if (!a || !offsets || n < 0 || !hit_offsets || !n_hits || !cigar_bytes || (n > 0 && !reads)) { bwt_set_error("bwt_aligner_run: null argument"); return BWT_ERR_ARG; }
+    memset(&a->stats, 0, sizeof a->stats);
+    hit_offsets[0] = 0;
+    *n_hits = 0; *cigar_bytes = 0;
+    if (n == 0) return BWT_OK;
+    std::vector<int64_t> bounds(1, 0);                      // chunk c = reads [bounds[c], bounds[c+1])
+    for (int64_t lo = 0; lo < n;) {
+        int64_t hi = chunk_end_lim(offsets, lo, n, a->chunk_reads, a->chunk_bytes);
+        if (offsets[hi] - offsets[lo] > a->chunk_bytes) { bwt_set_error("a single read exceeds %lld bytes", (long long)a->chunk_bytes); return BWT_ERR_LIMIT; }
+        bounds.push_back(hi);
+        lo = hi;
+    }
+    const int64_t nchunks = (int64_t)bounds.size() - 1;
+    const int depth = (int)std::min<int64_t>((int64_t)a->batches.size(), nchunks);
+    PipeShared sh;
+    std::vector<bwt_stats> wstats((size_t)depth);
+    auto worker = [&](int w) {
+        bwt_batch *b = a->batches[(size_t)w];
+        memset(&wstats[(size_t)w], 0, sizeof(bwt_stats));
+        for (int64_t c = w; c < nchunks; c += depth) {
+            const int64_t lo = bounds[(size_t)c], m = bounds[(size_t)c + 1] - lo;
+            int st = BWT_OK;
+            bool skip;
+            { std::lock_guard<std::mutex> g(sh.mu); skip = sh.status != BWT_OK; }
+            if (!skip) {
+                st = bwt_batch_upload(b, reads, offsets + lo, m);
+                if (st == BWT_OK) st = bwt_batch_run(b);
+            }
+            int64_t nh = (skip || st != BWT_OK) ? 0 : b->n_hits, nc = (skip || st != BWT_OK) ? 0 : b->cigar_bytes;
+            int64_t hb, cb;
+            bool room;
+            {
+                std::unique_lock<std::mutex> g(sh.mu);
+                if (st != BWT_OK && sh.status == BWT_OK) { sh.status = st; sh.error = bwt_last_error(); }
+                sh.cv.wait(g, [&] { return sh.next_chunk == c; });
+                hb = sh.hit_base; cb = sh.cig_base;
+                sh.hit_base += nh; sh.cig_base += nc;
+                if (!(hits && cigars && sh.hit_base <= hits_cap && sh.cig_base <= cigar_cap)) sh.space = false;
+                room = sh.space && sh.status == BWT_OK;
+                sh.next_chunk = c + 1;
+            }
+            sh.cv.notify_all();
+            if (skip || st != BWT_OK) continue;
+            if (room) {
+                const int64_t cnt = std::max(m + 1, nh);
+                rebase_result_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, b->stream>>>(b->d_hit_off64, m, b->d_hits, nh, hb, cb);
+                // entry m of this chunk equals entry 0 of the next one: only the last chunk writes it
+                st = cudaGetLastError() == cudaSuccess ? BWT_OK : BWT_ERR_CUDA;
+                if (st == BWT_OK) {
+                    cudaStream_t s = b->stream;
+                    cudaEventRecord(b->ev[4], s);
+                    if (read_status) cudaMemcpyAsync(read_status + lo, b->d_read_status, (size_t)m * sizeof(int32_t), cudaMemcpyDeviceToHost, s);
+                    cudaMemcpyAsync(hit_offsets + lo, b->d_hit_off64, (size_t)(m + (c + 1 == nchunks ? 1 : 0)) * sizeof(int64_t), cudaMemcpyDeviceToHost, s);
+                    if (nh) cudaMemcpyAsync(hits + hb, b->d_hits, (size_t)nh * sizeof(bwt_hit), cudaMemcpyDeviceToHost, s);
+                    if (nc) cudaMemcpyAsync(cigars + cb, b->d_cigars, (size_t)nc, cudaMemcpyDeviceToHost, s);
+                    cudaEventRecord(b->ev[5], s);
+                    cudaError_t e = cudaStreamSynchronize(s);
+                    if (e != cudaSuccess) { bwt_set_error("aligner download: %s", cudaGetErrorString(e)); st = BWT_ERR_CUDA; }
+                    else cudaEventElapsedTime(&b->stats.ms_d2h, b->ev[4], b->ev[5]);
+                }
+                if (st != BWT_OK) { std::lock_guard<std::mutex> g(sh.mu); if (sh.status == BWT_OK) { sh.status = st; sh.error = bwt_last_error(); } }
+            }
+            stats_add(wstats[(size_t)w], b->stats);
+        }
+    };
+    std::vector<std::thread> th;
+    for (int w = 1; w < depth; w++) th.emplace_back(worker, w);
+    worker(0);
+    for (auto &t : th) t.join();
+    for (int w = 0; w < depth; w++) stats_add(a->stats, wstats[(size_t)w]);
+    *n_hits = sh.hit_base; *cigar_bytes = sh.cig_base;
+    if (sh.status != BWT_OK) { bwt_set_error("%s", sh.error.c_str()); return sh.status; }
+    if (!sh.space) {
+        bwt_set_error("output capacity too small: need %lld hits and %lld CIGAR bytes", (long long)sh.hit_base, (long long)sh.cig_base);
+        return BWT_ERR_NOSPACE;
+    }
+    return BWT_OK;
+}
+
+// worker_bwt.erl:73-97 for one list of reads, host buffers in and out: a short-lived aligner
 extern "C" int bwt_align_batch(bwt_index *h, const uint8_t *reads, const int64_t *offsets, int64_t n,
                                int32_t *read_status, int64_t *hit_offsets, bwt_hit *hits, int64_t hits_cap,
                                int64_t *n_hits, char *cigars, int64_t cigar_cap, int64_t *cigar_bytes) {
     if (!h || !offsets || n < 0 || !hit_offsets || !n_hits || !cigar_bytes) { bwt_set_error("bwt_align_batch: null argument"); return BWT_ERR_ARG; }
-    int64_t total_bytes = offsets[n] - offsets[0];
-    bwt_batch *b = nullptr;
-    BWT_TRY(bwt_batch_create(h, std::max<int64_t>(1, std::min(n, CHUNK_READS)),
-                             std::max<int64_t>(16, std::min(total_bytes, CHUNK_BYTES) + 0), &b));
-    int st = BWT_OK;
-    int64_t hit_base = 0, cig_base = 0;
-    bool space = true;
-    hit_offsets[0] = 0;
-    for (int64_t lo = 0; lo < n && st == BWT_OK;) {
-        int64_t hi = chunk_end(offsets, lo, n);
-        if (offsets[hi] - offsets[lo] > b->max_bytes) { bwt_set_error("a single read exceeds %lld bytes", (long long)b->max_bytes); st = BWT_ERR_LIMIT; break; }
-        st = bwt_batch_upload(b, reads, offsets + lo, hi - lo);
-        if (st != BWT_OK) break;
-        st = bwt_batch_run(b);
-        if (st != BWT_OK) break;
-        int64_t nh = b->n_hits, nc = b->cigar_bytes;
-        if (space && hits && cigars && hit_base + nh <= hits_cap && cig_base + nc <= cigar_cap) {
-            st = bwt_batch_download(b, read_status ? read_status + lo : nullptr, hit_offsets + lo, hits + hit_base,
-                                    hits_cap - hit_base, cigars + cig_base, cigar_cap - cig_base);
-            if (st != BWT_OK) break;
-            if (hit_base || cig_base) {
-                for (int64_t r = lo; r <= hi; r++) hit_offsets[r] += hit_base;
-                for (int64_t k = hit_base; k < hit_base + nh; k++) hits[k].cigar_off += cig_base;
-            }
-        } else space = false;                 // keep counting so that the caller learns the needed sizes
-        hit_base += nh; cig_base += nc;
-        lo = hi;
-    }
-    bwt_batch_destroy(b);
-    if (st != BWT_OK) return st;
-    *n_hits = hit_base; *cigar_bytes = cig_base;
-    if (!space) {
-        bwt_set_error("output capacity too small: need %lld hits and %lld CIGAR bytes", (long long)hit_base, (long long)cig_base);
-        return BWT_ERR_NOSPACE;
-    }
-    return BWT_OK;
+    const int64_t total_bytes = offsets[n] - offsets[0];
+    const int64_t cr = std::max<int64_t>(1, std::min(n, CHUNK_READS)), cb = std::max<int64_t>(16, std::min(total_bytes, CHUNK_BYTES));
+    const int depth = n > 2 * CHUNK_READS ? 3 : (n > CHUNK_READS ? 2 : 1);
+    bwt_aligner *a = nullptr;
+    BWT_TRY(bwt_aligner_create(h, cr, cb, depth, &a));
+    int st = bwt_aligner_run(a, reads, offsets, n, read_status, hit_offsets, hits, hits_cap, n_hits, cigars, cigar_cap, cigar_bytes);
+    bwt_aligner_destroy(a);
+    return st;
 }
 
 extern "C" int bwt_sga_batch(bwt_index *h, const uint8_t *reads, const int64_t *offsets, int64_t n,

@@ -184,6 +184,20 @@ int bwt_batch_stats(bwt_batch *b, bwt_stats *out);
 /* device pointers of the last run's result (for an NCCL gather by the host harness; valid until the next run) */
 int bwt_batch_device_result(bwt_batch *b, void **d_hit_offsets, void **d_hits, void **d_cigars);
 
+/* ---- pipelined aligner: bwt_align_batch with persistent buffers and overlapped copies ------------------- */
+
+/* `depth` resident batches of up to chunk_reads reads / chunk_bytes read bytes, each driven by its own host thread
+ * and CUDA stream: the H2D copy of one chunk, the kernels of another and the D2H copy of a third overlap.  Same
+ * arguments and results as bwt_align_batch; pass pinned host memory for full copy bandwidth.  One run at a time
+ * per aligner; several aligners may share one index. */
+typedef struct bwt_aligner bwt_aligner;
+int bwt_aligner_create(bwt_index *h, int64_t chunk_reads, int64_t chunk_bytes, int depth, bwt_aligner **out);
+int bwt_aligner_run(bwt_aligner *a, const uint8_t *reads, const int64_t *offsets, int64_t n, int32_t *read_status,
+                    int64_t *hit_offsets, bwt_hit *hits, int64_t hits_cap, int64_t *n_hits, char *cigars,
+                    int64_t cigar_cap, int64_t *cigar_bytes);
+int bwt_aligner_stats(bwt_aligner *a, bwt_stats *out);   /* sums over the chunks of the last run */
+int bwt_aligner_destroy(bwt_aligner *a);
+
 /* Search-only resident benchmark entry: n fixed-length subsequences already in HBM are searched
  * `repeats` times; *ms = CUDA-event time of all repeats, *lf_steps = LF steps executed per repeat. */
 int bwt_search_resident(bwt_index *h, const uint8_t *subs, int64_t n, int32_t sub_len, int32_t repeats,

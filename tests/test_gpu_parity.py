@@ -432,3 +432,32 @@ def test_kmer_table_depths(gl_fm, gl_ref, gl_coracle):
                 assert (res[2] == base[2]).all()
         with pytest.raises(api.BwtError):
             ix.set_kmer_depth(16)
+
+
+def test_pipelined_aligner_equals_one_shot(gl_index, gl_ref, gl_coracle):
+    reads, offs, _ = sample_reads(gl_ref, 5000, 100, seed=31, edit_rate=0.02, n_rate=0.002)
+    want = gl_index.align(reads, offs)
+    for chunk_reads, chunk_bytes, depth in ((700, 1 << 20, 3), (5000, 30_000, 2), (64, 1 << 20, 4), (10000, 1 << 22, 1)):
+        al = api.Aligner(gl_index, chunk_reads, chunk_bytes, depth)
+        got = al.run(reads, offs)
+        assert (got[0] == want[0]).all() and (got[1] == want[1]).all() and got[3] == want[3]
+        assert (got[2] == want[2]).all()
+        st = al.stats()
+        assert st.reads == 5000 and st.launches > 0
+        # too little room: the needed sizes come back
+        nh, nc = len(want[2]), len(want[3])
+        hits = np.zeros(max(1, nh // 2), api.HIT_DTYPE)
+        cig = np.zeros(nc + 16, np.uint8)
+        stt = np.zeros(5000, np.int32)
+        ho = np.zeros(5001, np.int64)
+        with pytest.raises(api.NoSpace) as e:
+            al.run_ptr(reads.ctypes.data, offs.ctypes.data, 5000, stt.ctypes.data, ho.ctypes.data, hits.ctypes.data, len(hits),
+                       cig.ctypes.data, len(cig))
+        assert e.value.needed == (nh, nc)
+        al.close()
+    _check_align(gl_index, gl_coracle, reads, offs, min_hits=500)
+    # a read longer than the chunk byte limit is a documented error, not a hang
+    al = api.Aligner(gl_index, 10, 50, 2)
+    with pytest.raises(api.BwtError):
+        al.run(reads, offs)
+    al.close()

@@ -6,6 +6,7 @@
 // One bwt_batch owns its stream, device buffers and pinned staging, so several batches can be in flight on one
 // (immutable) index from different host threads.
 #include <algorithm>
+#include <chrono>
 #include <condition_variable>
 #include <mutex>
 #include <string.h>
@@ -535,7 +536,7 @@ extern "C" int bwt_aligner_stats(bwt_aligner *a, bwt_stats *out) {
 
 namespace {
 struct PipeShared {
-    std::mutex mu;
+    std::mutex mu, compute_mu;
     std::condition_variable cv;
     int64_t next_chunk = 0;          // chunks [0, next_chunk) have published their totals
     int64_t hit_base = 0, cig_base = 0;
@@ -572,6 +573,9 @@ extern "C" int bwt_aligner_run(bwt_aligner *a, const uint8_t *reads, const int64
     const int depth = (int)std::min<int64_t>((int64_t)a->batches.size(), nchunks);
     PipeShared sh;
     std::vector<bwt_stats> wstats((size_t)depth);
+    const bool trace = getenv("BWT_TRACE") != nullptr;       // per-chunk host timeline on stderr (debug aid)
+    const auto t_start = std::chrono::steady_clock::now();
+    auto now_ms = [&] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_start).count(); };
     auto worker = [&](int w) {
         bwt_batch *b = a->batches[(size_t)w];
         memset(&wstats[(size_t)w], 0, sizeof(bwt_stats));
@@ -580,9 +584,17 @@ extern "C" int bwt_aligner_run(bwt_aligner *a, const uint8_t *reads, const int64
             int st = BWT_OK;
             bool skip;
             { std::lock_guard<std::mutex> g(sh.mu); skip = sh.status != BWT_OK; }
+            double t0 = now_ms(), t1 = t0, t2 = t0, t3 = t0;
             if (!skip) {
                 st = bwt_batch_upload(b, reads, offsets + lo, m);
-                if (st == BWT_OK) st = bwt_batch_run(b);
+                t1 = now_ms();
+                if (st == BWT_OK) {
+                    // one chunk computes at a time: the others spend that time in their copies, instead of all chunks
+                    // copying together and then time-slicing the SMs together
+                    std::lock_guard<std::mutex> run_token(sh.compute_mu);
+                    st = bwt_batch_run(b);
+                }
+                t2 = now_ms();
             }
             int64_t nh = (skip || st != BWT_OK) ? 0 : b->n_hits, nc = (skip || st != BWT_OK) ? 0 : b->cigar_bytes;
             int64_t hb, cb;
@@ -598,6 +610,7 @@ extern "C" int bwt_aligner_run(bwt_aligner *a, const uint8_t *reads, const int64
                 sh.next_chunk = c + 1;
             }
             sh.cv.notify_all();
+            t3 = now_ms();
             if (skip || st != BWT_OK) continue;
             if (room) {
                 const int64_t cnt = std::max(m + 1, nh);
@@ -619,6 +632,9 @@ extern "C" int bwt_aligner_run(bwt_aligner *a, const uint8_t *reads, const int64
                 if (st != BWT_OK) { std::lock_guard<std::mutex> g(sh.mu); if (sh.status == BWT_OK) { sh.status = st; sh.error = bwt_last_error(); } }
             }
             stats_add(wstats[(size_t)w], b->stats);
+            if (trace)
+                fprintf(stderr, "chunk %3lld w%d: upload %.2f-%.2f run -%.2f (seed %.2f sw %.2f emit %.2f) wait -%.2f download -%.2f\n", (long long)c, w,
+                        t0, t1, t2, b->stats.ms_seed, b->stats.ms_sw, b->stats.ms_emit, t3, now_ms());
         }
     };
     std::vector<std::thread> th;

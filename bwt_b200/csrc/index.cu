@@ -234,7 +234,7 @@ extern "C" int bwt_set_kmer_depth(bwt_index *h, int k) {
 static int upload_padded_ref(const uint8_t *ref, uint64_t len, bool on_device, uint8_t **d_out) {
     uint8_t *d = nullptr;
     uint64_t tot = len + 2 * BWT_REF_EXT;
-    CU_TRY(cudaMalloc(&d, tot));
+    CU_TRY(cudaMalloc(&d, tot + 16));            // 16 bytes of slack: the extension kernel reads aligned words
     pad_fill_kernel<<<1, 256>>>(d, BWT_REF_EXT, 'N');
     pad_fill_kernel<<<1, 256>>>(d + BWT_REF_EXT + len, BWT_REF_EXT, 'N');
     CU_TRY(cudaGetLastError());

@@ -41,7 +41,6 @@ __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
     return r;
 }
 
-__device__ __forceinline__ bool is_acgt(uint8_t c) { return c == 'A' || c == 'C' || c == 'G' || c == 'T'; }
 __device__ __forceinline__ int lane16(uint32_t x, int lane) { return lane ? ((int)x >> 16) : ((int)(x << 16) >> 16); }
 __device__ __forceinline__ uint32_t both(int k) { return ((uint32_t)k & 0xFFFFu) * 0x10001u; }
 
@@ -153,29 +152,49 @@ __device__ __forceinline__ void sw_strip(uint32_t *__restrict__ row, const uint3
     sw_cols<MASKED, true>(row, refw, dstrip, lr_min + 1, lr_max, rmin, capv, profA, profB, S, mD_top);
 }
 
-// traceback of one lane (sw.erl:116-160) + CIGAR text; returns false when the run buffer overflowed
-__device__ __forceinline__ bool sw_traceback(const SwFastParams &p, const uint2 *dirs, uint32_t *runs, int lane, int lq,
+// traceback of one lane (sw.erl:116-160) + CIGAR text; returns false when the run buffer overflowed.
+// The direction words live in HBM/L2: instead of one dependent load per step, the SW_TB_BAND columns to the left of
+// the current cell are fetched together (independent loads) into the thread's shared-memory slice once per strip
+// (again only if the path leaves the band), and the walk reads them from there.
+constexpr int SW_TB_BAND = 16;
+
+__device__ __forceinline__ bool sw_traceback(const SwFastParams &p, const uint2 *dirs, uint32_t *scratch, int lane, int lq,
                                              int lr, int i_first, int j, int vmax, uint32_t cand) {
     constexpr int B = SW_BLOCK;
+    uint32_t *runs = scratch;                                          // runs[k*B], k < run_cap
+    const int run_cap = p.cap_cols - 2 * SW_TB_BAND;                   // the band sits behind the runs
+    uint32_t *band = scratch + (size_t)run_cap * B;                    // band[(2c)*B], band[(2c+1)*B] = the uint2 of column band_hi - c
     int i = lq, nr = 0, cur = -1, len = 0;
     bool ovf = false;
+    int band_s = -1, band_hi = -1;                                     // strip and rightmost column held in the band
     while (i > 0) {
         int op;                                               // 0 = M (up_left), 1 = D (left), 2 = I (up)
         if (j == 0) op = 2;
         else {
-            int t = i - i_first, s = t / SW_R, r = t - s * SW_R;
-            uint2 w = dirs[((size_t)s * p.cap_cols + j) * B];
+            const int t = i - i_first, s = t / SW_R, r = t - s * SW_R;
+            if (s != band_s || j > band_hi || j <= band_hi - SW_TB_BAND) {
+                band_s = s; band_hi = j;
+#pragma unroll
+                for (int c = 0; c < SW_TB_BAND; c++) {
+                    if (j - c >= 1) {
+                        const uint2 d = dirs[((size_t)s * p.cap_cols + (j - c)) * B];
+                        band[(2 * c) * B] = d.x;
+                        band[(2 * c + 1) * B] = d.y;
+                    }
+                }
+            }
+            const uint2 w = make_uint2(band[(2 * (band_hi - j)) * B], band[(2 * (band_hi - j) + 1) * B]);
             uint32_t code = ((r < 5 ? w.x >> (3 * r) : w.y >> (3 * (r - 5))) >> (16 * lane)) & 7u;
             op = code == 4u ? 0 : code == 2u ? 2 : 1;
         }
         if (op == cur) len++;
         else {
-            if (cur >= 0) { if (nr < p.cap_cols) runs[nr * B] = (uint32_t)((len << 2) | cur); else ovf = true; nr++; }
+            if (cur >= 0) { if (nr < run_cap) runs[nr * B] = (uint32_t)((len << 2) | cur); else ovf = true; nr++; }
             cur = op; len = 1;
         }
         if (op == 0) { i--; j--; } else if (op == 2) i--; else j--;
     }
-    if (nr < p.cap_cols) runs[nr * B] = (uint32_t)((len << 2) | cur); else ovf = true;
+    if (nr < run_cap) runs[nr * B] = (uint32_t)((len << 2) | cur); else ovf = true;
     nr++;
     if (ovf) return false;
     int clen = 0;
@@ -201,22 +220,46 @@ __device__ __forceinline__ bool sw_traceback(const SwFastParams &p, const uint2 
     return true;
 }
 
-// stage a window as 2-bit codes ((c>>1)&3: A0 C1 T2 G3) into slot `lane` of refw; returns false if not plain ACGT
-__device__ __forceinline__ bool sw_stage(const SwFastParams &p, const SwDesc &d, uint32_t *refw, int lane) {
-    constexpr int B = SW_BLOCK;
-    const uint8_t *q = p.qbase + d.q_off;
-    const uint8_t *w = p.rbase + d.r_off;
-    bool plain = true;
-    for (int j0 = 0; j0 < d.lr; j0 += 16) {
-        uint32_t word = 0;
-        for (int t = 0; t < 16 && j0 + t < d.lr; t++) {
-            uint8_t c = w[j0 + t];
-            plain &= is_acgt(c);
-            word |= (uint32_t)((c >> 1) & 3) << (2 * t);
+// Packs `len` ASCII bases at src (any alignment) into 2-bit codes (c>>1)&3 (A0 C1 T2 G3), 16 per word, word k to
+// dst[k*stride]; returns false if a byte is not one of A,C,G,T.  Reads aligned 32-bit words (up to 7 bytes beyond the
+// last base: every buffer handed to the kernel carries 16 bytes of slack) and validates four bases at a time.
+__device__ __forceinline__ bool sw_pack2(const uint8_t *src, int len, uint32_t *dst, int stride) {
+    const uintptr_t a = reinterpret_cast<uintptr_t>(src);
+    const uint32_t *base = reinterpret_cast<const uint32_t *>(a & ~(uintptr_t)3);
+    const int sh = (int)(a & 3) * 8;
+    uint32_t prev = __ldg(base);
+    int k = 1;
+    bool ok = true;
+    for (int j0 = 0; j0 < len; j0 += 16) {
+        uint32_t out = 0;
+#pragma unroll
+        for (int t4 = 0; t4 < 4; t4++) {
+            const int left = len - (j0 + 4 * t4);
+            if (left > 0) {
+                const uint32_t next = __ldg(base + k);
+                k++;
+                uint32_t wv = __funnelshift_r(prev, next, sh);
+                prev = next;
+                if (left < 4) wv = (wv & ((1u << (8 * left)) - 1u)) | (0x41414141u << (8 * left));   // pad with 'A'
+                const uint32_t x = (wv >> 1) & 0x03030303u;
+                // the ASCII byte each code stands for, four at a time: A 0x41, C 0x43, G 0x47, T 0x54
+                const uint32_t x0 = x & 0x01010101u, x1 = (x >> 1) & 0x01010101u, tt = x1 & ~x0;
+                ok &= ((0x40404040u | (x0 << 1) | (x1 << 2) | (tt << 4) | (tt ^ 0x01010101u)) == wv);
+                out |= (((x * 0x00041041u) >> 18) & 0xFFu) << (8 * t4);
+            }
         }
-        refw[(2 * (j0 >> 4) + lane) * B] = word;
+        dst[(j0 >> 4) * stride] = out;
     }
-    for (int i = 0; i < d.lq; i++) plain &= is_acgt(q[i]);
+    return ok;
+}
+
+constexpr int SW_MAXQW = 26;    // query code words per lane: ceil(400 / 16) + 1
+
+// stage one pair: window codes into slot `lane` of refw (shared), query codes into qc (registers / local)
+__device__ __forceinline__ bool sw_stage(const SwFastParams &p, const SwDesc &d, uint32_t *refw, int lane, uint32_t *qc) {
+    constexpr int B = SW_BLOCK;
+    bool plain = sw_pack2(p.rbase + d.r_off, d.lr, refw + lane * B, 2 * B);
+    plain &= sw_pack2(p.qbase + d.q_off, d.lq, qc, 1);
     return plain;
 }
 
@@ -247,16 +290,16 @@ __global__ void __launch_bounds__(SW_BLOCK) sw_fast_kernel(SwFastParams p) {
                 candA = c1; candB = 0xFFFFFFFFu;
             }
             SwDesc dA = p.desc[candA], dB = dA;
+            uint32_t qcA[SW_MAXQW], qcB[SW_MAXQW];
             KD_CHECK(dA.lq >= 1 && dA.lr >= 1 && dA.lr + 1 <= p.cap_cols && (dA.lq + R - 1) / R <= p.max_strips, "cand=%u lq=%d lr=%d", candA, dA.lq, dA.lr);
-            if (!sw_stage(p, dA, refw, 0)) { p.list_gen[atomicAdd(&p.ctr->n_general, 1u)] = candA; candA = 0xFFFFFFFFu; }
+            if (!sw_stage(p, dA, refw, 0, qcA)) { p.list_gen[atomicAdd(&p.ctr->n_general, 1u)] = candA; candA = 0xFFFFFFFFu; }
             if (candB != 0xFFFFFFFFu) {
                 dB = p.desc[candB];
-                if (!sw_stage(p, dB, refw, 1)) { p.list_gen[atomicAdd(&p.ctr->n_general, 1u)] = candB; candB = 0xFFFFFFFFu; }
+                if (!sw_stage(p, dB, refw, 1, qcB)) { p.list_gen[atomicAdd(&p.ctr->n_general, 1u)] = candB; candB = 0xFFFFFFFFu; }
             }
             if (candA == 0xFFFFFFFFu && candB == 0xFFFFFFFFu) continue;
-            if (candA == 0xFFFFFFFFu) { candA = candB; dA = dB; candB = 0xFFFFFFFFu; sw_stage(p, dA, refw, 0); }
-            if (candB == 0xFFFFFFFFu) { dB = dA; sw_stage(p, dB, refw, 1); }      // single: lane B shadows lane A
-            const uint8_t *qA = p.qbase + dA.q_off, *qB = p.qbase + dB.q_off;
+            if (candA == 0xFFFFFFFFu) { candA = candB; dA = dB; candB = 0xFFFFFFFFu; sw_stage(p, dA, refw, 0, qcA); }
+            if (candB == 0xFFFFFFFFu) { dB = dA; sw_stage(p, dB, refw, 1, qcB); }      // single: lane B shadows lane A
             const int lq = dA.lq, lrA = dA.lr, lrB = dB.lr;
             const int lr_min = min(lrA, lrB), lr_max = max(lrA, lrB);
             const uint32_t capv = (lrA > lr_min ? 0x7FFFu : 0x8000u) | ((lrB > lr_min ? 0x7FFFu : 0x8000u) << 16);
@@ -272,8 +315,9 @@ __global__ void __launch_bounds__(SW_BLOCK) sw_fast_kernel(SwFastParams p) {
                 uint32_t profA[R], profB[R];
 #pragma unroll
                 for (int r = 0; r < R; r++) {
-                    int i = i0 + r;
-                    uint32_t qa = (i >= 1) ? ((qA[i - 1] >> 1) & 3u) : 0u, qb = (i >= 1) ? ((qB[i - 1] >> 1) & 3u) : 0u;
+                    const int i = i0 + r;
+                    const int w = (i - 1) >> 4, sh = 2 * ((i - 1) & 15);
+                    const uint32_t qa = (i >= 1) ? ((qcA[w] >> sh) & 3u) : 0u, qb = (i >= 1) ? ((qcB[w] >> sh) & 3u) : 0u;
                     profA[r] = 0xFCFCFCFCu ^ (0xE8u << (8 * qa));        // byte qa = 20 (match), others = -4 (mismatch)
                     profB[r] = 0xFCFCFCFCu ^ (0xE8u << (8 * qb));
                 }
@@ -498,8 +542,8 @@ int sw_stage_run(SwStage &st, const uint8_t *d_qbase, const uint8_t *d_rbase, ui
     // two shared-memory tiers of the fast kernel: "narrow" holds windows up to Lq + 15 columns (almost every
     // candidate: D is the summed gap of the voting chain), "wide" up to Lq + 64; anything wider takes the general path
     const int cap_limit = 400;                           // 128 threads x 4.5 B x columns <= 227 KB, multiple of 16
-    int cap_narrow = std::min(cap_limit, ((max_lq + 1 + 15) + 15) & ~15);
-    int cap_wide = std::min(cap_limit, ((max_lq + 1 + 64) + 15) & ~15);
+    int cap_narrow = std::min(cap_limit, std::max(64, ((max_lq + 1 + 15) + 15) & ~15));   // >= 64: the traceback's band + runs
+    int cap_wide = std::min(cap_limit, std::max(64, ((max_lq + 1 + 64) + 15) & ~15));
     int max_strips = (std::min(max_lq, SW_FAST_MAX_LQ) + SW_R - 1) / SW_R;
     if (max_strips < 1) max_strips = 1;
     int sms = 0;

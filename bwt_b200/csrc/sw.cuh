@@ -25,7 +25,7 @@ struct SwCounters {
 
 constexpr int SW_R = 10;             // rows per register strip; ten 3-bit direction codes per 32-bit word
 constexpr int SW_BLOCK = 128;
-constexpr int SW_FAST_MAX_LQ = 1000; // int16 keys: |8V+7| + 20 <= 8*2*Lq+27 < 32768
+constexpr int SW_FAST_MAX_LQ = 400;  // query codes of the fast kernel: 25 words per lane; int16 keys are safe up to ~2000
 
 // Device-resident state of the extension stage (owned by a batch).
 struct SwStage {

@@ -461,3 +461,16 @@ def test_pipelined_aligner_equals_one_shot(gl_index, gl_ref, gl_coracle):
     with pytest.raises(api.BwtError):
         al.run(reads, offs)
     al.close()
+
+
+def test_fast_kernels_take_plain_reads(gl_index, gl_ref):
+    """ACGT-only inputs must stay on the fast kernels (a silent detour through the double-precision kernel would
+    still be correct, only slow): the work counters say which path ran."""
+    reads, offs, _ = sample_reads_fast(np.frombuffer(gl_ref, np.uint8), 20000, 100, seed=3)
+    b = api.Batch(gl_index, 20000, len(reads))
+    b.upload(reads, offs)
+    b.run()
+    s = b.stats()
+    assert s.reads == 20000 and s.sw_calls > 5000 and s.sw_general == 0
+    assert s.searches == 20000 * 12 and s.lf_steps > 0 and s.sw_cells > 0 and s.launches >= 5
+    b.close()

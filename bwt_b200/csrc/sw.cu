@@ -22,6 +22,8 @@
 //     back by the traceback.
 // General path (any byte, e.g. 'N' = 1.6 or IUPAC codes in the window, or sizes beyond the fast tiers):
 //   IEEE doubles added in the reference's order, one thread per pair, rows in HBM scratch.
+#include <type_traits>
+
 #include "sw.cuh"
 
 // -DBWT_KDEBUG builds print and bail out on a violated kernel invariant instead of faulting (debug only).
@@ -74,6 +76,7 @@ struct SwFastParams {
     const uint32_t *n_list;   // device counter: entries of list
     SwOut *out;
     uint32_t *list_gen;
+    uint32_t *list_ovf;       // pairs to redo with absolute boundary rows
     SwCounters *ctr;
     char *cig;
     uint32_t cig_cap;
@@ -90,13 +93,15 @@ struct StripState {
 
 // columns j_from..j_to of one strip.  CAPPED: a pair whose window ended before this column keeps computing (its lane
 // is garbage from here on) but must not raise its row maxima: its keys are clamped to -32768 for the maximum.
-template <bool MASKED, bool CAPPED>
-__device__ __forceinline__ void sw_cols(uint32_t *__restrict__ row, const uint32_t *__restrict__ refw,
+template <bool MASKED, bool CAPPED, bool DELTA>
+__device__ __forceinline__ void sw_cols(std::conditional_t<DELTA, uint16_t, uint32_t> *__restrict__ row, const uint32_t *__restrict__ refw,
                                         uint2 *__restrict__ dstrip, const int j_from, const int j_to, const int rmin,
                                         const uint32_t capv, const uint32_t (&profA)[SW_R], const uint32_t (&profB)[SW_R],
-                                        StripState &S, uint32_t &mD_top) {
+                                        StripState &S, uint32_t &kt_prev, uint32_t &kl_prev, uint32_t &ovf) {
     constexpr int B = SW_BLOCK;
     if (j_from > j_to) return;
+    // lanes whose window has ended (CAPPED) hold garbage: their differences must not raise the overflow flag
+    const uint32_t live = CAPPED ? (((capv & 0xFFFFu) == 0x7FFFu ? 0xFFFFu : 0u) | ((capv >> 16) == 0x7FFFu ? 0xFFFF0000u : 0u)) : 0xFFFFFFFFu;
     uint32_t rwA = refw[(2 * ((j_from - 1) >> 4)) * B] >> (2 * ((j_from - 1) & 15));
     uint32_t rwB = refw[(2 * ((j_from - 1) >> 4) + 1) * B] >> (2 * ((j_from - 1) & 15));
     for (int j = j_from; j <= j_to; j++) {
@@ -104,8 +109,11 @@ __device__ __forceinline__ void sw_cols(uint32_t *__restrict__ row, const uint32
         // PRMT selector: lane A = byte cA of profA sign-extended, lane B = byte cB of profB sign-extended
         const uint32_t sel = (rwA & 3u) * 0x11u + (rwB & 3u) * 0x1100u + 0xC480u;
         rwA >>= 2; rwB >>= 2;
-        const uint32_t kt = row[j * B];                                // K(i0-1, j)
+        // the boundary row is stored as one signed byte per lane: K(i0-1,j) - K(i0-1,j-1)  (|dV| <= 6 => |dK| < 64)
+        const uint32_t kt = DELTA ? __vadd2(kt_prev, prmt((uint32_t)row[j * B], 0u, 0x9180u)) : (uint32_t)row[j * B];   // K(i0-1, j)
         const uint32_t mT = kt & 0xFFF8FFF8u;
+        const uint32_t mD_top = kt_prev & 0xFFF8FFF8u;                 // m(i0-1, j-1)
+        kt_prev = kt;
         uint32_t mup = mT;
         uint32_t tup = (((kt & 0x00020002u) * 4u)) | 0xFFF2FFF2u;      // 8*[up] - 14 per lane
         uint32_t mdiag = mD_top;
@@ -126,17 +134,24 @@ __device__ __forceinline__ void sw_cols(uint32_t *__restrict__ row, const uint32
             S.mx[r] = __vmaxs2(S.mx[r], CAPPED ? __vmins2(K, capv) : K);
             if (r < 5) acc_lo += t7 << (3 * r); else acc_hi += t7 << (3 * (r - 5));
         }
-        mD_top = mT;
-        row[j * B] = K;
+        if (DELTA) {
+            const uint32_t dk = __vsub2(K, kl_prev);
+            const uint32_t d8 = prmt(dk, 0u, 0x0020u);                  // low bytes of both lanes' differences
+            ovf |= (prmt(d8, 0u, 0x9180u) ^ dk) & live;                 // a difference that does not fit a signed byte
+            row[j * B] = (uint16_t)d8;
+            kl_prev = K;
+        } else {
+            row[j * B] = K;
+        }
         dstrip[j * B] = make_uint2(acc_lo, acc_hi);
     }
 }
 
-template <bool MASKED>
-__device__ __forceinline__ void sw_strip(uint32_t *__restrict__ row, const uint32_t *__restrict__ refw,
+template <bool MASKED, bool DELTA>
+__device__ __forceinline__ void sw_strip(std::conditional_t<DELTA, uint16_t, uint32_t> *__restrict__ row, const uint32_t *__restrict__ refw,
                                          uint2 *__restrict__ dstrip, const int lr_min, const int lr_max, const uint32_t capv,
                                          const int i0, const uint32_t (&profA)[SW_R], const uint32_t (&profB)[SW_R],
-                                         StripState &S) {
+                                         StripState &S, uint32_t &ovf) {
     const int rmin = 1 - i0;                        // first real row of a masked strip (rows i <= 0 are row 0)
 #pragma unroll
     for (int r = 0; r < SW_R; r++) {
@@ -146,10 +161,10 @@ __device__ __forceinline__ void sw_strip(uint32_t *__restrict__ row, const uint3
         S.left15[r] = __vadd2(S.mleft[r], 0xFFF1FFF1u);
         S.mx[r] = both(k0);
     }
-    uint32_t mD_top = row[0] & 0xFFF8FFF8u;         // K(i0-1, 0)
-    row[0] = both(-8 * (i0 + SW_R) + 2);            // K(last row of the strip, 0)
-    sw_cols<MASKED, false>(row, refw, dstrip, 1, lr_min, rmin, 0u, profA, profB, S, mD_top);
-    sw_cols<MASKED, true>(row, refw, dstrip, lr_min + 1, lr_max, rmin, capv, profA, profB, S, mD_top);
+    uint32_t kt_prev = both(i0 - 1 >= 1 ? -8 * i0 + 2 : 0);     // K(i0-1, 0): column 0 is known in closed form
+    uint32_t kl_prev = both(-8 * (i0 + SW_R) + 2);              // K(last row of the strip, 0)
+    sw_cols<MASKED, false, DELTA>(row, refw, dstrip, 1, lr_min, rmin, 0u, profA, profB, S, kt_prev, kl_prev, ovf);
+    sw_cols<MASKED, true, DELTA>(row, refw, dstrip, lr_min + 1, lr_max, rmin, capv, profA, profB, S, kt_prev, kl_prev, ovf);
 }
 
 // traceback of one lane (sw.erl:116-160) + CIGAR text; returns false when the run buffer overflowed.
@@ -158,16 +173,17 @@ __device__ __forceinline__ void sw_strip(uint32_t *__restrict__ row, const uint3
 // (again only if the path leaves the band), and the walk reads them from there.
 constexpr int SW_TB_BAND = 16;
 
-__device__ __forceinline__ bool sw_traceback(const SwFastParams &p, const uint2 *dirs, uint32_t *scratch, int lane, int lq,
+__device__ __forceinline__ bool sw_traceback(const SwFastParams &p, const uint2 *dirs, uint16_t *scratch, int lane, int lq,
                                              int lr, int i_first, int j, int vmax, uint32_t cand) {
     constexpr int B = SW_BLOCK;
-    uint32_t *runs = scratch;                                          // runs[k*B], k < run_cap
-    const int run_cap = p.cap_cols - 2 * SW_TB_BAND;                   // the band sits behind the runs
-    uint32_t *band = scratch + (size_t)run_cap * B;                    // band[(2c)*B], band[(2c+1)*B] = the uint2 of column band_hi - c
+    uint16_t *runs = scratch;                                          // runs[k*B], k < run_cap
+    const int run_cap = p.cap_cols - 4 * SW_TB_BAND;                   // the band sits behind the runs
+    uint16_t *band = scratch + (size_t)run_cap * B;                    // band[(4c+h)*B], h = 0..3: the uint2 of column band_hi - c
     int i = lq, nr = 0, cur = -1, len = 0;
     bool ovf = false;
     int band_s = -1, band_hi = -1;                                     // strip and rightmost column held in the band
     while (i > 0) {
+        if (j < 0) return false;                              // cannot happen with consistent inputs: never spin
         int op;                                               // 0 = M (up_left), 1 = D (left), 2 = I (up)
         if (j == 0) op = 2;
         else {
@@ -178,23 +194,24 @@ __device__ __forceinline__ bool sw_traceback(const SwFastParams &p, const uint2 
                 for (int c = 0; c < SW_TB_BAND; c++) {
                     if (j - c >= 1) {
                         const uint2 d = dirs[((size_t)s * p.cap_cols + (j - c)) * B];
-                        band[(2 * c) * B] = d.x;
-                        band[(2 * c + 1) * B] = d.y;
+                        band[(4 * c) * B] = (uint16_t)d.x; band[(4 * c + 1) * B] = (uint16_t)(d.x >> 16);
+                        band[(4 * c + 2) * B] = (uint16_t)d.y; band[(4 * c + 3) * B] = (uint16_t)(d.y >> 16);
                     }
                 }
             }
-            const uint2 w = make_uint2(band[(2 * (band_hi - j)) * B], band[(2 * (band_hi - j) + 1) * B]);
-            uint32_t code = ((r < 5 ? w.x >> (3 * r) : w.y >> (3 * (r - 5))) >> (16 * lane)) & 7u;
+            // rows 0-4 of the strip sit in d.x, rows 5-9 in d.y; each half-word belongs to one lane
+            const uint32_t hw = band[(4 * (band_hi - j) + (r < 5 ? 0 : 2) + lane) * B];
+            uint32_t code = (hw >> (3 * (r < 5 ? r : r - 5))) & 7u;
             op = code == 4u ? 0 : code == 2u ? 2 : 1;
         }
         if (op == cur) len++;
         else {
-            if (cur >= 0) { if (nr < run_cap) runs[nr * B] = (uint32_t)((len << 2) | cur); else ovf = true; nr++; }
+            if (cur >= 0) { if (nr < run_cap) runs[nr * B] = (uint16_t)((len << 2) | cur); else ovf = true; nr++; }
             cur = op; len = 1;
         }
         if (op == 0) { i--; j--; } else if (op == 2) i--; else j--;
     }
-    if (nr < run_cap) runs[nr * B] = (uint32_t)((len << 2) | cur); else ovf = true;
+    if (nr < run_cap) runs[nr * B] = (uint16_t)((len << 2) | cur); else ovf = true;
     nr++;
     if (ovf) return false;
     int clen = 0;
@@ -263,13 +280,18 @@ __device__ __forceinline__ bool sw_stage(const SwFastParams &p, const SwDesc &d,
     return plain;
 }
 
+// DELTA: the boundary row is kept as signed-byte differences (half the shared memory, twice the resident warps);
+// pairs whose differences overflow are listed in list_ovf and redone by the DELTA = false instantiation.
+template <bool DELTA>
 __global__ void __launch_bounds__(SW_BLOCK) sw_fast_kernel(SwFastParams p) {
     extern __shared__ uint32_t smem[];
+    using RowT = std::conditional_t<DELTA, uint16_t, uint32_t>;
     constexpr int B = SW_BLOCK;
     constexpr int R = SW_R;
     const int tid = threadIdx.x;
-    uint32_t *row = smem + tid;                                                         // row[j*B]: both pairs' keys
-    uint32_t *refw = smem + p.cap_cols * B + tid;                                       // refw[(2w+lane)*B]
+    RowT *row = reinterpret_cast<RowT *>(smem) + tid;                                   // row[j*B]: both pairs' keys (or differences)
+    uint32_t *refw = smem + (p.cap_cols * B) / (DELTA ? 2 : 1) + tid;                   // refw[(2w+lane)*B]
+    uint16_t *scratch = reinterpret_cast<uint16_t *>(smem) + tid;                       // the traceback reuses the row as half-words
     uint2 *dirs = p.dirs + (size_t)blockIdx.x * p.max_strips * p.cap_cols * B + tid;    // dirs[(s*cap+j)*B]
     const uint32_t n_list = *p.n_list;
     const uint32_t n_units = (n_list + 1) / 2;
@@ -303,13 +325,14 @@ __global__ void __launch_bounds__(SW_BLOCK) sw_fast_kernel(SwFastParams p) {
             const int lq = dA.lq, lrA = dA.lr, lrB = dB.lr;
             const int lr_min = min(lrA, lrB), lr_max = max(lrA, lrB);
             const uint32_t capv = (lrA > lr_min ? 0x7FFFu : 0x8000u) | ((lrB > lr_min ? 0x7FFFu : 0x8000u) << 16);
-            for (int j = 0; j <= lr_max; j++) row[j * B] = 0;            // row 0: {0,undef}  (sw.erl:61)
+            for (int j = 0; j <= lr_max; j++) row[j * B] = 0;            // row 0: {0,undef} everywhere (sw.erl:61): all differences 0
             const int nstr = (lq + R - 1) / R;
             const int i_first = lq - nstr * R + 1;                       // row number of strip 0, r = 0 (<= 1)
             const int thr0 = -2 * (lq / 2);                              // sw.erl:62
             int rowsA = lq, rowsB = lq;
             bool failA = false, failB = false;
             StripState S;
+            uint32_t ovf = 0;                                            // per lane: a boundary-row difference left int8
             for (int s = 0; s < nstr; s++) {
                 const int i0 = i_first + s * R;
                 uint32_t profA[R], profB[R];
@@ -322,8 +345,8 @@ __global__ void __launch_bounds__(SW_BLOCK) sw_fast_kernel(SwFastParams p) {
                     profB[r] = 0xFCFCFCFCu ^ (0xE8u << (8 * qb));
                 }
                 uint2 *dstrip = dirs + (size_t)s * p.cap_cols * B;
-                if (i0 < 1) sw_strip<true>(row, refw, dstrip, lr_min, lr_max, capv, i0, profA, profB, S);
-                else sw_strip<false>(row, refw, dstrip, lr_min, lr_max, capv, i0, profA, profB, S);
+                if (i0 < 1) sw_strip<true, DELTA>(row, refw, dstrip, lr_min, lr_max, capv, i0, profA, profB, S, ovf);
+                else sw_strip<false, DELTA>(row, refw, dstrip, lr_min, lr_max, capv, i0, profA, profB, S, ovf);
                 // row threshold (sw.erl:69-71): Vmax of row i must reach thr0 + 2*i
 #pragma unroll
                 for (int r = 0; r < R; r++) {
@@ -335,22 +358,54 @@ __global__ void __launch_bounds__(SW_BLOCK) sw_fast_kernel(SwFastParams p) {
                 }
                 if (failA && failB) break;
             }
+            // a pair whose boundary row could not be difference-coded is redone by the general kernel (rare: it takes
+            // a gap run of a dozen bases right next to a high-scoring path)
+            if (ovf & 0xFFFFu) { p.list_ovf[atomicAdd(&p.ctr->n_ovf, 1u)] = candA; }
+            if ((ovf >> 16) && candB != 0xFFFFFFFFu) { p.list_ovf[atomicAdd(&p.ctr->n_ovf, 1u)] = candB; candB = 0xFFFFFFFFu; }
+            if (ovf & 0xFFFFu) {
+                if (candB == 0xFFFFFFFFu) continue;
+                // lane B alone survives: finish it below as the only pair of the unit
+                calls += 1; cells += (unsigned long long)rowsB * (unsigned)lrB;
+                SwOut ob; ob.score = 0; ob.status = BWT_HIT_NO_MATCH; ob.cigar_len = 0; ob.cigar_off = 0;
+                if (failB) { p.out[candB] = ob; continue; }
+                const int vB = lane16(S.mx[R - 1], 1) >> 3;
+                int jb = -1;
+                uint32_t kk = both(-8 * (lq + 1) + 2);
+                for (int j = 0; j <= lrB && jb < 0; j++) {
+                    if (j) kk = __vadd2(kk, prmt((uint32_t)row[j * B], 0u, 0x9180u));
+                    if ((lane16(kk, 1) >> 3) == vB) jb = j;
+                }
+                if (jb < 0 || !sw_traceback(p, dirs, scratch, 1, lq, lrB, i_first, jb, vB, candB)) {
+                    p.list_gen[atomicAdd(&p.ctr->n_general, 1u)] = candB; calls--; cells -= (unsigned long long)rowsB * (unsigned)lrB;
+                }
+                continue;
+            }
             calls += 1 + (candB != 0xFFFFFFFFu);
             cells += (unsigned long long)rowsA * (unsigned)lrA + (candB != 0xFFFFFFFFu ? (unsigned long long)rowsB * (unsigned)lrB : 0ull);
             SwOut o;
             o.score = 0; o.status = BWT_HIT_NO_MATCH; o.cigar_len = 0; o.cigar_off = 0;
             // leftmost maximum of the last row (sw.erl:110-112), for both lanes before the row buffer is reused
             const int vmaxA = lane16(S.mx[R - 1], 0) >> 3, vmaxB = lane16(S.mx[R - 1], 1) >> 3;
-            int jA = 0, jB = 0;
-            if (!failA) while ((lane16(row[jA * B], 0) >> 3) != vmaxA) { jA++; KD_CHECK(jA <= lrA, "cand=%u vmax=%d", candA, vmaxA); }
-            if (!failB && candB != 0xFFFFFFFFu) while ((lane16(row[jB * B], 1) >> 3) != vmaxB) { jB++; KD_CHECK(jB <= lrB, "cand=%u vmax=%d", candB, vmaxB); }
+            int jA = -1, jB = -1;
+            {
+                uint32_t k = both(-8 * (lq + 1) + 2);                    // K(lq, 0); then the running sum of the differences
+                const bool needA = !failA, needB = !failB && candB != 0xFFFFFFFFu;
+                for (int j = 0; j <= lr_max && ((needA && jA < 0) || (needB && jB < 0)); j++) {
+                    if (j) k = DELTA ? __vadd2(k, prmt((uint32_t)row[j * B], 0u, 0x9180u)) : (uint32_t)row[j * B];
+                    if (jA < 0 && j <= lrA && (lane16(k, 0) >> 3) == vmaxA) jA = j;
+                    if (jB < 0 && j <= lrB && (lane16(k, 1) >> 3) == vmaxB) jB = j;
+                }
+                KD_CHECK((!needA || jA >= 0) && (!needB || jB >= 0), "cand=%u/%u vmax=%d/%d", candA, candB, vmaxA, vmaxB);
+                if (needA && jA < 0) { p.list_gen[atomicAdd(&p.ctr->n_general, 1u)] = candA; failA = true; jA = 0; }
+                if (needB && jB < 0) { p.list_gen[atomicAdd(&p.ctr->n_general, 1u)] = candB; candB = 0xFFFFFFFFu; }
+            }
             if (failA) p.out[candA] = o;
-            else if (!sw_traceback(p, dirs, row, 0, lq, lrA, i_first, jA, vmaxA, candA)) {
+            else if (!sw_traceback(p, dirs, scratch, 0, lq, lrA, i_first, jA, vmaxA, candA)) {
                 p.list_gen[atomicAdd(&p.ctr->n_general, 1u)] = candA; calls--; cells -= (unsigned long long)rowsA * (unsigned)lrA;
             }
             if (candB != 0xFFFFFFFFu) {
                 if (failB) p.out[candB] = o;
-                else if (!sw_traceback(p, dirs, row, 1, lq, lrB, i_first, jB, vmaxB, candB)) {
+                else if (!sw_traceback(p, dirs, scratch, 1, lq, lrB, i_first, jB, vmaxB, candB)) {
                     p.list_gen[atomicAdd(&p.ctr->n_general, 1u)] = candB; calls--; cells -= (unsigned long long)rowsB * (unsigned)lrB;
                 }
             }
@@ -500,14 +555,15 @@ int grow(T *&p, size_t &cap_items, size_t need_items) {
 int sw_stage_reserve(SwStage &st, uint32_t pairs) {
     if (pairs <= st.cap && st.d_desc) return BWT_OK;
     uint32_t want = pairs + pairs / 4 + 1024;
-    if (st.d_desc) { cudaFree(st.d_desc); cudaFree(st.d_out); cudaFree(st.d_list_fast); cudaFree(st.d_list_wide); cudaFree(st.d_list_gen); }
-    st.d_desc = nullptr; st.d_out = nullptr; st.d_list_fast = nullptr; st.d_list_wide = nullptr; st.d_list_gen = nullptr;
+    if (st.d_desc) { cudaFree(st.d_desc); cudaFree(st.d_out); cudaFree(st.d_list_fast); cudaFree(st.d_list_wide); cudaFree(st.d_list_gen); cudaFree(st.d_list_ovf); }
+    st.d_desc = nullptr; st.d_out = nullptr; st.d_list_fast = nullptr; st.d_list_wide = nullptr; st.d_list_gen = nullptr; st.d_list_ovf = nullptr;
     st.cap = 0;
     CU_TRY(cudaMalloc(&st.d_desc, (size_t)want * sizeof(SwDesc)));
     CU_TRY(cudaMalloc(&st.d_out, (size_t)want * sizeof(SwOut)));
     CU_TRY(cudaMalloc(&st.d_list_fast, (size_t)want * sizeof(uint32_t)));
     CU_TRY(cudaMalloc(&st.d_list_wide, (size_t)want * sizeof(uint32_t)));
     CU_TRY(cudaMalloc(&st.d_list_gen, (size_t)want * sizeof(uint32_t)));
+    CU_TRY(cudaMalloc(&st.d_list_ovf, (size_t)want * sizeof(uint32_t)));
     if (!st.d_ctr) {
         CU_TRY(cudaMalloc(&st.d_ctr, sizeof(SwCounters)));
         CU_TRY(cudaMallocHost(&st.h_ctr, sizeof(SwCounters)));
@@ -525,7 +581,7 @@ int sw_stage_reserve(SwStage &st, uint32_t pairs) {
 }
 
 void sw_stage_free(SwStage &st) {
-    cudaFree(st.d_desc); cudaFree(st.d_out); cudaFree(st.d_list_fast); cudaFree(st.d_list_wide); cudaFree(st.d_list_gen);
+    cudaFree(st.d_desc); cudaFree(st.d_out); cudaFree(st.d_list_fast); cudaFree(st.d_list_wide); cudaFree(st.d_list_gen); cudaFree(st.d_list_ovf);
     cudaFree(st.d_ctr); if (st.h_ctr) cudaFreeHost(st.h_ctr);
     if (st.ev_k0) cudaEventDestroy(st.ev_k0);
     if (st.ev_k1) cudaEventDestroy(st.ev_k1);
@@ -541,22 +597,24 @@ int sw_stage_run(SwStage &st, const uint8_t *d_qbase, const uint8_t *d_rbase, ui
     if (n > st.cap) { bwt_set_error("sw_stage_run: %u pairs exceed the reserved %u", n, st.cap); return BWT_ERR_ARG; }
     // two shared-memory tiers of the fast kernel: "narrow" holds windows up to Lq + 15 columns (almost every
     // candidate: D is the summed gap of the voting chain), "wide" up to Lq + 64; anything wider takes the general path
-    const int cap_limit = 400;                           // 128 threads x 4.5 B x columns <= 227 KB, multiple of 16
-    int cap_narrow = std::min(cap_limit, std::max(64, ((max_lq + 1 + 15) + 15) & ~15));   // >= 64: the traceback's band + runs
-    int cap_wide = std::min(cap_limit, std::max(64, ((max_lq + 1 + 64) + 15) & ~15));
+    const int cap_limit = 384;                           // fast-kernel tier limit: the absolute-row variant needs 4.5 B x columns x 128 threads <= 227 KB
+    int cap_narrow = std::min(cap_limit, std::max(96, ((max_lq + 1 + 15) + 15) & ~15));   // >= 96: the traceback's band (64 half-words) + runs
+    int cap_wide = std::min(cap_limit, std::max(96, ((max_lq + 1 + 64) + 15) & ~15));
     int max_strips = (std::min(max_lq, SW_FAST_MAX_LQ) + SW_R - 1) / SW_R;
     if (max_strips < 1) max_strips = 1;
     int sms = 0;
     CU_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, st.device));
-    auto smem_of = [](int cap) { return (size_t)SW_BLOCK * ((size_t)cap * 4 + (size_t)(cap / 16) * 8); };
-    CU_TRY(cudaFuncSetAttribute(sw_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_of(cap_wide)));
-    unsigned grid[2];
-    const int caps[2] = {cap_narrow, cap_wide};
+    auto smem_of = [](int cap, bool delta) { return (size_t)SW_BLOCK * ((size_t)cap * (delta ? 2 : 4) + (size_t)(cap / 16) * 8); };
+    CU_TRY(cudaFuncSetAttribute(sw_fast_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_of(cap_wide, true)));
+    CU_TRY(cudaFuncSetAttribute(sw_fast_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_of(cap_wide, false)));
+    unsigned grid[3];
+    const int caps[3] = {cap_narrow, cap_wide, cap_wide};
     size_t need_dirs = 0;
-    for (int t = 0; t < 2; t++) {
+    for (int t = 0; t < 3; t++) {
         int per_sm = 0;
-        CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sw_fast_kernel, SW_BLOCK, smem_of(caps[t])));
-        if (per_sm < 1) { bwt_set_error("sw_fast_kernel does not fit an SM with %zu B of shared memory", smem_of(caps[t])); return BWT_ERR_CUDA; }
+        if (t < 2) CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sw_fast_kernel<true>, SW_BLOCK, smem_of(caps[t], true)));
+        else CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sw_fast_kernel<false>, SW_BLOCK, smem_of(caps[t], false)));
+        if (per_sm < 1) { bwt_set_error("sw_fast_kernel does not fit an SM with %zu B of shared memory", smem_of(caps[t], t < 2)); return BWT_ERR_CUDA; }
         uint64_t units = ((uint64_t)n + 1) / 2;
         grid[t] = (unsigned)std::min<uint64_t>((units + SW_BLOCK - 1) / SW_BLOCK, (uint64_t)sms * per_sm);
         need_dirs = std::max(need_dirs, (size_t)grid[t] * SW_BLOCK * max_strips * caps[t]);
@@ -570,18 +628,23 @@ int sw_stage_run(SwStage &st, const uint8_t *d_qbase, const uint8_t *d_rbase, ui
         K_CHECK(stream, "sw_classify_kernel");
         SwFastParams p;
         p.qbase = d_qbase; p.rbase = d_rbase; p.desc = st.d_desc; p.out = st.d_out;
-        p.list_gen = st.d_list_gen; p.ctr = st.d_ctr; p.cig = st.d_cig_tmp; p.cig_cap = st.cig_cap;
+        p.list_gen = st.d_list_gen; p.list_ovf = st.d_list_ovf; p.ctr = st.d_ctr; p.cig = st.d_cig_tmp; p.cig_cap = st.cig_cap;
         p.dirs = st.d_dirs; p.max_strips = max_strips;
         CU_TRY(cudaEventRecord(st.ev_k0, stream));
         p.list = st.d_list_fast; p.n_list = &st.d_ctr->n_fast; p.cap_cols = cap_narrow;
-        sw_fast_kernel<<<grid[0], SW_BLOCK, smem_of(cap_narrow), stream>>>(p);
+        sw_fast_kernel<true><<<grid[0], SW_BLOCK, smem_of(cap_narrow, true), stream>>>(p);
         K_CHECK(stream, "sw_fast_kernel (narrow)");
         if (cap_wide > cap_narrow) {                     // usually finds an empty list and returns at once
             p.list = st.d_list_wide; p.n_list = &st.d_ctr->n_wide; p.cap_cols = cap_wide;
-            sw_fast_kernel<<<grid[1], SW_BLOCK, smem_of(cap_wide), stream>>>(p);
+            sw_fast_kernel<true><<<grid[1], SW_BLOCK, smem_of(cap_wide, true), stream>>>(p);
             K_CHECK(stream, "sw_fast_kernel (wide)");
             st.launches += 1;
         }
+        // pairs whose boundary rows did not fit the difference coding: absolute rows (usually an empty list)
+        p.list = st.d_list_ovf; p.n_list = &st.d_ctr->n_ovf; p.cap_cols = cap_wide;
+        sw_fast_kernel<false><<<grid[2], SW_BLOCK, smem_of(cap_wide, false), stream>>>(p);
+        K_CHECK(stream, "sw_fast_kernel (absolute rows)");
+        st.launches += 1;
         CU_TRY(cudaEventRecord(st.ev_k1, stream));
         st.launches += 2;
         CU_TRY(cudaMemcpyAsync(st.h_ctr, st.d_ctr, sizeof(SwCounters), cudaMemcpyDeviceToHost, stream));

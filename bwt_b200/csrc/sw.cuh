@@ -18,7 +18,7 @@ struct SwOut {           // 16 B per pair
 
 struct SwCounters {
     unsigned long long sw_calls, cells;
-    uint32_t n_fast, n_wide, n_general, pad0;   // list cursors
+    uint32_t n_fast, n_wide, n_general, n_ovf;   // list cursors
     uint32_t cig_used, cig_overflow; // temporary CIGAR arena
     uint32_t general_done, pad;
 };
@@ -33,7 +33,7 @@ struct SwStage {
     uint32_t cap = 0;                // pairs
     SwDesc *d_desc = nullptr;
     SwOut *d_out = nullptr;
-    uint32_t *d_list_fast = nullptr, *d_list_wide = nullptr, *d_list_gen = nullptr;
+    uint32_t *d_list_fast = nullptr, *d_list_wide = nullptr, *d_list_gen = nullptr, *d_list_ovf = nullptr;
     SwCounters *d_ctr = nullptr, *h_ctr = nullptr;     // h_ctr pinned
     char *d_cig_tmp = nullptr;
     uint32_t cig_cap = 0;

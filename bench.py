@@ -46,8 +46,9 @@ def parse():
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="CPU work of the cpu_baseline leg (0 = skip)")
     ap.add_argument("--ref-step-reads", type=int, default=200_000, help="reads per step of --impl reference")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-side", action="store_true", help="skip the untimed peak / LF-walk side measurements")
     ap.add_argument("--chunk-reads", type=int, default=1 << 20, help="reads per pipelined chunk of the e2e leg")
-    ap.add_argument("--depth", type=int, default=3, help="chunks in flight in the e2e leg")
+    ap.add_argument("--depth", type=int, default=2, help="chunks in flight in the e2e leg")
     return ap.parse_args()
 
 
@@ -180,6 +181,25 @@ def main():
     if a.impl == "reference":
         return run_reference(a, ix, reads, offs, threads)
 
+    # -- untimed side measurements on rank 0: roofline denominators measured on this device, and the FM walk alone
+    extra = {}
+    if rank == 0 and not a.no_side:
+        extra["gather_gbs"] = api.peak_gather_gbs(dev, 8 << 30)          # random 32-byte sectors over 8 GiB
+        extra["dpx_gops"] = api.peak_dpx_gops(dev)
+        # LF steps/s of bwa:find_seeds alone: 15-mers cut from the reads, 4^8 table only (every later step reads two
+        # Occ sectors), the walk the deep table replaces in the aligned-reads path
+        k_auto = ix.info().kmer_k
+        ix.set_kmer_depth(8)
+        m = min(n, 4_000_000)
+        subs = np.ascontiguousarray(reads[:m * a.read_len].reshape(m, a.read_len)[:, a.read_len - 15:]).reshape(-1)
+        ms, lf, hbm_lf = api.search_resident(ix, subs, 15, repeats=3)
+        ix.set_kmer_depth(k_auto)
+        gbs = 64.0 * hbm_lf * 3 / (ms * 1e-3) / 1e9
+        extra["lf_walk"] = {"subsequences": m, "lf_steps_per_s": lf * 3 / (ms * 1e-3), "occ_steps_per_s": hbm_lf * 3 / (ms * 1e-3),
+                            "achieved_gbs": round(gbs, 1), "frac_of_hbm_copy_peak": round(gbs / load_peaks()[0], 4),
+                            "frac_of_random_gather": round(gbs / extra["gather_gbs"], 4), "kmer_depth": 8,
+                            "note": "64 B (two Occ sectors) per step beyond the 8-mer table"}
+
     batch = api.Batch(ix, n, n * a.read_len)
     batch.upload(reads, offs)
 
@@ -253,17 +273,36 @@ def main():
         K = a.steps
         value = world * n * K / (t_ev * 1e-3)
         hbm_peak, peak_src = load_peaks()
-        # dominant kernel and its algorithmic traffic (DESIGN.md "units"): per HBM-served LF step two 32-byte Occ
-        # blocks, per located row 4 bytes of SA, per read its bases once
-        sga_bytes = 64.0 * agg["hbm_lf"] + 4.0 * agg["located"] + float(n * a.read_len * K)
+        # algorithmic traffic / work of the two kernels that make up the step (DESIGN.md "units"):
+        #   sga_kernel : per LF step not served by the k-mer table two 32-byte Occ blocks, per table lookup one 8-byte
+        #                entry, per located row 4 bytes of SA, per read its bases once
+        #   sw_fast    : per pair Lq + Lr bases in and a 16-byte result + its CIGAR out; cells x 4.25 ALU-pipe
+        #                instructions (8.5 per cell pair: PRMT, 2 VIADDMNMX, VIMNMX, VIADD.16x2, 3.5 LOP3 -- from SASS)
+        sga_bytes = (64.0 * agg["hbm_lf"] + 8.0 * agg["searches"] + 4.0 * agg["located"] + float(n * a.read_len * K))
         sga_gbs = sga_bytes / (agg["ms_sga"] * 1e-3) / 1e9 if agg["ms_sga"] > 0 else 0.0
+        sw_bytes = agg["sw_calls"] * (2.0 * a.read_len + 16.0) + float(cig_bytes * K)
+        sw_gbs = sw_bytes / (agg["ms_sw"] * 1e-3) / 1e9 if agg["ms_sw"] > 0 else 0.0
+        gcups = agg["cells"] / (agg["ms_sw"] * 1e-3) / 1e9 if agg["ms_sw"] else 0.0
         dominant = "sga_kernel" if agg["ms_sga"] >= agg["ms_sw"] else "sw_fast_kernel"
-        tr = load_traffic("sga_kernel")
-        roof = {"kernel": "sga_kernel", "bound": "hbm", "achieved": round(sga_gbs, 1), "peak": hbm_peak, "unit": "GB/s",
-                "frac": round(sga_gbs / hbm_peak, 4), "traffic": tr["dram_bytes_per_launch"] if tr else None,
-                "peak_source": peak_src, "algorithmic_bytes_per_launch": sga_bytes / K,
-                "ms_per_launch": agg["ms_sga"] / K, "dominant_kernel": dominant,
-                "share_of_step": {"sga_kernel": round(agg["ms_sga"] / t_ev, 3), "sw_fast_kernel": round(agg["ms_sw"] / t_ev, 3)}}
+        share = {"sga_kernel": round(agg["ms_sga"] / t_ev, 3), "sw_fast_kernel": round(agg["ms_sw"] / t_ev, 3)}
+        tr = load_traffic(dominant)
+        dom_bytes, dom_gbs, dom_ms = (sga_bytes, sga_gbs, agg["ms_sga"]) if dominant == "sga_kernel" else (sw_bytes, sw_gbs, agg["ms_sw"])
+        roof = {"kernel": dominant, "bound": "hbm", "achieved": round(dom_gbs, 1), "peak": hbm_peak, "unit": "GB/s",
+                "frac": round(dom_gbs / hbm_peak, 4), "traffic": tr["dram_bytes_per_launch"] if tr else None,
+                "traffic_source": tr.get("source") if tr else None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": dom_bytes / K, "ms_per_launch": dom_ms / K, "share_of_step": share,
+                "note": "the dominant kernel is the integer DP (sw_fast_kernel): it is bound by ALU-pipe issue, not by HBM; "
+                        "see roofline_alu for its real ceiling and roofline_sga for the memory-bound kernel"}
+        dpx_peak = extra.get("dpx_gops")
+        roof_alu = {"kernel": "sw_fast_kernel", "bound": "alu-pipe issue (DPX VIADDMNMX.S16x2 / packed 16-bit)", "gcups": round(gcups, 1),
+                    "achieved": round(gcups * 4.25, 1), "peak": dpx_peak, "unit": "Gop/s (ALU-pipe thread instructions)",
+                    "frac": round(gcups * 4.25 / dpx_peak, 4) if dpx_peak else None,
+                    "peak_source": "bwt_peak_dpx_gops: VIADDMNMX issue rate measured in this run"}
+        roof_sga = {"kernel": "sga_kernel", "bound": "hbm random access", "achieved": round(sga_gbs, 1), "peak": hbm_peak,
+                    "unit": "GB/s", "frac": round(sga_gbs / hbm_peak, 4), "ms_per_launch": agg["ms_sga"] / K,
+                    "algorithmic_bytes_per_launch": sga_bytes / K,
+                    "random_gather_peak_gbs": extra.get("gather_gbs"),
+                    "frac_of_random_gather": round(sga_gbs / extra["gather_gbs"], 4) if extra.get("gather_gbs") else None}
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": a.warmup,
             "ms_per_step": t_ev / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32",
@@ -275,7 +314,8 @@ def main():
                        "index_build_s": round(build_s, 2), "timer": "CUDA events on the batch stream, max over ranks",
                        "wall_ms_per_step": t_wall / K},
             "clocks": clk, "gpu_launches": total_launches,
-            "roofline": roof,
+            "roofline": roof, "roofline_alu": roof_alu, "roofline_sga": roof_sga,
+            "lf_walk": extra.get("lf_walk"),
             "work": {"lf_steps_per_s": agg["lf"] / (agg["ms_sga"] * 1e-3) if agg["ms_sga"] else None,
                      "hbm_lf_steps_per_read": agg["hbm_lf"] / (n * K), "lf_steps_per_read": agg["lf"] / (n * K),
                      "located_rows_per_read": agg["located"] / (n * K), "clusters_per_read": agg["clusters"] / (n * K),

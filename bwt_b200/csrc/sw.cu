@@ -617,6 +617,7 @@ int sw_stage_run(SwStage &st, const uint8_t *d_qbase, const uint8_t *d_rbase, ui
         if (per_sm < 1) { bwt_set_error("sw_fast_kernel does not fit an SM with %zu B of shared memory", smem_of(caps[t], t < 2)); return BWT_ERR_CUDA; }
         uint64_t units = ((uint64_t)n + 1) / 2;
         grid[t] = (unsigned)std::min<uint64_t>((units + SW_BLOCK - 1) / SW_BLOCK, (uint64_t)sms * per_sm);
+        if (t == 2) grid[t] = std::min<unsigned>(grid[t], (unsigned)sms);       // the overflow list is short: one wave
         need_dirs = std::max(need_dirs, (size_t)grid[t] * SW_BLOCK * max_strips * caps[t]);
     }
     BWT_TRY(grow(st.d_dirs, st.dirs_words, need_dirs));

@@ -70,4 +70,14 @@ with open(os.path.join(out_dir, "%s_summary.md" % tag), "w") as f:
             tms = d["gpu__time_duration.sum"] * {"ms": 1, "us": 1e-3, "s": 1e3, "ns": 1e-6}[d["gpu__time_duration.sum@unit"]]
             f.write("| DRAM traffic per launch | %.4g | byte |\n| DRAM GB/s under ncu | %.1f | GB/s |\n" % (tot, tot / tms / 1e6))
             d["dram_bytes_per_launch"] = tot
+# per-launch DRAM traffic of the big launches, for bench.py's roofline.traffic (largest launch of each kernel)
+traffic = {}
+for d in kern:
+    name = d["kernel"].split("<")[0]
+    if "dram_bytes_per_launch" in d and d["dram_bytes_per_launch"] > traffic.get(name, {}).get("dram_bytes_per_launch", 0):
+        traffic[name] = {"dram_bytes_per_launch": d["dram_bytes_per_launch"], "ms_under_ncu": d["gpu__time_duration.sum"],
+                         "source": "profiles/%s_summary.md (ncu --set full: dram__bytes_read.sum + dram__bytes_write.sum; `%s`)" % (tag, cmd)}
+if len(sys.argv) > 5 and sys.argv[5] == "--traffic":
+    with open(os.path.join(out_dir, "ncu_traffic.json"), "w") as f:
+        json.dump(traffic, f, indent=1)
 print(json.dumps([{k: v for k, v in d.items() if "@" not in k} for d in kern], indent=1))

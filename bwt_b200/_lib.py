@@ -76,6 +76,8 @@ SIGNATURES = {
                                   C.POINTER(C.c_int64)]),
     "bwt_aligner_stats": (C.c_int, [P, C.POINTER(BwtStats)]),
     "bwt_aligner_destroy": (C.c_int, [P]),
+    "bwt_fastq_parse": (C.c_int, [P, C.c_int64, C.c_int, C.c_int64, P, C.c_int64, P, P, P, C.POINTER(C.c_int64),
+                                  C.POINTER(C.c_int64)]),
     "bwt_search_resident": (C.c_int, [P, P, C.c_int64, C.c_int32, C.c_int32, C.POINTER(C.c_float),
                                       C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "bwt_sample_reads": (C.c_int, [P, C.c_int64, C.c_int32, C.c_uint64, C.c_double, P, P]),

@@ -198,6 +198,17 @@ int bwt_aligner_run(bwt_aligner *a, const uint8_t *reads, const int64_t *offsets
 int bwt_aligner_stats(bwt_aligner *a, bwt_stats *out);   /* sums over the chunks of the last run */
 int bwt_aligner_destroy(bwt_aligner *a);
 
+/* ---- FASTQ ingest (host side; fastq:read_seq/1, fastq.erl:5-18) -------------------------------------------- */
+
+/* Parses up to max_reads records of the FASTQ text [text, text+len) into the packed layout the calls above take:
+ * bases appended to reads_out (capacity reads_cap), offsets[0..n], and per record the position/length of its name
+ * inside `text` (name = header line minus '@' and minus its last character, exactly as the reference).  Records are
+ * returned in FILE order.  final = 0: the buffer may end in the middle of a record, which is then left unconsumed
+ * (*consumed = bytes to drop before the next call); final = 1: the text is complete.  No GPU involved. */
+int bwt_fastq_parse(const uint8_t *text, int64_t len, int final, int64_t max_reads, uint8_t *reads_out,
+                    int64_t reads_cap, int64_t *offsets, int64_t *name_start, int32_t *name_len, int64_t *n_reads,
+                    int64_t *consumed);
+
 /* Search-only resident benchmark entry: n fixed-length subsequences already in HBM are searched
  * `repeats` times; *ms = CUDA-event time of all repeats, *lf_steps = LF steps executed per repeat. */
 int bwt_search_resident(bwt_index *h, const uint8_t *subs, int64_t n, int32_t sub_len, int32_t repeats,

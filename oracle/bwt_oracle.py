@@ -690,3 +690,116 @@ def read_candidates(fm: FMIndex, padded_ref: bytes, qseq: bytes, sw_fn=sw):
         if r != NO_MATCH:
             cigars.insert(0, (r, s - ref_len + fm.shift, window))
     return seeds, cigars
+
+
+# ---------------------------------------------------------------------------------------------
+# fastq.erl:5-40, master.erl:59,149-178 -- ingest, batch framing and the result sink (rows F2/F3)
+# ---------------------------------------------------------------------------------------------
+WORKLOAD_SIZE = 200     # master.erl:59
+WATERLINE = 10          # worker_bwt.erl:16
+SCORE_FILTER = 265      # master.erl:149
+
+
+class LineDev:
+    """file:read_line/1 over bytes: returns the next line INCLUDING its newline (if any), or None at eof."""
+
+    def __init__(self, data: bytes):
+        self.d = data
+        self.p = 0
+
+    def read_line(self):
+        if self.p >= len(self.d):
+            return None
+        k = self.d.find(b"\n", self.p)
+        k = len(self.d) if k < 0 else k + 1
+        ln = self.d[self.p:k]
+        self.p = k
+        return ln
+
+
+def fastq_read_seq(dev: LineDev):
+    """fastq.erl:5-18 -> (name, seq) | None (eof).  lists:droplast/1 drops the LAST character, newline or not."""
+    while True:
+        ln = dev.read_line()
+        if ln is None:
+            return None
+        if ln[:1] == b"@":
+            data = dev.read_line()
+            if data is None:
+                raise ReferenceCrash("badmatch: {ok,SeqData} = eof (fastq.erl:8)")
+            dev.read_line()
+            dev.read_line()
+            return ln[1:][:-1], data[:-1]
+
+
+def fastq_read_seqs(dev: LineDev, n: int):
+    """fastq.erl:20-40 -> ("ok", Acc) | ("eof", Acc) | "eof"; Acc is in REVERSE file order."""
+    acc = []
+    while n > 0:
+        s = fastq_read_seq(dev)
+        if s is None:
+            return "eof" if not acc else ("eof", acc)
+        acc.insert(0, s)
+        n -= 1
+    return ("ok", acc)
+
+
+def produce_workload(dev: LineDev, n: int, state: dict):
+    """master.erl:162-178 -> list of lists (newest first) | "stop".  state: {"fastq_eof": bool}"""
+    acc = []
+    while True:
+        if n == 0:
+            return acc
+        if not state["fastq_eof"]:
+            r = fastq_read_seqs(dev, WORKLOAD_SIZE)
+            if r == "eof":
+                state["fastq_eof"] = True
+                return acc
+            acc.insert(0, r[1])
+            n -= 1
+            continue
+        if not acc:
+            return "stop"
+        raise ReferenceCrash("function_clause: produce_workload with fastq_eof and a non-empty accumulator")
+
+
+def master_sink_line(msg, chromosome: str):
+    """master.erl:149-158: None for no_cigar and for scores below 265, else the printed line (io:format
+    "~n~s      ~s      ~b      ~s      ~b      ~s~n")."""
+    if msg == "no_cigar":
+        return None
+    _, name, (score, cigar), pos, refseq = msg
+    if score < SCORE_FILTER:
+        return None
+    return "\n%s      %s      %d      %s      %d      %s\n" % (name.decode("latin1"), chromosome, pos, cigar, score,
+                                                                refseq.decode("latin1"))
+
+
+def worker_messages(fm: FMIndex, padded_ref: bytes, qseq_list):
+    """worker_bwt.erl:73-108 for one list [(Qname, Qseq)] -> messages in emission order.  Equal top scores: the
+    LAST candidate of the ascending list wins (OTP lists:sort/2 with a strict comparator; recalled, unpinned)."""
+    seeds = []
+    for (name, q) in qseq_list:
+        r = sga(fm, q)
+        if r:
+            seeds.insert(0, ((name, q), r))
+    out = []
+    for ((name, q), sd) in seeds:
+        cigars = []
+        for (s, d) in sd:
+            ref_len = len(q) + d
+            start = s - ref_len + REF_EXTENSION_LEN
+            if start < 0 or start + ref_len > len(padded_ref):
+                raise ReferenceCrash("badmatch (worker_bwt.erl:89)")
+            w = padded_ref[start:start + ref_len]
+            c = sw(q, w)
+            if c != NO_MATCH:
+                cigars.insert(0, (c, s - ref_len + fm.shift, w))
+        if not cigars:
+            out.append("no_cigar")
+        elif len(cigars) == 1:
+            out.append(("cigar", name) + cigars[0])
+        else:
+            best = max(c[0][0] for c in cigars)
+            out.append(("cigar", name) + [c for c in cigars if c[0][0] == best][-1])
+    return out

@@ -497,3 +497,25 @@ def test_partitions_parity_and_merge(gl_ref):
     assert (np.diff(mho) == np.diff(parts[0][1]) + np.diff(parts[1][1])).all()
     # a read drawn from the first half aligns (if at all) in partition 0 with the same coordinates as un-partitioned
     assert set(np.unique(mhits["part"]).tolist()) == {0, 1}
+
+
+def test_master_run_end_to_end(gl_index, gl_fm, gl_ref):
+    """FASTQ text -> workloads of 200 in the reference's (reverse) order -> GPU path -> top-1 pick -> 265 filter -> the
+    lines master.erl prints; against the literal Python oracle of the same chain (150 bp reads: scores reach 265)."""
+    from bwt_b200 import master
+    reads, offs, _ = sample_reads(gl_ref, 260, 150, seed=77, edit_rate=0.01)
+    recs = [(b"read_%d/1 len=%d" % (k, offs[k + 1] - offs[k]), reads[offs[k]:offs[k + 1]].tobytes()) for k in range(260)]
+    text = b"".join(b"@" + n + b"\n" + s + b"\n+\n" + b"I" * len(s) + b"\n" for n, s in recs)
+    padded = O.pad_ref(gl_ref)
+    got, dealt = master.run(gl_index, padded, text, "GL000193.1")
+    dev, state, want = O.LineDev(text), {"fastq_eof": False}, []
+    while True:
+        wl = O.produce_workload(dev, O.WATERLINE, state)
+        if wl == "stop":
+            break
+        for lst in wl:
+            for msg in O.worker_messages(gl_fm, padded, lst):
+                ln = O.master_sink_line(msg, "GL000193.1")
+                if ln is not None:
+                    want.append(ln)
+    assert dealt == 260 and got == want and len(got) > 20

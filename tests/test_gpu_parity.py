@@ -519,3 +519,23 @@ def test_master_run_end_to_end(gl_index, gl_fm, gl_ref):
                 if ln is not None:
                     want.append(ln)
     assert dealt == 260 and got == want and len(got) > 20
+
+
+def test_make_indices_from_fasta(tmp_path):
+    """Row F1: fm_index:t/0 builds contigs "2" and "4" of bwt_files/test_genome.fasta (fm_index.erl:15-17); the files
+    must be what the oracle's builder + ETF writer produce (Appendix D-2 tables)."""
+    from bwt_b200 import fm_index
+    from test_oracle_golden import TOY_FASTA
+    fa = tmp_path / "test_genome.fasta"
+    fa.write_bytes(TOY_FASTA)
+    made = fm_index.make_indices(str(fa), ["2", "4"], str(tmp_path / "fm"))
+    assert [(m[0], m[1], m[2]) for m in made] == [("2", 1, 1), ("4", 1, 1)]
+    for name, j, shift, fm_path, ref_path in made:
+        sh, body = O.fasta_contig_body(TOY_FASTA, name)
+        fm = O.build_fm(body, sh + 1)
+        assert open(fm_path, "rb").read() == O.write_fm(fm)
+        assert open(ref_path, "rb").read() == body
+        meta, ix = fm_index.get_index(name, 1, str(tmp_path / "fm"))
+        assert dict(meta) == {"pointers": fm.pointers, "shift": sh + 1}
+        ix.close()
+    assert fm_index.make_indices(str(fa), ["3"], str(tmp_path / "fm"))[0][2] == 14      # 13 N trimmed on the left + Start 1

@@ -80,3 +80,17 @@ def test_pack():
     assert d.tobytes() == b"ACGTT" and o.tolist() == [0, 2, 2, 5]
     d, o = api.pack([])
     assert len(d) == 0 and o.tolist() == [0]
+
+
+def test_fasta_contig_extraction_matches_oracle():
+    from bwt_b200 import fm_index
+    from oracle import bwt_oracle as O
+    from test_oracle_golden import TOY_FASTA
+    got = {name: fm_index.contig_body(TOY_FASTA[off:off + ln]) for name, off, ln in fm_index._contigs(TOY_FASTA)}
+    assert sorted(got) == ["1", "2", "3", "4", "5"]
+    for name in got:
+        assert got[name] == O.fasta_contig_body(TOY_FASTA, name)
+    assert got["3"][0] == 13 and got["2"] == (0, b"AACCATGG")
+    crlf = b">x y z\r\nNNAC\r\nGT\r\nNN\r\n>y\nACGT"
+    got = {name: fm_index.contig_body(crlf[off:off + ln]) for name, off, ln in fm_index._contigs(crlf)}
+    assert got == {"x": (2, b"ACGT"), "y": (0, b"ACGT")}

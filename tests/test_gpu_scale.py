@@ -1,0 +1,136 @@
+"""Larger-than-oracle sizes (BASELINE.json configs[1..3]) through size-independent properties, plus oracle parity on a
+sample.  Default: a 512 Mbp synthetic index and 2 M reads (seconds); BWT_FULL=1 runs the bench's own size
+(3,137,454,466 bp, 10 M reads; about a minute, 40 GB of host memory for the sampled oracle check)."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from oracle.c_oracle import COracle, c_sw   # noqa: E402
+from bwt_b200 import api                   # noqa: E402
+from test_oracle_golden import TOY_FASTA    # noqa: E402
+from oracle import bwt_oracle as O          # noqa: E402
+
+FULL = os.environ.get("BWT_FULL", "0") == "1"
+REF_BP = 3_137_454_466 if FULL else 512_000_000
+N_READS = 10_000_000 if FULL else 2_000_000
+
+
+@pytest.fixture(scope="module")
+def big():
+    ix = api.Index.build_synthetic(REF_BP, seed=42, shift=1)
+    reads, offs, starts = api.sample_reads(ix, N_READS, 100, seed=1042, sub_rate=0.01, want_starts=True)
+    yield ix, reads, offs, starts
+    ix.close()
+
+
+def test_full_size_properties(big):
+    ix, reads, offs, starts = big
+    n = len(offs) - 1
+    al = api.Aligner(ix, 1 << 20, (1 << 20) * 100, 2)
+    st, ho, hits, cig = al.run(reads, offs)
+    assert (st == 0).all() and ho[n] == len(hits)
+    ok = hits["status"] == 0
+    assert ok.sum() > n // 4
+    # scores: at most 2 per base, at least the last row threshold 2*Lq - 2*(Lq div 2) (sw.erl:62-71)
+    assert hits["score"][ok].max() <= 200 and hits["score"][ok].min() >= 100
+    # Pos = S - Ref_len + Shift with Ref_len = Lq + D (worker_bwt.erl:86,94)
+    assert (hits["pos"] == hits["s"] - (100 + hits["d"]) + 1).all()
+    # per read the hit list is ascending in position (the reference's Cigars list)
+    read_of = np.repeat(np.arange(n), np.diff(ho))
+    same = read_of[1:] == read_of[:-1]
+    assert (hits["s"][1:][same] > hits["s"][:-1][same]).all()
+    # CIGAR arithmetic on a sample: M+I = Lq, M+D <= Lr, no empty runs, no adjacent equal ops
+    rng = np.random.default_rng(3)
+    sample = rng.choice(np.nonzero(ok)[0], size=20000, replace=False)
+    for k in sample:
+        h = hits[k]
+        c = cig[h["cigar_off"]:h["cigar_off"] + h["cigar_len"]].decode()
+        ops = re.findall(r"(\d+)([MID])", c)
+        assert "".join(a + b for a, b in ops) == c and all(int(a) > 0 for a, _ in ops)
+        assert all(x[1] != y[1] for x, y in zip(ops, ops[1:]))
+        assert sum(int(a) for a, b in ops if b in "MI") == 100
+        assert sum(int(a) for a, b in ops if b in "MD") <= 100 + h["d"]
+    # the k-mer table depth never changes a result (the deep table replaces up to 14 LF steps per search)
+    m = 300_000
+    deep = ix.info().kmer_k
+    a = ix.align(reads[:offs[m]], offs[:m + 1])
+    ix.set_kmer_depth(8)
+    b = ix.align(reads[:offs[m]], offs[:m + 1])
+    ix.set_kmer_depth(deep)
+    assert (a[1] == b[1]).all() and (a[2] == b[2]).all() and a[3] == b[3]
+    assert (a[1] == ho[:m + 1]).all() and (a[2] == hits[:ho[m]]).all()        # and sharding invariance
+    # sampled pairs re-aligned by the CPU port of sw:sw/2 on the window cut from the exported .ref
+    _, _, ref = ix.export(want_L=False, want_SA=False)
+    pad = 200
+    for k in sample[:3000]:
+        h = hits[k]
+        r = int(read_of[k])
+        lr = 100 + int(h["d"])
+        start = int(h["s"]) - lr                                    # unpadded coordinate of the window start
+        if start < 0 or start + lr > len(ref):
+            continue
+        want = c_sw(reads[offs[r]:offs[r + 1]].tobytes(), ref[start:start + lr].tobytes())
+        assert want == (int(h["score"]), cig[h["cigar_off"]:h["cigar_off"] + h["cigar_len"]].decode())
+    al.close()
+
+
+@pytest.mark.skipif(not FULL, reason="BWT_FULL=1: needs ~20 GB of host memory for the exported index")
+def test_full_size_oracle_sample(big):
+    ix, reads, offs, starts = big
+    L, SA, ref = ix.export()
+    orc = COracle(L, SA, tuple(ix.info().pointers), 1, ref, mode=1)
+    m = 50_000
+    sub = reads[:offs[m]]
+    st, ho, hits, cig = ix.align(sub, offs[:m + 1])
+    ncand, cand, _ = orc.align_batch(sub, offs[:m + 1], nthreads=16, cap_per_read=32)
+    tot = 0
+    for r in range(m):
+        c = int(ncand[r])
+        assert ho[r + 1] - ho[r] == c
+        for k in range(c):
+            w, h = cand[r * 32 + (c - 1 - k)], hits[ho[r] + k]
+            assert (int(h["s"]), int(h["d"]), int(h["status"])) == (w.S, w.D, w.status)
+            if w.status == 0:
+                assert (int(h["score"]), int(h["pos"])) == (w.score, w.pos)
+                assert cig[h["cigar_off"]:h["cigar_off"] + h["cigar_len"]] == w.cigar[:w.cigar_len]
+                tot += 1
+    assert tot > m // 4
+
+
+def test_config2_toy_contigs_million_reads():
+    """BASELINE.json configs[1]: bwt_files/test_genome.fasta contigs indexed, 1 M synthetic 100 bp reads, backward
+    search + locate (+ vote).  The contigs are shorter than the reads: a known-answer and launch-overhead case."""
+    n = 1_000_000
+    rng = np.random.default_rng(2)
+    reads = np.frombuffer(b"ACGT", np.uint8)[rng.integers(0, 4, size=n * 100)]
+    # plant pieces of the contigs so that some searches do find seeds
+    offs = np.arange(n + 1, dtype=np.int64) * 100
+    for name in ("1", "3", "4", "5"):
+        sh, body = O.fasta_contig_body(TOY_FASTA, name)
+        b = np.frombuffer(body, np.uint8)
+        for r in range(int(name) * 1000, n, 50_000):
+            reads[r * 100 + 100 - len(b):r * 100 + 100] = b
+    reads = np.ascontiguousarray(reads)
+    for name in ("1", "3", "4", "5"):
+        sh, body = O.fasta_contig_body(TOY_FASTA, name)
+        fm = O.build_fm(body, sh + 1)
+        orc = COracle(fm.L, fm.SA, fm.pointers, sh + 1, body, mode=0)
+        with api.Index.build(body, shift=sh + 1) as ix:
+            st, clo, S, D = ix.sga(reads, offs)
+            ncand, cand, _ = orc.align_batch(reads, offs, nthreads=16, with_sw=False, cap_per_read=8)
+            assert (st == 0).all()
+            assert (np.diff(clo) == ncand).all()
+            nz = np.nonzero(ncand)[0]
+            for r in nz[:5000]:
+                got = list(zip(S[clo[r]:clo[r + 1]].tolist(), D[clo[r]:clo[r + 1]].tolist()))
+                assert got == [(cand[r * 8 + k].S, cand[r * 8 + k].D) for k in range(int(ncand[r]))]
+            # every 15-mer search of the batch against the oracle's find_seeds, on a sample of subsequences
+            subs = [reads[r * 100:r * 100 + 100 - 8 * k].tobytes() for r in nz[:300] for k in range(12)]
+            if subs:
+                s2, sp, ep, nn = ix.search(subs)
+                for k, q in enumerate(subs):
+                    assert (int(s2[k]), int(sp[k]), int(ep[k]), int(nn[k])) == orc.find_seeds(q)

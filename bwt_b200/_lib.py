@@ -6,7 +6,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libbwt_b200.so")
+# BWT_B200_LIB picks another build of the same library (A/B timing of two builds inside one gpurun call)
+LIB_PATH = os.environ.get("BWT_B200_LIB") or os.path.join(_HERE, "libbwt_b200.so")
 
 
 class BwtError(RuntimeError):

@@ -98,6 +98,34 @@ __host__ __device__ __forceinline__ int bwt_code(uint8_t c) {
     return c == 'A' ? 0 : c == 'C' ? 1 : c == 'G' ? 2 : c == 'T' ? 3 : -1;
 }
 
+#ifdef __CUDACC__
+// Up to 16 ASCII bases at src (any alignment) -> 2-bit codes (c>>1)&3 (A0 C1 T2 G3), base t at bits 2t; ok is cleared
+// when a byte is not one of A,C,G,T.  Reads aligned 32-bit words, up to 7 bytes beyond the last base: every buffer the
+// kernels see carries 16 bytes of slack.  Four bases are converted and validated at a time.
+__device__ __forceinline__ uint32_t pack16_acgt(const uint8_t *src, int cnt, bool &ok) {
+    const uintptr_t a = reinterpret_cast<uintptr_t>(src);
+    const uint32_t *base = reinterpret_cast<const uint32_t *>(a & ~(uintptr_t)3);
+    const int sh = (int)(a & 3) * 8;
+    uint32_t prev = __ldg(base), out = 0;
+#pragma unroll
+    for (int t4 = 0; t4 < 4; t4++) {
+        const int left = cnt - 4 * t4;
+        if (left > 0) {
+            const uint32_t next = __ldg(base + t4 + 1);
+            uint32_t wv = __funnelshift_r(prev, next, sh);
+            prev = next;
+            if (left < 4) wv = (wv & ((1u << (8 * left)) - 1u)) | (0x41414141u << (8 * left));   // pad with 'A'
+            const uint32_t x = (wv >> 1) & 0x03030303u;
+            // the ASCII byte each code stands for, four at a time: A 0x41, C 0x43, G 0x47, T 0x54
+            const uint32_t x0 = x & 0x01010101u, x1 = (x >> 1) & 0x01010101u, tt = x1 & ~x0;
+            ok &= ((0x40404040u | (x0 << 1) | (x1 << 2) | (tt << 4) | (tt ^ 0x01010101u)) == wv);
+            out |= (((x * 0x00041041u) >> 18) & 0xFFu) << (8 * t4);
+        }
+    }
+    return out;
+}
+#endif
+
 static inline uint64_t div_up_u64(uint64_t a, uint64_t b) { return (a + b - 1) / b; }
 
 // ---- device scan (scan.cu) ----------------------------------------------------------------------

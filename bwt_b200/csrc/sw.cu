@@ -237,36 +237,10 @@ __device__ __forceinline__ bool sw_traceback(const SwFastParams &p, const uint2 
     return true;
 }
 
-// Packs `len` ASCII bases at src (any alignment) into 2-bit codes (c>>1)&3 (A0 C1 T2 G3), 16 per word, word k to
-// dst[k*stride]; returns false if a byte is not one of A,C,G,T.  Reads aligned 32-bit words (up to 7 bytes beyond the
-// last base: every buffer handed to the kernel carries 16 bytes of slack) and validates four bases at a time.
+// Packs `len` ASCII bases at src into 2-bit codes, 16 per word, word k to dst[k*stride]; false if not all ACGT.
 __device__ __forceinline__ bool sw_pack2(const uint8_t *src, int len, uint32_t *dst, int stride) {
-    const uintptr_t a = reinterpret_cast<uintptr_t>(src);
-    const uint32_t *base = reinterpret_cast<const uint32_t *>(a & ~(uintptr_t)3);
-    const int sh = (int)(a & 3) * 8;
-    uint32_t prev = __ldg(base);
-    int k = 1;
     bool ok = true;
-    for (int j0 = 0; j0 < len; j0 += 16) {
-        uint32_t out = 0;
-#pragma unroll
-        for (int t4 = 0; t4 < 4; t4++) {
-            const int left = len - (j0 + 4 * t4);
-            if (left > 0) {
-                const uint32_t next = __ldg(base + k);
-                k++;
-                uint32_t wv = __funnelshift_r(prev, next, sh);
-                prev = next;
-                if (left < 4) wv = (wv & ((1u << (8 * left)) - 1u)) | (0x41414141u << (8 * left));   // pad with 'A'
-                const uint32_t x = (wv >> 1) & 0x03030303u;
-                // the ASCII byte each code stands for, four at a time: A 0x41, C 0x43, G 0x47, T 0x54
-                const uint32_t x0 = x & 0x01010101u, x1 = (x >> 1) & 0x01010101u, tt = x1 & ~x0;
-                ok &= ((0x40404040u | (x0 << 1) | (x1 << 2) | (tt << 4) | (tt ^ 0x01010101u)) == wv);
-                out |= (((x * 0x00041041u) >> 18) & 0xFFu) << (8 * t4);
-            }
-        }
-        dst[(j0 >> 4) * stride] = out;
-    }
+    for (int j0 = 0; j0 < len; j0 += 16) dst[(j0 >> 4) * stride] = pack16_acgt(src + j0, min(16, len - j0), ok);
     return ok;
 }
 

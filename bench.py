@@ -81,7 +81,11 @@ class ClockSampler:
         for ln in self.p.stdout:
             self.rows.append([x.strip() for x in ln.split(",")])
 
-    def stop(self):
+    def mark(self):
+        """number of samples so far: call at the start and at the end of the timed region"""
+        return len(self.rows)
+
+    def stop(self, lo=0, hi=None):
         if not self.p:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.p.terminate()
@@ -91,7 +95,10 @@ class ClockSampler:
             self.p.kill()
         self.t.join(timeout=2)
         sm, mx, reasons, pw = [], [], set(), []
-        for r in self.rows:
+        hi = len(self.rows) if hi is None else hi
+        # samples taken inside the timed region; the loop period can exceed a short region: then the samples next to it
+        rows = self.rows[lo:hi] if hi > lo else self.rows[max(0, lo - 1):hi + 1]
+        for r in rows:
             try:
                 sm.append(float(r[1])); mx.append(float(r[2])); pw.append(float(r[3]))
             except (ValueError, IndexError):
@@ -204,11 +211,12 @@ def main():
     batch.upload(reads, offs)
 
     # -- resident: warm-up, then K timed steps (CUDA events inside the library, on the batch's own stream)
+    clocks = ClockSampler(dev)
+    clocks.start()                    # before the warm-up: nvidia-smi needs a moment to deliver its first sample
     for _ in range(max(a.warmup, 0)):
         batch.run()
-    clocks = ClockSampler(dev)
     barrier()
-    clocks.start()
+    c_lo = clocks.mark()
     w0 = time.perf_counter()
     ev_ms = 0.0
     agg = dict(lf=0, hbm_lf=0, located=0, searches=0, clusters=0, sw_calls=0, cells=0, general=0, launches=0,
@@ -224,7 +232,8 @@ def main():
         agg["ms_seed"] += s.ms_seed; agg["ms_swstage"] += s.ms_sw; agg["ms_emit"] += s.ms_emit
     barrier()
     wall_ms = (time.perf_counter() - w0) * 1e3
-    clk = clocks.stop()
+    time.sleep(0.12)                  # let the sample that covers the end of the region arrive
+    clk = clocks.stop(c_lo, clocks.mark())
     n_hits, cig_bytes = batch.result_size()
 
     # -- end to end through the C ABI: pinned host reads -> H2D -> run -> D2H of the hit tuples, every step

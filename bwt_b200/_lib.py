@@ -43,6 +43,11 @@ class BwtStats(C.Structure):
                 ("launches", C.c_uint32), ("reserved", C.c_uint32)]
 
 
+class BwtFsStats(C.Structure):
+    _fields_ = [("queries", C.c_uint64), ("nodes", C.c_uint64), ("lf_steps", C.c_uint64), ("raw_hits", C.c_uint64),
+                ("seeds", C.c_uint64), ("spills", C.c_uint64), ("ms_kernel", C.c_float), ("launches", C.c_uint32)]
+
+
 # every symbol include/bwt_b200.h declares: (restype, argtypes)
 P = C.c_void_p
 SIGNATURES = {
@@ -77,6 +82,8 @@ SIGNATURES = {
                                   C.POINTER(C.c_int64)]),
     "bwt_aligner_stats": (C.c_int, [P, C.POINTER(BwtStats)]),
     "bwt_aligner_destroy": (C.c_int, [P]),
+    "bwt_fs_find_seeds_batch": (C.c_int, [P, P, P, C.c_int64, C.c_int32, C.c_int32, C.c_int32, P, P, P, C.c_int64,
+                                          C.POINTER(C.c_int64), C.POINTER(BwtFsStats)]),
     "bwt_fastq_parse": (C.c_int, [P, C.c_int64, C.c_int, C.c_int64, P, C.c_int64, P, P, P, C.POINTER(C.c_int64),
                                   C.POINTER(C.c_int64)]),
     "bwt_search_resident": (C.c_int, [P, P, C.c_int64, C.c_int32, C.c_int32, C.POINTER(C.c_float),

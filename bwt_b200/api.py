@@ -9,7 +9,7 @@ from typing import List, Optional, Sequence, Tuple
 
 import numpy as np
 
-from ._lib import BwtError, BwtHit, BwtIndexInfo, BwtStats, NoSpace, check, lib
+from ._lib import BwtError, BwtFsStats, BwtHit, BwtIndexInfo, BwtStats, NoSpace, check, lib
 
 HIT_DTYPE = np.dtype([("pos", "<i8"), ("s", "<i8"), ("cigar_off", "<i8"), ("d", "<i4"), ("score", "<i4"),
                       ("status", "<i4"), ("cigar_len", "<i4")])
@@ -18,6 +18,7 @@ assert HIT_DTYPE.itemsize == C.sizeof(BwtHit) == 40
 SEEDS, NO_SEEDS, TOO_MANY_SEEDS, SEARCH_CRASH = 0, 1, 2, 3
 READ_OK, READ_CRASH, READ_LIMIT = 0, 1, 2
 HIT_MATCH, HIT_NO_MATCH, HIT_WINDOW_OOR = 0, 1, 2
+FS_OK, FS_SHORT, FS_LIMIT = 0, 1, 2
 
 
 def _u8(a) -> np.ndarray:
@@ -189,6 +190,31 @@ class Index:
                 continue
             check(rc)
             return st, ho, hits[:nh.value].copy(), cig[:nc.value].tobytes()
+
+    # -- seeds:generate_fs/3 + fs:find_seeds/1 (seeds.erl:11-62) ------------------------------------------
+    def fs_find_seeds(self, queries, offsets=None, length: int = 20, defects: int = 2, max_raw_hits: int = 1024):
+        """-> (status int32[n], seed_offsets int64[n+1], seeds int64[total] (1-based window starts, descending per
+        query, as fs:find_seeds/1 returns them), BwtFsStats)"""
+        if offsets is None:
+            queries, offsets = pack(queries)
+        queries = _u8(queries)
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        n = len(offsets) - 1
+        st = np.zeros(n, np.int32)
+        so = np.zeros(n + 1, np.int64)
+        cap = max(16, 2 * n)
+        total = C.c_int64()
+        stats = BwtFsStats()
+        while True:
+            seeds = np.zeros(cap, np.int64)
+            rc = lib().bwt_fs_find_seeds_batch(self._h, queries.ctypes.data, offsets.ctypes.data, n, int(length),
+                                               int(defects), int(max_raw_hits), st.ctypes.data, so.ctypes.data,
+                                               seeds.ctypes.data, cap, C.byref(total), C.byref(stats))
+            if rc == -6:
+                cap = int(total.value) + 16
+                continue
+            check(rc)
+            return st, so, seeds[:total.value].copy(), stats
 
 
 def sw_batch(q, q_offsets, r, r_offsets, device: int = 0):

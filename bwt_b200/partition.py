@@ -116,3 +116,69 @@ def align_partitioned(index: api.Index, reads, offsets, group=None, device="cpu"
     """This rank's partition against all reads + the gather; rank 0 returns the merged result."""
     res = aligner.run(reads, offsets) if aligner is not None else index.align(reads, offsets)
     return gather_hits(res[0], res[1], res[2], res[3], group=group, device=device)
+
+
+# ---- bounded-edit search (seeds.erl) across partitions: BASELINE.json configs[4] ----------------------------------------
+def merge_seed_partitions(parts):
+    """parts[p] = (status int32[n], seed_offsets int64[n+1], seeds int64 (1-based window starts in partition p's chunk,
+    descending per query), shift (the partition's meta shift)) -> (status[world, n], offsets[n+1], pos int64[total],
+    part int32[total]); per query the seeds of partition 0, then 1, ..., each turned into the 1-based contig coordinate
+    (N - 1) + Shift -- the same mapping worker_bwt.erl:94 applies to window starts."""
+    n = len(parts[0][1]) - 1
+    counts = np.stack([np.diff(p[1]) for p in parts])
+    so = np.zeros(n + 1, np.int64)
+    np.cumsum(counts.sum(axis=0), out=so[1:])
+    pos = np.zeros(int(so[n]), np.int64)
+    part = np.zeros(int(so[n]), np.int32)
+    before = np.zeros(n, np.int64)
+    for p, (st, pso, sd, shift) in enumerate(parts):
+        if len(sd):
+            q_of = np.repeat(np.arange(n), counts[p])
+            dst = so[q_of] + before[q_of] + (np.arange(len(sd)) - pso[q_of])
+            pos[dst] = np.asarray(sd, np.int64) - 1 + int(shift)
+            part[dst] = p
+        before += counts[p]
+    return np.stack([p[0] for p in parts]), so, pos, part
+
+
+def gather_seeds(status: np.ndarray, seed_offsets: np.ndarray, seeds: np.ndarray, shift: int, group=None, device="cpu"):
+    """The exchange step of the inexact mode: all_gather of the sizes, then of status | offsets | seeds (padded to the
+    largest rank); rank 0 returns merge_seed_partitions(...), the others None."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    n = len(seed_offsets) - 1
+    sizes = torch.tensor([len(seeds), int(shift)], dtype=torch.int64, device=device)
+    all_sizes = [torch.zeros_like(sizes) for _ in range(world)]
+    dist.all_gather(all_sizes, sizes, group=group)
+    all_sizes = [tuple(int(v) for v in s.cpu()) for s in all_sizes]
+    max_s = max(s[0] for s in all_sizes)
+    rec = np.zeros(4 * n + 8 * (n + 1) + 8 * max_s, dtype=np.uint8)
+    o = 0
+    rec[o:o + 4 * n] = np.ascontiguousarray(status, np.int32).view(np.uint8); o += 4 * n
+    rec[o:o + 8 * (n + 1)] = np.ascontiguousarray(seed_offsets, np.int64).view(np.uint8); o += 8 * (n + 1)
+    rec[o:o + 8 * len(seeds)] = np.ascontiguousarray(seeds, np.int64).view(np.uint8)
+    mine = _as_torch(rec, device)
+    gathered = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(gathered, mine, group=group)
+    if rank != 0:
+        return None
+    parts = []
+    for p in range(world):
+        buf = gathered[p].cpu().numpy()
+        ns, sh = all_sizes[p]
+        o = 0
+        st = buf[o:o + 4 * n].view(np.int32); o += 4 * n
+        so = buf[o:o + 8 * (n + 1)].view(np.int64); o += 8 * (n + 1)
+        sd = buf[o:o + 8 * ns].view(np.int64)
+        parts.append((st, so, sd, sh))
+    return merge_seed_partitions(parts)
+
+
+def fs_find_seeds_partitioned(index: api.Index, queries, offsets, length: int, defects: int, max_raw_hits: int = 1024,
+                              group=None, device="cpu"):
+    """This rank's partition against all queries (bwt_fs_find_seeds_batch) + the gather; rank 0 returns the merged
+    (status, offsets, contig positions, partition of each seed) and every rank the stats of its own search."""
+    st, so, sd, stats = index.fs_find_seeds(queries, offsets, length, defects, max_raw_hits)
+    return gather_seeds(st, so, sd, int(index.info().shift), group=group, device=device), stats

@@ -59,6 +59,14 @@ enum {
     BWT_HIT_WINDOW_OOR = 2  /* window outside the padded reference: badmatch at worker_bwt.erl:89 */
 };
 
+/* per-query status of the bounded-edit search (bwt_fs_find_seeds_batch) */
+enum {
+    BWT_FS_OK = 0,
+    BWT_FS_SHORT = 1,       /* Qsec shorter than Len + Defects: the fs.erl that seeds:generate_fs/3 writes has no usable
+                               clause or does not compile (a clause with fewer than Len arguments, seeds.erl:51-55) */
+    BWT_FS_LIMIT = 2        /* more than max_raw_hits/2 distinct matching windows, or the search stack outgrew its HBM spill area */
+};
+
 #define BWT_MAX_READ_LEN 1031          /* 128 subsequences of sga:sga/6 */
 #define BWT_MAX_SEEDS_PER_READ (1 << 22)
 
@@ -197,6 +205,31 @@ int bwt_aligner_run(bwt_aligner *a, const uint8_t *reads, const int64_t *offsets
                     int64_t cigar_cap, int64_t *cigar_bytes);
 int bwt_aligner_stats(bwt_aligner *a, bwt_stats *out);   /* sums over the chunks of the last run */
 int bwt_aligner_destroy(bwt_aligner *a);
+
+/* ---- bounded-edit search: seeds:generate_fs/3 + the fs:find_seeds/1 it generates (seeds.erl:11-62) -------------- */
+
+typedef struct bwt_fs_stats {
+    uint64_t queries, nodes, lf_steps, raw_hits, seeds, spills;  /* search states expanded, LF steps (one child each),
+                                                                    distinct matching windows before the walk, seeds kept,
+                                                                    stack spills to HBM */
+    float ms_kernel;         /* CUDA-event time of fs_search_kernel (all passes) */
+    uint32_t launches;
+} bwt_fs_stats;
+
+/* For every query Qsec: the list fs:find_seeds(Ref_Seq) returns after seeds:generate_fs(Qsec, Len, Defects), with
+ * Ref_Seq = the text of this index partition.  A window of Len characters matches when it fits one of gen_pattern/5's
+ * patterns (the first Len+Defects query characters with exactly `Defects` edits: `_` for a character, `_` inserted,
+ * character dropped; seeds.erl:51-62); the walk takes the leftmost matching window, jumps Len ahead, repeats
+ * (seeds.erl:23-43).  seeds[seed_offsets[r] .. seed_offsets[r+1]) = 1-based window starts N of query r in DESCENDING
+ * order, exactly the accumulator the Erlang function returns.  The patterns are never materialised: one warp per
+ * query walks the recursion on the FM index (inexact.cu).  The index text is over ACGT (the builder maps IUPAC codes
+ * as fm_index.erl:131-135), so a query character outside ACGT can only be covered by a defect.
+ * max_raw_hits (<= 0: 1024): per-query scratch for matching windows before the greedy walk; BWT_FS_LIMIT once more
+ * than half of it is taken by distinct windows.
+ * BWT_ERR_NOSPACE (with *total = needed) when cap is too small; status / seeds / stats may be NULL. */
+int bwt_fs_find_seeds_batch(bwt_index *h, const uint8_t *queries, const int64_t *offsets, int64_t n, int32_t len,
+                            int32_t defects, int32_t max_raw_hits, int32_t *status, int64_t *seed_offsets,
+                            int64_t *seeds, int64_t cap, int64_t *total, bwt_fs_stats *stats);
 
 /* ---- FASTQ ingest (host side; fastq:read_seq/1, fastq.erl:5-18) -------------------------------------------- */
 

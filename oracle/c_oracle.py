@@ -16,8 +16,8 @@ _SO = os.path.join(_HERE, "_build", "libbwt_oracle.so")
 
 
 def build_lib(force: bool = False) -> str:
-    src = os.path.join(_HERE, "bwt_oracle.c")
-    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+    srcs = [os.path.join(_HERE, f) for f in ("bwt_oracle.c", "seeds_oracle.c")]
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < max(os.path.getmtime(s) for s in srcs):
         subprocess.check_call(["make", "-C", _HERE, "-s"])
     return _SO
 
@@ -56,10 +56,36 @@ def lib():
         L.orc_align_batch.restype = C.c_int
         L.orc_align_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int64,
                                       C.c_void_p, C.c_void_p, C.POINTER(OrcStats)]
+        L.orc_fs_scan_patterns.restype = C.c_int64
+        L.orc_fs_scan_patterns.argtypes = [C.c_char_p, C.c_int64, C.c_int, C.c_char_p, C.c_int64, C.c_void_p, C.c_int64]
+        L.orc_fs_scan_dp.restype = C.c_int64
+        L.orc_fs_scan_dp.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_int64, C.c_void_p, C.c_int64,
+                                     C.c_void_p]
         L.orc_sizeof_cand.restype = C.c_size_t
         assert L.orc_sizeof_cand() == C.sizeof(OrcCand)
         _lib = L
     return _lib
+
+
+def c_fs_scan_patterns(patterns, length: int, ref: bytes) -> List[int]:
+    """fs:find_seeds/1 with the literal clause list (oracle/seeds_oracle.c) -> descending 1-based starts"""
+    blob = b"".join(patterns)
+    cap = len(ref) // max(1, length) + 2
+    out = np.zeros(cap, dtype=np.int64)
+    n = lib().orc_fs_scan_patterns(blob, len(patterns), length, ref, len(ref), out.ctypes.data, cap)
+    assert n >= 0
+    return out[:n].tolist()
+
+
+def c_fs_scan_dp(q: bytes, length: int, defects: int, ref: bytes, want_vec: bool = False):
+    """fs:find_seeds/1 with matches/Len as a reachability DP over gen_pattern/5 -> descending 1-based starts"""
+    cap = len(ref) // max(1, length) + 2
+    out = np.zeros(cap, dtype=np.int64)
+    vec = np.zeros(max(0, len(ref) - length + 1), dtype=np.uint8) if want_vec else None
+    n = lib().orc_fs_scan_dp(q, len(q), length, defects, ref, len(ref), out.ctypes.data, cap,
+                             vec.ctypes.data if want_vec else None)
+    assert n >= 0, "query shorter than Len + Defects (or Defects > 8)"
+    return (out[:n].tolist(), vec) if want_vec else out[:n].tolist()
 
 
 def c_sw(q: bytes, r: bytes, force_double: bool = False):

@@ -70,6 +70,52 @@ def test_partition_slices_follow_builder_formula():
     assert partition.partition_slices(100, 1) == [(0, 100, 1)]
 
 
+def _fake_seed_result(p, n, seed=9):
+    rng = np.random.default_rng(seed + 31 * p)
+    counts = rng.integers(0, 4, size=n)
+    so = np.zeros(n + 1, np.int64)
+    np.cumsum(counts, out=so[1:])
+    sd = np.concatenate([np.sort(rng.integers(1, 10_000, size=c))[::-1] for c in counts] + [np.zeros(0, np.int64)]).astype(np.int64)
+    st = rng.integers(0, 2, size=n).astype(np.int32)
+    return st, so, sd, 1 + 9_998 * p
+
+
+def _check_merged_seeds(merged, parts):
+    st, so, pos, part = merged
+    n = len(parts[0][1]) - 1
+    for r in range(n):
+        want = []
+        for p, (pst, pso, sd, shift) in enumerate(parts):
+            want += [(int(v) - 1 + shift, p) for v in sd[pso[r]:pso[r + 1]]]
+        assert list(zip(pos[so[r]:so[r + 1]].tolist(), part[so[r]:so[r + 1]].tolist())) == want
+    for p in range(len(parts)):
+        assert (st[p] == parts[p][0]).all()
+
+
+def test_seed_merge_is_concatenation_with_contig_coordinates():
+    parts = [_fake_seed_result(p, 200) for p in range(3)]
+    _check_merged_seeds(partition.merge_seed_partitions(parts), parts)
+
+
+def _seed_worker(rank, world, port, n, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        st, so, sd, shift = _fake_seed_result(rank, n)
+        merged = partition.gather_seeds(st, so, sd, shift, device="cpu")
+        if rank == 0:
+            _check_merged_seeds(merged, [_fake_seed_result(p, n) for p in range(world)])
+            q.put("ok")
+        else:
+            assert merged is None
+    except Exception as e:
+        q.put("rank %d: %r" % (rank, e))
+        raise
+    finally:
+        dist.destroy_process_group()
+
+
 def _worker(rank, world, port, n, q):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -102,6 +148,23 @@ def test_gather_over_gloo_world2():
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     procs = [ctx.Process(target=_worker, args=(r, 2, port, 300, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(100)
+    assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
+    assert q.get(timeout=5) == "ok"
+
+
+@pytest.mark.timeout(120)
+def test_seed_gather_over_gloo_world2():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_seed_worker, args=(r, 2, port, 300, q)) for r in range(2)]
     for p in procs:
         p.start()
     for p in procs:

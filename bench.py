@@ -219,7 +219,7 @@ def main():
     c_lo = clocks.mark()
     w0 = time.perf_counter()
     ev_ms = 0.0
-    agg = dict(lf=0, hbm_lf=0, located=0, searches=0, clusters=0, sw_calls=0, cells=0, general=0, launches=0,
+    agg = dict(lf=0, hbm_lf=0, located=0, searches=0, clusters=0, sw_calls=0, cells=0, general=0, launches=0, sc_calls=0, sc_cells=0,
                ms_sga=0.0, ms_sw=0.0, ms_seed=0.0, ms_swstage=0.0, ms_emit=0.0)
     for _ in range(a.steps):
         batch.run()
@@ -228,6 +228,7 @@ def main():
         agg["lf"] += s.lf_steps; agg["hbm_lf"] += s.hbm_lf_steps; agg["located"] += s.located_rows
         agg["searches"] += s.searches; agg["clusters"] += s.clusters; agg["sw_calls"] += s.sw_calls
         agg["cells"] += s.sw_cells; agg["general"] += s.sw_general; agg["launches"] += s.launches
+        agg["sc_calls"] += s.sw_shortcut; agg["sc_cells"] += s.sw_shortcut_cells
         agg["ms_sga"] += s.ms_sga_kernel; agg["ms_sw"] += s.ms_sw_kernel
         agg["ms_seed"] += s.ms_seed; agg["ms_swstage"] += s.ms_sw; agg["ms_emit"] += s.ms_emit
     barrier()
@@ -289,9 +290,12 @@ def main():
         #                instructions (8.5 per cell pair: PRMT, 2 VIADDMNMX, VIMNMX, VIADD.16x2, 3.5 LOP3 -- from SASS)
         sga_bytes = (64.0 * agg["hbm_lf"] + 8.0 * agg["searches"] + 4.0 * agg["located"] + float(n * a.read_len * K))
         sga_gbs = sga_bytes / (agg["ms_sga"] * 1e-3) / 1e9 if agg["ms_sga"] > 0 else 0.0
-        sw_bytes = agg["sw_calls"] * (2.0 * a.read_len + 16.0) + float(cig_bytes * K)
+        #   shortcut   : pairs whose result sw_classify_kernel proves without the DP (perfect / one-mismatch diagonal) are
+        #                NOT in the DP kernel's cell count: gcups = cells the DP kernel computed / its own time
+        dp_calls, dp_cells = agg["sw_calls"] - agg["sc_calls"], agg["cells"] - agg["sc_cells"]
+        sw_bytes = dp_calls * (2.0 * a.read_len + 16.0) + float(cig_bytes * K) * (dp_calls / max(1, agg["sw_calls"]))
         sw_gbs = sw_bytes / (agg["ms_sw"] * 1e-3) / 1e9 if agg["ms_sw"] > 0 else 0.0
-        gcups = agg["cells"] / (agg["ms_sw"] * 1e-3) / 1e9 if agg["ms_sw"] else 0.0
+        gcups = dp_cells / (agg["ms_sw"] * 1e-3) / 1e9 if agg["ms_sw"] else 0.0
         dominant = "sga_kernel" if agg["ms_sga"] >= agg["ms_sw"] else "sw_fast_kernel"
         share = {"sga_kernel": round(agg["ms_sga"] / t_ev, 3), "sw_fast_kernel": round(agg["ms_sw"] / t_ev, 3)}
         tr = load_traffic(dominant)
@@ -300,8 +304,10 @@ def main():
                 "frac": round(dom_gbs / hbm_peak, 4), "traffic": tr["dram_bytes_per_launch"] if tr else None,
                 "traffic_source": tr.get("source") if tr else None, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": dom_bytes / K, "ms_per_launch": dom_ms / K, "share_of_step": share,
-                "note": "the dominant kernel is the integer DP (sw_fast_kernel): it is bound by ALU-pipe issue, not by HBM; "
-                        "see roofline_alu for its real ceiling and roofline_sga for the memory-bound kernel"}
+                "note": ("the dominant kernel is the integer DP (sw_fast_kernel): it is bound by ALU-pipe issue, not by HBM; "
+                         "see roofline_alu for its real ceiling and roofline_sga for the memory-bound kernel") if dominant == "sw_fast_kernel"
+                else ("the dominant kernel is sga_kernel: dependent random 8-byte / 32-byte gathers over a 25 GB index (latency and "
+                      "DRAM-atom bound); frac_of_random_gather in roofline_sga is its fraction of the measured random-sector ceiling")}
         dpx_peak = extra.get("dpx_gops")
         roof_alu = {"kernel": "sw_fast_kernel", "bound": "alu-pipe issue (DPX VIADDMNMX.S16x2 / packed 16-bit)", "gcups": round(gcups, 1),
                     "achieved": round(gcups * 4.25, 1), "peak": dpx_peak, "unit": "Gop/s (ALU-pipe thread instructions)",
@@ -329,7 +335,9 @@ def main():
                      "hbm_lf_steps_per_read": agg["hbm_lf"] / (n * K), "lf_steps_per_read": agg["lf"] / (n * K),
                      "located_rows_per_read": agg["located"] / (n * K), "clusters_per_read": agg["clusters"] / (n * K),
                      "sw_calls_per_read": agg["sw_calls"] / (n * K), "cells_per_read": agg["cells"] / (n * K),
-                     "sw_gcups": agg["cells"] / (agg["ms_sw"] * 1e-3) / 1e9 if agg["ms_sw"] else None,
+                     "sw_gcups": gcups,
+                     "sw_shortcut_pairs_frac": agg["sc_calls"] / max(1, agg["sw_calls"]),
+                     "sw_cells_equivalent_gcups": agg["cells"] / (agg["ms_swstage"] * 1e-3) / 1e9 if agg["ms_swstage"] else None,
                      "sw_general_pairs": agg["general"], "hits_per_step": n_hits,
                      "ms_stage": {"seed": agg["ms_seed"] / K, "sw": agg["ms_swstage"] / K, "emit": agg["ms_emit"] / K}},
         }

@@ -40,7 +40,8 @@ class BwtStats(C.Structure):
                 ("sw_cells", C.c_uint64), ("sw_general", C.c_uint64),
                 ("ms_total", C.c_float), ("ms_seed", C.c_float), ("ms_sw", C.c_float), ("ms_emit", C.c_float),
                 ("ms_h2d", C.c_float), ("ms_d2h", C.c_float), ("ms_sga_kernel", C.c_float), ("ms_sw_kernel", C.c_float),
-                ("launches", C.c_uint32), ("reserved", C.c_uint32)]
+                ("launches", C.c_uint32), ("reserved", C.c_uint32),
+                ("sw_shortcut", C.c_uint64), ("sw_shortcut_cells", C.c_uint64)]
 
 
 class BwtFsStats(C.Structure):

@@ -59,6 +59,8 @@ struct DevIndex {
     const uint32_t *sa;        // full suffix array, SA[e-1] for 1-based row e (fmi.erl:89-100 reads it un-sampled)
     const uint2 *kmer;         // 4^8 entries, depth-8 interval table (format: KmerEntry below)
     const uint2 *kmer_deep;    // 4^deep_k entries, or null
+    const uint2 *kmer_mid;     // the tables of depth 9..deep_k-1 back to back (kmer_mid_offset), or null: a subsequence
+                               // with fewer than deep_k plain characters at its end still costs ONE lookup
     int deep_k;                // 9..15, or 0 when there is no deep table
     const uint8_t *ref;        // .ref padded with 200 'N' on both sides (worker_bwt.erl:53-55)
     uint64_t ref_len_padded;
@@ -82,6 +84,9 @@ __host__ __device__ __forceinline__ uint2 kmer_pack(uint32_t sp, uint32_t ep, in
     return make_uint2(sp, w | ((uint32_t)n << 28));
 }
 
+// first entry of the depth-d table inside kmer_mid: 4^9 + ... + 4^(d-1)
+__host__ __device__ __forceinline__ uint64_t kmer_mid_offset(int d) { return ((1ull << (2 * d)) - (1ull << 18)) / 3ull; }
+
 struct bwt_index {
     DevIndex dv{};
     int device = 0;
@@ -90,7 +95,8 @@ struct bwt_index {
     uint32_t pointers[4] = {0, 0, 0, 0};
     int64_t shift = 0;
     uint64_t device_bytes = 0;
-    void *d_occ = nullptr, *d_sa = nullptr, *d_kmer = nullptr, *d_ref = nullptr, *d_kmer_deep = nullptr;
+    uint64_t mid_bytes = 0;    // kmer_mid part of device_bytes
+    void *d_occ = nullptr, *d_sa = nullptr, *d_kmer = nullptr, *d_ref = nullptr, *d_kmer_deep = nullptr, *d_kmer_mid = nullptr;
 };
 
 // ASCII -> index code (A0 C1 G2 T3), -1 otherwise

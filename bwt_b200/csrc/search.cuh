@@ -87,10 +87,14 @@ __device__ __forceinline__ SearchRes search_core(const DevIndex &ix, const uint8
     int n = 1, k = len - 2;
     bool have = false, stopped = false;
     if (use_table && good >= BWT_MIN_LEN) {
-        // the table of depth d applies when the d-1 characters before the last are plain ACGT
-        const int depth = (ix.deep_k > 0 && good >= ix.deep_k) ? ix.deep_k : BWT_MIN_LEN;
-        uint2 e = depth == BWT_MIN_LEN ? __ldg(ix.kmer + (idx & 0xFFFFu))
-                                       : __ldg(ix.kmer_deep + (idx & ((1u << (2 * depth)) - 1u)));
+        // the table of depth d applies when the d-1 characters before the last are plain ACGT: the deepest one that fits
+        int depth = BWT_MIN_LEN;
+        const uint2 *tab = ix.kmer;
+        if (ix.deep_k > 0) {
+            if (good >= ix.deep_k) { depth = ix.deep_k; tab = ix.kmer_deep; }
+            else if (good > BWT_MIN_LEN && ix.kmer_mid) { depth = good; tab = ix.kmer_mid + kmer_mid_offset(good); }
+        }
+        const uint2 e = __ldg(tab + (idx & (uint32_t)((1ull << (2 * depth)) - 1ull)));
         int ne = (int)(e.y >> 28);
         if (ne) {
             R.table = ne;                              // characters whose steps the table served

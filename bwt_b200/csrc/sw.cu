@@ -22,6 +22,7 @@
 //     back by the traceback.
 // General path (any byte, e.g. 'N' = 1.6 or IUPAC codes in the window, or sizes beyond the fast tiers):
 //   IEEE doubles added in the reference's order, one thread per pair, rows in HBM scratch.
+#include <cstdlib>
 #include <type_traits>
 
 #include "sw.cuh"
@@ -47,23 +48,153 @@ __device__ __forceinline__ int lane16(uint32_t x, int lane) { return lane ? ((in
 __device__ __forceinline__ uint32_t both(int k) { return ((uint32_t)k & 0xFFFFu) * 0x10001u; }
 
 // ---------------------------------------------------------------------------------------------------
-// classification: narrow list / wide list / general list / immediate no_match
+// Pairs whose sw:sw/2 result is known without filling the table.
+//
+// Both strings plain ACGT, window slack Dd = Lr - Lq in 0..SW_SHORTCUT_MAX_D, Lq >= 4.  Diagonal o (0 <= o <= Dd) pairs
+// query character i with window character o + i.  With sigma in {2, -1}, gap open -2 / extend -1 and the reference's
+// direction-dependent gap rule never scoring a gapped path HIGHER than plain affine gaps would (sw.erl:88-107), every
+// path into the last row scores at most  2*Lq - 3*mismatches - 2*inserted - sum over gaps (1 + length):
+//   (a) some diagonal matches perfectly: Vmax = 2*Lq, reached only by perfect diagonals; get_starting_point takes the
+//       smallest column (sw.erl:110-112) = the smallest perfect o; every cell on that diagonal holds the row's largest
+//       possible value through its up_left candidate, which wins ties (up_left > up > left): CIGAR = "<Lq>M";
+//   (b) no perfect diagonal, some diagonal has exactly one mismatch: only a single deletion of one or two window
+//       characters between perfectly matching flanks could score as much (2*Lq-2, 2*Lq-3).  If no such split exists
+//       (lcp(o) + lcsuf(o + len) < Lq for len = 1, 2 and every o), Vmax = 2*Lq - 3 on the smallest one-mismatch
+//       diagonal, nothing left of it reaches that value, and the same tie argument gives "<Lq>M" again.
+// The row threshold -2*(Lq div 2) + 2*i (sw.erl:62,69-71) is never undercut on such a diagonal (Lq >= 4).
+// Everything else runs the DP.  tests/test_gpu_parity.py runs its SW cases with this shortcut on and off.
 // ---------------------------------------------------------------------------------------------------
-__global__ void sw_classify_kernel(const SwDesc *__restrict__ desc, SwOut *__restrict__ out, uint32_t n,
-                                   int cap_narrow, int cap_wide, uint32_t *__restrict__ list_fast,
-                                   uint32_t *__restrict__ list_wide, uint32_t *__restrict__ list_gen, SwCounters *ctr) {
-    uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= n) return;
-    if (out[k].status == BWT_HIT_WINDOW_OOR) return;
-    SwDesc d = desc[k];
-    if (d.lq <= 0 || d.lr <= 0) {                   // sw(_,_) -> no_match for empty strings (sw.erl:54)
-        SwOut o; o.score = 0; o.status = BWT_HIT_NO_MATCH; o.cigar_len = 0; o.cigar_off = 0;
-        out[k] = o;
-        return;
+__device__ __forceinline__ uint32_t ldu32(const uint8_t *p) {           // unaligned 32-bit load (buffers carry 16 B of slack)
+    const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+    const uint32_t *b = reinterpret_cast<const uint32_t *>(a & ~(uintptr_t)3);
+    const int sh = (int)(a & 3) * 8;
+    const uint32_t lo = __ldg(b);
+    return sh ? __funnelshift_r(lo, __ldg(b + 1), sh) : lo;
+}
+
+__device__ __forceinline__ bool acgt4(uint32_t wv) {                    // are all four bytes one of A, C, G, T
+    const uint32_t x = (wv >> 1) & 0x03030303u;
+    const uint32_t x0 = x & 0x01010101u, x1 = (x >> 1) & 0x01010101u, tt = x1 & ~x0;
+    return (0x40404040u | (x0 << 1) | (x1 << 2) | (tt << 4) | (tt ^ 0x01010101u)) == wv;
+}
+
+__device__ __forceinline__ bool acgt_all(const uint8_t *s, int len) {
+    int k = 0;
+    for (; k + 4 <= len; k += 4)
+        if (!acgt4(ldu32(s + k))) return false;
+    if (k < len) {
+        const int left = len - k;
+        const uint32_t wv = (ldu32(s + k) & ((1u << (8 * left)) - 1u)) | (0x41414141u << (8 * left));
+        if (!acgt4(wv)) return false;
     }
-    if (d.lq <= SW_FAST_MAX_LQ && d.lr + 1 <= cap_narrow) list_fast[atomicAdd(&ctr->n_fast, 1u)] = k;
-    else if (d.lq <= SW_FAST_MAX_LQ && d.lr + 1 <= cap_wide) list_wide[atomicAdd(&ctr->n_wide, 1u)] = k;
-    else list_gen[atomicAdd(&ctr->n_general, 1u)] = k;
+    return true;
+}
+
+// 0 = run the DP; otherwise the score of the pair, whose CIGAR is "<Lq>M"
+__device__ __forceinline__ int sw_shortcut(const uint8_t *q, int lq, const uint8_t *r, int lr) {
+    const int dd = lr - lq;
+    if (dd < 0 || dd > SW_SHORTCUT_MAX_D || lq < 4) return 0;
+    if (!acgt_all(q, lq) || !acgt_all(r, lr)) return 0;
+    int lcp1 = -1, lcp2 = -1;                       // lcp(o-1), lcp(o-2); -1 = no such diagonal
+    bool one = false, split = false;
+    for (int o = 0; o <= dd; o++) {
+        const uint8_t *w = r + o;
+        int x = 0;
+        for (; x + 4 <= lq; x += 4) {
+            const uint32_t df = ldu32(q + x) ^ ldu32(w + x);
+            if (df) { x += (__ffs((int)df) - 1) >> 3; goto lcp_done; }
+        }
+        while (x < lq && q[x] == w[x]) x++;
+    lcp_done:
+        if (x == lq) return 2 * lq;                 // (a): the smallest perfect diagonal
+        int y = 0;
+        for (; y + 4 <= lq; y += 4) {
+            const uint32_t df = ldu32(q + lq - y - 4) ^ ldu32(w + lq - y - 4);
+            if (df) { y += __clz((int)df) >> 3; goto lcs_done; }
+        }
+        while (y < lq && q[lq - 1 - y] == w[lq - 1 - y]) y++;
+    lcs_done:
+        one |= x + y == lq - 1;
+        split |= (lcp1 >= 0 && lcp1 + y >= lq) || (lcp2 >= 0 && lcp2 + y >= lq);
+        lcp2 = lcp1; lcp1 = x;
+    }
+    return (one && !split) ? 2 * lq - 3 : 0;       // (b)
+}
+
+// ---------------------------------------------------------------------------------------------------
+// classification: settled at once (no_match for empty strings, shortcut) / narrow list / wide list / general list
+// ---------------------------------------------------------------------------------------------------
+__global__ void sw_classify_kernel(const uint8_t *__restrict__ qbase, const uint8_t *__restrict__ rbase,
+                                   const SwDesc *__restrict__ desc, SwOut *__restrict__ out, uint32_t n,
+                                   int cap_narrow, int cap_wide, uint32_t *__restrict__ list_fast,
+                                   uint32_t *__restrict__ list_wide, uint32_t *__restrict__ list_gen, SwCounters *ctr,
+                                   char *__restrict__ cig, uint32_t cig_cap, int use_shortcut) {
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned lane = threadIdx.x & 31;
+    int score = 0, clen = 0, kind = -1;             // kind: 0 narrow, 1 wide, 2 general, 3 shortcut, -1 nothing to do
+    SwDesc d{};
+    if (k < n && out[k].status != BWT_HIT_WINDOW_OOR) {
+        d = desc[k];
+        if (d.lq <= 0 || d.lr <= 0) {               // sw(_,_) -> no_match for empty strings (sw.erl:54)
+            SwOut o; o.score = 0; o.status = BWT_HIT_NO_MATCH; o.cigar_len = 0; o.cigar_off = 0;
+            out[k] = o;
+        } else {
+            if (use_shortcut) score = sw_shortcut(qbase + d.q_off, d.lq, rbase + d.r_off, d.lr);
+            if (score) { kind = 3; clen = 2 + (d.lq >= 10) + (d.lq >= 100) + (d.lq >= 1000) + (d.lq >= 10000); }
+            else if (d.lq <= SW_FAST_MAX_LQ && d.lr + 1 <= cap_narrow) kind = 0;
+            else if (d.lq <= SW_FAST_MAX_LQ && d.lr + 1 <= cap_wide) kind = 1;
+            else kind = 2;
+        }
+    }
+    // one atomic per warp and list: the lanes of a kind take consecutive slots
+    uint32_t slot = 0;
+#pragma unroll
+    for (int t = 0; t < 3; t++) {
+        const unsigned m = __ballot_sync(0xFFFFFFFFu, kind == t);
+        if (m) {
+            uint32_t base = 0;
+            if (lane == (unsigned)(__ffs((int)m) - 1)) base = atomicAdd(t == 0 ? &ctr->n_fast : t == 1 ? &ctr->n_wide : &ctr->n_general, (uint32_t)__popc(m));
+            base = __shfl_sync(0xFFFFFFFFu, base, __ffs((int)m) - 1);
+            if (kind == t) slot = base + __popc(m & ((1u << lane) - 1u));
+        }
+    }
+    if (kind == 0) list_fast[slot] = k;
+    else if (kind == 1) list_wide[slot] = k;
+    else if (kind == 2) list_gen[slot] = k;
+    // shortcut pairs: CIGAR text "<Lq>M" from the temporary arena (one allocation per warp), result, counters
+    const unsigned ms = __ballot_sync(0xFFFFFFFFu, kind == 3);
+    if (ms) {
+        int incl = clen;
+        unsigned long long cells = kind == 3 ? (unsigned long long)d.lq * (unsigned)d.lr : 0ull;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+            if (lane >= (unsigned)o) incl += t;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) cells += __shfl_down_sync(0xFFFFFFFFu, cells, o);
+        const int total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+        uint32_t base = 0;
+        if (lane == 0) {
+            base = atomicAdd(&ctr->cig_used, (uint32_t)total);
+            atomicAdd(&ctr->sw_calls, (unsigned long long)__popc(ms));
+            atomicAdd(&ctr->cells, cells);
+            atomicAdd(&ctr->shortcut_calls, (unsigned long long)__popc(ms));
+            atomicAdd(&ctr->shortcut_cells, cells);
+            if ((uint64_t)base + total > cig_cap) atomicExch(&ctr->cig_overflow, 1u);
+        }
+        base = __shfl_sync(0xFFFFFFFFu, base, 0);
+        if (kind == 3) {
+            const uint32_t off = base + (uint32_t)(incl - clen);
+            if ((uint64_t)base + total <= cig_cap) {
+                int l = d.lq;
+                for (int t = clen - 2; t >= 0; t--) { cig[off + t] = (char)('0' + l % 10); l /= 10; }
+                cig[off + clen - 1] = 'M';
+            }
+            SwOut o; o.score = score; o.status = BWT_HIT_MATCH; o.cigar_len = clen; o.cigar_off = off;
+            out[k] = o;
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -565,8 +696,11 @@ void sw_stage_free(SwStage &st) {
 
 int sw_stage_run(SwStage &st, const uint8_t *d_qbase, const uint8_t *d_rbase, uint32_t n, int max_lq,
                  cudaStream_t stream) {
-    st.sw_calls = st.cells = st.n_general = 0;
+    st.sw_calls = st.cells = st.n_general = st.shortcut_calls = st.shortcut_cells = 0;
     st.ms_fast_kernel = 0;
+    // BWT_SW_SHORTCUT=0 sends every pair through the DP (A/B timing, and parity tests of the DP on easy pairs)
+    const char *env_sc = getenv("BWT_SW_SHORTCUT");
+    const int use_shortcut = !(env_sc && env_sc[0] == '0');
     if (n == 0) return BWT_OK;
     if (n > st.cap) { bwt_set_error("sw_stage_run: %u pairs exceed the reserved %u", n, st.cap); return BWT_ERR_ARG; }
     // two shared-memory tiers of the fast kernel: "narrow" holds windows up to Lq + 15 columns (almost every
@@ -598,8 +732,9 @@ int sw_stage_run(SwStage &st, const uint8_t *d_qbase, const uint8_t *d_rbase, ui
 
     for (int attempt = 0; attempt < 4; attempt++) {
         CU_TRY(cudaMemsetAsync(st.d_ctr, 0, sizeof(SwCounters), stream));
-        sw_classify_kernel<<<(n + 255) / 256, 256, 0, stream>>>(st.d_desc, st.d_out, n, cap_narrow, cap_wide, st.d_list_fast,
-                                                                st.d_list_wide, st.d_list_gen, st.d_ctr);
+        sw_classify_kernel<<<(n + 255) / 256, 256, 0, stream>>>(d_qbase, d_rbase, st.d_desc, st.d_out, n, cap_narrow, cap_wide,
+                                                                st.d_list_fast, st.d_list_wide, st.d_list_gen, st.d_ctr,
+                                                                st.d_cig_tmp, st.cig_cap, use_shortcut);
         K_CHECK(stream, "sw_classify_kernel");
         SwFastParams p;
         p.qbase = d_qbase; p.rbase = d_rbase; p.desc = st.d_desc; p.out = st.d_out;
@@ -669,6 +804,7 @@ int sw_stage_run(SwStage &st, const uint8_t *d_qbase, const uint8_t *d_rbase, ui
         if (!st.h_ctr->cig_overflow) {
             cudaEventElapsedTime(&st.ms_fast_kernel, st.ev_k0, st.ev_k1);
             st.sw_calls = st.h_ctr->sw_calls; st.cells = st.h_ctr->cells; st.n_general = st.h_ctr->n_general;
+            st.shortcut_calls = st.h_ctr->shortcut_calls; st.shortcut_cells = st.h_ctr->shortcut_cells;
             return BWT_OK;
         }
         // temporary CIGAR arena too small: grow to what this attempt asked for (and then some) and redo the stage

@@ -18,6 +18,7 @@ struct SwOut {           // 16 B per pair
 
 struct SwCounters {
     unsigned long long sw_calls, cells;
+    unsigned long long shortcut_calls, shortcut_cells;   // pairs settled by sw_classify_kernel without the DP (included above)
     uint32_t n_fast, n_wide, n_general, n_ovf;   // list cursors
     uint32_t cig_used, cig_overflow; // temporary CIGAR arena
     uint32_t general_done, pad;
@@ -25,6 +26,7 @@ struct SwCounters {
 
 constexpr int SW_R = 10;             // rows per register strip; ten 3-bit direction codes per 32-bit word
 constexpr int SW_BLOCK = 128;
+constexpr int SW_SHORTCUT_MAX_D = 16; // widest window slack (Lr - Lq) the no-DP shortcut looks at
 constexpr int SW_FAST_MAX_LQ = 400;  // query codes of the fast kernel: 25 words per lane; int16 keys are safe up to ~2000
 
 // Device-resident state of the extension stage (owned by a batch).
@@ -45,7 +47,7 @@ struct SwStage {
     size_t gen_off_cap = 0;
     int2 *d_gen_dims = nullptr;
     uint32_t launches = 0;
-    unsigned long long sw_calls = 0, cells = 0, n_general = 0;
+    unsigned long long sw_calls = 0, cells = 0, n_general = 0, shortcut_calls = 0, shortcut_cells = 0;
     cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr;   // around sw_fast_kernel
     float ms_fast_kernel = 0;
 };

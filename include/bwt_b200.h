@@ -103,6 +103,9 @@ typedef struct bwt_stats {   /* work counters of the last run (definitions: DESI
     float ms_sw_kernel;      /* sw_fast_kernel alone */
     uint32_t launches;       /* kernels of this library launched by the last run */
     uint32_t reserved;
+    uint64_t sw_shortcut, sw_shortcut_cells; /* pairs (and their cells, both INCLUDED in sw_calls / sw_cells) whose sw:sw/2
+                                                result was proven without filling the table: a perfect or one-mismatch
+                                                diagonal with no competing deletion (sw.cu, sw_shortcut) */
 } bwt_stats;
 
 const char *bwt_last_error(void);

@@ -19,6 +19,18 @@ from test_oracle_golden import (KAT_2_CIGARS, KAT_2_SGA, READ_KAT_1, READ_KAT_2,
                                 _rand_query, _rand_seq)
 
 
+@pytest.fixture(autouse=True, params=["shortcut", "dp_only"])
+def sw_mode(request):
+    """Every test of this file runs twice: with the no-DP shortcut of sw_classify_kernel (perfect / one-mismatch
+    diagonals) and with BWT_SW_SHORTCUT=0, which sends those pairs through the DP kernels as well."""
+    if request.param == "dp_only":
+        os.environ["BWT_SW_SHORTCUT"] = "0"
+    else:
+        os.environ.pop("BWT_SW_SHORTCUT", None)
+    yield request.param
+    os.environ.pop("BWT_SW_SHORTCUT", None)
+
+
 @pytest.fixture(scope="module")
 def gl_index(gl_fm, gl_ref):
     ix = api.Index.from_arrays(gl_fm.L, gl_fm.SA, gl_fm.pointers, gl_fm.shift, gl_ref)
@@ -250,6 +262,62 @@ def test_sw_parity_acgt():
     for it in range(500):                                   # unrelated strings: row-threshold aborts
         pairs.append((_rand_seq(rng, int(rng.integers(1, 120)), False), _rand_seq(rng, int(rng.integers(1, 160)), False)))
     assert _check_sw(pairs) > 4000
+
+
+def test_sw_shortcut_adversarial(sw_mode):
+    """Pairs aimed at the shortcut's decision: low-complexity and tandem-repeat strings (competing diagonals and
+    deletions between matching flanks), slack 0..20, zero to two substitutions or an indel."""
+    rng = np.random.default_rng(29)
+    pairs = []
+    for it in range(30000):
+        alpha = [b"ACGT", b"AC", b"ACGT", b"AAC", b"ACGT"][it % 5]
+        lq, dd = int(rng.integers(4, 130)), int(rng.integers(0, 21))
+        pick = lambda n: bytes(alpha[int(x)] for x in rng.integers(0, len(alpha), n))   # noqa: E731
+        mode = rng.random()
+        if mode < 0.55:
+            base = pick(lq + dd + 4)
+            s0 = int(rng.integers(0, dd + 3))
+            q = bytearray(base[s0:s0 + lq]) + bytearray(pick(max(0, lq - len(base[s0:s0 + lq]))))
+            for _ in range(int(rng.choice([0, 0, 1, 1, 1, 2]))):
+                u = rng.random()
+                if u < 0.7:
+                    q[int(rng.integers(0, lq))] = alpha[int(rng.integers(0, len(alpha)))]
+                elif u < 0.85 and len(q) > 5:
+                    del q[int(rng.integers(0, len(q)))]
+                    q += pick(1)
+                else:
+                    q.insert(int(rng.integers(0, len(q))), alpha[int(rng.integers(0, len(alpha)))])
+            pairs.append((bytes(q[:lq]), base[:lq + dd]))
+        elif mode < 0.85:
+            unit = pick(int(rng.integers(1, 5)))
+            base = (unit * 200)[:lq + dd]
+            r = bytearray(base)
+            for _ in range(int(rng.integers(0, 3))):
+                r[int(rng.integers(0, len(r)))] = b"ACGT"[int(rng.integers(0, 4))]
+            s0 = int(rng.integers(0, dd + 1))
+            q = bytearray(base[s0:s0 + lq])
+            for _ in range(int(rng.integers(0, 3))):
+                q[int(rng.integers(0, lq))] = b"ACGT"[int(rng.integers(0, 4))]
+            pairs.append((bytes(q), bytes(r)))
+        else:
+            pairs.append((pick(lq), pick(lq + dd)))
+    assert _check_sw(pairs) > 15000
+
+
+def test_shortcut_is_taken_and_counted(gl_index, gl_ref, sw_mode):
+    reads, offs, _ = sample_reads(gl_ref, 4000, 100, seed=77, edit_rate=0.01)
+    b = api.Batch(gl_index, 4000, len(reads))
+    try:
+        b.upload(reads, offs)
+        b.run()
+        s = b.stats()
+    finally:
+        b.close()
+    assert s.sw_calls > 1000
+    if sw_mode == "shortcut":
+        assert 0.1 * s.sw_calls < s.sw_shortcut <= s.sw_calls and 0 < s.sw_shortcut_cells <= s.sw_cells
+    else:
+        assert s.sw_shortcut == 0 and s.sw_shortcut_cells == 0
 
 
 def test_sw_parity_iupac_and_n():

@@ -32,7 +32,7 @@ def test_struct_layouts_match_header():
     from bwt_b200 import _lib, api
     assert C.sizeof(_lib.BwtHit) == 40 and api.HIT_DTYPE.itemsize == 40
     assert C.sizeof(_lib.BwtIndexInfo) == 64
-    assert C.sizeof(_lib.BwtStats) == 9 * 8 + 8 * 4 + 2 * 4
+    assert C.sizeof(_lib.BwtStats) == 9 * 8 + 8 * 4 + 2 * 4 + 2 * 8
 
 
 def test_no_cpu_fallback_without_device(tmp_path):

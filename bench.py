@@ -339,6 +339,7 @@ def main():
                      "sw_shortcut_pairs_frac": agg["sc_calls"] / max(1, agg["sw_calls"]),
                      "sw_cells_equivalent_gcups": agg["cells"] / (agg["ms_swstage"] * 1e-3) / 1e9 if agg["ms_swstage"] else None,
                      "sw_general_pairs": agg["general"], "hits_per_step": n_hits,
+                     "ms_sw_fast_kernels": agg["ms_sw"] / K, "ms_sga_kernel": agg["ms_sga"] / K,
                      "ms_stage": {"seed": agg["ms_seed"] / K, "sw": agg["ms_swstage"] / K, "emit": agg["ms_emit"] / K}},
         }
         if e2e:

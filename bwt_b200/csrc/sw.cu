@@ -78,47 +78,93 @@ __device__ __forceinline__ bool acgt4(uint32_t wv) {                    // are a
     return (0x40404040u | (x0 << 1) | (x1 << 2) | (tt << 4) | (tt ^ 0x01010101u)) == wv;
 }
 
-__device__ __forceinline__ bool acgt_all(const uint8_t *s, int len) {
-    int k = 0;
-    for (; k + 4 <= len; k += 4)
-        if (!acgt4(ldu32(s + k))) return false;
-    if (k < len) {
-        const int left = len - k;
-        const uint32_t wv = (ldu32(s + k) & ((1u << (8 * left)) - 1u)) | (0x41414141u << (8 * left));
-        if (!acgt4(wv)) return false;
+// Eight lanes per pair: lane t holds bytes [16t, 16t+16) of every 128-byte chunk, so a group's loads are coalesced and
+// one pass over a diagonal gives its first and last mismatch: lcp = first, lcsuf = Lq - 1 - last, and the diagonal has
+// exactly one mismatch iff first == last.
+constexpr int SC_LANES = 8;
+
+// 16 bytes at p (unaligned) -> 4 words; bytes at index >= valid are replaced by `fill`
+__device__ __forceinline__ void ld16(const uint8_t *p, int valid, uint32_t fill, uint32_t (&w)[4]) {
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const int left = valid - 4 * k;
+        uint32_t v = fill;
+        if (left > 0) {
+            v = ldu32(p + 4 * k);
+            if (left < 4) v = (v & ((1u << (8 * left)) - 1u)) | (fill << (8 * left));
+        }
+        w[k] = v;
     }
-    return true;
 }
 
-// 0 = run the DP; otherwise the score of the pair, whose CIGAR is "<Lq>M"
-__device__ __forceinline__ int sw_shortcut(const uint8_t *q, int lq, const uint8_t *r, int lr) {
+// reductions over the SC_LANES lanes of a group with FULL-mask shuffles: the four groups of a warp stay converged
+// (partial-mask primitives would split the warp into four serialised quarter-warps)
+__device__ __forceinline__ unsigned grp_min(unsigned v) {
+#pragma unroll
+    for (int o = 1; o < SC_LANES; o <<= 1) v = min(v, __shfl_xor_sync(0xFFFFFFFFu, v, o));
+    return v;
+}
+__device__ __forceinline__ unsigned grp_max(unsigned v) {
+#pragma unroll
+    for (int o = 1; o < SC_LANES; o <<= 1) v = max(v, __shfl_xor_sync(0xFFFFFFFFu, v, o));
+    return v;
+}
+
+// 0 = run the DP; otherwise the score of the pair, whose CIGAR is "<Lq>M".  Called by ALL lanes of the warp, converged;
+// the SC_LANES lanes of a group pass the same pair (valid = false: no pair); t = lane index inside the group.
+__device__ __forceinline__ int sw_shortcut(const uint8_t *q, int lq, const uint8_t *r, int lr, bool valid, int t, unsigned lane) {
+    const unsigned FULL = 0xFFFFFFFFu;
     const int dd = lr - lq;
-    if (dd < 0 || dd > SW_SHORTCUT_MAX_D || lq < 4) return 0;
-    if (!acgt_all(q, lq) || !acgt_all(r, lr)) return 0;
-    int lcp1 = -1, lcp2 = -1;                       // lcp(o-1), lcp(o-2); -1 = no such diagonal
-    bool one = false, split = false;
-    for (int o = 0; o <= dd; o++) {
-        const uint8_t *w = r + o;
-        int x = 0;
-        for (; x + 4 <= lq; x += 4) {
-            const uint32_t df = ldu32(q + x) ^ ldu32(w + x);
-            if (df) { x += (__ffs((int)df) - 1) >> 3; goto lcp_done; }
+    bool elig = valid && dd >= 0 && dd <= SW_SHORTCUT_MAX_D && lq >= 4;
+    // all plain ACGT?  (bytes past the end count as 'A')
+    bool plain = true;
+    if (elig)
+        for (int base = 16 * t; base < lr; base += 16 * SC_LANES) {
+            uint32_t w[4];
+            ld16(r + base, lr - base, 0x41414141u, w);
+            plain &= acgt4(w[0]) & acgt4(w[1]) & acgt4(w[2]) & acgt4(w[3]);
+            if (base < lq) {
+                ld16(q + base, lq - base, 0x41414141u, w);
+                plain &= acgt4(w[0]) & acgt4(w[1]) & acgt4(w[2]) & acgt4(w[3]);
+            }
         }
-        while (x < lq && q[x] == w[x]) x++;
-    lcp_done:
-        if (x == lq) return 2 * lq;                 // (a): the smallest perfect diagonal
-        int y = 0;
-        for (; y + 4 <= lq; y += 4) {
-            const uint32_t df = ldu32(q + lq - y - 4) ^ ldu32(w + lq - y - 4);
-            if (df) { y += __clz((int)df) >> 3; goto lcs_done; }
+    const unsigned plain_mask = __ballot_sync(FULL, plain);          // by every lane, before any short-circuit
+    elig = elig && ((plain_mask >> (lane - t)) & ((1u << SC_LANES) - 1u)) == ((1u << SC_LANES) - 1u);
+    const int dmax = (int)__reduce_max_sync(FULL, (unsigned)(elig ? dd + 1 : 0)) - 1;
+    int res = 0, lcp1 = -1, lcp2 = -1;              // lcp(o-1), lcp(o-2); -1 = no such diagonal
+    bool open = elig, one = false, split = false;  // open: no verdict yet
+    for (int o = 0; o <= dmax; o++) {
+        const bool act = open && o <= dd;
+        unsigned first = 0x7FFFFFFFu, lastp1 = 0;
+        if (act)
+            for (int base = 16 * t; base < lq; base += 16 * SC_LANES) {
+                uint32_t a[4], b[4];
+                ld16(q + base, lq - base, 0u, a);
+                ld16(r + o + base, lq - base, 0u, b);
+#pragma unroll
+                for (int k = 3; k >= 0; k--) {
+                    const uint32_t df = a[k] ^ b[k];
+                    if (df) {
+                        first = min(first, (unsigned)(base + 4 * k + ((__ffs((int)df) - 1) >> 3)));
+                        lastp1 = max(lastp1, (unsigned)(base + 4 * k + 4 - (__clz((int)df) >> 3)));
+                    }
+                }
+            }
+        first = grp_min(first);
+        lastp1 = grp_max(lastp1);
+        if (act) {
+            if (first == 0x7FFFFFFFu) { res = 2 * lq; open = false; }      // (a): the smallest perfect diagonal
+            else {
+                const int x = (int)first, y = lq - (int)lastp1;            // lcp, lcsuf
+                one |= x + y == lq - 1;
+                split |= (lcp1 >= 0 && lcp1 + y >= lq) || (lcp2 >= 0 && lcp2 + y >= lq);
+                lcp2 = lcp1; lcp1 = x;
+            }
         }
-        while (y < lq && q[lq - 1 - y] == w[lq - 1 - y]) y++;
-    lcs_done:
-        one |= x + y == lq - 1;
-        split |= (lcp1 >= 0 && lcp1 + y >= lq) || (lcp2 >= 0 && lcp2 + y >= lq);
-        lcp2 = lcp1; lcp1 = x;
+        if (__all_sync(FULL, !open || o >= dd)) break;
     }
-    return (one && !split) ? 2 * lq - 3 : 0;       // (b)
+    if (open && one && !split) res = 2 * lq - 3;    // (b)
+    return res;
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -129,22 +175,40 @@ __global__ void sw_classify_kernel(const uint8_t *__restrict__ qbase, const uint
                                    int cap_narrow, int cap_wide, uint32_t *__restrict__ list_fast,
                                    uint32_t *__restrict__ list_wide, uint32_t *__restrict__ list_gen, SwCounters *ctr,
                                    char *__restrict__ cig, uint32_t cig_cap, int use_shortcut) {
-    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    // Lane L of a warp keeps the books of pair kbase + L (32 pairs per warp: one atomic per warp and list).  The
+    // shortcut test itself runs SC_LANES lanes per pair: in round i the warp's four groups work on the pairs of lanes
+    // 4i..4i+3, whose descriptors they fetch by shuffle, and hand the verdict back the same way.
+    const unsigned FULL = 0xFFFFFFFFu;
     const unsigned lane = threadIdx.x & 31;
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
     int score = 0, clen = 0, kind = -1;             // kind: 0 narrow, 1 wide, 2 general, 3 shortcut, -1 nothing to do
     SwDesc d{};
+    bool todo = false;
     if (k < n && out[k].status != BWT_HIT_WINDOW_OOR) {
         d = desc[k];
         if (d.lq <= 0 || d.lr <= 0) {               // sw(_,_) -> no_match for empty strings (sw.erl:54)
             SwOut o; o.score = 0; o.status = BWT_HIT_NO_MATCH; o.cigar_len = 0; o.cigar_off = 0;
             out[k] = o;
-        } else {
-            if (use_shortcut) score = sw_shortcut(qbase + d.q_off, d.lq, rbase + d.r_off, d.lr);
-            if (score) { kind = 3; clen = 2 + (d.lq >= 10) + (d.lq >= 100) + (d.lq >= 1000) + (d.lq >= 10000); }
-            else if (d.lq <= SW_FAST_MAX_LQ && d.lr + 1 <= cap_narrow) kind = 0;
-            else if (d.lq <= SW_FAST_MAX_LQ && d.lr + 1 <= cap_wide) kind = 1;
-            else kind = 2;
+        } else todo = true;
+    }
+    if (use_shortcut && __any_sync(FULL, todo)) {
+        const int t = (int)(lane % SC_LANES), g = (int)(lane / SC_LANES);
+#pragma unroll 1
+        for (int i = 0; i < 32 / (32 / SC_LANES); i++) {
+            const int src = (32 / SC_LANES) * i + g;
+            const long long qo = __shfl_sync(FULL, (long long)d.q_off, src), ro = __shfl_sync(FULL, (long long)d.r_off, src);
+            const int lq = __shfl_sync(FULL, d.lq, src), lr = __shfl_sync(FULL, d.lr, src);
+            const bool td = __shfl_sync(FULL, (int)todo, src) != 0;
+            const int sc = sw_shortcut(qbase + qo, lq, rbase + ro, lr, td, t, lane);
+            const int got = __shfl_sync(FULL, sc, SC_LANES * (int)(lane % (32 / SC_LANES)));
+            if ((int)(lane / (32 / SC_LANES)) == i) score = got;
         }
+    }
+    if (todo) {
+        if (score) { kind = 3; clen = 2 + (d.lq >= 10) + (d.lq >= 100) + (d.lq >= 1000) + (d.lq >= 10000); }
+        else if (d.lq <= SW_FAST_MAX_LQ && d.lr + 1 <= cap_narrow) kind = 0;
+        else if (d.lq <= SW_FAST_MAX_LQ && d.lr + 1 <= cap_wide) kind = 1;
+        else kind = 2;
     }
     // one atomic per warp and list: the lanes of a kind take consecutive slots
     uint32_t slot = 0;

@@ -213,10 +213,6 @@ extern "C" int bwt_set_kmer_depth(bwt_index *h, int k) {
     h->dv.kmer_mid = nullptr;
     h->dv.deep_k = 0;
     if (k <= 8) return BWT_OK;                          // the depth-8 table alone
-    if (const char *dg = getenv("BWT_DUMMY_MB")) {       // experiment: an unused allocation in front of the tables
-        void *dummy = nullptr;
-        if (atoll(dg) > 0 && cudaMalloc(&dummy, (size_t)atoll(dg) << 20) != cudaSuccess) cudaGetLastError();
-    }
     uint2 *tab = nullptr;
     const uint64_t entries = 1ull << (2 * k);
     // BWT_KMER_MID=2 (or 1: separate allocation) also keeps the levels in between (a third of the deep table in all), so

@@ -9,6 +9,9 @@ namespace cg = cooperative_groups;
 namespace {
 
 constexpr int SGA_BLOCK = 128;
+#ifndef SGA_MIN_BLOCKS
+#define SGA_MIN_BLOCKS 8       // resident CTAs per SM the register allocation aims at (8 x 128 threads x 64 registers)
+#endif
 
 enum { CTR_SEARCHES = 0, CTR_LF, CTR_HBM_LF, CTR_LOCATED, CTR_CLUSTERS, CTR_N };
 
@@ -496,7 +499,7 @@ __device__ __forceinline__ int sga_fast_read(const Tile &tile, const DevIndex &i
 }
 
 template <int G, int MAXT>
-__global__ void __launch_bounds__(SGA_BLOCK) sga_kernel(DevIndex ix, const uint8_t *__restrict__ reads,
+__global__ void __launch_bounds__(SGA_BLOCK, SGA_MIN_BLOCKS) sga_kernel(DevIndex ix, const uint8_t *__restrict__ reads,
                                                         const int64_t *__restrict__ offs, int64_t n_reads,
                                                         int32_t *read_status, uint32_t *ncl, uint32_t *cl_base,
                                                         Cluster *clusters, uint32_t cl_cap, SlowRead *slow,

@@ -49,6 +49,7 @@ def parse():
     ap.add_argument("--no-side", action="store_true", help="skip the untimed peak / LF-walk side measurements")
     ap.add_argument("--chunk-reads", type=int, default=1 << 20, help="reads per pipelined chunk of the e2e leg")
     ap.add_argument("--depth", type=int, default=2, help="chunks in flight in the e2e leg")
+    ap.add_argument("--inexact-queries", type=int, default=50_000, help="queries of the untimed bounded-edit side leg (0 = skip)")
     return ap.parse_args()
 
 
@@ -207,6 +208,21 @@ def main():
                             "frac_of_random_gather": round(gbs / extra["gather_gbs"], 4), "kmer_depth": 8,
                             "note": "64 B (two Occ sectors) per step beyond the 8-mer table"}
 
+        # the bounded-edit search of seeds.erl (row A9/F4) on the same index: Len = read_len - 2, Defects = 2 on a
+        # sample of the reads; LF steps/s of a walk where every step reads two Occ sectors (no k-mer table)
+        mq = min(n, a.inexact_queries)
+        if mq > 0:
+            t0 = time.perf_counter()
+            fst, fso, fsd, fss = ix.fs_find_seeds(reads[:mq * a.read_len], offs[:mq + 1], a.read_len - 2, 2, 1024)
+            wall = time.perf_counter() - t0
+            extra["inexact"] = {"queries": mq, "len": a.read_len - 2, "defects": 2, "kernel_ms": fss.ms_kernel,
+                                "queries_per_s_kernel": mq / (fss.ms_kernel * 1e-3), "queries_per_s_call": mq / wall,
+                                "states_per_query": fss.nodes / mq, "lf_steps_per_s": fss.lf_steps / (fss.ms_kernel * 1e-3),
+                                "occ_gbs": round(64.0 * fss.lf_steps / (fss.ms_kernel * 1e-3) / 1e9, 1),
+                                "frac_of_random_gather": round(64.0 * fss.lf_steps / (fss.ms_kernel * 1e-3) / 1e9 / extra["gather_gbs"], 4),
+                                "seeds_per_query": len(fsd) / mq, "limit_status": int((fst == api.FS_LIMIT).sum()),
+                                "note": "fs_search_kernel: warp-per-query DFS over gen_pattern/5 (seeds.erl:51-62), 64 B per LF step"}
+
     batch = api.Batch(ix, n, n * a.read_len)
     batch.upload(reads, offs)
 
@@ -330,7 +346,7 @@ def main():
                        "wall_ms_per_step": t_wall / K},
             "clocks": clk, "gpu_launches": total_launches,
             "roofline": roof, "roofline_alu": roof_alu, "roofline_sga": roof_sga,
-            "lf_walk": extra.get("lf_walk"),
+            "lf_walk": extra.get("lf_walk"), "inexact": extra.get("inexact"),
             "work": {"lf_steps_per_s": agg["lf"] / (agg["ms_sga"] * 1e-3) if agg["ms_sga"] else None,
                      "hbm_lf_steps_per_read": agg["hbm_lf"] / (n * K), "lf_steps_per_read": agg["lf"] / (n * K),
                      "located_rows_per_read": agg["located"] / (n * K), "clusters_per_read": agg["clusters"] / (n * K),

@@ -40,7 +40,7 @@ namespace {
 
 constexpr int FS_WARPS = 8;              // warps per CTA
 constexpr int FS_STACK = 128;            // states per warp in shared memory (16 B each)
-constexpr int FS_SPILL = 16384;          // states per warp in the HBM spill area
+constexpr int FS_SPILL = 4096;           // states per warp in the HBM spill area
 constexpr int FS_MAX_D = 8;
 constexpr int FS_MAX_Q = 1024 + FS_MAX_D; // Len + Defects characters staged per warp
 

@@ -188,6 +188,46 @@ static ERL_NIF_TERM nif_sga(ErlNifEnv *env, int argc, const ERL_NIF_TERM argv[])
     return res;
 }
 
+/* fs_find_seeds(Index, [Qsec], Len, Defects) -> [short | limit | [N]]: what fs:find_seeds(Ref_Seq) returns after
+ * seeds:generate_fs(Qsec, Len, Defects) (seeds.erl:11-62), Ref_Seq = the text of the partition */
+static ERL_NIF_TERM nif_fs_find_seeds(ErlNifEnv *env, int argc, const ERL_NIF_TERM argv[]) {
+    bwt_index *h;
+    packed p;
+    int len, defects;
+    (void)argc;
+    if (!get_index(env, argv[0], &h) || !enif_get_int(env, argv[2], &len) || !enif_get_int(env, argv[3], &defects) ||
+        !pack_list(env, argv[1], -1, &p))
+        return enif_make_badarg(env);
+    int64_t n = p.n, cap = 4 * n + 16, total = 0;
+    int32_t *qs = (int32_t *)malloc((size_t)(n + 1) * 4);
+    int64_t *so = (int64_t *)malloc((size_t)(n + 1) * 8), *seeds = NULL;
+    int st;
+    for (;;) {
+        seeds = (int64_t *)realloc(seeds, (size_t)cap * 8);
+        st = bwt_fs_find_seeds_batch(h, p.data, p.offs, n, len, defects, 0, qs, so, seeds, cap, &total, NULL);
+        if (st != BWT_ERR_NOSPACE) break;
+        cap = total + 16;
+    }
+    ERL_NIF_TERM res;
+    if (st != BWT_OK) res = mk_error(env, st);
+    else {
+        ERL_NIF_TERM *items = (ERL_NIF_TERM *)malloc((size_t)(n + 1) * sizeof(ERL_NIF_TERM));
+        for (int64_t r = 0; r < n; r++) {
+            if (qs[r] == BWT_FS_SHORT) { items[r] = enif_make_atom(env, "short"); continue; }
+            if (qs[r] == BWT_FS_LIMIT) { items[r] = enif_make_atom(env, "limit"); continue; }
+            ERL_NIF_TERM l = enif_make_list(env, 0);
+            for (int64_t k = so[r + 1] - 1; k >= so[r]; k--)        /* cons from the tail: descending N, as the accumulator */
+                l = enif_make_list_cell(env, enif_make_int64(env, seeds[k]), l);
+            items[r] = l;
+        }
+        res = enif_make_list_from_array(env, items, (unsigned)n);
+        free(items);
+    }
+    free(qs); free(so); free(seeds);
+    packed_free(&p);
+    return res;
+}
+
 /* sw([{Qseq, Ref}], Device) -> [no_match | {Score, Cigar}] */
 static ERL_NIF_TERM nif_sw(ErlNifEnv *env, int argc, const ERL_NIF_TERM argv[]) {
     packed q, r;
@@ -276,6 +316,7 @@ static ErlNifFunc nif_funcs[] = {
     {"info", 1, nif_info, 0},
     {"find_seeds", 2, nif_find_seeds, ERL_NIF_DIRTY_JOB_CPU_BOUND},
     {"sga", 2, nif_sga, ERL_NIF_DIRTY_JOB_CPU_BOUND},
+    {"fs_find_seeds", 4, nif_fs_find_seeds, ERL_NIF_DIRTY_JOB_CPU_BOUND},
     {"sw", 2, nif_sw, ERL_NIF_DIRTY_JOB_CPU_BOUND},
     {"align", 2, nif_align, ERL_NIF_DIRTY_JOB_CPU_BOUND},
 };

@@ -50,19 +50,24 @@ __device__ __forceinline__ uint32_t both(int k) { return ((uint32_t)k & 0xFFFFu)
 // ---------------------------------------------------------------------------------------------------
 // Pairs whose sw:sw/2 result is known without filling the table.
 //
-// Both strings plain ACGT, window slack Dd = Lr - Lq in 0..SW_SHORTCUT_MAX_D, Lq >= 4.  Diagonal o (0 <= o <= Dd) pairs
-// query character i with window character o + i.  With sigma in {2, -1}, gap open -2 / extend -1 and the reference's
-// direction-dependent gap rule never scoring a gapped path HIGHER than plain affine gaps would (sw.erl:88-107), every
-// path into the last row scores at most  2*Lq - 3*mismatches - 2*inserted - sum over gaps (1 + length):
-//   (a) some diagonal matches perfectly: Vmax = 2*Lq, reached only by perfect diagonals; get_starting_point takes the
-//       smallest column (sw.erl:110-112) = the smallest perfect o; every cell on that diagonal holds the row's largest
-//       possible value through its up_left candidate, which wins ties (up_left > up > left): CIGAR = "<Lq>M";
-//   (b) no perfect diagonal, some diagonal has exactly one mismatch: only a single deletion of one or two window
-//       characters between perfectly matching flanks could score as much (2*Lq-2, 2*Lq-3).  If no such split exists
-//       (lcp(o) + lcsuf(o + len) < Lq for len = 1, 2 and every o), Vmax = 2*Lq - 3 on the smallest one-mismatch
-//       diagonal, nothing left of it reaches that value, and the same tie argument gives "<Lq>M" again.
-// The row threshold -2*(Lq div 2) + 2*i (sw.erl:62,69-71) is never undercut on such a diagonal (Lq >= 4).
-// Everything else runs the DP.  tests/test_gpu_parity.py runs its SW cases with this shortcut on and off.
+// Both strings plain ACGT, window slack Dd = Lr - Lq in 0..SW_SHORTCUT_MAX_D.  Diagonal o pairs query character i with
+// window character o + i.  Write a path's score as 2*Lq - penalty: a mismatch costs 3, a skipped window character 2
+// (gap open) or 1 (extension), a skipped query character 4 or 3 (the gap and the lost match).  With PLAIN affine gaps
+// the cheapest penalty p* and the diagonals on which a path of penalty p* reaches the last row follow from a wavefront
+// search (furthest query index per penalty, diagonal and state M / I / D -- the WFA recurrence), a few dozen short
+// string comparisons instead of Lq*Lr cells.  The reference's table is not plain affine (a gap is extended at -1 only
+// when the neighbour's CHOSEN direction is that gap, sw.erl:88-107), but that rule never scores a path higher than
+// plain affine gaps would, and a gapless diagonal scores the same under both.  So if the LEFTMOST diagonal o* on which
+// penalty p* reaches the last row does so without a gap (its own mismatch count is p*/3):
+//   * the last row's maximum is 2*Lq - p*, and no column left of o* + Lq reaches it, which is the column
+//     get_starting_point takes (sw.erl:110-112);
+//   * every cell of that diagonal holds exactly the diagonal's prefix score (more would push the end cell past the
+//     maximum), its up_left candidate attains it, and ties go up_left > up > left: the traceback is "<Lq>M";
+//   * the row threshold -2*(Lq div 2) + 2*i (sw.erl:62,69-71) is never undercut while p* <= 2*(Lq div 2).
+// Searched up to penalty SW_SHORTCUT_PMAX (three mismatches); paths may leave the window's diagonals by up to
+// SC_K = (PMAX-1)/3 on either side (column 0 starts with a query-side gap, sw.erl:72-77).  Anything else -- optimal
+// paths with a gap, more mismatches, other bytes -- runs the DP.  tests/test_gpu_parity.py runs its SW cases with
+// this shortcut on and off, including low-complexity strings built to break it.
 // ---------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t ldu32(const uint8_t *p) {           // unaligned 32-bit load (buffers carry 16 B of slack)
     const uintptr_t a = reinterpret_cast<uintptr_t>(p);
@@ -104,15 +109,35 @@ __device__ __forceinline__ unsigned grp_min(unsigned v) {
     for (int o = 1; o < SC_LANES; o <<= 1) v = min(v, __shfl_xor_sync(0xFFFFFFFFu, v, o));
     return v;
 }
-__device__ __forceinline__ unsigned grp_max(unsigned v) {
+__device__ __forceinline__ unsigned grp_sum(unsigned v) {
 #pragma unroll
-    for (int o = 1; o < SC_LANES; o <<= 1) v = max(v, __shfl_xor_sync(0xFFFFFFFFu, v, o));
+    for (int o = 1; o < SC_LANES; o <<= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
     return v;
 }
 
+constexpr int SC_PMAX = 9;                          // largest penalty searched: three mismatches
+constexpr int SC_K = (SC_PMAX - 1) / 3;             // query characters a path of that penalty can skip
+constexpr int SC_ND = 24;                           // diagonals -SC_K .. SW_SHORTCUT_MAX_D + SC_K, padded
+constexpr int SC_RING = 5;                          // wavefronts kept: s, s-1, .., s-4
+static_assert(SW_SHORTCUT_MAX_D + 2 * SC_K + 1 <= SC_ND, "diagonal slots");
+
+struct ScWave { int16_t v[SC_RING][3][SC_ND]; };    // furthest query index, -1 = unreachable; states M, I, D
+
+// furthest i' >= i with q[i..i') == r[o+i..o+i'), i' <= lim
+__device__ __forceinline__ int sc_extend(const uint8_t *q, const uint8_t *r, int o, int i, int lim) {
+    while (i < lim) {
+        const uint32_t df = ldu32(q + i) ^ ldu32(r + o + i);
+        if (df) { i += (__ffs((int)df) - 1) >> 3; break; }
+        i += 4;
+    }
+    return min(i, lim);
+}
+
 // 0 = run the DP; otherwise the score of the pair, whose CIGAR is "<Lq>M".  Called by ALL lanes of the warp, converged;
-// the SC_LANES lanes of a group pass the same pair (valid = false: no pair); t = lane index inside the group.
-__device__ __forceinline__ int sw_shortcut(const uint8_t *q, int lq, const uint8_t *r, int lr, bool valid, int t, unsigned lane) {
+// the SC_LANES lanes of a group pass the same pair (valid = false: no pair) and the group's wavefront storage;
+// t = lane index inside the group.
+__device__ __forceinline__ int sw_shortcut(const uint8_t *q, int lq, const uint8_t *r, int lr, bool valid, int t, unsigned lane,
+                                           ScWave &wf) {
     const unsigned FULL = 0xFFFFFFFFu;
     const int dd = lr - lq;
     bool elig = valid && dd >= 0 && dd <= SW_SHORTCUT_MAX_D && lq >= 4;
@@ -130,41 +155,58 @@ __device__ __forceinline__ int sw_shortcut(const uint8_t *q, int lq, const uint8
         }
     const unsigned plain_mask = __ballot_sync(FULL, plain);          // by every lane, before any short-circuit
     elig = elig && ((plain_mask >> (lane - t)) & ((1u << SC_LANES) - 1u)) == ((1u << SC_LANES) - 1u);
-    const int dmax = (int)__reduce_max_sync(FULL, (unsigned)(elig ? dd + 1 : 0)) - 1;
-    int res = 0, lcp1 = -1, lcp2 = -1;              // lcp(o-1), lcp(o-2); -1 = no such diagonal
-    bool open = elig, one = false, split = false;  // open: no verdict yet
-    for (int o = 0; o <= dmax; o++) {
-        const bool act = open && o <= dd;
-        unsigned first = 0x7FFFFFFFu, lastp1 = 0;
-        if (act)
-            for (int base = 16 * t; base < lq; base += 16 * SC_LANES) {
-                uint32_t a[4], b[4];
-                ld16(q + base, lq - base, 0u, a);
-                ld16(r + o + base, lq - base, 0u, b);
-#pragma unroll
-                for (int k = 3; k >= 0; k--) {
-                    const uint32_t df = a[k] ^ b[k];
-                    if (df) {
-                        first = min(first, (unsigned)(base + 4 * k + ((__ffs((int)df) - 1) >> 3)));
-                        lastp1 = max(lastp1, (unsigned)(base + 4 * k + 4 - (__clz((int)df) >> 3)));
-                    }
-                }
-            }
-        first = grp_min(first);
-        lastp1 = grp_max(lastp1);
+    for (int k = t; k < SC_RING * 3 * SC_ND; k += SC_LANES) (&wf.v[0][0][0])[k] = -1;
+    __syncwarp();
+    const int nd = dd + 2 * SC_K + 1;                                // diagonal slot d <-> o = d - SC_K
+    const int pmax = min(SC_PMAX, 2 * (lq >> 1));                   // the row threshold holds up to here
+    bool open = elig;
+    int pstar = -1, omin = 0x7FFF;
+    for (int s = 0; s <= SC_PMAX; s++) {
+        const bool act = open && s <= pmax;
+        unsigned best = 0x7FFFu;
         if (act) {
-            if (first == 0x7FFFFFFFu) { res = 2 * lq; open = false; }      // (a): the smallest perfect diagonal
-            else {
-                const int x = (int)first, y = lq - (int)lastp1;            // lcp, lcsuf
-                one |= x + y == lq - 1;
-                split |= (lcp1 >= 0 && lcp1 + y >= lq) || (lcp2 >= 0 && lcp2 + y >= lq);
-                lcp2 = lcp1; lcp1 = x;
+            const int cur = s % SC_RING, p1 = (s + SC_RING - 1) % SC_RING, p2 = (s + SC_RING - 2) % SC_RING,
+                      p3 = (s + SC_RING - 3) % SC_RING, p4 = (s + SC_RING - 4) % SC_RING;
+            for (int d = t; d < nd; d += SC_LANES) {
+                const int o = d - SC_K;
+                int dv = -1, iv = -1, mv = -1;
+                if (d > 0) {                                         // skip a window character: diagonal o-1 -> o
+                    dv = max((int)wf.v[p2][0][d - 1], (int)wf.v[p1][2][d - 1]);
+                    if (dv >= 0 && (o + dv < 0 || o + dv > lr)) dv = -1;
+                }
+                if (d + 1 < nd) {                                    // skip a query character: diagonal o+1 -> o
+                    iv = max((int)wf.v[p4][0][d + 1], (int)wf.v[p3][1][d + 1]);
+                    if (iv >= 0) { iv += 1; if (iv > lq || o + iv < 0) iv = -1; }
+                }
+                if (s == 0) mv = (o >= 0 && o <= lr) ? 0 : -1;       // row 0 is free (sw.erl:72)
+                else {
+                    const int pm = wf.v[p3][0][d];
+                    if (pm >= 0 && pm < lq && o + pm >= 0 && o + pm < lr) mv = pm + 1;   // mismatch
+                    mv = max(mv, max(dv, iv));
+                }
+                if (mv >= 0) mv = sc_extend(q, r, o, mv, min(lq, lr - o));
+                wf.v[cur][0][d] = (int16_t)mv; wf.v[cur][1][d] = (int16_t)iv; wf.v[cur][2][d] = (int16_t)dv;
+                if (mv == lq && o + lq >= 0 && o + lq <= lr) best = min(best, (unsigned)(o + SC_K));
             }
         }
-        if (__all_sync(FULL, !open || o >= dd)) break;
+        __syncwarp();
+        best = grp_min(best);
+        if (act && best != 0x7FFFu) { open = false; pstar = s; omin = (int)best - SC_K; }
+        if (__all_sync(FULL, !open || s >= pmax)) break;
     }
-    if (open && one && !split) res = 2 * lq - 3;    // (b)
-    return res;
+    // the leftmost optimal end must be a gapless diagonal of the window: count its mismatches
+    const bool check = pstar >= 0 && omin >= 0 && omin <= dd;
+    unsigned mism = 0;
+    if (check)
+        for (int base = 16 * t; base < lq; base += 16 * SC_LANES) {
+            uint32_t a[4], b[4];
+            ld16(q + base, lq - base, 0u, a);
+            ld16(r + omin + base, lq - base, 0u, b);
+#pragma unroll
+            for (int k = 0; k < 4; k++) mism += (unsigned)__popc(__vcmpne4(a[k], b[k])) >> 3;
+        }
+    mism = grp_sum(mism);
+    return (check && 3 * (int)mism == pstar) ? 2 * lq - pstar : 0;
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -178,6 +220,7 @@ __global__ void sw_classify_kernel(const uint8_t *__restrict__ qbase, const uint
     // Lane L of a warp keeps the books of pair kbase + L (32 pairs per warp: one atomic per warp and list).  The
     // shortcut test itself runs SC_LANES lanes per pair: in round i the warp's four groups work on the pairs of lanes
     // 4i..4i+3, whose descriptors they fetch by shuffle, and hand the verdict back the same way.
+    __shared__ ScWave s_wave[256 / SC_LANES];
     const unsigned FULL = 0xFFFFFFFFu;
     const unsigned lane = threadIdx.x & 31;
     const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
@@ -199,7 +242,7 @@ __global__ void sw_classify_kernel(const uint8_t *__restrict__ qbase, const uint
             const long long qo = __shfl_sync(FULL, (long long)d.q_off, src), ro = __shfl_sync(FULL, (long long)d.r_off, src);
             const int lq = __shfl_sync(FULL, d.lq, src), lr = __shfl_sync(FULL, d.lr, src);
             const bool td = __shfl_sync(FULL, (int)todo, src) != 0;
-            const int sc = sw_shortcut(qbase + qo, lq, rbase + ro, lr, td, t, lane);
+            const int sc = sw_shortcut(qbase + qo, lq, rbase + ro, lr, td, t, lane, s_wave[threadIdx.x / SC_LANES]);
             const int got = __shfl_sync(FULL, sc, SC_LANES * (int)(lane % (32 / SC_LANES)));
             if ((int)(lane / (32 / SC_LANES)) == i) score = got;
         }

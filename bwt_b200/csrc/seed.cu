@@ -1,5 +1,6 @@
 // Seeding kernels (see seed.cuh).  Reference semantics: sga.erl:17-76, bwa.erl:12-45, fmi.erl:25-39,89-100.
 #include <cooperative_groups.h>
+#include <cstdlib>
 
 #include "search.cuh"
 #include "seed.cuh"
@@ -582,6 +583,14 @@ int launch_sga(const DevIndex &ix, const uint8_t *d_reads, const int64_t *d_offs
                int32_t *d_read_status, uint32_t *d_ncl, uint32_t *d_cl_base, Cluster *d_clusters, uint32_t cl_cap,
                SlowRead *d_slow, uint32_t slow_cap, SeedCounters *d_ctr, cudaStream_t stream) {
     if (n_reads <= 0) return BWT_OK;
+    {   // L1 / shared-memory split of the seeding kernels: BWT_SGA_CARVEOUT = percent of shared memory (default: driver's choice)
+        static int carve = -2;
+        if (carve == -2) { const char *e = getenv("BWT_SGA_CARVEOUT"); carve = e ? atoi(e) : -1; }
+        if (carve >= 0) {
+            cudaFuncSetAttribute(sga_kernel<16, 16>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+            cudaFuncSetAttribute(sga_kernel<32, SGA_MAX_TASKS>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+        }
+    }
     // 16 lanes per read while every read has at most 16 subsequences (<= 135 bases), else a full warp
     if (max_read_len <= BWT_MIN_LEN * 15 + BWT_MAX_LEN) {
         int64_t blocks = (n_reads + 7) / 8;

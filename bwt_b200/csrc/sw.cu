@@ -69,38 +69,9 @@ __device__ __forceinline__ uint32_t both(int k) { return ((uint32_t)k & 0xFFFFu)
 // paths with a gap, more mismatches, other bytes -- runs the DP.  tests/test_gpu_parity.py runs its SW cases with
 // this shortcut on and off, including low-complexity strings built to break it.
 // ---------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t ldu32(const uint8_t *p) {           // unaligned 32-bit load (buffers carry 16 B of slack)
-    const uintptr_t a = reinterpret_cast<uintptr_t>(p);
-    const uint32_t *b = reinterpret_cast<const uint32_t *>(a & ~(uintptr_t)3);
-    const int sh = (int)(a & 3) * 8;
-    const uint32_t lo = __ldg(b);
-    return sh ? __funnelshift_r(lo, __ldg(b + 1), sh) : lo;
-}
-
-__device__ __forceinline__ bool acgt4(uint32_t wv) {                    // are all four bytes one of A, C, G, T
-    const uint32_t x = (wv >> 1) & 0x03030303u;
-    const uint32_t x0 = x & 0x01010101u, x1 = (x >> 1) & 0x01010101u, tt = x1 & ~x0;
-    return (0x40404040u | (x0 << 1) | (x1 << 2) | (tt << 4) | (tt ^ 0x01010101u)) == wv;
-}
-
-// Eight lanes per pair: lane t holds bytes [16t, 16t+16) of every 128-byte chunk, so a group's loads are coalesced and
-// one pass over a diagonal gives its first and last mismatch: lcp = first, lcsuf = Lq - 1 - last, and the diagonal has
-// exactly one mismatch iff first == last.
+// Eight lanes per pair: lane t packs bases [16t, 16t+16) of every 128-base chunk (coalesced loads) and owns the
+// diagonals t, t+8, t+16 of the wavefront search.
 constexpr int SC_LANES = 8;
-
-// 16 bytes at p (unaligned) -> 4 words; bytes at index >= valid are replaced by `fill`
-__device__ __forceinline__ void ld16(const uint8_t *p, int valid, uint32_t fill, uint32_t (&w)[4]) {
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-        const int left = valid - 4 * k;
-        uint32_t v = fill;
-        if (left > 0) {
-            v = ldu32(p + 4 * k);
-            if (left < 4) v = (v & ((1u << (8 * left)) - 1u)) | (fill << (8 * left));
-        }
-        w[k] = v;
-    }
-}
 
 // reductions over the SC_LANES lanes of a group with FULL-mask shuffles: the four groups of a warp stay converged
 // (partial-mask primitives would split the warp into four serialised quarter-warps)
@@ -109,104 +80,112 @@ __device__ __forceinline__ unsigned grp_min(unsigned v) {
     for (int o = 1; o < SC_LANES; o <<= 1) v = min(v, __shfl_xor_sync(0xFFFFFFFFu, v, o));
     return v;
 }
-__device__ __forceinline__ unsigned grp_sum(unsigned v) {
-#pragma unroll
-    for (int o = 1; o < SC_LANES; o <<= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
-    return v;
-}
-
 constexpr int SC_PMAX = 9;                          // largest penalty searched: three mismatches
 constexpr int SC_K = (SC_PMAX - 1) / 3;             // query characters a path of that penalty can skip
 constexpr int SC_ND = 24;                           // diagonals -SC_K .. SW_SHORTCUT_MAX_D + SC_K, padded
 constexpr int SC_RING = 5;                          // wavefronts kept: s, s-1, .., s-4
+constexpr int SC_MAXQ = 256;                        // longest query the shortcut looks at
+constexpr int SC_QW = SC_MAXQ / 16;                 // 2-bit packed query words (16 bases each)
+constexpr int SC_RW = (SC_MAXQ + SW_SHORTCUT_MAX_D + 15) / 16 + 2;
 static_assert(SW_SHORTCUT_MAX_D + 2 * SC_K + 1 <= SC_ND, "diagonal slots");
 
-struct ScWave { int16_t v[SC_RING][3][SC_ND]; };    // furthest query index, -1 = unreachable; states M, I, D
+// Per pair: the wavefronts (furthest query index, -1 = unreachable; states M, I, D) and both strings packed to 2 bits
+// per base, so that "extend along diagonal o" compares 16 bases per XOR instead of walking bytes.
+struct ScWave {
+    int16_t v[SC_RING][3][SC_ND];
+    uint32_t qp[SC_QW];
+    uint32_t rp[SC_RW];
+};
+
+// mismatch flags of query bases [16w, 16w+16) on diagonal o: bit 2b set <=> q[16w+b] != r[o+16w+b]
+// (window positions below 0 give garbage in the low flags: callers never look below i = -o)
+__device__ __forceinline__ uint32_t sc_diff(const ScWave &wf, int o, int w) {
+    const int p = o + 16 * w;
+    uint32_t rv;
+    if (p >= 0) rv = __funnelshift_r(wf.rp[p >> 4], wf.rp[(p >> 4) + 1], 2 * (p & 15));
+    else rv = wf.rp[0] << (2 * -p);
+    const uint32_t x = wf.qp[w] ^ rv;
+    return (x | (x >> 1)) & 0x55555555u;
+}
 
 // furthest i' >= i with q[i..i') == r[o+i..o+i'), i' <= lim
-__device__ __forceinline__ int sc_extend(const uint8_t *q, const uint8_t *r, int o, int i, int lim) {
-    while (i < lim) {
-        const uint32_t df = ldu32(q + i) ^ ldu32(r + o + i);
-        if (df) { i += (__ffs((int)df) - 1) >> 3; break; }
-        i += 4;
-    }
-    return min(i, lim);
+__device__ __forceinline__ int sc_extend(const ScWave &wf, int o, int i, int lim) {
+    if (i >= lim) return lim;
+    int w = i >> 4;
+    uint32_t m = sc_diff(wf, o, w) & (0xFFFFFFFFu << (2 * (i & 15)));
+    const int nw = (lim + 15) >> 4;
+    while (m == 0u && ++w < nw) m = sc_diff(wf, o, w);
+    return m ? min(lim, 16 * w + ((__ffs((int)m) - 1) >> 1)) : lim;
 }
 
 // 0 = run the DP; otherwise the score of the pair, whose CIGAR is "<Lq>M".  Called by ALL lanes of the warp, converged;
-// the SC_LANES lanes of a group pass the same pair (valid = false: no pair) and the group's wavefront storage;
-// t = lane index inside the group.
+// the SC_LANES lanes of a group pass the same pair (valid = false: no pair) and the group's storage; t = lane index
+// inside the group.
 __device__ __forceinline__ int sw_shortcut(const uint8_t *q, int lq, const uint8_t *r, int lr, bool valid, int t, unsigned lane,
                                            ScWave &wf) {
     const unsigned FULL = 0xFFFFFFFFu;
     const int dd = lr - lq;
-    bool elig = valid && dd >= 0 && dd <= SW_SHORTCUT_MAX_D && lq >= 4;
-    // all plain ACGT?  (bytes past the end count as 'A')
+    bool elig = valid && dd >= 0 && dd <= SW_SHORTCUT_MAX_D && lq >= 4 && lq <= SC_MAXQ;
+    // pack both strings (lane t: bases [16t, 16t+16) of every 128-base chunk); any byte outside ACGT: no shortcut
     bool plain = true;
-    if (elig)
-        for (int base = 16 * t; base < lr; base += 16 * SC_LANES) {
-            uint32_t w[4];
-            ld16(r + base, lr - base, 0x41414141u, w);
-            plain &= acgt4(w[0]) & acgt4(w[1]) & acgt4(w[2]) & acgt4(w[3]);
-            if (base < lq) {
-                ld16(q + base, lq - base, 0x41414141u, w);
-                plain &= acgt4(w[0]) & acgt4(w[1]) & acgt4(w[2]) & acgt4(w[3]);
-            }
-        }
+    if (elig) {
+        for (int pos = 16 * t; pos < 16 * SC_RW; pos += 16 * SC_LANES)
+            wf.rp[pos >> 4] = pos < lr ? pack16_acgt(r + pos, min(16, lr - pos), plain) : 0u;
+        for (int pos = 16 * t; pos < lq; pos += 16 * SC_LANES) wf.qp[pos >> 4] = pack16_acgt(q + pos, min(16, lq - pos), plain);
+    }
+    __syncwarp();                                                    // qp / rp visible to the whole group
     const unsigned plain_mask = __ballot_sync(FULL, plain);          // by every lane, before any short-circuit
     elig = elig && ((plain_mask >> (lane - t)) & ((1u << SC_LANES) - 1u)) == ((1u << SC_LANES) - 1u);
-    for (int k = t; k < SC_RING * 3 * SC_ND; k += SC_LANES) (&wf.v[0][0][0])[k] = -1;
-    __syncwarp();
     const int nd = dd + 2 * SC_K + 1;                                // diagonal slot d <-> o = d - SC_K
     const int pmax = min(SC_PMAX, 2 * (lq >> 1));                   // the row threshold holds up to here
     bool open = elig;
     int pstar = -1, omin = 0x7FFF;
+    int cur = 0;                                                     // ring slot of wavefront s
     for (int s = 0; s <= SC_PMAX; s++) {
         const bool act = open && s <= pmax;
         unsigned best = 0x7FFFu;
         if (act) {
-            const int cur = s % SC_RING, p1 = (s + SC_RING - 1) % SC_RING, p2 = (s + SC_RING - 2) % SC_RING,
-                      p3 = (s + SC_RING - 3) % SC_RING, p4 = (s + SC_RING - 4) % SC_RING;
+            const int p1 = cur == 0 ? SC_RING - 1 : cur - 1, p2 = p1 == 0 ? SC_RING - 1 : p1 - 1, p3 = p2 == 0 ? SC_RING - 1 : p2 - 1,
+                      p4 = p3 == 0 ? SC_RING - 1 : p3 - 1;
             for (int d = t; d < nd; d += SC_LANES) {
                 const int o = d - SC_K;
                 int dv = -1, iv = -1, mv = -1;
                 if (d > 0) {                                         // skip a window character: diagonal o-1 -> o
-                    dv = max((int)wf.v[p2][0][d - 1], (int)wf.v[p1][2][d - 1]);
+                    if (s >= 2) dv = wf.v[p2][0][d - 1];
+                    if (s >= 1) dv = max(dv, (int)wf.v[p1][2][d - 1]);
                     if (dv >= 0 && (o + dv < 0 || o + dv > lr)) dv = -1;
                 }
                 if (d + 1 < nd) {                                    // skip a query character: diagonal o+1 -> o
-                    iv = max((int)wf.v[p4][0][d + 1], (int)wf.v[p3][1][d + 1]);
+                    if (s >= 4) iv = wf.v[p4][0][d + 1];
+                    if (s >= 3) iv = max(iv, (int)wf.v[p3][1][d + 1]);
                     if (iv >= 0) { iv += 1; if (iv > lq || o + iv < 0) iv = -1; }
                 }
                 if (s == 0) mv = (o >= 0 && o <= lr) ? 0 : -1;       // row 0 is free (sw.erl:72)
                 else {
-                    const int pm = wf.v[p3][0][d];
+                    const int pm = s >= 3 ? (int)wf.v[p3][0][d] : -1;
                     if (pm >= 0 && pm < lq && o + pm >= 0 && o + pm < lr) mv = pm + 1;   // mismatch
                     mv = max(mv, max(dv, iv));
                 }
-                if (mv >= 0) mv = sc_extend(q, r, o, mv, min(lq, lr - o));
+                if (mv >= 0) mv = sc_extend(wf, o, mv, min(lq, lr - o));
                 wf.v[cur][0][d] = (int16_t)mv; wf.v[cur][1][d] = (int16_t)iv; wf.v[cur][2][d] = (int16_t)dv;
-                if (mv == lq && o + lq >= 0 && o + lq <= lr) best = min(best, (unsigned)(o + SC_K));
+                if (mv == lq && o + lq >= 0 && o + lq <= lr) best = min(best, (unsigned)d);
             }
         }
         __syncwarp();
         best = grp_min(best);
         if (act && best != 0x7FFFu) { open = false; pstar = s; omin = (int)best - SC_K; }
         if (__all_sync(FULL, !open || s >= pmax)) break;
+        cur = cur + 1 == SC_RING ? 0 : cur + 1;
     }
     // the leftmost optimal end must be a gapless diagonal of the window: count its mismatches
-    const bool check = pstar >= 0 && omin >= 0 && omin <= dd;
-    unsigned mism = 0;
-    if (check)
-        for (int base = 16 * t; base < lq; base += 16 * SC_LANES) {
-            uint32_t a[4], b[4];
-            ld16(q + base, lq - base, 0u, a);
-            ld16(r + omin + base, lq - base, 0u, b);
-#pragma unroll
-            for (int k = 0; k < 4; k++) mism += (unsigned)__popc(__vcmpne4(a[k], b[k])) >> 3;
-        }
-    mism = grp_sum(mism);
-    return (check && 3 * (int)mism == pstar) ? 2 * lq - pstar : 0;
+    if (!(pstar >= 0 && omin >= 0 && omin <= dd)) return 0;
+    int mism = 0;
+    for (int w = 0; w < (lq + 15) >> 4; w++) {
+        uint32_t f = sc_diff(wf, omin, w);
+        if (lq - 16 * w < 16) f &= (1u << (2 * (lq - 16 * w))) - 1u;   // bases past the query's end are padding
+        mism += __popc(f);
+    }
+    return 3 * mism == pstar ? 2 * lq - pstar : 0;
 }
 
 // ---------------------------------------------------------------------------------------------------

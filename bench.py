@@ -263,6 +263,7 @@ def main():
 
         aligner = api.Aligner(ix, chunk_reads=a.chunk_reads, chunk_bytes=a.chunk_reads * a.read_len, depth=a.depth)
         e2e_launches = 0
+        e2e_copy = [0.0, 0.0]
 
         def e2e_step():
             # the reference-facing call: host buffers in, hit tuples out; copies overlap the kernels chunk by chunk
@@ -273,13 +274,15 @@ def main():
         e0 = time.perf_counter()
         for _ in range(a.steps):
             nh, nc = e2e_step()
-            e2e_launches += aligner.stats().launches
+            ast_ = aligner.stats()
+            e2e_launches += ast_.launches
+            e2e_copy[0] += ast_.ms_h2d; e2e_copy[1] += ast_.ms_d2h
         barrier()
         e2e_s = time.perf_counter() - e0
         assert (nh, nc) == (n_hits, cig_bytes), "pipelined and resident paths disagree"
         h2d = n * a.read_len + (n + 1) * 8
         d2h = n * 4 + (n + 1) * 8 + nh * 40 + nc
-        e2e = [e2e_s, h2d, d2h]
+        e2e = [e2e_s, h2d, d2h, e2e_copy[0] / a.steps, e2e_copy[1] / a.steps]
 
     # -- max over ranks
     t_ev, t_wall = ev_ms, wall_ms
@@ -361,7 +364,11 @@ def main():
         if e2e:
             out["e2e"] = {"value": world * n * K / e2e[0], "unit": UNIT, "h2d_bytes_per_step": e2e[1], "d2h_bytes_per_step": e2e[2],
                           "timer": "wall clock around bwt_aligner_run (pinned host buffers in and out), barrier+synchronize both sides, max over ranks",
-                          "chunk_reads": a.chunk_reads, "chunks_in_flight": a.depth}
+                          "chunk_reads": a.chunk_reads, "chunks_in_flight": a.depth,
+                          "ms_h2d_per_step": e2e[3], "ms_d2h_per_step": e2e[4],
+                          "h2d_gbs": e2e[1] / (e2e[3] * 1e-3) / 1e9 if e2e[3] else None,
+                          "d2h_gbs": e2e[2] / (e2e[4] * 1e-3) / 1e9 if e2e[4] else None,
+                          "note": "copy times are summed over the chunks (CUDA events on each chunk's stream); chunks overlap"}
         if world == 1 and a.cpu_seconds > 0:
             out["cpu_baseline"] = cpu_baseline(a, ix, reads, offs, threads)
         print(json.dumps(out), flush=True)

@@ -576,6 +576,8 @@ extern "C" int bwt_aligner_run(bwt_aligner *a, const uint8_t *reads, const int64
     PipeShared sh;
     std::vector<bwt_stats> wstats((size_t)depth);
     const bool trace = getenv("BWT_TRACE") != nullptr;       // per-chunk host timeline on stderr (debug aid)
+    const char *env_tok = getenv("BWT_COMPUTE_TOKEN");       // 0: chunks may compute concurrently (their kernels interleave)
+    const bool use_token = !(env_tok && env_tok[0] == '0');
     const auto t_start = std::chrono::steady_clock::now();
     auto now_ms = [&] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_start).count(); };
     auto worker = [&](int w) {
@@ -593,7 +595,8 @@ extern "C" int bwt_aligner_run(bwt_aligner *a, const uint8_t *reads, const int64
                 if (st == BWT_OK) {
                     // one chunk computes at a time: the others spend that time in their copies, instead of all chunks
                     // copying together and then time-slicing the SMs together
-                    std::lock_guard<std::mutex> run_token(sh.compute_mu);
+                    std::unique_lock<std::mutex> run_token(sh.compute_mu, std::defer_lock);
+                    if (use_token) run_token.lock();
                     st = bwt_batch_run(b);
                 }
                 t2 = now_ms();

@@ -826,25 +826,43 @@ int sw_stage_run(SwStage &st, const uint8_t *d_qbase, const uint8_t *d_rbase, ui
         p.qbase = d_qbase; p.rbase = d_rbase; p.desc = st.d_desc; p.out = st.d_out;
         p.list_gen = st.d_list_gen; p.list_ovf = st.d_list_ovf; p.ctr = st.d_ctr; p.cig = st.d_cig_tmp; p.cig_cap = st.cig_cap;
         p.dirs = st.d_dirs; p.max_strips = max_strips;
+        // the list sizes are known on the host before the DP kernels go out: with the shortcut most lists are short or
+        // empty, and an empty launch of a large-shared-memory kernel still costs a quarter of a millisecond
+        CU_TRY(cudaMemcpyAsync(st.h_ctr, st.d_ctr, sizeof(SwCounters), cudaMemcpyDeviceToHost, stream));
+        CU_TRY(cudaStreamSynchronize(stream));
+        const uint32_t n_fast = st.h_ctr->n_fast, n_wide = st.h_ctr->n_wide;
+        auto grid_for = [&](uint32_t pairs, unsigned cap_grid) {
+            return (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((((uint64_t)pairs + 1) / 2 + SW_BLOCK - 1) / SW_BLOCK, cap_grid));
+        };
         CU_TRY(cudaEventRecord(st.ev_k0, stream));
-        p.list = st.d_list_fast; p.n_list = &st.d_ctr->n_fast; p.cap_cols = cap_narrow;
-        sw_fast_kernel<true><<<grid[0], SW_BLOCK, smem_of(cap_narrow, true), stream>>>(p);
-        K_CHECK(stream, "sw_fast_kernel (narrow)");
-        if (cap_wide > cap_narrow) {                     // usually finds an empty list and returns at once
+        if (n_fast > 0) {
+            p.list = st.d_list_fast; p.n_list = &st.d_ctr->n_fast; p.cap_cols = cap_narrow;
+            sw_fast_kernel<true><<<grid_for(n_fast, grid[0]), SW_BLOCK, smem_of(cap_narrow, true), stream>>>(p);
+            K_CHECK(stream, "sw_fast_kernel (narrow)");
+            st.launches += 1;
+        }
+        if (n_wide > 0) {
             p.list = st.d_list_wide; p.n_list = &st.d_ctr->n_wide; p.cap_cols = cap_wide;
-            sw_fast_kernel<true><<<grid[1], SW_BLOCK, smem_of(cap_wide, true), stream>>>(p);
+            sw_fast_kernel<true><<<grid_for(n_wide, grid[1]), SW_BLOCK, smem_of(cap_wide, true), stream>>>(p);
             K_CHECK(stream, "sw_fast_kernel (wide)");
             st.launches += 1;
         }
-        // pairs whose boundary rows did not fit the difference coding: absolute rows (usually an empty list)
-        p.list = st.d_list_ovf; p.n_list = &st.d_ctr->n_ovf; p.cap_cols = cap_wide;
-        sw_fast_kernel<false><<<grid[2], SW_BLOCK, smem_of(cap_wide, false), stream>>>(p);
-        K_CHECK(stream, "sw_fast_kernel (absolute rows)");
-        st.launches += 1;
         CU_TRY(cudaEventRecord(st.ev_k1, stream));
-        st.launches += 2;
-        CU_TRY(cudaMemcpyAsync(st.h_ctr, st.d_ctr, sizeof(SwCounters), cudaMemcpyDeviceToHost, stream));
-        CU_TRY(cudaStreamSynchronize(stream));
+        st.launches += 1;                                // the classification
+        if (n_fast > 0 || n_wide > 0) {
+            CU_TRY(cudaMemcpyAsync(st.h_ctr, st.d_ctr, sizeof(SwCounters), cudaMemcpyDeviceToHost, stream));
+            CU_TRY(cudaStreamSynchronize(stream));
+            if (st.h_ctr->n_ovf > 0 && !st.h_ctr->cig_overflow) {
+                // pairs whose boundary rows did not fit the difference coding: absolute rows (rare)
+                p.list = st.d_list_ovf; p.n_list = &st.d_ctr->n_ovf; p.cap_cols = cap_wide;
+                sw_fast_kernel<false><<<grid_for(st.h_ctr->n_ovf, grid[2]), SW_BLOCK, smem_of(cap_wide, false), stream>>>(p);
+                K_CHECK(stream, "sw_fast_kernel (absolute rows)");
+                st.launches += 1;
+                CU_TRY(cudaEventRecord(st.ev_k1, stream));
+                CU_TRY(cudaMemcpyAsync(st.h_ctr, st.d_ctr, sizeof(SwCounters), cudaMemcpyDeviceToHost, stream));
+                CU_TRY(cudaStreamSynchronize(stream));
+            }
+        }
         uint32_t ng = st.h_ctr->n_general;
         if (ng > 0 && !st.h_ctr->cig_overflow) {
             // size the per-pair scratch of the general kernel on the host

@@ -6,6 +6,7 @@
 // One bwt_batch owns its stream, device buffers and pinned staging, so several batches can be in flight on one
 // (immutable) index from different host threads.
 #include <algorithm>
+#include <cstddef>
 #include <chrono>
 #include <condition_variable>
 #include <mutex>
@@ -178,8 +179,9 @@ struct bwt_batch {
     uint32_t *d_ncl = nullptr, *d_cl_base = nullptr, *d_hit_off = nullptr, *d_cig_off = nullptr, *d_scan_tmp = nullptr;
     int64_t *d_hit_off64 = nullptr;
     // clusters
-    Cluster *d_clusters = nullptr;
-    size_t cl_cap = 0;
+    Cluster *d_clusters = nullptr;        // dense list (what windows / emit read)
+    Cluster *d_clusters_sparse = nullptr; // the sub-list regions sga_kernel appends to (launch_sga_finish packs them)
+    size_t cl_cap = 0, cl_sparse_cap = 0;
     SlowRead *d_slow = nullptr;
     uint32_t slow_cap = 0;
     uint64_t *d_slow_off = nullptr;
@@ -222,6 +224,7 @@ static int batch_alloc(bwt_batch *b) {
     b->sw.device = b->ix->device;
     size_t want_cl = (size_t)std::max<int64_t>(4 * nr, 4096);
     BWT_TRY(dev_grow(b->d_clusters, b->cl_cap, want_cl, false));
+    BWT_TRY(dev_grow(b->d_clusters_sparse, b->cl_sparse_cap, b->cl_cap, false));
     BWT_TRY(sw_stage_reserve(b->sw, (uint32_t)b->cl_cap));
     return BWT_OK;
 }
@@ -248,7 +251,7 @@ extern "C" int bwt_batch_destroy(bwt_batch *b) {
     if (b->stream) cudaStreamSynchronize(b->stream);
     cudaFree(b->d_reads); cudaFree(b->d_offs); cudaFree(b->d_read_status); cudaFree(b->d_ncl); cudaFree(b->d_cl_base);
     cudaFree(b->d_hit_off); cudaFree(b->d_cig_off); cudaFree(b->d_hit_off64); cudaFree(b->d_scan_tmp);
-    cudaFree(b->d_clusters); cudaFree(b->d_slow); cudaFree(b->d_slow_off); cudaFree(b->d_slow_scratch);
+    cudaFree(b->d_clusters); cudaFree(b->d_clusters_sparse); cudaFree(b->d_slow); cudaFree(b->d_slow_off); cudaFree(b->d_slow_scratch);
     cudaFree(b->d_ctr); cudaFree(b->d_totals); cudaFree(b->d_hits); cudaFree(b->d_cigars);
     if (b->h_ctr) cudaFreeHost(b->h_ctr);
     if (b->h_totals) cudaFreeHost(b->h_totals);
@@ -314,16 +317,21 @@ extern "C" int bwt_batch_upload(bwt_batch *b, const uint8_t *reads, const int64_
 
 // seeding stage with capacity retries; on return h_ctr holds the counters and clusters are complete
 static int run_seed_stage(bwt_batch *b) {
-    const DevIndex &ix = b->ix->dv;
+    DevIndex ix = b->ix->dv;
+    // one lookup for the short subsequence at the front of the reads (8 + Lq mod 8 characters) as well
+    const int tail = b->max_read_len >= 2 * BWT_MIN_LEN ? BWT_MIN_LEN + b->max_read_len % BWT_MIN_LEN : 0;
+    if (const uint2 *t = index_tail_table(b->ix, tail)) { ix.kmer_tail = t; ix.tail_k = tail; }
     for (int attempt = 0; attempt < 6; attempt++) {
+        BWT_TRY(dev_grow(b->d_clusters_sparse, b->cl_sparse_cap, b->cl_cap, false));
+        const uint32_t cl_cap = (uint32_t)std::min<size_t>(std::min(b->cl_cap, b->cl_sparse_cap), 0xFFFFFFF0u);
         CU_TRY(cudaMemsetAsync(b->d_ctr, 0, sizeof(SeedCounters), b->stream));
         CU_TRY(cudaEventRecord(b->ev[6], b->stream));
         BWT_TRY(launch_sga(ix, b->d_reads, b->d_offs, b->n, b->max_read_len, b->d_read_status, b->d_ncl, b->d_cl_base,
-                           b->d_clusters, (uint32_t)std::min<size_t>(b->cl_cap, 0xFFFFFFF0u), b->d_slow, b->slow_cap,
-                           b->d_ctr, b->stream));
+                           b->d_clusters_sparse, cl_cap, b->d_slow, b->slow_cap, b->d_ctr, b->stream));
         CU_TRY(cudaEventRecord(b->ev[7], b->stream));
         b->stats.launches += 1;
-        CU_TRY(cudaMemcpyAsync(b->h_ctr, b->d_ctr, sizeof(SeedCounters), cudaMemcpyDeviceToHost, b->stream));
+        // only the slow-read count is needed on the host now (the first 64 bytes of the counters)
+        CU_TRY(cudaMemcpyAsync(b->h_ctr, b->d_ctr, offsetof(SeedCounters, dense_base), cudaMemcpyDeviceToHost, b->stream));
         CU_TRY(cudaStreamSynchronize(b->stream));
         cudaEventElapsedTime(&b->stats.ms_sga_kernel, b->ev[6], b->ev[7]);
         uint32_t n_slow = b->h_ctr->n_slow;
@@ -347,15 +355,18 @@ static int run_seed_stage(bwt_batch *b) {
             BWT_TRY(dev_grow(b->d_slow_scratch, b->slow_scratch_cap, (size_t)off[n_slow]));
             CU_TRY(cudaMemcpyAsync(b->d_slow_off, off.data(), (n_slow + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, b->stream));
             BWT_TRY(launch_sga_slow(ix, b->d_reads, b->d_offs, b->d_slow, b->d_slow_off, n_slow, b->d_slow_scratch,
-                                    b->d_read_status, b->d_ncl, b->d_cl_base, b->d_clusters,
-                                    (uint32_t)std::min<size_t>(b->cl_cap, 0xFFFFFFF0u), b->d_ctr, b->stream));
+                                    b->d_read_status, b->d_ncl, b->d_cl_base, b->d_clusters_sparse, cl_cap, b->d_ctr, b->stream));
             b->stats.launches += 1;
-            CU_TRY(cudaMemcpyAsync(b->h_ctr, b->d_ctr, sizeof(SeedCounters), cudaMemcpyDeviceToHost, b->stream));
-            CU_TRY(cudaStreamSynchronize(b->stream));
         }
+        // sub-lists -> dense cluster list, dense cl_base, n_clusters
+        BWT_TRY(launch_sga_finish(b->d_clusters_sparse, b->d_clusters, cl_cap, b->d_cl_base, b->d_ncl, b->n, b->d_ctr, b->stream,
+                                  &b->stats.launches));
+        CU_TRY(cudaMemcpyAsync(b->h_ctr, b->d_ctr, offsetof(SeedCounters, dense_base), cudaMemcpyDeviceToHost, b->stream));
+        CU_TRY(cudaStreamSynchronize(b->stream));
         if (!b->h_ctr->cluster_overflow) return BWT_OK;
-        // cluster list too small: n_clusters is a lower bound of what is needed (deferred reads not yet counted)
-        size_t want = (size_t)b->h_ctr->n_clusters * 2 + 4096;
+        // a sub-list ran out of room: n_clusters is a lower bound of what is needed (refused reads not counted in full);
+        // the regions are equal shares, so ask for twice the total
+        size_t want = (size_t)std::max<uint64_t>(b->h_ctr->n_clusters, b->cl_cap) * 2 + 4096;
         BWT_TRY(dev_grow(b->d_clusters, b->cl_cap, want, false));
     }
     bwt_set_error("cluster list kept overflowing");

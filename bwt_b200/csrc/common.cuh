@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -61,6 +62,8 @@ struct DevIndex {
     const uint2 *kmer_deep;    // 4^deep_k entries, or null
     const uint2 *kmer_mid;     // the tables of depth 9..deep_k-1 back to back (kmer_mid_offset), or null: a subsequence
                                // with fewer than deep_k plain characters at its end still costs ONE lookup
+    const uint2 *kmer_tail;    // ONE table of depth tail_k (8 < tail_k < deep_k), or null: set per launch for the length of
+    int tail_k;                // the short subsequence at the front of the batch's reads (8 + Lq mod 8 characters)
     int deep_k;                // 9..15, or 0 when there is no deep table
     const uint8_t *ref;        // .ref padded with 200 'N' on both sides (worker_bwt.erl:53-55)
     uint64_t ref_len_padded;
@@ -96,6 +99,8 @@ struct bwt_index {
     int64_t shift = 0;
     uint64_t device_bytes = 0;
     uint64_t mid_bytes = 0;    // kmer_mid part of device_bytes
+    std::mutex *tail_mu = nullptr;                 // guards the lazily built single-depth tables below
+    void *d_tail[BWT_MAX_LEN] = {};                // d_tail[k]: table of depth k, built on first use (index_tail_table)
     void *d_occ = nullptr, *d_sa = nullptr, *d_kmer = nullptr, *d_ref = nullptr, *d_kmer_deep = nullptr, *d_kmer_mid = nullptr;
 };
 
@@ -146,6 +151,8 @@ int exclusive_scan_u32(uint32_t *d_data, size_t n, uint32_t *d_tmp, uint32_t *d_
 int index_finish_from_device(bwt_index *h, const uint8_t *d_L, uint64_t n, uint32_t *d_sa, uint8_t *d_ref_padded,
                              uint64_t ref_len, const uint32_t pointers[4], int64_t shift);
 int index_select_device(int device);
+// Depth-k interval table (8 < k < deep_k) of this index, built on first use and kept; null when it cannot be had.
+const uint2 *index_tail_table(bwt_index *h, int k);
 int index_upload_ref_device(const uint8_t *d_ref, uint64_t len, uint8_t **d_out);
 
 // ---- builder (build.cu) -------------------------------------------------------------------------

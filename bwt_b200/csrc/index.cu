@@ -197,10 +197,40 @@ int index_finish_from_device(bwt_index *h, const uint8_t *d_L, uint64_t n, uint3
     return bwt_set_kmer_depth(h, k);
 }
 
+// The short subsequence at the front of a read (8 + Lq mod 8 characters: 12 for 100 bp, 14 for 150 bp, 10 for 250 bp) is
+// too short for the deep table; with a table of exactly its depth it costs one lookup instead of a lookup plus up to
+// six dependent Occ steps.  Built on first use (4^k entries: 134 MB at k = 12), one per depth, kept with the index.
+const uint2 *index_tail_table(bwt_index *h, int k) {
+    if (!h || k <= BWT_MIN_LEN || k >= h->dv.deep_k || k >= BWT_MAX_LEN || !h->tail_mu) return nullptr;
+    const char *e = getenv("BWT_KMER_TAIL");
+    if (e && e[0] == '0') return nullptr;
+    std::lock_guard<std::mutex> g(*h->tail_mu);
+    if (h->d_tail[k]) return (const uint2 *)h->d_tail[k];
+    uint2 *tab = nullptr;
+    if (cudaSetDevice(h->device) != cudaSuccess || cudaMalloc(&tab, sizeof(uint2) << (2 * k)) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    DevIndex dv = h->dv;
+    dv.kmer_tail = nullptr; dv.tail_k = 0;
+    cudaMemcpy(tab, h->d_kmer, 65536 * sizeof(uint2), cudaMemcpyDeviceToDevice);
+    for (int d = 8; d < k; d++) kmer_expand_kernel<<<(unsigned)div_up_u64(1ull << (2 * d), 256), 256>>>(dv, tab, d);
+    if (cudaDeviceSynchronize() != cudaSuccess) { cudaGetLastError(); cudaFree(tab); return nullptr; }
+    h->d_tail[k] = tab;
+    h->device_bytes += sizeof(uint2) << (2 * k);
+    return tab;
+}
+
+static void free_tail_tables(bwt_index *h) {
+    if (!h->tail_mu) return;
+    std::lock_guard<std::mutex> g(*h->tail_mu);
+    for (int k = 0; k < BWT_MAX_LEN; k++)
+        if (h->d_tail[k]) { cudaFree(h->d_tail[k]); h->d_tail[k] = nullptr; h->device_bytes -= sizeof(uint2) << (2 * k); }
+}
+
 extern "C" int bwt_set_kmer_depth(bwt_index *h, int k) {
     if (!h || (k != 0 && (k < 8 || k > BWT_MAX_LEN))) { bwt_set_error("bwt_set_kmer_depth: depth must be 0 or 8..15"); return BWT_ERR_ARG; }
     CU_TRY(cudaSetDevice(h->device));
     CU_TRY(cudaDeviceSynchronize());
+    if (!h->tail_mu) h->tail_mu = new std::mutex();
+    free_tail_tables(h);
     if (h->d_kmer_deep) {
         h->device_bytes -= (8ull << (2 * h->dv.deep_k));
         cudaFree(h->d_kmer_deep);
@@ -339,6 +369,8 @@ extern "C" int bwt_open(const char *fm_path, const char *ref_path, int device, b
 extern "C" int bwt_close(bwt_index *h) {
     if (!h) return BWT_OK;
     cudaSetDevice(h->device);
+    free_tail_tables(h);
+    delete h->tail_mu;
     cudaFree(h->d_occ); cudaFree(h->d_sa); cudaFree(h->d_kmer); cudaFree(h->d_kmer_deep); cudaFree(h->d_kmer_mid); cudaFree(h->d_ref);
     delete h;
     return BWT_OK;

@@ -71,6 +71,19 @@ __global__ void __launch_bounds__(256) search_kernel(DevIndex ix, const uint8_t 
     if (ctr) flush_counters(s_ctr, ctr);
 }
 
+// `emitted` slots in this block's sub-list -> sparse index of the first one (the region's end when it is full: every
+// write is then refused by cluster_slot_ok and the host retries with a larger array)
+__device__ __forceinline__ uint32_t cluster_alloc(SeedCounters *ctr, uint32_t emitted, uint32_t cl_cap) {
+    const uint32_t r = blockIdx.x % SGA_SUBLISTS, cap_r = cl_cap / SGA_SUBLISTS;
+    const uint32_t local = atomicAdd(&ctr->sub_n[32 * r], emitted);
+    if ((uint64_t)local + emitted > cap_r) atomicExch(&ctr->cluster_overflow, 1u);
+    return r * cap_r + min(local, cap_r);
+}
+__device__ __forceinline__ bool cluster_slot_ok(uint32_t base_out, uint32_t rank, uint32_t cl_cap) {
+    const uint32_t r = blockIdx.x % SGA_SUBLISTS, cap_r = cl_cap / SGA_SUBLISTS;
+    return (uint64_t)(base_out - r * cap_r) + rank < cap_r;
+}
+
 // ---------------------------------------------------------------------------------------------------
 // sga:skip_Ns/1 (sga.erl:69-76): -1 = no_more_subseqs, else Skipped (the new length is len - Skipped).
 // The 'N' that ends a skipped stretch is itself counted as the first of the next eight.
@@ -254,7 +267,7 @@ __device__ __forceinline__ int sga_read(const Tile &tile, const DevIndex &ix, co
             uint32_t bal = tile.ballot(em);
             if (pass == 1 && em) {
                 uint32_t rank = emitted + __popc(bal & ((1u << lane) - 1u));
-                if ((uint64_t)base_out + rank < cl_cap) {      // on overflow the host retries with the needed capacity
+                if (cluster_slot_ok(base_out, rank, cl_cap)) { // on overflow the host retries with the needed capacity
                     Cluster c;
                     c.read = read; c.s = S; c.d = (int32_t)D; c.rank = rank;
                     clusters[base_out + rank] = c;
@@ -265,8 +278,7 @@ __device__ __forceinline__ int sga_read(const Tile &tile, const DevIndex &ix, co
         if (pass == 0) {
             if (emitted == 0) break;
             if (lane == 0) {
-                base_out = atomicAdd(&ctr->n_clusters, emitted);
-                if ((uint64_t)base_out + emitted > cl_cap) atomicExch(&ctr->cluster_overflow, 1u);
+                base_out = cluster_alloc(ctr, emitted, cl_cap);
             }
             base_out = tile.shfl(base_out, 0);
         }
@@ -380,15 +392,14 @@ __device__ __forceinline__ void sort_vote_regs(const Tile &tile, const uint32_t 
     uint32_t base_out = 0;
     if (emitted) {
         if (lane == 0) {
-            base_out = atomicAdd(&ctr->n_clusters, emitted);
-            if ((uint64_t)base_out + emitted > cl_cap) atomicExch(&ctr->cluster_overflow, 1u);
+            base_out = cluster_alloc(ctr, emitted, cl_cap);
         }
         base_out = tile.shfl(base_out, 0);
         uint32_t rank = inc - c;                                 // emitted in higher lanes
 #pragma unroll
         for (int r = EPL - 1; r >= 0; r--) {
             if ((em >> r) & 1u) {
-                if ((uint64_t)base_out + rank < cl_cap) {
+                if (cluster_slot_ok(base_out, rank, cl_cap)) {
                     Cluster cc;
                     cc.read = read; cc.s = v[r]; cc.d = (int32_t)dist[r]; cc.rank = rank;
                     clusters[base_out + rank] = cc;
@@ -567,6 +578,41 @@ __global__ void __launch_bounds__(SGA_BLOCK) sga_slow_kernel(DevIndex ix, const 
 }
 
 }  // namespace
+
+namespace {
+__global__ void cluster_offsets_kernel(SeedCounters *ctr, uint32_t cap_r) {     // one warp
+    uint32_t sum = 0, dense = 0;
+    for (int r = 0; r < SGA_SUBLISTS; r++) {
+        const uint32_t c = ctr->sub_n[32 * r];
+        if (threadIdx.x == 0) ctr->dense_base[r] = dense;
+        sum += c; dense += min(c, cap_r);
+    }
+    if (threadIdx.x == 0) ctr->n_clusters = sum;
+}
+__global__ void cluster_compact_kernel(const Cluster *__restrict__ sparse, Cluster *__restrict__ dense, const SeedCounters *ctr,
+                                       uint32_t cap_r) {
+    const uint32_t r = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < min(ctr->sub_n[32 * r], cap_r)) dense[ctr->dense_base[r] + i] = sparse[(size_t)r * cap_r + i];
+}
+__global__ void cluster_rebase_kernel(uint32_t *__restrict__ cl_base, const uint32_t *__restrict__ ncl, int64_t n,
+                                      const SeedCounters *ctr, uint32_t cap_r) {
+    const int64_t read = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (read >= n || ncl[read] == 0) return;
+    const uint32_t b = cl_base[read], r = min(b / cap_r, (uint32_t)SGA_SUBLISTS - 1);
+    cl_base[read] = ctr->dense_base[r] + (b - r * cap_r);
+}
+}  // namespace
+
+int launch_sga_finish(const Cluster *d_sparse, Cluster *d_dense, uint32_t cl_cap, uint32_t *d_cl_base, const uint32_t *d_ncl,
+                      int64_t n_reads, SeedCounters *d_ctr, cudaStream_t stream, uint32_t *launches) {
+    const uint32_t cap_r = cl_cap / SGA_SUBLISTS;
+    cluster_offsets_kernel<<<1, 32, 0, stream>>>(d_ctr, cap_r);
+    cluster_compact_kernel<<<dim3((cap_r + 255) / 256, SGA_SUBLISTS), 256, 0, stream>>>(d_sparse, d_dense, d_ctr, cap_r);
+    if (n_reads > 0) cluster_rebase_kernel<<<(unsigned)((n_reads + 255) / 256), 256, 0, stream>>>(d_cl_base, d_ncl, n_reads, d_ctr, cap_r);
+    if (launches) *launches += 3;
+    CU_TRY(cudaGetLastError());
+    return BWT_OK;
+}
 
 int launch_search(const DevIndex &ix, const uint8_t *d_subs, const int64_t *d_offs, int64_t n, int32_t fixed_len,
                   int32_t *d_status, uint32_t *d_sp, uint32_t *d_ep, int32_t *d_n, SeedCounters *d_ctr,

@@ -12,12 +12,19 @@ struct Cluster {        // one element of sga's result list, 16 B
     uint32_t rank;      // position in the reference's (descending) result list
 };
 
+// Clusters are appended to SGA_SUBLISTS sub-lists (one region of the cluster array and one cursor on its own 128-byte
+// line each, chosen by block): ten million appends to ONE cursor serialise in a single L2 slice (1.75 ns each: the
+// whole kernel ran at the speed of that atomic).  launch_sga_finish packs the regions into the dense list.
+constexpr int SGA_SUBLISTS = 64;
+
 struct SeedCounters {   // device-side counters of one run
     unsigned long long searches, lf_steps, hbm_lf_steps, located, clusters;
-    uint32_t n_clusters;      // append cursor of the cluster list
+    uint32_t n_clusters;      // clusters appended (sum over the sub-lists; set by launch_sga_finish)
     uint32_t n_slow;          // reads whose seed ends did not fit the shared-memory budget
     uint32_t cluster_overflow;
     uint32_t pad;
+    uint32_t dense_base[SGA_SUBLISTS];          // first dense slot of each sub-list (launch_sga_finish)
+    uint32_t sub_n[SGA_SUBLISTS * 32];          // cursor of sub-list r at [32 r]
 };
 
 struct SlowRead { uint32_t read; uint32_t seeds; };
@@ -31,6 +38,9 @@ int launch_search(const DevIndex &ix, const uint8_t *d_subs, const int64_t *d_of
 int launch_sga(const DevIndex &ix, const uint8_t *d_reads, const int64_t *d_offs, int64_t n_reads, int max_read_len,
                int32_t *d_read_status, uint32_t *d_ncl, uint32_t *d_cl_base, Cluster *d_clusters, uint32_t cl_cap,
                SlowRead *d_slow, uint32_t slow_cap, SeedCounters *d_ctr, cudaStream_t stream);
+// Packs the sub-lists of d_sparse into d_dense, turns cl_base into dense indices and sets d_ctr->n_clusters.
+int launch_sga_finish(const Cluster *d_sparse, Cluster *d_dense, uint32_t cl_cap, uint32_t *d_cl_base, const uint32_t *d_ncl,
+                      int64_t n_reads, SeedCounters *d_ctr, cudaStream_t stream, uint32_t *launches);
 int launch_sga_slow(const DevIndex &ix, const uint8_t *d_reads, const int64_t *d_offs, const SlowRead *d_slow,
                     const uint64_t *d_slow_off, uint32_t n_slow, uint32_t *d_scratch, int32_t *d_read_status,
                     uint32_t *d_ncl, uint32_t *d_cl_base, Cluster *d_clusters, uint32_t cl_cap, SeedCounters *d_ctr,

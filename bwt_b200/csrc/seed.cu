@@ -340,7 +340,7 @@ template <int G, int EPL, typename Tile>
 __device__ __forceinline__ void sort_vote_regs(const Tile &tile, const uint32_t *seeds, const uint32_t total,
                                                const uint32_t need, const uint32_t read, uint32_t *ncl, uint32_t *cl_base,
                                                Cluster *clusters, const uint32_t cl_cap, SeedCounters *ctr,
-                                               unsigned long long *s_ctr) {
+                                               uint32_t (&acc)[CTR_N]) {
     const int lane = tile.thread_rank();
     uint32_t v[EPL];
 #pragma unroll
@@ -411,7 +411,7 @@ __device__ __forceinline__ void sort_vote_regs(const Tile &tile, const uint32_t 
     if (lane == 0) {
         ncl[read] = emitted;
         cl_base[read] = base_out;
-        atomicAdd(&s_ctr[CTR_CLUSTERS], (unsigned long long)emitted);
+        acc[CTR_CLUSTERS] += emitted;
     }
 }
 
@@ -419,24 +419,21 @@ template <int G, int MAXT, typename Tile>
 __device__ __forceinline__ int sga_fast_read(const Tile &tile, const DevIndex &ix, const uint8_t *__restrict__ q, const int lq,
                                              const uint32_t read, uint32_t *seeds, uint32_t *pack, const GroupShared &gs,
                                              int32_t *read_status, uint32_t *ncl, uint32_t *cl_base, Cluster *clusters,
-                                             const uint32_t cl_cap, SeedCounters *ctr, unsigned long long *s_ctr) {
+                                             const uint32_t cl_cap, SeedCounters *ctr, uint32_t (&acc)[CTR_N]) {
     const int lane = tile.thread_rank();
-    // -- pack the read, reversed; any byte outside ACGT sends the read to the general path
+    // -- pack the read, reversed (base lq-1-i at bits 2i); any byte outside ACGT sends the read to the general path.
+    //    Word w holds the 16 bases ending at e = lq-1-16w: packed forward four bytes at a time, then turned round.
     const int nw = (lq + 15) >> 4;
     bool valid = true;
     for (int w = lane; w <= nw; w += G) {
         uint32_t word = 0;
         if (w < nw) {
-#pragma unroll 4
-            for (int t = 0; t < 16; t++) {
-                const int p = lq - 1 - (16 * w + t);
-                if (p >= 0) {
-                    const uint32_t ch = q[p];
-                    const uint32_t x = (ch >> 1) & 3u;                       // A0 C1 T2 G3
-                    valid &= ((0x47544341u >> (8 * x)) & 0xFFu) == ch;       // "ACTG"[x] == ch
-                    word |= (x ^ (x >> 1)) << (2 * t);                       // A0 C1 G2 T3
-                }
-            }
+            const int e = lq - 1 - 16 * w, start = max(e - 15, 0), cnt = e - start + 1;
+            uint32_t fw = pack16_acgt(q + start, cnt, valid);                // base start+t at bits 2t, codes A0 C1 T2 G3
+            fw ^= (fw >> 1) & 0x55555555u;                                   // -> A0 C1 G2 T3
+            fw <<= 2 * (16 - cnt);                                           // a short first word: bases to the top
+            const uint32_t rv = __brev(fw);                                  // reverses the bases and the bits inside each
+            word = ((rv & 0xAAAAAAAAu) >> 1) | ((rv & 0x55555555u) << 1);
         }
         pack[w] = word;                                                      // pack[nw] = 0: upper word of the last funnel shift
     }
@@ -479,11 +476,8 @@ __device__ __forceinline__ int sga_fast_read(const Tile &tile, const DevIndex &i
     }
     if (total > (uint32_t)(8 * G)) return SGA_FALLBACK;       // the general path redoes (and counts) the searches (rare)
     if (lane == 0) {
-        atomicAdd(&s_ctr[CTR_SEARCHES], (unsigned long long)nt);
-        atomicAdd(&s_ctr[CTR_LF], lf);
-        atomicAdd(&s_ctr[CTR_HBM_LF], hbm);
+        acc[CTR_SEARCHES] += (uint32_t)nt; acc[CTR_LF] += (uint32_t)lf; acc[CTR_HBM_LF] += (uint32_t)hbm; acc[CTR_LOCATED] += total;
         read_status[read] = BWT_READ_OK;
-        atomicAdd(&s_ctr[CTR_LOCATED], (unsigned long long)total);
     }
     if (qty < 2) {                                             // get_similar(0|1,_) -> []  (sga.erl:42-43)
         if (lane == 0) { ncl[read] = 0; cl_base[read] = 0; }
@@ -502,10 +496,10 @@ __device__ __forceinline__ int sga_fast_read(const Tile &tile, const DevIndex &i
     }
     tile.sync();
     const uint32_t need = 2 + qty / 7;
-    if (total <= (uint32_t)G) sort_vote_regs<G, 1>(tile, seeds, total, need, read, ncl, cl_base, clusters, cl_cap, ctr, s_ctr);
-    else if (total <= (uint32_t)(2 * G)) sort_vote_regs<G, 2>(tile, seeds, total, need, read, ncl, cl_base, clusters, cl_cap, ctr, s_ctr);
-    else if (total <= (uint32_t)(4 * G)) sort_vote_regs<G, 4>(tile, seeds, total, need, read, ncl, cl_base, clusters, cl_cap, ctr, s_ctr);
-    else sort_vote_regs<G, 8>(tile, seeds, total, need, read, ncl, cl_base, clusters, cl_cap, ctr, s_ctr);
+    if (total <= (uint32_t)G) sort_vote_regs<G, 1>(tile, seeds, total, need, read, ncl, cl_base, clusters, cl_cap, ctr, acc);
+    else if (total <= (uint32_t)(2 * G)) sort_vote_regs<G, 2>(tile, seeds, total, need, read, ncl, cl_base, clusters, cl_cap, ctr, acc);
+    else if (total <= (uint32_t)(4 * G)) sort_vote_regs<G, 4>(tile, seeds, total, need, read, ncl, cl_base, clusters, cl_cap, ctr, acc);
+    else sort_vote_regs<G, 8>(tile, seeds, total, need, read, ncl, cl_base, clusters, cl_cap, ctr, acc);
     tile.sync();
     return SGA_DONE;
 }
@@ -530,6 +524,7 @@ __global__ void __launch_bounds__(SGA_BLOCK, SGA_MIN_BLOCKS) sga_kernel(DevIndex
     auto tile = cg::tiled_partition<G>(cg::this_thread_block());
     const int g = threadIdx.x / G;
     GroupShared gs{s_end[g], s_shift[g], s_res[g], s_pos[g]};
+    uint32_t acc[CTR_N] = {0u, 0u, 0u, 0u, 0u};                   // lane 0 of the group: work counters of its fast-path reads
     for (int64_t read = (int64_t)blockIdx.x * GPB + g; read < n_reads; read += (int64_t)gridDim.x * GPB) {
         const uint8_t *q = reads + offs[read];
         int lq = (int)(offs[read + 1] - offs[read]);
@@ -542,11 +537,16 @@ __global__ void __launch_bounds__(SGA_BLOCK, SGA_MIN_BLOCKS) sga_kernel(DevIndex
         int how = SGA_FALLBACK;
         if (lq <= BWT_MIN_LEN * (MAXT - 1) + BWT_MAX_LEN)
             how = sga_fast_read<G, MAXT>(tile, ix, q, lq, (uint32_t)read, s_seeds[g], s_pack[g], gs, read_status, ncl, cl_base,
-                                         clusters, cl_cap, ctr, s_ctr);
+                                         clusters, cl_cap, ctr, acc);
         if (how == SGA_FALLBACK)                                  // 'N' / other bytes, or more seed ends than registers hold
             sga_read<G, MAXT, false>(tile, ix, q, lq, (uint32_t)read, s_seeds[g], CAP, gs, read_status, ncl, cl_base,
                                      clusters, cl_cap, slow, slow_cap, ctr, s_ctr);
         tile.sync();
+    }
+    if (tile.thread_rank() == 0) {
+#pragma unroll
+        for (int k = 0; k < CTR_N; k++)
+            if (acc[k]) atomicAdd(&s_ctr[k], (unsigned long long)acc[k]);
     }
     flush_counters(s_ctr, ctr);
 }

@@ -71,15 +71,18 @@ __global__ void __launch_bounds__(256) search_kernel(DevIndex ix, const uint8_t 
     if (ctr) flush_counters(s_ctr, ctr);
 }
 
-// `emitted` slots in this block's sub-list -> sparse index of the first one (the region's end when it is full: every
+// `emitted` slots in this block's sub-list (by block, not by read: neighbouring reads stay neighbours in the dense list,
+// which emit_kernel's gathers like: by read number emit went 0.71 -> 1.03 ms) -> sparse index of the first one (the region's end when it is full: every
 // write is then refused by cluster_slot_ok and the host retries with a larger array)
-__device__ __forceinline__ uint32_t cluster_alloc(SeedCounters *ctr, uint32_t emitted, uint32_t cl_cap) {
+__device__ __forceinline__ uint32_t cluster_alloc(SeedCounters *ctr, uint32_t read, uint32_t emitted, uint32_t cl_cap) {
+    (void)read;
     const uint32_t r = blockIdx.x % SGA_SUBLISTS, cap_r = cl_cap / SGA_SUBLISTS;
     const uint32_t local = atomicAdd(&ctr->sub_n[32 * r], emitted);
     if ((uint64_t)local + emitted > cap_r) atomicExch(&ctr->cluster_overflow, 1u);
     return r * cap_r + min(local, cap_r);
 }
-__device__ __forceinline__ bool cluster_slot_ok(uint32_t base_out, uint32_t rank, uint32_t cl_cap) {
+__device__ __forceinline__ bool cluster_slot_ok(uint32_t base_out, uint32_t read, uint32_t rank, uint32_t cl_cap) {
+    (void)read;
     const uint32_t r = blockIdx.x % SGA_SUBLISTS, cap_r = cl_cap / SGA_SUBLISTS;
     return (uint64_t)(base_out - r * cap_r) + rank < cap_r;
 }
@@ -267,7 +270,7 @@ __device__ __forceinline__ int sga_read(const Tile &tile, const DevIndex &ix, co
             uint32_t bal = tile.ballot(em);
             if (pass == 1 && em) {
                 uint32_t rank = emitted + __popc(bal & ((1u << lane) - 1u));
-                if (cluster_slot_ok(base_out, rank, cl_cap)) { // on overflow the host retries with the needed capacity
+                if (cluster_slot_ok(base_out, read, rank, cl_cap)) { // on overflow the host retries with the needed capacity
                     Cluster c;
                     c.read = read; c.s = S; c.d = (int32_t)D; c.rank = rank;
                     clusters[base_out + rank] = c;
@@ -278,7 +281,7 @@ __device__ __forceinline__ int sga_read(const Tile &tile, const DevIndex &ix, co
         if (pass == 0) {
             if (emitted == 0) break;
             if (lane == 0) {
-                base_out = cluster_alloc(ctr, emitted, cl_cap);
+                base_out = cluster_alloc(ctr, read, emitted, cl_cap);
             }
             base_out = tile.shfl(base_out, 0);
         }
@@ -392,14 +395,14 @@ __device__ __forceinline__ void sort_vote_regs(const Tile &tile, const uint32_t 
     uint32_t base_out = 0;
     if (emitted) {
         if (lane == 0) {
-            base_out = cluster_alloc(ctr, emitted, cl_cap);
+            base_out = cluster_alloc(ctr, read, emitted, cl_cap);
         }
         base_out = tile.shfl(base_out, 0);
         uint32_t rank = inc - c;                                 // emitted in higher lanes
 #pragma unroll
         for (int r = EPL - 1; r >= 0; r--) {
             if ((em >> r) & 1u) {
-                if (cluster_slot_ok(base_out, rank, cl_cap)) {
+                if (cluster_slot_ok(base_out, read, rank, cl_cap)) {
                     Cluster cc;
                     cc.read = read; cc.s = v[r]; cc.d = (int32_t)dist[r]; cc.rank = rank;
                     clusters[base_out + rank] = cc;

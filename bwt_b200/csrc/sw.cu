@@ -64,7 +64,7 @@ __device__ __forceinline__ uint32_t both(int k) { return ((uint32_t)k & 0xFFFFu)
 //   * every cell of that diagonal holds exactly the diagonal's prefix score (more would push the end cell past the
 //     maximum), its up_left candidate attains it, and ties go up_left > up > left: the traceback is "<Lq>M";
 //   * the row threshold -2*(Lq div 2) + 2*i (sw.erl:62,69-71) is never undercut while p* <= 2*(Lq div 2).
-// Searched up to penalty SW_SHORTCUT_PMAX (three mismatches); paths may leave the window's diagonals by up to
+// Searched up to penalty SC_PMAX (five mismatches); paths may leave the window's diagonals by up to
 // SC_K = (PMAX-1)/3 on either side (column 0 starts with a query-side gap, sw.erl:72-77).  Anything else -- optimal
 // paths with a gap, more mismatches, other bytes -- runs the DP.  tests/test_gpu_parity.py runs its SW cases with
 // this shortcut on and off, including low-complexity strings built to break it.
@@ -80,9 +80,9 @@ __device__ __forceinline__ unsigned grp_min(unsigned v) {
     for (int o = 1; o < SC_LANES; o <<= 1) v = min(v, __shfl_xor_sync(0xFFFFFFFFu, v, o));
     return v;
 }
-constexpr int SC_PMAX = 9;                          // largest penalty searched: three mismatches
+constexpr int SC_PMAX = 15;                         // largest penalty searched: five mismatches
 constexpr int SC_K = (SC_PMAX - 1) / 3;             // query characters a path of that penalty can skip
-constexpr int SC_ND = 24;                           // diagonals -SC_K .. SW_SHORTCUT_MAX_D + SC_K, padded
+constexpr int SC_ND = 32;                           // diagonals -SC_K .. SW_SHORTCUT_MAX_D + SC_K, padded
 constexpr int SC_RING = 5;                          // wavefronts kept: s, s-1, .., s-4
 constexpr int SC_MAXQ = 256;                        // longest query the shortcut looks at
 constexpr int SC_QW = SC_MAXQ / 16;                 // 2-bit packed query words (16 bases each)
@@ -136,8 +136,11 @@ __device__ __forceinline__ int sw_shortcut(const uint8_t *q, int lq, const uint8
     __syncwarp();                                                    // qp / rp visible to the whole group
     const unsigned plain_mask = __ballot_sync(FULL, plain);          // by every lane, before any short-circuit
     elig = elig && ((plain_mask >> (lane - t)) & ((1u << SC_LANES) - 1u)) == ((1u << SC_LANES) - 1u);
-    const int nd = dd + 2 * SC_K + 1;                                // diagonal slot d <-> o = d - SC_K
-    const int pmax = min(SC_PMAX, 2 * (lq >> 1));                   // the row threshold holds up to here
+    // penalty budget by read length (three mismatches up to 128 bp, four up to 192, five beyond): every level costs
+    // the whole warp time, and a wider budget also means more diagonals (kk on either side of the window's)
+    const int pmax = min(lq <= 128 ? 9 : lq <= 192 ? 12 : SC_PMAX, 2 * (lq >> 1));   // the row threshold holds up to 2*(Lq div 2)
+    const int kk = (pmax - 1) / 3;
+    const int nd = dd + 2 * kk + 1;                                  // diagonal slot d <-> o = d - kk
     bool open = elig;
     int pstar = -1, omin = 0x7FFF;
     int cur = 0;                                                     // ring slot of wavefront s
@@ -148,8 +151,12 @@ __device__ __forceinline__ int sw_shortcut(const uint8_t *q, int lq, const uint8
             const int p1 = cur == 0 ? SC_RING - 1 : cur - 1, p2 = p1 == 0 ? SC_RING - 1 : p1 - 1, p3 = p2 == 0 ? SC_RING - 1 : p2 - 1,
                       p4 = p3 == 0 ? SC_RING - 1 : p3 - 1;
             for (int d = t; d < nd; d += SC_LANES) {
-                const int o = d - SC_K;
+                const int o = d - kk;
                 int dv = -1, iv = -1, mv = -1;
+                if (s == 1) {                                        // nothing costs 1: an empty wavefront
+                    wf.v[cur][0][d] = -1; wf.v[cur][1][d] = -1; wf.v[cur][2][d] = -1;
+                    continue;
+                }
                 if (d > 0) {                                         // skip a window character: diagonal o-1 -> o
                     if (s >= 2) dv = wf.v[p2][0][d - 1];
                     if (s >= 1) dv = max(dv, (int)wf.v[p1][2][d - 1]);
@@ -173,7 +180,7 @@ __device__ __forceinline__ int sw_shortcut(const uint8_t *q, int lq, const uint8
         }
         __syncwarp();
         best = grp_min(best);
-        if (act && best != 0x7FFFu) { open = false; pstar = s; omin = (int)best - SC_K; }
+        if (act && best != 0x7FFFu) { open = false; pstar = s; omin = (int)best - kk; }
         if (__all_sync(FULL, !open || s >= pmax)) break;
         cur = cur + 1 == SC_RING ? 0 : cur + 1;
     }

@@ -13,15 +13,16 @@ ACGT = set(b"ACGT")
 NEG = -10 ** 6
 
 
-def wfa_shortcut(q: bytes, r: bytes, pmax: int = 9, maxd: int = 16):
+def wfa_shortcut(q: bytes, r: bytes, pmax: int = 15, maxd: int = 16):
     lq, lr = len(q), len(r)
     dd = lr - lq
     if dd < 0 or dd > maxd or lq < 4:
         return None
     pmax = min(pmax, 2 * (lq // 2))               # the row threshold -2*(Lq div 2) + 2i holds on the diagonal up to here
+    # (the kernel also narrows the budget by read length -- 9 up to 128 bp, 12 up to 192, 15 beyond: any budget is sound)
     if any(c not in ACGT for c in q) or any(c not in ACGT for c in r):
         return None
-    k = (9 - 1) // 3
+    k = max(0, (pmax - 1) // 3)
     lo, hi = -k, dd + k
 
     def ext(o, i):
@@ -79,7 +80,7 @@ def _cases(rng, n):
             s0 = rng.randint(0, dd + 2)
             q = bytearray(base[s0:s0 + lq])
             q += rs(lq - len(q), alpha)
-            for _k in range(rng.choice([0, 1, 1, 2, 2, 2, 3, 3, 4])):
+            for _k in range(rng.choice([0, 1, 1, 2, 2, 2, 3, 3, 4, 5, 5, 6])):
                 u = rng.random()
                 if u < 0.7:
                     q[rng.randrange(lq)] = rng.choice(alpha)
@@ -97,7 +98,7 @@ def _cases(rng, n):
                 r[rng.randrange(len(r))] = rng.choice(b"ACGT")
             s0 = rng.randint(0, dd)
             q = bytearray(base[s0:s0 + lq])
-            for _k in range(rng.randint(0, 3)):
+            for _k in range(rng.randint(0, 5)):
                 q[rng.randrange(lq)] = rng.choice(b"ACGT")
             yield bytes(q), bytes(r)
         else:
@@ -114,7 +115,7 @@ def test_rule_agrees_with_sw_on_adversarial_pairs():
         assert c_sw(q, r) == sc, (q, r, sc)
         m = (2 * len(q) - sc[0]) // 3
         settled[m] = settled.get(m, 0) + 1
-    assert all(settled.get(m, 0) > 300 for m in (0, 1, 2, 3)), settled
+    assert all(settled.get(m, 0) > 200 for m in (0, 1, 2, 3, 4, 5)), settled
 
 
 def test_rule_declines_what_it_cannot_prove():

@@ -793,7 +793,7 @@ int sw_stage_run(SwStage &st, const uint8_t *d_qbase, const uint8_t *d_rbase, ui
     st.ms_fast_kernel = 0;
     // BWT_SW_SHORTCUT=0 sends every pair through the DP (A/B timing, and parity tests of the DP on easy pairs)
     const char *env_sc = getenv("BWT_SW_SHORTCUT");
-    const int use_shortcut = !(env_sc && env_sc[0] == '0');
+    const int use_shortcut = !(env_sc && env_sc[0] == '0');      // (read per run: tests flip it between calls)
     if (n == 0) return BWT_OK;
     if (n > st.cap) { bwt_set_error("sw_stage_run: %u pairs exceed the reserved %u", n, st.cap); return BWT_ERR_ARG; }
     // two shared-memory tiers of the fast kernel: "narrow" holds windows up to Lq + 15 columns (almost every
@@ -803,21 +803,25 @@ int sw_stage_run(SwStage &st, const uint8_t *d_qbase, const uint8_t *d_rbase, ui
     int cap_wide = std::min(cap_limit, std::max(96, ((max_lq + 1 + 64) + 15) & ~15));
     int max_strips = (std::min(max_lq, SW_FAST_MAX_LQ) + SW_R - 1) / SW_R;
     if (max_strips < 1) max_strips = 1;
-    int sms = 0;
-    CU_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, st.device));
     auto smem_of = [](int cap, bool delta) { return (size_t)SW_BLOCK * ((size_t)cap * (delta ? 2 : 4) + (size_t)(cap / 16) * 8); };
-    CU_TRY(cudaFuncSetAttribute(sw_fast_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_of(cap_wide, true)));
-    CU_TRY(cudaFuncSetAttribute(sw_fast_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_of(cap_wide, false)));
-    unsigned grid[3];
     const int caps[3] = {cap_narrow, cap_wide, cap_wide};
+    if (st.cfg_max_lq != max_lq) {                       // attribute / occupancy queries once per configuration, not per batch
+        CU_TRY(cudaDeviceGetAttribute(&st.cfg_sms, cudaDevAttrMultiProcessorCount, st.device));
+        CU_TRY(cudaFuncSetAttribute(sw_fast_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_of(cap_wide, true)));
+        CU_TRY(cudaFuncSetAttribute(sw_fast_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_of(cap_wide, false)));
+        for (int t = 0; t < 3; t++) {
+            if (t < 2) CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&st.cfg_per_sm[t], sw_fast_kernel<true>, SW_BLOCK, smem_of(caps[t], true)));
+            else CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&st.cfg_per_sm[t], sw_fast_kernel<false>, SW_BLOCK, smem_of(caps[t], false)));
+            if (st.cfg_per_sm[t] < 1) { bwt_set_error("sw_fast_kernel does not fit an SM with %zu B of shared memory", smem_of(caps[t], t < 2)); return BWT_ERR_CUDA; }
+        }
+        st.cfg_max_lq = max_lq;
+    }
+    const int sms = st.cfg_sms;
+    unsigned grid[3];
     size_t need_dirs = 0;
     for (int t = 0; t < 3; t++) {
-        int per_sm = 0;
-        if (t < 2) CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sw_fast_kernel<true>, SW_BLOCK, smem_of(caps[t], true)));
-        else CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sw_fast_kernel<false>, SW_BLOCK, smem_of(caps[t], false)));
-        if (per_sm < 1) { bwt_set_error("sw_fast_kernel does not fit an SM with %zu B of shared memory", smem_of(caps[t], t < 2)); return BWT_ERR_CUDA; }
         uint64_t units = ((uint64_t)n + 1) / 2;
-        grid[t] = (unsigned)std::min<uint64_t>((units + SW_BLOCK - 1) / SW_BLOCK, (uint64_t)sms * per_sm);
+        grid[t] = (unsigned)std::min<uint64_t>((units + SW_BLOCK - 1) / SW_BLOCK, (uint64_t)sms * st.cfg_per_sm[t]);
         if (t == 2) grid[t] = std::min<unsigned>(grid[t], (unsigned)sms);       // the overflow list is short: one wave
         need_dirs = std::max(need_dirs, (size_t)grid[t] * SW_BLOCK * max_strips * caps[t]);
     }

@@ -48,6 +48,7 @@ struct SwStage {
     int2 *d_gen_dims = nullptr;
     uint32_t launches = 0;
     unsigned long long sw_calls = 0, cells = 0, n_general = 0, shortcut_calls = 0, shortcut_cells = 0;
+    int cfg_max_lq = -1, cfg_sms = 0, cfg_per_sm[3] = {0, 0, 0};   // launch configuration of the last run (host queries are not free)
     cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr;   // around sw_fast_kernel
     float ms_fast_kernel = 0;
 };

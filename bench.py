@@ -316,17 +316,21 @@ def main():
         sw_gbs = sw_bytes / (agg["ms_sw"] * 1e-3) / 1e9 if agg["ms_sw"] > 0 else 0.0
         gcups = dp_cells / (agg["ms_sw"] * 1e-3) / 1e9 if agg["ms_sw"] else 0.0
         dominant = "sga_kernel" if agg["ms_sga"] >= agg["ms_sw"] else "sw_fast_kernel"
-        share = {"sga_kernel": round(agg["ms_sga"] / t_ev, 3), "sw_fast_kernel": round(agg["ms_sw"] / t_ev, 3)}
+        share = {"sga_kernel": round(agg["ms_sga"] / t_ev, 3), "sw_fast_kernel": round(agg["ms_sw"] / t_ev, 3),
+                 "sw_classify_kernel (SW stage minus the DP kernels)": round((agg["ms_swstage"] - agg["ms_sw"]) / t_ev, 3)}
         tr = load_traffic(dominant)
         dom_bytes, dom_gbs, dom_ms = (sga_bytes, sga_gbs, agg["ms_sga"]) if dominant == "sga_kernel" else (sw_bytes, sw_gbs, agg["ms_sw"])
         roof = {"kernel": dominant, "bound": "hbm", "achieved": round(dom_gbs, 1), "peak": hbm_peak, "unit": "GB/s",
                 "frac": round(dom_gbs / hbm_peak, 4), "traffic": tr["dram_bytes_per_launch"] if tr else None,
                 "traffic_source": tr.get("source") if tr else None, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": dom_bytes / K, "ms_per_launch": dom_ms / K, "share_of_step": share,
+                "dram_gbs_from_traffic": round(tr["dram_bytes_per_launch"] / (dom_ms / K * 1e-3) / 1e9, 1) if tr and dom_ms else None,
                 "note": ("the dominant kernel is the integer DP (sw_fast_kernel): it is bound by ALU-pipe issue, not by HBM; "
                          "see roofline_alu for its real ceiling and roofline_sga for the memory-bound kernel") if dominant == "sw_fast_kernel"
-                else ("the dominant kernel is sga_kernel: dependent random 8-byte / 32-byte gathers over a 25 GB index (latency and "
-                      "DRAM-atom bound); frac_of_random_gather in roofline_sga is its fraction of the measured random-sector ceiling")}
+                else ("the dominant kernel is sga_kernel: random 8-byte table entries and ~14-byte suffix-array runs over a 25 GB index. "
+                      "`achieved` counts ALGORITHMIC bytes; `traffic` (ncu) is what DRAM really moves for them in 64-byte atoms -- "
+                      "traffic / ms_per_launch is the DRAM rate the kernel runs at; frac_of_random_gather in roofline_sga compares the "
+                      "algorithmic rate with the random 32-byte-sector gather ceiling measured in this run")}
         dpx_peak = extra.get("dpx_gops")
         roof_alu = {"kernel": "sw_fast_kernel", "bound": "alu-pipe issue (DPX VIADDMNMX.S16x2 / packed 16-bit)", "gcups": round(gcups, 1),
                     "achieved": round(gcups * 4.25, 1), "peak": dpx_peak, "unit": "Gop/s (ALU-pipe thread instructions)",

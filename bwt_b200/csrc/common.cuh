@@ -60,8 +60,6 @@ struct DevIndex {
     const uint32_t *sa;        // full suffix array, SA[e-1] for 1-based row e (fmi.erl:89-100 reads it un-sampled)
     const uint2 *kmer;         // 4^8 entries, depth-8 interval table (format: KmerEntry below)
     const uint2 *kmer_deep;    // 4^deep_k entries, or null
-    const uint2 *kmer_mid;     // the tables of depth 9..deep_k-1 back to back (kmer_mid_offset), or null: a subsequence
-                               // with fewer than deep_k plain characters at its end still costs ONE lookup
     const uint2 *kmer_tail;    // ONE table of depth tail_k (8 < tail_k < deep_k), or null: set per launch for the length of
     int tail_k;                // the short subsequence at the front of the batch's reads (8 + Lq mod 8 characters)
     int deep_k;                // 9..15, or 0 when there is no deep table
@@ -87,9 +85,6 @@ __host__ __device__ __forceinline__ uint2 kmer_pack(uint32_t sp, uint32_t ep, in
     return make_uint2(sp, w | ((uint32_t)n << 28));
 }
 
-// first entry of the depth-d table inside kmer_mid: 4^9 + ... + 4^(d-1)
-__host__ __device__ __forceinline__ uint64_t kmer_mid_offset(int d) { return ((1ull << (2 * d)) - (1ull << 18)) / 3ull; }
-
 struct bwt_index {
     DevIndex dv{};
     int device = 0;
@@ -98,10 +93,9 @@ struct bwt_index {
     uint32_t pointers[4] = {0, 0, 0, 0};
     int64_t shift = 0;
     uint64_t device_bytes = 0;
-    uint64_t mid_bytes = 0;    // kmer_mid part of device_bytes
     std::mutex *tail_mu = nullptr;                 // guards the lazily built single-depth tables below
     void *d_tail[BWT_MAX_LEN] = {};                // d_tail[k]: table of depth k, built on first use (index_tail_table)
-    void *d_occ = nullptr, *d_sa = nullptr, *d_kmer = nullptr, *d_ref = nullptr, *d_kmer_deep = nullptr, *d_kmer_mid = nullptr;
+    void *d_occ = nullptr, *d_sa = nullptr, *d_kmer = nullptr, *d_ref = nullptr, *d_kmer_deep = nullptr;
 };
 
 // ASCII -> index code (A0 C1 G2 T3), -1 otherwise

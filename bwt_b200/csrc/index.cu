@@ -236,45 +236,25 @@ extern "C" int bwt_set_kmer_depth(bwt_index *h, int k) {
         cudaFree(h->d_kmer_deep);
         h->d_kmer_deep = nullptr;
     }
-    h->device_bytes -= h->mid_bytes;
-    h->mid_bytes = 0;
-    if (h->d_kmer_mid) { cudaFree(h->d_kmer_mid); h->d_kmer_mid = nullptr; }
     h->dv.kmer_deep = nullptr;
-    h->dv.kmer_mid = nullptr;
     h->dv.deep_k = 0;
     if (k <= 8) return BWT_OK;                          // the depth-8 table alone
     uint2 *tab = nullptr;
     const uint64_t entries = 1ull << (2 * k);
-    // BWT_KMER_MID=2 (or 1: separate allocation) also keeps the levels in between (a third of the deep table in all), so
-    // that a subsequence shorter than k -- the 12 characters left at the front of a 100 bp read -- needs no Occ walk
-    // either.  OFF by default: on the 3.1 Gbp bench it removes the last 4 Occ steps per read, yet the step gets 10 %
-    // SLOWER, every kernel including the ones that never touch the tables (A/B in profiles/r1d_summary.md: the extra
-    // 2.9 GB moves where the later buffers land in HBM, and an unused dummy allocation has the same effect).
-    const char *env_mid = getenv("BWT_KMER_MID");
-    const int mid_mode = env_mid ? atoi(env_mid) : 0;
-    const uint64_t mid_entries = mid_mode ? kmer_mid_offset(k) : 0;
-    if (cudaMalloc(&tab, (entries + (mid_mode == 2 ? mid_entries : 0)) * sizeof(uint2)) != cudaSuccess) {
+    if (cudaMalloc(&tab, entries * sizeof(uint2)) != cudaSuccess) {
         cudaGetLastError();
         bwt_set_error("k-mer table of depth %d (%llu MB) does not fit", k, (unsigned long long)(entries * 8 >> 20));
         return BWT_ERR_NOMEM;
     }
-    uint2 *mid = nullptr;
-    if (mid_mode == 2 && mid_entries) mid = tab + entries;
-    else if (mid_mode == 1 && mid_entries && cudaMalloc(&mid, mid_entries * sizeof(uint2)) != cudaSuccess) { cudaGetLastError(); mid = nullptr; }
     CU_TRY(cudaMemcpy(tab, h->d_kmer, 65536 * sizeof(uint2), cudaMemcpyDeviceToDevice));
     for (int d = 8; d < k; d++) {
-        if (d > 8 && mid) CU_TRY(cudaMemcpy(mid + kmer_mid_offset(d), tab, (sizeof(uint2)) << (2 * d), cudaMemcpyDeviceToDevice));
         kmer_expand_kernel<<<(unsigned)div_up_u64(1ull << (2 * d), 256), 256>>>(h->dv, tab, d);
         CU_TRY(cudaGetLastError());
     }
     cudaError_t e = cudaDeviceSynchronize();
-    if (e != cudaSuccess) { cudaFree(tab); if (mid_mode == 1) cudaFree(mid); bwt_set_error("k-mer table build: %s", cudaGetErrorString(e)); return BWT_ERR_CUDA; }
+    if (e != cudaSuccess) { cudaFree(tab); bwt_set_error("k-mer table build: %s", cudaGetErrorString(e)); return BWT_ERR_CUDA; }
     h->d_kmer_deep = tab;
-    h->d_kmer_mid = mid_mode == 1 ? mid : nullptr;      // owned separately only in mode 1
-    h->mid_bytes = mid ? mid_entries * sizeof(uint2) : 0;
     h->dv.kmer_deep = tab;
-    h->dv.kmer_mid = mid;
-    if (mid) h->device_bytes += mid_entries * sizeof(uint2);
     h->dv.deep_k = k;
     h->device_bytes += entries * 8;
     return BWT_OK;
@@ -371,7 +351,7 @@ extern "C" int bwt_close(bwt_index *h) {
     cudaSetDevice(h->device);
     free_tail_tables(h);
     delete h->tail_mu;
-    cudaFree(h->d_occ); cudaFree(h->d_sa); cudaFree(h->d_kmer); cudaFree(h->d_kmer_deep); cudaFree(h->d_kmer_mid); cudaFree(h->d_ref);
+    cudaFree(h->d_occ); cudaFree(h->d_sa); cudaFree(h->d_kmer); cudaFree(h->d_kmer_deep); cudaFree(h->d_ref);
     delete h;
     return BWT_OK;
 }

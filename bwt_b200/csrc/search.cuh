@@ -97,7 +97,6 @@ __device__ __forceinline__ SearchRes search_core(const DevIndex &ix, const uint8
         if (ix.deep_k > 0) {
             if (good >= ix.deep_k) { depth = ix.deep_k; tab = ix.kmer_deep; }
             else if (ix.tail_k > 0 && good >= ix.tail_k) { depth = ix.tail_k; tab = ix.kmer_tail; }
-            else if (good > BWT_MIN_LEN && ix.kmer_mid) { depth = good; tab = ix.kmer_mid + kmer_mid_offset(good); }
         }
         const uint2 e = __ldg(tab + (idx & (uint32_t)((1ull << (2 * depth)) - 1ull)));
         int ne = (int)(e.y >> 28);

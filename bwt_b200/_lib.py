@@ -109,7 +109,7 @@ def lib():
             fn = getattr(L, name)          # AttributeError here = the .so does not export a declared symbol
             fn.restype = res
             fn.argtypes = args
-        if L.bwt_abi_version() != 1:
+        if L.bwt_abi_version() != 2:
             raise ImportError("bwt_b200: ABI version mismatch")
         _lib = L
     return _lib

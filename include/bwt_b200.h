@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define BWT_B200_ABI_VERSION 1
+#define BWT_B200_ABI_VERSION 2   /* 2: bwt_stats grew (sw_shortcut, sw_shortcut_cells), bwt_fs_find_seeds_batch */
 
 typedef enum bwt_status {
     BWT_OK = 0,
@@ -142,7 +142,10 @@ int bwt_info(const bwt_index *h, bwt_index_info *info);
 /* Depth of the k-mer interval table: entry = state of bwa:find_seeds/6 (bwa.erl:12-45) after the last k characters
  * of a subsequence, so those k-1 LF steps cost one lookup.  0 or 8 = the 4^8 table only; 9..15 adds a 4^k-entry
  * table (8 bytes each; k = 15 = MAX_LEN makes a whole search one lookup, 8.6 GB).  Chosen automatically at open
- * (largest k with 4^k <= 4 * rows); results never depend on it.  Not thread-safe against running batches. */
+ * (largest k with 4^k <= 4 * rows); results never depend on it.  Not thread-safe against running batches.
+ * Besides this table the handle lazily builds (under its own lock, on first use) one table of exactly the depth of the
+ * short subsequence at the front of a batch's reads (8 + Lq mod 8 characters; 134 MB at depth 12), so that those
+ * searches need no Occ walk either; BWT_KMER_TAIL=0 in the environment disables it. */
 int bwt_set_kmer_depth(bwt_index *h, int k);
 int bwt_close(bwt_index *h);
 

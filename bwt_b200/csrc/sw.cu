@@ -88,6 +88,7 @@ constexpr int SC_MAXQ = 256;                        // longest query the shortcu
 constexpr int SC_QW = SC_MAXQ / 16;                 // 2-bit packed query words (16 bases each)
 constexpr int SC_RW = (SC_MAXQ + SW_SHORTCUT_MAX_D + 15) / 16 + 2;
 static_assert(SW_SHORTCUT_MAX_D + 2 * SC_K + 1 <= SC_ND, "diagonal slots");
+static_assert(SC_RING == 5, "the level loop rotates five ring slots");
 
 // Per pair: the wavefronts (furthest query index, -1 = unreachable; states M, I, D) and both strings packed to 2 bits
 // per base, so that "extend along diagonal o" compares 16 bases per XOR instead of walking bytes.
@@ -143,13 +144,11 @@ __device__ __forceinline__ int sw_shortcut(const uint8_t *q, int lq, const uint8
     const int nd = dd + 2 * kk + 1;                                  // diagonal slot d <-> o = d - kk
     bool open = elig;
     int pstar = -1, omin = 0x7FFF;
-    int cur = 0;                                                     // ring slot of wavefront s
+    int cur = 0, p1 = 4, p2 = 3, p3 = 2, p4 = 1;                      // ring slots of wavefronts s, s-1, .., s-4
     for (int s = 0; s <= SC_PMAX; s++) {
         const bool act = open && s <= pmax;
         unsigned best = 0x7FFFu;
         if (act) {
-            const int p1 = cur == 0 ? SC_RING - 1 : cur - 1, p2 = p1 == 0 ? SC_RING - 1 : p1 - 1, p3 = p2 == 0 ? SC_RING - 1 : p2 - 1,
-                      p4 = p3 == 0 ? SC_RING - 1 : p3 - 1;
             for (int d = t; d < nd; d += SC_LANES) {
                 const int o = d - kk;
                 int dv = -1, iv = -1, mv = -1;
@@ -182,17 +181,21 @@ __device__ __forceinline__ int sw_shortcut(const uint8_t *q, int lq, const uint8
         best = grp_min(best);
         if (act && best != 0x7FFFu) { open = false; pstar = s; omin = (int)best - kk; }
         if (__all_sync(FULL, !open || s >= pmax)) break;
-        cur = cur + 1 == SC_RING ? 0 : cur + 1;
+        { const int free_slot = p4; p4 = p3; p3 = p2; p2 = p1; p1 = cur; cur = free_slot; }
     }
-    // the leftmost optimal end must be a gapless diagonal of the window: count its mismatches
-    if (!(pstar >= 0 && omin >= 0 && omin <= dd)) return 0;
-    int mism = 0;
-    for (int w = 0; w < (lq + 15) >> 4; w++) {
-        uint32_t f = sc_diff(wf, omin, w);
-        if (lq - 16 * w < 16) f &= (1u << (2 * (lq - 16 * w))) - 1u;   // bases past the query's end are padding
-        mism += __popc(f);
-    }
-    return 3 * mism == pstar ? 2 * lq - pstar : 0;
+    // the leftmost optimal end must be a gapless diagonal of the window: count its mismatches (lane t: words t, t+8, ..)
+    const bool check = pstar >= 0 && omin >= 0 && omin <= dd;
+    unsigned mism = 0;
+    if (check)
+        for (int w = t; w < (lq + 15) >> 4; w += SC_LANES) {
+            uint32_t f = sc_diff(wf, omin, w);
+            if (lq - 16 * w < 16) f &= (1u << (2 * (lq - 16 * w))) - 1u;   // bases past the query's end are padding
+            mism += (unsigned)__popc(f);
+        }
+#pragma unroll
+    for (int o = 1; o < SC_LANES; o <<= 1) mism += __shfl_xor_sync(FULL, mism, o);
+    if (!check) return 0;
+    return 3 * (int)mism == pstar ? 2 * lq - pstar : 0;
 }
 
 // ---------------------------------------------------------------------------------------------------

@@ -269,16 +269,17 @@ def test_sw_shortcut_adversarial(sw_mode):
     deletions between matching flanks), slack 0..20, zero to two substitutions or an indel."""
     rng = np.random.default_rng(29)
     pairs = []
-    for it in range(30000):
+    for it in range(38000):
         alpha = [b"ACGT", b"AC", b"ACGT", b"AAC", b"ACGT"][it % 5]
-        lq, dd = int(rng.integers(4, 130)), int(rng.integers(0, 21))
+        # the last 8000: 130..260 bp (penalty budgets 12 and 15, up to nine diagonals beside the window's, the 256 bp limit)
+        lq, dd = (int(rng.integers(4, 130)) if it < 30000 else int(rng.integers(130, 261))), int(rng.integers(0, 21))
         pick = lambda n: bytes(alpha[int(x)] for x in rng.integers(0, len(alpha), n))   # noqa: E731
         mode = rng.random()
         if mode < 0.55:
             base = pick(lq + dd + 4)
             s0 = int(rng.integers(0, dd + 3))
             q = bytearray(base[s0:s0 + lq]) + bytearray(pick(max(0, lq - len(base[s0:s0 + lq]))))
-            for _ in range(int(rng.choice([0, 0, 1, 1, 1, 2]))):
+            for _ in range(int(rng.choice([0, 0, 1, 1, 1, 2, 3, 4, 5, 6]))):
                 u = rng.random()
                 if u < 0.7:
                     q[int(rng.integers(0, lq))] = alpha[int(rng.integers(0, len(alpha)))]
@@ -290,18 +291,18 @@ def test_sw_shortcut_adversarial(sw_mode):
             pairs.append((bytes(q[:lq]), base[:lq + dd]))
         elif mode < 0.85:
             unit = pick(int(rng.integers(1, 5)))
-            base = (unit * 200)[:lq + dd]
+            base = (unit * 400)[:lq + dd]
             r = bytearray(base)
             for _ in range(int(rng.integers(0, 3))):
                 r[int(rng.integers(0, len(r)))] = b"ACGT"[int(rng.integers(0, 4))]
             s0 = int(rng.integers(0, dd + 1))
             q = bytearray(base[s0:s0 + lq])
-            for _ in range(int(rng.integers(0, 3))):
+            for _ in range(int(rng.integers(0, 6))):
                 q[int(rng.integers(0, lq))] = b"ACGT"[int(rng.integers(0, 4))]
             pairs.append((bytes(q), bytes(r)))
         else:
             pairs.append((pick(lq), pick(lq + dd)))
-    assert _check_sw(pairs) > 15000
+    assert _check_sw(pairs) > 18000
 
 
 def test_shortcut_is_taken_and_counted(gl_index, gl_ref, sw_mode):

@@ -201,12 +201,19 @@ struct bwt_batch {
     cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     bwt_stats stats{};
     std::mutex *stage_token = nullptr;    // set by the pipelined aligner: one chunk at a time inside a stage
+    cudaStream_t dl_stream = nullptr;     // the aligner's D2H copies: the next chunk's upload does not wait for them
+    cudaEvent_t ev_run_done = nullptr, ev_dl0 = nullptr, ev_dl1 = nullptr;
+    bool dl_pending = false;
 };
 
 static int batch_alloc(bwt_batch *b) {
     int64_t nr = b->max_reads;
     CU_TRY(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
+    CU_TRY(cudaStreamCreateWithFlags(&b->dl_stream, cudaStreamNonBlocking));
     for (auto &e : b->ev) CU_TRY(cudaEventCreate(&e));
+    CU_TRY(cudaEventCreate(&b->ev_run_done));
+    CU_TRY(cudaEventCreate(&b->ev_dl0));
+    CU_TRY(cudaEventCreate(&b->ev_dl1));
     CU_TRY(cudaMalloc(&b->d_reads, (size_t)b->max_bytes + 16));
     CU_TRY(cudaMalloc(&b->d_offs, (size_t)(nr + 1) * sizeof(int64_t)));
     CU_TRY(cudaMalloc(&b->d_read_status, (size_t)nr * sizeof(int32_t)));
@@ -259,6 +266,10 @@ extern "C" int bwt_batch_destroy(bwt_batch *b) {
     if (b->h_stage) cudaFreeHost(b->h_stage);
     sw_stage_free(b->sw);
     for (auto &e : b->ev) if (e) cudaEventDestroy(e);
+    if (b->ev_run_done) cudaEventDestroy(b->ev_run_done);
+    if (b->ev_dl0) cudaEventDestroy(b->ev_dl0);
+    if (b->ev_dl1) cudaEventDestroy(b->ev_dl1);
+    if (b->dl_stream) { cudaStreamSynchronize(b->dl_stream); cudaStreamDestroy(b->dl_stream); }
     if (b->stream) cudaStreamDestroy(b->stream);
     delete b;
     return BWT_OK;
@@ -615,9 +626,13 @@ extern "C" int bwt_aligner_run(bwt_aligner *a, const uint8_t *reads, const int64
             if (!skip) {
                 st = bwt_batch_upload(b, reads, offsets + lo, m);
                 t1 = now_ms();
+                if (st == BWT_OK && b->dl_pending) {     // the previous chunk's results must have left before this run overwrites them
+                    cudaError_t e = cudaStreamSynchronize(b->dl_stream);
+                    b->dl_pending = false;
+                    if (e != cudaSuccess) { bwt_set_error("aligner download: %s", cudaGetErrorString(e)); st = BWT_ERR_CUDA; }
+                    else { float ms = 0; cudaEventElapsedTime(&ms, b->ev_dl0, b->ev_dl1); wstats[(size_t)w].ms_d2h += ms; }
+                }
                 if (st == BWT_OK) {
-                    // one chunk computes at a time: the others spend that time in their copies, instead of all chunks
-                    // copying together and then time-slicing the SMs together
                     // BWT_COMPUTE_TOKEN: 2 (default) = one chunk at a time inside a whole run; 1 = inside a stage; 0 = free
                     // (measured on 10 M x 100 bp, depth 2 / 3: 289 / 283 M reads/s, 290 / 247, 256 / -)
                     std::unique_lock<std::mutex> run_token(sh.compute_mu, std::defer_lock);
@@ -650,16 +665,19 @@ extern "C" int bwt_aligner_run(bwt_aligner *a, const uint8_t *reads, const int64
                 // entry m of this chunk equals entry 0 of the next one: only the last chunk writes it
                 st = cudaGetLastError() == cudaSuccess ? BWT_OK : BWT_ERR_CUDA;
                 if (st == BWT_OK) {
-                    cudaStream_t s = b->stream;
-                    cudaEventRecord(b->ev[4], s);
+                    // D2H on the batch's download stream, behind the rebase kernel; not waited for here: the worker goes on
+                    // to upload its next chunk (other buffers) and collects the copy before its next run
+                    cudaEventRecord(b->ev_run_done, b->stream);
+                    cudaStream_t s = b->dl_stream;
+                    cudaStreamWaitEvent(s, b->ev_run_done, 0);
+                    cudaEventRecord(b->ev_dl0, s);
                     if (read_status) cudaMemcpyAsync(read_status + lo, b->d_read_status, (size_t)m * sizeof(int32_t), cudaMemcpyDeviceToHost, s);
                     cudaMemcpyAsync(hit_offsets + lo, b->d_hit_off64, (size_t)(m + (c + 1 == nchunks ? 1 : 0)) * sizeof(int64_t), cudaMemcpyDeviceToHost, s);
                     if (nh) cudaMemcpyAsync(hits + hb, b->d_hits, (size_t)nh * sizeof(bwt_hit), cudaMemcpyDeviceToHost, s);
                     if (nc) cudaMemcpyAsync(cigars + cb, b->d_cigars, (size_t)nc, cudaMemcpyDeviceToHost, s);
-                    cudaEventRecord(b->ev[5], s);
-                    cudaError_t e = cudaStreamSynchronize(s);
-                    if (e != cudaSuccess) { bwt_set_error("aligner download: %s", cudaGetErrorString(e)); st = BWT_ERR_CUDA; }
-                    else cudaEventElapsedTime(&b->stats.ms_d2h, b->ev[4], b->ev[5]);
+                    cudaEventRecord(b->ev_dl1, s);
+                    if (cudaGetLastError() != cudaSuccess) { bwt_set_error("aligner download: enqueue failed"); st = BWT_ERR_CUDA; }
+                    else b->dl_pending = true;
                 }
                 if (st != BWT_OK) { std::lock_guard<std::mutex> g(sh.mu); if (sh.status == BWT_OK) { sh.status = st; sh.error = bwt_last_error(); } }
             }
@@ -669,9 +687,19 @@ extern "C" int bwt_aligner_run(bwt_aligner *a, const uint8_t *reads, const int64
                         t0, t1, t2, b->stats.ms_seed, b->stats.ms_sw, b->stats.ms_emit, t3, now_ms());
         }
     };
+    auto worker_all = [&](int w) {
+        worker(w);
+        bwt_batch *b = a->batches[(size_t)w];
+        if (b->dl_pending) {
+            cudaError_t e = cudaStreamSynchronize(b->dl_stream);
+            b->dl_pending = false;
+            if (e != cudaSuccess) { std::lock_guard<std::mutex> g(sh.mu); if (sh.status == BWT_OK) { sh.status = BWT_ERR_CUDA; sh.error = cudaGetErrorString(e); } }
+            else { float ms = 0; cudaEventElapsedTime(&ms, b->ev_dl0, b->ev_dl1); wstats[(size_t)w].ms_d2h += ms; }
+        }
+    };
     std::vector<std::thread> th;
-    for (int w = 1; w < depth; w++) th.emplace_back(worker, w);
-    worker(0);
+    for (int w = 1; w < depth; w++) th.emplace_back(worker_all, w);
+    worker_all(0);
     for (auto &t : th) t.join();
     for (int w = 0; w < depth; w++) stats_add(a->stats, wstats[(size_t)w]);
     *n_hits = sh.hit_base; *cigar_bytes = sh.cig_base;

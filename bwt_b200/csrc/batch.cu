@@ -379,6 +379,15 @@ static int run_seed_stage(bwt_batch *b) {
         // a sub-list ran out of room: n_clusters is a lower bound of what is needed (refused reads not counted in full);
         // the regions are equal shares, so ask for twice the total
         size_t want = (size_t)std::max<uint64_t>(b->h_ctr->n_clusters, b->cl_cap) * 2 + 4096;
+        {   // and every region must hold the fullest sub-list (one read with very many clusters fills a single region)
+            std::vector<uint32_t> sub((size_t)SGA_SUBLISTS * 32);
+            CU_TRY(cudaMemcpy(sub.data(), reinterpret_cast<const uint8_t *>(b->d_ctr) + offsetof(SeedCounters, sub_n),
+                              sub.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+            uint64_t fullest = 0;
+            for (int r = 0; r < SGA_SUBLISTS; r++) fullest = std::max<uint64_t>(fullest, sub[(size_t)32 * r]);
+            want = std::max<size_t>(want, (size_t)(fullest + fullest / 4 + 64) * SGA_SUBLISTS);
+        }
+        if (want * sizeof(Cluster) > (48ull << 30)) { bwt_set_error("cluster list beyond 48 GiB: use smaller batches"); return BWT_ERR_NOMEM; }
         BWT_TRY(dev_grow(b->d_clusters, b->cl_cap, want, false));
     }
     bwt_set_error("cluster list kept overflowing");

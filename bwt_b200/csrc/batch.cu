@@ -721,17 +721,53 @@ extern "C" int bwt_aligner_run(bwt_aligner *a, const uint8_t *reads, const int64
 }
 
 // worker_bwt.erl:73-97 for one list of reads, host buffers in and out: a short-lived aligner
+void aligner_cache_drop(bwt_index *h) {
+    if (!h || !h->cached_aligner) return;
+    bwt_aligner_destroy(static_cast<bwt_aligner *>(h->cached_aligner));
+    h->cached_aligner = nullptr;
+    h->cached_busy = false;
+}
+
+static int64_t round_up_pow2(int64_t v, int64_t lo) {
+    int64_t p = lo;
+    while (p < v) p <<= 1;
+    return p;
+}
+
 extern "C" int bwt_align_batch(bwt_index *h, const uint8_t *reads, const int64_t *offsets, int64_t n,
                                int32_t *read_status, int64_t *hit_offsets, bwt_hit *hits, int64_t hits_cap,
                                int64_t *n_hits, char *cigars, int64_t cigar_cap, int64_t *cigar_bytes) {
     if (!h || !offsets || n < 0 || !hit_offsets || !n_hits || !cigar_bytes) { bwt_set_error("bwt_align_batch: null argument"); return BWT_ERR_ARG; }
     const int64_t total_bytes = offsets[n] - offsets[0];
-    const int64_t cr = std::max<int64_t>(1, std::min(n, CHUNK_READS)), cb = std::max<int64_t>(16, std::min(total_bytes, CHUNK_BYTES));
+    // sizes rounded up to powers of two: the aligner kept with the index then fits the next call as well
+    const int64_t cr = std::min(round_up_pow2(std::max<int64_t>(1, n), 1024), CHUNK_READS);
+    const int64_t cb = std::min(round_up_pow2(std::max<int64_t>(16, total_bytes), 1 << 17), CHUNK_BYTES);
     const int depth = n > 2 * CHUNK_READS ? 3 : (n > CHUNK_READS ? 2 : 1);
     bwt_aligner *a = nullptr;
-    BWT_TRY(bwt_aligner_create(h, cr, cb, depth, &a));
+    bool temporary = false;
+    if (h->tail_mu) {
+        std::lock_guard<std::mutex> g(*h->tail_mu);
+        if (h->cached_aligner && !h->cached_busy && h->cached_reads >= cr && h->cached_bytes >= cb && h->cached_depth >= depth) {
+            a = static_cast<bwt_aligner *>(h->cached_aligner);
+            h->cached_busy = true;
+        }
+    }
+    if (!a) {
+        BWT_TRY(bwt_aligner_create(h, cr, cb, depth, &a));
+        temporary = true;
+        if (h->tail_mu) {
+            std::lock_guard<std::mutex> g(*h->tail_mu);
+            if (!h->cached_busy) {                          // keep the new one (it is at least as large in the dimension that missed)
+                if (h->cached_aligner) bwt_aligner_destroy(static_cast<bwt_aligner *>(h->cached_aligner));
+                h->cached_aligner = a; h->cached_reads = cr; h->cached_bytes = cb; h->cached_depth = depth;
+                h->cached_busy = true;
+                temporary = false;
+            }
+        }
+    }
     int st = bwt_aligner_run(a, reads, offsets, n, read_status, hit_offsets, hits, hits_cap, n_hits, cigars, cigar_cap, cigar_bytes);
-    bwt_aligner_destroy(a);
+    if (temporary) bwt_aligner_destroy(a);
+    else { std::lock_guard<std::mutex> g(*h->tail_mu); h->cached_busy = false; }
     return st;
 }
 

@@ -93,7 +93,13 @@ struct bwt_index {
     uint32_t pointers[4] = {0, 0, 0, 0};
     int64_t shift = 0;
     uint64_t device_bytes = 0;
-    std::mutex *tail_mu = nullptr;                 // guards the lazily built single-depth tables below
+    // one pipelined aligner kept for bwt_align_batch (the NIF calls it per 200-read list: creating streams, events and
+    // two dozen device buffers per call would cost far more than the alignment); batch.cu owns it
+    void *cached_aligner = nullptr;
+    bool cached_busy = false;
+    int64_t cached_reads = 0, cached_bytes = 0;
+    int cached_depth = 0;
+    std::mutex *tail_mu = nullptr;                 // guards the lazily built single-depth tables below and the aligner cache
     void *d_tail[BWT_MAX_LEN] = {};                // d_tail[k]: table of depth k, built on first use (index_tail_table)
     void *d_occ = nullptr, *d_sa = nullptr, *d_kmer = nullptr, *d_ref = nullptr, *d_kmer_deep = nullptr;
 };
@@ -147,6 +153,8 @@ int index_finish_from_device(bwt_index *h, const uint8_t *d_L, uint64_t n, uint3
 int index_select_device(int device);
 // Depth-k interval table (8 < k < deep_k) of this index, built on first use and kept; null when it cannot be had.
 const uint2 *index_tail_table(bwt_index *h, int k);
+// Destroys the aligner bwt_align_batch keeps with the index (batch.cu); called by bwt_close.
+void aligner_cache_drop(bwt_index *h);
 int index_upload_ref_device(const uint8_t *d_ref, uint64_t len, uint8_t **d_out);
 
 // ---- builder (build.cu) -------------------------------------------------------------------------

@@ -349,6 +349,7 @@ extern "C" int bwt_open(const char *fm_path, const char *ref_path, int device, b
 extern "C" int bwt_close(bwt_index *h) {
     if (!h) return BWT_OK;
     cudaSetDevice(h->device);
+    aligner_cache_drop(h);
     free_tail_tables(h);
     delete h->tail_mu;
     cudaFree(h->d_occ); cudaFree(h->d_sa); cudaFree(h->d_kmer); cudaFree(h->d_kmer_deep); cudaFree(h->d_ref);

@@ -176,7 +176,10 @@ int bwt_sw_batch(int device, const uint8_t *q, const int64_t *q_offsets, const u
 /* The worker's inner loop for one list of reads (worker_bwt.erl:73-108), minus the top-1 pick that
  * stays in Erlang (worker_bwt.erl:99-106): for read r, hits[hit_offsets[r]..hit_offsets[r+1]) are ALL
  * sga clusters in ascending position; those with status BWT_HIT_MATCH are exactly the reference's Cigars
- * list, in its order.  BWT_ERR_NOSPACE (with *n_hits / *cigar_bytes = needed) if a capacity is too small. */
+ * list, in its order.  BWT_ERR_NOSPACE (with *n_hits / *cigar_bytes = needed) if a capacity is too small.
+ * The handle keeps one pipelined aligner (streams, events, device buffers sized to the largest call so far) between
+ * calls, so that worker-sized calls (200-read lists) do not pay its construction every time; a concurrent second call
+ * builds a temporary one.  bwt_close releases it. */
 int bwt_align_batch(bwt_index *h, const uint8_t *reads, const int64_t *offsets, int64_t n,
                     int32_t *read_status, int64_t *hit_offsets, bwt_hit *hits, int64_t hits_cap, int64_t *n_hits,
                     char *cigars, int64_t cigar_cap, int64_t *cigar_bytes);

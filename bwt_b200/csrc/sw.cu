@@ -800,10 +800,11 @@ int sw_stage_run(SwStage &st, const uint8_t *d_qbase, const uint8_t *d_rbase, ui
     if (n == 0) return BWT_OK;
     if (n > st.cap) { bwt_set_error("sw_stage_run: %u pairs exceed the reserved %u", n, st.cap); return BWT_ERR_ARG; }
     // two shared-memory tiers of the fast kernel: "narrow" holds windows up to Lq + 15 columns (almost every
-    // candidate: D is the summed gap of the voting chain), "wide" up to Lq + 64; anything wider takes the general path
+    // candidate: D is the summed gap of the voting chain), "wide" up to Lq + 160; anything wider takes the general path
+    // (one thread per pair: a single such pair costs ~2 ms, more than a whole worker-sized batch)
     const int cap_limit = 384;                           // fast-kernel tier limit: the absolute-row variant needs 4.5 B x columns x 128 threads <= 227 KB
     int cap_narrow = std::min(cap_limit, std::max(96, ((max_lq + 1 + 15) + 15) & ~15));   // >= 96: the traceback's band (64 half-words) + runs
-    int cap_wide = std::min(cap_limit, std::max(96, ((max_lq + 1 + 64) + 15) & ~15));
+    int cap_wide = std::min(cap_limit, std::max(96, ((max_lq + 1 + 160) + 15) & ~15));    // D up to 160: the largest slack seen on GL000193.1 is 142
     int max_strips = (std::min(max_lq, SW_FAST_MAX_LQ) + SW_R - 1) / SW_R;
     if (max_strips < 1) max_strips = 1;
     auto smem_of = [](int cap, bool delta) { return (size_t)SW_BLOCK * ((size_t)cap * (delta ? 2 : 4) + (size_t)(cap / 16) * 8); };

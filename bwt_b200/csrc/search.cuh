@@ -56,12 +56,10 @@ __device__ __forceinline__ bool lf_step(const DevIndex &ix, uint32_t &sp, uint32
     OccHit hi = occ_at(ix, ep, c);
     uint32_t b = hi.occ - hi.is_c;               // occ(c, Ep-1)
     if (b <= a) return false;
-    // Indexed read of the kernel parameter: the compiler keeps a 104-byte copy of `ix` in local memory for it.  Selecting
-    // among ix.P[0..3] instead removes that copy -- and makes sga_kernel AND the streaming kernels after it ~25 % slower
-    // in the bench pipeline (sga 17.3 -> 21.7 ms, emit 0.79 -> 0.99 ms, five A/B runs; under ncu, kernel by kernel, the
-    // two builds time the same).  Not understood; kept as measured.  DESIGN.md section 9, profiles/r1d_summary.md.
-    sp = ix.P[c] - 1 + a;
-    ep = ix.P[c] - 2 + hi.occ;
+    // select chain, not ix.P[c]: an indexed read makes the compiler keep a 104-byte copy of the kernel parameter in local memory
+    const uint32_t pc = c == 0 ? ix.P[0] : c == 1 ? ix.P[1] : c == 2 ? ix.P[2] : ix.P[3];
+    sp = pc - 1 + a;
+    ep = pc - 2 + hi.occ;
     return true;
 }
 

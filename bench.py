@@ -41,7 +41,9 @@ def parse():
     ap.add_argument("--ref-bp", type=int, default=REF_BP)
     ap.add_argument("--reads", type=int, default=10_000_000, help="reads per GPU per step")
     ap.add_argument("--read-len", type=int, default=100)
-    ap.add_argument("--sub-rate", type=float, default=0.01)
+    ap.add_argument("--sub-rate", type=float, default=0.01, help="per-base edit probability")
+    ap.add_argument("--edits", default="indel", choices=["indel", "sub"],
+                    help="indel: SURVEY.md 8(d) model, 80/10/10 substitution/insertion/deletion, ragged lengths; sub: substitutions only")
     ap.add_argument("--seed", type=int, default=42)
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="CPU work of the cpu_baseline leg (0 = skip)")
     ap.add_argument("--ref-step-reads", type=int, default=200_000, help="reads per step of --impl reference")
@@ -54,8 +56,10 @@ def parse():
 
 
 def workload_name(a):
+    edits = ("%.1f %% edits (80 %% substitution / 10 %% insertion / 10 %% deletion, lengths %d +- few)" % (100 * a.sub_rate, a.read_len)
+             if a.edits == "indel" else "%.1f %% substitutions" % (100 * a.sub_rate))
     return ("synthetic %.3f Gbp reference (human_g1k_v37_decoy bp total), un-chunked FM index; %d synthetic %d bp reads "
-            "per GPU, %.1f %% substitutions; sga + sw + hit tuples" % (a.ref_bp / 1e9, a.reads, a.read_len, 100 * a.sub_rate))
+            "per GPU, %s; sga + sw + hit tuples" % (a.ref_bp / 1e9, a.reads, a.read_len, edits))
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -142,12 +146,51 @@ def cpu_port_setup(ix, a):
     return orc, time.time() - t0
 
 
-def cpu_port_run(orc, reads, offs, lo, hi, threads):
-    """-> seconds for reads [lo, hi)"""
+def cpu_port_run(orc, reads, offs, lo, hi, threads, cap=16):
+    """-> (seconds for reads [lo, hi), stats, ncand, candidates)"""
     sub_offs = np.ascontiguousarray(offs[lo:hi + 1])
     t0 = time.perf_counter()
-    ncand, cand, st = orc.align_batch(reads, sub_offs, nthreads=threads, with_sw=True, cap_per_read=16)
-    return time.perf_counter() - t0, st
+    ncand, cand, st = orc.align_batch(reads, sub_offs, nthreads=threads, with_sw=True, cap_per_read=cap)
+    return time.perf_counter() - t0, st, ncand, cand
+
+
+ORC_DTYPE = np.dtype([("S", "<i8"), ("D", "<i8"), ("pos", "<i8"), ("score", "<i8"), ("status", "<i4"), ("cigar_len", "<i4"),
+                      ("cigar", "u1", (96,))])
+
+
+def parity_compare(m, ncand, cand, cap, st_g, ho, hits, cig):
+    """The CPU port's candidate lists of reads [0, m) against the GPU hits of the same reads: counts, S, D, status and --
+    for matches -- score, Pos and the CIGAR text.  Vectorised; -> number of reads + candidates that differ."""
+    cand = np.frombuffer(cand, dtype=ORC_DTYPE)
+    cnt_c = np.asarray(ncand[:m], np.int64)
+    cnt_g = np.diff(ho[:m + 1])
+    crash = cnt_c < 0
+    bad_reads = int(np.count_nonzero(crash != (st_g[:m] == 1)))
+    ok = ~crash
+    bad_reads += int(np.count_nonzero(cnt_g[ok] != cnt_c[ok]))
+    agree = ok & (cnt_g == cnt_c)
+    use = np.where(agree, np.minimum(cnt_c, cap), 0)
+    tot = int(use.sum())
+    if tot == 0:
+        return bad_reads, 0
+    rr = np.repeat(np.arange(m, dtype=np.int64), use)
+    k = np.arange(tot, dtype=np.int64) - np.repeat(np.cumsum(use) - use, use)
+    Cc = cand[rr * cap + k]                                   # the port lists sga's order (descending S) ...
+    Gg = hits[ho[rr] + (cnt_c[rr] - 1 - k)]                   # ... the ABI the reference's Cigars order (ascending)
+    bad = (Cc["S"] != Gg["s"]) | (Cc["D"] != Gg["d"]) | (Cc["status"] != Gg["status"])
+    mt = (Cc["status"] == 0) & ~bad
+    bad |= mt & ((Cc["score"] != Gg["score"]) | (Cc["pos"] != Gg["pos"]) | (Cc["cigar_len"] != Gg["cigar_len"]))
+    mt &= ~bad
+    idx = np.nonzero(mt)[0]
+    if len(idx):
+        L = np.minimum(Cc["cigar_len"][idx], 96)
+        off = Gg["cigar_off"][idx]
+        cg = Cc["cigar"][idx]
+        cig = np.frombuffer(cig, np.uint8) if not isinstance(cig, np.ndarray) else cig
+        for t in range(int(L.max())):
+            sel = L > t
+            bad[idx[sel]] |= cg[sel, t] != cig[off[sel] + t]
+    return bad_reads + int(np.count_nonzero(bad)), tot
 
 
 def main():
@@ -179,11 +222,17 @@ def main():
     ix = api.Index.build_synthetic(a.ref_bp, seed=a.seed, shift=1, device=dev)
     build_s = time.time() - t0
     n = a.reads
-    reads_t = torch.empty(n * a.read_len, dtype=torch.uint8).pin_memory()
-    reads = reads_t.numpy()
-    api.sample_reads(ix, n, a.read_len, seed=a.seed + 1000 * (rank + 1), sub_rate=a.sub_rate, out=reads)
-    offs_t = (torch.arange(n + 1, dtype=torch.int64) * a.read_len).pin_memory()
+    reads_t = torch.empty(n * a.read_len + max(4096, n // 8), dtype=torch.uint8).pin_memory()
+    offs_t = torch.empty(n + 1, dtype=torch.int64).pin_memory()
     offs = offs_t.numpy()
+    if a.edits == "indel":
+        reads, _, _ = api.sample_reads_edits(ix, n, a.read_len, seed=a.seed + 1000 * (rank + 1), edit_rate=a.sub_rate,
+                                             out=reads_t.numpy(), offsets=offs)
+    else:
+        reads = reads_t.numpy()[:n * a.read_len]
+        api.sample_reads(ix, n, a.read_len, seed=a.seed + 1000 * (rank + 1), sub_rate=a.sub_rate, out=reads)
+        offs[:] = np.arange(n + 1, dtype=np.int64) * a.read_len
+    read_bytes = int(offs[n])
     threads = os.cpu_count() or 1
 
     if a.impl == "reference":
@@ -199,7 +248,7 @@ def main():
         k_auto = ix.info().kmer_k
         ix.set_kmer_depth(8)
         m = min(n, 4_000_000)
-        subs = np.ascontiguousarray(reads[:m * a.read_len].reshape(m, a.read_len)[:, a.read_len - 15:]).reshape(-1)
+        subs = np.ascontiguousarray(reads[(offs[1:m + 1] - 15)[:, None] + np.arange(15)[None, :]]).reshape(-1)   # the last 15 bases of each read
         ms, lf, hbm_lf = api.search_resident(ix, subs, 15, repeats=3)
         ix.set_kmer_depth(k_auto)
         gbs = 64.0 * hbm_lf * 3 / (ms * 1e-3) / 1e9
@@ -213,9 +262,9 @@ def main():
         mq = min(n, a.inexact_queries)
         if mq > 0:
             t0 = time.perf_counter()
-            fst, fso, fsd, fss = ix.fs_find_seeds(reads[:mq * a.read_len], offs[:mq + 1], a.read_len - 2, 2, 1024)
+            fst, fso, fsd, fss = ix.fs_find_seeds(reads[:offs[mq]], offs[:mq + 1], a.read_len - 4, 2, 1024)
             wall = time.perf_counter() - t0
-            extra["inexact"] = {"queries": mq, "len": a.read_len - 2, "defects": 2, "kernel_ms": fss.ms_kernel,
+            extra["inexact"] = {"queries": mq, "len": a.read_len - 4, "defects": 2, "kernel_ms": fss.ms_kernel,
                                 "queries_per_s_kernel": mq / (fss.ms_kernel * 1e-3), "queries_per_s_call": mq / wall,
                                 "states_per_query": fss.nodes / mq, "lf_steps_per_s": fss.lf_steps / (fss.ms_kernel * 1e-3),
                                 "occ_gbs": round(64.0 * fss.lf_steps / (fss.ms_kernel * 1e-3) / 1e9, 1),
@@ -223,7 +272,7 @@ def main():
                                 "seeds_per_query": len(fsd) / mq, "limit_status": int((fst == api.FS_LIMIT).sum()),
                                 "note": "fs_search_kernel: warp-per-query DFS over gen_pattern/5 (seeds.erl:51-62), 64 B per LF step"}
 
-    batch = api.Batch(ix, n, n * a.read_len)
+    batch = api.Batch(ix, n, read_bytes)
     batch.upload(reads, offs)
 
     # -- resident: warm-up, then K timed steps (CUDA events inside the library, on the batch's own stream)
@@ -261,7 +310,7 @@ def main():
         hits_t = torch.empty((n_hits + n_hits // 8 + 1024) * 40, dtype=torch.uint8).pin_memory()
         cig_t = torch.empty(cig_bytes + cig_bytes // 8 + 4096, dtype=torch.uint8).pin_memory()
 
-        aligner = api.Aligner(ix, chunk_reads=a.chunk_reads, chunk_bytes=a.chunk_reads * a.read_len, depth=a.depth)
+        aligner = api.Aligner(ix, chunk_reads=a.chunk_reads, chunk_bytes=a.chunk_reads * (a.read_len + 2), depth=a.depth)
         e2e_launches = 0
         e2e_copy = [0.0, 0.0]
 
@@ -280,7 +329,7 @@ def main():
         barrier()
         e2e_s = time.perf_counter() - e0
         assert (nh, nc) == (n_hits, cig_bytes), "pipelined and resident paths disagree"
-        h2d = n * a.read_len + (n + 1) * 8
+        h2d = read_bytes + (n + 1) * 8
         d2h = n * 4 + (n + 1) * 8 + nh * 40 + nc
         e2e = [e2e_s, h2d, d2h, e2e_copy[0] / a.steps, e2e_copy[1] / a.steps]
 
@@ -307,7 +356,7 @@ def main():
         #                entry, per located row 4 bytes of SA, per read its bases once
         #   sw_fast    : per pair Lq + Lr bases in and a 16-byte result + its CIGAR out; cells x 4.25 ALU-pipe
         #                instructions (8.5 per cell pair: PRMT, 2 VIADDMNMX, VIMNMX, VIADD.16x2, 3.5 LOP3 -- from SASS)
-        sga_bytes = (64.0 * agg["hbm_lf"] + 8.0 * agg["searches"] + 4.0 * agg["located"] + float(n * a.read_len * K))
+        sga_bytes = (64.0 * agg["hbm_lf"] + 8.0 * agg["searches"] + 4.0 * agg["located"] + float(read_bytes * K))
         sga_gbs = sga_bytes / (agg["ms_sga"] * 1e-3) / 1e9 if agg["ms_sga"] > 0 else 0.0
         #   shortcut   : pairs whose result sw_classify_kernel proves without the DP (perfect / one-mismatch diagonal) are
         #                NOT in the DP kernel's cell count: gcups = cells the DP kernel computed / its own time
@@ -348,7 +397,7 @@ def main():
             "config": {"workload": workload_name(a), "reads_per_gpu_per_step": n, "read_len": a.read_len, "ref_bp": a.ref_bp,
                        "parallelism": "read sharding, index replicated x%d" % world,
                        "l2": "inputs larger than L2 (index %.1f GB, reads %.2f GB per step); no flush needed" % (
-                           ix.info().device_bytes / 1e9, n * a.read_len / 1e9),
+                           ix.info().device_bytes / 1e9, read_bytes / 1e9),
                        "index_build_s": round(build_s, 2), "timer": "CUDA events on the batch stream, max over ranks",
                        "wall_ms_per_step": t_wall / K},
             "clocks": clk, "gpu_launches": total_launches,
@@ -374,8 +423,11 @@ def main():
                           "d2h_gbs": e2e[2] / (e2e[4] * 1e-3) / 1e9 if e2e[4] else None,
                           "note": "copy times are summed over the chunks (CUDA events on each chunk's stream); chunks overlap"}
         if world == 1 and a.cpu_seconds > 0:
-            out["cpu_baseline"] = cpu_baseline(a, ix, reads, offs, threads)
+            out["cpu_baseline"], out["parity_sample"] = cpu_baseline(a, ix, reads, offs, threads, batch.download())
         print(json.dumps(out), flush=True)
+        if out.get("parity_sample", {}).get("mismatches", 0) != 0:
+            print("bench.py: GPU hits differ from the CPU port on the sampled reads", file=sys.stderr)
+            return 3
     batch.close()
     ix.close()
     if dist is not None:
@@ -384,18 +436,26 @@ def main():
     return 0
 
 
-def cpu_baseline(a, ix, reads, offs, threads):
+def cpu_baseline(a, ix, reads, offs, threads, gpu_result):
+    """The CPU port timed on a bounded sample of the step's own reads, and -- with the candidates it produced anyway --
+    the in-run parity check: they must equal the GPU hits of the same reads."""
     orc, setup_s = cpu_port_setup(ix, a)
     probe = min(a.reads, 20_000 * threads)
-    t, _ = cpu_port_run(orc, reads, offs, 0, probe, threads)
+    t, _, _, _ = cpu_port_run(orc, reads, offs, 0, probe, threads)
     rate = probe / t
     m = int(min(a.reads, max(probe, rate * a.cpu_seconds)))
-    t, st = cpu_port_run(orc, reads, offs, 0, m, threads)
+    t, st, ncand, cand = cpu_port_run(orc, reads, offs, 0, m, threads)
     orc.close()
-    return {"value": m / t, "unit": UNIT, "cores": threads, "kind": "port",
-            "sample": "first %d of the step's %d reads, same index (exported from the device), %.1f s of CPU work on %d threads; "
-                      "C port of the reference's algorithm (oracle/bwt_oracle.c), not BEAM" % (m, a.reads, t, threads),
-            "lf_steps_per_read": st.lf_steps / m, "cells_per_read": st.cells / m, "setup_s": round(setup_s, 1)}
+    out = {"value": m / t, "unit": UNIT, "cores": threads, "kind": "port",
+           "sample": "first %d of the step's %d reads, same index (exported from the device), %.1f s of CPU work on %d threads; "
+                     "C port of the reference's algorithm (oracle/bwt_oracle.c), not BEAM" % (m, a.reads, t, threads),
+           "lf_steps_per_read": st.lf_steps / m, "cells_per_read": st.cells / m, "setup_s": round(setup_s, 1)}
+    st_g, ho, hits, cig = gpu_result
+    t0 = time.perf_counter()
+    mism, compared = parity_compare(m, ncand, cand, 16, st_g, ho, hits, cig)
+    parity = {"reads": m, "candidates": compared, "mismatches": mism, "compare_s": round(time.perf_counter() - t0, 1),
+              "what": "CPU port vs GPU hits of the same reads: candidate count, S, D, status, score, Pos, CIGAR text"}
+    return out, parity
 
 
 def run_reference(a, ix, reads, offs, threads):
@@ -410,7 +470,7 @@ def run_reference(a, ix, reads, offs, threads):
         nonlocal pos
         if pos + m > a.reads:
             pos = 0
-        t, st = cpu_port_run(orc, reads, offs, pos, pos + m, threads)
+        t = cpu_port_run(orc, reads, offs, pos, pos + m, threads)[0]
         pos += m
         return t
     for _ in range(a.warmup):

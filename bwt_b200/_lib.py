@@ -49,6 +49,12 @@ class BwtFsStats(C.Structure):
                 ("seeds", C.c_uint64), ("spills", C.c_uint64), ("ms_kernel", C.c_float), ("launches", C.c_uint32)]
 
 
+class BwtSampleOpts(C.Structure):
+    _fields_ = [("n", C.c_int64), ("read_len", C.c_int32), ("device", C.c_int32), ("seed", C.c_uint64),
+                ("edit_rate", C.c_double), ("ins_share", C.c_double), ("del_share", C.c_double), ("n_rate", C.c_double),
+                ("synth_len", C.c_uint64), ("synth_seed", C.c_uint64)]
+
+
 # every symbol include/bwt_b200.h declares: (restype, argtypes)
 P = C.c_void_p
 SIGNATURES = {
@@ -59,6 +65,8 @@ SIGNATURES = {
     "bwt_open_arrays": (C.c_int, [P, C.c_uint64, P, P, C.c_int64, P, C.c_uint64, C.c_int, C.POINTER(P)]),
     "bwt_build": (C.c_int, [P, C.c_uint64, C.c_int64, C.c_int, C.POINTER(P)]),
     "bwt_build_synthetic": (C.c_int, [C.c_uint64, C.c_uint64, C.c_int64, C.c_int, C.POINTER(P)]),
+    "bwt_build_synthetic_part": (C.c_int, [C.c_uint64, C.c_uint64, C.c_uint64, C.c_int64, C.c_int, C.POINTER(P)]),
+    "bwt_sample_reads_edits": (C.c_int, [P, C.POINTER(BwtSampleOpts), P, C.c_int64, P, P, C.POINTER(C.c_int64)]),
     "bwt_save": (C.c_int, [P, C.c_char_p, C.c_char_p]),
     "bwt_export": (C.c_int, [P, P, P, P]),
     "bwt_info": (C.c_int, [P, C.POINTER(BwtIndexInfo)]),

@@ -9,7 +9,7 @@ from typing import List, Optional, Sequence, Tuple
 
 import numpy as np
 
-from ._lib import BwtError, BwtFsStats, BwtHit, BwtIndexInfo, BwtStats, NoSpace, check, lib
+from ._lib import BwtError, BwtFsStats, BwtHit, BwtIndexInfo, BwtSampleOpts, BwtStats, NoSpace, check, lib
 
 HIT_DTYPE = np.dtype([("pos", "<i8"), ("s", "<i8"), ("cigar_off", "<i8"), ("d", "<i4"), ("score", "<i4"),
                       ("status", "<i4"), ("cigar_len", "<i4")])
@@ -79,6 +79,13 @@ class Index:
     def build_synthetic(cls, length: int, seed: int = 42, shift: int = 1, device: int = 0) -> "Index":
         h = C.c_void_p()
         check(lib().bwt_build_synthetic(int(length), int(seed), int(shift), device, C.byref(h)))
+        return cls(h.value)
+
+    @classmethod
+    def build_synthetic_part(cls, start: int, length: int, seed: int = 42, shift: int = 1, device: int = 0) -> "Index":
+        """bases [start, start+length) of the synthetic reference ``seed``: one ``_pJ`` partition (fm_index.erl:113-124)"""
+        h = C.c_void_p()
+        check(lib().bwt_build_synthetic_part(int(start), int(length), int(seed), int(shift), device, C.byref(h)))
         return cls(h.value)
 
     # -- lifetime ---------------------------------------------------------------------------------
@@ -374,6 +381,29 @@ def sample_reads(index: Index, n: int, read_len: int, seed: int = 42, sub_rate: 
     return out, offs, starts
 
 
+def sample_reads_edits(index: Optional[Index], n: int, read_len: int, seed: int = 42, edit_rate: float = 0.01,
+                       ins_share: float = 0.1, del_share: float = 0.1, n_rate: float = 0.0, synth: Optional[Tuple[int, int]] = None,
+                       device: int = 0, out: Optional[np.ndarray] = None, offsets: Optional[np.ndarray] = None,
+                       want_starts: bool = False):
+    """SURVEY.md 8(d) edit model (substitutions / 1-base insertions / deletions; ragged lengths), sampled on the device
+    from the index's .ref, or -- index None, synth = (length, seed) -- from the synthetic reference itself.
+    -> (uint8[total], int64 offsets[n+1], starts|None)"""
+    o = BwtSampleOpts(int(n), int(read_len), int(device), int(seed), float(edit_rate), float(ins_share), float(del_share),
+                      float(n_rate), int(synth[0]) if synth else 0, int(synth[1]) if synth else 0)
+    if offsets is None:
+        offsets = np.empty(n + 1, np.int64)
+    if out is None:
+        out = np.empty(n * read_len + max(4096, n // 8), np.uint8)
+    starts = np.empty(n, np.int64) if want_starts else None
+    tot = C.c_int64()
+    h = index.handle if index is not None else None
+    rc = lib().bwt_sample_reads_edits(h, C.byref(o), out.ctypes.data, len(out), offsets.ctypes.data, _ptr(starts), C.byref(tot))
+    if rc == -6:
+        raise NoSpace(lib().bwt_last_error().decode(), (int(tot.value),))
+    check(rc)
+    return out[:tot.value], offsets, starts
+
+
 def search_resident(index: Index, subs: np.ndarray, sub_len: int, repeats: int = 1):
     """-> (ms for all repeats, LF steps per repeat, LF steps per repeat not served by the 8-mer table)"""
     subs = _u8(subs)
@@ -397,5 +427,5 @@ def peak_dpx_gops(device: int = 0) -> float:
     return float(g.value)
 
 
-__all__ = ["Index", "Batch", "Aligner", "sample_reads", "BwtError", "NoSpace", "pack", "sw_batch", "search_resident", "peak_gather_gbs",
+__all__ = ["Index", "Batch", "Aligner", "sample_reads", "sample_reads_edits", "BwtError", "NoSpace", "pack", "sw_batch", "search_resident", "peak_gather_gbs",
            "peak_dpx_gops", "device_count", "HIT_DTYPE"]

@@ -8,6 +8,7 @@
 // CUB's radix sort is the only library primitive used, and only here in the offline builder.
 // Then L[e] = Seq[SA[e]-1] ('$' for SA[e] = 0), pointers from the symbol counts (fmi.erl:66-84).
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
 
 #include "common.cuh"
 
@@ -157,20 +158,22 @@ __global__ void map_acgt_kernel(const uint8_t *__restrict__ in, uint64_t len, ui
     out[i] = o;
 }
 
-__global__ void synth_kernel(uint8_t *__restrict__ out, uint64_t len, uint64_t seed) {
-    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= len) return;
-    uint64_t z = seed + 0x9E3779B97F4A7C15ull * (i / 32 + 1);        // splitmix64 of the 32-base word index
-    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-    z ^= z >> 31;
-    out[i] = (uint8_t)"ACGT"[(z >> (2 * (i & 31))) & 3];
-}
-
 __device__ __forceinline__ uint64_t mix64(uint64_t z) {           // splitmix64 finaliser
     z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
     z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
     return z ^ (z >> 31);
+}
+
+// base i of the synthetic reference (seed): a pure function of the position, so that a partition of it (or a read
+// drawn from it) can be produced anywhere without holding the whole text
+__device__ __forceinline__ uint8_t synth_base(uint64_t seed, uint64_t i) {
+    const uint64_t z = mix64(seed + 0x9E3779B97F4A7C15ull * (i / 32 + 1));   // splitmix64 of the 32-base word index
+    return (uint8_t)"ACGT"[(z >> (2 * (i & 31))) & 3];
+}
+
+__global__ void synth_kernel(uint8_t *__restrict__ out, uint64_t start, uint64_t len, uint64_t seed) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < len) out[i] = synth_base(seed, start + i);
 }
 
 // one thread per base: read r starts at hash(seed, r) mod (ref_len - len + 1); base p of read r is substituted
@@ -191,6 +194,46 @@ __global__ void sample_reads_kernel(const uint8_t *__restrict__ ref, uint64_t re
         if (k >= 0) c = (uint8_t)"ACGT"[(k + 1 + (int)((h >> 32) % 3)) & 3];
     }
     out[t] = c;
+}
+
+// SURVEY.md 8(d) edit model, one thread per read: each of the `len` reference bases drawn for read r is edited with
+// probability thresh / 2^32 -- substituted, followed by one inserted base (16-bit draw < ins_cut), or deleted
+// (< del_cut) -- so the read comes out len + #insertions - #deletions long; afterwards every base of the read turns
+// into 'N' with probability n_thresh / 2^32.  out == nullptr: only the length is computed (pass 1).
+// ref == nullptr: the bases come from the synthetic reference (synth_seed).
+__global__ void sample_edits_kernel(const uint8_t *__restrict__ ref, uint64_t synth_seed, uint64_t ref_len, int64_t n,
+                                    int32_t len, uint64_t seed, uint32_t thresh, uint32_t ins_cut, uint32_t del_cut,
+                                    uint32_t n_thresh, const int64_t *__restrict__ offs, uint8_t *__restrict__ out,
+                                    int64_t *__restrict__ lens, int64_t *__restrict__ starts) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    const uint64_t start = mix64(seed ^ (0x9E3779B97F4A7C15ull * (uint64_t)(r + 1))) % (ref_len - (uint64_t)len + 1);
+    uint8_t *o = out ? out + offs[r] : nullptr;
+    int64_t w = 0;
+    for (int32_t p = 0; p < len; p++) {
+        uint8_t c = ref ? ref[start + p] : synth_base(synth_seed, start + p);
+        const uint64_t h = mix64((seed + 0x51ED270B1ull) ^ (0xD6E8FEB86659FD93ull * (uint64_t)(r * len + p + 1)));
+        uint8_t extra = 0;
+        bool drop = false;
+        if ((uint32_t)h < thresh) {
+            const uint32_t kind = (uint32_t)(h >> 32) & 0xFFFFu, pick = (uint32_t)(h >> 48);
+            if (kind < ins_cut) extra = (uint8_t)"ACGT"[pick & 3];
+            else if (kind < del_cut) drop = true;
+            else { const int k = bwt_code(c); if (k >= 0) c = (uint8_t)"ACGT"[(k + 1 + (int)(pick % 3)) & 3]; }
+        }
+        for (int e = 0; e < 2; e++) {
+            if (e == 0 ? drop : !extra) continue;
+            uint8_t b = e == 0 ? c : extra;
+            if (n_thresh) {
+                const uint64_t hn = mix64((seed + 0x7F4A7C15ull) ^ (0xA24BAED4963EE407ull * (uint64_t)(2 * (r * len + p) + e + 1)));
+                if ((uint32_t)hn < n_thresh) b = 'N';
+            }
+            if (o) o[w] = b;
+            w++;
+        }
+    }
+    if (!out) lens[r] = w;
+    if (starts && !out) starts[r] = (int64_t)start;
 }
 
 struct DevBuf {
@@ -375,9 +418,65 @@ extern "C" int bwt_build_synthetic(uint64_t len, uint64_t seed, int64_t shift, i
     BWT_TRY(index_select_device(device));
     DevBuf d;
     BWT_TRY(d.alloc(len));
-    synth_kernel<<<blocks_for(len), 256>>>(d.as<uint8_t>(), len, seed);
+    synth_kernel<<<blocks_for(len), 256>>>(d.as<uint8_t>(), 0, len, seed);
     CU_TRY(cudaGetLastError());
     return build_from_device_chunk(d.as<uint8_t>(), len, shift, device, true, out);
+}
+
+extern "C" int bwt_build_synthetic_part(uint64_t start, uint64_t len, uint64_t seed, int64_t shift, int device, bwt_index **out) {
+    if (!out) { bwt_set_error("bwt_build_synthetic_part: null argument"); return BWT_ERR_ARG; }
+    BWT_TRY(index_select_device(device));
+    DevBuf d;
+    BWT_TRY(d.alloc(len));
+    synth_kernel<<<blocks_for(len), 256>>>(d.as<uint8_t>(), start, len, seed);
+    CU_TRY(cudaGetLastError());
+    return build_from_device_chunk(d.as<uint8_t>(), len, shift, device, true, out);
+}
+
+extern "C" int bwt_sample_reads_edits(const bwt_index *h, const bwt_sample_opts *o, uint8_t *reads_out, int64_t reads_cap,
+                                      int64_t *offsets_out, int64_t *starts_out, int64_t *total_bytes) {
+    if (!o || !offsets_out || !total_bytes || o->n < 0 || o->read_len <= 0 || o->edit_rate < 0 || o->edit_rate > 1 ||
+        o->ins_share < 0 || o->del_share < 0 || o->ins_share + o->del_share > 1 || o->n_rate < 0 || o->n_rate > 1) {
+        bwt_set_error("bwt_sample_reads_edits: bad argument");
+        return BWT_ERR_ARG;
+    }
+    const uint64_t ref_len = h ? h->ref_len : o->synth_len;
+    if ((uint64_t)o->read_len > ref_len) { bwt_set_error("bwt_sample_reads_edits: reads longer than the reference"); return BWT_ERR_ARG; }
+    const int64_t n = o->n;
+    *total_bytes = 0;
+    offsets_out[0] = 0;
+    if (n == 0) return BWT_OK;
+    BWT_TRY(index_select_device(h ? h->device : o->device));
+    auto frac32 = [](double f) { double t = f * 4294967296.0; return t >= 4294967295.0 ? 0xFFFFFFFFu : (uint32_t)t; };
+    const uint32_t thresh = frac32(o->edit_rate), n_thresh = frac32(o->n_rate);
+    const uint32_t ins_cut = (uint32_t)(o->ins_share * 65536.0), del_cut = (uint32_t)((o->ins_share + o->del_share) * 65536.0);
+    const uint8_t *ref = h ? (const uint8_t *)h->d_ref + BWT_REF_EXT : nullptr;
+    DevBuf lens, offs, st, tmp, out;
+    BWT_TRY(lens.alloc((size_t)(n + 1) * sizeof(int64_t)));
+    BWT_TRY(offs.alloc((size_t)(n + 1) * sizeof(int64_t)));
+    if (starts_out) BWT_TRY(st.alloc((size_t)n * sizeof(int64_t)));
+    CU_TRY(cudaMemset(lens.p, 0, (size_t)(n + 1) * sizeof(int64_t)));
+    sample_edits_kernel<<<blocks_for((uint64_t)n, 128), 128>>>(ref, o->synth_seed, ref_len, n, o->read_len, o->seed, thresh, ins_cut, del_cut,
+                                                             n_thresh, nullptr, nullptr, lens.as<int64_t>(),
+                                                             starts_out ? st.as<int64_t>() : nullptr);
+    CU_TRY(cudaGetLastError());
+    size_t tmp_bytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, lens.as<int64_t>(), offs.as<int64_t>(), (int64_t)(n + 1));
+    BWT_TRY(tmp.alloc(tmp_bytes));
+    cudaError_t e = cub::DeviceScan::ExclusiveSum(tmp.p, tmp_bytes, lens.as<int64_t>(), offs.as<int64_t>(), (int64_t)(n + 1));
+    if (e != cudaSuccess) { bwt_set_error("bwt_sample_reads_edits: scan failed: %s", cudaGetErrorString(e)); return BWT_ERR_CUDA; }
+    CU_TRY(cudaMemcpy(offsets_out, offs.p, (size_t)(n + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost));
+    const int64_t total = offsets_out[n];
+    *total_bytes = total;
+    if (starts_out) CU_TRY(cudaMemcpy(starts_out, st.p, (size_t)n * sizeof(int64_t), cudaMemcpyDeviceToHost));
+    if (!reads_out || total > reads_cap) { bwt_set_error("bwt_sample_reads_edits: reads need %lld bytes", (long long)total); return BWT_ERR_NOSPACE; }
+    lens.release(); tmp.release();
+    BWT_TRY(out.alloc((size_t)total + 16));
+    sample_edits_kernel<<<blocks_for((uint64_t)n, 128), 128>>>(ref, o->synth_seed, ref_len, n, o->read_len, o->seed, thresh, ins_cut, del_cut,
+                                                             n_thresh, offs.as<int64_t>(), out.as<uint8_t>(), nullptr, nullptr);
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaMemcpy(reads_out, out.p, (size_t)total, cudaMemcpyDeviceToHost));
+    return BWT_OK;
 }
 
 extern "C" int bwt_sample_reads(const bwt_index *h, int64_t n, int32_t read_len, uint64_t seed, double sub_rate,

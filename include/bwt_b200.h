@@ -263,6 +263,30 @@ int bwt_search_resident(bwt_index *h, const uint8_t *subs, int64_t n, int32_t su
 int bwt_sample_reads(const bwt_index *h, int64_t n, int32_t read_len, uint64_t seed, double sub_rate,
                      uint8_t *reads_out, int64_t *starts_out);
 
+/* The same generator restricted to bases [start, start+len) of that synthetic reference: the text of one _pJ partition
+ * (fm_index.erl:113-124 gives start/len; shift = contig shift + Start_J), built where it is needed without holding the
+ * whole reference. */
+int bwt_build_synthetic_part(uint64_t start, uint64_t len, uint64_t seed, int64_t shift, int device, bwt_index **out);
+
+/* Synthetic reads with the edit model of SURVEY.md 8(d): read r = read_len reference bases from a uniform position, each
+ * edited with probability edit_rate -- a share ins_share of the edits inserts one random base after the base, a share
+ * del_share deletes the base, the rest substitute it by a different base -- so read lengths vary (read_len + #ins - #del).
+ * Afterwards every base turns into 'N' with probability n_rate.  Forward strand.  h != NULL: bases from the index's .ref;
+ * h == NULL: from the synthetic reference (synth_len, synth_seed) of bwt_build_synthetic, generated on `device` (every
+ * rank of a partitioned run draws the SAME reads without holding the whole text).
+ * offsets_out[n+1] always; reads_out (capacity reads_cap) and starts_out may be NULL; *total_bytes = bytes of all reads
+ * (BWT_ERR_NOSPACE when reads_cap is too small). */
+typedef struct bwt_sample_opts {
+    int64_t n;
+    int32_t read_len;
+    int32_t device;
+    uint64_t seed;
+    double edit_rate, ins_share, del_share, n_rate;
+    uint64_t synth_len, synth_seed;
+} bwt_sample_opts;
+int bwt_sample_reads_edits(const bwt_index *h, const bwt_sample_opts *o, uint8_t *reads_out, int64_t reads_cap,
+                           int64_t *offsets_out, int64_t *starts_out, int64_t *total_bytes);
+
 /* Microbenchmarks that give the roofline denominators measured on the device at hand:
  * random 32-byte-sector gather bandwidth (GB/s) and DPX (VIADDMNMX/VIMNMX3) issue rate (Gop/s). */
 int bwt_peak_gather_gbs(int device, uint64_t bytes, double *gbs);

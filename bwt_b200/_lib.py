@@ -29,9 +29,20 @@ class BwtHit(C.Structure):
                 ("score", C.c_int32), ("status", C.c_int32), ("cigar_len", C.c_int32)]
 
 
+class BwtHit16(C.Structure):
+    _fields_ = [("s", C.c_uint32), ("d_flags", C.c_uint32), ("cigar_off", C.c_uint32), ("score", C.c_int16), ("cigar_len", C.c_uint16)]
+
+
+class BwtPackedReads(C.Structure):
+    _fields_ = [("n", C.c_int64), ("fixed_len", C.c_int32), ("reserved", C.c_int32), ("lens", C.c_void_p), ("words", C.c_void_p),
+                ("n_words", C.c_int64), ("n_exc", C.c_int64), ("exc_idx", C.c_void_p), ("exc_off", C.c_void_p),
+                ("exc_ascii", C.c_void_p)]
+
+
 class BwtIndexInfo(C.Structure):
     _fields_ = [("n_rows", C.c_uint64), ("pointers", C.c_uint32 * 4), ("shift", C.c_int64), ("ref_len", C.c_uint64),
-                ("dollar_row", C.c_uint64), ("device_bytes", C.c_uint64), ("device", C.c_int32), ("kmer_k", C.c_int32)]
+                ("dollar_row", C.c_uint64), ("device_bytes", C.c_uint64), ("device", C.c_int32), ("kmer_k", C.c_int32),
+                ("fused", C.c_int32), ("reserved", C.c_int32)]
 
 
 class BwtStats(C.Structure):
@@ -85,6 +96,14 @@ SIGNATURES = {
     "bwt_batch_result_size": (C.c_int, [P, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "bwt_batch_download": (C.c_int, [P, P, P, P, C.c_int64, P, C.c_int64]),
     "bwt_batch_stats": (C.c_int, [P, C.POINTER(BwtStats)]),
+    "bwt_pack_words": (C.c_int64, [P, C.c_int64]),
+    "bwt_pack_reads": (C.c_int, [P, P, C.c_int64, C.c_int, P, C.c_int64, P, P, C.c_int64, P, P, C.c_int64,
+                                 C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "bwt_batch_upload_packed": (C.c_int, [P, C.POINTER(BwtPackedReads)]),
+    "bwt_batch_run_compact": (C.c_int, [P]),
+    "bwt_batch_download_compact": (C.c_int, [P, P, P, P, C.c_int64, P, C.c_int64]),
+    "bwt_aligner_run_packed": (C.c_int, [P, C.POINTER(BwtPackedReads), P, P, P, C.c_int64, C.POINTER(C.c_int64), P, C.c_int64,
+                                         C.POINTER(C.c_int64)]),
     "bwt_batch_device_result": (C.c_int, [P, C.POINTER(P), C.POINTER(P), C.POINTER(P)]),
     "bwt_aligner_create": (C.c_int, [P, C.c_int64, C.c_int64, C.c_int, C.POINTER(P)]),
     "bwt_aligner_run": (C.c_int, [P, P, P, C.c_int64, P, P, P, C.c_int64, C.POINTER(C.c_int64), P, C.c_int64,
@@ -117,7 +136,7 @@ def lib():
             fn = getattr(L, name)          # AttributeError here = the .so does not export a declared symbol
             fn.restype = res
             fn.argtypes = args
-        if L.bwt_abi_version() != 2:
+        if L.bwt_abi_version() != 3:
             raise ImportError("bwt_b200: ABI version mismatch")
         _lib = L
     return _lib

@@ -9,11 +9,16 @@ from typing import List, Optional, Sequence, Tuple
 
 import numpy as np
 
-from ._lib import BwtError, BwtFsStats, BwtHit, BwtIndexInfo, BwtSampleOpts, BwtStats, NoSpace, check, lib
+from ._lib import (BwtError, BwtFsStats, BwtHit, BwtHit16, BwtIndexInfo, BwtPackedReads, BwtSampleOpts, BwtStats, NoSpace,
+                   check, lib)
 
 HIT_DTYPE = np.dtype([("pos", "<i8"), ("s", "<i8"), ("cigar_off", "<i8"), ("d", "<i4"), ("score", "<i4"),
                       ("status", "<i4"), ("cigar_len", "<i4")])
 assert HIT_DTYPE.itemsize == C.sizeof(BwtHit) == 40
+
+HIT16_DTYPE = np.dtype([("s", "<u4"), ("d_flags", "<u4"), ("cigar_off", "<u4"), ("score", "<i2"), ("cigar_len", "<u2")])
+assert HIT16_DTYPE.itemsize == C.sizeof(BwtHit16) == 16
+HIT16_FULL_M = 0x40000000
 
 SEEDS, NO_SEEDS, TOO_MANY_SEEDS, SEARCH_CRASH = 0, 1, 2, 3
 READ_OK, READ_CRASH, READ_LIMIT = 0, 1, 2
@@ -251,6 +256,94 @@ def sw_batch(q, q_offsets, r, r_offsets, device: int = 0):
         return st, sc, cigars
 
 
+class PackedReads:
+    """An ASCII batch in the 2-bit packed layout of ``bwt_packed_reads`` (``bwt_pack_reads``); keeps its arrays alive.
+    ``pinned=True`` puts them into page-locked memory (torch) so that uploads run at full PCIe speed."""
+
+    def __init__(self, reads, offsets=None, threads: int = 8, pinned: bool = False, fixed_len: int = 0):
+        if offsets is None:
+            reads, offsets = pack(reads)
+        reads = _u8(reads)
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        n = len(offsets) - 1
+        nw = lib().bwt_pack_words(offsets.ctypes.data, n)
+        if nw < 0:
+            raise BwtError(-1, "offsets must be non-decreasing")
+
+        def buf(count, dtype):
+            if pinned:
+                import torch
+                t = torch.empty(max(1, count), dtype={np.uint32: torch.int32, np.uint16: torch.int16, np.int64: torch.int64,
+                                                      np.uint8: torch.uint8}[dtype]).pin_memory()
+                self._keep.append(t)
+                return t.numpy().view(dtype)
+            return np.empty(max(1, count), dtype)
+        self._keep = []
+        self.n = n
+        self.words = buf(nw + 1, np.uint32)
+        self.lens = buf(n, np.uint16)
+        ne, nb, nwo = C.c_int64(), C.c_int64(), C.c_int64()
+        ecap, bcap = 0, 0
+        self.exc_idx = self.exc_off = self.exc_ascii = None
+        while True:
+            rc = lib().bwt_pack_reads(reads.ctypes.data if len(reads) else None, offsets.ctypes.data, n, int(threads),
+                                      self.words.ctypes.data, len(self.words), self.lens.ctypes.data, _ptr(self.exc_idx), ecap,
+                                      _ptr(self.exc_off), _ptr(self.exc_ascii), bcap, C.byref(nwo), C.byref(ne), C.byref(nb))
+            if rc == -6 and (ne.value > ecap or nb.value > bcap):
+                ecap, bcap = int(ne.value), int(nb.value)
+                self.exc_idx = buf(ecap, np.uint32)
+                self.exc_off = buf(ecap + 1, np.int64)
+                self.exc_ascii = buf(bcap, np.uint8)
+                continue
+            check(rc)
+            break
+        self.n_words, self.n_exc, self.exc_bytes = int(nwo.value), int(ne.value), int(nb.value)
+        self.fixed_len = int(fixed_len)
+        if self.fixed_len:
+            assert n == 0 or (self.lens[:n] == self.fixed_len).all(), "fixed_len given for a ragged batch"
+        self.struct = BwtPackedReads(n, self.fixed_len, 0, self.lens.ctypes.data, self.words.ctypes.data, self.n_words, self.n_exc,
+                                     _ptr(self.exc_idx), _ptr(self.exc_off), _ptr(self.exc_ascii))
+
+    def upload_bytes(self) -> int:
+        """bytes a run moves to the device for this batch"""
+        return 4 * (self.n_words + 1) + (0 if self.fixed_len else 2 * self.n) + self.n_exc * 12 + self.exc_bytes
+
+
+def expand_compact(read_status8, hit_off32, hits16, cigars, read_lens, shift: int):
+    """compact result (uint8 status, uint32 offsets, HIT16 records, arena) -> the wide layout of ``Index.align``:
+    (int32 status, int64 offsets, HIT_DTYPE hits, cigar bytes) with "<Lq>M" CIGARs written out and Pos = S - (Lq+D) + Shift"""
+    n = len(read_status8)
+    ho = hit_off32.astype(np.int64)
+    nh = int(ho[n]) if n else 0
+    h16 = hits16[:nh]
+    out = np.zeros(nh, HIT_DTYPE)
+    lens = np.repeat(np.asarray(read_lens, np.int64), np.diff(ho))
+    d = (h16["d_flags"] & 0x0FFFFFFF).astype(np.int64)
+    out["s"] = h16["s"]
+    out["d"] = d
+    out["status"] = (h16["d_flags"] >> 28) & 3
+    out["score"] = h16["score"]
+    out["pos"] = h16["s"].astype(np.int64) - (lens + d) + int(shift)
+    full = (h16["d_flags"] & HIT16_FULL_M) != 0
+    texts = []
+    cig = bytes(cigars)
+    off = 0
+    clen = np.zeros(nh, np.int32)
+    coff = np.zeros(nh, np.int64)
+    for k in range(nh):
+        if full[k]:
+            t = b"%dM" % lens[k]
+        else:
+            t = cig[int(h16["cigar_off"][k]):int(h16["cigar_off"][k]) + int(h16["cigar_len"][k])]
+        texts.append(t)
+        coff[k] = off
+        clen[k] = len(t)
+        off += len(t)
+    out["cigar_off"] = coff
+    out["cigar_len"] = clen
+    return read_status8.astype(np.int32), ho, out, b"".join(texts)
+
+
 class Batch:
     """Resident batch: upload / run / download as separate calls (``bwt_batch``)."""
 
@@ -278,8 +371,26 @@ class Batch:
         self._n = n
         check(lib().bwt_batch_upload(self._b, reads_ptr, offsets_ptr, n))
 
+    def upload_packed(self, packed: "PackedReads"):
+        self._n = packed.n
+        check(lib().bwt_batch_upload_packed(self._b, C.byref(packed.struct)))
+
     def run(self):
         check(lib().bwt_batch_run(self._b))
+
+    def run_compact(self):
+        check(lib().bwt_batch_run_compact(self._b))
+
+    def download_compact(self):
+        """-> (uint8 status[n], uint32 offsets[n+1], HIT16 hits, uint8 cigars)"""
+        nh, nc = self.result_size()
+        n = self._n
+        st = np.zeros(n, np.uint8)
+        ho = np.zeros(n + 1, np.uint32)
+        hits = np.zeros(max(nh, 1), HIT16_DTYPE)
+        cig = np.zeros(max(nc, 1), np.uint8)
+        check(lib().bwt_batch_download_compact(self._b, st.ctypes.data, ho.ctypes.data, hits.ctypes.data, len(hits), cig.ctypes.data, len(cig)))
+        return st, ho, hits[:nh], cig[:nc]
 
     def result_size(self) -> Tuple[int, int]:
         a, b = C.c_int64(), C.c_int64()
@@ -343,6 +454,32 @@ class Aligner:
             raise NoSpace(lib().bwt_last_error().decode(), (int(nh.value), int(nc.value)))
         check(rc)
         return int(nh.value), int(nc.value)
+
+    def run_packed_ptr(self, packed: "PackedReads", status_ptr, hit_offs_ptr, hits_ptr, hits_cap, cig_ptr, cig_cap):
+        """packed reads in, compact records out (raw pointers of the caller); -> (n_hits, cigar_bytes)"""
+        nh, nc = C.c_int64(), C.c_int64()
+        rc = lib().bwt_aligner_run_packed(self._a, C.byref(packed.struct), status_ptr, hit_offs_ptr, hits_ptr, int(hits_cap),
+                                          C.byref(nh), cig_ptr, int(cig_cap), C.byref(nc))
+        if rc == -6:
+            raise NoSpace(lib().bwt_last_error().decode(), (int(nh.value), int(nc.value)))
+        check(rc)
+        return int(nh.value), int(nc.value)
+
+    def run_packed(self, packed: "PackedReads"):
+        """-> (uint8 status[n], uint32 offsets[n+1], HIT16 hits, uint8 cigars)"""
+        n = packed.n
+        st = np.zeros(n, np.uint8)
+        ho = np.zeros(n + 1, np.uint32)
+        hcap, ccap = max(16, 2 * n), max(256, 16 * n)
+        while True:
+            hits = np.zeros(hcap, HIT16_DTYPE)
+            cig = np.zeros(ccap, np.uint8)
+            try:
+                nh, nc = self.run_packed_ptr(packed, st.ctypes.data, ho.ctypes.data, hits.ctypes.data, hcap, cig.ctypes.data, ccap)
+            except NoSpace as e:
+                hcap, ccap = e.needed[0] + 16, e.needed[1] + 16
+                continue
+            return st, ho, hits[:nh].copy(), cig[:nc].copy()
 
     def run(self, reads, offsets=None):
         if offsets is None:
@@ -427,5 +564,5 @@ def peak_dpx_gops(device: int = 0) -> float:
     return float(g.value)
 
 
-__all__ = ["Index", "Batch", "Aligner", "sample_reads", "sample_reads_edits", "BwtError", "NoSpace", "pack", "sw_batch", "search_resident", "peak_gather_gbs",
+__all__ = ["Index", "Batch", "Aligner", "PackedReads", "expand_compact", "sample_reads", "sample_reads_edits", "HIT16_DTYPE", "BwtError", "NoSpace", "pack", "sw_batch", "search_resident", "peak_gather_gbs",
            "peak_dpx_gops", "device_count", "HIT_DTYPE"]

@@ -1,10 +1,13 @@
 // The worker's inner loop (worker_bwt.erl:73-108) as a resident batch pipeline, and the C ABI on top of it.
 //
-//   upload (H2D)  ->  sga_kernel  ->  [sga_slow_kernel]  ->  windows  ->  sw_classify / sw_fast / [sw_general]
-//                 ->  emit (scan + gather into the caller-facing layout)  ->  download (D2H)
+//   upload (H2D: ASCII + offsets, or 2-bit packed words)  ->  [pack]  ->  sga_kernel  ->  sga_slow_kernel  ->  windows
+//                 ->  sw_classify / sw_wfa / sw_fast  ->  emit (scan + gather into the caller-facing layout)  ->  download (D2H)
 //
-// One bwt_batch owns its stream, device buffers and pinned staging, so several batches can be in flight on one
-// (immutable) index from different host threads.
+// A run is ENQUEUED as a whole: every kernel takes its counts from device memory and every buffer is sized by capacity,
+// so the host synchronises once, at the end, and then only looks at a handful of counters.  What the data rarely needs
+// (wide windows, rows that do not fit the difference coding, strings with 'N', capacity overflows) is a second,
+// synchronous round behind that.  One bwt_batch owns its stream, device buffers and pinned staging, so several batches
+// can be in flight on one (immutable) index from different host threads, and their kernels overlap on the device.
 #include <algorithm>
 #include <cstddef>
 #include <chrono>
@@ -14,6 +17,7 @@
 #include <thread>
 
 #include "common.cuh"
+#include "reads.cuh"
 #include "seed.cuh"
 #include "sw.cuh"
 
@@ -35,22 +39,6 @@ int dev_grow(T *&p, size_t &cap, size_t need, bool keep_slack = true) {
     return BWT_OK;
 }
 
-// offsets arrive as the caller has them: find the longest read and check that they do not decrease (the rebase to
-// 0 is a second kernel, so that nobody reads an element a neighbour has already rewritten)
-__global__ void prep_offsets_kernel(const int64_t *__restrict__ offs, int64_t n, uint32_t *__restrict__ info) {
-    int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    int64_t len = k < n ? offs[k + 1] - offs[k] : 0;
-    uint32_t l = len < 0 ? 0u : (len > (1 << 30) ? (1u << 30) : (uint32_t)len);
-    if (len < 0) atomicExch(info + 1, 1u);
-    for (int d = 16; d > 0; d >>= 1) l = max(l, __shfl_down_sync(0xFFFFFFFFu, l, d));
-    if ((threadIdx.x & 31) == 0 && l) atomicMax(info, l);
-}
-
-__global__ void rebase_offsets_kernel(int64_t *__restrict__ offs, int64_t n, int64_t base) {
-    int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (k <= n) offs[k] -= base;
-}
-
 // pipelined aligner: results of a chunk move to their place in the caller's arrays
 __global__ void rebase_result_kernel(int64_t *__restrict__ hit_off64, int64_t n, bwt_hit *__restrict__ hits, int64_t n_hits,
                                      int64_t hit_base, int64_t cig_base) {
@@ -58,36 +46,45 @@ __global__ void rebase_result_kernel(int64_t *__restrict__ hit_off64, int64_t n,
     if (k <= n) hit_off64[k] += hit_base;
     if (k < n_hits) hits[k].cigar_off += cig_base;
 }
-
-// windows of worker_bwt.erl:84-90: Ref_len = Lq + D, Start = S - Ref_len + 200 into the padded reference
-__global__ void windows_kernel(const Cluster *__restrict__ cl, uint32_t n, const int64_t *__restrict__ offs,
-                               uint64_t ref_len_padded, SwDesc *__restrict__ desc, SwOut *__restrict__ out) {
-    uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= n) return;
-    Cluster c = cl[k];
-    int64_t q0 = offs[c.read];
-    int32_t lq = (int32_t)(offs[c.read + 1] - q0);
-    int64_t ref_len = (int64_t)lq + c.d;
-    int64_t start = (int64_t)c.s - ref_len + BWT_REF_EXT;
-    SwDesc d;
-    d.q_off = q0; d.r_off = start; d.lq = lq; d.lr = (int32_t)ref_len;
-    desc[k] = d;
-    SwOut o;
-    o.score = 0; o.cigar_len = 0; o.cigar_off = 0;
-    // <<_:Start_pos/bytes, Ref_seq:Ref_len/bytes, _/binary>> = Ref  -> badmatch outside the binary
-    o.status = (start < 0 || (uint64_t)(start + ref_len) > ref_len_padded) ? BWT_HIT_WINDOW_OOR : -1;
-    out[k] = o;
+__global__ void rebase_result16_kernel(uint32_t *__restrict__ hit_off, int64_t n, bwt_hit16 *__restrict__ hits, int64_t n_hits,
+                                       uint32_t hit_base, uint32_t cig_base) {
+    int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k <= n) hit_off[k] += hit_base;
+    if (k < n_hits) hits[k].cigar_off += cig_base;
 }
 
-// per read: number of hits and CIGAR bytes (inputs of the two scans)
+// windows of worker_bwt.erl:84-90: Ref_len = Lq + D, Start = S - Ref_len + 200 into the padded reference
+__global__ void windows_kernel(const Cluster *__restrict__ cl, const uint32_t *__restrict__ n_ptr, const uint32_t *__restrict__ len,
+                               uint64_t ref_len_padded, SwDesc *__restrict__ desc, SwOut *__restrict__ out) {
+    const uint32_t n = *n_ptr;
+    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+        Cluster c = cl[k];
+        const int32_t lq = (int32_t)len[c.read];
+        const int64_t ref_len = (int64_t)lq + c.d;
+        const int64_t start = (int64_t)c.s - ref_len + BWT_REF_EXT;
+        SwDesc d;
+        d.r_off = start; d.read = c.read; d.lq = lq; d.lr = (int32_t)ref_len; d.pad = 0;
+        desc[k] = d;
+        SwOut o;
+        o.score = 0; o.cigar_len = 0; o.cigar_off = 0;
+        // <<_:Start_pos/bytes, Ref_seq:Ref_len/bytes, _/binary>> = Ref  -> badmatch outside the binary
+        o.status = (start < 0 || (uint64_t)(start + ref_len) > ref_len_padded) ? BWT_HIT_WINDOW_OOR : -1;
+        out[k] = o;
+    }
+}
+
+// per read: number of hits and CIGAR bytes (inputs of the two scans).  compact: "<Lq>M" CIGARs are not stored.
 __global__ void emit_count_kernel(const uint32_t *__restrict__ ncl, const uint32_t *__restrict__ cl_base,
-                                  const SwOut *__restrict__ out, int64_t n, uint32_t *__restrict__ hit_cnt,
+                                  const SwOut *__restrict__ out, int64_t n, int compact, uint32_t *__restrict__ hit_cnt,
                                   uint32_t *__restrict__ cig_cnt) {
     int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r > n) return;
     if (r == n) { hit_cnt[n] = 0; cig_cnt[n] = 0; return; }   // slot n turns into the total under the exclusive scan
     uint32_t c = ncl[r], b = cl_base[r], bytes = 0;
-    for (uint32_t k = 0; k < c; k++) bytes += (uint32_t)out[b + k].cigar_len;
+    for (uint32_t k = 0; k < c; k++) {
+        const SwOut o = out[b + k];
+        if (!(compact && (o.status & SW_FULL_M))) bytes += (uint32_t)o.cigar_len;
+    }
     hit_cnt[r] = c;
     cig_cnt[r] = bytes;
 }
@@ -98,7 +95,8 @@ __global__ void emit_kernel(const uint32_t *__restrict__ ncl, const uint32_t *__
                             const Cluster *__restrict__ cl, const SwDesc *__restrict__ desc,
                             const SwOut *__restrict__ out, const char *__restrict__ cig_tmp, int64_t n,
                             const uint32_t *__restrict__ hit_off, const uint32_t *__restrict__ cig_off, int64_t shift,
-                            int64_t *__restrict__ hit_off64, bwt_hit *__restrict__ hits, char *__restrict__ cigars) {
+                            int64_t *__restrict__ hit_off64, bwt_hit *__restrict__ hits, char *__restrict__ cigars,
+                            uint32_t hits_cap, uint32_t cig_cap) {
     int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r > n) return;
     if (r == n) { hit_off64[n] = hit_off[n]; return; }
@@ -113,12 +111,44 @@ __global__ void emit_kernel(const uint32_t *__restrict__ ncl, const uint32_t *__
         h.d = cc.d;
         h.pos = (int64_t)cc.s - (int64_t)desc[src].lr + shift;     // S - Ref_len + Shift (worker_bwt.erl:94)
         h.score = o.score;
-        h.status = o.status;
+        h.status = o.status & 0xFF;
         h.cigar_len = o.cigar_len;
         h.cigar_off = co;
-        hits[ho + k] = h;
-        for (int t = 0; t < o.cigar_len; t++) cigars[co + t] = cig_tmp[o.cigar_off + t];
+        if (ho + k < hits_cap) hits[ho + k] = h;
+        if ((uint64_t)co + (uint32_t)o.cigar_len <= cig_cap)
+            for (int t = 0; t < o.cigar_len; t++) cigars[co + t] = cig_tmp[o.cigar_off + t];
         co += (uint32_t)o.cigar_len;
+    }
+}
+
+// the same in the compact wire format (bwt_hit16, uint8 status, uint32 offsets)
+__global__ void emit16_kernel(const uint32_t *__restrict__ ncl, const uint32_t *__restrict__ cl_base,
+                              const Cluster *__restrict__ cl, const SwOut *__restrict__ out, const char *__restrict__ cig_tmp,
+                              const int32_t *__restrict__ read_status, int64_t n, const uint32_t *__restrict__ hit_off,
+                              const uint32_t *__restrict__ cig_off, uint8_t *__restrict__ status8, bwt_hit16 *__restrict__ hits,
+                              char *__restrict__ cigars, uint32_t hits_cap, uint32_t cig_cap, uint32_t *__restrict__ flags) {
+    int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    status8[r] = (uint8_t)read_status[r];
+    uint32_t c = ncl[r], b = cl_base[r], ho = hit_off[r], co = cig_off[r];
+    for (uint32_t k = 0; k < c; k++) {
+        uint32_t src = b + (c - 1 - k);
+        Cluster cc = cl[src];
+        SwOut o = out[src];
+        const bool full_m = (o.status & SW_FULL_M) != 0;
+        if (o.cigar_len > 65535 || (uint32_t)cc.d >= (1u << 28) || o.score > 32767 || o.score < -32768) atomicExch(flags, 1u);
+        bwt_hit16 h;
+        h.s = cc.s;
+        h.d_flags = ((uint32_t)cc.d & 0x0FFFFFFFu) | ((uint32_t)(o.status & 3) << 28) | (full_m ? BWT_HIT16_FULL_M : 0u);
+        h.score = (int16_t)o.score;
+        h.cigar_len = full_m ? (uint16_t)0 : (uint16_t)o.cigar_len;
+        h.cigar_off = full_m ? 0u : co;
+        if (ho + k < hits_cap) hits[ho + k] = h;
+        if (!full_m) {
+            if ((uint64_t)co + (uint32_t)o.cigar_len <= cig_cap)
+                for (int t = 0; t < o.cigar_len; t++) cigars[co + t] = cig_tmp[o.cigar_off + t];
+            co += (uint32_t)o.cigar_len;
+        }
     }
 }
 
@@ -139,7 +169,7 @@ __global__ void desc_from_offsets_kernel(const int64_t *__restrict__ qo, const i
     uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
     SwDesc d;
-    d.q_off = qo[k]; d.r_off = ro[k]; d.lq = (int32_t)(qo[k + 1] - qo[k]); d.lr = (int32_t)(ro[k + 1] - ro[k]);
+    d.r_off = ro[k]; d.read = k; d.lq = (int32_t)(qo[k + 1] - qo[k]); d.lr = (int32_t)(ro[k + 1] - ro[k]); d.pad = 0;
     desc[k] = d;
     SwOut o; o.score = 0; o.status = -1; o.cigar_len = 0; o.cigar_off = 0;
     out[k] = o;
@@ -157,19 +187,39 @@ __global__ void sw_pairs_emit_kernel(const SwOut *__restrict__ out, const char *
     uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
     SwOut o = out[k];
-    status[k] = o.status; score[k] = o.score; cig_off[k] = off[k]; cig_len[k] = o.cigar_len;
+    status[k] = o.status & 0xFF; score[k] = o.score; cig_off[k] = off[k]; cig_len[k] = o.cigar_len;
     for (int t = 0; t < o.cigar_len; t++) cigars[off[k] + t] = cig_tmp[o.cigar_off + t];
 }
 
+bool is_pinned(const void *p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+}
+
 }  // namespace
+
+// what the last lines of a run copy back, in one pinned block
+struct RunTotals {
+    uint32_t hits, cig_bytes;       // exclusive-scan totals of the emit stage
+    uint32_t info[2];               // [1]: the ASCII offsets decreased
+    uint32_t emit_flags;            // compact emit: a field did not fit bwt_hit16
+    uint32_t pad;
+};
 
 struct bwt_batch {
     bwt_index *ix = nullptr;
     cudaStream_t stream = nullptr;
     int64_t max_reads = 0, max_bytes = 0;
-    // inputs
-    uint8_t *d_reads = nullptr;
-    int64_t *d_offs = nullptr;
+    // reads
+    uint8_t *d_ascii = nullptr;  size_t ascii_cap = 0;
+    int64_t *d_aoff = nullptr;
+    uint32_t *d_pk = nullptr;    size_t pk_cap = 0;        // words
+    uint32_t *d_woff = nullptr, *d_len = nullptr, *d_exc = nullptr, *d_exc_idx = nullptr;
+    size_t exc_cap = 0;
+    uint16_t *d_len16 = nullptr;
+    DevReads R{};
+    bool need_pack = false;               // ASCII batch: the run packs it first
     uint8_t *h_stage = nullptr;           // pinned staging for pageable callers
     size_t h_stage_bytes = 0;
     int64_t n = 0, n_bytes = 0;
@@ -178,29 +228,26 @@ struct bwt_batch {
     int32_t *d_read_status = nullptr;
     uint32_t *d_ncl = nullptr, *d_cl_base = nullptr, *d_hit_off = nullptr, *d_cig_off = nullptr, *d_scan_tmp = nullptr;
     int64_t *d_hit_off64 = nullptr;
+    uint8_t *d_status8 = nullptr;
     // clusters
     Cluster *d_clusters = nullptr;        // dense list (what windows / emit read)
     Cluster *d_clusters_sparse = nullptr; // the sub-list regions sga_kernel appends to (launch_sga_finish packs them)
     size_t cl_cap = 0, cl_sparse_cap = 0;
     SlowRead *d_slow = nullptr;
     uint32_t slow_cap = 0;
-    uint64_t *d_slow_off = nullptr;
-    size_t slow_off_cap = 0;
     uint32_t *d_slow_scratch = nullptr;
     size_t slow_scratch_cap = 0;
     SeedCounters *d_ctr = nullptr, *h_ctr = nullptr;
-    uint32_t *d_totals = nullptr, *h_totals = nullptr;   // [0] hits, [1] cigar bytes
+    RunTotals *d_totals = nullptr, *h_totals = nullptr;
     SwStage sw;
-    // outputs
-    bwt_hit *d_hits = nullptr;
-    size_t hits_cap = 0;
-    char *d_cigars = nullptr;
-    size_t cigars_cap = 0;
+    // outputs (sized by capacity: cl_cap hits, sw.cig_cap CIGAR bytes)
+    bwt_hit *d_hits = nullptr;     size_t hits_cap = 0;
+    bwt_hit16 *d_hits16 = nullptr; size_t hits16_cap = 0;
+    char *d_cigars = nullptr;      size_t cigars_cap = 0;
     int64_t n_hits = 0, cigar_bytes = 0;
-    bool has_result = false;
-    cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    bool has_result = false, result_compact = false;
+    cudaEvent_t ev[10] = {};
     bwt_stats stats{};
-    std::mutex *stage_token = nullptr;    // set by the pipelined aligner: one chunk at a time inside a stage
     cudaStream_t dl_stream = nullptr;     // the aligner's D2H copies: the next chunk's upload does not wait for them
     cudaEvent_t ev_run_done = nullptr, ev_dl0 = nullptr, ev_dl1 = nullptr;
     bool dl_pending = false;
@@ -214,9 +261,15 @@ static int batch_alloc(bwt_batch *b) {
     CU_TRY(cudaEventCreate(&b->ev_run_done));
     CU_TRY(cudaEventCreate(&b->ev_dl0));
     CU_TRY(cudaEventCreate(&b->ev_dl1));
-    CU_TRY(cudaMalloc(&b->d_reads, (size_t)b->max_bytes + 16));
-    CU_TRY(cudaMalloc(&b->d_offs, (size_t)(nr + 1) * sizeof(int64_t)));
+    b->pk_cap = (size_t)b->max_bytes / 16 + (size_t)nr + 2;
+    CU_TRY(cudaMalloc(&b->d_pk, b->pk_cap * sizeof(uint32_t)));
+    CU_TRY(cudaMalloc(&b->d_aoff, (size_t)(nr + 1) * sizeof(int64_t)));
+    CU_TRY(cudaMalloc(&b->d_woff, (size_t)(nr + 1) * sizeof(uint32_t)));
+    CU_TRY(cudaMalloc(&b->d_len, (size_t)(nr + 1) * sizeof(uint32_t)));
+    CU_TRY(cudaMalloc(&b->d_len16, (size_t)(nr + 1) * sizeof(uint16_t)));
+    CU_TRY(cudaMalloc(&b->d_exc, (size_t)(nr / 32 + 2) * sizeof(uint32_t)));
     CU_TRY(cudaMalloc(&b->d_read_status, (size_t)nr * sizeof(int32_t)));
+    CU_TRY(cudaMalloc(&b->d_status8, (size_t)nr));
     CU_TRY(cudaMalloc(&b->d_ncl, (size_t)nr * sizeof(uint32_t)));
     CU_TRY(cudaMalloc(&b->d_cl_base, (size_t)nr * sizeof(uint32_t)));
     CU_TRY(cudaMalloc(&b->d_hit_off, (size_t)(nr + 1) * sizeof(uint32_t)));
@@ -225,12 +278,13 @@ static int batch_alloc(bwt_batch *b) {
     CU_TRY(cudaMalloc(&b->d_scan_tmp, scan_tmp_words((size_t)nr + 1) * sizeof(uint32_t)));
     CU_TRY(cudaMalloc(&b->d_ctr, sizeof(SeedCounters)));
     CU_TRY(cudaMallocHost(&b->h_ctr, sizeof(SeedCounters)));
-    CU_TRY(cudaMalloc(&b->d_totals, 2 * sizeof(uint32_t)));
-    CU_TRY(cudaMallocHost(&b->h_totals, 2 * sizeof(uint32_t)));
-    b->slow_cap = (uint32_t)std::min<int64_t>(nr, 1 << 20);
+    CU_TRY(cudaMalloc(&b->d_totals, sizeof(RunTotals)));
+    CU_TRY(cudaMallocHost(&b->h_totals, sizeof(RunTotals)));
+    b->slow_cap = (uint32_t)std::min<int64_t>(nr, 1 << 16);
     CU_TRY(cudaMalloc(&b->d_slow, (size_t)b->slow_cap * sizeof(SlowRead)));
+    BWT_TRY(dev_grow(b->d_slow_scratch, b->slow_scratch_cap, (size_t)1 << 20, false));
     b->sw.device = b->ix->device;
-    size_t want_cl = (size_t)std::max<int64_t>(4 * nr, 4096);
+    size_t want_cl = (size_t)std::max<int64_t>(2 * nr, 4096);
     BWT_TRY(dev_grow(b->d_clusters, b->cl_cap, want_cl, false));
     BWT_TRY(dev_grow(b->d_clusters_sparse, b->cl_sparse_cap, b->cl_cap, false));
     BWT_TRY(sw_stage_reserve(b->sw, (uint32_t)b->cl_cap));
@@ -257,10 +311,12 @@ extern "C" int bwt_batch_destroy(bwt_batch *b) {
     if (!b) return BWT_OK;
     cudaSetDevice(b->ix->device);
     if (b->stream) cudaStreamSynchronize(b->stream);
-    cudaFree(b->d_reads); cudaFree(b->d_offs); cudaFree(b->d_read_status); cudaFree(b->d_ncl); cudaFree(b->d_cl_base);
+    if (b->dl_stream) cudaStreamSynchronize(b->dl_stream);
+    cudaFree(b->d_ascii); cudaFree(b->d_aoff); cudaFree(b->d_pk); cudaFree(b->d_woff); cudaFree(b->d_len); cudaFree(b->d_len16);
+    cudaFree(b->d_exc); cudaFree(b->d_exc_idx); cudaFree(b->d_read_status); cudaFree(b->d_status8); cudaFree(b->d_ncl); cudaFree(b->d_cl_base);
     cudaFree(b->d_hit_off); cudaFree(b->d_cig_off); cudaFree(b->d_hit_off64); cudaFree(b->d_scan_tmp);
-    cudaFree(b->d_clusters); cudaFree(b->d_clusters_sparse); cudaFree(b->d_slow); cudaFree(b->d_slow_off); cudaFree(b->d_slow_scratch);
-    cudaFree(b->d_ctr); cudaFree(b->d_totals); cudaFree(b->d_hits); cudaFree(b->d_cigars);
+    cudaFree(b->d_clusters); cudaFree(b->d_clusters_sparse); cudaFree(b->d_slow); cudaFree(b->d_slow_scratch);
+    cudaFree(b->d_ctr); cudaFree(b->d_totals); cudaFree(b->d_hits); cudaFree(b->d_hits16); cudaFree(b->d_cigars);
     if (b->h_ctr) cudaFreeHost(b->h_ctr);
     if (b->h_totals) cudaFreeHost(b->h_totals);
     if (b->h_stage) cudaFreeHost(b->h_stage);
@@ -269,43 +325,53 @@ extern "C" int bwt_batch_destroy(bwt_batch *b) {
     if (b->ev_run_done) cudaEventDestroy(b->ev_run_done);
     if (b->ev_dl0) cudaEventDestroy(b->ev_dl0);
     if (b->ev_dl1) cudaEventDestroy(b->ev_dl1);
-    if (b->dl_stream) { cudaStreamSynchronize(b->dl_stream); cudaStreamDestroy(b->dl_stream); }
+    if (b->dl_stream) cudaStreamDestroy(b->dl_stream);
     if (b->stream) cudaStreamDestroy(b->stream);
     delete b;
     return BWT_OK;
 }
 
-static bool is_pinned(const void *p) {
-    cudaPointerAttributes a;
-    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
-    return a.type == cudaMemoryTypeHost;
+static int stage_reserve(bwt_batch *b, size_t need) {
+    if (need <= b->h_stage_bytes) return BWT_OK;
+    if (b->h_stage) cudaFreeHost(b->h_stage);
+    b->h_stage = nullptr;
+    b->h_stage_bytes = need + need / 4 + 4096;
+    CU_TRY(cudaMallocHost(&b->h_stage, b->h_stage_bytes));
+    return BWT_OK;
 }
 
+static void view_reset(bwt_batch *b) {
+    DevReads &R = b->R;
+    R.pk = b->d_pk; R.woff = b->d_woff; R.len = b->d_len; R.exc = b->d_exc;
+    R.ascii = b->d_ascii; R.aoff = b->d_aoff; R.exc_idx = b->d_exc_idx;
+    R.n_exc = 0; R.ascii_full = 0; R.aoff_base = 0; R.exc_base = 0;
+}
+
+// ASCII batch: the bytes and the offsets go up as they are; lengths, word offsets and the 2-bit words are made on the
+// device (the packing itself at the start of the run: it is part of the work on an ASCII batch).  No synchronisation
+// unless the caller's memory is pageable (then it is staged through pinned memory, which must not be reused too early).
 extern "C" int bwt_batch_upload(bwt_batch *b, const uint8_t *reads, const int64_t *offsets, int64_t n) {
     if (!b || !offsets || n < 0 || (n > 0 && !reads)) { bwt_set_error("bwt_batch_upload: bad argument"); return BWT_ERR_ARG; }
     if (n > b->max_reads) { bwt_set_error("batch of %lld reads exceeds max_reads %lld", (long long)n, (long long)b->max_reads); return BWT_ERR_ARG; }
-    int64_t base = offsets[0], bytes = offsets[n] - base;
+    const int64_t base = offsets[0], bytes = offsets[n] - base;
     if (bytes < 0 || bytes > b->max_bytes) { bwt_set_error("batch of %lld read bytes exceeds max_read_bytes %lld", (long long)bytes, (long long)b->max_bytes); return BWT_ERR_ARG; }
-    CU_TRY(cudaSetDevice(b->ix->device));
-    // pageable callers are staged through pinned memory; the offsets are rebased and checked on the device
-    const bool pin_r = bytes == 0 || is_pinned(reads + base), pin_o = is_pinned(offsets);
-    size_t need = (pin_r ? 0 : (size_t)bytes) + (pin_o ? 0 : (size_t)(n + 1) * sizeof(int64_t));
-    if (need > b->h_stage_bytes) {
-        if (b->h_stage) cudaFreeHost(b->h_stage);
-        b->h_stage = nullptr;
-        b->h_stage_bytes = need + need / 4 + 4096;
-        CU_TRY(cudaMallocHost(&b->h_stage, b->h_stage_bytes));
+    // the longest read and the monotonic check on the host: the offsets are here anyway
+    int64_t maxlen = 0, words = 0;
+    for (int64_t k = 0; k < n; k++) {
+        const int64_t l = offsets[k + 1] - offsets[k];
+        if (l < 0) { bwt_set_error("offsets must be non-decreasing"); return BWT_ERR_ARG; }
+        maxlen = std::max(maxlen, l);
+        if (l <= BWT_PACK_MAX) words += (l + 15) >> 4;
     }
+    CU_TRY(cudaSetDevice(b->ix->device));
+    if ((size_t)words + 2 > b->pk_cap) BWT_TRY(dev_grow(b->d_pk, b->pk_cap, (size_t)words + 2));
+    if ((size_t)bytes + 16 > b->ascii_cap) BWT_TRY(dev_grow(b->d_ascii, b->ascii_cap, (size_t)bytes + 16, false));
+    const bool pin_r = bytes == 0 || is_pinned(reads + base), pin_o = is_pinned(offsets);
+    BWT_TRY(stage_reserve(b, (pin_r ? 0 : (size_t)bytes) + (pin_o ? 0 : (size_t)(n + 1) * sizeof(int64_t))));
     const int64_t *src_o = offsets;
     if (!pin_o) { memcpy(b->h_stage, offsets, (size_t)(n + 1) * sizeof(int64_t)); src_o = reinterpret_cast<const int64_t *>(b->h_stage); }
     CU_TRY(cudaEventRecord(b->ev[4], b->stream));
-    CU_TRY(cudaMemcpyAsync(b->d_offs, src_o, (size_t)(n + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, b->stream));
-    CU_TRY(cudaMemsetAsync(b->d_totals, 0, 2 * sizeof(uint32_t), b->stream));
-    unsigned blocks = (unsigned)((n + 1 + 255) / 256);
-    prep_offsets_kernel<<<blocks, 256, 0, b->stream>>>(b->d_offs, n, b->d_totals);
-    rebase_offsets_kernel<<<blocks, 256, 0, b->stream>>>(b->d_offs, n, base);
-    CU_TRY(cudaGetLastError());
-    CU_TRY(cudaMemcpyAsync(b->h_totals, b->d_totals, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, b->stream));
+    CU_TRY(cudaMemcpyAsync(b->d_aoff, src_o, (size_t)(n + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, b->stream));
     if (bytes > 0) {
         const uint8_t *src = reads + base;
         if (!pin_r) {
@@ -313,173 +379,272 @@ extern "C" int bwt_batch_upload(bwt_batch *b, const uint8_t *reads, const int64_
             memcpy(sr, src, (size_t)bytes);
             src = sr;
         }
-        CU_TRY(cudaMemcpyAsync(b->d_reads, src, (size_t)bytes, cudaMemcpyHostToDevice, b->stream));
+        CU_TRY(cudaMemcpyAsync(b->d_ascii, src, (size_t)bytes, cudaMemcpyHostToDevice, b->stream));
     }
     CU_TRY(cudaEventRecord(b->ev[5], b->stream));
-    CU_TRY(cudaStreamSynchronize(b->stream));
-    if (b->h_totals[1]) { bwt_set_error("offsets must be non-decreasing"); return BWT_ERR_ARG; }
-    int maxlen = (int)b->h_totals[0];
-    float ms = 0;
-    cudaEventElapsedTime(&ms, b->ev[4], b->ev[5]);
-    b->stats.ms_h2d = ms;
-    b->n = n; b->n_bytes = bytes; b->max_read_len = maxlen;
+    view_reset(b);
+    b->R.ascii_full = 1; b->R.aoff_base = base;
+    b->need_pack = true;
+    b->n = n; b->n_bytes = bytes; b->max_read_len = (int)std::min<int64_t>(maxlen, 1 << 30);
     b->has_result = false;
+    if (!pin_r || !pin_o) CU_TRY(cudaStreamSynchronize(b->stream));     // the staging buffer is free again
     return BWT_OK;
 }
 
-// seeding stage with capacity retries; on return h_ctr holds the counters and clusters are complete
-static int run_seed_stage(bwt_batch *b) {
-    DevIndex ix = b->ix->dv;
-    // one lookup for the short subsequence at the front of the reads (8 + Lq mod 8 characters) as well
-    const int tail = b->max_read_len >= 2 * BWT_MIN_LEN ? BWT_MIN_LEN + b->max_read_len % BWT_MIN_LEN : 0;
-    if (const uint2 *t = index_tail_table(b->ix, tail)) { ix.kmer_tail = t; ix.tail_k = tail; }
-    for (int attempt = 0; attempt < 6; attempt++) {
+// Packed batch (bwt_pack_reads / a FASTQ ingest that packs): words, lengths and the flagged reads' ASCII go up; a
+// quarter of the bytes of an ASCII batch.  lo/hi select reads [lo, hi) of p (the pipelined aligner's chunks);
+// word_base = words of p before read lo.
+static int batch_upload_packed_range(bwt_batch *b, const bwt_packed_reads *p, int64_t lo, int64_t hi, int64_t word_base,
+                                     int64_t words, int maxlen) {
+    const int64_t n = hi - lo;
+    if (n > b->max_reads) { bwt_set_error("batch of %lld reads exceeds max_reads %lld", (long long)n, (long long)b->max_reads); return BWT_ERR_ARG; }
+    CU_TRY(cudaSetDevice(b->ix->device));
+    if ((size_t)words + 2 > b->pk_cap) BWT_TRY(dev_grow(b->d_pk, b->pk_cap, (size_t)words + 2));
+    // the flagged reads of the range
+    int64_t e0 = 0, e1 = 0;
+    if (p->n_exc > 0) {
+        e0 = std::lower_bound(p->exc_idx, p->exc_idx + p->n_exc, (uint32_t)lo) - p->exc_idx;
+        e1 = std::lower_bound(p->exc_idx, p->exc_idx + p->n_exc, (uint32_t)hi) - p->exc_idx;
+    }
+    const int64_t ne = e1 - e0, eb = ne ? p->exc_off[e1] - p->exc_off[e0] : 0;
+    if ((size_t)ne + 1 > b->exc_cap) BWT_TRY(dev_grow(b->d_exc_idx, b->exc_cap, (size_t)ne + 1));
+    if ((size_t)eb + 16 > b->ascii_cap) BWT_TRY(dev_grow(b->d_ascii, b->ascii_cap, (size_t)eb + 16));
+    if (ne > b->max_reads) { bwt_set_error("more flagged reads than reads"); return BWT_ERR_ARG; }
+    const bool pinned = is_pinned(p->words) && (p->fixed_len > 0 || is_pinned(p->lens)) && (ne == 0 || (is_pinned(p->exc_idx) && is_pinned(p->exc_off) && is_pinned(p->exc_ascii)));
+    const uint32_t *src_w = p->words + word_base;
+    const uint16_t *src_l = p->fixed_len > 0 ? nullptr : p->lens + lo;
+    const uint32_t *src_ei = ne ? p->exc_idx + e0 : nullptr;
+    const int64_t *src_eo = ne ? p->exc_off + e0 : nullptr;
+    const uint8_t *src_ea = ne ? p->exc_ascii + p->exc_off[e0] : nullptr;
+    if (!pinned) {
+        const size_t bw = (size_t)(words + 1) * 4, bl = src_l ? (size_t)n * 2 : 0, bi = (size_t)ne * 4, bo = (size_t)(ne ? ne + 1 : 0) * 8;
+        BWT_TRY(stage_reserve(b, bw + bl + bi + bo + (size_t)eb + 64));
+        uint8_t *s = b->h_stage;
+        memcpy(s, src_w, bw); src_w = (const uint32_t *)s; s += (bw + 7) & ~(size_t)7;
+        if (ne) { memcpy(s, src_eo, bo); src_eo = (const int64_t *)s; s += bo; }
+        if (ne) { memcpy(s, src_ei, bi); src_ei = (const uint32_t *)s; s += (bi + 7) & ~(size_t)7; }
+        if (src_l) { memcpy(s, src_l, bl); src_l = (const uint16_t *)s; s += (bl + 7) & ~(size_t)7; }
+        if (ne) { memcpy(s, src_ea, (size_t)eb); src_ea = s; }
+    }
+    CU_TRY(cudaEventRecord(b->ev[4], b->stream));
+    CU_TRY(cudaMemcpyAsync(b->d_pk, src_w, (size_t)(words + 1) * 4, cudaMemcpyHostToDevice, b->stream));   // + the pad word
+    if (src_l) CU_TRY(cudaMemcpyAsync(b->d_len16, src_l, (size_t)n * 2, cudaMemcpyHostToDevice, b->stream));
+    if (ne) {
+        CU_TRY(cudaMemcpyAsync(b->d_exc_idx, src_ei, (size_t)ne * 4, cudaMemcpyHostToDevice, b->stream));
+        CU_TRY(cudaMemcpyAsync(b->d_aoff, src_eo, (size_t)(ne + 1) * 8, cudaMemcpyHostToDevice, b->stream));
+        CU_TRY(cudaMemcpyAsync(b->d_ascii, src_ea, (size_t)eb, cudaMemcpyHostToDevice, b->stream));
+    }
+    CU_TRY(cudaEventRecord(b->ev[5], b->stream));
+    uint32_t launches = 0;
+    if (p->fixed_len > 0) BWT_TRY(reads_geom_fixed(n, (uint32_t)p->fixed_len, b->d_len, b->d_woff, b->stream, &launches));
+    else BWT_TRY(reads_geom_from_len16(b->d_len16, n, b->d_len, b->d_woff, b->d_scan_tmp, b->stream, &launches));
+    view_reset(b);
+    b->R.n_exc = (uint32_t)ne; b->R.exc_base = (uint32_t)lo; b->R.aoff_base = ne ? p->exc_off[e0] : 0;
+    BWT_TRY(reads_exc_scatter(b->d_exc_idx, (uint32_t)ne, (uint32_t)lo, n, b->d_exc, b->stream, &launches));
+    b->need_pack = false;
+    b->n = n; b->n_bytes = words * 4; b->max_read_len = maxlen;
+    b->has_result = false;
+    if (!pinned) CU_TRY(cudaStreamSynchronize(b->stream));
+    return BWT_OK;
+}
+
+static int packed_check(const bwt_packed_reads *p) {
+    if (!p || p->n < 0 || p->n >= (1ll << 31) || (p->n > 0 && !p->words) || (p->fixed_len <= 0 && p->n > 0 && !p->lens) || p->n_exc < 0 ||
+        (p->n_exc > 0 && (!p->exc_idx || !p->exc_off || !p->exc_ascii)) || p->fixed_len > 65535) {
+        bwt_set_error("bwt_packed_reads: bad argument");
+        return BWT_ERR_ARG;
+    }
+    return BWT_OK;
+}
+
+// words and longest read of reads [lo, hi) of a packed batch
+static void packed_geom(const bwt_packed_reads *p, int64_t lo, int64_t hi, int64_t *words, int *maxlen) {
+    if (p->fixed_len > 0) {
+        *words = (hi - lo) * (p->fixed_len > BWT_PACK_MAX ? 0 : (p->fixed_len + 15) >> 4);
+        *maxlen = p->fixed_len;
+        return;
+    }
+    int64_t w = 0;
+    int m = 0;
+    for (int64_t r = lo; r < hi; r++) {
+        const int l = p->lens[r];
+        m = std::max(m, l);
+        if (l <= BWT_PACK_MAX) w += (l + 15) >> 4;
+    }
+    *words = w; *maxlen = m;
+}
+
+extern "C" int bwt_batch_upload_packed(bwt_batch *b, const bwt_packed_reads *p) {
+    if (!b) { bwt_set_error("bwt_batch_upload_packed: null batch"); return BWT_ERR_ARG; }
+    BWT_TRY(packed_check(p));
+    int64_t words;
+    int maxlen;
+    packed_geom(p, 0, p->n, &words, &maxlen);
+    return batch_upload_packed_range(b, p, 0, p->n, 0, words, maxlen);
+}
+
+// ---- one run ------------------------------------------------------------------------------------------------------
+
+// everything up to the dense cluster list, enqueued
+static int enqueue_seed_stage(bwt_batch *b, uint32_t cl_cap) {
+    const DevIndex &ix = b->ix->dv;
+    CU_TRY(cudaMemsetAsync(b->d_ctr, 0, sizeof(SeedCounters), b->stream));
+    CU_TRY(cudaEventRecord(b->ev[6], b->stream));
+    BWT_TRY(launch_sga(ix, b->R, b->n, b->max_read_len, b->d_read_status, b->d_ncl, b->d_cl_base,
+                       b->d_clusters_sparse, cl_cap, b->d_slow, b->slow_cap, b->d_ctr, b->stream));
+    CU_TRY(cudaEventRecord(b->ev[7], b->stream));
+    // reads whose seed ends did not fit on chip (a few blocks that leave at once when there are none)
+    BWT_TRY(launch_sga_slow(ix, b->R, b->d_slow, b->slow_cap, b->d_slow_scratch, b->slow_scratch_cap, b->d_read_status,
+                            b->d_ncl, b->d_cl_base, b->d_clusters_sparse, cl_cap, b->d_ctr, b->stream));
+    b->stats.launches += 2;
+    // sub-lists -> dense cluster list, dense cl_base, n_clusters
+    return launch_sga_finish(b->d_clusters_sparse, b->d_clusters, cl_cap, b->d_cl_base, b->d_ncl, b->n, b->d_ctr, b->stream,
+                             &b->stats.launches);
+}
+
+static int enqueue_emit_stage(bwt_batch *b, bool compact) {
+    const int64_t n = b->n;
+    const unsigned blocks = (unsigned)((n + 1 + 255) / 256);
+    const size_t hcap = b->cl_cap, ccap = (size_t)b->sw.cig_cap + 16;
+    if (compact) BWT_TRY(dev_grow(b->d_hits16, b->hits16_cap, hcap, false));
+    else BWT_TRY(dev_grow(b->d_hits, b->hits_cap, hcap, false));
+    BWT_TRY(dev_grow(b->d_cigars, b->cigars_cap, ccap, false));
+    emit_count_kernel<<<blocks, 256, 0, b->stream>>>(b->d_ncl, b->d_cl_base, b->sw.d_out, n, compact ? 1 : 0, b->d_hit_off, b->d_cig_off);
+    b->stats.launches += 1;
+    CU_TRY(cudaGetLastError());
+    // element n of an exclusive scan over n+1 items is the total (item n is written as 0 above)
+    BWT_TRY(exclusive_scan_u32(b->d_hit_off, (size_t)n + 1, b->d_scan_tmp, &b->d_totals->hits, b->stream, &b->stats.launches));
+    BWT_TRY(exclusive_scan_u32(b->d_cig_off, (size_t)n + 1, b->d_scan_tmp, &b->d_totals->cig_bytes, b->stream, &b->stats.launches));
+    if (compact)
+        emit16_kernel<<<blocks, 256, 0, b->stream>>>(b->d_ncl, b->d_cl_base, b->d_clusters, b->sw.d_out, b->sw.d_cig_tmp, b->d_read_status, n,
+                                                     b->d_hit_off, b->d_cig_off, b->d_status8, b->d_hits16, b->d_cigars,
+                                                     (uint32_t)std::min<size_t>(b->hits16_cap, 0xFFFFFFFFu), (uint32_t)std::min<size_t>(b->cigars_cap, 0xFFFFFFFFu),
+                                                     &b->d_totals->emit_flags);
+    else
+        emit_kernel<<<blocks, 256, 0, b->stream>>>(b->d_ncl, b->d_cl_base, b->d_clusters, b->sw.d_desc, b->sw.d_out,
+                                                   b->sw.d_cig_tmp, n, b->d_hit_off, b->d_cig_off, b->ix->shift,
+                                                   b->d_hit_off64, b->d_hits, b->d_cigars,
+                                                   (uint32_t)std::min<size_t>(b->hits_cap, 0xFFFFFFFFu), (uint32_t)std::min<size_t>(b->cigars_cap, 0xFFFFFFFFu));
+    b->stats.launches += 1;
+    CU_TRY(cudaGetLastError());
+    return BWT_OK;
+}
+
+static int run_core(bwt_batch *b, bool with_sw, bool compact) {
+    if (!b) { bwt_set_error("null batch"); return BWT_ERR_ARG; }
+    CU_TRY(cudaSetDevice(b->ix->device));
+    const float h2d = b->stats.ms_h2d;
+    memset(&b->stats, 0, sizeof b->stats);
+    b->stats.ms_h2d = h2d;
+    b->sw.launches = 0;
+    b->n_hits = 0; b->cigar_bytes = 0;
+    b->has_result = false;
+    const DevIndex &ix = b->ix->dv;
+    const int64_t n = b->n;
+    if (n == 0) {
+        memset(b->h_ctr, 0, sizeof(SeedCounters));
+        memset(b->sw.h_ctr, 0, sizeof(SwCounters));
+        b->stats.reads = 0;
+        b->has_result = with_sw; b->result_compact = compact;
+        return BWT_OK;
+    }
+    for (int attempt = 0; attempt < 8; attempt++) {
         BWT_TRY(dev_grow(b->d_clusters_sparse, b->cl_sparse_cap, b->cl_cap, false));
+        BWT_TRY(sw_stage_reserve(b->sw, (uint32_t)b->cl_cap));
         const uint32_t cl_cap = (uint32_t)std::min<size_t>(std::min(b->cl_cap, b->cl_sparse_cap), 0xFFFFFFF0u);
-        CU_TRY(cudaMemsetAsync(b->d_ctr, 0, sizeof(SeedCounters), b->stream));
-        CU_TRY(cudaEventRecord(b->ev[6], b->stream));
-        BWT_TRY(launch_sga(ix, b->d_reads, b->d_offs, b->n, b->max_read_len, b->d_read_status, b->d_ncl, b->d_cl_base,
-                           b->d_clusters_sparse, cl_cap, b->d_slow, b->slow_cap, b->d_ctr, b->stream));
-        CU_TRY(cudaEventRecord(b->ev[7], b->stream));
-        b->stats.launches += 1;
-        // only the slow-read count is needed on the host now (the first 64 bytes of the counters)
+        b->stats.launches = 0; b->sw.launches = 0;
+        CU_TRY(cudaMemsetAsync(b->d_totals, 0, sizeof(RunTotals), b->stream));
+        CU_TRY(cudaEventRecord(b->ev[0], b->stream));
+        if (b->need_pack) {           // ASCII batch: lengths, word offsets, 2-bit words (part of the work on such a batch)
+            BWT_TRY(reads_geom_from_ascii(b->d_aoff, n, b->d_len, b->d_woff, b->d_scan_tmp, b->d_totals->info, b->stream, &b->stats.launches));
+            BWT_TRY(reads_pack_device(b->d_ascii, b->d_aoff, b->R.aoff_base, n, b->d_len, b->d_woff, b->d_pk, b->d_exc, b->stream, &b->stats.launches));
+        }
+        BWT_TRY(enqueue_seed_stage(b, cl_cap));
+        CU_TRY(cudaEventRecord(b->ev[1], b->stream));
+        if (with_sw) {
+            windows_kernel<<<148 * 8, 256, 0, b->stream>>>(b->d_clusters, &b->d_ctr->n_clusters, b->d_len, ix.ref_len_padded, b->sw.d_desc, b->sw.d_out);
+            b->stats.launches += 1;
+            K_CHECK(b->stream, "windows_kernel");
+            BWT_TRY(sw_stage_enqueue(b->sw, b->R, ix.ref, ix.ref2, ix.refx, &b->d_ctr->n_clusters, cl_cap, b->max_read_len, b->stream));
+            CU_TRY(cudaMemcpyAsync(b->sw.h_ctr, b->sw.d_ctr, sizeof(SwCounters), cudaMemcpyDeviceToHost, b->stream));
+            CU_TRY(cudaEventRecord(b->ev[2], b->stream));
+            BWT_TRY(enqueue_emit_stage(b, compact));
+        } else {
+            CU_TRY(cudaEventRecord(b->ev[2], b->stream));
+        }
+        CU_TRY(cudaEventRecord(b->ev[3], b->stream));
         CU_TRY(cudaMemcpyAsync(b->h_ctr, b->d_ctr, offsetof(SeedCounters, dense_base), cudaMemcpyDeviceToHost, b->stream));
-        CU_TRY(cudaStreamSynchronize(b->stream));
-        cudaEventElapsedTime(&b->stats.ms_sga_kernel, b->ev[6], b->ev[7]);
-        uint32_t n_slow = b->h_ctr->n_slow;
-        if (n_slow > b->slow_cap) {          // cannot happen with slow_cap = max_reads unless capped at 2^20
+        CU_TRY(cudaMemcpyAsync(b->h_totals, b->d_totals, sizeof(RunTotals), cudaMemcpyDeviceToHost, b->stream));
+        CU_TRY(cudaStreamSynchronize(b->stream));                      // the one synchronisation of a run
+        if (b->h_totals->info[1]) { bwt_set_error("offsets must be non-decreasing"); return BWT_ERR_ARG; }
+        // capacity overflows of the seeding stage: grow and run again (rare: the capacities start generous)
+        const SeedCounters &sc = *b->h_ctr;
+        if (sc.n_slow > b->slow_cap) {
             cudaFree(b->d_slow); b->d_slow = nullptr;
-            b->slow_cap = n_slow + 1024;
+            b->slow_cap = sc.n_slow + sc.n_slow / 4 + 1024;
             CU_TRY(cudaMalloc(&b->d_slow, (size_t)b->slow_cap * sizeof(SlowRead)));
             continue;
         }
-        if (n_slow > 0 && !b->h_ctr->cluster_overflow) {
-            std::vector<SlowRead> sl(n_slow);
-            CU_TRY(cudaMemcpy(sl.data(), b->d_slow, n_slow * sizeof(SlowRead), cudaMemcpyDeviceToHost));
-            std::vector<uint64_t> off(n_slow + 1);
-            off[0] = 0;
-            for (uint32_t k = 0; k < n_slow; k++) {
-                uint64_t p = 1;
-                while (p < sl[k].seeds) p <<= 1;
-                off[k + 1] = off[k] + p;
-            }
-            BWT_TRY(dev_grow(b->d_slow_off, b->slow_off_cap, (size_t)n_slow + 1));
-            BWT_TRY(dev_grow(b->d_slow_scratch, b->slow_scratch_cap, (size_t)off[n_slow]));
-            CU_TRY(cudaMemcpyAsync(b->d_slow_off, off.data(), (n_slow + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, b->stream));
-            BWT_TRY(launch_sga_slow(ix, b->d_reads, b->d_offs, b->d_slow, b->d_slow_off, n_slow, b->d_slow_scratch,
-                                    b->d_read_status, b->d_ncl, b->d_cl_base, b->d_clusters_sparse, cl_cap, b->d_ctr, b->stream));
-            b->stats.launches += 1;
+        if (sc.scratch_overflow) {
+            BWT_TRY(dev_grow(b->d_slow_scratch, b->slow_scratch_cap, (size_t)std::max<unsigned long long>(sc.scratch_used, 2 * b->slow_scratch_cap)));
+            continue;
         }
-        // sub-lists -> dense cluster list, dense cl_base, n_clusters
-        BWT_TRY(launch_sga_finish(b->d_clusters_sparse, b->d_clusters, cl_cap, b->d_cl_base, b->d_ncl, b->n, b->d_ctr, b->stream,
-                                  &b->stats.launches));
-        CU_TRY(cudaMemcpyAsync(b->h_ctr, b->d_ctr, offsetof(SeedCounters, dense_base), cudaMemcpyDeviceToHost, b->stream));
-        CU_TRY(cudaStreamSynchronize(b->stream));
-        if (!b->h_ctr->cluster_overflow) return BWT_OK;
-        // a sub-list ran out of room: n_clusters is a lower bound of what is needed (refused reads not counted in full);
-        // the regions are equal shares, so ask for twice the total
-        size_t want = (size_t)std::max<uint64_t>(b->h_ctr->n_clusters, b->cl_cap) * 2 + 4096;
-        {   // and every region must hold the fullest sub-list (one read with very many clusters fills a single region)
+        if (sc.cluster_overflow) {
+            // a sub-list ran out of room: n_clusters is a lower bound of what is needed (refused reads not counted in full);
+            // the regions are equal shares, so ask for twice the total, and every region must hold the fullest sub-list
+            size_t want = (size_t)std::max<uint64_t>(sc.n_clusters, b->cl_cap) * 2 + 4096;
             std::vector<uint32_t> sub((size_t)SGA_SUBLISTS * 32);
             CU_TRY(cudaMemcpy(sub.data(), reinterpret_cast<const uint8_t *>(b->d_ctr) + offsetof(SeedCounters, sub_n),
                               sub.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost));
             uint64_t fullest = 0;
             for (int r = 0; r < SGA_SUBLISTS; r++) fullest = std::max<uint64_t>(fullest, sub[(size_t)32 * r]);
             want = std::max<size_t>(want, (size_t)(fullest + fullest / 4 + 64) * SGA_SUBLISTS);
+            if (want * sizeof(Cluster) > (48ull << 30)) { bwt_set_error("cluster list beyond 48 GiB: use smaller batches"); return BWT_ERR_NOMEM; }
+            BWT_TRY(dev_grow(b->d_clusters, b->cl_cap, want, false));
+            continue;
         }
-        if (want * sizeof(Cluster) > (48ull << 30)) { bwt_set_error("cluster list beyond 48 GiB: use smaller batches"); return BWT_ERR_NOMEM; }
-        BWT_TRY(dev_grow(b->d_clusters, b->cl_cap, want, false));
+        const uint32_t ncl = sc.n_clusters;
+        if (with_sw) {
+            bool redo_emit = false;
+            const int rc = sw_stage_finish(b->sw, b->R, ix.ref, ix.ref2, ix.refx, cl_cap, b->max_read_len, b->stream, &redo_emit);
+            if (rc == BWT_ERR_NOSPACE) continue;                         // CIGAR arena grown
+            BWT_TRY(rc);
+            if (redo_emit) {
+                CU_TRY(cudaMemsetAsync(&b->d_totals->emit_flags, 0, sizeof(uint32_t), b->stream));
+                BWT_TRY(enqueue_emit_stage(b, compact));
+                CU_TRY(cudaEventRecord(b->ev[3], b->stream));
+                CU_TRY(cudaMemcpyAsync(b->h_totals, b->d_totals, sizeof(RunTotals), cudaMemcpyDeviceToHost, b->stream));
+                CU_TRY(cudaStreamSynchronize(b->stream));
+            }
+            if (compact && b->h_totals->emit_flags) { bwt_set_error("a hit does not fit the compact record (CIGAR beyond 65535 bytes): use the wide API"); return BWT_ERR_LIMIT; }
+            b->n_hits = b->h_totals->hits;
+            b->cigar_bytes = b->h_totals->cig_bytes;
+        } else {
+            b->n_hits = ncl;
+        }
+        bwt_stats &s = b->stats;
+        s.reads = (uint64_t)n;
+        s.searches = sc.searches; s.lf_steps = sc.lf_steps; s.hbm_lf_steps = sc.hbm_lf_steps;
+        s.located_rows = sc.located;
+        s.ms_sw_kernel = with_sw ? b->sw.ms_fast_kernel : 0.f;
+        s.clusters = ncl;
+        s.sw_calls = b->sw.sw_calls; s.sw_cells = b->sw.cells; s.sw_general = b->sw.n_general;
+        s.sw_shortcut = b->sw.shortcut_calls; s.sw_shortcut_cells = b->sw.shortcut_cells;
+        s.launches += b->sw.launches;
+        cudaEventElapsedTime(&s.ms_sga_kernel, b->ev[6], b->ev[7]);
+        cudaEventElapsedTime(&s.ms_seed, b->ev[0], b->ev[1]);
+        cudaEventElapsedTime(&s.ms_sw, b->ev[1], b->ev[2]);
+        cudaEventElapsedTime(&s.ms_emit, b->ev[2], b->ev[3]);
+        cudaEventElapsedTime(&s.ms_total, b->ev[0], b->ev[3]);
+        b->has_result = with_sw; b->result_compact = compact;
+        return BWT_OK;
     }
-    bwt_set_error("cluster list kept overflowing");
+    bwt_set_error("a capacity kept overflowing");
     return BWT_ERR_NOMEM;
 }
 
-static int run_emit_stage(bwt_batch *b, uint32_t ncl) {
-    int64_t n = b->n;
-    unsigned blocks = (unsigned)((n + 1 + 255) / 256);
-    emit_count_kernel<<<blocks, 256, 0, b->stream>>>(b->d_ncl, b->d_cl_base, b->sw.d_out, n, b->d_hit_off, b->d_cig_off);
-    b->stats.launches += 1;
-    CU_TRY(cudaGetLastError());
-    BWT_TRY(exclusive_scan_u32(b->d_hit_off, (size_t)n + 1, b->d_scan_tmp, nullptr, b->stream, &b->stats.launches));
-    BWT_TRY(exclusive_scan_u32(b->d_cig_off, (size_t)n + 1, b->d_scan_tmp, nullptr, b->stream, &b->stats.launches));
-    // element n of an exclusive scan over n+1 items is the total (item n is garbage-free: written as 0 below)
-    BWT_TRY(dev_grow(b->d_hits, b->hits_cap, (size_t)ncl));
-    BWT_TRY(dev_grow(b->d_cigars, b->cigars_cap, (size_t)b->sw.h_ctr->cig_used + 16));
-    emit_kernel<<<blocks, 256, 0, b->stream>>>(b->d_ncl, b->d_cl_base, b->d_clusters, b->sw.d_desc, b->sw.d_out,
-                                               b->sw.d_cig_tmp, n, b->d_hit_off, b->d_cig_off, b->ix->shift,
-                                               b->d_hit_off64, b->d_hits, b->d_cigars);
-    b->stats.launches += 1;
-    CU_TRY(cudaGetLastError());
-    CU_TRY(cudaMemcpyAsync(b->h_totals, b->d_hit_off + n, sizeof(uint32_t), cudaMemcpyDeviceToHost, b->stream));
-    CU_TRY(cudaMemcpyAsync(b->h_totals + 1, b->d_cig_off + n, sizeof(uint32_t), cudaMemcpyDeviceToHost, b->stream));
-    return BWT_OK;
-}
-
-static int run_core(bwt_batch *b, bool with_sw) {
-    if (!b) { bwt_set_error("null batch"); return BWT_ERR_ARG; }
-    CU_TRY(cudaSetDevice(b->ix->device));
-    float h2d = b->stats.ms_h2d;
-    memset(&b->stats, 0, sizeof b->stats);
-    b->stats.ms_h2d = h2d;
-    b->sw.launches = 0;
-    b->n_hits = 0; b->cigar_bytes = 0;
-    // The aligner's chunks take the token stage by stage: while one chunk's host thread sits between two stages (reading
-    // counters, sizing the next launch), another chunk's stage runs instead of the GPU idling.
-    struct Token {
-        std::mutex *m;
-        explicit Token(std::mutex *mu) : m(mu) { if (m) m->lock(); }
-        ~Token() { if (m) m->unlock(); }
-    };
-    CU_TRY(cudaEventRecord(b->ev[0], b->stream));
-    if (b->n > 0) { Token tk(b->stage_token); BWT_TRY(run_seed_stage(b)); }
-    else memset(b->h_ctr, 0, sizeof(SeedCounters));
-    CU_TRY(cudaEventRecord(b->ev[1], b->stream));
-    uint32_t ncl = b->n > 0 ? b->h_ctr->n_clusters : 0;
-    if (with_sw) {
-        BWT_TRY(sw_stage_reserve(b->sw, (uint32_t)b->cl_cap));
-        if (ncl > 0) {
-            Token tk(b->stage_token);
-            windows_kernel<<<(ncl + 255) / 256, 256, 0, b->stream>>>(b->d_clusters, ncl, b->d_offs, b->ix->dv.ref_len_padded,
-                                                                     b->sw.d_desc, b->sw.d_out);
-            b->stats.launches += 1;
-            K_CHECK(b->stream, "windows_kernel");
-            BWT_TRY(sw_stage_run(b->sw, b->d_reads, b->ix->dv.ref, ncl, b->max_read_len, b->stream));
-        } else {
-            memset(b->sw.h_ctr, 0, sizeof(SwCounters));
-        }
-        CU_TRY(cudaEventRecord(b->ev[2], b->stream));
-        {
-            Token tk(b->stage_token);
-            if (b->n > 0) BWT_TRY(run_emit_stage(b, ncl));
-            CU_TRY(cudaEventRecord(b->ev[3], b->stream));
-            CU_TRY(cudaStreamSynchronize(b->stream));
-        }
-        b->n_hits = b->n > 0 ? b->h_totals[0] : 0;
-        b->cigar_bytes = b->n > 0 ? b->h_totals[1] : 0;
-    } else {
-        CU_TRY(cudaEventRecord(b->ev[2], b->stream));
-        CU_TRY(cudaEventRecord(b->ev[3], b->stream));
-        CU_TRY(cudaStreamSynchronize(b->stream));
-        b->n_hits = ncl;
-    }
-    bwt_stats &s = b->stats;
-    s.reads = (uint64_t)b->n;
-    s.searches = b->h_ctr->searches; s.lf_steps = b->h_ctr->lf_steps; s.hbm_lf_steps = b->h_ctr->hbm_lf_steps;
-    s.located_rows = b->h_ctr->located;
-    s.ms_sw_kernel = with_sw ? b->sw.ms_fast_kernel : 0.f;
-    s.clusters = ncl;
-    s.sw_calls = b->sw.sw_calls; s.sw_cells = b->sw.cells; s.sw_general = b->sw.n_general;
-    s.sw_shortcut = b->sw.shortcut_calls; s.sw_shortcut_cells = b->sw.shortcut_cells;
-    s.launches += b->sw.launches;
-    cudaEventElapsedTime(&s.ms_seed, b->ev[0], b->ev[1]);
-    cudaEventElapsedTime(&s.ms_sw, b->ev[1], b->ev[2]);
-    cudaEventElapsedTime(&s.ms_emit, b->ev[2], b->ev[3]);
-    cudaEventElapsedTime(&s.ms_total, b->ev[0], b->ev[3]);
-    b->has_result = with_sw;
-    return BWT_OK;
-}
-
-extern "C" int bwt_batch_run(bwt_batch *b) { return run_core(b, true); }
+extern "C" int bwt_batch_run(bwt_batch *b) { return run_core(b, true, false); }
+extern "C" int bwt_batch_run_compact(bwt_batch *b) { return run_core(b, true, true); }
 
 extern "C" int bwt_batch_result_size(bwt_batch *b, int64_t *n_hits, int64_t *cigar_bytes) {
     if (!b) { bwt_set_error("null batch"); return BWT_ERR_ARG; }
@@ -490,13 +655,13 @@ extern "C" int bwt_batch_result_size(bwt_batch *b, int64_t *n_hits, int64_t *cig
 
 extern "C" int bwt_batch_download(bwt_batch *b, int32_t *read_status, int64_t *hit_offsets, bwt_hit *hits,
                                   int64_t hits_cap, char *cigars, int64_t cigar_cap) {
-    if (!b || !b->has_result) { bwt_set_error("bwt_batch_download: no result (call bwt_batch_run first)"); return BWT_ERR_ARG; }
+    if (!b || !b->has_result || b->result_compact) { bwt_set_error("bwt_batch_download: no result (call bwt_batch_run first)"); return BWT_ERR_ARG; }
     if (hits_cap < b->n_hits || cigar_cap < b->cigar_bytes) {
         bwt_set_error("output capacity too small: need %lld hits and %lld CIGAR bytes", (long long)b->n_hits, (long long)b->cigar_bytes);
         return BWT_ERR_NOSPACE;
     }
     CU_TRY(cudaSetDevice(b->ix->device));
-    CU_TRY(cudaEventRecord(b->ev[4], b->stream));
+    CU_TRY(cudaEventRecord(b->ev[8], b->stream));
     if (read_status && b->n) CU_TRY(cudaMemcpyAsync(read_status, b->d_read_status, (size_t)b->n * sizeof(int32_t), cudaMemcpyDeviceToHost, b->stream));
     if (hit_offsets) {
         if (b->n) CU_TRY(cudaMemcpyAsync(hit_offsets, b->d_hit_off64, (size_t)(b->n + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, b->stream));
@@ -504,9 +669,31 @@ extern "C" int bwt_batch_download(bwt_batch *b, int32_t *read_status, int64_t *h
     }
     if (hits && b->n_hits) CU_TRY(cudaMemcpyAsync(hits, b->d_hits, (size_t)b->n_hits * sizeof(bwt_hit), cudaMemcpyDeviceToHost, b->stream));
     if (cigars && b->cigar_bytes) CU_TRY(cudaMemcpyAsync(cigars, b->d_cigars, (size_t)b->cigar_bytes, cudaMemcpyDeviceToHost, b->stream));
-    CU_TRY(cudaEventRecord(b->ev[5], b->stream));
+    CU_TRY(cudaEventRecord(b->ev[9], b->stream));
     CU_TRY(cudaStreamSynchronize(b->stream));
-    cudaEventElapsedTime(&b->stats.ms_d2h, b->ev[4], b->ev[5]);
+    cudaEventElapsedTime(&b->stats.ms_d2h, b->ev[8], b->ev[9]);
+    return BWT_OK;
+}
+
+extern "C" int bwt_batch_download_compact(bwt_batch *b, uint8_t *read_status, uint32_t *hit_offsets, bwt_hit16 *hits,
+                                          int64_t hits_cap, char *cigars, int64_t cigar_cap) {
+    if (!b || !b->has_result || !b->result_compact) { bwt_set_error("bwt_batch_download_compact: no compact result (call bwt_batch_run_compact first)"); return BWT_ERR_ARG; }
+    if (hits_cap < b->n_hits || cigar_cap < b->cigar_bytes) {
+        bwt_set_error("output capacity too small: need %lld hits and %lld CIGAR bytes", (long long)b->n_hits, (long long)b->cigar_bytes);
+        return BWT_ERR_NOSPACE;
+    }
+    CU_TRY(cudaSetDevice(b->ix->device));
+    CU_TRY(cudaEventRecord(b->ev[8], b->stream));
+    if (read_status && b->n) CU_TRY(cudaMemcpyAsync(read_status, b->d_status8, (size_t)b->n, cudaMemcpyDeviceToHost, b->stream));
+    if (hit_offsets) {
+        if (b->n) CU_TRY(cudaMemcpyAsync(hit_offsets, b->d_hit_off, (size_t)(b->n + 1) * sizeof(uint32_t), cudaMemcpyDeviceToHost, b->stream));
+        else hit_offsets[0] = 0;
+    }
+    if (hits && b->n_hits) CU_TRY(cudaMemcpyAsync(hits, b->d_hits16, (size_t)b->n_hits * sizeof(bwt_hit16), cudaMemcpyDeviceToHost, b->stream));
+    if (cigars && b->cigar_bytes) CU_TRY(cudaMemcpyAsync(cigars, b->d_cigars, (size_t)b->cigar_bytes, cudaMemcpyDeviceToHost, b->stream));
+    CU_TRY(cudaEventRecord(b->ev[9], b->stream));
+    CU_TRY(cudaStreamSynchronize(b->stream));
+    cudaEventElapsedTime(&b->stats.ms_d2h, b->ev[8], b->ev[9]);
     return BWT_OK;
 }
 
@@ -518,9 +705,18 @@ extern "C" int bwt_batch_stats(bwt_batch *b, bwt_stats *out) {
 
 extern "C" int bwt_batch_device_result(bwt_batch *b, void **d_hit_offsets, void **d_hits, void **d_cigars) {
     if (!b || !b->has_result) { bwt_set_error("bwt_batch_device_result: no result"); return BWT_ERR_ARG; }
-    if (d_hit_offsets) *d_hit_offsets = b->d_hit_off64;
-    if (d_hits) *d_hits = b->d_hits;
+    if (d_hit_offsets) *d_hit_offsets = b->result_compact ? (void *)b->d_hit_off : (void *)b->d_hit_off64;
+    if (d_hits) *d_hits = b->result_compact ? (void *)b->d_hits16 : (void *)b->d_hits;
     if (d_cigars) *d_cigars = b->d_cigars;
+    return BWT_OK;
+}
+
+// internals the partition gather (gather.cu) needs
+int batch_result_view(bwt_batch *b, int *device, cudaStream_t *stream, int64_t *n, const uint8_t **d_status8, const uint32_t **d_hit_off,
+                      const bwt_hit16 **d_hits16, const char **d_cigars, int64_t *n_hits, int64_t *cigar_bytes) {
+    if (!b || !b->has_result || !b->result_compact) { bwt_set_error("partition gather needs a compact result (bwt_batch_run_compact)"); return BWT_ERR_ARG; }
+    *device = b->ix->device; *stream = b->stream; *n = b->n; *d_status8 = b->d_status8; *d_hit_off = b->d_hit_off; *d_hits16 = b->d_hits16;
+    *d_cigars = b->d_cigars; *n_hits = b->n_hits; *cigar_bytes = b->cigar_bytes;
     return BWT_OK;
 }
 
@@ -542,8 +738,9 @@ static int64_t chunk_end(const int64_t *offsets, int64_t lo, int64_t n) { return
 
 // ---- pipelined aligner ------------------------------------------------------------------------------
 // `depth` resident batches, one host thread each; chunk c is uploaded, run and downloaded by thread c mod depth on
-// that batch's own stream, so the H2D of one chunk, the kernels of another and the D2H of a third overlap.  Results
-// land in the caller's arrays at their final place: a chunk learns its bases once every earlier chunk has finished.
+// that batch's own stream, so the H2D of one chunk, the kernels of another and the D2H of a third overlap -- and so do
+// the kernels of two chunks (the seeding kernel waits on HBM, the extension kernels on the ALU pipe).  Results land in
+// the caller's arrays at their final place: a chunk learns its bases once every earlier chunk has finished.
 struct bwt_aligner {
     bwt_index *ix = nullptr;
     int64_t chunk_reads = 0, chunk_bytes = 0;
@@ -589,7 +786,7 @@ struct PipeShared {
     std::string error;
 };
 
-static void stats_add(bwt_stats &t, const bwt_stats &s) {
+void stats_add(bwt_stats &t, const bwt_stats &s) {
     t.reads += s.reads; t.searches += s.searches; t.lf_steps += s.lf_steps; t.hbm_lf_steps += s.hbm_lf_steps;
     t.located_rows += s.located_rows; t.clusters += s.clusters; t.sw_calls += s.sw_calls; t.sw_cells += s.sw_cells;
     t.sw_shortcut += s.sw_shortcut; t.sw_shortcut_cells += s.sw_shortcut_cells;
@@ -597,22 +794,48 @@ static void stats_add(bwt_stats &t, const bwt_stats &s) {
     t.ms_h2d += s.ms_h2d; t.ms_d2h += s.ms_d2h; t.ms_sga_kernel += s.ms_sga_kernel; t.ms_sw_kernel += s.ms_sw_kernel;
     t.launches += s.launches;
 }
-}  // namespace
 
-extern "C" int bwt_aligner_run(bwt_aligner *a, const uint8_t *reads, const int64_t *offsets, int64_t n, int32_t *read_status,
-                               int64_t *hit_offsets, bwt_hit *hits, int64_t hits_cap, int64_t *n_hits, char *cigars,
-                               int64_t cigar_cap, int64_t *cigar_bytes) {
-    if (!a || !offsets || n < 0 || !hit_offsets || !n_hits || !cigar_bytes || (n > 0 && !reads)) { bwt_set_error("bwt_aligner_run: null argument"); return BWT_ERR_ARG; }
+// the two faces of an aligner run: ASCII in / wide records out (the reference-shaped call), packed in / compact out
+struct AlignIO {
+    // input
+    const uint8_t *reads = nullptr; const int64_t *offsets = nullptr;     // ASCII
+    const bwt_packed_reads *packed = nullptr;                             // packed
+    int64_t n = 0;
+    // output
+    bool compact = false;
+    int32_t *status32 = nullptr; int64_t *off64 = nullptr; bwt_hit *hits = nullptr;
+    uint8_t *status8 = nullptr; uint32_t *off32 = nullptr; bwt_hit16 *hits16 = nullptr;
+    int64_t hits_cap = 0; char *cigars = nullptr; int64_t cigar_cap = 0;
+    int64_t *n_hits = nullptr, *cigar_bytes = nullptr;
+};
+
+int aligner_run_io(bwt_aligner *a, const AlignIO &io) {
     memset(&a->stats, 0, sizeof a->stats);
-    hit_offsets[0] = 0;
-    *n_hits = 0; *cigar_bytes = 0;
+    if (io.compact) io.off32[0] = 0; else io.off64[0] = 0;
+    *io.n_hits = 0; *io.cigar_bytes = 0;
+    const int64_t n = io.n;
     if (n == 0) return BWT_OK;
     std::vector<int64_t> bounds(1, 0);                      // chunk c = reads [bounds[c], bounds[c+1])
-    for (int64_t lo = 0; lo < n;) {
-        int64_t hi = chunk_end_lim(offsets, lo, n, a->chunk_reads, a->chunk_bytes);
-        if (offsets[hi] - offsets[lo] > a->chunk_bytes) { bwt_set_error("a single read exceeds %lld bytes", (long long)a->chunk_bytes); return BWT_ERR_LIMIT; }
-        bounds.push_back(hi);
-        lo = hi;
+    std::vector<int64_t> wbase, wcount;                     // packed input: word base / count / longest read per chunk
+    std::vector<int> wmax;
+    if (io.packed) {
+        int64_t wb = 0;
+        for (int64_t lo = 0; lo < n;) {
+            const int64_t hi = std::min(n, lo + a->chunk_reads);
+            int64_t words; int mx;
+            packed_geom(io.packed, lo, hi, &words, &mx);
+            wbase.push_back(wb); wcount.push_back(words); wmax.push_back(mx);
+            wb += words;
+            bounds.push_back(hi);
+            lo = hi;
+        }
+    } else {
+        for (int64_t lo = 0; lo < n;) {
+            int64_t hi = chunk_end_lim(io.offsets, lo, n, a->chunk_reads, a->chunk_bytes);
+            if (io.offsets[hi] - io.offsets[lo] > a->chunk_bytes) { bwt_set_error("a single read exceeds %lld bytes", (long long)a->chunk_bytes); return BWT_ERR_LIMIT; }
+            bounds.push_back(hi);
+            lo = hi;
+        }
     }
     const int64_t nchunks = (int64_t)bounds.size() - 1;
     const int depth = (int)std::min<int64_t>((int64_t)a->batches.size(), nchunks);
@@ -620,7 +843,7 @@ extern "C" int bwt_aligner_run(bwt_aligner *a, const uint8_t *reads, const int64
     std::vector<bwt_stats> wstats((size_t)depth);
     const bool trace = getenv("BWT_TRACE") != nullptr;       // per-chunk host timeline on stderr (debug aid)
     const char *env_tok = getenv("BWT_COMPUTE_TOKEN");
-    const int token_mode = env_tok ? atoi(env_tok) : 2;
+    const int token_mode = env_tok ? atoi(env_tok) : 0;      // 1: one chunk at a time inside a run (A/B against free overlap)
     const auto t_start = std::chrono::steady_clock::now();
     auto now_ms = [&] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_start).count(); };
     auto worker = [&](int w) {
@@ -633,22 +856,21 @@ extern "C" int bwt_aligner_run(bwt_aligner *a, const uint8_t *reads, const int64
             { std::lock_guard<std::mutex> g(sh.mu); skip = sh.status != BWT_OK; }
             double t0 = now_ms(), t1 = t0, t2 = t0, t3 = t0;
             if (!skip) {
-                st = bwt_batch_upload(b, reads, offsets + lo, m);
-                t1 = now_ms();
-                if (st == BWT_OK && b->dl_pending) {     // the previous chunk's results must have left before this run overwrites them
+                if (b->dl_pending) {     // the previous chunk's results must have left before this run overwrites them
                     cudaError_t e = cudaStreamSynchronize(b->dl_stream);
                     b->dl_pending = false;
                     if (e != cudaSuccess) { bwt_set_error("aligner download: %s", cudaGetErrorString(e)); st = BWT_ERR_CUDA; }
                     else { float ms = 0; cudaEventElapsedTime(&ms, b->ev_dl0, b->ev_dl1); wstats[(size_t)w].ms_d2h += ms; }
                 }
+                if (st == BWT_OK)
+                    st = io.packed ? batch_upload_packed_range(b, io.packed, lo, lo + m, wbase[(size_t)c], wcount[(size_t)c], wmax[(size_t)c])
+                                   : bwt_batch_upload(b, io.reads, io.offsets + lo, m);
+                t1 = now_ms();
                 if (st == BWT_OK) {
-                    // BWT_COMPUTE_TOKEN: 2 (default) = one chunk at a time inside a whole run; 1 = inside a stage; 0 = free
-                    // (measured on 10 M x 100 bp, depth 2 / 3: 289 / 283 M reads/s, 290 / 247, 256 / -)
                     std::unique_lock<std::mutex> run_token(sh.compute_mu, std::defer_lock);
-                    if (token_mode == 2) run_token.lock();
-                    b->stage_token = token_mode == 1 ? &sh.compute_mu : nullptr;
-                    st = bwt_batch_run(b);
-                    b->stage_token = nullptr;
+                    if (token_mode == 1) run_token.lock();
+                    st = run_core(b, true, io.compact);
+                    if (st == BWT_OK) { float ms = 0; cudaEventElapsedTime(&ms, b->ev[4], b->ev[5]); b->stats.ms_h2d = ms; }
                 }
                 t2 = now_ms();
             }
@@ -661,7 +883,10 @@ extern "C" int bwt_aligner_run(bwt_aligner *a, const uint8_t *reads, const int64
                 sh.cv.wait(g, [&] { return sh.next_chunk == c; });
                 hb = sh.hit_base; cb = sh.cig_base;
                 sh.hit_base += nh; sh.cig_base += nc;
-                if (!(hits && cigars && sh.hit_base <= hits_cap && sh.cig_base <= cigar_cap)) sh.space = false;
+                if (!((io.compact ? (void *)io.hits16 : (void *)io.hits) && io.cigars && sh.hit_base <= io.hits_cap && sh.cig_base <= io.cigar_cap)) sh.space = false;
+                if (io.compact && (sh.hit_base >= (1ll << 32) || sh.cig_base >= (1ll << 32)) && sh.status == BWT_OK) {
+                    sh.status = BWT_ERR_LIMIT; sh.error = "compact results address 2^32 hits / CIGAR bytes per run: split the call";
+                }
                 room = sh.space && sh.status == BWT_OK;
                 sh.next_chunk = c + 1;
             }
@@ -670,7 +895,8 @@ extern "C" int bwt_aligner_run(bwt_aligner *a, const uint8_t *reads, const int64
             if (skip || st != BWT_OK) continue;
             if (room) {
                 const int64_t cnt = std::max(m + 1, nh);
-                rebase_result_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, b->stream>>>(b->d_hit_off64, m, b->d_hits, nh, hb, cb);
+                if (io.compact) rebase_result16_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, b->stream>>>(b->d_hit_off, m, b->d_hits16, nh, (uint32_t)hb, (uint32_t)cb);
+                else rebase_result_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, b->stream>>>(b->d_hit_off64, m, b->d_hits, nh, hb, cb);
                 // entry m of this chunk equals entry 0 of the next one: only the last chunk writes it
                 st = cudaGetLastError() == cudaSuccess ? BWT_OK : BWT_ERR_CUDA;
                 if (st == BWT_OK) {
@@ -680,10 +906,17 @@ extern "C" int bwt_aligner_run(bwt_aligner *a, const uint8_t *reads, const int64
                     cudaStream_t s = b->dl_stream;
                     cudaStreamWaitEvent(s, b->ev_run_done, 0);
                     cudaEventRecord(b->ev_dl0, s);
-                    if (read_status) cudaMemcpyAsync(read_status + lo, b->d_read_status, (size_t)m * sizeof(int32_t), cudaMemcpyDeviceToHost, s);
-                    cudaMemcpyAsync(hit_offsets + lo, b->d_hit_off64, (size_t)(m + (c + 1 == nchunks ? 1 : 0)) * sizeof(int64_t), cudaMemcpyDeviceToHost, s);
-                    if (nh) cudaMemcpyAsync(hits + hb, b->d_hits, (size_t)nh * sizeof(bwt_hit), cudaMemcpyDeviceToHost, s);
-                    if (nc) cudaMemcpyAsync(cigars + cb, b->d_cigars, (size_t)nc, cudaMemcpyDeviceToHost, s);
+                    const size_t last = c + 1 == nchunks ? 1 : 0;
+                    if (io.compact) {
+                        if (io.status8) cudaMemcpyAsync(io.status8 + lo, b->d_status8, (size_t)m, cudaMemcpyDeviceToHost, s);
+                        cudaMemcpyAsync(io.off32 + lo, b->d_hit_off, ((size_t)m + last) * sizeof(uint32_t), cudaMemcpyDeviceToHost, s);
+                        if (nh) cudaMemcpyAsync(io.hits16 + hb, b->d_hits16, (size_t)nh * sizeof(bwt_hit16), cudaMemcpyDeviceToHost, s);
+                    } else {
+                        if (io.status32) cudaMemcpyAsync(io.status32 + lo, b->d_read_status, (size_t)m * sizeof(int32_t), cudaMemcpyDeviceToHost, s);
+                        cudaMemcpyAsync(io.off64 + lo, b->d_hit_off64, ((size_t)m + last) * sizeof(int64_t), cudaMemcpyDeviceToHost, s);
+                        if (nh) cudaMemcpyAsync(io.hits + hb, b->d_hits, (size_t)nh * sizeof(bwt_hit), cudaMemcpyDeviceToHost, s);
+                    }
+                    if (nc) cudaMemcpyAsync(io.cigars + cb, b->d_cigars, (size_t)nc, cudaMemcpyDeviceToHost, s);
                     cudaEventRecord(b->ev_dl1, s);
                     if (cudaGetLastError() != cudaSuccess) { bwt_set_error("aligner download: enqueue failed"); st = BWT_ERR_CUDA; }
                     else b->dl_pending = true;
@@ -711,13 +944,37 @@ extern "C" int bwt_aligner_run(bwt_aligner *a, const uint8_t *reads, const int64
     worker_all(0);
     for (auto &t : th) t.join();
     for (int w = 0; w < depth; w++) stats_add(a->stats, wstats[(size_t)w]);
-    *n_hits = sh.hit_base; *cigar_bytes = sh.cig_base;
+    *io.n_hits = sh.hit_base; *io.cigar_bytes = sh.cig_base;
     if (sh.status != BWT_OK) { bwt_set_error("%s", sh.error.c_str()); return sh.status; }
     if (!sh.space) {
         bwt_set_error("output capacity too small: need %lld hits and %lld CIGAR bytes", (long long)sh.hit_base, (long long)sh.cig_base);
         return BWT_ERR_NOSPACE;
     }
     return BWT_OK;
+}
+}  // namespace
+
+extern "C" int bwt_aligner_run(bwt_aligner *a, const uint8_t *reads, const int64_t *offsets, int64_t n, int32_t *read_status,
+                               int64_t *hit_offsets, bwt_hit *hits, int64_t hits_cap, int64_t *n_hits, char *cigars,
+                               int64_t cigar_cap, int64_t *cigar_bytes) {
+    if (!a || !offsets || n < 0 || !hit_offsets || !n_hits || !cigar_bytes || (n > 0 && !reads)) { bwt_set_error("bwt_aligner_run: null argument"); return BWT_ERR_ARG; }
+    AlignIO io;
+    io.reads = reads; io.offsets = offsets; io.n = n;
+    io.status32 = read_status; io.off64 = hit_offsets; io.hits = hits; io.hits_cap = hits_cap; io.cigars = cigars; io.cigar_cap = cigar_cap;
+    io.n_hits = n_hits; io.cigar_bytes = cigar_bytes;
+    return aligner_run_io(a, io);
+}
+
+extern "C" int bwt_aligner_run_packed(bwt_aligner *a, const bwt_packed_reads *p, uint8_t *read_status, uint32_t *hit_offsets,
+                                      bwt_hit16 *hits, int64_t hits_cap, int64_t *n_hits, char *cigars, int64_t cigar_cap,
+                                      int64_t *cigar_bytes) {
+    if (!a || !hit_offsets || !n_hits || !cigar_bytes) { bwt_set_error("bwt_aligner_run_packed: null argument"); return BWT_ERR_ARG; }
+    BWT_TRY(packed_check(p));
+    AlignIO io;
+    io.packed = p; io.n = p->n; io.compact = true;
+    io.status8 = read_status; io.off32 = hit_offsets; io.hits16 = hits; io.hits_cap = hits_cap; io.cigars = cigars; io.cigar_cap = cigar_cap;
+    io.n_hits = n_hits; io.cigar_bytes = cigar_bytes;
+    return aligner_run_io(a, io);
 }
 
 // worker_bwt.erl:73-97 for one list of reads, host buffers in and out: a short-lived aligner
@@ -788,7 +1045,7 @@ extern "C" int bwt_sga_batch(bwt_index *h, const uint8_t *reads, const int64_t *
     for (int64_t lo = 0; lo < n && st == BWT_OK;) {
         int64_t hi = chunk_end(offsets, lo, n), m = hi - lo;
         if ((st = bwt_batch_upload(b, reads, offsets + lo, m)) != BWT_OK) break;
-        if ((st = run_core(b, false)) != BWT_OK) break;
+        if ((st = run_core(b, false, false)) != BWT_OK) break;
         int64_t nc = b->n_hits;
         // offsets = exclusive scan of the per-read cluster counts
         cudaMemcpyAsync(b->d_hit_off, b->d_ncl, (size_t)m * sizeof(uint32_t), cudaMemcpyDeviceToDevice, b->stream);
@@ -870,7 +1127,7 @@ extern "C" int bwt_search_resident(bwt_index *h, const uint8_t *subs, int64_t n,
     uint32_t *d_sp = nullptr, *d_ep = nullptr;
     SeedCounters *d_ctr = nullptr;
     cudaEvent_t e0, e1;
-    CU_TRY(cudaMalloc(&d_subs, (size_t)n * sub_len));
+    CU_TRY(cudaMalloc(&d_subs, (size_t)n * sub_len + 16));
     CU_TRY(cudaMalloc(&d_sp, (size_t)n * 4));
     CU_TRY(cudaMalloc(&d_ep, (size_t)n * 4));
     CU_TRY(cudaMalloc(&d_ctr, sizeof(SeedCounters)));
@@ -910,58 +1167,79 @@ extern "C" int bwt_sw_batch(int device, const uint8_t *q, const int64_t *q_offse
     int64_t qb = q_offsets[0], rb = r_offsets[0], qbytes = q_offsets[n] - qb, rbytes = r_offsets[n] - rb;
     std::vector<int64_t> qo((size_t)n + 1), ro((size_t)n + 1);
     int max_lq = 0;
+    int64_t words = 0;
     for (int64_t k = 0; k <= n; k++) {
         qo[k] = q_offsets[k] - qb; ro[k] = r_offsets[k] - rb;
-        if (k) max_lq = (int)std::max<int64_t>(max_lq, std::min<int64_t>(qo[k] - qo[k - 1], 1 << 30));
+        if (k) {
+            const int64_t l = qo[k] - qo[k - 1];
+            if (l < 0 || ro[k] < ro[k - 1]) { bwt_set_error("bwt_sw_batch: offsets must be non-decreasing"); return BWT_ERR_ARG; }
+            max_lq = (int)std::max<int64_t>(max_lq, std::min<int64_t>(l, 1 << 30));
+            if (l <= BWT_PACK_MAX) words += (l + 15) >> 4;
+        }
     }
     SwStage sw;
     sw.device = device;
     uint8_t *d_q = nullptr, *d_r = nullptr;
     int64_t *d_qo = nullptr, *d_ro = nullptr;
-    uint32_t *d_off = nullptr, *d_tmp = nullptr;
-    int32_t *d_status = nullptr, *d_score = nullptr, *d_len = nullptr;
+    uint32_t *d_off = nullptr, *d_tmp = nullptr, *d_pk = nullptr, *d_woff = nullptr, *d_len = nullptr, *d_exc = nullptr, *d_ref2 = nullptr, *d_refx = nullptr, *d_info = nullptr;
+    int32_t *d_status = nullptr, *d_score = nullptr, *d_len_out = nullptr;
     int64_t *d_coff = nullptr;
     char *d_cig = nullptr;
     cudaStream_t stream = 0;
     int st = BWT_OK;
     do {
         if ((st = sw_stage_reserve(sw, (uint32_t)n)) != BWT_OK) break;
-        if (cudaMalloc(&d_q, (size_t)qbytes + 16) || cudaMalloc(&d_r, (size_t)rbytes + 16) || cudaMalloc(&d_qo, (size_t)(n + 1) * 8) ||
+        if (cudaMalloc(&d_q, (size_t)qbytes + 16) || cudaMalloc(&d_r, (size_t)rbytes + 32) || cudaMalloc(&d_qo, (size_t)(n + 1) * 8) ||
             cudaMalloc(&d_ro, (size_t)(n + 1) * 8) || cudaMalloc(&d_off, (size_t)(n + 1) * 4) ||
             cudaMalloc(&d_tmp, scan_tmp_words((size_t)n + 1) * 4) || cudaMalloc(&d_status, (size_t)n * 4) ||
-            cudaMalloc(&d_score, (size_t)n * 4) || cudaMalloc(&d_len, (size_t)n * 4) || cudaMalloc(&d_coff, (size_t)n * 8)) {
+            cudaMalloc(&d_score, (size_t)n * 4) || cudaMalloc(&d_len_out, (size_t)n * 4) || cudaMalloc(&d_coff, (size_t)n * 8) ||
+            cudaMalloc(&d_pk, (size_t)(words + 2) * 4) || cudaMalloc(&d_woff, (size_t)(n + 1) * 4) || cudaMalloc(&d_len, (size_t)(n + 1) * 4) ||
+            cudaMalloc(&d_exc, (size_t)(n / 32 + 2) * 4) || cudaMalloc(&d_info, 16)) {
             bwt_set_error("device allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
             st = BWT_ERR_NOMEM; break;
         }
         if (qbytes) cudaMemcpy(d_q, q + qb, (size_t)qbytes, cudaMemcpyHostToDevice);
+        cudaMemset(d_r, 'A', (size_t)rbytes + 32);
         if (rbytes) cudaMemcpy(d_r, r + rb, (size_t)rbytes, cudaMemcpyHostToDevice);
         cudaMemcpy(d_qo, qo.data(), (size_t)(n + 1) * 8, cudaMemcpyHostToDevice);
         cudaMemcpy(d_ro, ro.data(), (size_t)(n + 1) * 8, cudaMemcpyHostToDevice);
-        desc_from_offsets_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(d_qo, d_ro, (uint32_t)n, sw.d_desc, sw.d_out);
+        const uint32_t n32 = (uint32_t)n;
+        uint32_t info0[4] = {n32, 0, 0, 0};
+        cudaMemcpy(d_info, info0, 16, cudaMemcpyHostToDevice);
+        cudaMemset(d_pk, 0, (size_t)(words + 2) * 4);
+        // the queries become the batch's "reads", the windows' buffer its window source
+        if ((st = reads_geom_from_ascii(d_qo, n, d_len, d_woff, d_tmp, d_info + 2, stream, nullptr)) != BWT_OK) break;
+        if ((st = reads_pack_device(d_q, d_qo, 0, n, d_len, d_woff, d_pk, d_exc, stream, nullptr)) != BWT_OK) break;
+        if ((st = pack_ref_device(d_r, (uint64_t)rbytes, &d_ref2, &d_refx, stream)) != BWT_OK) break;
+        DevReads R{};
+        R.pk = d_pk; R.woff = d_woff; R.len = d_len; R.exc = d_exc; R.ascii = d_q; R.aoff = d_qo; R.exc_idx = nullptr;
+        R.n_exc = 0; R.ascii_full = 1; R.aoff_base = 0; R.exc_base = 0;
+        desc_from_offsets_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(d_qo, d_ro, n32, sw.d_desc, sw.d_out);
         { cudaError_t e0 = cudaGetLastError(); if (e0 == cudaSuccess && bwt_debug_sync()) e0 = cudaStreamSynchronize(stream);
           if (e0 != cudaSuccess) { bwt_set_error("desc_from_offsets_kernel: %s", cudaGetErrorString(e0)); st = BWT_ERR_CUDA; break; } }
-        if ((st = sw_stage_run(sw, d_q, d_r, (uint32_t)n, max_lq, stream)) != BWT_OK) break;
+        if ((st = sw_stage_run(sw, R, d_r, d_ref2, d_refx, d_info, n32, max_lq, stream)) != BWT_OK) break;
         cudaMemsetAsync(d_off + n, 0, 4, stream);
-        sw_pairs_emit_count_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(sw.d_out, (uint32_t)n, d_off);
+        sw_pairs_emit_count_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(sw.d_out, n32, d_off);
         if ((st = exclusive_scan_u32(d_off, (size_t)n + 1, d_tmp, nullptr, stream, nullptr)) != BWT_OK) break;
         uint32_t tot = 0;
         cudaMemcpy(&tot, d_off + n, 4, cudaMemcpyDeviceToHost);
         *cigar_total = tot;
         if (cudaMalloc(&d_cig, (size_t)tot + 16)) { bwt_set_error("device allocation failed"); st = BWT_ERR_NOMEM; break; }
-        sw_pairs_emit_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(sw.d_out, sw.d_cig_tmp, (uint32_t)n, d_off, d_status,
-                                                                            d_score, d_coff, d_len, d_cig);
+        sw_pairs_emit_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(sw.d_out, sw.d_cig_tmp, n32, d_off, d_status,
+                                                                            d_score, d_coff, d_len_out, d_cig);
         cudaError_t e = cudaDeviceSynchronize();
         if (e != cudaSuccess) { bwt_set_error("sw emit failed: %s", cudaGetErrorString(e)); st = BWT_ERR_CUDA; break; }
         cudaMemcpy(status, d_status, (size_t)n * 4, cudaMemcpyDeviceToHost);
         cudaMemcpy(score, d_score, (size_t)n * 4, cudaMemcpyDeviceToHost);
         cudaMemcpy(cigar_off, d_coff, (size_t)n * 8, cudaMemcpyDeviceToHost);
-        cudaMemcpy(cigar_len, d_len, (size_t)n * 4, cudaMemcpyDeviceToHost);
+        cudaMemcpy(cigar_len, d_len_out, (size_t)n * 4, cudaMemcpyDeviceToHost);
         if ((int64_t)tot > cigar_cap || !cigars) {
             if (tot) { bwt_set_error("CIGAR capacity too small: need %u bytes", tot); st = BWT_ERR_NOSPACE; break; }
         } else if (tot) cudaMemcpy(cigars, d_cig, tot, cudaMemcpyDeviceToHost);
     } while (0);
     cudaFree(d_q); cudaFree(d_r); cudaFree(d_qo); cudaFree(d_ro); cudaFree(d_off); cudaFree(d_tmp); cudaFree(d_status);
-    cudaFree(d_score); cudaFree(d_len); cudaFree(d_coff); cudaFree(d_cig);
+    cudaFree(d_score); cudaFree(d_len_out); cudaFree(d_coff); cudaFree(d_cig); cudaFree(d_pk); cudaFree(d_woff); cudaFree(d_len);
+    cudaFree(d_exc); cudaFree(d_ref2); cudaFree(d_refx); cudaFree(d_info);
     sw_stage_free(sw);
     return st;
 }

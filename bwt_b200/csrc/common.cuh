@@ -58,18 +58,42 @@ bool bwt_debug_sync();
 struct DevIndex {
     const uint4 *occ;
     const uint32_t *sa;        // full suffix array, SA[e-1] for 1-based row e (fmi.erl:89-100 reads it un-sampled)
-    const uint2 *kmer;         // 4^8 entries, depth-8 interval table (format: KmerEntry below)
-    const uint2 *kmer_deep;    // 4^deep_k entries, or null
-    const uint2 *kmer_tail;    // ONE table of depth tail_k (8 < tail_k < deep_k), or null: set per launch for the length of
-    int tail_k;                // the short subsequence at the front of the batch's reads (8 + Lq mod 8 characters)
-    int deep_k;                // 9..15, or 0 when there is no deep table
+    const uint2 *ktab;         // interval tables of depth 8 .. min(deep_k, 14), one after the other (ktab_off(d); format: KmerEntry below)
+    const uint2 *kdeep;        // the depth-15 table (deep_k == 15 and no fused table), else null
+    const uint4 *fused;        // depth 15, 64 B per entry: {Sp, width | n << 28, SA[Sp-1 .. Sp-1+14)}: interval AND its first seed ends
+    int deep_k;                // deepest table: 8..15
     const uint8_t *ref;        // .ref padded with 200 'N' on both sides (worker_bwt.erl:53-55)
+    const uint32_t *ref2;      // the same, 2 bits per base (A0 C1 G2 T3; anything else as A), 16 bases per word
+    const uint32_t *refx;      // bit w set: word w of ref2 holds a byte outside ACGT
     uint64_t ref_len_padded;
     uint32_t n;                // rows
     uint32_t P[4];             // 1-based first row whose F is A (=2), C, G, T
     uint32_t last;
     uint32_t dollar;           // 1-based row whose L is '$'
     int64_t shift;
+};
+
+// first entry of the depth-d table inside ktab: 4^8 + 4^9 + .. + 4^(d-1)
+__host__ __device__ __forceinline__ uint64_t ktab_off(int d) { return ((1ull << (2 * d)) - 65536ull) / 3ull; }
+
+// ---- reads as the kernels see them -----------------------------------------------------------------
+// 2 bits per base, REVERSED: counting j from the END of read r (j = Lq-1-i), base j sits at bits 2(j mod 16) of word
+// woff[r] + j/16.  The k-mer table index of the subsequence sga:sga/6 cuts 8k bases before the end is then one funnel
+// shift at bit 16k.  Reads that hold a byte outside ACGT (or are longer than BWT_PACK_MAX) are flagged in `exc` and
+// take the ASCII paths: their text is in `ascii` (all reads when the batch arrived as ASCII, else only those reads).
+#define BWT_PACK_MAX 1040
+struct DevReads {
+    const uint32_t *pk;
+    const uint32_t *woff;      // n+1 word offsets into pk
+    const uint32_t *len;       // n lengths in bases
+    const uint32_t *exc;       // bit r: read r takes the ASCII path
+    const uint8_t *ascii;
+    const int64_t *aoff;       // ascii_full: n+1 offsets of all reads, else n_exc+1 offsets of the flagged reads
+    const uint32_t *exc_idx;   // !ascii_full: indices of the flagged reads, ascending
+    uint32_t n_exc;
+    int ascii_full;
+    int64_t aoff_base;         // subtracted from every aoff entry (the caller's offsets go up as they are)
+    uint32_t exc_base;         // subtracted from every exc_idx entry (a chunk of a larger packed batch)
 };
 
 // k-mer interval table entry (uint2): the state of bwa:find_seeds/6 after walking the last k characters of a
@@ -99,9 +123,9 @@ struct bwt_index {
     bool cached_busy = false;
     int64_t cached_reads = 0, cached_bytes = 0;
     int cached_depth = 0;
-    std::mutex *tail_mu = nullptr;                 // guards the lazily built single-depth tables below and the aligner cache
-    void *d_tail[BWT_MAX_LEN] = {};                // d_tail[k]: table of depth k, built on first use (index_tail_table)
-    void *d_occ = nullptr, *d_sa = nullptr, *d_kmer = nullptr, *d_ref = nullptr, *d_kmer_deep = nullptr;
+    std::mutex *tail_mu = nullptr;                 // guards the aligner cache
+    void *d_occ = nullptr, *d_sa = nullptr, *d_ktab = nullptr, *d_ref = nullptr, *d_kdeep = nullptr, *d_fused = nullptr;
+    void *d_ref2 = nullptr, *d_refx = nullptr;
 };
 
 // ASCII -> index code (A0 C1 G2 T3), -1 otherwise
@@ -135,6 +159,61 @@ __device__ __forceinline__ uint32_t pack16_acgt(const uint8_t *src, int cnt, boo
     }
     return out;
 }
+
+// reversed 2-bit groups of a word: group t <-> group 15-t
+__device__ __forceinline__ uint32_t rev2(uint32_t x) {
+    x = __brev(x);
+    return ((x & 0xAAAAAAAAu) >> 1) | ((x & 0x55555555u) << 1);
+}
+
+__device__ __forceinline__ bool read_is_exc(const DevReads &R, uint32_t r) { return (__ldg(R.exc + (r >> 5)) >> (r & 31)) & 1u; }
+
+// ASCII text of read r (only valid for reads whose text is resident: all of them when ascii_full, else the flagged ones)
+__device__ __forceinline__ const uint8_t *read_ascii(const DevReads &R, uint32_t r, int &lq) {
+    uint32_t k = r;
+    if (!R.ascii_full) {
+        uint32_t lo = 0, hi = R.n_exc;
+        while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (__ldg(R.exc_idx + mid) - R.exc_base < r) lo = mid + 1; else hi = mid; }
+        k = lo;
+    }
+    const int64_t o = R.aoff[k];
+    const int64_t l = R.aoff[k + 1] - o;
+    lq = l > (1 << 30) ? (1 << 30) : (int)l;
+    return R.ascii + (o - R.aoff_base);
+}
+
+// Bases [16w, 16w+16) of a packed read (pkr = its first word, lq its length) in FORWARD order: base 16w+t at bits 2t,
+// zeros ('A') past the end.  One word beyond the read's last may be read (every packed buffer carries a pad word).
+__device__ __forceinline__ uint32_t read_fwd_word(const uint32_t *__restrict__ pkr, int lq, int w) {
+    const int jlo = lq - 16 - 16 * w;                 // reversed index of base 16w+15
+    uint32_t x;
+    if (jlo >= 0) x = __funnelshift_r(__ldg(pkr + (jlo >> 4)), __ldg(pkr + (jlo >> 4) + 1), 2 * (jlo & 15));
+    else x = __ldg(pkr) << (2 * -jlo);
+    return rev2(x);
+}
+// code of base i (forward position) of a packed read
+__device__ __forceinline__ int read_code(const uint32_t *__restrict__ pkr, int lq, int i) {
+    const int j = lq - 1 - i;
+    return (int)((__ldg(pkr + (j >> 4)) >> (2 * (j & 15))) & 3u);
+}
+
+// 16 bases of the packed reference starting at (padded) position p: base p+t at bits 2t
+__device__ __forceinline__ uint32_t ref_word(const uint32_t *__restrict__ ref2, int64_t p) {
+    const int64_t w = p >> 4;
+    return __funnelshift_r(__ldg(ref2 + w), __ldg(ref2 + w + 1), 2 * (int)(p & 15));
+}
+// true when bases [p, p+len) of the packed reference are all plain ACGT (conservative to 16-base words)
+__device__ __forceinline__ bool ref_plain(const uint32_t *__restrict__ refx, int64_t p, int len) {
+    if (len <= 0) return true;
+    const int64_t b0 = p >> 4, b1 = (p + len - 1) >> 4;
+    for (int64_t w = b0 >> 5; w <= (b1 >> 5); w++) {
+        uint32_t m = __ldg(refx + w);
+        if (w == (b0 >> 5)) m &= 0xFFFFFFFFu << (b0 & 31);
+        if (w == (b1 >> 5)) m &= 0xFFFFFFFFu >> (31 - (b1 & 31));
+        if (m) return false;
+    }
+    return true;
+}
 #endif
 
 static inline uint64_t div_up_u64(uint64_t a, uint64_t b) { return (a + b - 1) / b; }
@@ -151,8 +230,9 @@ int exclusive_scan_u32(uint32_t *d_data, size_t n, uint32_t *d_tmp, uint32_t *d_
 int index_finish_from_device(bwt_index *h, const uint8_t *d_L, uint64_t n, uint32_t *d_sa, uint8_t *d_ref_padded,
                              uint64_t ref_len, const uint32_t pointers[4], int64_t shift);
 int index_select_device(int device);
-// Depth-k interval table (8 < k < deep_k) of this index, built on first use and kept; null when it cannot be had.
-const uint2 *index_tail_table(bwt_index *h, int k);
+// 2-bit copy + non-ACGT flags of an ASCII buffer on the device (len bytes; reads 16-byte aligned words: d_ascii from
+// cudaMalloc with >= 16 bytes of slack): *d_ref2 gets len/16 + 4 words, *d_refx one bit per word.
+int pack_ref_device(const uint8_t *d_ascii, uint64_t len, uint32_t **d_ref2, uint32_t **d_refx, cudaStream_t stream);
 // Destroys the aligner bwt_align_batch keeps with the index (batch.cu); called by bwt_close.
 void aligner_cache_drop(bwt_index *h);
 int index_upload_ref_device(const uint8_t *d_ref, uint64_t len, uint8_t **d_out);

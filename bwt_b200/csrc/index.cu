@@ -7,6 +7,7 @@
 //   kmer  : 65536 x 8 B         interval after the first 8 characters (L2-resident)
 //   ref   : ref_len + 400 B     ASCII .ref padded with 200 'N' each side
 #include <stdarg.h>
+#include <algorithm>
 #include <stdlib.h>
 #include <string.h>
 
@@ -131,6 +132,48 @@ __global__ void pad_fill_kernel(uint8_t *p, uint64_t n, uint8_t v) {
     if (i < n) p[i] = v;
 }
 
+// depth-15 interval table -> fused entries: the interval and the first 14 seed ends' SA values in one 64-byte line
+// (sector 0: Sp, width|n, SA x 6; sector 1: SA x 8), so that a whole bwa:find_seeds/6 + fmi:get_seed_ends/4 of an
+// N-free 15-character subsequence is ONE DRAM access instead of a table entry and a suffix-array run somewhere else.
+__global__ void fused_build_kernel(const uint2 *__restrict__ kdeep, const uint32_t *__restrict__ sa, uint4 *__restrict__ fused,
+                                   uint64_t entries) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= entries) return;
+    const uint2 e = kdeep[i];
+    const uint32_t ne = e.y >> 28, w = e.y & KMER_W_MASK;
+    uint32_t cnt = 0;
+    if (ne == BWT_MAX_LEN) cnt = w > BWT_MAX_RANGE ? 0u : w + 1;          // bwa.erl:31-32 width check
+    else if (ne >= BWT_MIN_LEN) cnt = w + 1;                               // not_found stop: no width check (bwa.erl:37-38)
+    uint32_t v[14];
+#pragma unroll
+    for (int t = 0; t < 14; t++) v[t] = (uint32_t)t < cnt ? sa[(size_t)(e.x - 1) + t] : 0u;
+    uint4 *o = fused + 4 * i;
+    o[0] = make_uint4(e.x, e.y, v[0], v[1]);
+    o[1] = make_uint4(v[2], v[3], v[4], v[5]);
+    o[2] = make_uint4(v[6], v[7], v[8], v[9]);
+    o[3] = make_uint4(v[10], v[11], v[12], v[13]);
+}
+
+// one thread per 16-byte word of an ASCII buffer: 2-bit codes (A0 C1 G2 T3, anything else as A) + a flag per word
+__global__ void pack_ref_kernel(const uint8_t *__restrict__ a, uint64_t len, uint64_t nwords, uint32_t *__restrict__ ref2,
+                                uint32_t *__restrict__ refx) {
+    const uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t out = 0;
+    bool bad = false;
+    if (w < nwords) {
+        const uint64_t base = w * 16;
+#pragma unroll
+        for (int t = 0; t < 16; t++) {
+            int c = 0;
+            if (base + t < len) { c = bwt_code(a[base + t]); if (c < 0) { bad = true; c = 0; } }
+            out |= (uint32_t)c << (2 * t);
+        }
+        ref2[w] = out;
+    }
+    const uint32_t m = __ballot_sync(0xFFFFFFFFu, bad);
+    if ((threadIdx.x & 31) == 0 && (w >> 5) < (nwords + 31) / 32 + 1) refx[w >> 5] = m;
+}
+
 }  // namespace
 
 int index_finish_from_device(bwt_index *h, const uint8_t *d_L, uint64_t n, uint32_t *d_sa, uint8_t *d_ref_padded,
@@ -148,12 +191,11 @@ int index_finish_from_device(bwt_index *h, const uint8_t *d_L, uint64_t n, uint3
     uint64_t nb = (n + 63) / 64;
     uint4 *d_occ = nullptr;
     uint32_t *d_cnt = nullptr, *d_tmp = nullptr, *d_flags = nullptr;
-    uint2 *d_kmer = nullptr;
+    uint2 *d_kmer = nullptr;   // (unused: the tables are built by bwt_set_kmer_depth)
     CU_TRY(cudaMalloc(&d_occ, nb * 32));
     CU_TRY(cudaMalloc(&d_cnt, nb * 4 * sizeof(uint32_t)));
     CU_TRY(cudaMalloc(&d_tmp, scan_tmp_words(nb) * sizeof(uint32_t)));
     CU_TRY(cudaMalloc(&d_flags, 4 * sizeof(uint32_t)));
-    CU_TRY(cudaMalloc(&d_kmer, 65536 * sizeof(uint2)));
     uint32_t init[4] = {0xFFFFFFFFu, 0, 0, 0};   // dollar row (min), #dollars, #bad symbols
     CU_TRY(cudaMemcpy(d_flags, init, sizeof init, cudaMemcpyHostToDevice));
     uint32_t *cA = d_cnt, *cC = d_cnt + nb, *cG = d_cnt + 2 * nb, *cT = d_cnt + 3 * nb;
@@ -174,22 +216,27 @@ int index_finish_from_device(bwt_index *h, const uint8_t *d_L, uint64_t n, uint3
     h->ref_len = ref_len;
     h->shift = shift;
     memcpy(h->pointers, pointers, sizeof h->pointers);
-    h->d_occ = d_occ; h->d_sa = d_sa; h->d_kmer = d_kmer; h->d_ref = d_ref_padded;
+    h->d_occ = d_occ; h->d_sa = d_sa; h->d_ref = d_ref_padded;
     DevIndex &dv = h->dv;
-    dv.occ = d_occ; dv.sa = d_sa; dv.kmer = d_kmer; dv.ref = d_ref_padded;
+    dv.occ = d_occ; dv.sa = d_sa; dv.ref = d_ref_padded;
     dv.ref_len_padded = ref_len + 2 * BWT_REF_EXT;
     dv.n = (uint32_t)n;
     dv.P[0] = 2; dv.P[1] = pointers[0]; dv.P[2] = pointers[1]; dv.P[3] = pointers[2];
     dv.last = pointers[3];
     dv.dollar = flags[0];
     dv.shift = shift;
-    dv.kmer_deep = nullptr;
+    dv.ktab = nullptr; dv.kdeep = nullptr; dv.fused = nullptr;
     dv.deep_k = 0;
-    kmer_kernel<<<256, 256>>>(dv, d_kmer);
-    CU_TRY(cudaGetLastError());
-    CU_TRY(cudaDeviceSynchronize());
-    h->device_bytes = nb * 32 + n * 4 + 65536 * 8 + dv.ref_len_padded;
-    // deep table: the largest depth <= 15 whose 4^k entries do not outnumber 4 rows of the index each
+    cudaFree(d_kmer);
+    {   // 2-bit copy of the padded reference for the extension kernels' window fetches
+        uint32_t *r2 = nullptr, *rx = nullptr;
+        BWT_TRY(pack_ref_device(d_ref_padded, dv.ref_len_padded, &r2, &rx, 0));
+        CU_TRY(cudaDeviceSynchronize());
+        h->d_ref2 = r2; h->d_refx = rx;
+        dv.ref2 = r2; dv.refx = rx;
+    }
+    h->device_bytes = nb * 32 + n * 4 + dv.ref_len_padded + dv.ref_len_padded / 4 + dv.ref_len_padded / 128;
+    // deepest table: the largest depth <= 15 whose 4^k entries do not outnumber 4 rows of the index each
     // (GL000193.1: k = 9; 3.1 Gbp: k = 15 = MAX_LEN, a whole search is one lookup); BWT_KMER_K overrides
     int k = 8;
     while (k < BWT_MAX_LEN && (1ull << (2 * (k + 1))) <= 4ull * n) k++;
@@ -197,66 +244,84 @@ int index_finish_from_device(bwt_index *h, const uint8_t *d_L, uint64_t n, uint3
     return bwt_set_kmer_depth(h, k);
 }
 
-// The short subsequence at the front of a read (8 + Lq mod 8 characters: 12 for 100 bp, 14 for 150 bp, 10 for 250 bp) is
-// too short for the deep table; with a table of exactly its depth it costs one lookup instead of a lookup plus up to
-// six dependent Occ steps.  Built on first use (4^k entries: 134 MB at k = 12), one per depth, kept with the index.
-const uint2 *index_tail_table(bwt_index *h, int k) {
-    if (!h || k <= BWT_MIN_LEN || k >= h->dv.deep_k || k >= BWT_MAX_LEN || !h->tail_mu) return nullptr;
-    const char *e = getenv("BWT_KMER_TAIL");
-    if (e && e[0] == '0') return nullptr;
-    std::lock_guard<std::mutex> g(*h->tail_mu);
-    if (h->d_tail[k]) return (const uint2 *)h->d_tail[k];
-    uint2 *tab = nullptr;
-    if (cudaSetDevice(h->device) != cudaSuccess || cudaMalloc(&tab, sizeof(uint2) << (2 * k)) != cudaSuccess) { cudaGetLastError(); return nullptr; }
-    DevIndex dv = h->dv;
-    dv.kmer_tail = nullptr; dv.tail_k = 0;
-    cudaMemcpy(tab, h->d_kmer, 65536 * sizeof(uint2), cudaMemcpyDeviceToDevice);
-    for (int d = 8; d < k; d++) kmer_expand_kernel<<<(unsigned)div_up_u64(1ull << (2 * d), 256), 256>>>(dv, tab, d);
-    if (cudaDeviceSynchronize() != cudaSuccess) { cudaGetLastError(); cudaFree(tab); return nullptr; }
-    h->d_tail[k] = tab;
-    h->device_bytes += sizeof(uint2) << (2 * k);
-    return tab;
+int pack_ref_device(const uint8_t *d_ascii, uint64_t len, uint32_t **d_ref2, uint32_t **d_refx, cudaStream_t stream) {
+    const uint64_t nwords = len / 16 + 4;                 // ref_word() reads up to two words past the last base
+    uint32_t *r2 = nullptr, *rx = nullptr;
+    const uint64_t nflags = (nwords + 31) / 32 + 2;
+    CU_TRY(cudaMalloc(&r2, nwords * 4));
+    if (cudaMalloc(&rx, nflags * 4) != cudaSuccess) { cudaGetLastError(); cudaFree(r2); bwt_set_error("pack_ref_device: allocation failed"); return BWT_ERR_NOMEM; }
+    cudaMemsetAsync(rx, 0, nflags * 4, stream);
+    const uint64_t threads = (nwords + 31) / 32 * 32;
+    pack_ref_kernel<<<(unsigned)div_up_u64(threads, 256), 256, 0, stream>>>(d_ascii, len, nwords, r2, rx);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { cudaFree(r2); cudaFree(rx); bwt_set_error("pack_ref_kernel: %s", cudaGetErrorString(e)); return BWT_ERR_CUDA; }
+    *d_ref2 = r2; *d_refx = rx;
+    return BWT_OK;
 }
 
-static void free_tail_tables(bwt_index *h) {
-    if (!h->tail_mu) return;
-    std::lock_guard<std::mutex> g(*h->tail_mu);
-    for (int k = 0; k < BWT_MAX_LEN; k++)
-        if (h->d_tail[k]) { cudaFree(h->d_tail[k]); h->d_tail[k] = nullptr; h->device_bytes -= sizeof(uint2) << (2 * k); }
-}
-
+// Interval tables of EVERY depth 8..k (k <= 15): a subsequence of d < 15 plain characters (the short one at the front of
+// a read: 8 + Lq mod 8 characters, any depth once read lengths vary) costs one lookup in the table of exactly its depth
+// instead of a shallower lookup plus dependent Occ steps.  Depths 8..14 share one allocation (2.9 GB when complete).
+// With k = 15 the deepest table becomes the FUSED table (64 B per 15-mer, 68.7 GB) when BWT_FUSED=1, or -- BWT_FUSED
+// unset -- when that leaves 40 GB of the device free; BWT_FUSED=0 keeps the plain 8-byte table (8.6 GB).
 extern "C" int bwt_set_kmer_depth(bwt_index *h, int k) {
     if (!h || (k != 0 && (k < 8 || k > BWT_MAX_LEN))) { bwt_set_error("bwt_set_kmer_depth: depth must be 0 or 8..15"); return BWT_ERR_ARG; }
+    if (k == 0) k = 8;
     CU_TRY(cudaSetDevice(h->device));
     CU_TRY(cudaDeviceSynchronize());
     if (!h->tail_mu) h->tail_mu = new std::mutex();
-    free_tail_tables(h);
-    if (h->d_kmer_deep) {
-        h->device_bytes -= (8ull << (2 * h->dv.deep_k));
-        cudaFree(h->d_kmer_deep);
-        h->d_kmer_deep = nullptr;
+    auto drop = [&](void *&p, uint64_t bytes) { if (p) { cudaFree(p); p = nullptr; h->device_bytes -= bytes; } };
+    if (h->dv.deep_k) {
+        drop(h->d_ktab, ktab_off(std::min(h->dv.deep_k, 14) + 1) * 8);
+        drop(h->d_kdeep, 8ull << 30);
+        drop(h->d_fused, 64ull << 30);
     }
-    h->dv.kmer_deep = nullptr;
-    h->dv.deep_k = 0;
-    if (k <= 8) return BWT_OK;                          // the depth-8 table alone
-    uint2 *tab = nullptr;
-    const uint64_t entries = 1ull << (2 * k);
-    if (cudaMalloc(&tab, entries * sizeof(uint2)) != cudaSuccess) {
+    h->dv.ktab = nullptr; h->dv.kdeep = nullptr; h->dv.fused = nullptr; h->dv.deep_k = 0;
+    const int kt = std::min(k, 14);
+    uint2 *ktab = nullptr, *work = nullptr;
+    const uint64_t kt_entries = ktab_off(kt + 1), work_entries = 1ull << (2 * k);
+    if (cudaMalloc(&ktab, kt_entries * sizeof(uint2)) != cudaSuccess || cudaMalloc(&work, work_entries * sizeof(uint2)) != cudaSuccess) {
         cudaGetLastError();
-        bwt_set_error("k-mer table of depth %d (%llu MB) does not fit", k, (unsigned long long)(entries * 8 >> 20));
+        cudaFree(ktab);
+        bwt_set_error("k-mer tables of depth %d (%llu MB) do not fit", k, (unsigned long long)((kt_entries + work_entries) * 8 >> 20));
         return BWT_ERR_NOMEM;
     }
-    CU_TRY(cudaMemcpy(tab, h->d_kmer, 65536 * sizeof(uint2), cudaMemcpyDeviceToDevice));
-    for (int d = 8; d < k; d++) {
-        kmer_expand_kernel<<<(unsigned)div_up_u64(1ull << (2 * d), 256), 256>>>(h->dv, tab, d);
+    kmer_kernel<<<256, 256>>>(h->dv, work);
+    for (int d = 8; d <= k; d++) {
+        if (d <= kt) CU_TRY(cudaMemcpyAsync(ktab + ktab_off(d), work, (sizeof(uint2)) << (2 * d), cudaMemcpyDeviceToDevice, 0));
+        if (d < k) kmer_expand_kernel<<<(unsigned)div_up_u64(1ull << (2 * d), 256), 256>>>(h->dv, work, d);
         CU_TRY(cudaGetLastError());
     }
     cudaError_t e = cudaDeviceSynchronize();
-    if (e != cudaSuccess) { cudaFree(tab); bwt_set_error("k-mer table build: %s", cudaGetErrorString(e)); return BWT_ERR_CUDA; }
-    h->d_kmer_deep = tab;
-    h->dv.kmer_deep = tab;
-    h->dv.deep_k = k;
-    h->device_bytes += entries * 8;
+    if (e != cudaSuccess) { cudaFree(ktab); cudaFree(work); bwt_set_error("k-mer table build: %s", cudaGetErrorString(e)); return BWT_ERR_CUDA; }
+    h->d_ktab = ktab; h->dv.ktab = ktab; h->dv.deep_k = k;
+    h->device_bytes += kt_entries * 8;
+    if (k < BWT_MAX_LEN) { cudaFree(work); return BWT_OK; }
+    h->d_kdeep = work; h->dv.kdeep = work;
+    h->device_bytes += 8ull << 30;
+    // fused table?
+    const char *ef = getenv("BWT_FUSED");
+    int want = ef ? atoi(ef) : -1;
+    const uint64_t fused_bytes = 64ull << 30;
+    if (want < 0) {
+        size_t fr = 0, tot = 0;
+        if (cudaMemGetInfo(&fr, &tot) != cudaSuccess) { cudaGetLastError(); fr = 0; }
+        want = fr >= fused_bytes + (40ull << 30) ? 1 : 0;
+    }
+    if (!want) return BWT_OK;
+    uint4 *fused = nullptr;
+    if (cudaMalloc(&fused, fused_bytes) != cudaSuccess) {
+        cudaGetLastError();
+        if (ef) { bwt_set_error("fused k-mer table (64 GiB) does not fit"); return BWT_ERR_NOMEM; }
+        return BWT_OK;
+    }
+    fused_build_kernel<<<(unsigned)div_up_u64(work_entries, 256), 256>>>(work, h->dv.sa, fused, work_entries);
+    e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { cudaFree(fused); bwt_set_error("fused table build: %s", cudaGetErrorString(e)); return BWT_ERR_CUDA; }
+    cudaFree(work);
+    h->d_kdeep = nullptr; h->dv.kdeep = nullptr;
+    h->d_fused = fused; h->dv.fused = fused;
+    h->device_bytes += fused_bytes - (8ull << 30);
     return BWT_OK;
 }
 
@@ -350,9 +415,9 @@ extern "C" int bwt_close(bwt_index *h) {
     if (!h) return BWT_OK;
     cudaSetDevice(h->device);
     aligner_cache_drop(h);
-    free_tail_tables(h);
     delete h->tail_mu;
-    cudaFree(h->d_occ); cudaFree(h->d_sa); cudaFree(h->d_kmer); cudaFree(h->d_kmer_deep); cudaFree(h->d_ref);
+    cudaFree(h->d_occ); cudaFree(h->d_sa); cudaFree(h->d_ktab); cudaFree(h->d_kdeep); cudaFree(h->d_fused); cudaFree(h->d_ref);
+    cudaFree(h->d_ref2); cudaFree(h->d_refx);
     delete h;
     return BWT_OK;
 }
@@ -367,6 +432,7 @@ extern "C" int bwt_info(const bwt_index *h, bwt_index_info *info) {
     info->device_bytes = h->device_bytes;
     info->device = h->device;
     info->kmer_k = h->dv.deep_k ? h->dv.deep_k : 8;
+    info->fused = h->dv.fused ? 1 : 0;
     return BWT_OK;
 }
 

@@ -78,11 +78,21 @@ __device__ __forceinline__ void first_interval(const DevIndex &ix, int c, uint32
     else { sp = ix.P[3]; ep = ix.last; }
 }
 
+// entry of the depth-`depth` interval table (8 <= depth <= ix.deep_k) for the k-mer idx (last character in bits 0-1)
+__device__ __forceinline__ uint2 kmer_lookup(const DevIndex &ix, int depth, uint32_t idx) {
+    idx &= (uint32_t)((1ull << (2 * depth)) - 1ull);
+    if (depth == BWT_MAX_LEN)
+        return ix.fused ? __ldg(reinterpret_cast<const uint2 *>(ix.fused + 4 * (size_t)idx)) : __ldg(ix.kdeep + idx);
+    return __ldg(ix.ktab + ktab_off(depth) + idx);
+}
+
 // bwa:find_seeds/6 on q[0..len), len >= 1, once the characters next to the end are known as 2-bit codes:
 // c = code of the last character ('N' counts as 'A'), idx = codes of the last `good` characters (last one in
 // bits 0-1), all of them plain ACGT.  use_table: consult the k-mer tables (false while building them).
-__device__ __forceinline__ SearchRes search_core(const DevIndex &ix, const uint8_t *q, int len, int c, uint32_t idx,
-                                                 int good, bool use_table) {
+// PACKED: q is null and the characters come from the packed read pkr (length lq_total) -- plain ACGT throughout.
+template <bool PACKED>
+__device__ __forceinline__ SearchRes search_core_t(const DevIndex &ix, const uint8_t *q, const uint32_t *pkr, int lq_total, int len,
+                                                   int c, uint32_t idx, int good, bool use_table) {
     SearchRes R;
     R.table = 0;
     uint32_t sp = 0, ep = 0;
@@ -90,13 +100,8 @@ __device__ __forceinline__ SearchRes search_core(const DevIndex &ix, const uint8
     bool have = false, stopped = false;
     if (use_table && good >= BWT_MIN_LEN) {
         // the table of depth d applies when the d-1 characters before the last are plain ACGT: the deepest one that fits
-        int depth = BWT_MIN_LEN;
-        const uint2 *tab = ix.kmer;
-        if (ix.deep_k > 0) {
-            if (good >= ix.deep_k) { depth = ix.deep_k; tab = ix.kmer_deep; }
-            else if (ix.tail_k > 0 && good >= ix.tail_k) { depth = ix.tail_k; tab = ix.kmer_tail; }
-        }
-        const uint2 e = __ldg(tab + (idx & (uint32_t)((1ull << (2 * depth)) - 1ull)));
+        const int depth = good < ix.deep_k ? good : ix.deep_k;
+        const uint2 e = kmer_lookup(ix, depth, idx);
         int ne = (int)(e.y >> 28);
         if (ne) {
             R.table = ne;                              // characters whose steps the table served
@@ -110,18 +115,22 @@ __device__ __forceinline__ SearchRes search_core(const DevIndex &ix, const uint8
     while (!stopped) {
         if (n == BWT_MAX_LEN) { checked = true; break; }             // bwa.erl:31-32
         if (k < 0) { checked = true; break; }                        // bwa.erl:44-45
-        uint8_t ch = q[k];
-        if (ch == 'N') { checked = true; break; }                    // bwa.erl:33-34
-        int cc = bwt_code(ch);
-        if (cc < 0) {
-            if (ch == '$' && sp < ep && ix.dollar >= sp && ix.dollar <= ep - 1) {
-                // the '$' row's I is 0: the walk lands on (0,0) and every later clause reaches
-                // get_seed_ends(FM,0,0,N): no_seeds for N < 8, element(0,FM) = badarg otherwise
-                n++;
-                R.sp = R.ep = 0; R.n = n; R.status = n < BWT_MIN_LEN ? BWT_NO_SEEDS : BWT_SEARCH_CRASH;
-                return R;
+        int cc;
+        if (PACKED) cc = read_code(pkr, lq_total, k);
+        else {
+            uint8_t ch = q[k];
+            if (ch == 'N') { checked = true; break; }                // bwa.erl:33-34
+            cc = bwt_code(ch);
+            if (cc < 0) {
+                if (ch == '$' && sp < ep && ix.dollar >= sp && ix.dollar <= ep - 1) {
+                    // the '$' row's I is 0: the walk lands on (0,0) and every later clause reaches
+                    // get_seed_ends(FM,0,0,N): no_seeds for N < 8, element(0,FM) = badarg otherwise
+                    n++;
+                    R.sp = R.ep = 0; R.n = n; R.status = n < BWT_MIN_LEN ? BWT_NO_SEEDS : BWT_SEARCH_CRASH;
+                    return R;
+                }
+                checked = false; break;                              // no row has this L: not_found
             }
-            checked = false; break;                                  // no row has this L: not_found
         }
         if (!lf_step(ix, sp, ep, cc)) { checked = false; break; }    // bwa.erl:37-38: no width check here
         n++; k--;
@@ -130,6 +139,16 @@ __device__ __forceinline__ SearchRes search_core(const DevIndex &ix, const uint8
     if (checked && ep - sp > BWT_MAX_RANGE) R.status = BWT_TOO_MANY_SEEDS;
     else R.status = n >= BWT_MIN_LEN ? BWT_SEEDS : BWT_NO_SEEDS;
     return R;
+}
+
+__device__ __forceinline__ SearchRes search_core(const DevIndex &ix, const uint8_t *q, int len, int c, uint32_t idx,
+                                                 int good, bool use_table) {
+    return search_core_t<false>(ix, q, nullptr, 0, len, c, idx, good, use_table);
+}
+
+// bwa:find_seeds/6 on the first `end` bases of a packed read (plain ACGT): idx = its last 15 (or fewer) codes
+__device__ __forceinline__ SearchRes search_packed(const DevIndex &ix, const uint32_t *pkr, int lq, int end, uint32_t idx) {
+    return search_core_t<true>(ix, nullptr, pkr, lq, end, (int)(idx & 3u), idx, end < BWT_MAX_LEN ? end : BWT_MAX_LEN, true);
 }
 
 // bwa:find_seeds/6 on q[0..len), len >= 1, from the ASCII bytes

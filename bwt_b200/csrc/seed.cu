@@ -112,8 +112,10 @@ struct GroupShared {        // per-group scratch for the task list of one read
 enum { SGA_DONE = 0, SGA_DEFER = 1 };
 
 // One read, one group of G lanes.  `seeds` holds `cap` uint32 (a power of two) in shared or global memory.
+// q: the read's ASCII text, or null when it is a plain (packed) read: then pkr points at its packed words.
 template <int G, int MAXT, bool SLOW, typename Tile>
-__device__ __forceinline__ int sga_read(const Tile &tile, const DevIndex &ix, const uint8_t *__restrict__ q, int lq,
+__device__ __forceinline__ int sga_read(const Tile &tile, const DevIndex &ix, const uint8_t *__restrict__ q,
+                                        const uint32_t *__restrict__ pkr, int lq,
                                         uint32_t read, uint32_t *seeds, uint32_t cap, const GroupShared &gs,
                                         int32_t *read_status, uint32_t *ncl, uint32_t *cl_base, Cluster *clusters,
                                         uint32_t cl_cap, SlowRead *slow, uint32_t slow_cap, SeedCounters *ctr,
@@ -125,8 +127,10 @@ __device__ __forceinline__ int sga_read(const Tile &tile, const DevIndex &ix, co
     }
     // -- task list: where each subsequence ends and what is added to its seed ends
     bool has_n = false;
-    for (int i = lane; i < lq; i += G) has_n |= (q[i] == 'N');
-    has_n = tile.any(has_n);
+    if (q) {
+        for (int i = lane; i < lq; i += G) has_n |= (q[i] == 'N');
+        has_n = tile.any(has_n);
+    }
     int nt;
     if (!has_n) {
         nt = lq >= BWT_MIN_LEN ? (lq - BWT_MIN_LEN) / BWT_MIN_LEN + 1 : 0;
@@ -153,7 +157,9 @@ __device__ __forceinline__ int sga_read(const Tile &tile, const DevIndex &ix, co
     unsigned long long lf = 0, hbm = 0;
     for (int k = lane; k < nt; k += G) {
         int end = has_n ? (int)gs.t_end[k] : lq - BWT_MIN_LEN * k;
-        SearchRes r = search_sub(ix, q, end, true);
+        SearchRes r;
+        if (q) r = search_sub(ix, q, end, true);
+        else r = search_packed(ix, pkr, lq, end, __funnelshift_r(__ldg(pkr + (k >> 1)), __ldg(pkr + (k >> 1) + 1), (k & 1) * 16) & 0x3FFFFFFFu);
         crash |= (r.status == BWT_SEARCH_CRASH);
         uint32_t cnt = (r.status == BWT_SEEDS) ? (r.ep - r.sp + 1) : 0u;
         if (cnt > BWT_MAX_SEEDS_PER_READ) cnt = BWT_MAX_SEEDS_PER_READ + 1;     // flagged below
@@ -418,84 +424,88 @@ __device__ __forceinline__ void sort_vote_regs(const Tile &tile, const uint32_t 
     }
 }
 
+// One plain read (packed words pkr, lq bases).  Per subsequence ONE lookup: the fused depth-15 entry (interval + its
+// first 14 SA values in one 64-byte line) when the subsequence has 15 characters or more, else the interval table of
+// exactly its depth (+ the suffix-array run).  The lane that looked a subsequence up writes its seed ends.
 template <int G, int MAXT, typename Tile>
-__device__ __forceinline__ int sga_fast_read(const Tile &tile, const DevIndex &ix, const uint8_t *__restrict__ q, const int lq,
-                                             const uint32_t read, uint32_t *seeds, uint32_t *pack, const GroupShared &gs,
+__device__ __forceinline__ int sga_fast_read(const Tile &tile, const DevIndex &ix, const uint32_t *__restrict__ pkr, const int lq,
+                                             const uint32_t read, uint32_t *seeds,
                                              int32_t *read_status, uint32_t *ncl, uint32_t *cl_base, Cluster *clusters,
                                              const uint32_t cl_cap, SeedCounters *ctr, uint32_t (&acc)[CTR_N]) {
     const int lane = tile.thread_rank();
-    // -- pack the read, reversed (base lq-1-i at bits 2i); any byte outside ACGT sends the read to the general path.
-    //    Word w holds the 16 bases ending at e = lq-1-16w: packed forward four bytes at a time, then turned round.
-    const int nw = (lq + 15) >> 4;
-    bool valid = true;
-    for (int w = lane; w <= nw; w += G) {
-        uint32_t word = 0;
-        if (w < nw) {
-            const int e = lq - 1 - 16 * w, start = max(e - 15, 0), cnt = e - start + 1;
-            uint32_t fw = pack16_acgt(q + start, cnt, valid);                // base start+t at bits 2t, codes A0 C1 T2 G3
-            fw ^= (fw >> 1) & 0x55555555u;                                   // -> A0 C1 G2 T3
-            fw <<= 2 * (16 - cnt);                                           // a short first word: bases to the top
-            const uint32_t rv = __brev(fw);                                  // reverses the bases and the bits inside each
-            word = ((rv & 0xAAAAAAAAu) >> 1) | ((rv & 0x55555555u) << 1);
-        }
-        pack[w] = word;                                                      // pack[nw] = 0: upper word of the last funnel shift
-    }
-    if (tile.any(!valid)) return SGA_FALLBACK;
-    tile.sync();
     const int nt = lq >= BWT_MIN_LEN ? (lq - BWT_MIN_LEN) / BWT_MIN_LEN + 1 : 0;
-    // -- searches: lane k takes subsequences k, k+G, ...; subsequence k ends 8k bases before the end of the read
-    unsigned long long lf = 0, hbm = 0;
-    for (int k = lane; k < nt; k += G) {
-        const int end = lq - BWT_MIN_LEN * k;
-        const uint32_t idx = __funnelshift_r(pack[k >> 1], pack[(k >> 1) + 1], (k & 1) * 16) & 0x3FFFFFFFu;
-        SearchRes r = search_core(ix, q, end, (int)(idx & 3u), idx, end < BWT_MAX_LEN ? end : BWT_MAX_LEN, true);
-        uint32_t cnt = (r.status == BWT_SEEDS) ? (r.ep - r.sp + 1) : 0u;
-        if (cnt > BWT_MAX_SEEDS_PER_READ) cnt = BWT_MAX_SEEDS_PER_READ + 1;
-        gs.t_res[k] = make_uint2(r.sp, (cnt << 4) | (uint32_t)r.n);
-        int steps = r.n > 0 ? r.n - 1 : 0;
-        lf += steps;
-        hbm += r.table ? r.n - r.table : steps;
-    }
-    tile.sync();
-    // -- slots: exclusive prefix of the seed counts; Qty = searches that produced a list (sga.erl:30-33)
-    uint32_t total = 0, qty = 0;
+    uint32_t total = 0, qty = 0, lf = 0, hbm = 0;
+    bool fb = false;
     for (int k0 = 0; k0 < nt; k0 += G) {
-        int k = k0 + lane;
-        uint32_t c = k < nt ? (gs.t_res[k].y >> 4) : 0u;
-        uint32_t inc = c;
+        const int k = k0 + lane;
+        uint32_t cnt = 0, sp = 0, add = 0;
+        uint4 a = make_uint4(0u, 0u, 0u, 0u), b = a;
+        const uint4 *e = nullptr;
+        if (k < nt) {
+            const int end = lq - BWT_MIN_LEN * k;                 // subsequence k ends 8k bases before the end of the read
+            const uint32_t idx = __funnelshift_r(__ldg(pkr + (k >> 1)), __ldg(pkr + (k >> 1) + 1), (k & 1) * 16) & 0x3FFFFFFFu;
+            if (end >= BWT_MAX_LEN && ix.fused) {
+                e = ix.fused + 4 * (size_t)idx;
+                a = __ldg(e); b = __ldg(e + 1);
+                const uint32_t ne = a.y >> 28, w = a.y & KMER_W_MASK;
+                if (ne == 0) fb = true;                            // width beyond 28 bits: the general path walks it
+                else {
+                    if (ne == BWT_MAX_LEN) cnt = w > BWT_MAX_RANGE ? 0u : w + 1;     // bwa.erl:31-32
+                    else if (ne >= BWT_MIN_LEN) cnt = w + 1;                          // not_found stop: no width check
+                    sp = a.x; add = ne + (uint32_t)(BWT_MIN_LEN * k);
+                    lf += ne - 1;
+                }
+            } else {
+                const SearchRes r = search_packed(ix, pkr, lq, end, idx);
+                if (r.status == BWT_SEEDS) cnt = r.ep - r.sp + 1;
+                sp = r.sp; add = (uint32_t)r.n + (uint32_t)(BWT_MIN_LEN * k);
+                const uint32_t steps = r.n > 0 ? r.n - 1 : 0;
+                lf += steps;
+                hbm += r.table ? r.n - r.table : steps;
+            }
+            if (cnt > BWT_MAX_SEEDS_PER_READ) cnt = BWT_MAX_SEEDS_PER_READ + 1;
+        }
+        // slots: exclusive prefix of the seed counts; Qty = searches that produced a list (sga.erl:30-33)
+        uint32_t inc = cnt;
 #pragma unroll
         for (int d = 1; d < G; d <<= 1) {
-            uint32_t t = tile.shfl_up(inc, d);
+            const uint32_t t = tile.shfl_up(inc, d);
             if (lane >= d) inc += t;
         }
-        if (k < nt) gs.t_pos[k] = total + inc - c;
+        const uint32_t pos = total + inc - cnt;
         total += tile.shfl(inc, G - 1);
-        qty += __popc(tile.ballot(c > 0));
+        qty += __popc(tile.ballot(cnt > 0));
+        // seed ends = SA + N + the subsequence's shift (fmi.erl:89-100, sga.erl:37-39); beyond 8G the read leaves this path
+        if (cnt && pos + cnt <= (uint32_t)(8 * G)) {
+            uint32_t t0 = 0;
+            if (e) {
+                const uint32_t v[6] = {a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+                for (int t = 0; t < 6; t++) if ((uint32_t)t < cnt) seeds[pos + t] = v[t] + add;
+                if (cnt > 6) {
+                    const uint4 c = __ldg(e + 2), d = __ldg(e + 3);
+                    const uint32_t u[8] = {c.x, c.y, c.z, c.w, d.x, d.y, d.z, d.w};
+#pragma unroll
+                    for (int t = 0; t < 8; t++) if ((uint32_t)(t + 6) < cnt) seeds[pos + 6 + t] = u[t] + add;
+                }
+                t0 = 14;
+            }
+            for (uint32_t t = t0; t < cnt; t++) seeds[pos + t] = __ldg(ix.sa + (sp - 1) + t) + add;
+        }
     }
+    if (tile.any(fb) || total > (uint32_t)(8 * G)) return SGA_FALLBACK;   // the general path redoes (and counts) the searches (rare)
 #pragma unroll
     for (int d = G / 2; d > 0; d >>= 1) {
         lf += tile.shfl_down(lf, d);
         hbm += tile.shfl_down(hbm, d);
     }
-    if (total > (uint32_t)(8 * G)) return SGA_FALLBACK;       // the general path redoes (and counts) the searches (rare)
     if (lane == 0) {
-        acc[CTR_SEARCHES] += (uint32_t)nt; acc[CTR_LF] += (uint32_t)lf; acc[CTR_HBM_LF] += (uint32_t)hbm; acc[CTR_LOCATED] += total;
+        acc[CTR_SEARCHES] += (uint32_t)nt; acc[CTR_LF] += lf; acc[CTR_HBM_LF] += hbm; acc[CTR_LOCATED] += total;
         read_status[read] = BWT_READ_OK;
     }
     if (qty < 2) {                                             // get_similar(0|1,_) -> []  (sga.erl:42-43)
         if (lane == 0) { ncl[read] = 0; cl_base[read] = 0; }
         return SGA_DONE;
-    }
-    tile.sync();
-    // -- locate, balanced over all rows: row t belongs to the last task whose first slot is <= t
-    for (uint32_t t = lane; t < total; t += G) {
-        int lo = 0, hi = nt - 1;                               // invariant: t_pos[lo] <= t
-        while (lo < hi) {
-            int mid = (lo + hi + 1) >> 1;
-            if (gs.t_pos[mid] <= t) lo = mid; else hi = mid - 1;
-        }
-        const uint2 tr = gs.t_res[lo];
-        seeds[t] = __ldg(ix.sa + (tr.x - 1) + (t - gs.t_pos[lo])) + (tr.y & 15u) + (uint32_t)(BWT_MIN_LEN * lo);
     }
     tile.sync();
     const uint32_t need = 2 + qty / 7;
@@ -508,8 +518,7 @@ __device__ __forceinline__ int sga_fast_read(const Tile &tile, const DevIndex &i
 }
 
 template <int G, int MAXT>
-__global__ void __launch_bounds__(SGA_BLOCK, SGA_MIN_BLOCKS) sga_kernel(DevIndex ix, const uint8_t *__restrict__ reads,
-                                                        const int64_t *__restrict__ offs, int64_t n_reads,
+__global__ void __launch_bounds__(SGA_BLOCK, SGA_MIN_BLOCKS) sga_kernel(DevIndex ix, DevReads R, int64_t n_reads,
                                                         int32_t *read_status, uint32_t *ncl, uint32_t *cl_base,
                                                         Cluster *clusters, uint32_t cl_cap, SlowRead *slow,
                                                         uint32_t slow_cap, SeedCounters *ctr) {
@@ -519,8 +528,6 @@ __global__ void __launch_bounds__(SGA_BLOCK, SGA_MIN_BLOCKS) sga_kernel(DevIndex
     __shared__ uint16_t s_end[GPB][MAXT], s_shift[GPB][MAXT];
     __shared__ uint2 s_res[GPB][MAXT];
     __shared__ uint32_t s_pos[GPB][MAXT];
-    constexpr int MAXW = (BWT_MIN_LEN * (MAXT - 1) + BWT_MAX_LEN + 15) / 16 + 2;     // packed read words
-    __shared__ uint32_t s_pack[GPB][MAXW];
     __shared__ unsigned long long s_ctr[CTR_N];
     if (threadIdx.x < CTR_N) s_ctr[threadIdx.x] = 0;
     __syncthreads();
@@ -529,8 +536,12 @@ __global__ void __launch_bounds__(SGA_BLOCK, SGA_MIN_BLOCKS) sga_kernel(DevIndex
     GroupShared gs{s_end[g], s_shift[g], s_res[g], s_pos[g]};
     uint32_t acc[CTR_N] = {0u, 0u, 0u, 0u, 0u};                   // lane 0 of the group: work counters of its fast-path reads
     for (int64_t read = (int64_t)blockIdx.x * GPB + g; read < n_reads; read += (int64_t)gridDim.x * GPB) {
-        const uint8_t *q = reads + offs[read];
-        int lq = (int)(offs[read + 1] - offs[read]);
+        int lq = (int)__ldg(R.len + read);
+        const bool plain = !read_is_exc(R, (uint32_t)read);
+        const uint8_t *q = nullptr;
+        const uint32_t *pkr = nullptr;
+        if (plain) pkr = R.pk + __ldg(R.woff + read);
+        else q = read_ascii(R, (uint32_t)read, lq);
         // a read with more subsequences than MAXT cannot run in this instantiation: the launcher picks
         // G/MAXT from the longest read of the batch, so this only guards against misuse
         if (lq > BWT_MIN_LEN * (MAXT - 1) + BWT_MAX_LEN && MAXT < SGA_MAX_TASKS) {
@@ -538,11 +549,11 @@ __global__ void __launch_bounds__(SGA_BLOCK, SGA_MIN_BLOCKS) sga_kernel(DevIndex
             continue;
         }
         int how = SGA_FALLBACK;
-        if (lq <= BWT_MIN_LEN * (MAXT - 1) + BWT_MAX_LEN)
-            how = sga_fast_read<G, MAXT>(tile, ix, q, lq, (uint32_t)read, s_seeds[g], s_pack[g], gs, read_status, ncl, cl_base,
+        if (plain && lq <= BWT_MIN_LEN * (MAXT - 1) + BWT_MAX_LEN)
+            how = sga_fast_read<G, MAXT>(tile, ix, pkr, lq, (uint32_t)read, s_seeds[g], read_status, ncl, cl_base,
                                          clusters, cl_cap, ctr, acc);
         if (how == SGA_FALLBACK)                                  // 'N' / other bytes, or more seed ends than registers hold
-            sga_read<G, MAXT, false>(tile, ix, q, lq, (uint32_t)read, s_seeds[g], CAP, gs, read_status, ncl, cl_base,
+            sga_read<G, MAXT, false>(tile, ix, q, pkr, lq, (uint32_t)read, s_seeds[g], CAP, gs, read_status, ncl, cl_base,
                                      clusters, cl_cap, slow, slow_cap, ctr, s_ctr);
         tile.sync();
     }
@@ -554,12 +565,12 @@ __global__ void __launch_bounds__(SGA_BLOCK, SGA_MIN_BLOCKS) sga_kernel(DevIndex
     flush_counters(s_ctr, ctr);
 }
 
-// reads whose seed ends overflow the shared-memory budget: one warp per read, seeds in HBM scratch
-__global__ void __launch_bounds__(SGA_BLOCK) sga_slow_kernel(DevIndex ix, const uint8_t *__restrict__ reads,
-                                                             const int64_t *__restrict__ offs,
-                                                             const SlowRead *__restrict__ slow,
-                                                             const uint64_t *__restrict__ slow_off, uint32_t n_slow,
-                                                             uint32_t *scratch, int32_t *read_status, uint32_t *ncl,
+// reads whose seed ends overflow the shared-memory budget: one warp per read, seeds in an HBM scratch handed out by a
+// device-side cursor (scratch_cap words; a read that does not fit raises scratch_overflow and the host retries larger)
+__global__ void __launch_bounds__(SGA_BLOCK) sga_slow_kernel(DevIndex ix, DevReads R,
+                                                             const SlowRead *__restrict__ slow, uint32_t slow_cap,
+                                                             uint32_t *scratch, unsigned long long scratch_cap,
+                                                             int32_t *read_status, uint32_t *ncl,
                                                              uint32_t *cl_base, Cluster *clusters, uint32_t cl_cap,
                                                              SeedCounters *ctr) {
     constexpr int G = 32, GPB = SGA_BLOCK / G, MAXT = SGA_MAX_TASKS;
@@ -569,12 +580,24 @@ __global__ void __launch_bounds__(SGA_BLOCK) sga_slow_kernel(DevIndex ix, const 
     auto tile = cg::tiled_partition<G>(cg::this_thread_block());
     const int g = threadIdx.x / G;
     GroupShared gs{s_end[g], s_shift[g], s_res[g], s_pos[g]};
+    const uint32_t n_slow = min(ctr->n_slow, slow_cap);
     for (uint32_t w = blockIdx.x * GPB + g; w < n_slow; w += gridDim.x * GPB) {
-        uint32_t read = slow[w].read;
-        const uint8_t *q = reads + offs[read];
-        int lq = (int)(offs[read + 1] - offs[read]);
-        uint64_t cap = slow_off[w + 1] - slow_off[w];
-        sga_read<G, MAXT, true>(tile, ix, q, lq, read, scratch + slow_off[w], (uint32_t)cap, gs, read_status, ncl,
+        const uint32_t read = slow[w].read;
+        unsigned long long p = 1;
+        while (p < slow[w].seeds) p <<= 1;
+        unsigned long long base = 0;
+        if (tile.thread_rank() == 0) base = atomicAdd(&ctr->scratch_used, p);
+        base = tile.shfl(base, 0);
+        if (base + p > scratch_cap) {
+            if (tile.thread_rank() == 0) { atomicExch(&ctr->scratch_overflow, 1u); ncl[read] = 0; cl_base[read] = 0; }
+            continue;
+        }
+        int lq = (int)R.len[read];
+        const uint8_t *q = nullptr;
+        const uint32_t *pkr = nullptr;
+        if (!read_is_exc(R, read)) pkr = R.pk + R.woff[read];
+        else q = read_ascii(R, read, lq);
+        sga_read<G, MAXT, true>(tile, ix, q, pkr, lq, read, scratch + base, (uint32_t)p, gs, read_status, ncl,
                                 cl_base, clusters, cl_cap, nullptr, 0, ctr, nullptr);
         tile.sync();
     }
@@ -628,7 +651,7 @@ int launch_search(const DevIndex &ix, const uint8_t *d_subs, const int64_t *d_of
     return BWT_OK;
 }
 
-int launch_sga(const DevIndex &ix, const uint8_t *d_reads, const int64_t *d_offs, int64_t n_reads, int max_read_len,
+int launch_sga(const DevIndex &ix, const DevReads &R, int64_t n_reads, int max_read_len,
                int32_t *d_read_status, uint32_t *d_ncl, uint32_t *d_cl_base, Cluster *d_clusters, uint32_t cl_cap,
                SlowRead *d_slow, uint32_t slow_cap, SeedCounters *d_ctr, cudaStream_t stream) {
     if (n_reads <= 0) return BWT_OK;
@@ -644,12 +667,12 @@ int launch_sga(const DevIndex &ix, const uint8_t *d_reads, const int64_t *d_offs
     if (max_read_len <= BWT_MIN_LEN * 15 + BWT_MAX_LEN) {
         int64_t blocks = (n_reads + 7) / 8;
         if (blocks > 148 * 256) blocks = 148 * 256;
-        sga_kernel<16, 16><<<(unsigned)blocks, SGA_BLOCK, 0, stream>>>(ix, d_reads, d_offs, n_reads, d_read_status, d_ncl,
+        sga_kernel<16, 16><<<(unsigned)blocks, SGA_BLOCK, 0, stream>>>(ix, R, n_reads, d_read_status, d_ncl,
                                                                      d_cl_base, d_clusters, cl_cap, d_slow, slow_cap, d_ctr);
     } else {
         int64_t blocks = (n_reads + 3) / 4;
         if (blocks > 148 * 256) blocks = 148 * 256;
-        sga_kernel<32, SGA_MAX_TASKS><<<(unsigned)blocks, SGA_BLOCK, 0, stream>>>(ix, d_reads, d_offs, n_reads, d_read_status,
+        sga_kernel<32, SGA_MAX_TASKS><<<(unsigned)blocks, SGA_BLOCK, 0, stream>>>(ix, R, n_reads, d_read_status,
                                                                                d_ncl, d_cl_base, d_clusters, cl_cap, d_slow,
                                                                                slow_cap, d_ctr);
     }
@@ -657,15 +680,13 @@ int launch_sga(const DevIndex &ix, const uint8_t *d_reads, const int64_t *d_offs
     return BWT_OK;
 }
 
-int launch_sga_slow(const DevIndex &ix, const uint8_t *d_reads, const int64_t *d_offs, const SlowRead *d_slow,
-                    const uint64_t *d_slow_off, uint32_t n_slow, uint32_t *d_scratch, int32_t *d_read_status,
+// always launched (the list length is read on the device): a few blocks that leave at once when no read was deferred
+int launch_sga_slow(const DevIndex &ix, const DevReads &R, const SlowRead *d_slow, uint32_t slow_cap,
+                    uint32_t *d_scratch, uint64_t scratch_cap, int32_t *d_read_status,
                     uint32_t *d_ncl, uint32_t *d_cl_base, Cluster *d_clusters, uint32_t cl_cap, SeedCounters *d_ctr,
                     cudaStream_t stream) {
-    if (n_slow == 0) return BWT_OK;
-    unsigned blocks = (n_slow + 3) / 4;
-    if (blocks > 148 * 16) blocks = 148 * 16;
-    sga_slow_kernel<<<blocks, SGA_BLOCK, 0, stream>>>(ix, d_reads, d_offs, d_slow, d_slow_off, n_slow, d_scratch,
-                                                      d_read_status, d_ncl, d_cl_base, d_clusters, cl_cap, d_ctr);
+    sga_slow_kernel<<<148, SGA_BLOCK, 0, stream>>>(ix, R, d_slow, slow_cap, d_scratch, (unsigned long long)scratch_cap,
+                                                   d_read_status, d_ncl, d_cl_base, d_clusters, cl_cap, d_ctr);
     CU_TRY(cudaGetLastError());
     return BWT_OK;
 }

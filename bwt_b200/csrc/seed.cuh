@@ -22,7 +22,8 @@ struct SeedCounters {   // device-side counters of one run
     uint32_t n_clusters;      // clusters appended (sum over the sub-lists; set by launch_sga_finish)
     uint32_t n_slow;          // reads whose seed ends did not fit the shared-memory budget
     uint32_t cluster_overflow;
-    uint32_t pad;
+    uint32_t scratch_overflow;   // a deferred read did not fit the slow kernel's scratch
+    unsigned long long scratch_used;
     uint32_t dense_base[SGA_SUBLISTS];          // first dense slot of each sub-list (launch_sga_finish)
     uint32_t sub_n[SGA_SUBLISTS * 32];          // cursor of sub-list r at [32 r]
 };
@@ -35,13 +36,13 @@ constexpr int SGA_MAX_TASKS = 128;    // subsequences per read => BWT_MAX_READ_L
 int launch_search(const DevIndex &ix, const uint8_t *d_subs, const int64_t *d_offs, int64_t n, int32_t fixed_len,
                   int32_t *d_status, uint32_t *d_sp, uint32_t *d_ep, int32_t *d_n, SeedCounters *d_ctr,
                   cudaStream_t stream);
-int launch_sga(const DevIndex &ix, const uint8_t *d_reads, const int64_t *d_offs, int64_t n_reads, int max_read_len,
+int launch_sga(const DevIndex &ix, const DevReads &R, int64_t n_reads, int max_read_len,
                int32_t *d_read_status, uint32_t *d_ncl, uint32_t *d_cl_base, Cluster *d_clusters, uint32_t cl_cap,
                SlowRead *d_slow, uint32_t slow_cap, SeedCounters *d_ctr, cudaStream_t stream);
 // Packs the sub-lists of d_sparse into d_dense, turns cl_base into dense indices and sets d_ctr->n_clusters.
 int launch_sga_finish(const Cluster *d_sparse, Cluster *d_dense, uint32_t cl_cap, uint32_t *d_cl_base, const uint32_t *d_ncl,
                       int64_t n_reads, SeedCounters *d_ctr, cudaStream_t stream, uint32_t *launches);
-int launch_sga_slow(const DevIndex &ix, const uint8_t *d_reads, const int64_t *d_offs, const SlowRead *d_slow,
-                    const uint64_t *d_slow_off, uint32_t n_slow, uint32_t *d_scratch, int32_t *d_read_status,
+int launch_sga_slow(const DevIndex &ix, const DevReads &R, const SlowRead *d_slow, uint32_t slow_cap,
+                    uint32_t *d_scratch, uint64_t scratch_cap, int32_t *d_read_status,
                     uint32_t *d_ncl, uint32_t *d_cl_base, Cluster *d_clusters, uint32_t cl_cap, SeedCounters *d_ctr,
                     cudaStream_t stream);

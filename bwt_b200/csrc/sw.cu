@@ -121,22 +121,25 @@ __device__ __forceinline__ int sc_extend(const ScWave &wf, int o, int i, int lim
 
 // 0 = run the DP; otherwise the score of the pair, whose CIGAR is "<Lq>M".  Called by ALL lanes of the warp, converged;
 // the SC_LANES lanes of a group pass the same pair (valid = false: no pair) and the group's storage; t = lane index
-// inside the group.
-__device__ __forceinline__ int sw_shortcut(const uint8_t *q, int lq, const uint8_t *r, int lr, bool valid, int t, unsigned lane,
-                                           ScWave &wf) {
+// inside the group.  Both strings are plain ACGT (the caller checked): pkr = the read's packed words, the window is
+// bases [r_off, r_off+lr) of the packed window source ref2.
+__device__ __forceinline__ int sw_shortcut(const uint32_t *__restrict__ pkr, int lq, const uint32_t *__restrict__ ref2, int64_t r_off,
+                                           int lr, bool valid, int t, unsigned lane, ScWave &wf) {
     const unsigned FULL = 0xFFFFFFFFu;
     const int dd = lr - lq;
-    bool elig = valid && dd >= 0 && dd <= SW_SHORTCUT_MAX_D && lq >= 4 && lq <= SC_MAXQ;
-    // pack both strings (lane t: bases [16t, 16t+16) of every 128-base chunk); any byte outside ACGT: no shortcut
-    bool plain = true;
+    const bool elig = valid && dd >= 0 && dd <= SW_SHORTCUT_MAX_D && lq >= 4 && lq <= SC_MAXQ;
+    // both strings as 2-bit words, 16 bases each, forward (lane t: words t, t+8, ..): window padded with 'A' past its end
     if (elig) {
-        for (int pos = 16 * t; pos < 16 * SC_RW; pos += 16 * SC_LANES)
-            wf.rp[pos >> 4] = pos < lr ? pack16_acgt(r + pos, min(16, lr - pos), plain) : 0u;
-        for (int pos = 16 * t; pos < lq; pos += 16 * SC_LANES) wf.qp[pos >> 4] = pack16_acgt(q + pos, min(16, lq - pos), plain);
+        for (int w = t; w < SC_RW; w += SC_LANES) {
+            uint32_t x = 0u;
+            const int left = lr - 16 * w;
+            if (left > 0) { x = ref_word(ref2, r_off + 16 * w); if (left < 16) x &= (1u << (2 * left)) - 1u; }
+            wf.rp[w] = x;
+        }
+        for (int w = t; 16 * w < lq; w += SC_LANES) wf.qp[w] = read_fwd_word(pkr, lq, w);
     }
     __syncwarp();                                                    // qp / rp visible to the whole group
-    const unsigned plain_mask = __ballot_sync(FULL, plain);          // by every lane, before any short-circuit
-    elig = elig && ((plain_mask >> (lane - t)) & ((1u << SC_LANES) - 1u)) == ((1u << SC_LANES) - 1u);
+    (void)lane;
     // penalty budget by read length (three mismatches up to 128 bp, four up to 192, five beyond): every level costs
     // the whole warp time, and a wider budget also means more diagonals (kk on either side of the window's)
     const int pmax = min(lq <= 128 ? 9 : lq <= 192 ? 12 : SC_PMAX, 2 * (lq >> 1));   // the row threshold holds up to 2*(Lq div 2)
@@ -199,97 +202,177 @@ __device__ __forceinline__ int sw_shortcut(const uint8_t *q, int lq, const uint8
 }
 
 // ---------------------------------------------------------------------------------------------------
-// classification: settled at once (no_match for empty strings, shortcut) / narrow list / wide list / general list
+// classification.  Stage 1 (sw_classify_kernel, one thread per pair): pairs the quick test settles, and the routing of
+// the rest.  Stage 2 (sw_wfa_kernel, eight lanes per pair): the wavefront rule above on the pairs stage 1 left open.
+//
+// Quick test = the two cases of the wavefront rule that need no wavefront (both strings plain ACGT, 0 <= Dd <= 16,
+// 4 <= Lq <= 256, exactly the rule's own domain):
+//   * some diagonal of the window is a PERFECT match: p* = 0, only gapless perfect diagonals cost 0 (a diagonal that
+//     starts left of the window begins with a query-side gap, >= 4), and the leftmost of them is o*:  {2*Lq, "<Lq>M"};
+//   * Dd = 0 and the one diagonal has ONE mismatch: every other path needs a query-side gap (>= 4 > 3) -- a window-side
+//     gap alone leaves the window, column 0 costs 4 -- so p* = 3 on that diagonal:  {2*Lq - 3, "<Lq>M"}.
+// Everything else with a chance (more mismatches, Dd > 0 without a perfect diagonal) goes to the wavefront search.
 // ---------------------------------------------------------------------------------------------------
-__global__ void sw_classify_kernel(const uint8_t *__restrict__ qbase, const uint8_t *__restrict__ rbase,
-                                   const SwDesc *__restrict__ desc, SwOut *__restrict__ out, uint32_t n,
-                                   int cap_narrow, int cap_wide, uint32_t *__restrict__ list_fast,
-                                   uint32_t *__restrict__ list_wide, uint32_t *__restrict__ list_gen, SwCounters *ctr,
-                                   char *__restrict__ cig, uint32_t cig_cap, int use_shortcut) {
-    // Lane L of a warp keeps the books of pair kbase + L (32 pairs per warp: one atomic per warp and list).  The
-    // shortcut test itself runs SC_LANES lanes per pair: in round i the warp's four groups work on the pairs of lanes
-    // 4i..4i+3, whose descriptors they fetch by shuffle, and hand the verdict back the same way.
-    __shared__ ScWave s_wave[256 / SC_LANES];
-    const unsigned FULL = 0xFFFFFFFFu;
-    const unsigned lane = threadIdx.x & 31;
-    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-    int score = 0, clen = 0, kind = -1;             // kind: 0 narrow, 1 wide, 2 general, 3 shortcut, -1 nothing to do
-    SwDesc d{};
-    bool todo = false;
-    if (k < n && out[k].status != BWT_HIT_WINDOW_OOR) {
-        d = desc[k];
-        if (d.lq <= 0 || d.lr <= 0) {               // sw(_,_) -> no_match for empty strings (sw.erl:54)
-            SwOut o; o.score = 0; o.status = BWT_HIT_NO_MATCH; o.cigar_len = 0; o.cigar_off = 0;
-            out[k] = o;
-        } else todo = true;
-    }
-    if (use_shortcut && __any_sync(FULL, todo)) {
-        const int t = (int)(lane % SC_LANES), g = (int)(lane / SC_LANES);
-#pragma unroll 1
-        for (int i = 0; i < 32 / (32 / SC_LANES); i++) {
-            const int src = (32 / SC_LANES) * i + g;
-            const long long qo = __shfl_sync(FULL, (long long)d.q_off, src), ro = __shfl_sync(FULL, (long long)d.r_off, src);
-            const int lq = __shfl_sync(FULL, d.lq, src), lr = __shfl_sync(FULL, d.lr, src);
-            const bool td = __shfl_sync(FULL, (int)todo, src) != 0;
-            const int sc = sw_shortcut(qbase + qo, lq, rbase + ro, lr, td, t, lane, s_wave[threadIdx.x / SC_LANES]);
-            const int got = __shfl_sync(FULL, sc, SC_LANES * (int)(lane % (32 / SC_LANES)));
-            if ((int)(lane / (32 / SC_LANES)) == i) score = got;
-        }
-    }
-    if (todo) {
-        if (score) { kind = 3; clen = 2 + (d.lq >= 10) + (d.lq >= 100) + (d.lq >= 1000) + (d.lq >= 10000); }
-        else if (d.lq <= SW_FAST_MAX_LQ && d.lr + 1 <= cap_narrow) kind = 0;
-        else if (d.lq <= SW_FAST_MAX_LQ && d.lr + 1 <= cap_wide) kind = 1;
-        else kind = 2;
-    }
-    // one atomic per warp and list: the lanes of a kind take consecutive slots
+// mismatch flags of query word w (forward, from the packed read) against the window on diagonal o
+__device__ __forceinline__ uint32_t quick_diff(const uint32_t *__restrict__ pkr, int lq, const uint32_t *__restrict__ ref2, int64_t r_off,
+                                               int o, int w) {
+    const uint32_t x = read_fwd_word(pkr, lq, w) ^ ref_word(ref2, r_off + o + 16 * w);
+    uint32_t f = (x | (x >> 1)) & 0x55555555u;
+    if (lq - 16 * w < 16) f &= (1u << (2 * (lq - 16 * w))) - 1u;     // bases past the query's end are padding
+    return f;
+}
+
+// lists: one atomic per warp and list, the lanes of a kind take consecutive slots
+__device__ __forceinline__ void sw_route(int kind, uint32_t k, unsigned lane, SwCounters *ctr, uint32_t *__restrict__ list_fast,
+                                         uint32_t *__restrict__ list_wide, uint32_t *__restrict__ list_gen, uint32_t *__restrict__ list_wfa) {
     uint32_t slot = 0;
 #pragma unroll
-    for (int t = 0; t < 3; t++) {
-        const unsigned m = __ballot_sync(0xFFFFFFFFu, kind == t);
+    for (int t = 0; t < 4; t++) {
+        const int kk = t < 3 ? t : 4;
+        const unsigned m = __ballot_sync(0xFFFFFFFFu, kind == kk);
         if (m) {
             uint32_t base = 0;
-            if (lane == (unsigned)(__ffs((int)m) - 1)) base = atomicAdd(t == 0 ? &ctr->n_fast : t == 1 ? &ctr->n_wide : &ctr->n_general, (uint32_t)__popc(m));
+            if (lane == (unsigned)(__ffs((int)m) - 1))
+                base = atomicAdd(t == 0 ? &ctr->n_fast : t == 1 ? &ctr->n_wide : t == 2 ? &ctr->n_general : &ctr->n_wfa, (uint32_t)__popc(m));
             base = __shfl_sync(0xFFFFFFFFu, base, __ffs((int)m) - 1);
-            if (kind == t) slot = base + __popc(m & ((1u << lane) - 1u));
+            if (kind == kk) slot = base + __popc(m & ((1u << lane) - 1u));
         }
     }
     if (kind == 0) list_fast[slot] = k;
     else if (kind == 1) list_wide[slot] = k;
     else if (kind == 2) list_gen[slot] = k;
-    // shortcut pairs: CIGAR text "<Lq>M" from the temporary arena (one allocation per warp), result, counters
+    else if (kind == 4) list_wfa[slot] = k;
+}
+
+// pairs settled without the table (kind == 3): CIGAR text "<Lq>M" from the temporary arena (one allocation per warp),
+// result, counters.  Called by all lanes of the warp.
+__device__ __forceinline__ void sw_settle(int kind, uint32_t k, int lq, int lr, int score, unsigned lane, SwOut *__restrict__ out,
+                                          SwCounters *ctr, char *__restrict__ cig, uint32_t cig_cap) {
     const unsigned ms = __ballot_sync(0xFFFFFFFFu, kind == 3);
-    if (ms) {
-        int incl = clen;
-        unsigned long long cells = kind == 3 ? (unsigned long long)d.lq * (unsigned)d.lr : 0ull;
+    if (!ms) return;
+    const int clen = kind == 3 ? 2 + (lq >= 10) + (lq >= 100) + (lq >= 1000) + (lq >= 10000) : 0;
+    int incl = clen;
+    unsigned long long cells = kind == 3 ? (unsigned long long)lq * (unsigned)lr : 0ull;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-            if (lane >= (unsigned)o) incl += t;
-        }
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+        if (lane >= (unsigned)o) incl += t;
+    }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) cells += __shfl_down_sync(0xFFFFFFFFu, cells, o);
-        const int total = __shfl_sync(0xFFFFFFFFu, incl, 31);
-        uint32_t base = 0;
-        if (lane == 0) {
-            base = atomicAdd(&ctr->cig_used, (uint32_t)total);
-            atomicAdd(&ctr->sw_calls, (unsigned long long)__popc(ms));
-            atomicAdd(&ctr->cells, cells);
-            atomicAdd(&ctr->shortcut_calls, (unsigned long long)__popc(ms));
-            atomicAdd(&ctr->shortcut_cells, cells);
-            if ((uint64_t)base + total > cig_cap) atomicExch(&ctr->cig_overflow, 1u);
+    for (int o = 16; o > 0; o >>= 1) cells += __shfl_down_sync(0xFFFFFFFFu, cells, o);
+    const int total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+    uint32_t base = 0;
+    if (lane == 0) {
+        base = atomicAdd(&ctr->cig_used, (uint32_t)total);
+        atomicAdd(&ctr->sw_calls, (unsigned long long)__popc(ms));
+        atomicAdd(&ctr->cells, cells);
+        atomicAdd(&ctr->shortcut_calls, (unsigned long long)__popc(ms));
+        atomicAdd(&ctr->shortcut_cells, cells);
+        if ((uint64_t)base + total > cig_cap) atomicExch(&ctr->cig_overflow, 1u);
+    }
+    base = __shfl_sync(0xFFFFFFFFu, base, 0);
+    if (kind == 3) {
+        const uint32_t off = base + (uint32_t)(incl - clen);
+        if ((uint64_t)base + total <= cig_cap) {
+            int l = lq;
+            for (int t = clen - 2; t >= 0; t--) { cig[off + t] = (char)('0' + l % 10); l /= 10; }
+            cig[off + clen - 1] = 'M';
         }
-        base = __shfl_sync(0xFFFFFFFFu, base, 0);
-        if (kind == 3) {
-            const uint32_t off = base + (uint32_t)(incl - clen);
-            if ((uint64_t)base + total <= cig_cap) {
-                int l = d.lq;
-                for (int t = clen - 2; t >= 0; t--) { cig[off + t] = (char)('0' + l % 10); l /= 10; }
-                cig[off + clen - 1] = 'M';
+        SwOut o; o.score = score; o.status = BWT_HIT_MATCH | SW_FULL_M; o.cigar_len = clen; o.cigar_off = off;
+        out[k] = o;
+    }
+}
+
+__device__ __forceinline__ int sw_dp_kind(const SwDesc &d, int cap_narrow, int cap_wide) {
+    if (d.lq <= SW_FAST_MAX_LQ && d.lr + 1 <= cap_narrow) return 0;
+    if (d.lq <= SW_FAST_MAX_LQ && d.lr + 1 <= cap_wide) return 1;
+    return 2;
+}
+
+// use_shortcut: bit 0 = quick test, bit 1 = wavefront rule
+__global__ void __launch_bounds__(256) sw_classify_kernel(DevReads R, const uint32_t *__restrict__ ref2, const uint32_t *__restrict__ refx,
+                                   const SwDesc *__restrict__ desc, SwOut *__restrict__ out, const uint32_t *__restrict__ n_ptr,
+                                   int cap_narrow, int cap_wide, uint32_t *__restrict__ list_fast,
+                                   uint32_t *__restrict__ list_wide, uint32_t *__restrict__ list_gen, uint32_t *__restrict__ list_wfa,
+                                   SwCounters *ctr, char *__restrict__ cig, uint32_t cig_cap, int use_shortcut) {
+    const unsigned lane = threadIdx.x & 31;
+    const uint32_t n = *n_ptr;
+    for (uint32_t k0 = blockIdx.x * blockDim.x; k0 < n; k0 += gridDim.x * blockDim.x) {
+        const uint32_t k = k0 + threadIdx.x;
+        int score = 0, kind = -1;             // kind: 0 narrow, 1 wide, 2 general, 3 settled, 4 wavefront list, -1 nothing to do
+        SwDesc d{};
+        if (k < n && out[k].status != BWT_HIT_WINDOW_OOR) {
+            d = desc[k];
+            if (d.lq <= 0 || d.lr <= 0) {               // sw(_,_) -> no_match for empty strings (sw.erl:54)
+                SwOut o; o.score = 0; o.status = BWT_HIT_NO_MATCH; o.cigar_len = 0; o.cigar_off = 0;
+                out[k] = o;
+            } else if (read_is_exc(R, d.read) || !ref_plain(refx, d.r_off, d.lr)) {
+                kind = 2;                               // 'N' / IUPAC / other bytes on either side: doubles (bwt.hrl:15)
+            } else {
+                const int dd = d.lr - d.lq;
+                const bool elig = dd >= 0 && dd <= SW_SHORTCUT_MAX_D && d.lq >= 4 && d.lq <= SC_MAXQ;
+                if (elig && (use_shortcut & 1)) {
+                    const uint32_t *pkr = R.pk + __ldg(R.woff + d.read);
+                    const int nw = (d.lq + 15) >> 4;
+                    if (dd == 0) {
+                        int mism = 0;
+                        for (int w = 0; w < nw && mism <= 1; w++) mism += __popc(quick_diff(pkr, d.lq, ref2, d.r_off, 0, w));
+                        if (mism <= 1) score = 2 * d.lq - 3 * mism;
+                    } else {
+                        for (int o = 0; o <= dd && !score; o++) {
+                            int w = 0;
+                            while (w < nw && quick_diff(pkr, d.lq, ref2, d.r_off, o, w) == 0u) w++;
+                            if (w == nw) score = 2 * d.lq;
+                        }
+                    }
+                }
+                if (score) kind = 3;
+                else if (elig && (use_shortcut & 2)) kind = 4;
+                else kind = sw_dp_kind(d, cap_narrow, cap_wide);
             }
-            SwOut o; o.score = score; o.status = BWT_HIT_MATCH; o.cigar_len = clen; o.cigar_off = off;
-            out[k] = o;
         }
+        sw_route(kind, k, lane, ctr, list_fast, list_wide, list_gen, list_wfa);
+        sw_settle(kind, k, d.lq, d.lr, score, lane, out, ctr, cig, cig_cap);
+    }
+}
+
+// Stage 2: the wavefront rule on the pairs of list_wfa (all plain, all inside the rule's domain).  Lane L of a warp
+// keeps the books of list entry base + L (32 pairs per warp: one atomic per warp and list); the rule itself runs
+// SC_LANES lanes per pair: in round i the warp's four groups work on the pairs of lanes 4i..4i+3, whose descriptors
+// they fetch by shuffle, and hand the verdict back the same way.
+__global__ void __launch_bounds__(256) sw_wfa_kernel(DevReads R, const uint32_t *__restrict__ ref2,
+                              const SwDesc *__restrict__ desc, SwOut *__restrict__ out, const uint32_t *__restrict__ list_wfa,
+                              int cap_narrow, int cap_wide, uint32_t *__restrict__ list_fast,
+                              uint32_t *__restrict__ list_wide, uint32_t *__restrict__ list_gen, SwCounters *ctr,
+                              char *__restrict__ cig, uint32_t cig_cap) {
+    __shared__ ScWave s_wave[256 / SC_LANES];
+    const unsigned FULL = 0xFFFFFFFFu;
+    const unsigned lane = threadIdx.x & 31;
+    const uint32_t n = ctr->n_wfa;
+    for (uint32_t e0 = blockIdx.x * blockDim.x; e0 < n; e0 += gridDim.x * blockDim.x) {
+        const uint32_t e = e0 + threadIdx.x;
+        int score = 0, kind = -1;
+        SwDesc d{};
+        uint32_t k = 0;
+        const bool todo = e < n;
+        unsigned long long pk_addr = 0;
+        if (todo) { k = list_wfa[e]; d = desc[k]; pk_addr = (unsigned long long)(R.pk + __ldg(R.woff + d.read)); }
+        const int t = (int)(lane % SC_LANES), g = (int)(lane / SC_LANES);
+#pragma unroll 1
+        for (int i = 0; i < 32 / (32 / SC_LANES); i++) {
+            const int src = (32 / SC_LANES) * i + g;
+            const unsigned long long qa = __shfl_sync(FULL, pk_addr, src);
+            const long long ro = __shfl_sync(FULL, (long long)d.r_off, src);
+            const int lq = __shfl_sync(FULL, d.lq, src), lr = __shfl_sync(FULL, d.lr, src);
+            const bool td = __shfl_sync(FULL, (int)todo, src) != 0;
+            if (!__any_sync(FULL, td)) continue;
+            const int sc = sw_shortcut(reinterpret_cast<const uint32_t *>(qa), lq, ref2, ro, lr, td, t, lane, s_wave[threadIdx.x / SC_LANES]);
+            const int got = __shfl_sync(FULL, sc, SC_LANES * (int)(lane % (32 / SC_LANES)));
+            if ((int)(lane / (32 / SC_LANES)) == i) score = got;
+        }
+        if (todo) kind = score ? 3 : sw_dp_kind(d, cap_narrow, cap_wide);
+        sw_route(kind, k, lane, ctr, list_fast, list_wide, list_gen, nullptr);
+        sw_settle(kind, k, d.lq, d.lr, score, lane, out, ctr, cig, cig_cap);
     }
 }
 
@@ -297,7 +380,8 @@ __global__ void sw_classify_kernel(const uint8_t *__restrict__ qbase, const uint
 // fast path
 // ---------------------------------------------------------------------------------------------------
 struct SwFastParams {
-    const uint8_t *qbase, *rbase;
+    DevReads R;
+    const uint32_t *ref2;
     const SwDesc *desc;
     const uint32_t *list;
     const uint32_t *n_list;   // device counter: entries of list
@@ -322,7 +406,7 @@ struct StripState {
 // is garbage from here on) but must not raise its row maxima: its keys are clamped to -32768 for the maximum.
 template <bool MASKED, bool CAPPED, bool DELTA>
 __device__ __forceinline__ void sw_cols(std::conditional_t<DELTA, uint16_t, uint32_t> *__restrict__ row, const uint32_t *__restrict__ refw,
-                                        uint2 *__restrict__ dstrip, const int j_from, const int j_to, const int rmin,
+                                        uint2 *__restrict__ dstrip, const int j_from, const int j_to, const int rminA, const int rminB,
                                         const uint32_t capv, const uint32_t (&profA)[SW_R], const uint32_t (&profB)[SW_R],
                                         StripState &S, uint32_t &kt_prev, uint32_t &kl_prev, uint32_t &ovf) {
     constexpr int B = SW_BLOCK;
@@ -350,7 +434,7 @@ __device__ __forceinline__ void sw_cols(std::conditional_t<DELTA, uint16_t, uint
             const uint32_t s = prmt(profA[r], profB[r], sel);          // 8*sigma + 4, both lanes
             const uint32_t x = __viaddmax_s16x2(mdiag, s, S.left15[r]);   // max(diag, left)
             K = __viaddmax_s16x2(mup, tup, x);                          // max(up, .)
-            if (MASKED) K = (r >= rmin) ? K : 0u;
+            if (MASKED) K &= (r >= rminA ? 0x0000FFFFu : 0u) | (r >= rminB ? 0xFFFF0000u : 0u);
             mdiag = S.mleft[r];
             const uint32_t t7 = K & 0x00070007u;
             const uint32_t m = K & 0xFFF8FFF8u;
@@ -374,24 +458,28 @@ __device__ __forceinline__ void sw_cols(std::conditional_t<DELTA, uint16_t, uint
     }
 }
 
+// The two pairs of a thread may have different query lengths: both are aligned at their LAST row, so lane X's row r of
+// this strip is query row i0X + r, and rows <= 0 (only in the first strips, more of them for the shorter query) act as
+// row 0 of the table.
 template <bool MASKED, bool DELTA>
 __device__ __forceinline__ void sw_strip(std::conditional_t<DELTA, uint16_t, uint32_t> *__restrict__ row, const uint32_t *__restrict__ refw,
                                          uint2 *__restrict__ dstrip, const int lr_min, const int lr_max, const uint32_t capv,
-                                         const int i0, const uint32_t (&profA)[SW_R], const uint32_t (&profB)[SW_R],
+                                         const int i0A, const int i0B, const uint32_t (&profA)[SW_R], const uint32_t (&profB)[SW_R],
                                          StripState &S, uint32_t &ovf) {
-    const int rmin = 1 - i0;                        // first real row of a masked strip (rows i <= 0 are row 0)
+    const int rminA = 1 - i0A, rminB = 1 - i0B;     // first real row of a masked strip (rows i <= 0 are row 0)
+    auto col0 = [](int i) { return i >= 1 ? -8 * (i + 1) + 2 : 0; };      // column 0: V = -(i+1), dir = up   (sw.erl:72-77)
+    auto pack2 = [](int a, int b) { return ((uint32_t)a & 0xFFFFu) | ((uint32_t)b << 16); };
 #pragma unroll
     for (int r = 0; r < SW_R; r++) {
-        int k0 = -8 * (i0 + r + 1) + 2;             // column 0: V = -(i+1), dir = up   (sw.erl:72-77)
-        if (MASKED && r < rmin) k0 = 0;
-        S.mleft[r] = both(k0 & ~7);
+        const int kA = col0(i0A + r), kB = col0(i0B + r);
+        S.mleft[r] = pack2(kA & ~7, kB & ~7);
         S.left15[r] = __vadd2(S.mleft[r], 0xFFF1FFF1u);
-        S.mx[r] = both(k0);
+        S.mx[r] = pack2(kA, kB);
     }
-    uint32_t kt_prev = both(i0 - 1 >= 1 ? -8 * i0 + 2 : 0);     // K(i0-1, 0): column 0 is known in closed form
-    uint32_t kl_prev = both(-8 * (i0 + SW_R) + 2);              // K(last row of the strip, 0)
-    sw_cols<MASKED, false, DELTA>(row, refw, dstrip, 1, lr_min, rmin, 0u, profA, profB, S, kt_prev, kl_prev, ovf);
-    sw_cols<MASKED, true, DELTA>(row, refw, dstrip, lr_min + 1, lr_max, rmin, capv, profA, profB, S, kt_prev, kl_prev, ovf);
+    uint32_t kt_prev = pack2(col0(i0A - 1), col0(i0B - 1));              // K(i0-1, 0): column 0 is known in closed form
+    uint32_t kl_prev = pack2(col0(i0A + SW_R - 1), col0(i0B + SW_R - 1));    // K(last row of the strip, 0)
+    sw_cols<MASKED, false, DELTA>(row, refw, dstrip, 1, lr_min, rminA, rminB, 0u, profA, profB, S, kt_prev, kl_prev, ovf);
+    sw_cols<MASKED, true, DELTA>(row, refw, dstrip, lr_min + 1, lr_max, rminA, rminB, capv, profA, profB, S, kt_prev, kl_prev, ovf);
 }
 
 // traceback of one lane (sw.erl:116-160) + CIGAR text; returns false when the run buffer overflowed.
@@ -464,21 +552,15 @@ __device__ __forceinline__ bool sw_traceback(const SwFastParams &p, const uint2 
     return true;
 }
 
-// Packs `len` ASCII bases at src into 2-bit codes, 16 per word, word k to dst[k*stride]; false if not all ACGT.
-__device__ __forceinline__ bool sw_pack2(const uint8_t *src, int len, uint32_t *dst, int stride) {
-    bool ok = true;
-    for (int j0 = 0; j0 < len; j0 += 16) dst[(j0 >> 4) * stride] = pack16_acgt(src + j0, min(16, len - j0), ok);
-    return ok;
-}
-
 constexpr int SW_MAXQW = 26;    // query code words per lane: ceil(400 / 16) + 1
 
-// stage one pair: window codes into slot `lane` of refw (shared), query codes into qc (registers / local)
-__device__ __forceinline__ bool sw_stage(const SwFastParams &p, const SwDesc &d, uint32_t *refw, int lane, uint32_t *qc) {
+// stage one pair (both strings plain ACGT: the classification checked): window codes into slot `lane` of refw (shared),
+// query codes into qc (registers / local)
+__device__ __forceinline__ void sw_stage(const SwFastParams &p, const SwDesc &d, uint32_t *refw, int lane, uint32_t *qc) {
     constexpr int B = SW_BLOCK;
-    bool plain = sw_pack2(p.rbase + d.r_off, d.lr, refw + lane * B, 2 * B);
-    plain &= sw_pack2(p.qbase + d.q_off, d.lq, qc, 1);
-    return plain;
+    for (int j0 = 0; j0 < d.lr; j0 += 16) refw[((j0 >> 4) * 2 + lane) * B] = ref_word(p.ref2, d.r_off + j0);
+    const uint32_t *pkr = p.R.pk + __ldg(p.R.woff + d.read);
+    for (int w = 0; 16 * w < d.lq; w++) qc[w] = read_fwd_word(pkr, d.lq, w);
 }
 
 // DELTA: the boundary row is kept as signed-byte differences (half the shared memory, twice the resident warps);
@@ -497,118 +579,86 @@ __global__ void __launch_bounds__(SW_BLOCK) sw_fast_kernel(SwFastParams p) {
     const uint32_t n_list = *p.n_list;
     const uint32_t n_units = (n_list + 1) / 2;
     unsigned long long calls = 0, cells = 0;
+    auto pack2 = [](int a, int b) { return ((uint32_t)a & 0xFFFFu) | ((uint32_t)b << 16); };
 
     for (uint32_t unit = blockIdx.x * B + tid; unit < n_units; unit += gridDim.x * B) {
-        uint32_t c0 = p.list[2 * unit];
-        uint32_t c1 = 2 * unit + 1 < n_list ? p.list[2 * unit + 1] : 0xFFFFFFFFu;
-        // a unit is processed as one packed pass when both pairs have the same query length, else as two passes
-        for (int pass = 0; pass < 2; pass++) {
-            uint32_t candA, candB;
-            if (pass == 0) {
-                candA = c0; candB = c1;
-                if (c1 != 0xFFFFFFFFu && p.desc[c0].lq != p.desc[c1].lq) candB = 0xFFFFFFFFu;
-                else c1 = 0xFFFFFFFFu;                                  // nothing left for the second pass
-            } else {
-                if (c1 == 0xFFFFFFFFu) break;
-                candA = c1; candB = 0xFFFFFFFFu;
-            }
-            SwDesc dA = p.desc[candA], dB = dA;
-            uint32_t qcA[SW_MAXQW], qcB[SW_MAXQW];
-            KD_CHECK(dA.lq >= 1 && dA.lr >= 1 && dA.lr + 1 <= p.cap_cols && (dA.lq + R - 1) / R <= p.max_strips, "cand=%u lq=%d lr=%d", candA, dA.lq, dA.lr);
-            if (!sw_stage(p, dA, refw, 0, qcA)) { p.list_gen[atomicAdd(&p.ctr->n_general, 1u)] = candA; candA = 0xFFFFFFFFu; }
-            if (candB != 0xFFFFFFFFu) {
-                dB = p.desc[candB];
-                if (!sw_stage(p, dB, refw, 1, qcB)) { p.list_gen[atomicAdd(&p.ctr->n_general, 1u)] = candB; candB = 0xFFFFFFFFu; }
-            }
-            if (candA == 0xFFFFFFFFu && candB == 0xFFFFFFFFu) continue;
-            if (candA == 0xFFFFFFFFu) { candA = candB; dA = dB; candB = 0xFFFFFFFFu; sw_stage(p, dA, refw, 0, qcA); }
-            if (candB == 0xFFFFFFFFu) { dB = dA; sw_stage(p, dB, refw, 1, qcB); }      // single: lane B shadows lane A
-            const int lq = dA.lq, lrA = dA.lr, lrB = dB.lr;
-            const int lr_min = min(lrA, lrB), lr_max = max(lrA, lrB);
-            const uint32_t capv = (lrA > lr_min ? 0x7FFFu : 0x8000u) | ((lrB > lr_min ? 0x7FFFu : 0x8000u) << 16);
-            for (int j = 0; j <= lr_max; j++) row[j * B] = 0;            // row 0: {0,undef} everywhere (sw.erl:61): all differences 0
-            const int nstr = (lq + R - 1) / R;
-            const int i_first = lq - nstr * R + 1;                       // row number of strip 0, r = 0 (<= 1)
-            const int thr0 = -2 * (lq / 2);                              // sw.erl:62
-            int rowsA = lq, rowsB = lq;
-            bool failA = false, failB = false;
-            StripState S;
-            uint32_t ovf = 0;                                            // per lane: a boundary-row difference left int8
-            for (int s = 0; s < nstr; s++) {
-                const int i0 = i_first + s * R;
-                uint32_t profA[R], profB[R];
+        // two pairs per thread, one in each half of the packed registers; their query lengths may differ (they are
+        // aligned at their last rows); a lone last pair is shadowed by itself
+        uint32_t candA = p.list[2 * unit];
+        uint32_t candB = 2 * unit + 1 < n_list ? p.list[2 * unit + 1] : 0xFFFFFFFFu;
+        SwDesc dA = p.desc[candA], dB = candB != 0xFFFFFFFFu ? p.desc[candB] : dA;
+        uint32_t qcA[SW_MAXQW], qcB[SW_MAXQW];
+        KD_CHECK(dA.lq >= 1 && dA.lr >= 1 && dA.lr + 1 <= p.cap_cols && (dA.lq + R - 1) / R <= p.max_strips, "cand=%u lq=%d lr=%d", candA, dA.lq, dA.lr);
+        sw_stage(p, dA, refw, 0, qcA);
+        sw_stage(p, dB, refw, 1, qcB);
+        const int lqA = dA.lq, lqB = dB.lq, lrA = dA.lr, lrB = dB.lr;
+        const int lr_min = min(lrA, lrB), lr_max = max(lrA, lrB);
+        const uint32_t capv = (lrA > lr_min ? 0x7FFFu : 0x8000u) | ((lrB > lr_min ? 0x7FFFu : 0x8000u) << 16);
+        for (int j = 0; j <= lr_max; j++) row[j * B] = 0;            // row 0: {0,undef} everywhere (sw.erl:61): all differences 0
+        const int nstr = (max(lqA, lqB) + R - 1) / R;
+        const int ifA = lqA - nstr * R + 1, ifB = lqB - nstr * R + 1;    // row number of strip 0, r = 0 (<= 1), per lane
+        const int thrA = -2 * (lqA / 2), thrB = -2 * (lqB / 2);          // sw.erl:62
+        int rowsA = lqA, rowsB = lqB;
+        bool failA = false, failB = false;
+        StripState S;
+        uint32_t ovf = 0;                                            // per lane: a boundary-row difference left int8
+        for (int s = 0; s < nstr; s++) {
+            const int i0A = ifA + s * R, i0B = ifB + s * R;
+            uint32_t profA[R], profB[R];
 #pragma unroll
-                for (int r = 0; r < R; r++) {
-                    const int i = i0 + r;
-                    const int w = (i - 1) >> 4, sh = 2 * ((i - 1) & 15);
-                    const uint32_t qa = (i >= 1) ? ((qcA[w] >> sh) & 3u) : 0u, qb = (i >= 1) ? ((qcB[w] >> sh) & 3u) : 0u;
-                    profA[r] = 0xFCFCFCFCu ^ (0xE8u << (8 * qa));        // byte qa = 20 (match), others = -4 (mismatch)
-                    profB[r] = 0xFCFCFCFCu ^ (0xE8u << (8 * qb));
-                }
-                uint2 *dstrip = dirs + (size_t)s * p.cap_cols * B;
-                if (i0 < 1) sw_strip<true, DELTA>(row, refw, dstrip, lr_min, lr_max, capv, i0, profA, profB, S, ovf);
-                else sw_strip<false, DELTA>(row, refw, dstrip, lr_min, lr_max, capv, i0, profA, profB, S, ovf);
-                // row threshold (sw.erl:69-71): Vmax of row i must reach thr0 + 2*i
+            for (int r = 0; r < R; r++) {
+                const int iA = i0A + r, iB = i0B + r;
+                const uint32_t qa = (iA >= 1) ? ((qcA[(iA - 1) >> 4] >> (2 * ((iA - 1) & 15))) & 3u) : 0u;
+                const uint32_t qb = (iB >= 1) ? ((qcB[(iB - 1) >> 4] >> (2 * ((iB - 1) & 15))) & 3u) : 0u;
+                profA[r] = 0xFCFCFCFCu ^ (0xE8u << (8 * qa));        // byte qa = 20 (match), others = -4 (mismatch)
+                profB[r] = 0xFCFCFCFCu ^ (0xE8u << (8 * qb));
+            }
+            uint2 *dstrip = dirs + (size_t)s * p.cap_cols * B;
+            if (i0A < 1 || i0B < 1) sw_strip<true, DELTA>(row, refw, dstrip, lr_min, lr_max, capv, i0A, i0B, profA, profB, S, ovf);
+            else sw_strip<false, DELTA>(row, refw, dstrip, lr_min, lr_max, capv, i0A, i0B, profA, profB, S, ovf);
+            // row threshold (sw.erl:69-71): Vmax of row i must reach thr0 + 2*i
 #pragma unroll
-                for (int r = 0; r < R; r++) {
-                    int i = i0 + r;
-                    if (i >= 1) {
-                        if (!failA && (lane16(S.mx[r], 0) >> 3) < thr0 + 2 * i) { failA = true; rowsA = i; }
-                        if (!failB && (lane16(S.mx[r], 1) >> 3) < thr0 + 2 * i) { failB = true; rowsB = i; }
-                    }
-                }
-                if (failA && failB) break;
+            for (int r = 0; r < R; r++) {
+                const int iA = i0A + r, iB = i0B + r;
+                if (iA >= 1 && !failA && (lane16(S.mx[r], 0) >> 3) < thrA + 2 * iA) { failA = true; rowsA = iA; }
+                if (iB >= 1 && !failB && (lane16(S.mx[r], 1) >> 3) < thrB + 2 * iB) { failB = true; rowsB = iB; }
             }
-            // a pair whose boundary row could not be difference-coded is redone by the general kernel (rare: it takes
-            // a gap run of a dozen bases right next to a high-scoring path)
-            if (ovf & 0xFFFFu) { p.list_ovf[atomicAdd(&p.ctr->n_ovf, 1u)] = candA; }
-            if ((ovf >> 16) && candB != 0xFFFFFFFFu) { p.list_ovf[atomicAdd(&p.ctr->n_ovf, 1u)] = candB; candB = 0xFFFFFFFFu; }
-            if (ovf & 0xFFFFu) {
-                if (candB == 0xFFFFFFFFu) continue;
-                // lane B alone survives: finish it below as the only pair of the unit
-                calls += 1; cells += (unsigned long long)rowsB * (unsigned)lrB;
-                SwOut ob; ob.score = 0; ob.status = BWT_HIT_NO_MATCH; ob.cigar_len = 0; ob.cigar_off = 0;
-                if (failB) { p.out[candB] = ob; continue; }
-                const int vB = lane16(S.mx[R - 1], 1) >> 3;
-                int jb = -1;
-                uint32_t kk = both(-8 * (lq + 1) + 2);
-                for (int j = 0; j <= lrB && jb < 0; j++) {
-                    if (j) kk = __vadd2(kk, prmt((uint32_t)row[j * B], 0u, 0x9180u));
-                    if ((lane16(kk, 1) >> 3) == vB) jb = j;
-                }
-                if (jb < 0 || !sw_traceback(p, dirs, scratch, 1, lq, lrB, i_first, jb, vB, candB)) {
-                    p.list_gen[atomicAdd(&p.ctr->n_general, 1u)] = candB; calls--; cells -= (unsigned long long)rowsB * (unsigned)lrB;
-                }
-                continue;
+            if (failA && failB) break;
+        }
+        // a pair whose boundary row could not be difference-coded is redone with absolute rows (rare: it takes
+        // a gap run of a dozen bases right next to a high-scoring path)
+        bool liveA = true, liveB = candB != 0xFFFFFFFFu;
+        if (ovf & 0xFFFFu) { p.list_ovf[atomicAdd(&p.ctr->n_ovf, 1u)] = candA; liveA = false; }
+        if ((ovf >> 16) && liveB) { p.list_ovf[atomicAdd(&p.ctr->n_ovf, 1u)] = candB; liveB = false; }
+        SwOut o;
+        o.score = 0; o.status = BWT_HIT_NO_MATCH; o.cigar_len = 0; o.cigar_off = 0;
+        // leftmost maximum of the last row (sw.erl:110-112), for both lanes before the row buffer is reused
+        const int vmaxA = lane16(S.mx[R - 1], 0) >> 3, vmaxB = lane16(S.mx[R - 1], 1) >> 3;
+        int jA = -1, jB = -1;
+        {
+            uint32_t k = pack2(-8 * (lqA + 1) + 2, -8 * (lqB + 1) + 2);   // K(lq, 0); then the running sum of the differences
+            const bool needA = liveA && !failA, needB = liveB && !failB;
+            for (int j = 0; j <= lr_max && ((needA && jA < 0) || (needB && jB < 0)); j++) {
+                if (j) k = DELTA ? __vadd2(k, prmt((uint32_t)row[j * B], 0u, 0x9180u)) : (uint32_t)row[j * B];
+                if (jA < 0 && j <= lrA && (lane16(k, 0) >> 3) == vmaxA) jA = j;
+                if (jB < 0 && j <= lrB && (lane16(k, 1) >> 3) == vmaxB) jB = j;
             }
-            calls += 1 + (candB != 0xFFFFFFFFu);
-            cells += (unsigned long long)rowsA * (unsigned)lrA + (candB != 0xFFFFFFFFu ? (unsigned long long)rowsB * (unsigned)lrB : 0ull);
-            SwOut o;
-            o.score = 0; o.status = BWT_HIT_NO_MATCH; o.cigar_len = 0; o.cigar_off = 0;
-            // leftmost maximum of the last row (sw.erl:110-112), for both lanes before the row buffer is reused
-            const int vmaxA = lane16(S.mx[R - 1], 0) >> 3, vmaxB = lane16(S.mx[R - 1], 1) >> 3;
-            int jA = -1, jB = -1;
-            {
-                uint32_t k = both(-8 * (lq + 1) + 2);                    // K(lq, 0); then the running sum of the differences
-                const bool needA = !failA, needB = !failB && candB != 0xFFFFFFFFu;
-                for (int j = 0; j <= lr_max && ((needA && jA < 0) || (needB && jB < 0)); j++) {
-                    if (j) k = DELTA ? __vadd2(k, prmt((uint32_t)row[j * B], 0u, 0x9180u)) : (uint32_t)row[j * B];
-                    if (jA < 0 && j <= lrA && (lane16(k, 0) >> 3) == vmaxA) jA = j;
-                    if (jB < 0 && j <= lrB && (lane16(k, 1) >> 3) == vmaxB) jB = j;
-                }
-                KD_CHECK((!needA || jA >= 0) && (!needB || jB >= 0), "cand=%u/%u vmax=%d/%d", candA, candB, vmaxA, vmaxB);
-                if (needA && jA < 0) { p.list_gen[atomicAdd(&p.ctr->n_general, 1u)] = candA; failA = true; jA = 0; }
-                if (needB && jB < 0) { p.list_gen[atomicAdd(&p.ctr->n_general, 1u)] = candB; candB = 0xFFFFFFFFu; }
-            }
+            KD_CHECK((!needA || jA >= 0) && (!needB || jB >= 0), "cand=%u/%u vmax=%d/%d", candA, candB, vmaxA, vmaxB);
+            if (needA && jA < 0) { p.list_gen[atomicAdd(&p.ctr->n_general, 1u)] = candA; liveA = false; }
+            if (needB && jB < 0) { p.list_gen[atomicAdd(&p.ctr->n_general, 1u)] = candB; liveB = false; }
+        }
+        if (liveA) {
+            calls++; cells += (unsigned long long)rowsA * (unsigned)lrA;
             if (failA) p.out[candA] = o;
-            else if (!sw_traceback(p, dirs, scratch, 0, lq, lrA, i_first, jA, vmaxA, candA)) {
+            else if (!sw_traceback(p, dirs, scratch, 0, lqA, lrA, ifA, jA, vmaxA, candA)) {
                 p.list_gen[atomicAdd(&p.ctr->n_general, 1u)] = candA; calls--; cells -= (unsigned long long)rowsA * (unsigned)lrA;
             }
-            if (candB != 0xFFFFFFFFu) {
-                if (failB) p.out[candB] = o;
-                else if (!sw_traceback(p, dirs, scratch, 1, lq, lrB, i_first, jB, vmaxB, candB)) {
-                    p.list_gen[atomicAdd(&p.ctr->n_general, 1u)] = candB; calls--; cells -= (unsigned long long)rowsB * (unsigned)lrB;
-                }
+        }
+        if (liveB) {
+            calls++; cells += (unsigned long long)rowsB * (unsigned)lrB;
+            if (failB) p.out[candB] = o;
+            else if (!sw_traceback(p, dirs, scratch, 1, lqB, lrB, ifB, jB, vmaxB, candB)) {
+                p.list_gen[atomicAdd(&p.ctr->n_general, 1u)] = candB; calls--; cells -= (unsigned long long)rowsB * (unsigned)lrB;
             }
         }
     }
@@ -652,7 +702,7 @@ __host__ __device__ inline uint64_t sw_general_scratch_bytes(int lq, int lr) {
     return (b + 15) & ~15ull;
 }
 
-__global__ void __launch_bounds__(64) sw_general_kernel(const uint8_t *__restrict__ qbase, const uint8_t *__restrict__ rbase,
+__global__ void __launch_bounds__(64) sw_general_kernel(DevReads R, const uint8_t *__restrict__ rbase,
                                                         const SwDesc *__restrict__ desc, const uint32_t *__restrict__ list,
                                                         uint32_t first, uint32_t count, const uint64_t *__restrict__ off,
                                                         uint8_t *scratch, SwOut *out, SwCounters *ctr, char *cig,
@@ -661,8 +711,13 @@ __global__ void __launch_bounds__(64) sw_general_kernel(const uint8_t *__restric
     if (t >= count) return;
     const uint32_t cand = list[first + t];
     const SwDesc d = desc[cand];
-    const uint8_t *q = qbase + d.q_off, *w = rbase + d.r_off;
+    // the read's text: ASCII when it is resident (flagged reads always are), else out of the packed words
+    const uint8_t *w = rbase + d.r_off;
     const int lq = d.lq, lr = d.lr, W = lr + 1;
+    const uint8_t *q = nullptr;
+    const uint32_t *pkr = nullptr;
+    if (R.ascii_full || read_is_exc(R, d.read)) { int l2; q = read_ascii(R, d.read, l2); }
+    else pkr = R.pk + R.woff[d.read];
     uint8_t *base = scratch + (off[first + t] - off[first]);
     double *pv = reinterpret_cast<double *>(base), *cv = pv + W;
     uint8_t *dirs = reinterpret_cast<uint8_t *>(cv + W);                 // (lq+1) x W, codes 0 left 1 up 2 up_left 3 undef
@@ -678,7 +733,7 @@ __global__ void __launch_bounds__(64) sw_general_kernel(const uint8_t *__restric
         cv[0] = pv[0] + (i == 1 ? -2.0 : -1.0);                           // sw.erl:72-77
         cd[0] = 1;
         double rowmax = cv[0];
-        const uint8_t qc = q[i - 1];
+        const uint8_t qc = q ? q[i - 1] : (uint8_t)"ACGT"[read_code(pkr, lq, i - 1)];
         for (int j = 1; j < W; j++) {                                     // sw.erl:88-98
             double bv = __dadd_rn(pv[j - 1], sigma_ref(qc, w[j - 1]));
             int bd = 2;
@@ -756,8 +811,8 @@ int grow(T *&p, size_t &cap_items, size_t need_items) {
 int sw_stage_reserve(SwStage &st, uint32_t pairs) {
     if (pairs <= st.cap && st.d_desc) return BWT_OK;
     uint32_t want = pairs + pairs / 4 + 1024;
-    if (st.d_desc) { cudaFree(st.d_desc); cudaFree(st.d_out); cudaFree(st.d_list_fast); cudaFree(st.d_list_wide); cudaFree(st.d_list_gen); cudaFree(st.d_list_ovf); }
-    st.d_desc = nullptr; st.d_out = nullptr; st.d_list_fast = nullptr; st.d_list_wide = nullptr; st.d_list_gen = nullptr; st.d_list_ovf = nullptr;
+    if (st.d_desc) { cudaFree(st.d_desc); cudaFree(st.d_out); cudaFree(st.d_list_fast); cudaFree(st.d_list_wide); cudaFree(st.d_list_gen); cudaFree(st.d_list_ovf); cudaFree(st.d_list_wfa); }
+    st.d_desc = nullptr; st.d_out = nullptr; st.d_list_fast = nullptr; st.d_list_wide = nullptr; st.d_list_gen = nullptr; st.d_list_ovf = nullptr; st.d_list_wfa = nullptr;
     st.cap = 0;
     CU_TRY(cudaMalloc(&st.d_desc, (size_t)want * sizeof(SwDesc)));
     CU_TRY(cudaMalloc(&st.d_out, (size_t)want * sizeof(SwOut)));
@@ -765,6 +820,7 @@ int sw_stage_reserve(SwStage &st, uint32_t pairs) {
     CU_TRY(cudaMalloc(&st.d_list_wide, (size_t)want * sizeof(uint32_t)));
     CU_TRY(cudaMalloc(&st.d_list_gen, (size_t)want * sizeof(uint32_t)));
     CU_TRY(cudaMalloc(&st.d_list_ovf, (size_t)want * sizeof(uint32_t)));
+    CU_TRY(cudaMalloc(&st.d_list_wfa, (size_t)want * sizeof(uint32_t)));
     if (!st.d_ctr) {
         CU_TRY(cudaMalloc(&st.d_ctr, sizeof(SwCounters)));
         CU_TRY(cudaMallocHost(&st.h_ctr, sizeof(SwCounters)));
@@ -783,6 +839,7 @@ int sw_stage_reserve(SwStage &st, uint32_t pairs) {
 
 void sw_stage_free(SwStage &st) {
     cudaFree(st.d_desc); cudaFree(st.d_out); cudaFree(st.d_list_fast); cudaFree(st.d_list_wide); cudaFree(st.d_list_gen); cudaFree(st.d_list_ovf);
+    cudaFree(st.d_list_wfa);
     cudaFree(st.d_ctr); if (st.h_ctr) cudaFreeHost(st.h_ctr);
     if (st.ev_k0) cudaEventDestroy(st.ev_k0);
     if (st.ev_k1) cudaEventDestroy(st.ev_k1);
@@ -790,29 +847,25 @@ void sw_stage_free(SwStage &st) {
     st = SwStage();
 }
 
-int sw_stage_run(SwStage &st, const uint8_t *d_qbase, const uint8_t *d_rbase, uint32_t n, int max_lq,
-                 cudaStream_t stream) {
-    st.sw_calls = st.cells = st.n_general = st.shortcut_calls = st.shortcut_cells = 0;
-    st.ms_fast_kernel = 0;
-    // BWT_SW_SHORTCUT=0 sends every pair through the DP (A/B timing, and parity tests of the DP on easy pairs)
-    const char *env_sc = getenv("BWT_SW_SHORTCUT");
-    const int use_shortcut = !(env_sc && env_sc[0] == '0');      // (read per run: tests flip it between calls)
-    if (n == 0) return BWT_OK;
-    if (n > st.cap) { bwt_set_error("sw_stage_run: %u pairs exceed the reserved %u", n, st.cap); return BWT_ERR_ARG; }
+namespace {
+struct SwPlan {        // launch geometry of one configuration (max_lq)
+    int cap_narrow, cap_wide, max_strips;
+    unsigned grid[3];
+};
+size_t smem_of(int cap, bool delta) { return (size_t)SW_BLOCK * ((size_t)cap * (delta ? 2 : 4) + (size_t)(cap / 16) * 8); }
+
+int sw_plan(SwStage &st, uint32_t n_cap, int max_lq, SwPlan &pl) {
     // two shared-memory tiers of the fast kernel: "narrow" holds windows up to Lq + 15 columns (almost every
     // candidate: D is the summed gap of the voting chain), "wide" up to Lq + 160; anything wider takes the general path
-    // (one thread per pair: a single such pair costs ~2 ms, more than a whole worker-sized batch)
     const int cap_limit = 384;                           // fast-kernel tier limit: the absolute-row variant needs 4.5 B x columns x 128 threads <= 227 KB
-    int cap_narrow = std::min(cap_limit, std::max(96, ((max_lq + 1 + 15) + 15) & ~15));   // >= 96: the traceback's band (64 half-words) + runs
-    int cap_wide = std::min(cap_limit, std::max(96, ((max_lq + 1 + 160) + 15) & ~15));    // D up to 160: the largest slack seen on GL000193.1 is 142
-    int max_strips = (std::min(max_lq, SW_FAST_MAX_LQ) + SW_R - 1) / SW_R;
-    if (max_strips < 1) max_strips = 1;
-    auto smem_of = [](int cap, bool delta) { return (size_t)SW_BLOCK * ((size_t)cap * (delta ? 2 : 4) + (size_t)(cap / 16) * 8); };
-    const int caps[3] = {cap_narrow, cap_wide, cap_wide};
+    pl.cap_narrow = std::min(cap_limit, std::max(96, ((max_lq + 1 + 15) + 15) & ~15));   // >= 96: the traceback's band (64 half-words) + runs
+    pl.cap_wide = std::min(cap_limit, std::max(96, ((max_lq + 1 + 160) + 15) & ~15));    // D up to 160: the largest slack seen on GL000193.1 is 142
+    pl.max_strips = std::max(1, (std::min(max_lq, SW_FAST_MAX_LQ) + SW_R - 1) / SW_R);
+    const int caps[3] = {pl.cap_narrow, pl.cap_wide, pl.cap_wide};
     if (st.cfg_max_lq != max_lq) {                       // attribute / occupancy queries once per configuration, not per batch
         CU_TRY(cudaDeviceGetAttribute(&st.cfg_sms, cudaDevAttrMultiProcessorCount, st.device));
-        CU_TRY(cudaFuncSetAttribute(sw_fast_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_of(cap_wide, true)));
-        CU_TRY(cudaFuncSetAttribute(sw_fast_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_of(cap_wide, false)));
+        CU_TRY(cudaFuncSetAttribute(sw_fast_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_of(pl.cap_wide, true)));
+        CU_TRY(cudaFuncSetAttribute(sw_fast_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_of(pl.cap_wide, false)));
         for (int t = 0; t < 3; t++) {
             if (t < 2) CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&st.cfg_per_sm[t], sw_fast_kernel<true>, SW_BLOCK, smem_of(caps[t], true)));
             else CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&st.cfg_per_sm[t], sw_fast_kernel<false>, SW_BLOCK, smem_of(caps[t], false)));
@@ -820,119 +873,174 @@ int sw_stage_run(SwStage &st, const uint8_t *d_qbase, const uint8_t *d_rbase, ui
         }
         st.cfg_max_lq = max_lq;
     }
-    const int sms = st.cfg_sms;
-    unsigned grid[3];
     size_t need_dirs = 0;
     for (int t = 0; t < 3; t++) {
-        uint64_t units = ((uint64_t)n + 1) / 2;
-        grid[t] = (unsigned)std::min<uint64_t>((units + SW_BLOCK - 1) / SW_BLOCK, (uint64_t)sms * st.cfg_per_sm[t]);
-        if (t == 2) grid[t] = std::min<unsigned>(grid[t], (unsigned)sms);       // the overflow list is short: one wave
-        need_dirs = std::max(need_dirs, (size_t)grid[t] * SW_BLOCK * max_strips * caps[t]);
+        const uint64_t units = ((uint64_t)n_cap + 1) / 2;
+        pl.grid[t] = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((units + SW_BLOCK - 1) / SW_BLOCK, (uint64_t)st.cfg_sms * st.cfg_per_sm[t]));
+        if (t == 2) pl.grid[t] = std::min<unsigned>(pl.grid[t], (unsigned)st.cfg_sms);       // the overflow list is short: one wave
+        need_dirs = std::max(need_dirs, (size_t)pl.grid[t] * SW_BLOCK * pl.max_strips * caps[t]);
     }
-    BWT_TRY(grow(st.d_dirs, st.dirs_words, need_dirs));
+    return grow(st.d_dirs, st.dirs_words, need_dirs);
+}
 
-    for (int attempt = 0; attempt < 4; attempt++) {
-        CU_TRY(cudaMemsetAsync(st.d_ctr, 0, sizeof(SwCounters), stream));
-        sw_classify_kernel<<<(n + 255) / 256, 256, 0, stream>>>(d_qbase, d_rbase, st.d_desc, st.d_out, n, cap_narrow, cap_wide,
-                                                                st.d_list_fast, st.d_list_wide, st.d_list_gen, st.d_ctr,
-                                                                st.d_cig_tmp, st.cig_cap, use_shortcut);
-        K_CHECK(stream, "sw_classify_kernel");
-        SwFastParams p;
-        p.qbase = d_qbase; p.rbase = d_rbase; p.desc = st.d_desc; p.out = st.d_out;
-        p.list_gen = st.d_list_gen; p.list_ovf = st.d_list_ovf; p.ctr = st.d_ctr; p.cig = st.d_cig_tmp; p.cig_cap = st.cig_cap;
-        p.dirs = st.d_dirs; p.max_strips = max_strips;
-        // the list sizes are known on the host before the DP kernels go out: with the shortcut most lists are short or
-        // empty, and an empty launch of a large-shared-memory kernel still costs a quarter of a millisecond
+SwFastParams sw_params(SwStage &st, const DevReads &R, const uint32_t *d_ref2, const SwPlan &pl) {
+    SwFastParams p;
+    p.R = R; p.ref2 = d_ref2; p.desc = st.d_desc; p.out = st.d_out;
+    p.list_gen = st.d_list_gen; p.list_ovf = st.d_list_ovf; p.ctr = st.d_ctr; p.cig = st.d_cig_tmp; p.cig_cap = st.cig_cap;
+    p.dirs = st.d_dirs; p.max_strips = pl.max_strips;
+    p.list = nullptr; p.n_list = nullptr; p.cap_cols = 0;
+    return p;
+}
+
+int sw_use_shortcut() {
+    // BWT_SW_SHORTCUT: 3 (default) quick test + wavefront rule, 2 the wavefront rule alone, 1 the quick test alone,
+    // 0 every pair through the DP (A/B timing, and parity tests of the DP on easy pairs); read per run: tests flip it
+    const char *e = getenv("BWT_SW_SHORTCUT");
+    if (!e || !*e) return 3;
+    const int v = atoi(e);
+    return v < 0 || v > 3 ? 3 : v;
+}
+}  // namespace
+
+// Everything of the stage whose launch geometry the host knows without looking at the data: classification (quick test,
+// wavefront rule) and the narrow DP tier, all sized by n_cap and driven by device-side counts (*d_n pairs).  No host
+// synchronisation: the caller copies st.d_ctr to st.h_ctr behind it and calls sw_stage_finish once that has arrived.
+int sw_stage_enqueue(SwStage &st, const DevReads &R, const uint8_t *d_rbase, const uint32_t *d_ref2, const uint32_t *d_refx,
+                     const uint32_t *d_n, uint32_t n_cap, int max_lq, cudaStream_t stream) {
+    (void)d_rbase;
+    st.sw_calls = st.cells = st.n_general = st.shortcut_calls = st.shortcut_cells = 0;
+    st.ms_fast_kernel = 0;
+    if (n_cap > st.cap) { bwt_set_error("sw_stage: %u pairs exceed the reserved %u", n_cap, st.cap); return BWT_ERR_ARG; }
+    SwPlan pl;
+    BWT_TRY(sw_plan(st, n_cap, max_lq, pl));
+    const int use_shortcut = sw_use_shortcut();
+    CU_TRY(cudaMemsetAsync(st.d_ctr, 0, sizeof(SwCounters), stream));
+    const unsigned cgrid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(((uint64_t)n_cap + 255) / 256, (uint64_t)148 * 32));
+    sw_classify_kernel<<<cgrid, 256, 0, stream>>>(R, d_ref2, d_refx, st.d_desc, st.d_out, d_n, pl.cap_narrow, pl.cap_wide,
+                                                  st.d_list_fast, st.d_list_wide, st.d_list_gen, st.d_list_wfa, st.d_ctr,
+                                                  st.d_cig_tmp, st.cig_cap, use_shortcut);
+    K_CHECK(stream, "sw_classify_kernel");
+    st.launches += 1;
+    if (use_shortcut & 2) {
+        sw_wfa_kernel<<<std::min(cgrid, 148u * 8u), 256, 0, stream>>>(R, d_ref2, st.d_desc, st.d_out, st.d_list_wfa, pl.cap_narrow, pl.cap_wide,
+                                                                     st.d_list_fast, st.d_list_wide, st.d_list_gen, st.d_ctr,
+                                                                     st.d_cig_tmp, st.cig_cap);
+        K_CHECK(stream, "sw_wfa_kernel");
+        st.launches += 1;
+    }
+    SwFastParams p = sw_params(st, R, d_ref2, pl);
+    CU_TRY(cudaEventRecord(st.ev_k0, stream));
+    p.list = st.d_list_fast; p.n_list = &st.d_ctr->n_fast; p.cap_cols = pl.cap_narrow;
+    sw_fast_kernel<true><<<pl.grid[0], SW_BLOCK, smem_of(pl.cap_narrow, true), stream>>>(p);
+    K_CHECK(stream, "sw_fast_kernel (narrow)");
+    st.launches += 1;
+    CU_TRY(cudaEventRecord(st.ev_k1, stream));
+    return BWT_OK;
+}
+
+// With st.h_ctr = the counters after sw_stage_enqueue: the rare tiers (wide windows, absolute rows, doubles), each
+// launched only when its list is not empty.  *redo_emit is set when any of them ran (results changed after the caller's
+// optimistic emit).  BWT_ERR_NOSPACE: the temporary CIGAR arena overflowed; it has been grown, run the stage again.
+int sw_stage_finish(SwStage &st, const DevReads &R, const uint8_t *d_rbase, const uint32_t *d_ref2, const uint32_t *d_refx,
+                    uint32_t n_cap, int max_lq, cudaStream_t stream, bool *redo_emit) {
+    (void)d_refx;
+    *redo_emit = false;
+    SwPlan pl;
+    BWT_TRY(sw_plan(st, n_cap, max_lq, pl));
+    SwFastParams p = sw_params(st, R, d_ref2, pl);
+    auto grid_for = [&](uint32_t pairs, unsigned cap_grid) {
+        return (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((((uint64_t)pairs + 1) / 2 + SW_BLOCK - 1) / SW_BLOCK, cap_grid));
+    };
+    auto refresh = [&]() -> int {
         CU_TRY(cudaMemcpyAsync(st.h_ctr, st.d_ctr, sizeof(SwCounters), cudaMemcpyDeviceToHost, stream));
         CU_TRY(cudaStreamSynchronize(stream));
-        const uint32_t n_fast = st.h_ctr->n_fast, n_wide = st.h_ctr->n_wide;
-        auto grid_for = [&](uint32_t pairs, unsigned cap_grid) {
-            return (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((((uint64_t)pairs + 1) / 2 + SW_BLOCK - 1) / SW_BLOCK, cap_grid));
-        };
-        CU_TRY(cudaEventRecord(st.ev_k0, stream));
-        if (n_fast > 0) {
-            p.list = st.d_list_fast; p.n_list = &st.d_ctr->n_fast; p.cap_cols = cap_narrow;
-            sw_fast_kernel<true><<<grid_for(n_fast, grid[0]), SW_BLOCK, smem_of(cap_narrow, true), stream>>>(p);
-            K_CHECK(stream, "sw_fast_kernel (narrow)");
+        return BWT_OK;
+    };
+    if (!st.h_ctr->cig_overflow && st.h_ctr->n_wide > 0) {
+        p.list = st.d_list_wide; p.n_list = &st.d_ctr->n_wide; p.cap_cols = pl.cap_wide;
+        sw_fast_kernel<true><<<grid_for(st.h_ctr->n_wide, pl.grid[1]), SW_BLOCK, smem_of(pl.cap_wide, true), stream>>>(p);
+        K_CHECK(stream, "sw_fast_kernel (wide)");
+        st.launches += 1;
+        *redo_emit = true;
+        BWT_TRY(refresh());
+    }
+    if (!st.h_ctr->cig_overflow && st.h_ctr->n_ovf > 0) {
+        // pairs whose boundary rows did not fit the difference coding: absolute rows (rare)
+        p.list = st.d_list_ovf; p.n_list = &st.d_ctr->n_ovf; p.cap_cols = pl.cap_wide;
+        sw_fast_kernel<false><<<grid_for(st.h_ctr->n_ovf, pl.grid[2]), SW_BLOCK, smem_of(pl.cap_wide, false), stream>>>(p);
+        K_CHECK(stream, "sw_fast_kernel (absolute rows)");
+        st.launches += 1;
+        *redo_emit = true;
+        BWT_TRY(refresh());
+    }
+    const uint32_t ng = st.h_ctr->n_general;
+    if (ng > 0 && !st.h_ctr->cig_overflow) {
+        // size the per-pair scratch of the general kernel on the host
+        if (ng + 1 > st.gen_off_cap) {
+            if (st.d_gen_off) cudaFree(st.d_gen_off);
+            if (st.d_gen_dims) cudaFree(st.d_gen_dims);
+            st.d_gen_off = nullptr; st.d_gen_dims = nullptr;
+            const size_t cap_items = (size_t)ng + ng / 2 + 64;
+            CU_TRY(cudaMalloc(&st.d_gen_off, cap_items * sizeof(uint64_t)));
+            CU_TRY(cudaMalloc(&st.d_gen_dims, cap_items * sizeof(int2)));
+            st.gen_off_cap = cap_items;
+        }
+        sw_dims_kernel<<<(ng + 255) / 256, 256, 0, stream>>>(st.d_desc, st.d_list_gen, ng, st.d_gen_dims);
+        st.launches += 1;
+        std::vector<int2> dims(ng);
+        CU_TRY(cudaMemcpyAsync(dims.data(), st.d_gen_dims, ng * sizeof(int2), cudaMemcpyDeviceToHost, stream));
+        CU_TRY(cudaStreamSynchronize(stream));
+        std::vector<uint64_t> off(ng + 1);
+        off[0] = 0;
+        for (uint32_t k = 0; k < ng; k++) off[k + 1] = off[k] + sw_general_scratch_bytes(dims[k].x, dims[k].y);
+        CU_TRY(cudaMemcpyAsync(st.d_gen_off, off.data(), (ng + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, stream));
+        // rounds of at most ~2 GB of scratch
+        const uint64_t round_bytes = 2ull << 30;
+        uint32_t first = 0;
+        while (first < ng) {
+            uint32_t last = first + 1;
+            while (last < ng && off[last + 1] - off[first] <= round_bytes) last++;
+            uint64_t need = off[last] - off[first];
+            BWT_TRY(grow(st.d_gen_scratch, st.gen_scratch_bytes, (size_t)need));
+            uint32_t cnt = last - first;
+            sw_general_kernel<<<(cnt + 63) / 64, 64, 0, stream>>>(R, d_rbase, st.d_desc, st.d_list_gen, first, cnt,
+                                                                 st.d_gen_off, st.d_gen_scratch, st.d_out, st.d_ctr,
+                                                                 st.d_cig_tmp, st.cig_cap);
             st.launches += 1;
-        }
-        if (n_wide > 0) {
-            p.list = st.d_list_wide; p.n_list = &st.d_ctr->n_wide; p.cap_cols = cap_wide;
-            sw_fast_kernel<true><<<grid_for(n_wide, grid[1]), SW_BLOCK, smem_of(cap_wide, true), stream>>>(p);
-            K_CHECK(stream, "sw_fast_kernel (wide)");
-            st.launches += 1;
-        }
-        CU_TRY(cudaEventRecord(st.ev_k1, stream));
-        st.launches += 1;                                // the classification
-        if (n_fast > 0 || n_wide > 0) {
-            CU_TRY(cudaMemcpyAsync(st.h_ctr, st.d_ctr, sizeof(SwCounters), cudaMemcpyDeviceToHost, stream));
+            K_CHECK(stream, "sw_general_kernel");
             CU_TRY(cudaStreamSynchronize(stream));
-            if (st.h_ctr->n_ovf > 0 && !st.h_ctr->cig_overflow) {
-                // pairs whose boundary rows did not fit the difference coding: absolute rows (rare)
-                p.list = st.d_list_ovf; p.n_list = &st.d_ctr->n_ovf; p.cap_cols = cap_wide;
-                sw_fast_kernel<false><<<grid_for(st.h_ctr->n_ovf, grid[2]), SW_BLOCK, smem_of(cap_wide, false), stream>>>(p);
-                K_CHECK(stream, "sw_fast_kernel (absolute rows)");
-                st.launches += 1;
-                CU_TRY(cudaEventRecord(st.ev_k1, stream));
-                CU_TRY(cudaMemcpyAsync(st.h_ctr, st.d_ctr, sizeof(SwCounters), cudaMemcpyDeviceToHost, stream));
-                CU_TRY(cudaStreamSynchronize(stream));
-            }
+            first = last;
         }
-        uint32_t ng = st.h_ctr->n_general;
-        if (ng > 0 && !st.h_ctr->cig_overflow) {
-            // size the per-pair scratch of the general kernel on the host
-            size_t cap_items = st.gen_off_cap;
-            if (ng + 1 > st.gen_off_cap) {
-                if (st.d_gen_off) cudaFree(st.d_gen_off);
-                if (st.d_gen_dims) cudaFree(st.d_gen_dims);
-                st.d_gen_off = nullptr; st.d_gen_dims = nullptr;
-                cap_items = (size_t)ng + ng / 2 + 64;
-                CU_TRY(cudaMalloc(&st.d_gen_off, cap_items * sizeof(uint64_t)));
-                CU_TRY(cudaMalloc(&st.d_gen_dims, cap_items * sizeof(int2)));
-                st.gen_off_cap = cap_items;
-            }
-            sw_dims_kernel<<<(ng + 255) / 256, 256, 0, stream>>>(st.d_desc, st.d_list_gen, ng, st.d_gen_dims);
-            st.launches += 1;
-            std::vector<int2> dims(ng);
-            CU_TRY(cudaMemcpyAsync(dims.data(), st.d_gen_dims, ng * sizeof(int2), cudaMemcpyDeviceToHost, stream));
-            CU_TRY(cudaStreamSynchronize(stream));
-            std::vector<uint64_t> off(ng + 1);
-            off[0] = 0;
-            for (uint32_t k = 0; k < ng; k++) off[k + 1] = off[k] + sw_general_scratch_bytes(dims[k].x, dims[k].y);
-            CU_TRY(cudaMemcpyAsync(st.d_gen_off, off.data(), (ng + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, stream));
-            // rounds of at most ~2 GB of scratch
-            const uint64_t round_bytes = 2ull << 30;
-            uint32_t first = 0;
-            while (first < ng) {
-                uint32_t last = first + 1;
-                while (last < ng && off[last + 1] - off[first] <= round_bytes) last++;
-                uint64_t need = off[last] - off[first];
-                BWT_TRY(grow(st.d_gen_scratch, st.gen_scratch_bytes, (size_t)need));
-                uint32_t cnt = last - first;
-                sw_general_kernel<<<(cnt + 63) / 64, 64, 0, stream>>>(d_qbase, d_rbase, st.d_desc, st.d_list_gen, first, cnt,
-                                                                     st.d_gen_off, st.d_gen_scratch, st.d_out, st.d_ctr,
-                                                                     st.d_cig_tmp, st.cig_cap);
-                st.launches += 1;
-                K_CHECK(stream, "sw_general_kernel");
-                CU_TRY(cudaStreamSynchronize(stream));
-                first = last;
-            }
-            CU_TRY(cudaMemcpyAsync(st.h_ctr, st.d_ctr, sizeof(SwCounters), cudaMemcpyDeviceToHost, stream));
-            CU_TRY(cudaStreamSynchronize(stream));
-        }
-        if (!st.h_ctr->cig_overflow) {
-            cudaEventElapsedTime(&st.ms_fast_kernel, st.ev_k0, st.ev_k1);
-            st.sw_calls = st.h_ctr->sw_calls; st.cells = st.h_ctr->cells; st.n_general = st.h_ctr->n_general;
-            st.shortcut_calls = st.h_ctr->shortcut_calls; st.shortcut_cells = st.h_ctr->shortcut_cells;
-            return BWT_OK;
-        }
-        // temporary CIGAR arena too small: grow to what this attempt asked for (and then some) and redo the stage
-        uint64_t want = (uint64_t)st.h_ctr->cig_used * 2 + 4096;
-        if (want > 0xFFFFFFF0ull) { bwt_set_error("CIGAR arena beyond 4 GiB for one batch: use smaller batches"); return BWT_ERR_LIMIT; }
-        cudaFree(st.d_cig_tmp);
-        st.d_cig_tmp = nullptr;
-        st.cig_cap = (uint32_t)want;
-        CU_TRY(cudaMalloc(&st.d_cig_tmp, st.cig_cap));
+        *redo_emit = true;
+        BWT_TRY(refresh());
+    }
+    if (!st.h_ctr->cig_overflow) {
+        cudaEventElapsedTime(&st.ms_fast_kernel, st.ev_k0, st.ev_k1);
+        st.sw_calls = st.h_ctr->sw_calls; st.cells = st.h_ctr->cells; st.n_general = st.h_ctr->n_general;
+        st.shortcut_calls = st.h_ctr->shortcut_calls; st.shortcut_cells = st.h_ctr->shortcut_cells;
+        return BWT_OK;
+    }
+    // temporary CIGAR arena too small: grow to what this attempt asked for (and then some); the caller redoes the stage
+    uint64_t want = (uint64_t)st.h_ctr->cig_used * 2 + 4096;
+    if (want > 0xFFFFFFF0ull) { bwt_set_error("CIGAR arena beyond 4 GiB for one batch: use smaller batches"); return BWT_ERR_LIMIT; }
+    cudaFree(st.d_cig_tmp);
+    st.d_cig_tmp = nullptr;
+    st.cig_cap = (uint32_t)want;
+    CU_TRY(cudaMalloc(&st.d_cig_tmp, st.cig_cap));
+    return BWT_ERR_NOSPACE;
+}
+
+// enqueue + finish with the synchronisations in between (one-shot callers: bwt_sw_batch)
+int sw_stage_run(SwStage &st, const DevReads &R, const uint8_t *d_rbase, const uint32_t *d_ref2, const uint32_t *d_refx,
+                 const uint32_t *d_n, uint32_t n, int max_lq, cudaStream_t stream) {
+    if (n == 0) return BWT_OK;
+    for (int attempt = 0; attempt < 4; attempt++) {
+        BWT_TRY(sw_stage_enqueue(st, R, d_rbase, d_ref2, d_refx, d_n, n, max_lq, stream));
+        CU_TRY(cudaMemcpyAsync(st.h_ctr, st.d_ctr, sizeof(SwCounters), cudaMemcpyDeviceToHost, stream));
+        CU_TRY(cudaStreamSynchronize(stream));
+        bool redo = false;
+        const int rc = sw_stage_finish(st, R, d_rbase, d_ref2, d_refx, n, max_lq, stream, &redo);
+        if (rc != BWT_ERR_NOSPACE) return rc;
     }
     bwt_set_error("CIGAR arena kept overflowing");
     return BWT_ERR_NOMEM;

@@ -2,11 +2,12 @@
 #pragma once
 #include "common.cuh"
 
-struct SwDesc {          // one (query, window) pair; offsets are into the q / r base buffers
-    int64_t q_off;
+struct SwDesc {          // one (query, window) pair: read `read` of the batch against bytes [r_off, r_off+lr) of the window source
     int64_t r_off;
+    uint32_t read;
     int32_t lq;
     int32_t lr;
+    uint32_t pad;
 };
 
 struct SwOut {           // 16 B per pair
@@ -20,10 +21,12 @@ struct SwCounters {
     unsigned long long sw_calls, cells;
     unsigned long long shortcut_calls, shortcut_cells;   // pairs settled by sw_classify_kernel without the DP (included above)
     uint32_t n_fast, n_wide, n_general, n_ovf;   // list cursors
+    uint32_t n_wfa, pad2;                        // pairs the quick test left to the wavefront rule
     uint32_t cig_used, cig_overflow; // temporary CIGAR arena
     uint32_t general_done, pad;
 };
 
+constexpr int32_t SW_FULL_M = 0x100;  // flag on SwOut.status (internal): the CIGAR is "<Lq>M" (pairs settled without the table)
 constexpr int SW_R = 10;             // rows per register strip; ten 3-bit direction codes per 32-bit word
 constexpr int SW_BLOCK = 128;
 constexpr int SW_SHORTCUT_MAX_D = 16; // widest window slack (Lr - Lq) the no-DP shortcut looks at
@@ -35,7 +38,7 @@ struct SwStage {
     uint32_t cap = 0;                // pairs
     SwDesc *d_desc = nullptr;
     SwOut *d_out = nullptr;
-    uint32_t *d_list_fast = nullptr, *d_list_wide = nullptr, *d_list_gen = nullptr, *d_list_ovf = nullptr;
+    uint32_t *d_list_fast = nullptr, *d_list_wide = nullptr, *d_list_gen = nullptr, *d_list_ovf = nullptr, *d_list_wfa = nullptr;
     SwCounters *d_ctr = nullptr, *h_ctr = nullptr;     // h_ctr pinned
     char *d_cig_tmp = nullptr;
     uint32_t cig_cap = 0;
@@ -55,7 +58,12 @@ struct SwStage {
 
 int sw_stage_reserve(SwStage &st, uint32_t pairs);
 void sw_stage_free(SwStage &st);
-// Runs the extension of pairs [0,n): d_desc must be filled, d_out[k].status preset to BWT_HIT_WINDOW_OOR for pairs
-// to skip and anything else for pairs to align.  max_lq = longest query (sizes the shared-memory tier).
-int sw_stage_run(SwStage &st, const uint8_t *d_qbase, const uint8_t *d_rbase, uint32_t n, int max_lq,
-                 cudaStream_t stream);
+// The extension of pairs [0,*d_n): d_desc must be filled, d_out[k].status preset to BWT_HIT_WINDOW_OOR for pairs
+// to skip and anything else for pairs to align.  max_lq = longest query (sizes the shared-memory tier), n_cap >= *d_n.
+// R: the batch's reads; d_rbase / d_ref2 / d_refx: the window source as ASCII, 2-bit words and non-ACGT flags.
+int sw_stage_enqueue(SwStage &st, const DevReads &R, const uint8_t *d_rbase, const uint32_t *d_ref2, const uint32_t *d_refx,
+                     const uint32_t *d_n, uint32_t n_cap, int max_lq, cudaStream_t stream);
+int sw_stage_finish(SwStage &st, const DevReads &R, const uint8_t *d_rbase, const uint32_t *d_ref2, const uint32_t *d_refx,
+                    uint32_t n_cap, int max_lq, cudaStream_t stream, bool *redo_emit);
+int sw_stage_run(SwStage &st, const DevReads &R, const uint8_t *d_rbase, const uint32_t *d_ref2, const uint32_t *d_refx,
+                 const uint32_t *d_n, uint32_t n, int max_lq, cudaStream_t stream);

@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define BWT_B200_ABI_VERSION 2   /* 2: bwt_stats grew (sw_shortcut, sw_shortcut_cells), bwt_fs_find_seeds_batch */
+#define BWT_B200_ABI_VERSION 3   /* 3: packed reads in, compact hits out, bwt_index_info.fused, bwt_sample_reads_edits */
 
 typedef enum bwt_status {
     BWT_OK = 0,
@@ -82,6 +82,8 @@ typedef struct bwt_index_info {
     uint64_t device_bytes;  /* HBM held by this handle */
     int32_t device;
     int32_t kmer_k;         /* depth of the deepest k-mer interval table (8..15) */
+    int32_t fused;          /* 1: the depth-15 table is the fused one (64 B per 15-mer: interval + first 14 SA values) */
+    int32_t reserved;
 } bwt_index_info;
 
 /* One candidate of one read: an element of worker_bwt's Cigars fold (worker_bwt.erl:84-97), plus the
@@ -95,6 +97,37 @@ typedef struct bwt_hit {
     int32_t status;     /* BWT_HIT_* */
     int32_t cigar_len;
 } bwt_hit;
+
+/* The same candidate in 16 bytes, for bulk results (a third of the bytes over PCIe / NVLink): Pos = s - (Lq + D) + Shift is
+ * left to the consumer, and a CIGAR that is exactly "<Lq>M" is flagged instead of stored. */
+typedef struct bwt_hit16 {
+    uint32_t s;           /* sga's S */
+    uint32_t d_flags;     /* bits 0-27: sga's D; bits 28-29: BWT_HIT_* status; bit 30: BWT_HIT16_FULL_M */
+    uint32_t cigar_off;   /* byte offset in the CIGAR arena (0 when the CIGAR is not stored) */
+    int16_t score;        /* trunc(Vmax) */
+    uint16_t cigar_len;   /* 0 when the CIGAR is not stored */
+} bwt_hit16;
+#define BWT_HIT16_D(h) ((h).d_flags & 0x0FFFFFFFu)
+#define BWT_HIT16_STATUS(h) (((h).d_flags >> 28) & 3u)
+#define BWT_HIT16_FULL_M 0x40000000u   /* the CIGAR is "<Lq>M" (Lq = the read's length) and takes no arena bytes */
+
+/* Reads as the kernels take them: 2 bits per base (A0 C1 G2 T3), read r REVERSED (its last base in bits 0-1 of its first
+ * word), ceil(len/16) words per read, reads one after the other, one zero pad word at the very end.  A read that holds a
+ * byte outside ACGT (sga:skip_Ns/1, the 1.6 of bwt.hrl:15 and the case_clause of bwa.erl:15-24 need the bytes), or is
+ * longer than 1040 bases (then it has no words), is listed in exc_idx and brings its ASCII text.  bwt_pack_reads fills
+ * one of these from an ASCII batch. */
+typedef struct bwt_packed_reads {
+    int64_t n;
+    int32_t fixed_len;          /* > 0: every read has this length and lens is unused */
+    int32_t reserved;
+    const uint16_t *lens;       /* n lengths (capped at 65535) */
+    const uint32_t *words;      /* n_words + 1 words */
+    int64_t n_words;
+    int64_t n_exc;              /* flagged reads: */
+    const uint32_t *exc_idx;    /*   their indices, ascending */
+    const int64_t *exc_off;     /*   n_exc + 1 offsets into exc_ascii */
+    const uint8_t *exc_ascii;   /*   their text */
+} bwt_packed_reads;
 
 typedef struct bwt_stats {   /* work counters of the last run (definitions: DESIGN.md "units") */
     uint64_t reads, searches, lf_steps, hbm_lf_steps, located_rows, clusters, sw_calls, sw_cells, sw_general;
@@ -198,7 +231,20 @@ int bwt_batch_result_size(bwt_batch *b, int64_t *n_hits, int64_t *cigar_bytes);
 int bwt_batch_download(bwt_batch *b, int32_t *read_status, int64_t *hit_offsets, bwt_hit *hits, int64_t hits_cap,
                        char *cigars, int64_t cigar_cap);
 int bwt_batch_stats(bwt_batch *b, bwt_stats *out);
-/* device pointers of the last run's result (for an NCCL gather by the host harness; valid until the next run) */
+
+/* The same with packed reads in and compact records out: bwt_batch_upload_packed / bwt_batch_run_compact /
+ * bwt_batch_download_compact (uint8 read status, uint32 offsets, bwt_hit16). */
+int64_t bwt_pack_words(const int64_t *offsets, int64_t n);     /* words bwt_pack_reads will write (excluding the pad word); -1: bad offsets */
+/* ASCII batch -> packed layout on `threads` host threads.  words (capacity words_cap >= bwt_pack_words + 1) and lens[n]
+ * always; the flagged reads into exc_idx / exc_off / exc_ascii (BWT_ERR_NOSPACE with *n_exc / *exc_bytes = needed). */
+int bwt_pack_reads(const uint8_t *reads, const int64_t *offsets, int64_t n, int threads, uint32_t *words, int64_t words_cap,
+                   uint16_t *lens, uint32_t *exc_idx, int64_t exc_cap, int64_t *exc_off, uint8_t *exc_ascii,
+                   int64_t exc_ascii_cap, int64_t *n_words, int64_t *n_exc, int64_t *exc_bytes);
+int bwt_batch_upload_packed(bwt_batch *b, const bwt_packed_reads *p);
+int bwt_batch_run_compact(bwt_batch *b);
+int bwt_batch_download_compact(bwt_batch *b, uint8_t *read_status, uint32_t *hit_offsets, bwt_hit16 *hits, int64_t hits_cap,
+                               char *cigars, int64_t cigar_cap);
+/* device pointers of the last run's result (wide or compact, as it was run; valid until the next run) */
 int bwt_batch_device_result(bwt_batch *b, void **d_hit_offsets, void **d_hits, void **d_cigars);
 
 /* ---- pipelined aligner: bwt_align_batch with persistent buffers and overlapped copies ------------------- */
@@ -212,6 +258,10 @@ int bwt_aligner_create(bwt_index *h, int64_t chunk_reads, int64_t chunk_bytes, i
 int bwt_aligner_run(bwt_aligner *a, const uint8_t *reads, const int64_t *offsets, int64_t n, int32_t *read_status,
                     int64_t *hit_offsets, bwt_hit *hits, int64_t hits_cap, int64_t *n_hits, char *cigars,
                     int64_t cigar_cap, int64_t *cigar_bytes);
+/* packed reads in, compact records out: 28 + ~22 bytes per 100 bp read over PCIe instead of 108 + 54 */
+int bwt_aligner_run_packed(bwt_aligner *a, const bwt_packed_reads *p, uint8_t *read_status, uint32_t *hit_offsets,
+                           bwt_hit16 *hits, int64_t hits_cap, int64_t *n_hits, char *cigars, int64_t cigar_cap,
+                           int64_t *cigar_bytes);
 int bwt_aligner_stats(bwt_aligner *a, bwt_stats *out);   /* sums over the chunks of the last run */
 int bwt_aligner_destroy(bwt_aligner *a);
 

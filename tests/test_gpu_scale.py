@@ -71,6 +71,29 @@ def test_full_size_properties(big):
     b = ix.align(reads[:offs[m]], offs[:m + 1])
     ix.set_kmer_depth(deep)
     assert (a[1] == b[1]).all() and (a[2] == b[2]).all() and a[3] == b[3]
+    # nor does the fused depth-15 table (interval + first SA values in one 64-byte line) against the plain 8-byte one
+    if deep == 15:
+        was = ix.info().fused
+        for fused in (0, 1):
+            os.environ["BWT_FUSED"] = str(fused)
+            try:
+                ix.set_kmer_depth(15)
+            finally:
+                os.environ.pop("BWT_FUSED", None)
+            assert ix.info().fused == fused
+            c = ix.align(reads[:offs[m]], offs[:m + 1])
+            assert (a[1] == c[1]).all() and (a[2] == c[2]).all() and a[3] == c[3]
+        if not was:
+            os.environ["BWT_FUSED"] = "0"
+            ix.set_kmer_depth(15)
+            os.environ.pop("BWT_FUSED", None)
+    # ragged reads with indels (SURVEY.md 8d model): packed reads in / compact records out == ASCII in / wide out
+    rr, ro, _ = api.sample_reads_edits(ix, 400_000, 100, seed=77, edit_rate=0.01)
+    w = al.run(rr, ro)
+    pk = api.PackedReads(rr, ro, threads=8)
+    g = api.expand_compact(*al.run_packed(pk), read_lens=np.diff(ro), shift=1)
+    assert (g[0] == w[0]).all() and (g[1] == w[1]).all() and (g[2] == w[2]).all() and g[3] == w[3]
+    assert (w[2]["status"] == 0).sum() > 100_000 and pk.n_exc == 0
     assert (a[1] == ho[:m + 1]).all() and (a[2] == hits[:ho[m]]).all()        # and sharding invariance
     # sampled pairs re-aligned by the CPU port of sw:sw/2 on the window cut from the exported .ref
     _, _, ref = ix.export(want_L=False, want_SA=False)

@@ -25,13 +25,15 @@ def test_library_exports_every_declared_symbol():
     L = _lib.lib()                                   # raises if a symbol is missing
     for n in names:
         assert getattr(L, n) is not None
-    assert L.bwt_abi_version() == 2
+    assert L.bwt_abi_version() == 3
 
 
 def test_struct_layouts_match_header():
     from bwt_b200 import _lib, api
     assert C.sizeof(_lib.BwtHit) == 40 and api.HIT_DTYPE.itemsize == 40
-    assert C.sizeof(_lib.BwtIndexInfo) == 64
+    assert C.sizeof(_lib.BwtIndexInfo) == 72
+    assert C.sizeof(_lib.BwtHit16) == 16 and api.HIT16_DTYPE.itemsize == 16
+    assert C.sizeof(_lib.BwtPackedReads) == 72 and C.sizeof(_lib.BwtSampleOpts) == 72
     assert C.sizeof(_lib.BwtStats) == 9 * 8 + 8 * 4 + 2 * 4 + 2 * 8
 
 

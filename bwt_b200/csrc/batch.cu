@@ -75,11 +75,11 @@ __global__ void windows_kernel(const Cluster *__restrict__ cl, const uint32_t *_
 
 // per read: number of hits and CIGAR bytes (inputs of the two scans).  compact: "<Lq>M" CIGARs are not stored.
 __global__ void emit_count_kernel(const uint32_t *__restrict__ ncl, const uint32_t *__restrict__ cl_base,
-                                  const SwOut *__restrict__ out, int64_t n, int compact, uint32_t *__restrict__ hit_cnt,
-                                  uint32_t *__restrict__ cig_cnt) {
+                                  const SwOut *__restrict__ out, int64_t n, int compact, const uint32_t *__restrict__ abort,
+                                  uint32_t *__restrict__ hit_cnt, uint32_t *__restrict__ cig_cnt) {
     int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r > n) return;
-    if (r == n) { hit_cnt[n] = 0; cig_cnt[n] = 0; return; }   // slot n turns into the total under the exclusive scan
+    if (r == n || *abort) { hit_cnt[r] = 0; cig_cnt[r] = 0; return; }   // slot n turns into the total under the exclusive scan
     uint32_t c = ncl[r], b = cl_base[r], bytes = 0;
     for (uint32_t k = 0; k < c; k++) {
         const SwOut o = out[b + k];
@@ -96,10 +96,10 @@ __global__ void emit_kernel(const uint32_t *__restrict__ ncl, const uint32_t *__
                             const SwOut *__restrict__ out, const char *__restrict__ cig_tmp, int64_t n,
                             const uint32_t *__restrict__ hit_off, const uint32_t *__restrict__ cig_off, int64_t shift,
                             int64_t *__restrict__ hit_off64, bwt_hit *__restrict__ hits, char *__restrict__ cigars,
-                            uint32_t hits_cap, uint32_t cig_cap) {
+                            uint32_t hits_cap, uint32_t cig_cap, uint32_t tmp_cap, const uint32_t *__restrict__ abort) {
     int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r > n) return;
-    if (r == n) { hit_off64[n] = hit_off[n]; return; }
+    if (r == n || *abort) { hit_off64[r] = hit_off[r]; return; }
     uint32_t c = ncl[r], b = cl_base[r], ho = hit_off[r], co = cig_off[r];
     hit_off64[r] = ho;
     for (uint32_t k = 0; k < c; k++) {
@@ -115,7 +115,7 @@ __global__ void emit_kernel(const uint32_t *__restrict__ ncl, const uint32_t *__
         h.cigar_len = o.cigar_len;
         h.cigar_off = co;
         if (ho + k < hits_cap) hits[ho + k] = h;
-        if ((uint64_t)co + (uint32_t)o.cigar_len <= cig_cap)
+        if ((uint64_t)co + (uint32_t)o.cigar_len <= cig_cap && (uint64_t)o.cigar_off + (uint32_t)o.cigar_len <= tmp_cap)
             for (int t = 0; t < o.cigar_len; t++) cigars[co + t] = cig_tmp[o.cigar_off + t];
         co += (uint32_t)o.cigar_len;
     }
@@ -126,9 +126,10 @@ __global__ void emit16_kernel(const uint32_t *__restrict__ ncl, const uint32_t *
                               const Cluster *__restrict__ cl, const SwOut *__restrict__ out, const char *__restrict__ cig_tmp,
                               const int32_t *__restrict__ read_status, int64_t n, const uint32_t *__restrict__ hit_off,
                               const uint32_t *__restrict__ cig_off, uint8_t *__restrict__ status8, bwt_hit16 *__restrict__ hits,
-                              char *__restrict__ cigars, uint32_t hits_cap, uint32_t cig_cap, uint32_t *__restrict__ flags) {
+                              char *__restrict__ cigars, uint32_t hits_cap, uint32_t cig_cap, uint32_t tmp_cap,
+                              const uint32_t *__restrict__ abort, uint32_t *__restrict__ flags) {
     int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= n) return;
+    if (r >= n || *abort) return;
     status8[r] = (uint8_t)read_status[r];
     uint32_t c = ncl[r], b = cl_base[r], ho = hit_off[r], co = cig_off[r];
     for (uint32_t k = 0; k < c; k++) {
@@ -145,7 +146,7 @@ __global__ void emit16_kernel(const uint32_t *__restrict__ ncl, const uint32_t *
         h.cigar_off = full_m ? 0u : co;
         if (ho + k < hits_cap) hits[ho + k] = h;
         if (!full_m) {
-            if ((uint64_t)co + (uint32_t)o.cigar_len <= cig_cap)
+            if ((uint64_t)co + (uint32_t)o.cigar_len <= cig_cap && (uint64_t)o.cigar_off + (uint32_t)o.cigar_len <= tmp_cap)
                 for (int t = 0; t < o.cigar_len; t++) cigars[co + t] = cig_tmp[o.cigar_off + t];
             co += (uint32_t)o.cigar_len;
         }
@@ -284,7 +285,7 @@ static int batch_alloc(bwt_batch *b) {
     CU_TRY(cudaMalloc(&b->d_slow, (size_t)b->slow_cap * sizeof(SlowRead)));
     BWT_TRY(dev_grow(b->d_slow_scratch, b->slow_scratch_cap, (size_t)1 << 20, false));
     b->sw.device = b->ix->device;
-    size_t want_cl = (size_t)std::max<int64_t>(2 * nr, 4096);
+    size_t want_cl = (size_t)std::max<int64_t>(4 * nr, 4096);
     BWT_TRY(dev_grow(b->d_clusters, b->cl_cap, want_cl, false));
     BWT_TRY(dev_grow(b->d_clusters_sparse, b->cl_sparse_cap, b->cl_cap, false));
     BWT_TRY(sw_stage_reserve(b->sw, (uint32_t)b->cl_cap));
@@ -498,7 +499,7 @@ static int enqueue_seed_stage(bwt_batch *b, uint32_t cl_cap) {
                             b->d_ncl, b->d_cl_base, b->d_clusters_sparse, cl_cap, b->d_ctr, b->stream));
     b->stats.launches += 2;
     // sub-lists -> dense cluster list, dense cl_base, n_clusters
-    return launch_sga_finish(b->d_clusters_sparse, b->d_clusters, cl_cap, b->d_cl_base, b->d_ncl, b->n, b->d_ctr, b->stream,
+    return launch_sga_finish(b->d_clusters_sparse, b->d_clusters, cl_cap, b->d_cl_base, b->d_ncl, b->n, b->slow_cap, b->d_ctr, b->stream,
                              &b->stats.launches);
 }
 
@@ -509,9 +510,9 @@ static int enqueue_emit_stage(bwt_batch *b, bool compact) {
     if (compact) BWT_TRY(dev_grow(b->d_hits16, b->hits16_cap, hcap, false));
     else BWT_TRY(dev_grow(b->d_hits, b->hits_cap, hcap, false));
     BWT_TRY(dev_grow(b->d_cigars, b->cigars_cap, ccap, false));
-    emit_count_kernel<<<blocks, 256, 0, b->stream>>>(b->d_ncl, b->d_cl_base, b->sw.d_out, n, compact ? 1 : 0, b->d_hit_off, b->d_cig_off);
+    emit_count_kernel<<<blocks, 256, 0, b->stream>>>(b->d_ncl, b->d_cl_base, b->sw.d_out, n, compact ? 1 : 0, &b->d_ctr->abort, b->d_hit_off, b->d_cig_off);
     b->stats.launches += 1;
-    CU_TRY(cudaGetLastError());
+    K_CHECK(b->stream, "emit_count_kernel");
     // element n of an exclusive scan over n+1 items is the total (item n is written as 0 above)
     BWT_TRY(exclusive_scan_u32(b->d_hit_off, (size_t)n + 1, b->d_scan_tmp, &b->d_totals->hits, b->stream, &b->stats.launches));
     BWT_TRY(exclusive_scan_u32(b->d_cig_off, (size_t)n + 1, b->d_scan_tmp, &b->d_totals->cig_bytes, b->stream, &b->stats.launches));
@@ -519,14 +520,15 @@ static int enqueue_emit_stage(bwt_batch *b, bool compact) {
         emit16_kernel<<<blocks, 256, 0, b->stream>>>(b->d_ncl, b->d_cl_base, b->d_clusters, b->sw.d_out, b->sw.d_cig_tmp, b->d_read_status, n,
                                                      b->d_hit_off, b->d_cig_off, b->d_status8, b->d_hits16, b->d_cigars,
                                                      (uint32_t)std::min<size_t>(b->hits16_cap, 0xFFFFFFFFu), (uint32_t)std::min<size_t>(b->cigars_cap, 0xFFFFFFFFu),
-                                                     &b->d_totals->emit_flags);
+                                                     b->sw.cig_cap, &b->d_ctr->abort, &b->d_totals->emit_flags);
     else
         emit_kernel<<<blocks, 256, 0, b->stream>>>(b->d_ncl, b->d_cl_base, b->d_clusters, b->sw.d_desc, b->sw.d_out,
                                                    b->sw.d_cig_tmp, n, b->d_hit_off, b->d_cig_off, b->ix->shift,
                                                    b->d_hit_off64, b->d_hits, b->d_cigars,
-                                                   (uint32_t)std::min<size_t>(b->hits_cap, 0xFFFFFFFFu), (uint32_t)std::min<size_t>(b->cigars_cap, 0xFFFFFFFFu));
+                                                   (uint32_t)std::min<size_t>(b->hits_cap, 0xFFFFFFFFu), (uint32_t)std::min<size_t>(b->cigars_cap, 0xFFFFFFFFu),
+                                                   b->sw.cig_cap, &b->d_ctr->abort);
     b->stats.launches += 1;
-    CU_TRY(cudaGetLastError());
+    K_CHECK(b->stream, "emit_kernel");
     return BWT_OK;
 }
 
@@ -562,10 +564,10 @@ static int run_core(bwt_batch *b, bool with_sw, bool compact) {
         BWT_TRY(enqueue_seed_stage(b, cl_cap));
         CU_TRY(cudaEventRecord(b->ev[1], b->stream));
         if (with_sw) {
-            windows_kernel<<<148 * 8, 256, 0, b->stream>>>(b->d_clusters, &b->d_ctr->n_clusters, b->d_len, ix.ref_len_padded, b->sw.d_desc, b->sw.d_out);
+            windows_kernel<<<148 * 8, 256, 0, b->stream>>>(b->d_clusters, &b->d_ctr->n_pairs, b->d_len, ix.ref_len_padded, b->sw.d_desc, b->sw.d_out);
             b->stats.launches += 1;
             K_CHECK(b->stream, "windows_kernel");
-            BWT_TRY(sw_stage_enqueue(b->sw, b->R, ix.ref, ix.ref2, ix.refx, &b->d_ctr->n_clusters, cl_cap, b->max_read_len, b->stream));
+            BWT_TRY(sw_stage_enqueue(b->sw, b->R, ix.ref, ix.ref2, ix.refx, &b->d_ctr->n_pairs, cl_cap, b->max_read_len, b->stream));
             CU_TRY(cudaMemcpyAsync(b->sw.h_ctr, b->sw.d_ctr, sizeof(SwCounters), cudaMemcpyDeviceToHost, b->stream));
             CU_TRY(cudaEventRecord(b->ev[2], b->stream));
             BWT_TRY(enqueue_emit_stage(b, compact));

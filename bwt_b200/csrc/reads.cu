@@ -83,7 +83,7 @@ __global__ void exc_scatter_kernel(const uint32_t *__restrict__ idx, uint32_t n_
 int reads_geom_from_ascii(const int64_t *d_aoff, int64_t n, uint32_t *d_len, uint32_t *d_woff, uint32_t *d_scan_tmp,
                           uint32_t *d_info, cudaStream_t stream, uint32_t *launches) {
     ascii_geom_kernel<<<(unsigned)((n + 1 + 255) / 256), 256, 0, stream>>>(d_aoff, n, d_len, d_woff, d_info);
-    CU_TRY(cudaGetLastError());
+    K_CHECK(stream, "ascii_geom_kernel");
     if (launches) *launches += 1;
     return exclusive_scan_u32(d_woff, (size_t)n + 1, d_scan_tmp, nullptr, stream, launches);
 }
@@ -108,7 +108,7 @@ int reads_pack_device(const uint8_t *d_ascii, const int64_t *d_aoff, int64_t aof
     if (n <= 0) return BWT_OK;
     const int64_t threads = (n + 31) & ~(int64_t)31;
     pack_reads_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, stream>>>(d_ascii, d_aoff, aoff_base, n, d_len, d_woff, d_pk, d_exc);
-    CU_TRY(cudaGetLastError());
+    K_CHECK(stream, "pack_reads_kernel");
     if (launches) *launches += 1;
     return BWT_OK;
 }

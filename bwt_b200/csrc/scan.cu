@@ -92,7 +92,7 @@ int exclusive_scan_u32(uint32_t *d_data, size_t n, uint32_t *d_tmp, uint32_t *d_
     if (nb == 1) {
         scan_down_kernel<<<1, SCAN_THREADS, 0, stream>>>(d_data, n, nullptr, d_total);
         if (launches) *launches += 1;
-        CU_TRY(cudaGetLastError());
+        K_CHECK(stream, "scan_down_kernel");
         return BWT_OK;
     }
     scan_reduce_kernel<<<(unsigned)nb, SCAN_THREADS, 0, stream>>>(d_data, n, d_tmp);
@@ -101,6 +101,6 @@ int exclusive_scan_u32(uint32_t *d_data, size_t n, uint32_t *d_tmp, uint32_t *d_
     BWT_TRY(exclusive_scan_u32(d_tmp, nb, d_tmp + nb, nullptr, stream, launches));
     scan_down_kernel<<<(unsigned)nb, SCAN_THREADS, 0, stream>>>(d_data, n, d_tmp, d_total);
     if (launches) *launches += 1;
-    CU_TRY(cudaGetLastError());
+    K_CHECK(stream, "scan_down_kernel");
     return BWT_OK;
 }

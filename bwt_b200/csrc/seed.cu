@@ -213,6 +213,7 @@ __device__ __forceinline__ int sga_read(const Tile &tile, const DevIndex &ix, co
         if (lane == 0) {
             uint32_t slot = atomicAdd(&ctr->n_slow, 1u);
             if (slot < slow_cap) { slow[slot].read = read; slow[slot].seeds = total; }
+            ncl[read] = 0; cl_base[read] = 0;          // until the slow kernel has done the read
         }
         return SGA_DEFER;
     }
@@ -606,14 +607,21 @@ __global__ void __launch_bounds__(SGA_BLOCK) sga_slow_kernel(DevIndex ix, DevRea
 }  // namespace
 
 namespace {
-__global__ void cluster_offsets_kernel(SeedCounters *ctr, uint32_t cap_r) {     // one warp
+__global__ void cluster_offsets_kernel(SeedCounters *ctr, uint32_t cap_r, uint32_t slow_cap) {     // one warp
     uint32_t sum = 0, dense = 0;
     for (int r = 0; r < SGA_SUBLISTS; r++) {
         const uint32_t c = ctr->sub_n[32 * r];
         if (threadIdx.x == 0) ctr->dense_base[r] = dense;
         sum += c; dense += min(c, cap_r);
     }
-    if (threadIdx.x == 0) ctr->n_clusters = sum;
+    if (threadIdx.x == 0) {
+        // a capacity overflowed (cluster sub-list, deferred-read list, slow scratch): per-read results are incomplete, so the
+        // kernels behind this one get nothing to do and the host grows the capacity and runs the batch again
+        const uint32_t ab = (ctr->cluster_overflow | ctr->scratch_overflow | (ctr->n_slow > slow_cap ? 1u : 0u)) ? 1u : 0u;
+        ctr->n_clusters = sum;
+        ctr->abort = ab;
+        ctr->n_pairs = ab ? 0u : sum;
+    }
 }
 __global__ void cluster_compact_kernel(const Cluster *__restrict__ sparse, Cluster *__restrict__ dense, const SeedCounters *ctr,
                                        uint32_t cap_r) {
@@ -630,13 +638,13 @@ __global__ void cluster_rebase_kernel(uint32_t *__restrict__ cl_base, const uint
 }  // namespace
 
 int launch_sga_finish(const Cluster *d_sparse, Cluster *d_dense, uint32_t cl_cap, uint32_t *d_cl_base, const uint32_t *d_ncl,
-                      int64_t n_reads, SeedCounters *d_ctr, cudaStream_t stream, uint32_t *launches) {
+                      int64_t n_reads, uint32_t slow_cap, SeedCounters *d_ctr, cudaStream_t stream, uint32_t *launches) {
     const uint32_t cap_r = cl_cap / SGA_SUBLISTS;
-    cluster_offsets_kernel<<<1, 32, 0, stream>>>(d_ctr, cap_r);
+    cluster_offsets_kernel<<<1, 32, 0, stream>>>(d_ctr, cap_r, slow_cap);
     cluster_compact_kernel<<<dim3((cap_r + 255) / 256, SGA_SUBLISTS), 256, 0, stream>>>(d_sparse, d_dense, d_ctr, cap_r);
     if (n_reads > 0) cluster_rebase_kernel<<<(unsigned)((n_reads + 255) / 256), 256, 0, stream>>>(d_cl_base, d_ncl, n_reads, d_ctr, cap_r);
     if (launches) *launches += 3;
-    CU_TRY(cudaGetLastError());
+    K_CHECK(stream, "cluster_offsets / compact / rebase kernels");
     return BWT_OK;
 }
 
@@ -676,7 +684,7 @@ int launch_sga(const DevIndex &ix, const DevReads &R, int64_t n_reads, int max_r
                                                                                d_ncl, d_cl_base, d_clusters, cl_cap, d_slow,
                                                                                slow_cap, d_ctr);
     }
-    CU_TRY(cudaGetLastError());
+    K_CHECK(stream, "sga_kernel");
     return BWT_OK;
 }
 
@@ -687,6 +695,6 @@ int launch_sga_slow(const DevIndex &ix, const DevReads &R, const SlowRead *d_slo
                     cudaStream_t stream) {
     sga_slow_kernel<<<148, SGA_BLOCK, 0, stream>>>(ix, R, d_slow, slow_cap, d_scratch, (unsigned long long)scratch_cap,
                                                    d_read_status, d_ncl, d_cl_base, d_clusters, cl_cap, d_ctr);
-    CU_TRY(cudaGetLastError());
+    K_CHECK(stream, "sga_slow_kernel");
     return BWT_OK;
 }

@@ -24,6 +24,9 @@ struct SeedCounters {   // device-side counters of one run
     uint32_t cluster_overflow;
     uint32_t scratch_overflow;   // a deferred read did not fit the slow kernel's scratch
     unsigned long long scratch_used;
+    uint32_t n_pairs;            // what the kernels behind the seeding stage work on: n_clusters, or 0 when a capacity overflowed
+    uint32_t abort;              // a capacity overflowed: the rest of the run is skipped on the device, the host grows and reruns
+    uint32_t pad2[2];
     uint32_t dense_base[SGA_SUBLISTS];          // first dense slot of each sub-list (launch_sga_finish)
     uint32_t sub_n[SGA_SUBLISTS * 32];          // cursor of sub-list r at [32 r]
 };
@@ -41,7 +44,7 @@ int launch_sga(const DevIndex &ix, const DevReads &R, int64_t n_reads, int max_r
                SlowRead *d_slow, uint32_t slow_cap, SeedCounters *d_ctr, cudaStream_t stream);
 // Packs the sub-lists of d_sparse into d_dense, turns cl_base into dense indices and sets d_ctr->n_clusters.
 int launch_sga_finish(const Cluster *d_sparse, Cluster *d_dense, uint32_t cl_cap, uint32_t *d_cl_base, const uint32_t *d_ncl,
-                      int64_t n_reads, SeedCounters *d_ctr, cudaStream_t stream, uint32_t *launches);
+                      int64_t n_reads, uint32_t slow_cap, SeedCounters *d_ctr, cudaStream_t stream, uint32_t *launches);
 int launch_sga_slow(const DevIndex &ix, const DevReads &R, const SlowRead *d_slow, uint32_t slow_cap,
                     uint32_t *d_scratch, uint64_t scratch_cap, int32_t *d_read_status,
                     uint32_t *d_ncl, uint32_t *d_cl_base, Cluster *d_clusters, uint32_t cl_cap, SeedCounters *d_ctr,

@@ -811,8 +811,8 @@ int grow(T *&p, size_t &cap_items, size_t need_items) {
 int sw_stage_reserve(SwStage &st, uint32_t pairs) {
     if (pairs <= st.cap && st.d_desc) return BWT_OK;
     uint32_t want = pairs + pairs / 4 + 1024;
-    if (st.d_desc) { cudaFree(st.d_desc); cudaFree(st.d_out); cudaFree(st.d_list_fast); cudaFree(st.d_list_wide); cudaFree(st.d_list_gen); cudaFree(st.d_list_ovf); cudaFree(st.d_list_wfa); }
-    st.d_desc = nullptr; st.d_out = nullptr; st.d_list_fast = nullptr; st.d_list_wide = nullptr; st.d_list_gen = nullptr; st.d_list_ovf = nullptr; st.d_list_wfa = nullptr;
+    if (st.d_desc) { cudaFree(st.d_desc); cudaFree(st.d_out); cudaFree(st.d_list_fast); cudaFree(st.d_list_wide); cudaFree(st.d_list_gen); cudaFree(st.d_list_ovf); cudaFree(st.d_list_wfa); cudaFree(st.d_list_big); }
+    st.d_desc = nullptr; st.d_out = nullptr; st.d_list_fast = nullptr; st.d_list_wide = nullptr; st.d_list_gen = nullptr; st.d_list_ovf = nullptr; st.d_list_wfa = nullptr; st.d_list_big = nullptr;
     st.cap = 0;
     CU_TRY(cudaMalloc(&st.d_desc, (size_t)want * sizeof(SwDesc)));
     CU_TRY(cudaMalloc(&st.d_out, (size_t)want * sizeof(SwOut)));
@@ -821,6 +821,7 @@ int sw_stage_reserve(SwStage &st, uint32_t pairs) {
     CU_TRY(cudaMalloc(&st.d_list_gen, (size_t)want * sizeof(uint32_t)));
     CU_TRY(cudaMalloc(&st.d_list_ovf, (size_t)want * sizeof(uint32_t)));
     CU_TRY(cudaMalloc(&st.d_list_wfa, (size_t)want * sizeof(uint32_t)));
+    CU_TRY(cudaMalloc(&st.d_list_big, (size_t)want * sizeof(uint32_t)));
     if (!st.d_ctr) {
         CU_TRY(cudaMalloc(&st.d_ctr, sizeof(SwCounters)));
         CU_TRY(cudaMallocHost(&st.h_ctr, sizeof(SwCounters)));
@@ -839,7 +840,7 @@ int sw_stage_reserve(SwStage &st, uint32_t pairs) {
 
 void sw_stage_free(SwStage &st) {
     cudaFree(st.d_desc); cudaFree(st.d_out); cudaFree(st.d_list_fast); cudaFree(st.d_list_wide); cudaFree(st.d_list_gen); cudaFree(st.d_list_ovf);
-    cudaFree(st.d_list_wfa);
+    cudaFree(st.d_list_wfa); cudaFree(st.d_list_big); cudaFree(st.d_gw_scratch);
     cudaFree(st.d_ctr); if (st.h_ctr) cudaFreeHost(st.h_ctr);
     if (st.ev_k0) cudaEventDestroy(st.ev_k0);
     if (st.ev_k1) cudaEventDestroy(st.ev_k1);
@@ -935,6 +936,14 @@ int sw_stage_enqueue(SwStage &st, const DevReads &R, const uint8_t *d_rbase, con
     K_CHECK(stream, "sw_fast_kernel (narrow)");
     st.launches += 1;
     CU_TRY(cudaEventRecord(st.ev_k1, stream));
+    // pairs with 'N' / IUPAC / other bytes, or beyond the fast tiers: one warp per pair, doubles; always launched (its
+    // blocks leave at once when the list is empty)
+    SwGwPlan gw;
+    BWT_TRY(sw_general_warp_plan(max_lq, st.cfg_sms, &gw));
+    BWT_TRY(grow(st.d_gw_scratch, st.gw_scratch_words, (size_t)gw.scratch_words));
+    BWT_TRY(launch_sw_general_warp(gw, R, d_rbase, st.d_desc, st.d_list_gen, 0, &st.d_ctr->gen_cursor, st.d_list_big, st.d_gw_scratch,
+                                   st.d_out, st.d_ctr, st.d_cig_tmp, st.cig_cap, stream));
+    st.launches += 1;
     return BWT_OK;
 }
 
@@ -951,6 +960,7 @@ int sw_stage_finish(SwStage &st, const DevReads &R, const uint8_t *d_rbase, cons
     auto grid_for = [&](uint32_t pairs, unsigned cap_grid) {
         return (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((((uint64_t)pairs + 1) / 2 + SW_BLOCK - 1) / SW_BLOCK, cap_grid));
     };
+    const uint32_t done_general = st.h_ctr->n_general;      // what the always-launched general kernel saw
     auto refresh = [&]() -> int {
         CU_TRY(cudaMemcpyAsync(st.h_ctr, st.d_ctr, sizeof(SwCounters), cudaMemcpyDeviceToHost, stream));
         CU_TRY(cudaStreamSynchronize(stream));
@@ -973,9 +983,20 @@ int sw_stage_finish(SwStage &st, const DevReads &R, const uint8_t *d_rbase, cons
         *redo_emit = true;
         BWT_TRY(refresh());
     }
-    const uint32_t ng = st.h_ctr->n_general;
+    if (!st.h_ctr->cig_overflow && st.h_ctr->n_general > done_general) {
+        // pairs the wide / absolute-row kernels handed on after the general kernel had run
+        SwGwPlan gw;
+        BWT_TRY(sw_general_warp_plan(max_lq, st.cfg_sms, &gw));
+        CU_TRY(cudaMemsetAsync(&st.d_ctr->gen_cursor, 0, sizeof(uint32_t), stream));
+        BWT_TRY(launch_sw_general_warp(gw, R, d_rbase, st.d_desc, st.d_list_gen, done_general, &st.d_ctr->gen_cursor, st.d_list_big,
+                                       st.d_gw_scratch, st.d_out, st.d_ctr, st.d_cig_tmp, st.cig_cap, stream));
+        st.launches += 1;
+        *redo_emit = true;
+        BWT_TRY(refresh());
+    }
+    const uint32_t ng = st.h_ctr->n_big;
     if (ng > 0 && !st.h_ctr->cig_overflow) {
-        // size the per-pair scratch of the general kernel on the host
+        // pairs too large for the warp kernel's slots: one thread per pair, scratch sized on the host
         if (ng + 1 > st.gen_off_cap) {
             if (st.d_gen_off) cudaFree(st.d_gen_off);
             if (st.d_gen_dims) cudaFree(st.d_gen_dims);
@@ -985,7 +1006,7 @@ int sw_stage_finish(SwStage &st, const DevReads &R, const uint8_t *d_rbase, cons
             CU_TRY(cudaMalloc(&st.d_gen_dims, cap_items * sizeof(int2)));
             st.gen_off_cap = cap_items;
         }
-        sw_dims_kernel<<<(ng + 255) / 256, 256, 0, stream>>>(st.d_desc, st.d_list_gen, ng, st.d_gen_dims);
+        sw_dims_kernel<<<(ng + 255) / 256, 256, 0, stream>>>(st.d_desc, st.d_list_big, ng, st.d_gen_dims);
         st.launches += 1;
         std::vector<int2> dims(ng);
         CU_TRY(cudaMemcpyAsync(dims.data(), st.d_gen_dims, ng * sizeof(int2), cudaMemcpyDeviceToHost, stream));
@@ -1003,7 +1024,7 @@ int sw_stage_finish(SwStage &st, const DevReads &R, const uint8_t *d_rbase, cons
             uint64_t need = off[last] - off[first];
             BWT_TRY(grow(st.d_gen_scratch, st.gen_scratch_bytes, (size_t)need));
             uint32_t cnt = last - first;
-            sw_general_kernel<<<(cnt + 63) / 64, 64, 0, stream>>>(R, d_rbase, st.d_desc, st.d_list_gen, first, cnt,
+            sw_general_kernel<<<(cnt + 63) / 64, 64, 0, stream>>>(R, d_rbase, st.d_desc, st.d_list_big, first, cnt,
                                                                  st.d_gen_off, st.d_gen_scratch, st.d_out, st.d_ctr,
                                                                  st.d_cig_tmp, st.cig_cap);
             st.launches += 1;

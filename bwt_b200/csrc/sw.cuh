@@ -22,6 +22,7 @@ struct SwCounters {
     unsigned long long shortcut_calls, shortcut_cells;   // pairs settled by sw_classify_kernel without the DP (included above)
     uint32_t n_fast, n_wide, n_general, n_ovf;   // list cursors
     uint32_t n_wfa, pad2;                        // pairs the quick test left to the wavefront rule
+    uint32_t n_big, gen_cursor;                  // general pairs too large for the warp kernel's slots; its work cursor
     uint32_t cig_used, cig_overflow; // temporary CIGAR arena
     uint32_t general_done, pad;
 };
@@ -44,6 +45,9 @@ struct SwStage {
     uint32_t cig_cap = 0;
     uint2 *d_dirs = nullptr;          // direction scratch: one uint2 per (strip, column, thread)
     size_t dirs_words = 0;
+    uint32_t *d_list_big = nullptr;
+    uint32_t *d_gw_scratch = nullptr; // slots of the warp-per-pair general kernel
+    size_t gw_scratch_words = 0;
     uint8_t *d_gen_scratch = nullptr;
     size_t gen_scratch_bytes = 0;
     uint64_t *d_gen_off = nullptr;
@@ -55,6 +59,13 @@ struct SwStage {
     cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr;   // around sw_fast_kernel
     float ms_fast_kernel = 0;
 };
+
+// warp-per-pair general kernel (swg.cu)
+struct SwGwPlan { int wc_cap; uint64_t slot_words, scratch_words; size_t smem; int blocks; };
+int sw_general_warp_plan(int max_lq, int sms, SwGwPlan *pl);
+int launch_sw_general_warp(const SwGwPlan &pl, const DevReads &R, const uint8_t *d_rbase, const SwDesc *d_desc, const uint32_t *d_list,
+                           uint32_t first, uint32_t *d_cursor, uint32_t *d_list_big, uint32_t *d_scratch, SwOut *d_out, SwCounters *d_ctr,
+                           char *d_cig, uint32_t cig_cap, cudaStream_t stream);
 
 int sw_stage_reserve(SwStage &st, uint32_t pairs);
 void sw_stage_free(SwStage &st);

@@ -109,6 +109,11 @@ SIGNATURES = {
     "bwt_aligner_run": (C.c_int, [P, P, P, C.c_int64, P, P, P, C.c_int64, C.POINTER(C.c_int64), P, C.c_int64,
                                   C.POINTER(C.c_int64)]),
     "bwt_aligner_stats": (C.c_int, [P, C.POINTER(BwtStats)]),
+    "bwt_comm_unique_id": (C.c_int, [P]),
+    "bwt_comm_create": (C.c_int, [P, C.c_int, C.c_int, C.c_int, C.POINTER(P)]),
+    "bwt_comm_destroy": (C.c_int, [P]),
+    "bwt_partition_gather": (C.c_int, [P, P, C.c_int, P, P, P, C.c_int64, P, C.c_int64, P, P, C.POINTER(C.c_float),
+                                       C.POINTER(C.c_int64)]),
     "bwt_aligner_destroy": (C.c_int, [P]),
     "bwt_fs_find_seeds_batch": (C.c_int, [P, P, P, C.c_int64, C.c_int32, C.c_int32, C.c_int32, P, P, P, C.c_int64,
                                           C.POINTER(C.c_int64), C.POINTER(BwtFsStats)]),

@@ -426,6 +426,62 @@ class Batch:
         return a.value, b.value, c.value
 
 
+class Comm:
+    """NCCL communicator of the genome-partition mode (``bwt_comm``): the gather of the per-partition records straight out
+    of the batches' device-resident results.  ``unique_id()`` on one rank, handed to the others by the host program."""
+
+    @staticmethod
+    def unique_id() -> bytes:
+        buf = (C.c_uint8 * 128)()
+        check(lib().bwt_comm_unique_id(buf))
+        return bytes(buf)
+
+    def __init__(self, uid: Optional[bytes], world: int, rank: int, device: int = 0):
+        self.world, self.rank = int(world), int(rank)
+        self._c = C.c_void_p()
+        idbuf = (C.c_uint8 * 128).from_buffer_copy(uid) if uid is not None else None
+        check(lib().bwt_comm_create(idbuf, self.world, self.rank, int(device), C.byref(self._c)))
+
+    def close(self):
+        if self._c:
+            lib().bwt_comm_destroy(self._c)
+            self._c = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def gather(self, batch: "Batch", root: int = 0, out=None):
+        """Collective over the ranks' batches (run with ``run_compact`` on the same reads).  ``out`` = (status uint8[world*n],
+        offsets uint32[world*(n+1)], hits HIT16[cap], cigars uint8[cap]) on the root (allocated when None; grown on NoSpace).
+        -> (parts, ms, link_bytes): parts[p] = (status, offsets, hits, cigars) views of rank p's block on the root, None elsewhere."""
+        n, W = batch._n, self.world
+        ph = np.zeros(W, np.int64)
+        pc = np.zeros(W, np.int64)
+        ms = C.c_float()
+        lb = C.c_int64()
+        is_root = self.rank == root
+        if is_root and out is None:
+            nh, nc = batch.result_size()
+            out = (np.zeros(W * n, np.uint8), np.zeros(W * (n + 1), np.uint32), np.zeros(max(16, 2 * W * nh), HIT16_DTYPE),
+                   np.zeros(max(256, 2 * W * nc), np.uint8))
+        st, ho, hits, cig = out if is_root else (None, None, None, None)
+        rc = lib().bwt_partition_gather(self._c, batch._b, int(root), _ptr(st), _ptr(ho), _ptr(hits), len(hits) if is_root else 0,
+                                        _ptr(cig), len(cig) if is_root else 0, ph.ctypes.data, pc.ctypes.data, C.byref(ms), C.byref(lb))
+        if rc == -6:
+            raise NoSpace(lib().bwt_last_error().decode(), (int(ph.sum()), int(pc.sum())))
+        check(rc)
+        if not is_root:
+            return None, float(ms.value), int(lb.value)
+        parts, hb, cb = [], 0, 0
+        for p in range(W):
+            parts.append((st[p * n:(p + 1) * n], ho[p * (n + 1):(p + 1) * (n + 1)], hits[hb:hb + ph[p]], cig[cb:cb + pc[p]]))
+            hb += int(ph[p]); cb += int(pc[p])
+        return parts, float(ms.value), int(lb.value)
+
+
 class Aligner:
     """Pipelined ``bwt_align_batch``: persistent chunk buffers, copies overlapped with kernels (``bwt_aligner``)."""
 
@@ -564,5 +620,5 @@ def peak_dpx_gops(device: int = 0) -> float:
     return float(g.value)
 
 
-__all__ = ["Index", "Batch", "Aligner", "PackedReads", "expand_compact", "sample_reads", "sample_reads_edits", "HIT16_DTYPE", "BwtError", "NoSpace", "pack", "sw_batch", "search_resident", "peak_gather_gbs",
+__all__ = ["Index", "Batch", "Aligner", "Comm", "PackedReads", "expand_compact", "sample_reads", "sample_reads_edits", "HIT16_DTYPE", "BwtError", "NoSpace", "pack", "sw_batch", "search_resident", "peak_gather_gbs",
            "peak_dpx_gops", "device_count", "HIT_DTYPE"]

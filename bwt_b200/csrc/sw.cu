@@ -213,15 +213,6 @@ __device__ __forceinline__ int sw_shortcut(const uint32_t *__restrict__ pkr, int
 //     gap alone leaves the window, column 0 costs 4 -- so p* = 3 on that diagonal:  {2*Lq - 3, "<Lq>M"}.
 // Everything else with a chance (more mismatches, Dd > 0 without a perfect diagonal) goes to the wavefront search.
 // ---------------------------------------------------------------------------------------------------
-// mismatch flags of query word w (forward, from the packed read) against the window on diagonal o
-__device__ __forceinline__ uint32_t quick_diff(const uint32_t *__restrict__ pkr, int lq, const uint32_t *__restrict__ ref2, int64_t r_off,
-                                               int o, int w) {
-    const uint32_t x = read_fwd_word(pkr, lq, w) ^ ref_word(ref2, r_off + o + 16 * w);
-    uint32_t f = (x | (x >> 1)) & 0x55555555u;
-    if (lq - 16 * w < 16) f &= (1u << (2 * (lq - 16 * w))) - 1u;     // bases past the query's end are padding
-    return f;
-}
-
 // lists: one atomic per warp and list, the lanes of a kind take consecutive slots
 __device__ __forceinline__ void sw_route(int kind, uint32_t k, unsigned lane, SwCounters *ctr, uint32_t *__restrict__ list_fast,
                                          uint32_t *__restrict__ list_wide, uint32_t *__restrict__ list_gen, uint32_t *__restrict__ list_wfa) {
@@ -289,18 +280,25 @@ __device__ __forceinline__ int sw_dp_kind(const SwDesc &d, int cap_narrow, int c
     return 2;
 }
 
-// use_shortcut: bit 0 = quick test, bit 1 = wavefront rule
+// use_shortcut: bit 0 = quick test, bit 1 = wavefront rule.
+// Lane L of a warp keeps the books of pair k0 + L; the quick test itself runs EIGHT lanes per pair (lane t compares
+// words t and t+8 of the query with the window: coalesced loads, no dependent chain per thread): in round i the warp's
+// four groups take the pairs of lanes 4i..4i+3, whose descriptors they fetch by shuffle, and hand the verdict back.
 __global__ void __launch_bounds__(256) sw_classify_kernel(DevReads R, const uint32_t *__restrict__ ref2, const uint32_t *__restrict__ refx,
                                    const SwDesc *__restrict__ desc, SwOut *__restrict__ out, const uint32_t *__restrict__ n_ptr,
                                    int cap_narrow, int cap_wide, uint32_t *__restrict__ list_fast,
                                    uint32_t *__restrict__ list_wide, uint32_t *__restrict__ list_gen, uint32_t *__restrict__ list_wfa,
                                    SwCounters *ctr, char *__restrict__ cig, uint32_t cig_cap, int use_shortcut) {
+    const unsigned FULL = 0xFFFFFFFFu;
     const unsigned lane = threadIdx.x & 31;
+    const int t = (int)(lane & 7u), g = (int)(lane >> 3);
     const uint32_t n = *n_ptr;
     for (uint32_t k0 = blockIdx.x * blockDim.x; k0 < n; k0 += gridDim.x * blockDim.x) {
         const uint32_t k = k0 + threadIdx.x;
         int score = 0, kind = -1;             // kind: 0 narrow, 1 wide, 2 general, 3 settled, 4 wavefront list, -1 nothing to do
         SwDesc d{};
+        bool elig = false;
+        unsigned long long pk_addr = 0;
         if (k < n && out[k].status != BWT_HIT_WINDOW_OOR) {
             d = desc[k];
             if (d.lq <= 0 || d.lr <= 0) {               // sw(_,_) -> no_match for empty strings (sw.erl:54)
@@ -310,27 +308,47 @@ __global__ void __launch_bounds__(256) sw_classify_kernel(DevReads R, const uint
                 kind = 2;                               // 'N' / IUPAC / other bytes on either side: doubles (bwt.hrl:15)
             } else {
                 const int dd = d.lr - d.lq;
-                const bool elig = dd >= 0 && dd <= SW_SHORTCUT_MAX_D && d.lq >= 4 && d.lq <= SC_MAXQ;
-                if (elig && (use_shortcut & 1)) {
-                    const uint32_t *pkr = R.pk + __ldg(R.woff + d.read);
-                    const int nw = (d.lq + 15) >> 4;
-                    if (dd == 0) {
-                        int mism = 0;
-                        for (int w = 0; w < nw && mism <= 1; w++) mism += __popc(quick_diff(pkr, d.lq, ref2, d.r_off, 0, w));
-                        if (mism <= 1) score = 2 * d.lq - 3 * mism;
-                    } else {
-                        for (int o = 0; o <= dd && !score; o++) {
-                            int w = 0;
-                            while (w < nw && quick_diff(pkr, d.lq, ref2, d.r_off, o, w) == 0u) w++;
-                            if (w == nw) score = 2 * d.lq;
-                        }
-                    }
-                }
-                if (score) kind = 3;
-                else if (elig && (use_shortcut & 2)) kind = 4;
-                else kind = sw_dp_kind(d, cap_narrow, cap_wide);
+                elig = dd >= 0 && dd <= SW_SHORTCUT_MAX_D && d.lq >= 4 && d.lq <= SC_MAXQ;
+                kind = elig && (use_shortcut & 2) ? 4 : sw_dp_kind(d, cap_narrow, cap_wide);
+                if (elig) pk_addr = (unsigned long long)(R.pk + __ldg(R.woff + d.read));
             }
         }
+        const bool quick = elig && (use_shortcut & 1);
+        if (__any_sync(FULL, quick)) {
+#pragma unroll 2
+            for (int i = 0; i < 8; i++) {
+                const int src = 4 * i + g;
+                const bool qk = __shfl_sync(FULL, (int)quick, src) != 0;
+                if (!__any_sync(FULL, qk)) continue;
+                const uint32_t *pkr = reinterpret_cast<const uint32_t *>(__shfl_sync(FULL, pk_addr, src));
+                const long long ro = __shfl_sync(FULL, (long long)d.r_off, src);
+                const int lq = __shfl_sync(FULL, d.lq, src), dd = __shfl_sync(FULL, d.lr, src) - lq;
+                const int nw = (lq + 15) >> 4;
+                const bool h0 = qk && t < nw, h1 = qk && t + 8 < nw;        // this lane's words: t and t + 8
+                const uint32_t q0 = h0 ? read_fwd_word(pkr, lq, t) : 0u, q1 = h1 ? read_fwd_word(pkr, lq, t + 8) : 0u;
+                const uint32_t m0 = h0 ? (lq - 16 * t < 16 ? (1u << (2 * (lq - 16 * t))) - 1u : 0xFFFFFFFFu) & 0x55555555u : 0u;
+                const uint32_t m1 = h1 ? (lq - 16 * (t + 8) < 16 ? (1u << (2 * (lq - 16 * (t + 8)))) - 1u : 0xFFFFFFFFu) & 0x55555555u : 0u;
+                int sc = 0;
+                const int omax = __reduce_max_sync(FULL, qk ? dd : 0);
+                for (int o = 0; o <= omax; o++) {                       // diagonals of the window, leftmost first
+                    const bool live = qk && o <= dd && sc == 0;
+                    uint32_t f0 = 0u, f1 = 0u;
+                    if (live && h0) { const uint32_t x = q0 ^ ref_word(ref2, ro + o + 16 * t); f0 = (x | (x >> 1)) & m0; }
+                    if (live && h1) { const uint32_t x = q1 ^ ref_word(ref2, ro + o + 16 * (t + 8)); f1 = (x | (x >> 1)) & m1; }
+                    int mism = __popc(f0) + __popc(f1);
+                    mism += __shfl_xor_sync(FULL, mism, 1);
+                    mism += __shfl_xor_sync(FULL, mism, 2);
+                    mism += __shfl_xor_sync(FULL, mism, 4);
+                    if (live) {
+                        if (mism == 0) sc = 2 * lq;                     // the leftmost perfect diagonal
+                        else if (dd == 0 && mism == 1) sc = 2 * lq - 3; // one mismatch, no room for a gap
+                    }
+                }
+                const int got = __shfl_sync(FULL, sc, 8 * (int)(lane & 3u));
+                if ((int)(lane >> 2) == i) score = got;
+            }
+        }
+        if (score) kind = 3;
         sw_route(kind, k, lane, ctr, list_fast, list_wide, list_gen, list_wfa);
         sw_settle(kind, k, d.lq, d.lr, score, lane, out, ctr, cig, cig_cap);
     }

@@ -265,6 +265,27 @@ int bwt_aligner_run_packed(bwt_aligner *a, const bwt_packed_reads *p, uint8_t *r
 int bwt_aligner_stats(bwt_aligner *a, bwt_stats *out);   /* sums over the chunks of the last run */
 int bwt_aligner_destroy(bwt_aligner *a);
 
+/* ---- genome-partition mode: the gather of the per-partition records (BASELINE.json configs[4]) ---------------------- */
+
+/* One _pJ partition per GPU (fm_index.erl:113-124 writes them; worker_bwt.erl:48,53 loads one), every GPU aligns ALL reads
+ * against its partition, and the records of every partition go to the root over NCCL (NVLink / NVSwitch) straight out of
+ * the batches' device-resident compact results.  The reference defines no reduction across partitions (master.erl:151-155
+ * prints every cigar it receives): the root gets the partitions' records side by side, in rank order.
+ * NCCL is bound at run time (libnccl.so.2); with world = 1 it is never touched.  The 128-byte id is made on one rank
+ * (bwt_comm_unique_id) and handed to the others by the host program (the Erlang host's distribution, MPI, a file...). */
+typedef struct bwt_comm bwt_comm;
+int bwt_comm_unique_id(uint8_t id[128]);
+int bwt_comm_create(const uint8_t id[128], int world, int rank, int device, bwt_comm **out);
+int bwt_comm_destroy(bwt_comm *c);
+/* Collective: every rank passes the batch it ran with bwt_batch_run_compact on the SAME n reads.  On the root, rank p's
+ * block lands at status_out[p*n], hit_off_out[p*(n+1)] (rank p's own offsets, from 0), and its hits / CIGAR bytes at the
+ * running sums of part_hits / part_cig, which come back on every rank (world entries each).  ms_gather: CUDA-event time
+ * of the exchange (sizes all-gather + sends / receives); link_bytes: bytes received by the root over the links.
+ * BWT_ERR_NOSPACE on the root when a capacity is too small (the sizes are in part_hits / part_cig). */
+int bwt_partition_gather(bwt_comm *c, bwt_batch *b, int root, uint8_t *status_out, uint32_t *hit_off_out, bwt_hit16 *hits_out,
+                         int64_t hits_cap, char *cig_out, int64_t cig_cap, int64_t *part_hits, int64_t *part_cig,
+                         float *ms_gather, int64_t *link_bytes);
+
 /* ---- bounded-edit search: seeds:generate_fs/3 + the fs:find_seeds/1 it generates (seeds.erl:11-62) -------------- */
 
 typedef struct bwt_fs_stats {

@@ -186,3 +186,24 @@ def test_indel_reads_sampler_and_depth_invariance(gl_index, gl_ref):
         assert (r1[1] == r2[1]).all() and (r1[0] == r2[0]).all()
         with api.Index.build_synthetic_part(1000, 50_000, seed=5, shift=1001) as px:
             assert (px.export()[2] == sx.export()[2][1000:51000]).all() and px.info().shift == 1001
+
+
+def test_partition_gather_single_rank(gl_index, gl_ref):
+    """bwt_partition_gather with one rank (no NCCL): the root's block is the batch's own compact result."""
+    reads, offs, _ = sample_reads(gl_ref, 1500, 100, seed=13, edit_rate=0.01)
+    b = api.Batch(gl_index, 1500, len(reads))
+    comm = api.Comm(None, 1, 0)
+    try:
+        b.upload(reads, offs)
+        b.run_compact()
+        want = b.download_compact()
+        parts, ms, link = comm.gather(b, 0)
+        assert len(parts) == 1 and link == 0 and ms >= 0
+        got = parts[0]
+        assert (got[0] == want[0]).all() and (got[1] == want[1]).all() and (got[2] == want[2]).all() and (got[3] == want[3]).all()
+        with pytest.raises(api.NoSpace) as e:
+            comm.gather(b, 0, (np.zeros(1500, np.uint8), np.zeros(1501, np.uint32), np.zeros(4, api.HIT16_DTYPE), np.zeros(1 << 16, np.uint8)))
+        assert e.value.needed[0] == len(want[2])
+    finally:
+        comm.close()
+        b.close()

@@ -36,7 +36,7 @@ class BwtHit16(C.Structure):
 class BwtPackedReads(C.Structure):
     _fields_ = [("n", C.c_int64), ("fixed_len", C.c_int32), ("reserved", C.c_int32), ("lens", C.c_void_p), ("words", C.c_void_p),
                 ("n_words", C.c_int64), ("n_exc", C.c_int64), ("exc_idx", C.c_void_p), ("exc_off", C.c_void_p),
-                ("exc_ascii", C.c_void_p)]
+                ("exc_ascii", C.c_void_p), ("word_index", C.c_void_p), ("maxlen_index", C.c_void_p)]
 
 
 class BwtIndexInfo(C.Structure):
@@ -75,12 +75,14 @@ SIGNATURES = {
     "bwt_open": (C.c_int, [C.c_char_p, C.c_char_p, C.c_int, C.POINTER(P)]),
     "bwt_open_arrays": (C.c_int, [P, C.c_uint64, P, P, C.c_int64, P, C.c_uint64, C.c_int, C.POINTER(P)]),
     "bwt_build": (C.c_int, [P, C.c_uint64, C.c_int64, C.c_int, C.POINTER(P)]),
+    "bwt_build_n": (C.c_int, [P, C.c_uint64, C.c_int64, C.c_int, P, C.POINTER(P)]),
     "bwt_build_synthetic": (C.c_int, [C.c_uint64, C.c_uint64, C.c_int64, C.c_int, C.POINTER(P)]),
     "bwt_build_synthetic_part": (C.c_int, [C.c_uint64, C.c_uint64, C.c_uint64, C.c_int64, C.c_int, C.POINTER(P)]),
     "bwt_sample_reads_edits": (C.c_int, [P, C.POINTER(BwtSampleOpts), P, C.c_int64, P, P, C.POINTER(C.c_int64)]),
     "bwt_save": (C.c_int, [P, C.c_char_p, C.c_char_p]),
     "bwt_export": (C.c_int, [P, P, P, P]),
     "bwt_info": (C.c_int, [P, C.POINTER(BwtIndexInfo)]),
+    "bwt_fm_inspect": (C.c_int, [C.c_char_p, C.POINTER(C.c_uint64), P, C.POINTER(C.c_int64)]),
     "bwt_set_kmer_depth": (C.c_int, [P, C.c_int]),
     "bwt_close": (C.c_int, [P]),
     "bwt_search_batch": (C.c_int, [P, P, P, C.c_int64, P, P, P, P]),
@@ -99,6 +101,7 @@ SIGNATURES = {
     "bwt_pack_words": (C.c_int64, [P, C.c_int64]),
     "bwt_pack_reads": (C.c_int, [P, P, C.c_int64, C.c_int, P, C.c_int64, P, P, C.c_int64, P, P, C.c_int64,
                                  C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "bwt_pack_index": (C.c_int, [P, C.c_int64, P, P]),
     "bwt_batch_upload_packed": (C.c_int, [P, C.POINTER(BwtPackedReads)]),
     "bwt_batch_run_compact": (C.c_int, [P]),
     "bwt_batch_download_compact": (C.c_int, [P, P, P, P, C.c_int64, P, C.c_int64]),

@@ -20,6 +20,8 @@ HIT16_DTYPE = np.dtype([("s", "<u4"), ("d_flags", "<u4"), ("cigar_off", "<u4"), 
 assert HIT16_DTYPE.itemsize == C.sizeof(BwtHit16) == 16
 HIT16_FULL_M = 0x40000000
 
+AS183_SEED0 = (3172, 9814, 20125)      # random:seed0/0 of OTP's stdlib: the state of a process that never seeded
+
 SEEDS, NO_SEEDS, TOO_MANY_SEEDS, SEARCH_CRASH = 0, 1, 2, 3
 READ_OK, READ_CRASH, READ_LIMIT = 0, 1, 2
 HIT_MATCH, HIT_NO_MATCH, HIT_WINDOW_OOR = 0, 1, 2
@@ -49,6 +51,14 @@ def device_count() -> int:
     return lib().bwt_device_count()
 
 
+def fm_inspect(fm_path: str):
+    """(n_rows, (Pc,Pg,Pt,Last), shift) of a <Chrom>_pJ.fm, read on the host (no GPU)"""
+    n, sh = C.c_uint64(), C.c_int64()
+    ptr = (C.c_uint32 * 4)()
+    check(lib().bwt_fm_inspect(fm_path.encode(), C.byref(n), ptr, C.byref(sh)))
+    return int(n.value), tuple(int(x) for x in ptr), int(sh.value)
+
+
 class Index:
     """One FM-index partition + its padded .ref resident in HBM (opaque ``bwt_index``)."""
 
@@ -74,10 +84,17 @@ class Index:
         return cls(h.value)
 
     @classmethod
-    def build(cls, chunk, shift: int = 1, device: int = 0) -> "Index":
+    def build(cls, chunk, shift: int = 1, device: int = 0, n_state: Optional[np.ndarray] = None) -> "Index":
+        """fm_index:make_index/4 on the device.  n_state: uint32[3] AS183 state (``AS183_SEED0`` for a fresh Erlang process),
+        updated in place: every 'N' of the chunk is replaced in the indexed text by random:uniform(4)'s pick
+        (fm_index.erl:131); None: a chunk with 'N' is rejected."""
         chunk = _u8(chunk)
         h = C.c_void_p()
-        check(lib().bwt_build(chunk.ctypes.data, len(chunk), int(shift), device, C.byref(h)))
+        if n_state is not None:
+            assert n_state.dtype == np.uint32 and len(n_state) == 3
+            check(lib().bwt_build_n(chunk.ctypes.data, len(chunk), int(shift), device, n_state.ctypes.data, C.byref(h)))
+        else:
+            check(lib().bwt_build(chunk.ctypes.data, len(chunk), int(shift), device, C.byref(h)))
         return cls(h.value)
 
     @classmethod
@@ -301,8 +318,13 @@ class PackedReads:
         self.fixed_len = int(fixed_len)
         if self.fixed_len:
             assert n == 0 or (self.lens[:n] == self.fixed_len).all(), "fixed_len given for a ragged batch"
+        nblk = n // 65536 + 2
+        self.word_index = np.zeros(nblk, np.int64)
+        self.maxlen_index = np.zeros(nblk, np.uint16)
+        check(lib().bwt_pack_index(self.lens.ctypes.data, n, self.word_index.ctypes.data, self.maxlen_index.ctypes.data))
         self.struct = BwtPackedReads(n, self.fixed_len, 0, self.lens.ctypes.data, self.words.ctypes.data, self.n_words, self.n_exc,
-                                     _ptr(self.exc_idx), _ptr(self.exc_off), _ptr(self.exc_ascii))
+                                     _ptr(self.exc_idx), _ptr(self.exc_off), _ptr(self.exc_ascii), self.word_index.ctypes.data,
+                                     self.maxlen_index.ctypes.data)
 
     def upload_bytes(self) -> int:
         """bytes a run moves to the device for this batch"""

@@ -458,21 +458,32 @@ static int packed_check(const bwt_packed_reads *p) {
     return BWT_OK;
 }
 
-// words and longest read of reads [lo, hi) of a packed batch
-static void packed_geom(const bwt_packed_reads *p, int64_t lo, int64_t hi, int64_t *words, int *maxlen) {
-    if (p->fixed_len > 0) {
-        *words = (hi - lo) * (p->fixed_len > BWT_PACK_MAX ? 0 : (p->fixed_len + 15) >> 4);
-        *maxlen = p->fixed_len;
-        return;
-    }
-    int64_t w = 0;
-    int m = 0;
-    for (int64_t r = lo; r < hi; r++) {
+// words before read `at`, and the longest read of [lo, hi), of a packed batch: from its index where there is one
+static int64_t packed_words_before(const bwt_packed_reads *p, int64_t at) {
+    if (p->fixed_len > 0) return at * (p->fixed_len > BWT_PACK_MAX ? 0 : (p->fixed_len + 15) >> 4);
+    int64_t w = 0, from = 0;
+    if (p->word_index) { from = at / BWT_PACK_INDEX_STRIDE * BWT_PACK_INDEX_STRIDE; w = p->word_index[at / BWT_PACK_INDEX_STRIDE]; }
+    for (int64_t r = from; r < at; r++) {
         const int l = p->lens[r];
-        m = std::max(m, l);
         if (l <= BWT_PACK_MAX) w += (l + 15) >> 4;
     }
-    *words = w; *maxlen = m;
+    return w;
+}
+static int packed_maxlen(const bwt_packed_reads *p, int64_t lo, int64_t hi) {
+    if (p->fixed_len > 0) return p->fixed_len;
+    int m = 0;
+    int64_t r = lo;
+    while (r < hi) {
+        if (p->maxlen_index && r % BWT_PACK_INDEX_STRIDE == 0 && r + BWT_PACK_INDEX_STRIDE <= hi) {
+            m = std::max<int>(m, p->maxlen_index[r / BWT_PACK_INDEX_STRIDE]);
+            r += BWT_PACK_INDEX_STRIDE;
+        } else { m = std::max<int>(m, p->lens[r]); r++; }
+    }
+    return m;
+}
+static void packed_geom(const bwt_packed_reads *p, int64_t lo, int64_t hi, int64_t *words, int *maxlen) {
+    *words = packed_words_before(p, hi) - packed_words_before(p, lo);
+    *maxlen = packed_maxlen(p, lo, hi);
 }
 
 extern "C" int bwt_batch_upload_packed(bwt_batch *b, const bwt_packed_reads *p) {

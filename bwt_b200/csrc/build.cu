@@ -10,6 +10,9 @@
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
+#include <string.h>
+#include <vector>
+
 #include "common.cuh"
 
 namespace {
@@ -372,20 +375,25 @@ int build_sa_device(const uint8_t *d_text, uint64_t len, uint32_t **d_sa_out, ui
     return BWT_OK;
 }
 
-static int build_from_device_chunk(uint8_t *d_chunk, uint64_t len, int64_t shift, int device, bool already_acgt,
+// d_chunk: the .ref bytes on the device (kept as the window source); the text is the ACGT mapping of d_text_src
+// (null: of d_chunk itself -- they differ when 'N's were substituted on the host)
+static int build_from_device_chunk(uint8_t *d_chunk, const uint8_t *d_text_src, uint64_t len, int64_t shift, int device, bool already_acgt,
                                    bwt_index **out) {
-    // d_chunk: the .ref bytes on the device (kept as the window source); text = its ACGT mapping
     uint8_t *d_text = d_chunk;
     DevBuf mapped, flags;
     if (!already_acgt) {
         BWT_TRY(mapped.alloc(len));
         BWT_TRY(flags.alloc(8));
         CU_TRY(cudaMemset(flags.p, 0, 8));
-        map_acgt_kernel<<<blocks_for(len), 256>>>(d_chunk, len, mapped.as<uint8_t>(), flags.as<uint32_t>());
+        map_acgt_kernel<<<blocks_for(len), 256>>>(d_text_src ? d_text_src : d_chunk, len, mapped.as<uint8_t>(), flags.as<uint32_t>());
         uint32_t f[2];
         CU_TRY(cudaMemcpy(f, flags.p, 8, cudaMemcpyDeviceToHost));
         if (f[1]) { bwt_set_error("builder: %u symbols outside ACGT/IUPAC (fm_index.erl:136 raises)", f[1]); return BWT_ERR_FORMAT; }
-        if (f[0]) { bwt_set_error("builder: %u 'N' in the chunk; the reference substitutes random:uniform(4), which is not reproducible", f[0]); return BWT_ERR_FORMAT; }
+        if (f[0]) {
+            bwt_set_error("builder: %u 'N' in the chunk; the reference substitutes random:uniform(4) (fm_index.erl:131): pass an AS183 "
+                          "state to bwt_build_n to reproduce it", f[0]);
+            return BWT_ERR_FORMAT;
+        }
         d_text = mapped.as<uint8_t>();
     }
     uint32_t *d_sa = nullptr;
@@ -404,13 +412,39 @@ static int build_from_device_chunk(uint8_t *d_chunk, uint64_t len, int64_t shift
     return BWT_OK;
 }
 
-extern "C" int bwt_build(const uint8_t *chunk, uint64_t len, int64_t shift, int device, bwt_index **out) {
+// random:uniform(4) of OTP's `random` module (AS183, Wichmann-Hill): the generator fm_index.erl:131 draws an 'N''s
+// replacement from.  state = {A1,A2,A3}; the default seed of a fresh process is {3172, 9814, 20125}.  (From the OTP
+// stdlib, which is not in the reference tree: parity of this substitution is unpinned there; the first draw of the
+// default seed, 0.4435846174457203, is the value every Erlang shell prints.)
+static int as183_uniform4(uint32_t st[3]) {
+    st[0] = (st[0] * 171u) % 30269u;
+    st[1] = (st[1] * 172u) % 30307u;
+    st[2] = (st[2] * 170u) % 30323u;
+    double r = (double)st[0] / 30269.0 + (double)st[1] / 30307.0 + (double)st[2] / 30323.0;
+    r -= (double)(long long)r;
+    return (int)(r * 4.0) + 1;
+}
+
+extern "C" int bwt_build_n(const uint8_t *chunk, uint64_t len, int64_t shift, int device, uint32_t as183_state[3], bwt_index **out) {
     if (!chunk || !out) { bwt_set_error("bwt_build: null argument"); return BWT_ERR_ARG; }
     BWT_TRY(index_select_device(device));
-    DevBuf d;
+    DevBuf d, dt;
     BWT_TRY(d.alloc(len));
     CU_TRY(cudaMemcpy(d.p, chunk, len, cudaMemcpyHostToDevice));
-    return build_from_device_chunk(d.as<uint8_t>(), len, shift, device, false, out);
+    if (as183_state && memchr(chunk, 'N', len)) {
+        // element(random:uniform(4), {$A,$C,$G,$T}) per 'N', in text order (lists:map/2 walks the list from its head)
+        std::vector<uint8_t> text(chunk, chunk + len);
+        for (uint64_t k = 0; k < len; k++)
+            if (text[k] == 'N') text[k] = (uint8_t)"ACGT"[as183_uniform4(as183_state) - 1];
+        BWT_TRY(dt.alloc(len));
+        CU_TRY(cudaMemcpy(dt.p, text.data(), len, cudaMemcpyHostToDevice));
+        return build_from_device_chunk(d.as<uint8_t>(), dt.as<uint8_t>(), len, shift, device, false, out);
+    }
+    return build_from_device_chunk(d.as<uint8_t>(), nullptr, len, shift, device, false, out);
+}
+
+extern "C" int bwt_build(const uint8_t *chunk, uint64_t len, int64_t shift, int device, bwt_index **out) {
+    return bwt_build_n(chunk, len, shift, device, nullptr, out);
 }
 
 extern "C" int bwt_build_synthetic(uint64_t len, uint64_t seed, int64_t shift, int device, bwt_index **out) {
@@ -420,7 +454,7 @@ extern "C" int bwt_build_synthetic(uint64_t len, uint64_t seed, int64_t shift, i
     BWT_TRY(d.alloc(len));
     synth_kernel<<<blocks_for(len), 256>>>(d.as<uint8_t>(), 0, len, seed);
     CU_TRY(cudaGetLastError());
-    return build_from_device_chunk(d.as<uint8_t>(), len, shift, device, true, out);
+    return build_from_device_chunk(d.as<uint8_t>(), nullptr, len, shift, device, true, out);
 }
 
 extern "C" int bwt_build_synthetic_part(uint64_t start, uint64_t len, uint64_t seed, int64_t shift, int device, bwt_index **out) {
@@ -430,7 +464,7 @@ extern "C" int bwt_build_synthetic_part(uint64_t start, uint64_t len, uint64_t s
     BWT_TRY(d.alloc(len));
     synth_kernel<<<blocks_for(len), 256>>>(d.as<uint8_t>(), start, len, seed);
     CU_TRY(cudaGetLastError());
-    return build_from_device_chunk(d.as<uint8_t>(), len, shift, device, true, out);
+    return build_from_device_chunk(d.as<uint8_t>(), nullptr, len, shift, device, true, out);
 }
 
 extern "C" int bwt_sample_reads_edits(const bwt_index *h, const bwt_sample_opts *o, uint8_t *reads_out, int64_t reads_cap,

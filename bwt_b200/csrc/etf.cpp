@@ -9,6 +9,7 @@
 // Only L, SA, pointers and shift are kept: F and I are functions of them.
 #include "etf.hpp"
 
+#include <new>
 #include <stdio.h>
 #include <string.h>
 
@@ -49,9 +50,14 @@ struct Rd {
         ok = false;
         return false;
     }
+    // ATOM_EXT (100, what OTP 17 wrote: the shipped fixture), SMALL_ATOM_EXT (115), and the UTF-8 forms current OTP
+    // (26+) writes: ATOM_UTF8_EXT (118), SMALL_ATOM_UTF8_EXT (119)
     bool atom(const char *want) {
-        if (u8() != 100) { ok = false; return false; }
-        uint16_t k = be16();
+        const uint8_t tag = u8();
+        size_t k;
+        if (tag == 100 || tag == 118) k = be16();
+        else if (tag == 115 || tag == 119) k = u8();
+        else { ok = false; return false; }
         size_t wl = strlen(want);
         if (!ok || (size_t)(end - p) < k || k != wl || memcmp(p, want, k) != 0) { ok = false; return false; }
         p += k;
@@ -96,8 +102,16 @@ bool etf_parse_fm(const uint8_t *data, size_t size, EtfIndex &out, std::string &
     else if (tag == 104) n = r.u8();
     else { err = "FM is not a tuple"; return false; }
     if (!r.ok) { err = "truncated header"; return false; }
-    out.L.resize(n);
-    out.SA.resize(n);
+    // the smallest row is 10 bytes (104 4 + four SMALL_INTEGERs): a count beyond that is a truncated or corrupt file,
+    // not a reason to ask for gigabytes
+    if (n > (uint64_t)(r.end - r.p) / 10) { err = "row count exceeds the file size (truncated or corrupt .fm)"; return false; }
+    try {
+        out.L.resize(n);
+        out.SA.resize(n);
+    } catch (const std::bad_alloc &) {
+        err = "out of host memory for the index rows";
+        return false;
+    }
     for (uint64_t e = 0; e < n; e++) {
         int64_t F, L, I, SA;
         if (!r.small_tuple(4) || !r.integer(F) || !r.integer(L) || !r.integer(I) || !r.integer(SA)) {

@@ -8,6 +8,7 @@
 //   ref   : ref_len + 400 B     ASCII .ref padded with 200 'N' each side
 #include <stdarg.h>
 #include <algorithm>
+#include <new>
 #include <stdlib.h>
 #include <string.h>
 
@@ -127,6 +128,13 @@ __global__ void kmer_expand_kernel(DevIndex ix, uint2 *__restrict__ tab, int k) 
     tab[i] = child[0];
 }
 
+// every suffix start must lie inside the text: SA values index the reference
+__global__ void sa_check_kernel(const uint32_t *__restrict__ sa, uint64_t n, uint32_t *__restrict__ bad) {
+    uint32_t b = 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) b |= sa[i] >= n ? 1u : 0u;
+    if (__any_sync(0xFFFFFFFFu, b) && (threadIdx.x & 31) == 0) atomicExch(bad, 1u);
+}
+
 __global__ void pad_fill_kernel(uint8_t *p, uint64_t n, uint8_t v) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) p[i] = v;
@@ -192,12 +200,16 @@ int index_finish_from_device(bwt_index *h, const uint8_t *d_L, uint64_t n, uint3
     uint4 *d_occ = nullptr;
     uint32_t *d_cnt = nullptr, *d_tmp = nullptr, *d_flags = nullptr;
     uint2 *d_kmer = nullptr;   // (unused: the tables are built by bwt_set_kmer_depth)
-    CU_TRY(cudaMalloc(&d_occ, nb * 32));
-    CU_TRY(cudaMalloc(&d_cnt, nb * 4 * sizeof(uint32_t)));
-    CU_TRY(cudaMalloc(&d_tmp, scan_tmp_words(nb) * sizeof(uint32_t)));
-    CU_TRY(cudaMalloc(&d_flags, 4 * sizeof(uint32_t)));
-    uint32_t init[4] = {0xFFFFFFFFu, 0, 0, 0};   // dollar row (min), #dollars, #bad symbols
+    if (cudaMalloc(&d_occ, nb * 32) != cudaSuccess || cudaMalloc(&d_cnt, nb * 4 * sizeof(uint32_t)) != cudaSuccess ||
+        cudaMalloc(&d_tmp, scan_tmp_words(nb) * sizeof(uint32_t)) != cudaSuccess || cudaMalloc(&d_flags, 4 * sizeof(uint32_t)) != cudaSuccess) {
+        cudaGetLastError();
+        cudaFree(d_occ); cudaFree(d_cnt); cudaFree(d_tmp); cudaFree(d_flags);
+        bwt_set_error("index layout: device allocation for %llu rows failed", (unsigned long long)n);
+        return BWT_ERR_NOMEM;
+    }
+    uint32_t init[4] = {0xFFFFFFFFu, 0, 0, 0};   // dollar row (min), #dollars, #bad symbols, SA value out of range
     CU_TRY(cudaMemcpy(d_flags, init, sizeof init, cudaMemcpyHostToDevice));
+    sa_check_kernel<<<148 * 8, 256>>>(d_sa, n, d_flags + 3);
     uint32_t *cA = d_cnt, *cC = d_cnt + nb, *cG = d_cnt + 2 * nb, *cT = d_cnt + 3 * nb;
     planes_kernel<<<(unsigned)div_up_u64(nb, 256), 256>>>(d_L, n, d_occ, cA, cC, cG, cT, d_flags, d_flags + 2);
     CU_TRY(cudaGetLastError());
@@ -205,11 +217,36 @@ int index_finish_from_device(bwt_index *h, const uint8_t *d_L, uint64_t n, uint3
     counts_kernel<<<(unsigned)div_up_u64(nb, 256), 256>>>(d_occ, nb, cA, cC, cG, cT);
     CU_TRY(cudaGetLastError());
     uint32_t flags[4];
-    CU_TRY(cudaMemcpy(flags, d_flags, sizeof flags, cudaMemcpyDeviceToHost));
-    cudaFree(d_cnt); cudaFree(d_tmp); cudaFree(d_flags);
+    uint32_t tot[4] = {0, 0, 0, 0};                 // symbols of L per letter ('$' counted as A): last block's checkpoint + its own count
+    {
+        cudaError_t e = cudaMemcpy(flags, d_flags, sizeof flags, cudaMemcpyDeviceToHost);
+        uint4 last_cp;
+        if (e == cudaSuccess) e = cudaMemcpy(&last_cp, d_occ + 2 * (nb - 1), sizeof last_cp, cudaMemcpyDeviceToHost);
+        uint4 last_pl;
+        if (e == cudaSuccess) e = cudaMemcpy(&last_pl, d_occ + 2 * (nb - 1) + 1, sizeof last_pl, cudaMemcpyDeviceToHost);
+        cudaFree(d_cnt); cudaFree(d_tmp); cudaFree(d_flags);
+        if (e != cudaSuccess) { cudaFree(d_occ); bwt_set_error("index layout: %s", cudaGetErrorString(e)); return BWT_ERR_CUDA; }
+        const uint32_t cp[4] = {last_cp.x, last_cp.y, last_cp.z, last_cp.w};
+        const uint64_t rows_last = n - (nb - 1) * 64;
+        for (uint64_t k = 0; k < rows_last; k++) {
+            const uint32_t lo = ((k < 32 ? last_pl.x : last_pl.y) >> (k & 31)) & 1u, hi = ((k < 32 ? last_pl.z : last_pl.w) >> (k & 31)) & 1u;
+            tot[hi * 2 + lo]++;
+        }
+        for (int c = 0; c < 4; c++) tot[c] += cp[c];
+    }
     if (flags[2] != 0 || flags[1] != 1) {
-        cudaFree(d_occ); cudaFree(d_kmer);
+        cudaFree(d_occ);
         bwt_set_error("L column must hold exactly one '$' and otherwise only ACGT (%u '$', %u other symbols)", flags[1], flags[2]);
+        return BWT_ERR_FORMAT;
+    }
+    if (flags[3]) { cudaFree(d_occ); bwt_set_error("SA column holds a value beyond the %llu rows", (unsigned long long)n); return BWT_ERR_FORMAT; }
+    // the LF mapping adds occ counts taken from L to the pointers taken from the file: they must describe the same text
+    // (F is L sorted), or a step walks off the index
+    if ((uint64_t)pointers[0] != 2ull + (tot[0] - 1) || (uint64_t)pointers[1] != (uint64_t)pointers[0] + tot[1] ||
+        (uint64_t)pointers[2] != (uint64_t)pointers[1] + tot[2] || (uint64_t)pointers[2] + tot[3] != n + 1) {
+        cudaFree(d_occ);
+        bwt_set_error("pointers {%u,%u,%u,%u} disagree with the symbol counts of L (A %u, C %u, G %u, T %u)", pointers[0], pointers[1],
+                      pointers[2], pointers[3], tot[0] - 1, tot[1], tot[2], tot[3]);
         return BWT_ERR_FORMAT;
     }
     h->n = n;
@@ -390,8 +427,19 @@ static int read_file(const char *path, std::vector<uint8_t> &buf) {
     return BWT_OK;
 }
 
+static int bwt_open_impl(const char *fm_path, const char *ref_path, int device, bwt_index **out);
+
 extern "C" int bwt_open(const char *fm_path, const char *ref_path, int device, bwt_index **out) {
     if (!fm_path || !ref_path || !out) { bwt_set_error("bwt_open: null argument"); return BWT_ERR_ARG; }
+    try {
+        return bwt_open_impl(fm_path, ref_path, device, out);
+    } catch (const std::bad_alloc &) {         // never across the extern "C" boundary
+        bwt_set_error("bwt_open: out of host memory reading %s", fm_path);
+        return BWT_ERR_NOMEM;
+    }
+}
+
+static int bwt_open_impl(const char *fm_path, const char *ref_path, int device, bwt_index **out) {
     BWT_TRY(index_select_device(device));   // fail before any file work when there is no GPU
     std::vector<uint8_t> fm, ref;
     BWT_TRY(read_file(fm_path, fm));
@@ -400,7 +448,7 @@ extern "C" int bwt_open(const char *fm_path, const char *ref_path, int device, b
     std::string err;
     if (!etf_parse_fm(fm.data(), fm.size(), ix, err)) {
         bwt_set_error("%s: %s", fm_path, err.c_str());
-        return BWT_ERR_FORMAT;
+        return err.find("out of host memory") != std::string::npos ? BWT_ERR_NOMEM : BWT_ERR_FORMAT;
     }
     fm.clear(); fm.shrink_to_fit();
     if (ix.L.size() != ref.size() + 1) {
@@ -409,6 +457,28 @@ extern "C" int bwt_open(const char *fm_path, const char *ref_path, int device, b
         return BWT_ERR_FORMAT;
     }
     return bwt_open_arrays(ix.L.data(), ix.L.size(), ix.SA.data(), ix.pointers, ix.shift, ref.data(), ref.size(), device, out);
+}
+
+// host only: the header of a <Chrom>_pJ.fm without touching a GPU (tooling; the CPU tests of the container reader)
+extern "C" int bwt_fm_inspect(const char *fm_path, uint64_t *n_rows, uint32_t pointers[4], int64_t *shift) {
+    if (!fm_path) { bwt_set_error("bwt_fm_inspect: null argument"); return BWT_ERR_ARG; }
+    try {
+        std::vector<uint8_t> fm;
+        BWT_TRY(read_file(fm_path, fm));
+        EtfIndex ix;
+        std::string err;
+        if (!etf_parse_fm(fm.data(), fm.size(), ix, err)) {
+            bwt_set_error("%s: %s", fm_path, err.c_str());
+            return err.find("out of host memory") != std::string::npos ? BWT_ERR_NOMEM : BWT_ERR_FORMAT;
+        }
+        if (n_rows) *n_rows = ix.L.size();
+        if (pointers) memcpy(pointers, ix.pointers, sizeof ix.pointers);
+        if (shift) *shift = ix.shift;
+        return BWT_OK;
+    } catch (const std::bad_alloc &) {
+        bwt_set_error("bwt_fm_inspect: out of host memory reading %s", fm_path);
+        return BWT_ERR_NOMEM;
+    }
 }
 
 extern "C" int bwt_close(bwt_index *h) {

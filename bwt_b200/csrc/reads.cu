@@ -214,3 +214,21 @@ extern "C" int bwt_pack_reads(const uint8_t *reads, const int64_t *offsets, int6
         }
     return BWT_OK;
 }
+
+extern "C" int bwt_pack_index(const uint16_t *lens, int64_t n, int64_t *word_index, uint16_t *maxlen_index) {
+    if (!lens || n < 0 || !word_index || !maxlen_index) { bwt_set_error("bwt_pack_index: bad argument"); return BWT_ERR_ARG; }
+    int64_t w = 0;
+    word_index[0] = 0;
+    for (int64_t b = 0, k = 0; b < n; b += BWT_PACK_INDEX_STRIDE, k++) {
+        const int64_t e = std::min<int64_t>(n, b + BWT_PACK_INDEX_STRIDE);
+        uint16_t m = 0;
+        for (int64_t r = b; r < e; r++) {
+            const uint16_t l = lens[r];
+            m = std::max(m, l);
+            if (l <= BWT_PACK_MAX) w += (l + 15) >> 4;
+        }
+        maxlen_index[k] = m;
+        word_index[k + 1] = w;
+    }
+    return BWT_OK;
+}

@@ -213,64 +213,85 @@ __device__ __forceinline__ int sw_shortcut(const uint32_t *__restrict__ pkr, int
 //     gap alone leaves the window, column 0 costs 4 -- so p* = 3 on that diagonal:  {2*Lq - 3, "<Lq>M"}.
 // Everything else with a chance (more mismatches, Dd > 0 without a perfect diagonal) goes to the wavefront search.
 // ---------------------------------------------------------------------------------------------------
-// lists: one atomic per warp and list, the lanes of a kind take consecutive slots
-__device__ __forceinline__ void sw_route(int kind, uint32_t k, unsigned lane, SwCounters *ctr, uint32_t *__restrict__ list_fast,
-                                         uint32_t *__restrict__ list_wide, uint32_t *__restrict__ list_gen, uint32_t *__restrict__ list_wfa) {
-    uint32_t slot = 0;
+// Per-thread work counters of the classification kernels, flushed once per block at the end of the kernel.
+struct ScStats { unsigned long long cells = 0; uint32_t settled = 0; };
+
+// The end of a classification round for a whole 256-thread block: list slots for kinds 0 / 1 / 2 / 4 and CIGAR text
+// "<Lq>M" + result for kind 3 (settled without the table).  ONE atomic per block and counter: the lanes of a kind take
+// consecutive slots (warp ballots, per-warp counts summed in shared memory).  Called by all threads of the block.
+__device__ __forceinline__ void sw_route_settle(int kind, uint32_t k, int lq, int lr, int score, SwOut *__restrict__ out, SwCounters *ctr,
+                                                uint32_t *__restrict__ list_fast, uint32_t *__restrict__ list_wide,
+                                                uint32_t *__restrict__ list_gen, uint32_t *__restrict__ list_wfa,
+                                                char *__restrict__ cig, uint32_t cig_cap, ScStats &acc) {
+    __shared__ uint32_t s_w[8][5];            // per warp: members of kinds 0, 1, 2, 4 and CIGAR bytes of kind 3
+    __shared__ uint32_t s_b[5];               // the block's bases
+    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int kk = kind == 4 ? 3 : kind;      // list column: kinds 0, 1, 2 -> 0, 1, 2; kind 4 -> 3
+    unsigned mine = 0;
 #pragma unroll
     for (int t = 0; t < 4; t++) {
-        const int kk = t < 3 ? t : 4;
-        const unsigned m = __ballot_sync(0xFFFFFFFFu, kind == kk);
-        if (m) {
-            uint32_t base = 0;
-            if (lane == (unsigned)(__ffs((int)m) - 1))
-                base = atomicAdd(t == 0 ? &ctr->n_fast : t == 1 ? &ctr->n_wide : t == 2 ? &ctr->n_general : &ctr->n_wfa, (uint32_t)__popc(m));
-            base = __shfl_sync(0xFFFFFFFFu, base, __ffs((int)m) - 1);
-            if (kind == kk) slot = base + __popc(m & ((1u << lane) - 1u));
-        }
+        const unsigned m = __ballot_sync(0xFFFFFFFFu, kind != 3 && kind >= 0 && kk == t);
+        if (lane == 0) s_w[warp][t] = (uint32_t)__popc(m);
+        if (kind != 3 && kind >= 0 && kk == t) mine = m;
     }
-    if (kind == 0) list_fast[slot] = k;
-    else if (kind == 1) list_wide[slot] = k;
-    else if (kind == 2) list_gen[slot] = k;
-    else if (kind == 4) list_wfa[slot] = k;
-}
-
-// pairs settled without the table (kind == 3): CIGAR text "<Lq>M" from the temporary arena (one allocation per warp),
-// result, counters.  Called by all lanes of the warp.
-__device__ __forceinline__ void sw_settle(int kind, uint32_t k, int lq, int lr, int score, unsigned lane, SwOut *__restrict__ out,
-                                          SwCounters *ctr, char *__restrict__ cig, uint32_t cig_cap) {
-    const unsigned ms = __ballot_sync(0xFFFFFFFFu, kind == 3);
-    if (!ms) return;
     const int clen = kind == 3 ? 2 + (lq >= 10) + (lq >= 100) + (lq >= 1000) + (lq >= 10000) : 0;
     int incl = clen;
-    unsigned long long cells = kind == 3 ? (unsigned long long)lq * (unsigned)lr : 0ull;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-        const int t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-        if (lane >= (unsigned)o) incl += t;
+        const int v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+        if (lane >= (unsigned)o) incl += v;
     }
+    if (lane == 31) s_w[warp][4] = (uint32_t)incl;
+    __syncthreads();
+    if (threadIdx.x < 5) {
+        const int t = (int)threadIdx.x;
+        uint32_t sum = 0;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) cells += __shfl_down_sync(0xFFFFFFFFu, cells, o);
-    const int total = __shfl_sync(0xFFFFFFFFu, incl, 31);
-    uint32_t base = 0;
-    if (lane == 0) {
-        base = atomicAdd(&ctr->cig_used, (uint32_t)total);
-        atomicAdd(&ctr->sw_calls, (unsigned long long)__popc(ms));
-        atomicAdd(&ctr->cells, cells);
-        atomicAdd(&ctr->shortcut_calls, (unsigned long long)__popc(ms));
-        atomicAdd(&ctr->shortcut_cells, cells);
-        if ((uint64_t)base + total > cig_cap) atomicExch(&ctr->cig_overflow, 1u);
+        for (int w = 0; w < 8; w++) { const uint32_t c = s_w[w][t]; s_w[w][t] = sum; sum += c; }
+        uint32_t base = 0;
+        if (sum) {
+            if (t < 4) base = atomicAdd(t == 0 ? &ctr->n_fast : t == 1 ? &ctr->n_wide : t == 2 ? &ctr->n_general : &ctr->n_wfa, sum);
+            else { bool ok; base = sw_cig_alloc(ctr, cig_cap, sum, ok); if (!ok) base = 0xFFFFFFFFu; }
+        }
+        s_b[t] = base;
     }
-    base = __shfl_sync(0xFFFFFFFFu, base, 0);
+    __syncthreads();
     if (kind == 3) {
-        const uint32_t off = base + (uint32_t)(incl - clen);
-        if ((uint64_t)base + total <= cig_cap) {
+        acc.settled += 1; acc.cells += (unsigned long long)lq * (unsigned)lr;
+        const uint32_t base = s_b[4];
+        uint32_t off = 0;
+        if (base != 0xFFFFFFFFu) {
+            off = base + s_w[warp][4] + (uint32_t)(incl - clen);
             int l = lq;
             for (int t = clen - 2; t >= 0; t--) { cig[off + t] = (char)('0' + l % 10); l /= 10; }
             cig[off + clen - 1] = 'M';
         }
         SwOut o; o.score = score; o.status = BWT_HIT_MATCH | SW_FULL_M; o.cigar_len = clen; o.cigar_off = off;
         out[k] = o;
+    } else if (kind >= 0) {
+        const uint32_t slot = s_b[kk] + s_w[warp][kk] + (uint32_t)__popc(mine & ((1u << lane) - 1u));
+        (kk == 0 ? list_fast : kk == 1 ? list_wide : kk == 2 ? list_gen : list_wfa)[slot] = k;
+    }
+    __syncthreads();                          // s_w / s_b are reused by the next round
+}
+
+// the block's work counters -> global (one atomic per block and counter)
+__device__ __forceinline__ void sc_stats_flush(const ScStats &acc, SwCounters *ctr) {
+    __shared__ unsigned long long s_cells;
+    __shared__ uint32_t s_settled;
+    if (threadIdx.x == 0) { s_cells = 0; s_settled = 0; }
+    __syncthreads();
+    unsigned long long c = acc.cells;
+    uint32_t n = acc.settled;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { c += __shfl_down_sync(0xFFFFFFFFu, c, o); n += __shfl_down_sync(0xFFFFFFFFu, n, o); }
+    if ((threadIdx.x & 31) == 0 && n) { atomicAdd(&s_cells, c); atomicAdd(&s_settled, n); }
+    __syncthreads();
+    if (threadIdx.x == 0 && s_settled) {
+        atomicAdd(&ctr->sw_calls, (unsigned long long)s_settled);
+        atomicAdd(&ctr->cells, s_cells);
+        atomicAdd(&ctr->shortcut_calls, (unsigned long long)s_settled);
+        atomicAdd(&ctr->shortcut_cells, s_cells);
     }
 }
 
@@ -293,6 +314,7 @@ __global__ void __launch_bounds__(256) sw_classify_kernel(DevReads R, const uint
     const unsigned lane = threadIdx.x & 31;
     const int t = (int)(lane & 7u), g = (int)(lane >> 3);
     const uint32_t n = *n_ptr;
+    ScStats acc;
     for (uint32_t k0 = blockIdx.x * blockDim.x; k0 < n; k0 += gridDim.x * blockDim.x) {
         const uint32_t k = k0 + threadIdx.x;
         int score = 0, kind = -1;             // kind: 0 narrow, 1 wide, 2 general, 3 settled, 4 wavefront list, -1 nothing to do
@@ -349,9 +371,9 @@ __global__ void __launch_bounds__(256) sw_classify_kernel(DevReads R, const uint
             }
         }
         if (score) kind = 3;
-        sw_route(kind, k, lane, ctr, list_fast, list_wide, list_gen, list_wfa);
-        sw_settle(kind, k, d.lq, d.lr, score, lane, out, ctr, cig, cig_cap);
+        sw_route_settle(kind, k, d.lq, d.lr, score, out, ctr, list_fast, list_wide, list_gen, list_wfa, cig, cig_cap, acc);
     }
+    sc_stats_flush(acc, ctr);
 }
 
 // Stage 2: the wavefront rule on the pairs of list_wfa (all plain, all inside the rule's domain).  Lane L of a warp
@@ -367,6 +389,7 @@ __global__ void __launch_bounds__(256) sw_wfa_kernel(DevReads R, const uint32_t 
     const unsigned FULL = 0xFFFFFFFFu;
     const unsigned lane = threadIdx.x & 31;
     const uint32_t n = ctr->n_wfa;
+    ScStats acc;
     for (uint32_t e0 = blockIdx.x * blockDim.x; e0 < n; e0 += gridDim.x * blockDim.x) {
         const uint32_t e = e0 + threadIdx.x;
         int score = 0, kind = -1;
@@ -389,9 +412,9 @@ __global__ void __launch_bounds__(256) sw_wfa_kernel(DevReads R, const uint32_t 
             if ((int)(lane / (32 / SC_LANES)) == i) score = got;
         }
         if (todo) kind = score ? 3 : sw_dp_kind(d, cap_narrow, cap_wide);
-        sw_route(kind, k, lane, ctr, list_fast, list_wide, list_gen, nullptr);
-        sw_settle(kind, k, d.lq, d.lr, score, lane, out, ctr, cig, cig_cap);
+        sw_route_settle(kind, k, d.lq, d.lr, score, out, ctr, list_fast, list_wide, list_gen, nullptr, cig, cig_cap, acc);
     }
+    sc_stats_flush(acc, ctr);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -552,8 +575,9 @@ __device__ __forceinline__ bool sw_traceback(const SwFastParams &p, const uint2 
         int l = (int)(runs[k * B] >> 2);
         clen += 2 + (l >= 10) + (l >= 100) + (l >= 1000) + (l >= 10000);
     }
-    uint32_t off = atomicAdd(&p.ctr->cig_used, (uint32_t)clen);
-    if ((uint64_t)off + clen <= p.cig_cap) {
+    bool room;
+    uint32_t off = sw_cig_alloc(p.ctr, p.cig_cap, (uint32_t)clen, room);
+    if (room) {
         char *c = p.cig + off;
         for (int k = nr - 1; k >= 0; k--) {
             int v = (int)runs[k * B];
@@ -563,7 +587,7 @@ __device__ __forceinline__ bool sw_traceback(const SwFastParams &p, const uint2 
             c[nd] = op == 0 ? 'M' : op == 1 ? 'D' : 'I';
             c += nd + 1;
         }
-    } else atomicExch(&p.ctr->cig_overflow, 1u);
+    }
     SwOut o;
     o.score = vmax; o.status = BWT_HIT_MATCH; o.cigar_len = clen; o.cigar_off = off;
     p.out[cand] = o;
@@ -791,8 +815,9 @@ __global__ void __launch_bounds__(64) sw_general_kernel(DevReads R, const uint8_
         while (l >= 10) { nd++; l /= 10; }
         clen += nd + 1;
     }
-    uint32_t offc = atomicAdd(&ctr->cig_used, (uint32_t)clen);
-    if ((uint64_t)offc + clen <= cig_cap) {
+    bool room;
+    uint32_t offc = sw_cig_alloc(ctr, cig_cap, (uint32_t)clen, room);
+    if (room) {
         char *c = cig + offc;
         for (int k = nr - 1; k >= 0; k--) {
             uint32_t l = runs[k] >> 2;
@@ -802,7 +827,7 @@ __global__ void __launch_bounds__(64) sw_general_kernel(DevReads R, const uint8_
             c[nd] = op == 0 ? 'M' : op == 1 ? 'D' : 'I';
             c += nd + 1;
         }
-    } else atomicExch(&ctr->cig_overflow, 1u);
+    }
     o.score = (int32_t)(long long)vmax;                                    // trunc/1 (sw.erl:123)
     o.status = BWT_HIT_MATCH; o.cigar_len = clen; o.cigar_off = offc;
     out[cand] = o;
@@ -1060,7 +1085,7 @@ int sw_stage_finish(SwStage &st, const DevReads &R, const uint8_t *d_rbase, cons
         return BWT_OK;
     }
     // temporary CIGAR arena too small: grow to what this attempt asked for (and then some); the caller redoes the stage
-    uint64_t want = (uint64_t)st.h_ctr->cig_used * 2 + 4096;
+    uint64_t want = (uint64_t)st.cig_cap * 2 + 4096;                     // a region of the arena ran full
     if (want > 0xFFFFFFF0ull) { bwt_set_error("CIGAR arena beyond 4 GiB for one batch: use smaller batches"); return BWT_ERR_LIMIT; }
     cudaFree(st.d_cig_tmp);
     st.d_cig_tmp = nullptr;

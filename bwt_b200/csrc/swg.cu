@@ -53,6 +53,8 @@ __global__ void __launch_bounds__(GW_WARPS * 32) sw_general_warp_kernel(DevReads
     uint8_t *rch = reinterpret_cast<uint8_t *>(gw_smem + (size_t)GW_WARPS * wc_cap * 32) + (size_t)wib * wc_cap * 32;   // rch[c*32 + lane]
     uint32_t *slot = scratch + ((size_t)blockIdx.x * GW_WARPS + wib) * slot_words;
     const uint32_t n_list = ctr->n_general;
+    uint32_t n_done = 0;                                                    // this warp's work counters, flushed at the end
+    unsigned long long n_cells = 0;
     for (;;) {
         uint32_t e = 0;
         if (lane == 0) e = first + atomicAdd(cursor, 1u);
@@ -138,11 +140,7 @@ __global__ void __launch_bounds__(GW_WARPS * 32) sw_general_warp_kernel(DevReads
         SwOut o;
         o.score = 0; o.status = BWT_HIT_NO_MATCH; o.cigar_len = 0; o.cigar_off = 0;
         const int rows_done = fail_row >= 0 ? fail_row : lq;
-        if (lane == 0) {
-            atomicAdd(&ctr->sw_calls, 1ull);
-            atomicAdd(&ctr->cells, (unsigned long long)rows_done * (unsigned)lr);
-            atomicAdd(&ctr->general_done, 1u);
-        }
+        n_done++; n_cells += (unsigned long long)rows_done * (unsigned)lr;
         if (fail_row >= 0) { if (lane == 0) out[cand] = o; __syncwarp(); continue; }
         // leftmost column of the last row that holds its maximum (sw.erl:110-112); column 0 holds -(lq+1)
         const double vmax = __shfl_sync(FULL, vmax_last, last_lane);
@@ -175,8 +173,9 @@ __global__ void __launch_bounds__(GW_WARPS * 32) sw_general_warp_kernel(DevReads
                 while (l >= 10) { ndg++; l /= 10; }
                 clen += ndg + 1;
             }
-            const uint32_t offc = atomicAdd(&ctr->cig_used, (uint32_t)clen);
-            if ((uint64_t)offc + clen <= cig_cap) {
+            bool room;
+            const uint32_t offc = sw_cig_alloc(ctr, cig_cap, (uint32_t)clen, room);
+            if (room) {
                 char *cp = cig + offc;
                 for (int k = nr - 1; k >= 0; k--) {
                     uint32_t l = runs[k] >> 2;
@@ -187,12 +186,17 @@ __global__ void __launch_bounds__(GW_WARPS * 32) sw_general_warp_kernel(DevReads
                     cp[ndg] = op == 0 ? 'M' : op == 1 ? 'D' : 'I';
                     cp += ndg + 1;
                 }
-            } else atomicExch(&ctr->cig_overflow, 1u);
+            }
             o.score = (int32_t)(long long)vmax;                             // trunc/1 (sw.erl:123)
             o.status = BWT_HIT_MATCH; o.cigar_len = clen; o.cigar_off = offc;
             out[cand] = o;
         }
         __syncwarp();
+    }
+    if (lane == 0 && n_done) {
+        atomicAdd(&ctr->sw_calls, (unsigned long long)n_done);
+        atomicAdd(&ctr->cells, n_cells);
+        atomicAdd(&ctr->general_done, n_done);
     }
 }
 

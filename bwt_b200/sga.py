@@ -1,6 +1,6 @@
 """Mirror of sga.erl: sga/6 (sga.erl:17-64) on the GPU index."""
 from . import api
-from .errors import ReferenceCrash
+from .errors import LibraryLimit, ReferenceCrash
 
 
 def sga(fm, pc, pg, pt, last, qseq: bytes):
@@ -15,6 +15,6 @@ def sga_batch(fm, qseqs):
         if st[r] == api.READ_CRASH:
             raise ReferenceCrash("bwa:find_seeds crashes on a subsequence of read %d" % r)
         if st[r] == api.READ_LIMIT:
-            raise ValueError("read %d exceeds BWT_MAX_READ_LEN" % r)
+            raise LibraryLimit("read %d exceeds BWT_MAX_READ_LEN" % r)
         out.append(list(zip(S[clo[r]:clo[r + 1]].tolist(), D[clo[r]:clo[r + 1]].tolist())))
     return out

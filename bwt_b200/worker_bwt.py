@@ -1,7 +1,7 @@
 """Mirror of worker_bwt.erl's inner loop (worker_bwt.erl:73-108): one list of {Qname,Qseq} in, the messages the
 worker would cast to the master out, in the reference's emission order."""
 from . import api
-from .errors import ReferenceCrash
+from .errors import LibraryLimit, ReferenceCrash
 
 REF_EXTENSION_LEN = 200   # worker_bwt.erl:17
 
@@ -23,6 +23,8 @@ def process_list(fm, padded_ref: bytes, qseq_list):
     for r in range(len(qseq_list) - 1, -1, -1):
         if st[r] == api.READ_CRASH:
             raise ReferenceCrash("case_clause in bwa:find_seeds for read %r" % (qseq_list[r][0],))
+        if st[r] == api.READ_LIMIT:          # not "no clusters": the reference would have aligned this read
+            raise LibraryLimit("read %r exceeds this library's limits (1031 bases / 2^22 seed ends)" % (qseq_list[r][0],))
         hs = hits[ho[r]:ho[r + 1]]
         if len(hs) == 0:
             continue

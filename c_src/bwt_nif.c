@@ -13,9 +13,16 @@
  *   open(FmPath, RefPath, Device)     -> {ok, Index} | {error, {Code, Msg}}          fm_index:get_index/2 + .ref load
  *   info(Index)                       -> {{Pc,Pg,Pt,Last}, Shift, NRows}
  *   find_seeds(Index, [Subseq])       -> [{seeds|no_seeds|too_many_seeds|crash, Sp, Ep, N}]   bwa:find_seeds/6
- *   sga(Index, [Qseq])                -> [[{S,D}] | crash]                           sga:sga/6
+ *   sga(Index, [Qseq])                -> [[{S,D}] | crash | limit]                   sga:sga/6
  *   sw([{Qseq, Ref}], Device)         -> [no_match | {Score, Cigar}]                 sw:sw/2
- *   align(Index, [Qseq])              -> [[{Status, Score, Cigar, Pos, S, D}] | crash]   worker_bwt.erl:76-97
+ *   align(Index, [Qseq])              -> [[{Status, Score, Cigar, Pos, S, D}] | crash | limit]   worker_bwt.erl:76-97
+ *   align_workload(Index, [[Qseq]])   -> [[...as align...]]   a whole {workload, [[Qseq] x 10]} (worker_bwt.erl:64-69) in ONE call
+ *   close(Index)                      -> ok        releases the HBM now (dirty scheduler) instead of at garbage collection
+ * Per-read atoms: `crash` = the reference worker would crash on this read (case_clause in bwa:find_seeds/6 on a last
+ * character outside ACGTN, bwa.erl:15-24); `limit` = THIS library's limit (read longer than 1031 bases or more than
+ * 2^22 seed ends), not a crash in the reference: the shim falls back to the Erlang sga/sw for that read, or logs and
+ * skips it.
+ * Allocation failures come back as {error, enomem}.
  * Qseq / Subseq / Ref are strings (lists of bytes) or binaries.
  */
 #include <erl_nif.h>
@@ -29,11 +36,21 @@ static ErlNifResourceType *INDEX_RES;
 
 typedef struct { bwt_index *h; } index_res;
 
+/* Runs when the last reference to the resource is collected -- on a NORMAL scheduler thread, where cudaFree of tens of
+ * gigabytes does not belong: workers call close/1 (dirty) when they stop; this is the fallback for a crashed owner. */
 static void index_dtor(ErlNifEnv *env, void *obj) {
     (void)env;
     index_res *r = (index_res *)obj;
     if (r->h) bwt_close(r->h);
     r->h = NULL;
+}
+
+static ERL_NIF_TERM mk_enomem(ErlNifEnv *env) {
+    return enif_make_tuple2(env, enif_make_atom(env, "error"), enif_make_atom(env, "enomem"));
+}
+
+static ERL_NIF_TERM read_status_atom(ErlNifEnv *env, int32_t rs) {
+    return enif_make_atom(env, rs == BWT_READ_LIMIT ? "limit" : "crash");
 }
 
 static int on_load(ErlNifEnv *env, void **priv, ERL_NIF_TERM info) {
@@ -60,6 +77,7 @@ static int pack_list(ErlNifEnv *env, ERL_NIF_TERM list, int tuple_field, packed 
     out->n = (int64_t)len;
     out->offs = (int64_t *)malloc(((size_t)len + 1) * sizeof(int64_t));
     out->data = NULL;
+    if (!out->offs) return 0;
     size_t cap = 0, used = 0;
     ERL_NIF_TERM head, tail = list;
     int64_t k = 0;
@@ -76,13 +94,16 @@ static int pack_list(ErlNifEnv *env, ERL_NIF_TERM list, int tuple_field, packed 
         if (!enif_inspect_iolist_as_binary(env, item, &bin)) { packed_free(out); return 0; }
         if (used + bin.size + 16 > cap) {
             cap = (used + bin.size + 16) * 2;
-            out->data = (uint8_t *)realloc(out->data, cap);
+            uint8_t *grown = (uint8_t *)realloc(out->data, cap);
+            if (!grown) { packed_free(out); return 0; }
+            out->data = grown;
         }
         memcpy(out->data + used, bin.data, bin.size);
         used += bin.size;
         out->offs[++k] = (int64_t)used;
     }
     if (!out->data) out->data = (uint8_t *)malloc(16);
+    if (!out->data) { packed_free(out); return 0; }
     return 1;
 }
 
@@ -134,19 +155,22 @@ static ERL_NIF_TERM nif_find_seeds(ErlNifEnv *env, int argc, const ERL_NIF_TERM 
     int64_t n = p.n;
     int32_t *status = (int32_t *)malloc((size_t)(n + 1) * 4), *nm = (int32_t *)malloc((size_t)(n + 1) * 4);
     uint32_t *sp = (uint32_t *)malloc((size_t)(n + 1) * 4), *ep = (uint32_t *)malloc((size_t)(n + 1) * 4);
+    ERL_NIF_TERM *items = (ERL_NIF_TERM *)malloc((size_t)(n + 1) * sizeof(ERL_NIF_TERM));
+    if (!status || !nm || !sp || !ep || !items) {
+        free(status); free(nm); free(sp); free(ep); free(items); packed_free(&p);
+        return mk_enomem(env);
+    }
     int st = bwt_search_batch(h, p.data, p.offs, n, status, sp, ep, nm);
     ERL_NIF_TERM res;
     if (st != BWT_OK) res = mk_error(env, st);
     else {
         static const char *names[4] = {"seeds", "no_seeds", "too_many_seeds", "crash"};
-        ERL_NIF_TERM *items = (ERL_NIF_TERM *)malloc((size_t)(n + 1) * sizeof(ERL_NIF_TERM));
         for (int64_t k = 0; k < n; k++)
             items[k] = enif_make_tuple4(env, enif_make_atom(env, names[status[k] & 3]), enif_make_uint(env, sp[k]),
                                         enif_make_uint(env, ep[k]), enif_make_int(env, nm[k]));
         res = enif_make_list_from_array(env, items, (unsigned)n);
-        free(items);
     }
-    free(status); free(nm); free(sp); free(ep);
+    free(status); free(nm); free(sp); free(ep); free(items);
     packed_free(&p);
     return res;
 }
@@ -161,29 +185,33 @@ static ERL_NIF_TERM nif_sga(ErlNifEnv *env, int argc, const ERL_NIF_TERM argv[])
     int32_t *rs = (int32_t *)malloc((size_t)(n + 1) * 4);
     int64_t *clo = (int64_t *)malloc((size_t)(n + 1) * 8), *S = NULL;
     int32_t *D = NULL;
-    int st;
-    for (;;) {
-        S = (int64_t *)realloc(S, (size_t)cap * 8);
-        D = (int32_t *)realloc(D, (size_t)cap * 4);
+    ERL_NIF_TERM *items = (ERL_NIF_TERM *)malloc((size_t)(n + 1) * sizeof(ERL_NIF_TERM));
+    int st = rs && clo && items ? BWT_OK : BWT_ERR_NOMEM;
+    while (st == BWT_OK) {
+        int64_t *S2 = (int64_t *)realloc(S, (size_t)cap * 8);
+        int32_t *D2 = (int32_t *)realloc(D, (size_t)cap * 4);
+        if (S2) S = S2;
+        if (D2) D = D2;
+        if (!S2 || !D2) { st = BWT_ERR_NOMEM; break; }
         st = bwt_sga_batch(h, p.data, p.offs, n, rs, clo, S, D, cap, &total);
         if (st != BWT_ERR_NOSPACE) break;
         cap = total + 16;
+        st = BWT_OK;
     }
     ERL_NIF_TERM res;
-    if (st != BWT_OK) res = mk_error(env, st);
+    if (st == BWT_ERR_NOMEM) res = mk_enomem(env);
+    else if (st != BWT_OK) res = mk_error(env, st);
     else {
-        ERL_NIF_TERM *items = (ERL_NIF_TERM *)malloc((size_t)(n + 1) * sizeof(ERL_NIF_TERM));
         for (int64_t r = 0; r < n; r++) {
-            if (rs[r] != BWT_READ_OK) { items[r] = enif_make_atom(env, "crash"); continue; }
+            if (rs[r] != BWT_READ_OK) { items[r] = read_status_atom(env, rs[r]); continue; }
             ERL_NIF_TERM l = enif_make_list(env, 0);
             for (int64_t k = clo[r + 1] - 1; k >= clo[r]; k--)      /* cons from the tail: list keeps sga's order */
                 l = enif_make_list_cell(env, enif_make_tuple2(env, enif_make_int64(env, S[k]), enif_make_int(env, D[k])), l);
             items[r] = l;
         }
         res = enif_make_list_from_array(env, items, (unsigned)n);
-        free(items);
     }
-    free(rs); free(clo); free(S); free(D);
+    free(rs); free(clo); free(S); free(D); free(items);
     packed_free(&p);
     return res;
 }
@@ -201,17 +229,21 @@ static ERL_NIF_TERM nif_fs_find_seeds(ErlNifEnv *env, int argc, const ERL_NIF_TE
     int64_t n = p.n, cap = 4 * n + 16, total = 0;
     int32_t *qs = (int32_t *)malloc((size_t)(n + 1) * 4);
     int64_t *so = (int64_t *)malloc((size_t)(n + 1) * 8), *seeds = NULL;
-    int st;
-    for (;;) {
-        seeds = (int64_t *)realloc(seeds, (size_t)cap * 8);
+    ERL_NIF_TERM *items = (ERL_NIF_TERM *)malloc((size_t)(n + 1) * sizeof(ERL_NIF_TERM));
+    int st = qs && so && items ? BWT_OK : BWT_ERR_NOMEM;
+    while (st == BWT_OK) {
+        int64_t *s2 = (int64_t *)realloc(seeds, (size_t)cap * 8);
+        if (!s2) { st = BWT_ERR_NOMEM; break; }
+        seeds = s2;
         st = bwt_fs_find_seeds_batch(h, p.data, p.offs, n, len, defects, 0, qs, so, seeds, cap, &total, NULL);
         if (st != BWT_ERR_NOSPACE) break;
         cap = total + 16;
+        st = BWT_OK;
     }
     ERL_NIF_TERM res;
-    if (st != BWT_OK) res = mk_error(env, st);
+    if (st == BWT_ERR_NOMEM) res = mk_enomem(env);
+    else if (st != BWT_OK) res = mk_error(env, st);
     else {
-        ERL_NIF_TERM *items = (ERL_NIF_TERM *)malloc((size_t)(n + 1) * sizeof(ERL_NIF_TERM));
         for (int64_t r = 0; r < n; r++) {
             if (qs[r] == BWT_FS_SHORT) { items[r] = enif_make_atom(env, "short"); continue; }
             if (qs[r] == BWT_FS_LIMIT) { items[r] = enif_make_atom(env, "limit"); continue; }
@@ -221,9 +253,8 @@ static ERL_NIF_TERM nif_fs_find_seeds(ErlNifEnv *env, int argc, const ERL_NIF_TE
             items[r] = l;
         }
         res = enif_make_list_from_array(env, items, (unsigned)n);
-        free(items);
     }
-    free(qs); free(so); free(seeds);
+    free(qs); free(so); free(seeds); free(items);
     packed_free(&p);
     return res;
 }
@@ -240,57 +271,57 @@ static ERL_NIF_TERM nif_sw(ErlNifEnv *env, int argc, const ERL_NIF_TERM argv[]) 
     int32_t *clen = (int32_t *)malloc((size_t)(n + 1) * 4);
     int64_t *coff = (int64_t *)malloc((size_t)(n + 1) * 8);
     char *cig = NULL;
-    int st;
-    for (;;) {
-        cig = (char *)realloc(cig, (size_t)ccap);
+    ERL_NIF_TERM *items = (ERL_NIF_TERM *)malloc((size_t)(n + 1) * sizeof(ERL_NIF_TERM));
+    int st = status && score && clen && coff && items ? BWT_OK : BWT_ERR_NOMEM;
+    while (st == BWT_OK) {
+        char *c2 = (char *)realloc(cig, (size_t)ccap);
+        if (!c2) { st = BWT_ERR_NOMEM; break; }
+        cig = c2;
         st = bwt_sw_batch(device, q.data, q.offs, r.data, r.offs, n, status, score, coff, clen, cig, ccap, &ctot);
         if (st != BWT_ERR_NOSPACE) break;
         ccap = ctot + 16;
+        st = BWT_OK;
     }
     ERL_NIF_TERM res;
-    if (st != BWT_OK) res = mk_error(env, st);
+    if (st == BWT_ERR_NOMEM) res = mk_enomem(env);
+    else if (st != BWT_OK) res = mk_error(env, st);
     else {
-        ERL_NIF_TERM *items = (ERL_NIF_TERM *)malloc((size_t)(n + 1) * sizeof(ERL_NIF_TERM));
         for (int64_t k = 0; k < n; k++)
             items[k] = status[k] == BWT_HIT_MATCH
                            ? enif_make_tuple2(env, enif_make_int(env, score[k]),
                                               enif_make_string_len(env, cig + coff[k], (size_t)clen[k], ERL_NIF_LATIN1))
                            : enif_make_atom(env, "no_match");
         res = enif_make_list_from_array(env, items, (unsigned)n);
-        free(items);
     }
-    free(status); free(score); free(clen); free(coff); free(cig);
+    free(status); free(score); free(clen); free(coff); free(cig); free(items);
     packed_free(&q); packed_free(&r);
     return res;
 }
 
-/* align(Index, [Qseq]) -> per read: crash | [{Status, Score, Cigar, Pos, S, D}] in Cigars order (ascending position);
- * Status: match | no_match | window_oor (the reference badmatches there, worker_bwt.erl:89) */
-static ERL_NIF_TERM nif_align(ErlNifEnv *env, int argc, const ERL_NIF_TERM argv[]) {
-    bwt_index *h;
-    packed p;
-    (void)argc;
-    if (!get_index(env, argv[0], &h) || !pack_list(env, argv[1], -1, &p)) return enif_make_badarg(env);
-    int64_t n = p.n, hcap = 4 * n + 16, ccap = 64 * n + 256, nh = 0, nc = 0;
+/* the worker's inner loop for the reads of p (one bwt_align_batch call) -> items[r] = crash | limit | [{Status, Score,
+ * Cigar, Pos, S, D}] in Cigars order (ascending position); 0 = ok, else a bwt_status */
+static int align_core(ErlNifEnv *env, bwt_index *h, const packed *p, ERL_NIF_TERM *items) {
+    int64_t n = p->n, hcap = 4 * n + 16, ccap = 64 * n + 256, nh = 0, nc = 0;
     int32_t *rs = (int32_t *)malloc((size_t)(n + 1) * 4);
     int64_t *ho = (int64_t *)malloc((size_t)(n + 1) * 8);
     bwt_hit *hits = NULL;
     char *cig = NULL;
-    int st;
-    for (;;) {
-        hits = (bwt_hit *)realloc(hits, (size_t)hcap * sizeof(bwt_hit));
-        cig = (char *)realloc(cig, (size_t)ccap);
-        st = bwt_align_batch(h, p.data, p.offs, n, rs, ho, hits, hcap, &nh, cig, ccap, &nc);
+    int st = rs && ho ? BWT_OK : BWT_ERR_NOMEM;
+    while (st == BWT_OK) {
+        bwt_hit *h2 = (bwt_hit *)realloc(hits, (size_t)hcap * sizeof(bwt_hit));
+        char *c2 = (char *)realloc(cig, (size_t)ccap);
+        if (h2) hits = h2;
+        if (c2) cig = c2;
+        if (!h2 || !c2) { st = BWT_ERR_NOMEM; break; }
+        st = bwt_align_batch(h, p->data, p->offs, n, rs, ho, hits, hcap, &nh, cig, ccap, &nc);
         if (st != BWT_ERR_NOSPACE) break;
         hcap = nh + 16; ccap = nc + 16;
+        st = BWT_OK;
     }
-    ERL_NIF_TERM res;
-    if (st != BWT_OK) res = mk_error(env, st);
-    else {
+    if (st == BWT_OK) {
         static const char *names[3] = {"match", "no_match", "window_oor"};
-        ERL_NIF_TERM *items = (ERL_NIF_TERM *)malloc((size_t)(n + 1) * sizeof(ERL_NIF_TERM));
         for (int64_t r = 0; r < n; r++) {
-            if (rs[r] != BWT_READ_OK) { items[r] = enif_make_atom(env, "crash"); continue; }
+            if (rs[r] != BWT_READ_OK) { items[r] = read_status_atom(env, rs[r]); continue; }
             ERL_NIF_TERM l = enif_make_list(env, 0);
             for (int64_t k = ho[r + 1] - 1; k >= ho[r]; k--) {
                 const bwt_hit *x = &hits[k];
@@ -303,12 +334,72 @@ static ERL_NIF_TERM nif_align(ErlNifEnv *env, int argc, const ERL_NIF_TERM argv[
             }
             items[r] = l;
         }
-        res = enif_make_list_from_array(env, items, (unsigned)n);
-        free(items);
     }
     free(rs); free(ho); free(hits); free(cig);
+    return st;
+}
+
+/* align(Index, [Qseq]) -> per read: crash | limit | [{Status, Score, Cigar, Pos, S, D}];
+ * Status: match | no_match | window_oor (the reference badmatches there, worker_bwt.erl:89) */
+static ERL_NIF_TERM nif_align(ErlNifEnv *env, int argc, const ERL_NIF_TERM argv[]) {
+    bwt_index *h;
+    packed p;
+    (void)argc;
+    if (!get_index(env, argv[0], &h) || !pack_list(env, argv[1], -1, &p)) return enif_make_badarg(env);
+    ERL_NIF_TERM *items = (ERL_NIF_TERM *)malloc((size_t)(p.n + 1) * sizeof(ERL_NIF_TERM));
+    int st = items ? align_core(env, h, &p, items) : BWT_ERR_NOMEM;
+    ERL_NIF_TERM res = st == BWT_OK ? enif_make_list_from_array(env, items, (unsigned)p.n)
+                                    : st == BWT_ERR_NOMEM ? mk_enomem(env) : mk_error(env, st);
+    free(items);
     packed_free(&p);
     return res;
+}
+
+/* align_workload(Index, [[Qseq]]) -> [[per read as align/2]]: the whole {workload, [QseqList x 10]} of worker_bwt.erl:64-69
+ * in ONE call (2000 reads instead of ten calls of 200: the GPU path is launch-latency bound at that size) */
+static ERL_NIF_TERM nif_align_workload(ErlNifEnv *env, int argc, const ERL_NIF_TERM argv[]) {
+    bwt_index *h;
+    unsigned nlists;
+    (void)argc;
+    if (!get_index(env, argv[0], &h) || !enif_get_list_length(env, argv[1], &nlists)) return enif_make_badarg(env);
+    /* flatten: one packed batch, the list boundaries kept */
+    unsigned *cnt = (unsigned *)malloc(((size_t)nlists + 1) * sizeof(unsigned));
+    if (!cnt) return mk_enomem(env);
+    ERL_NIF_TERM flat = enif_make_list(env, 0), head, tail = argv[1];
+    unsigned k = 0;
+    /* build the flat list in reverse, then reverse once */
+    while (enif_get_list_cell(env, tail, &head, &tail)) {
+        unsigned len;
+        ERL_NIF_TERM h2, t2 = head;
+        if (!enif_get_list_length(env, head, &len)) { free(cnt); return enif_make_badarg(env); }
+        cnt[k++] = len;
+        while (enif_get_list_cell(env, t2, &h2, &t2)) flat = enif_make_list_cell(env, h2, flat);
+    }
+    ERL_NIF_TERM fwd;
+    if (!enif_make_reverse_list(env, flat, &fwd)) { free(cnt); return enif_make_badarg(env); }
+    packed p;
+    if (!pack_list(env, fwd, -1, &p)) { free(cnt); return enif_make_badarg(env); }
+    ERL_NIF_TERM *items = (ERL_NIF_TERM *)malloc((size_t)(p.n + 1) * sizeof(ERL_NIF_TERM));
+    ERL_NIF_TERM *lists = (ERL_NIF_TERM *)malloc(((size_t)nlists + 1) * sizeof(ERL_NIF_TERM));
+    int st = items && lists ? align_core(env, h, &p, items) : BWT_ERR_NOMEM;
+    ERL_NIF_TERM res;
+    if (st == BWT_OK) {
+        int64_t at = 0;
+        for (unsigned l = 0; l < nlists; l++) { lists[l] = enif_make_list_from_array(env, items + at, cnt[l]); at += cnt[l]; }
+        res = enif_make_list_from_array(env, lists, nlists);
+    } else res = st == BWT_ERR_NOMEM ? mk_enomem(env) : mk_error(env, st);
+    free(items); free(lists); free(cnt);
+    packed_free(&p);
+    return res;
+}
+
+/* close(Index) -> ok: release the device memory now, on a dirty scheduler */
+static ERL_NIF_TERM nif_close(ErlNifEnv *env, int argc, const ERL_NIF_TERM argv[]) {
+    index_res *r;
+    (void)argc;
+    if (!enif_get_resource(env, argv[0], INDEX_RES, (void **)&r)) return enif_make_badarg(env);
+    if (r->h) { bwt_close(r->h); r->h = NULL; }
+    return enif_make_atom(env, "ok");
 }
 
 static ErlNifFunc nif_funcs[] = {
@@ -319,6 +410,8 @@ static ErlNifFunc nif_funcs[] = {
     {"fs_find_seeds", 4, nif_fs_find_seeds, ERL_NIF_DIRTY_JOB_CPU_BOUND},
     {"sw", 2, nif_sw, ERL_NIF_DIRTY_JOB_CPU_BOUND},
     {"align", 2, nif_align, ERL_NIF_DIRTY_JOB_CPU_BOUND},
+    {"align_workload", 2, nif_align_workload, ERL_NIF_DIRTY_JOB_CPU_BOUND},
+    {"close", 1, nif_close, ERL_NIF_DIRTY_JOB_IO_BOUND},
 };
 
 ERL_NIF_INIT(bwt_nif, nif_funcs, on_load, NULL, NULL, NULL)

@@ -127,7 +127,13 @@ typedef struct bwt_packed_reads {
     const uint32_t *exc_idx;    /*   their indices, ascending */
     const int64_t *exc_off;     /*   n_exc + 1 offsets into exc_ascii */
     const uint8_t *exc_ascii;   /*   their text */
+    /* optional index for cutting the batch into chunks without scanning the lengths (NULL / 0: scanned when needed):
+     * word_index[k] = words before read k * BWT_PACK_INDEX_STRIDE, k = 0 .. ceil(n / stride); maxlen_index[k] = longest read
+     * of block k */
+    const int64_t *word_index;
+    const uint16_t *maxlen_index;
 } bwt_packed_reads;
+#define BWT_PACK_INDEX_STRIDE 65536
 
 typedef struct bwt_stats {   /* work counters of the last run (definitions: DESIGN.md "units") */
     uint64_t reads, searches, lf_steps, hbm_lf_steps, located_rows, clusters, sw_calls, sw_cells, sw_general;
@@ -159,6 +165,11 @@ int bwt_open_arrays(const uint8_t *L, uint64_t n, const uint32_t *SA, const uint
  * mapped as fm_index.erl:131-135; 'N' is rejected because the reference substitutes random:uniform(4)).
  * Suffix array by radix sort of 2-bit packed prefixes; any correct SA equals dsa:dsa/1's (dsa.erl:15-48). */
 int bwt_build(const uint8_t *chunk, uint64_t len, int64_t shift, int device, bwt_index **out);
+/* The same for chunks that hold 'N': each one is replaced in the indexed text (not in the .ref) by
+ * element(random:uniform(4), {$A,$C,$G,$T}) as fm_index.erl:131 does, drawn from OTP's `random` generator (AS183) whose
+ * state {A1,A2,A3} the caller carries from chunk to chunk of one make_indices run (in/out; a fresh Erlang process starts at
+ * {3172, 9814, 20125}).  as183_state = NULL: 'N' is rejected, as bwt_build does. */
+int bwt_build_n(const uint8_t *chunk, uint64_t len, int64_t shift, int device, uint32_t as183_state[3], bwt_index **out);
 
 /* Synthetic reference for the benchmark configs: len i.i.d. uniform ACGT bases from a counter-based
  * generator (seed), generated on the device, then indexed like bwt_build. */
@@ -171,6 +182,10 @@ int bwt_save(const bwt_index *h, const char *fm_path, const char *ref_path);
 int bwt_export(const bwt_index *h, uint8_t *L, uint32_t *SA, uint8_t *ref);
 
 int bwt_info(const bwt_index *h, bwt_index_info *info);
+
+/* Host only (no GPU needed): rows, pointers and shift of a <Chrom>_pJ.fm as fm_index:get_index/2 would return them
+ * (fm_index.erl:154-156).  Atoms in any of the external-format encodings (ATOM_EXT of OTP 17, the UTF-8 forms of OTP 26+). */
+int bwt_fm_inspect(const char *fm_path, uint64_t *n_rows, uint32_t pointers[4], int64_t *shift);
 
 /* Depth of the k-mer interval table: entry = state of bwa:find_seeds/6 (bwa.erl:12-45) after the last k characters
  * of a subsequence, so those k-1 LF steps cost one lookup.  0 or 8 = the 4^8 table only; 9..15 adds a 4^k-entry
@@ -240,6 +255,8 @@ int64_t bwt_pack_words(const int64_t *offsets, int64_t n);     /* words bwt_pack
 int bwt_pack_reads(const uint8_t *reads, const int64_t *offsets, int64_t n, int threads, uint32_t *words, int64_t words_cap,
                    uint16_t *lens, uint32_t *exc_idx, int64_t exc_cap, int64_t *exc_off, uint8_t *exc_ascii,
                    int64_t exc_ascii_cap, int64_t *n_words, int64_t *n_exc, int64_t *exc_bytes);
+/* the chunking index of a packed batch: word_index[n / stride + 2], maxlen_index[n / stride + 1] (stride = BWT_PACK_INDEX_STRIDE) */
+int bwt_pack_index(const uint16_t *lens, int64_t n, int64_t *word_index, uint16_t *maxlen_index);
 int bwt_batch_upload_packed(bwt_batch *b, const bwt_packed_reads *p);
 int bwt_batch_run_compact(bwt_batch *b);
 int bwt_batch_download_compact(bwt_batch *b, uint8_t *read_status, uint32_t *hit_offsets, bwt_hit16 *hits, int64_t hits_cap,

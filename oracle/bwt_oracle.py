@@ -81,11 +81,28 @@ _IUPAC_TO_ACGT = {  # fm_index.erl:131-135 ; 'N' -> random:uniform(4) is NOT res
 }
 
 
-def map_chunk_to_acgt(chunk: bytes) -> bytes:
+AS183_SEED0 = (3172, 9814, 20125)    # random:seed0/0 (OTP stdlib random.erl; NOT in the reference tree: unpinned there)
+
+
+def as183_uniform(state: list) -> float:
+    """random:uniform/0 of OTP's `random` module (AS183); state = [A1, A2, A3], updated in place."""
+    state[0] = (state[0] * 171) % 30269
+    state[1] = (state[1] * 172) % 30307
+    state[2] = (state[2] * 170) % 30323
+    r = state[0] / 30269 + state[1] / 30307 + state[2] / 30323
+    return r - int(r)
+
+
+def map_chunk_to_acgt(chunk: bytes, n_state: Optional[list] = None) -> bytes:
+    """fm_index.erl:131-136.  n_state: AS183 state carried across the chunks of one make_indices run ('N' ->
+    element(random:uniform(4), {$A,$C,$G,$T})); None: a chunk with 'N' is refused."""
     out = bytearray(len(chunk))
     for k, c in enumerate(chunk):
         if c == ord("N"):
-            raise ValueError("chunk holds 'N': the reference substitutes random:uniform(4) (AS183), which is unpinned")
+            if n_state is None:
+                raise ValueError("chunk holds 'N': the reference substitutes random:uniform(4) (AS183): pass n_state")
+            out[k] = b"ACGT"[int(as183_uniform(n_state) * 4)]
+            continue
         if c not in _IUPAC_TO_ACGT:
             raise ReferenceCrash("error(%d): unknown symbol (fm_index.erl:136)" % c)
         out[k] = _IUPAC_TO_ACGT[c]

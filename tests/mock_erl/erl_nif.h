@@ -34,6 +34,7 @@ ERL_NIF_TERM enif_make_tuple(ErlNifEnv *, unsigned, ...);
 ERL_NIF_TERM enif_make_list(ErlNifEnv *, unsigned, ...);
 ERL_NIF_TERM enif_make_list_cell(ErlNifEnv *, ERL_NIF_TERM, ERL_NIF_TERM);
 ERL_NIF_TERM enif_make_list_from_array(ErlNifEnv *, const ERL_NIF_TERM[], unsigned);
+int enif_make_reverse_list(ErlNifEnv *, ERL_NIF_TERM, ERL_NIF_TERM *);
 ERL_NIF_TERM enif_make_badarg(ErlNifEnv *);
 int enif_get_list_length(ErlNifEnv *, ERL_NIF_TERM, unsigned *);
 int enif_get_list_cell(ErlNifEnv *, ERL_NIF_TERM, ERL_NIF_TERM *, ERL_NIF_TERM *);

@@ -15,10 +15,10 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 out_dir = os.path.join(ROOT, "profiles")
 os.makedirs(out_dir, exist_ok=True)
 
-rows = [r for r in csv.reader(open(launches)) if len(r) > 10]
+rows = [r for r in csv.reader(open(launches)) if len(r) > 10] if launches != "-" else [["ID", "Kernel Name", "Metric Value", "Grid Size", "Block Size"]]
 hdr = rows[0]
 ki, vi, gi, bi = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Grid Size"), hdr.index("Block Size")
-with open(os.path.join(out_dir, "%s_launches.csv" % tag), "w") as f:
+with open(os.path.join(out_dir, "%s_launches.csv" % tag) if launches != "-" else os.devnull, "w") as f:
     f.write("# %s\n# ncu --metrics gpu__time_duration.sum --clock-control none (cold-cache, serialised: compare shares)\n" % cmd)
     f.write("id,kernel,grid,block,time_us\n")
     for r in rows[1:]:

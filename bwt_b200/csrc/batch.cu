@@ -578,6 +578,7 @@ static int run_core(bwt_batch *b, bool with_sw, bool compact) {
             windows_kernel<<<148 * 8, 256, 0, b->stream>>>(b->d_clusters, &b->d_ctr->n_pairs, b->d_len, ix.ref_len_padded, b->sw.d_desc, b->sw.d_out);
             b->stats.launches += 1;
             K_CHECK(b->stream, "windows_kernel");
+            b->sw.small = n <= (int64_t)std::max(0, sw_small_limit());
             BWT_TRY(sw_stage_enqueue(b->sw, b->R, ix.ref, ix.ref2, ix.refx, &b->d_ctr->n_pairs, cl_cap, b->max_read_len, b->stream));
             CU_TRY(cudaMemcpyAsync(b->sw.h_ctr, b->sw.d_ctr, sizeof(SwCounters), cudaMemcpyDeviceToHost, b->stream));
             CU_TRY(cudaEventRecord(b->ev[2], b->stream));

@@ -119,6 +119,12 @@ __device__ __forceinline__ int sc_extend(const ScWave &wf, int o, int i, int lim
     return m ? min(lim, 16 * w + ((__ffs((int)m) - 1) >> 1)) : lim;
 }
 
+// penalty budget of the wavefront search by read length (three mismatches up to 128 bp, four up to 192, five beyond):
+// every level costs the whole warp time, and a wider budget also means more diagonals (kk on either side of the window's)
+__device__ __forceinline__ int sc_pmax(int lq) {
+    return min(lq <= 128 ? 9 : lq <= 192 ? 12 : SC_PMAX, 2 * (lq >> 1));     // the row threshold holds up to 2*(Lq div 2)
+}
+
 // 0 = run the DP; otherwise the score of the pair, whose CIGAR is "<Lq>M".  Called by ALL lanes of the warp, converged;
 // the SC_LANES lanes of a group pass the same pair (valid = false: no pair) and the group's storage; t = lane index
 // inside the group.  Both strings are plain ACGT (the caller checked): pkr = the read's packed words, the window is
@@ -140,9 +146,7 @@ __device__ __forceinline__ int sw_shortcut(const uint32_t *__restrict__ pkr, int
     }
     __syncwarp();                                                    // qp / rp visible to the whole group
     (void)lane;
-    // penalty budget by read length (three mismatches up to 128 bp, four up to 192, five beyond): every level costs
-    // the whole warp time, and a wider budget also means more diagonals (kk on either side of the window's)
-    const int pmax = min(lq <= 128 ? 9 : lq <= 192 ? 12 : SC_PMAX, 2 * (lq >> 1));   // the row threshold holds up to 2*(Lq div 2)
+    const int pmax = sc_pmax(lq);
     const int kk = (pmax - 1) / 3;
     const int nd = dd + 2 * kk + 1;                                  // diagonal slot d <-> o = d - kk
     bool open = elig;
@@ -350,7 +354,7 @@ __global__ void __launch_bounds__(256) sw_classify_kernel(DevReads R, const uint
                 const uint32_t q0 = h0 ? read_fwd_word(pkr, lq, t) : 0u, q1 = h1 ? read_fwd_word(pkr, lq, t + 8) : 0u;
                 const uint32_t m0 = h0 ? (lq - 16 * t < 16 ? (1u << (2 * (lq - 16 * t))) - 1u : 0xFFFFFFFFu) & 0x55555555u : 0u;
                 const uint32_t m1 = h1 ? (lq - 16 * (t + 8) < 16 ? (1u << (2 * (lq - 16 * (t + 8)))) - 1u : 0xFFFFFFFFu) & 0x55555555u : 0u;
-                int sc = 0;
+                int sc = 0, mn = 0x7FFF;                                // mn: fewest mismatches on a diagonal of the window
                 const int omax = __reduce_max_sync(FULL, qk ? dd : 0);
                 for (int o = 0; o <= omax; o++) {                       // diagonals of the window, leftmost first
                     const bool live = qk && o <= dd && sc == 0;
@@ -362,15 +366,22 @@ __global__ void __launch_bounds__(256) sw_classify_kernel(DevReads R, const uint
                     mism += __shfl_xor_sync(FULL, mism, 2);
                     mism += __shfl_xor_sync(FULL, mism, 4);
                     if (live) {
+                        mn = min(mn, mism);
                         if (mism == 0) sc = 2 * lq;                     // the leftmost perfect diagonal
                         else if (dd == 0 && mism == 1) sc = 2 * lq - 3; // one mismatch, no room for a gap
                     }
                 }
+                // The wavefront rule can only settle a pair on a window diagonal with at most pmax/3 mismatches (its own
+                // acceptance test): when every diagonal has more -- the usual picture of a read with an indel, whose
+                // diagonals all disagree from the indel on -- the search would run every level and then hand the pair to
+                // the DP anyway.  -1 = skip the search.
+                if (sc == 0 && 3 * mn > sc_pmax(lq)) sc = -1;
                 const int got = __shfl_sync(FULL, sc, 8 * (int)(lane & 3u));
                 if ((int)(lane >> 2) == i) score = got;
             }
         }
-        if (score) kind = 3;
+        if (score > 0) kind = 3;
+        else if (score < 0 && kind == 4) kind = sw_dp_kind(d, cap_narrow, cap_wide);
         sw_route_settle(kind, k, d.lq, d.lr, score, out, ctr, list_fast, list_wide, list_gen, list_wfa, cig, cig_cap, acc);
     }
     sc_stats_flush(acc, ctr);
@@ -712,6 +723,68 @@ __global__ void __launch_bounds__(SW_BLOCK) sw_fast_kernel(SwFastParams p) {
 }
 
 // ---------------------------------------------------------------------------------------------------
+// The DP list ordered by shape.  sw_fast_kernel runs two pairs per thread and 32 threads per warp in lock step: a warp
+// pays for its longest window (columns), its largest strip count (Lq = 101 needs one strip more than Lq = 100) and for
+// BOTH instantiations of the first strip when some of its lanes start on a full strip and others on a masked one.
+// With ragged read lengths (98-102 bp) that cost 15 % of the lanes (27 of 32 active in the inner loop).  A counting
+// sort by (Lq, Lr) -- histogram, one-block scan, scatter; warp-aggregated atomics because a batch has a few dozen
+// shapes -- puts equal shapes next to each other.  The order inside a shape is arbitrary; results do not depend on it.
+// ---------------------------------------------------------------------------------------------------
+constexpr uint32_t SW_SORT_LR = 512;          // window lengths per query length (the fast tiers end at 384 columns)
+__device__ __forceinline__ uint32_t sw_shape_key(const SwDesc &d, uint32_t nbins) {
+    const uint32_t k = (uint32_t)d.lq * SW_SORT_LR + min((uint32_t)d.lr, SW_SORT_LR - 1u);
+    return min(k, nbins - 1u);
+}
+
+__global__ void __launch_bounds__(256) sw_shape_hist_kernel(const SwDesc *__restrict__ desc, const uint32_t *__restrict__ list,
+                                                            const uint32_t *__restrict__ n_ptr, uint32_t *__restrict__ bins, uint32_t nbins) {
+    const uint32_t n = *n_ptr;
+    const unsigned lane = threadIdx.x & 31;
+    for (uint32_t e0 = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; e0 < n; e0 += gridDim.x * blockDim.x) {
+        const uint32_t e = e0 + lane;
+        const uint32_t key = e < n ? sw_shape_key(desc[list[e]], nbins) : 0xFFFFFFFFu;
+        const unsigned m = __match_any_sync(0xFFFFFFFFu, key);
+        if (e < n && lane == (unsigned)(__ffs((int)m) - 1)) atomicAdd(&bins[key], (uint32_t)__popc(m));
+    }
+}
+
+__global__ void __launch_bounds__(1024) sw_shape_scan_kernel(uint32_t *__restrict__ bins, uint32_t nbins) {
+    __shared__ uint32_t s_part[1024];
+    const uint32_t tid = threadIdx.x, per = (nbins + 1023u) / 1024u;
+    const uint32_t lo = min(nbins, tid * per), hi = min(nbins, lo + per);
+    uint32_t sum = 0;
+    for (uint32_t i = lo; i < hi; i++) sum += bins[i];
+    s_part[tid] = sum;
+    __syncthreads();
+    for (uint32_t o = 1; o < 1024u; o <<= 1) {
+        const uint32_t v = tid >= o ? s_part[tid - o] : 0u;
+        __syncthreads();
+        s_part[tid] += v;
+        __syncthreads();
+    }
+    uint32_t run = s_part[tid] - sum;
+    for (uint32_t i = lo; i < hi; i++) { const uint32_t c = bins[i]; bins[i] = run; run += c; }
+}
+
+__global__ void __launch_bounds__(256) sw_shape_scatter_kernel(const SwDesc *__restrict__ desc, const uint32_t *__restrict__ list,
+                                                               const uint32_t *__restrict__ n_ptr, uint32_t *__restrict__ bins, uint32_t nbins,
+                                                               uint32_t *__restrict__ sorted) {
+    const uint32_t n = *n_ptr;
+    const unsigned lane = threadIdx.x & 31;
+    for (uint32_t e0 = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; e0 < n; e0 += gridDim.x * blockDim.x) {
+        const uint32_t e = e0 + lane;
+        const uint32_t k = e < n ? list[e] : 0u;
+        const uint32_t key = e < n ? sw_shape_key(desc[k], nbins) : 0xFFFFFFFFu;
+        const unsigned m = __match_any_sync(0xFFFFFFFFu, key);
+        const int leader = __ffs((int)m) - 1;
+        uint32_t base = 0;
+        if (e < n && (int)lane == leader) base = atomicAdd(&bins[key], (uint32_t)__popc(m));
+        base = __shfl_sync(0xFFFFFFFFu, base, leader);
+        if (e < n) sorted[base + (uint32_t)__popc(m & ((1u << lane) - 1u))] = k;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
 // general path: doubles, any alphabet, any size
 // ---------------------------------------------------------------------------------------------------
 __device__ __forceinline__ double sigma_ref(uint8_t q, uint8_t r) {      // sw.erl:164-202, first clause wins
@@ -854,7 +927,8 @@ int grow(T *&p, size_t &cap_items, size_t need_items) {
 int sw_stage_reserve(SwStage &st, uint32_t pairs) {
     if (pairs <= st.cap && st.d_desc) return BWT_OK;
     uint32_t want = pairs + pairs / 4 + 1024;
-    if (st.d_desc) { cudaFree(st.d_desc); cudaFree(st.d_out); cudaFree(st.d_list_fast); cudaFree(st.d_list_wide); cudaFree(st.d_list_gen); cudaFree(st.d_list_ovf); cudaFree(st.d_list_wfa); cudaFree(st.d_list_big); }
+    if (st.d_desc) { cudaFree(st.d_desc); cudaFree(st.d_out); cudaFree(st.d_list_fast); cudaFree(st.d_list_wide); cudaFree(st.d_list_gen); cudaFree(st.d_list_ovf); cudaFree(st.d_list_wfa); cudaFree(st.d_list_big); cudaFree(st.d_list_sorted); }
+    st.d_list_sorted = nullptr;
     st.d_desc = nullptr; st.d_out = nullptr; st.d_list_fast = nullptr; st.d_list_wide = nullptr; st.d_list_gen = nullptr; st.d_list_ovf = nullptr; st.d_list_wfa = nullptr; st.d_list_big = nullptr;
     st.cap = 0;
     CU_TRY(cudaMalloc(&st.d_desc, (size_t)want * sizeof(SwDesc)));
@@ -865,6 +939,7 @@ int sw_stage_reserve(SwStage &st, uint32_t pairs) {
     CU_TRY(cudaMalloc(&st.d_list_ovf, (size_t)want * sizeof(uint32_t)));
     CU_TRY(cudaMalloc(&st.d_list_wfa, (size_t)want * sizeof(uint32_t)));
     CU_TRY(cudaMalloc(&st.d_list_big, (size_t)want * sizeof(uint32_t)));
+    CU_TRY(cudaMalloc(&st.d_list_sorted, (size_t)want * sizeof(uint32_t)));
     if (!st.d_ctr) {
         CU_TRY(cudaMalloc(&st.d_ctr, sizeof(SwCounters)));
         CU_TRY(cudaMallocHost(&st.h_ctr, sizeof(SwCounters)));
@@ -883,7 +958,7 @@ int sw_stage_reserve(SwStage &st, uint32_t pairs) {
 
 void sw_stage_free(SwStage &st) {
     cudaFree(st.d_desc); cudaFree(st.d_out); cudaFree(st.d_list_fast); cudaFree(st.d_list_wide); cudaFree(st.d_list_gen); cudaFree(st.d_list_ovf);
-    cudaFree(st.d_list_wfa); cudaFree(st.d_list_big); cudaFree(st.d_gw_scratch);
+    cudaFree(st.d_list_wfa); cudaFree(st.d_list_big); cudaFree(st.d_list_sorted); cudaFree(st.d_sort_bins); cudaFree(st.d_gw_scratch);
     cudaFree(st.d_ctr); if (st.h_ctr) cudaFreeHost(st.h_ctr);
     if (st.ev_k0) cudaEventDestroy(st.ev_k0);
     if (st.ev_k1) cudaEventDestroy(st.ev_k1);
@@ -936,6 +1011,21 @@ SwFastParams sw_params(SwStage &st, const DevReads &R, const uint32_t *d_ref2, c
     return p;
 }
 
+// BWT_SW_SORT: smallest pair capacity for which the DP list is ordered by shape (default 32768; -1 = never, 0 = always)
+int sw_sort_min_pairs() {
+    const char *e = getenv("BWT_SW_SORT");
+    return e && *e ? atoi(e) : 32768;
+}
+
+}  // namespace
+// BWT_SW_SMALL: largest batch (reads, or pairs of a bwt_sw_batch call) whose DP pairs all take the warp-per-pair kernel
+// (default 4096; 0 = never: the fast tiers even for a handful of pairs)
+int sw_small_limit() {
+    const char *e = getenv("BWT_SW_SMALL");
+    return e && *e ? atoi(e) : 4096;
+}
+namespace {
+
 int sw_use_shortcut() {
     // BWT_SW_SHORTCUT: 3 (default) quick test + wavefront rule, 2 the wavefront rule alone, 1 the quick test alone,
     // 0 every pair through the DP (A/B timing, and parity tests of the DP on easy pairs); read per run: tests flip it
@@ -958,26 +1048,47 @@ int sw_stage_enqueue(SwStage &st, const DevReads &R, const uint8_t *d_rbase, con
     SwPlan pl;
     BWT_TRY(sw_plan(st, n_cap, max_lq, pl));
     const int use_shortcut = sw_use_shortcut();
+    // worker-sized batches (st.small): the thread-per-two-pairs DP kernel is a throughput design -- one pair costs it
+    // ~0.4 ms however short the list, and its launch alone (100 KB of shared memory per block) a quarter of that -- so
+    // every pair that needs the table goes to the warp-per-pair kernel (tens of microseconds for a few hundred pairs;
+    // same recurrence in doubles, exact for plain ACGT as well) and the fast tiers are not launched at all.
+    const int cap_narrow = st.small ? 0 : pl.cap_narrow, cap_wide = st.small ? 0 : pl.cap_wide;
     CU_TRY(cudaMemsetAsync(st.d_ctr, 0, sizeof(SwCounters), stream));
     const unsigned cgrid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(((uint64_t)n_cap + 255) / 256, (uint64_t)148 * 32));
-    sw_classify_kernel<<<cgrid, 256, 0, stream>>>(R, d_ref2, d_refx, st.d_desc, st.d_out, d_n, pl.cap_narrow, pl.cap_wide,
+    sw_classify_kernel<<<cgrid, 256, 0, stream>>>(R, d_ref2, d_refx, st.d_desc, st.d_out, d_n, cap_narrow, cap_wide,
                                                   st.d_list_fast, st.d_list_wide, st.d_list_gen, st.d_list_wfa, st.d_ctr,
                                                   st.d_cig_tmp, st.cig_cap, use_shortcut);
     K_CHECK(stream, "sw_classify_kernel");
     st.launches += 1;
     if (use_shortcut & 2) {
-        sw_wfa_kernel<<<std::min(cgrid, 148u * 8u), 256, 0, stream>>>(R, d_ref2, st.d_desc, st.d_out, st.d_list_wfa, pl.cap_narrow, pl.cap_wide,
+        sw_wfa_kernel<<<std::min(cgrid, 148u * 8u), 256, 0, stream>>>(R, d_ref2, st.d_desc, st.d_out, st.d_list_wfa, cap_narrow, cap_wide,
                                                                      st.d_list_fast, st.d_list_wide, st.d_list_gen, st.d_ctr,
                                                                      st.d_cig_tmp, st.cig_cap);
         K_CHECK(stream, "sw_wfa_kernel");
         st.launches += 1;
     }
     SwFastParams p = sw_params(st, R, d_ref2, pl);
+    // large batches: the DP list ordered by shape (see sw_shape_hist_kernel); small ones are not worth three launches
+    const uint32_t *fast_list = st.d_list_fast;
+    if (!st.small && sw_sort_min_pairs() >= 0 && n_cap >= (uint32_t)sw_sort_min_pairs()) {
+        const uint32_t nbins = (uint32_t)(std::min(max_lq, SW_FAST_MAX_LQ) + 1) * SW_SORT_LR;
+        BWT_TRY(grow(st.d_sort_bins, st.sort_bins_cap, (size_t)nbins));
+        CU_TRY(cudaMemsetAsync(st.d_sort_bins, 0, (size_t)nbins * sizeof(uint32_t), stream));
+        const unsigned sgrid = std::min(cgrid, 148u * 8u);
+        sw_shape_hist_kernel<<<sgrid, 256, 0, stream>>>(st.d_desc, st.d_list_fast, &st.d_ctr->n_fast, st.d_sort_bins, nbins);
+        sw_shape_scan_kernel<<<1, 1024, 0, stream>>>(st.d_sort_bins, nbins);
+        sw_shape_scatter_kernel<<<sgrid, 256, 0, stream>>>(st.d_desc, st.d_list_fast, &st.d_ctr->n_fast, st.d_sort_bins, nbins, st.d_list_sorted);
+        K_CHECK(stream, "sw_shape_* kernels");
+        st.launches += 3;
+        fast_list = st.d_list_sorted;
+    }
     CU_TRY(cudaEventRecord(st.ev_k0, stream));
-    p.list = st.d_list_fast; p.n_list = &st.d_ctr->n_fast; p.cap_cols = pl.cap_narrow;
-    sw_fast_kernel<true><<<pl.grid[0], SW_BLOCK, smem_of(pl.cap_narrow, true), stream>>>(p);
-    K_CHECK(stream, "sw_fast_kernel (narrow)");
-    st.launches += 1;
+    if (!st.small) {
+        p.list = fast_list; p.n_list = &st.d_ctr->n_fast; p.cap_cols = pl.cap_narrow;
+        sw_fast_kernel<true><<<pl.grid[0], SW_BLOCK, smem_of(pl.cap_narrow, true), stream>>>(p);
+        K_CHECK(stream, "sw_fast_kernel (narrow)");
+        st.launches += 1;
+    }
     CU_TRY(cudaEventRecord(st.ev_k1, stream));
     // pairs with 'N' / IUPAC / other bytes, or beyond the fast tiers: one warp per pair, doubles; always launched (its
     // blocks leave at once when the list is empty)
@@ -1098,6 +1209,7 @@ int sw_stage_finish(SwStage &st, const DevReads &R, const uint8_t *d_rbase, cons
 int sw_stage_run(SwStage &st, const DevReads &R, const uint8_t *d_rbase, const uint32_t *d_ref2, const uint32_t *d_refx,
                  const uint32_t *d_n, uint32_t n, int max_lq, cudaStream_t stream) {
     if (n == 0) return BWT_OK;
+    st.small = n <= (uint32_t)std::max(0, sw_small_limit());
     for (int attempt = 0; attempt < 4; attempt++) {
         BWT_TRY(sw_stage_enqueue(st, R, d_rbase, d_ref2, d_refx, d_n, n, max_lq, stream));
         CU_TRY(cudaMemcpyAsync(st.h_ctr, st.d_ctr, sizeof(SwCounters), cudaMemcpyDeviceToHost, stream));

@@ -62,6 +62,9 @@ struct SwStage {
     uint2 *d_dirs = nullptr;          // direction scratch: one uint2 per (strip, column, thread)
     size_t dirs_words = 0;
     uint32_t *d_list_big = nullptr;
+    uint32_t *d_list_sorted = nullptr; // d_list_fast ordered by (Lq, Lr)
+    uint32_t *d_sort_bins = nullptr;   // its counting-sort bins
+    size_t sort_bins_cap = 0;
     uint32_t *d_gw_scratch = nullptr; // slots of the warp-per-pair general kernel
     size_t gw_scratch_words = 0;
     uint8_t *d_gen_scratch = nullptr;
@@ -70,6 +73,7 @@ struct SwStage {
     size_t gen_off_cap = 0;
     int2 *d_gen_dims = nullptr;
     uint32_t launches = 0;
+    bool small = false;               // worker-sized batch: DP pairs go to the warp-per-pair kernel, fast tiers not launched
     unsigned long long sw_calls = 0, cells = 0, n_general = 0, shortcut_calls = 0, shortcut_cells = 0;
     int cfg_max_lq = -1, cfg_sms = 0, cfg_per_sm[3] = {0, 0, 0};   // launch configuration of the last run (host queries are not free)
     cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr;   // around sw_fast_kernel
@@ -83,6 +87,7 @@ int launch_sw_general_warp(const SwGwPlan &pl, const DevReads &R, const uint8_t 
                            uint32_t first, uint32_t *d_cursor, uint32_t *d_list_big, uint32_t *d_scratch, SwOut *d_out, SwCounters *d_ctr,
                            char *d_cig, uint32_t cig_cap, cudaStream_t stream);
 
+int sw_small_limit();
 int sw_stage_reserve(SwStage &st, uint32_t pairs);
 void sw_stage_free(SwStage &st);
 // The extension of pairs [0,*d_n): d_desc must be filled, d_out[k].status preset to BWT_HIT_WINDOW_OOR for pairs

@@ -19,16 +19,21 @@ from test_oracle_golden import (KAT_2_CIGARS, KAT_2_SGA, READ_KAT_1, READ_KAT_2,
                                 _rand_query, _rand_seq)
 
 
-@pytest.fixture(autouse=True, params=["shortcut", "dp_only"])
+@pytest.fixture(autouse=True, params=["shortcut", "dp_only", "small"])
 def sw_mode(request):
-    """Every test of this file runs twice: with the no-DP shortcut of sw_classify_kernel (perfect / one-mismatch
-    diagonals) and with BWT_SW_SHORTCUT=0, which sends those pairs through the DP kernels as well."""
+    """Every test of this file runs three times: with the no-DP shortcut of sw_classify_kernel / sw_wfa_kernel and the
+    packed-integer DP tiers behind it; with BWT_SW_SHORTCUT=0, which sends every pair through those DP kernels; and in
+    the routing of worker-sized batches (BWT_SW_SMALL: every pair that needs the table takes the warp-per-pair kernel
+    in doubles, the fast tiers are never launched), forced here for batches of any size."""
+    os.environ.pop("BWT_SW_SHORTCUT", None)
+    os.environ["BWT_SW_SMALL"] = "0"
     if request.param == "dp_only":
         os.environ["BWT_SW_SHORTCUT"] = "0"
-    else:
-        os.environ.pop("BWT_SW_SHORTCUT", None)
+    elif request.param == "small":
+        os.environ["BWT_SW_SMALL"] = "2000000000"
     yield request.param
     os.environ.pop("BWT_SW_SHORTCUT", None)
+    os.environ.pop("BWT_SW_SMALL", None)
 
 
 @pytest.fixture(scope="module")
@@ -315,7 +320,7 @@ def test_shortcut_is_taken_and_counted(gl_index, gl_ref, sw_mode):
     finally:
         b.close()
     assert s.sw_calls > 1000
-    if sw_mode == "shortcut":
+    if sw_mode in ("shortcut", "small"):
         assert 0.1 * s.sw_calls < s.sw_shortcut <= s.sw_calls and 0 < s.sw_shortcut_cells <= s.sw_cells
     else:
         assert s.sw_shortcut == 0 and s.sw_shortcut_cells == 0
@@ -532,9 +537,11 @@ def test_pipelined_aligner_equals_one_shot(gl_index, gl_ref, gl_coracle):
     al.close()
 
 
-def test_fast_kernels_take_plain_reads(gl_index, gl_ref):
+def test_fast_kernels_take_plain_reads(gl_index, gl_ref, sw_mode):
     """ACGT-only inputs must stay on the fast kernels (a silent detour through the double-precision kernel would
     still be correct, only slow): the work counters say which path ran."""
+    if sw_mode == "small":
+        pytest.skip("the small-batch routing sends DP pairs to the warp-per-pair kernel on purpose")
     reads, offs, _ = sample_reads_fast(np.frombuffer(gl_ref, np.uint8), 20000, 100, seed=3)
     b = api.Batch(gl_index, 20000, len(reads))
     b.upload(reads, offs)

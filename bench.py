@@ -487,7 +487,7 @@ def run_config3(a, env, api, ix, build_s):
     # -- untimed side measurements on rank 0: roofline denominators measured on this device, and the FM walk alone
     extra = {}
     if rank == 0 and not a.no_side:
-        extra["gather_gbs"] = api.peak_gather_gbs(dev, 8 << 30)          # random 32-byte sectors over 8 GiB
+        extra["gather_gbs"] = api.peak_gather_gbs(dev, 8 << 30)          # random 64-byte atoms over 8 GiB
         extra["dpx_gops"] = api.peak_dpx_gops(dev)
         # LF steps/s of bwa:find_seeds alone: 15-mers cut from the reads, 4^8 table only (every later step reads two
         # Occ sectors), the walk the deep tables replace in the aligned-reads path

@@ -57,7 +57,8 @@ class BwtStats(C.Structure):
 
 class BwtFsStats(C.Structure):
     _fields_ = [("queries", C.c_uint64), ("nodes", C.c_uint64), ("lf_steps", C.c_uint64), ("raw_hits", C.c_uint64),
-                ("seeds", C.c_uint64), ("spills", C.c_uint64), ("ms_kernel", C.c_float), ("launches", C.c_uint32)]
+                ("seeds", C.c_uint64), ("spills", C.c_uint64), ("ms_kernel", C.c_float), ("launches", C.c_uint32),
+                ("settled", C.c_uint64)]
 
 
 class BwtSampleOpts(C.Structure):
@@ -144,7 +145,7 @@ def lib():
             fn = getattr(L, name)          # AttributeError here = the .so does not export a declared symbol
             fn.restype = res
             fn.argtypes = args
-        if L.bwt_abi_version() != 3:
+        if L.bwt_abi_version() != 4:
             raise ImportError("bwt_b200: ABI version mismatch")
         _lib = L
     return _lib

@@ -47,7 +47,7 @@ constexpr int FS_MAX_Q = 1024 + FS_MAX_D; // Len + Defects characters staged per
 enum { OP_NONE = 0, OP_INS = 1, OP_DEL = 2 };
 
 struct FsCounters {
-    unsigned long long nodes, lf_steps, raw_hits, seeds, spills;
+    unsigned long long nodes, lf_steps, raw_hits, seeds, spills, settled;
     unsigned int next_query;
     unsigned int pad;
 };
@@ -106,11 +106,148 @@ __device__ uint32_t warp_sort_unique(uint32_t *v, uint32_t raw, int lane) {
     return kept;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Pigeonhole front end (Defects 1 or 2).  A pattern of gen_pattern/5 carries exactly Defects edits -- `_` elements and
+// dropped query characters -- so of Defects+1 equal pieces of the pattern at least one holds neither a `_` nor a drop
+// between two of its elements: that piece of a matching window is a verbatim copy of the query, Q[a+s, b+s) for the
+// piece [a, b) of the pattern and a shift s = drops - insertions in front of it, |s| <= Defects.  So instead of the
+// depth-first search, whose first ~14 steps branch into every 2-edit neighbour that still occurs in the text:
+//   * (Defects+1)(2 Defects+1) <= 15 EXACT backward searches, one per lane;
+//   * every occurrence names one candidate window, start = SA - a;
+//   * each distinct candidate is verified against the text by a bit-parallel run of the SAME state machine the
+//     depth-first search walks (states (diff = q-p, d, m) in one 64-bit word per pattern position).
+// The verified set is exactly the clause list's window set (complete by the pigeonhole argument, sound by the
+// verification).  Anything the front end does not cover falls back to the depth-first search of the same query: a
+// piece that occurs more than FS_PIG_WIDTH times (repeats), a candidate that touches a byte of the .ref outside ACGT
+// (the index holds a substituted letter there, fm_index.erl:131-137, which only the FM walk sees), more candidates
+// than the caller's scratch.  BWT_FS_PIGEON=0 switches it off (tests run both ways).
+// ---------------------------------------------------------------------------------------------------
+constexpr uint32_t FS_PIG_WIDTH = 32;
+
+// one candidate window W = text[s0, s0+len) against the patterns of (Q, len, D); D <= 2.  Mirrors fs_search_kernel's
+// transitions with the text character known instead of searched for.
+__device__ bool fs_verify_window(const uint8_t *__restrict__ W, const uint8_t *__restrict__ Q, const int len, const int D) {
+    const int DD = D + 1, NDI = 2 * D + 1;
+    auto bit = [&](int di, int d, int m) { return 1ull << ((di * DD + d) * DD + m); };
+    uint64_t S = 0;
+    for (int sft = 0; sft < NDI; sft++)
+        if (len - D + sft >= 0) S |= bit(sft, D, 0);                 // pattern ends after query character Len - D + sft
+    for (int p = len; p >= 1; p--) {
+        if (p < len) {                                              // drops (seeds.erl:60; not once the pattern is complete, guard :57)
+            for (int rep = 0; rep < D; rep++)
+                for (int di = 1; di < NDI; di++) {
+                    if (p + di - D < 1) continue;
+                    for (int d = 1; d <= D; d++)
+                        for (int m = 0; m <= D; m++)
+                            if (S & bit(di, d, m)) S |= bit(di - 1, d - 1, m);
+                }
+        }
+        const uint8_t t = W[p - 1];
+        uint64_t N = 0;
+        for (int di = 0; di < NDI; di++) {
+            const int q = p + di - D;
+            const bool hasq = q >= 1;
+            const uint8_t qch = hasq ? Q[q - 1] : (uint8_t)0;
+            const bool eq = hasq && qch == t && bwt_code(qch) >= 0;
+            for (int d = 0; d <= D; d++)
+                for (int m = 0; m <= D; m++) {
+                    if (!(S & bit(di, d, m))) continue;
+                    if (eq) N |= bit(di, d, m < D ? m + 1 : m);                       // match
+                    if (hasq && qch != t && d >= 1) N |= bit(di, d - 1, m);            // `_` in place of the query character
+                    if (d >= 1 && di + 1 < NDI) N |= bit(di + 1, d - 1, m);            // `_` inserted
+                }
+        }
+        S = N;
+        if (!S) return false;
+    }
+    for (int di = 0; di < NDI; di++) {
+        const int q = di - D;                                        // query characters left in front of the pattern
+        if (q < 0) continue;
+        for (int d = 0; d <= D; d++)
+            for (int m = 0; m <= D; m++)
+                if ((S & bit(di, d, m)) && q <= d && d - q <= m) return true;
+    }
+    return false;
+}
+
+// -> true: my_hits[0, *raw_out) holds the matching window starts (1-based, ascending, distinct).  false: run the search.
+__device__ bool fs_pigeonhole(const DevIndex &ix, const uint8_t *__restrict__ Q, const int8_t *qc, const int len, const int D,
+                              uint32_t *my_hits, const uint32_t cap, const int lane, uint32_t &raw_out,
+                              unsigned long long &c_lf, unsigned long long &c_nodes) {
+    const unsigned FULL = 0xFFFFFFFFu;
+    const int NDI = 2 * D + 1, nsearch = (D + 1) * NDI;
+    const uint32_t n_rows = ix.n;
+    // ---- exact search of one piece at one shift per lane ----
+    uint32_t lo = 0, hi = 0;
+    int a = 0;
+    if (lane < nsearch) {
+        const int j = lane / NDI, sft = lane % NDI - D;
+        a = (int)((long long)j * len / (D + 1));
+        const int b = (int)((long long)(j + 1) * len / (D + 1));
+        const int qa = a + sft, qb = b + sft;
+        if (qa >= 0 && qb <= len + D && b > a) {
+            lo = 0; hi = n_rows;
+            for (int x = qb - 1; x >= qa && lo < hi; x--) {
+                const int c = (int)qc[x];
+                if (c < 0) { hi = lo; break; }
+                uint32_t nlo, nhi;
+                lf_extend(ix, c, lo, hi, nlo, nhi);
+                lo = nlo; hi = nhi;
+                c_lf++;
+            }
+        }
+    }
+    const uint32_t width = hi > lo ? hi - lo : 0u;
+    if (__any_sync(FULL, width > FS_PIG_WIDTH)) return false;
+    uint32_t incl = width;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(FULL, incl, o);
+        if (lane >= o) incl += t;
+    }
+    const uint32_t total = __shfl_sync(FULL, incl, 31);
+    if (total == 0) { c_nodes += (lane == 0) ? nsearch : 0; raw_out = 0; return true; }
+    if (total > cap) return false;
+    const uint32_t n_text = n_rows - 1;                              // the text without its '$'
+    for (uint32_t r = 0; r < width; r++) {
+        const uint32_t t = __ldg(ix.sa + lo + r);
+        const bool inside = t >= (uint32_t)a && (uint64_t)(t - (uint32_t)a) + (uint32_t)len <= n_text;
+        my_hits[incl - width + r] = inside ? t - (uint32_t)a + 1u : 0xFFFFFFFFu;
+    }
+    __syncwarp();
+    uint32_t raw = warp_sort_unique(my_hits, total, lane);
+    __syncwarp();
+    if (raw && my_hits[raw - 1] == 0xFFFFFFFFu) raw--;               // the marker of the candidates that leave the text
+    // ---- verification, one candidate per lane; accepted starts compacted in place (reads run ahead of the writes) ----
+    uint32_t kept = 0;
+    bool dirty = false;
+    for (uint32_t base = 0; base < raw; base += 32) {
+        const uint32_t i = base + lane;
+        uint32_t v = 0;
+        bool ok = false;
+        if (i < raw) {
+            v = my_hits[i];
+            const int64_t pos = (int64_t)(v - 1u) + 200;             // padded .ref coordinate (worker_bwt.erl:53-55)
+            if (!ref_plain(ix.refx, pos, len)) dirty = true;
+            else ok = fs_verify_window(ix.ref + pos, Q, len, D);
+        }
+        __syncwarp();
+        const unsigned km = __ballot_sync(FULL, ok);
+        if (ok) my_hits[kept + __popc(km & ((1u << lane) - 1u))] = v;
+        kept += __popc(km);
+        __syncwarp();
+    }
+    if (__any_sync(FULL, dirty)) return false;
+    c_nodes += (lane == 0) ? raw + (uint32_t)nsearch : 0;      // piece searches + verified candidates
+    raw_out = kept;
+    return true;
+}
+
 __global__ void __launch_bounds__(FS_WARPS * 32) fs_search_kernel(DevIndex ix, const uint8_t *__restrict__ queries,
                                                                   const int64_t *__restrict__ offs, uint32_t n_queries,
                                                                   int len, int D, uint32_t *__restrict__ hits, uint32_t cap,
                                                                   uint32_t *__restrict__ n_seeds, int32_t *__restrict__ status,
-                                                                  uint4 *__restrict__ spill, int stack_cap, FsCounters *ctr) {
+                                                                  uint4 *__restrict__ spill, int stack_cap, FsCounters *ctr, int pigeon) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     FsShared &sh = *reinterpret_cast<FsShared *>(smem_raw);
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -118,7 +255,7 @@ __global__ void __launch_bounds__(FS_WARPS * 32) fs_search_kernel(DevIndex ix, c
     uint4 *stack = sh.stack[w];
     int8_t *qc = sh.q[w];
     uint4 *my_spill = spill + ((size_t)blockIdx.x * FS_WARPS + w) * FS_SPILL;
-    unsigned long long c_nodes = 0, c_lf = 0, c_raw = 0, c_seeds = 0, c_spills = 0;
+    unsigned long long c_nodes = 0, c_lf = 0, c_raw = 0, c_seeds = 0, c_spills = 0, c_settled = 0;
     const uint32_t n_rows = ix.n;
 
     for (;;) {
@@ -134,9 +271,15 @@ __global__ void __launch_bounds__(FS_WARPS * 32) fs_search_kernel(DevIndex ix, c
             continue;
         }
         for (int k = lane; k < len + D; k += 32) qc[k] = (int8_t)bwt_code(Q[k]);
+        __syncwarp();
         int top = 0, sp_top = 0;
+        uint32_t raw = 0;
+        bool overflow = false;
+        const bool settled = pigeon && ix.ref && ix.refx && D >= 1 && D <= 2 && len > D && fs_pigeonhole(ix, Q, qc, len, D, my_hits, cap, lane, raw, c_lf, c_nodes);
+        c_settled += (lane == 0 && settled) ? 1 : 0;
         // start states: the pattern ends after query character q_end = Len + (deletions - insertions)
-        {
+        if (!settled) {
+            raw = 0;
             const int qe = len - D + lane;
             const bool valid = lane <= 2 * D && qe >= 0;
             const unsigned vm = __ballot_sync(FULL, valid);
@@ -144,8 +287,6 @@ __global__ void __launch_bounds__(FS_WARPS * 32) fs_search_kernel(DevIndex ix, c
             top = __popc(vm);
         }
         __syncwarp();
-        uint32_t raw = 0;
-        bool overflow = false;
 
         while (top > 0 || sp_top > 0) {
             if (top == 0) {                                 // refill from the spill area
@@ -295,6 +436,7 @@ __global__ void __launch_bounds__(FS_WARPS * 32) fs_search_kernel(DevIndex ix, c
         atomicAdd(&ctr->raw_hits, c_raw);
         atomicAdd(&ctr->seeds, c_seeds);
         atomicAdd(&ctr->spills, c_spills);
+        atomicAdd(&ctr->settled, c_settled);
     }
 }
 
@@ -324,6 +466,8 @@ extern "C" int bwt_fs_find_seeds_batch(bwt_index *h, const uint8_t *queries, con
     if (max_raw_hits <= 0) max_raw_hits = 1024;
     int stack_cap = FS_STACK;                               // BWT_FS_STACK=32..384 shrinks the shared-memory stack (tests of the spill path)
     if (const char *e = getenv("BWT_FS_STACK")) { int v = atoi(e); if (v >= 32 && v <= FS_STACK) stack_cap = v; }
+    int pigeon = 1;                                         // BWT_FS_PIGEON=0: depth-first search for every query (A/B, tests of the search)
+    if (const char *e = getenv("BWT_FS_PIGEON")) pigeon = atoi(e) != 0;
     uint32_t hcap = 32;
     while (hcap < (uint32_t)max_raw_hits) hcap <<= 1;        // the sort pads to a power of two
     BWT_TRY(index_select_device(h->device));
@@ -391,7 +535,7 @@ extern "C" int bwt_fs_find_seeds_batch(bwt_index *h, const uint8_t *queries, con
             const unsigned grid = (unsigned)std::min<int64_t>((int64_t)dev_sms * per_sm, (m + FS_WARPS - 1) / FS_WARPS);
             cudaEventRecord(e0, stream);
             fs_search_kernel<<<grid, FS_WARPS * 32, smem, stream>>>(h->dv, d_q, d_offs, (uint32_t)m, len, defects, d_hits, hcap,
-                                                                    d_nseeds, d_status, d_spill, stack_cap, d_ctr);
+                                                                    d_nseeds, d_status, d_spill, stack_cap, d_ctr, pigeon);
             cudaEventRecord(e1, stream);
             launches++;
             { cudaError_t e = cudaGetLastError(); if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
@@ -401,7 +545,7 @@ extern "C" int bwt_fs_find_seeds_batch(bwt_index *h, const uint8_t *queries, con
             ms_total += ms;
             FsCounters c;
             cudaMemcpy(&c, d_ctr, sizeof c, cudaMemcpyDeviceToHost);
-            sum.nodes += c.nodes; sum.lf_steps += c.lf_steps; sum.raw_hits += c.raw_hits; sum.seeds += c.seeds; sum.spills += c.spills;
+            sum.nodes += c.nodes; sum.lf_steps += c.lf_steps; sum.raw_hits += c.raw_hits; sum.seeds += c.seeds; sum.spills += c.spills; sum.settled += c.settled;
             // offsets = exclusive scan of the per-query seed counts
             cudaMemcpyAsync(d_scan, d_nseeds, (size_t)m * 4, cudaMemcpyDeviceToDevice, stream);
             cudaMemsetAsync(d_scan + m, 0, 4, stream);
@@ -435,7 +579,7 @@ extern "C" int bwt_fs_find_seeds_batch(bwt_index *h, const uint8_t *queries, con
     *total = base;
     if (stats) {
         stats->queries = (uint64_t)n; stats->nodes = sum.nodes; stats->lf_steps = sum.lf_steps; stats->raw_hits = sum.raw_hits;
-        stats->seeds = sum.seeds; stats->spills = sum.spills; stats->ms_kernel = ms_total; stats->launches = launches;
+        stats->seeds = sum.seeds; stats->spills = sum.spills; stats->settled = sum.settled; stats->ms_kernel = ms_total; stats->launches = launches;
     }
     if (!space) { bwt_set_error("output capacity too small: need %lld seeds", (long long)base); return BWT_ERR_NOSPACE; }
     return BWT_OK;

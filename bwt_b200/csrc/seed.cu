@@ -425,6 +425,14 @@ __device__ __forceinline__ void sort_vote_regs(const Tile &tile, const uint32_t 
     }
 }
 
+// A miss of a plain load makes the L2 fetch the whole 128-byte line (ncu on scripts/probes/gather_probe.cu: 127-137 B of
+// DRAM per random 16/32-byte access); with the L2::64B prefetch-size qualifier it fetches 64 bytes (69 B per access).
+__device__ __forceinline__ uint4 ldg_l2_64(const uint4 *p) {
+    uint4 v;
+    asm volatile("ld.global.nc.L2::64B.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+
 // One plain read (packed words pkr, lq bases).  Per subsequence ONE lookup: the fused depth-15 entry (interval + its
 // first 14 SA values in one 64-byte line) when the subsequence has 15 characters or more, else the interval table of
 // exactly its depth (+ the suffix-array run).  The lane that looked a subsequence up writes its seed ends.
@@ -432,7 +440,8 @@ template <int G, int MAXT, typename Tile>
 __device__ __forceinline__ int sga_fast_read(const Tile &tile, const DevIndex &ix, const uint32_t *__restrict__ pkr, const int lq,
                                              const uint32_t read, uint32_t *seeds,
                                              int32_t *read_status, uint32_t *ncl, uint32_t *cl_base, Cluster *clusters,
-                                             const uint32_t cl_cap, SeedCounters *ctr, uint32_t (&acc)[CTR_N]) {
+                                             const uint32_t cl_cap, SeedCounters *ctr, uint32_t (&acc)[CTR_N], const bool hint64) {
+    constexpr int EPLMAX = G == 8 ? 16 : 8;                       // seed ends per lane the register sort takes: 128 per read either way
     const int lane = tile.thread_rank();
     const int nt = lq >= BWT_MIN_LEN ? (lq - BWT_MIN_LEN) / BWT_MIN_LEN + 1 : 0;
     uint32_t total = 0, qty = 0, lf = 0, hbm = 0;
@@ -447,7 +456,8 @@ __device__ __forceinline__ int sga_fast_read(const Tile &tile, const DevIndex &i
             const uint32_t idx = __funnelshift_r(__ldg(pkr + (k >> 1)), __ldg(pkr + (k >> 1) + 1), (k & 1) * 16) & 0x3FFFFFFFu;
             if (end >= BWT_MAX_LEN && ix.fused) {
                 e = ix.fused + 4 * (size_t)idx;
-                a = __ldg(e); b = __ldg(e + 1);
+                if (hint64) { a = ldg_l2_64(e); b = ldg_l2_64(e + 1); }   // one 64-byte entry: do not drag the 128-byte line in
+                else { a = __ldg(e); b = __ldg(e + 1); }
                 const uint32_t ne = a.y >> 28, w = a.y & KMER_W_MASK;
                 if (ne == 0) fb = true;                            // width beyond 28 bits: the general path walks it
                 else {
@@ -477,14 +487,14 @@ __device__ __forceinline__ int sga_fast_read(const Tile &tile, const DevIndex &i
         total += tile.shfl(inc, G - 1);
         qty += __popc(tile.ballot(cnt > 0));
         // seed ends = SA + N + the subsequence's shift (fmi.erl:89-100, sga.erl:37-39); beyond 8G the read leaves this path
-        if (cnt && pos + cnt <= (uint32_t)(8 * G)) {
+        if (cnt && pos + cnt <= (uint32_t)(EPLMAX * G)) {
             uint32_t t0 = 0;
             if (e) {
                 const uint32_t v[6] = {a.z, a.w, b.x, b.y, b.z, b.w};
 #pragma unroll
                 for (int t = 0; t < 6; t++) if ((uint32_t)t < cnt) seeds[pos + t] = v[t] + add;
                 if (cnt > 6) {
-                    const uint4 c = __ldg(e + 2), d = __ldg(e + 3);
+                    const uint4 c = hint64 ? ldg_l2_64(e + 2) : __ldg(e + 2), d = hint64 ? ldg_l2_64(e + 3) : __ldg(e + 3);
                     const uint32_t u[8] = {c.x, c.y, c.z, c.w, d.x, d.y, d.z, d.w};
 #pragma unroll
                     for (int t = 0; t < 8; t++) if ((uint32_t)(t + 6) < cnt) seeds[pos + 6 + t] = u[t] + add;
@@ -494,7 +504,7 @@ __device__ __forceinline__ int sga_fast_read(const Tile &tile, const DevIndex &i
             for (uint32_t t = t0; t < cnt; t++) seeds[pos + t] = __ldg(ix.sa + (sp - 1) + t) + add;
         }
     }
-    if (tile.any(fb) || total > (uint32_t)(8 * G)) return SGA_FALLBACK;   // the general path redoes (and counts) the searches (rare)
+    if (tile.any(fb) || total > (uint32_t)(EPLMAX * G)) return SGA_FALLBACK;   // the general path redoes (and counts) the searches (rare)
 #pragma unroll
     for (int d = G / 2; d > 0; d >>= 1) {
         lf += tile.shfl_down(lf, d);
@@ -513,16 +523,38 @@ __device__ __forceinline__ int sga_fast_read(const Tile &tile, const DevIndex &i
     if (total <= (uint32_t)G) sort_vote_regs<G, 1>(tile, seeds, total, need, read, ncl, cl_base, clusters, cl_cap, ctr, acc);
     else if (total <= (uint32_t)(2 * G)) sort_vote_regs<G, 2>(tile, seeds, total, need, read, ncl, cl_base, clusters, cl_cap, ctr, acc);
     else if (total <= (uint32_t)(4 * G)) sort_vote_regs<G, 4>(tile, seeds, total, need, read, ncl, cl_base, clusters, cl_cap, ctr, acc);
-    else sort_vote_regs<G, 8>(tile, seeds, total, need, read, ncl, cl_base, clusters, cl_cap, ctr, acc);
+    else if (EPLMAX == 8 || total <= (uint32_t)(8 * G)) sort_vote_regs<G, 8>(tile, seeds, total, need, read, ncl, cl_base, clusters, cl_cap, ctr, acc);
+    else sort_vote_regs<G, EPLMAX>(tile, seeds, total, need, read, ncl, cl_base, clusters, cl_cap, ctr, acc);
     tile.sync();
     return SGA_DONE;
+}
+
+// The fused entries of the group's NEXT read, asked into L2 while the current read is looked up, sorted and voted on:
+// a group otherwise has loads in flight only while it waits for its own 13 entries (~1 us) and none during the ~40 %
+// of its time it spends on the seed ends, and random access on this part is bound by the misses in flight, not by
+// DRAM bytes (scripts/probes/gather_probe.cu: 35-47 G random accesses/s whether a miss moves 64 or 128 bytes).
+// mode 1: prefetch.global.L2 (a 128-byte line), mode 2: cp.async.bulk.prefetch.L2 of exactly the 64-byte entry (a
+// warp-uniform instruction: the compiler loops over the lanes), mode 3: a discarded ld.global.nc.L2::64B.
+template <int G>
+__device__ __forceinline__ void sga_prefetch_next(const DevIndex &ix, const DevReads &R, const int64_t nxt, const int lane, const int mode) {
+    const int lq = (int)__ldg(R.len + nxt);
+    const uint32_t *pkr = R.pk + __ldg(R.woff + nxt);
+    const int nt = lq >= BWT_MIN_LEN ? (lq - BWT_MIN_LEN) / BWT_MIN_LEN + 1 : 0;
+    for (int k = lane; k < nt; k += G) {
+        if (lq - BWT_MIN_LEN * k < BWT_MAX_LEN) continue;              // the short front subsequence uses the small tables
+        const uint32_t idx = __funnelshift_r(__ldg(pkr + (k >> 1)), __ldg(pkr + (k >> 1) + 1), (k & 1) * 16) & 0x3FFFFFFFu;
+        const uint4 *e = ix.fused + 4 * (size_t)idx;
+        if (mode == 1) asm volatile("prefetch.global.L2 [%0];" :: "l"(e));
+        else if (mode == 3) asm volatile("{ .reg .b32 t; ld.global.nc.L2::64B.b32 t, [%0]; }" :: "l"(e));   // a load nobody waits for
+        else asm volatile("cp.async.bulk.prefetch.L2.global [%0], 64;" :: "l"(e) : "memory");
+    }
 }
 
 template <int G, int MAXT>
 __global__ void __launch_bounds__(SGA_BLOCK, SGA_MIN_BLOCKS) sga_kernel(DevIndex ix, DevReads R, int64_t n_reads,
                                                         int32_t *read_status, uint32_t *ncl, uint32_t *cl_base,
                                                         Cluster *clusters, uint32_t cl_cap, SlowRead *slow,
-                                                        uint32_t slow_cap, SeedCounters *ctr) {
+                                                        uint32_t slow_cap, SeedCounters *ctr, int prefetch) {
     constexpr int GPB = SGA_BLOCK / G;
     constexpr int CAP = 32 * G;
     __shared__ uint32_t s_seeds[GPB][CAP];
@@ -541,6 +573,8 @@ __global__ void __launch_bounds__(SGA_BLOCK, SGA_MIN_BLOCKS) sga_kernel(DevIndex
         const bool plain = !read_is_exc(R, (uint32_t)read);
         const uint8_t *q = nullptr;
         const uint32_t *pkr = nullptr;
+        if ((prefetch & 7) && ix.fused && read + (int64_t)gridDim.x * GPB < n_reads)
+            sga_prefetch_next<G>(ix, R, read + (int64_t)gridDim.x * GPB, (int)tile.thread_rank(), prefetch & 7);
         if (plain) pkr = R.pk + __ldg(R.woff + read);
         else q = read_ascii(R, (uint32_t)read, lq);
         // a read with more subsequences than MAXT cannot run in this instantiation: the launcher picks
@@ -552,7 +586,7 @@ __global__ void __launch_bounds__(SGA_BLOCK, SGA_MIN_BLOCKS) sga_kernel(DevIndex
         int how = SGA_FALLBACK;
         if (plain && lq <= BWT_MIN_LEN * (MAXT - 1) + BWT_MAX_LEN)
             how = sga_fast_read<G, MAXT>(tile, ix, pkr, lq, (uint32_t)read, s_seeds[g], read_status, ncl, cl_base,
-                                         clusters, cl_cap, ctr, acc);
+                                         clusters, cl_cap, ctr, acc, (prefetch & 8) != 0);
         if (how == SGA_FALLBACK)                                  // 'N' / other bytes, or more seed ends than registers hold
             sga_read<G, MAXT, false>(tile, ix, q, pkr, lq, (uint32_t)read, s_seeds[g], CAP, gs, read_status, ncl, cl_base,
                                      clusters, cl_cap, slow, slow_cap, ctr, s_ctr);
@@ -671,18 +705,22 @@ int launch_sga(const DevIndex &ix, const DevReads &R, int64_t n_reads, int max_r
             cudaFuncSetAttribute(sga_kernel<32, SGA_MAX_TASKS>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
         }
     }
+    // BWT_SGA_PREFETCH (default 8): +8 = fused entries loaded with the L2::64B qualifier (DRAM read 15.8 -> 8.8 GB per 10 M reads, time +-2 %);
+    // low bits: 0 off (default: measured 5-13 % slower with any of the modes), 1 prefetch.global.L2, 2 64-byte bulk prefetch, 3 discarded load
+    static int prefetch = -1;
+    if (prefetch < 0) { const char *e = getenv("BWT_SGA_PREFETCH"); prefetch = e && *e ? atoi(e) : 8; }
     // 16 lanes per read while every read has at most 16 subsequences (<= 135 bases), else a full warp
     if (max_read_len <= BWT_MIN_LEN * 15 + BWT_MAX_LEN) {
         int64_t blocks = (n_reads + 7) / 8;
         if (blocks > 148 * 256) blocks = 148 * 256;
         sga_kernel<16, 16><<<(unsigned)blocks, SGA_BLOCK, 0, stream>>>(ix, R, n_reads, d_read_status, d_ncl,
-                                                                     d_cl_base, d_clusters, cl_cap, d_slow, slow_cap, d_ctr);
+                                                                     d_cl_base, d_clusters, cl_cap, d_slow, slow_cap, d_ctr, prefetch);
     } else {
         int64_t blocks = (n_reads + 3) / 4;
         if (blocks > 148 * 256) blocks = 148 * 256;
         sga_kernel<32, SGA_MAX_TASKS><<<(unsigned)blocks, SGA_BLOCK, 0, stream>>>(ix, R, n_reads, d_read_status,
                                                                                d_ncl, d_cl_base, d_clusters, cl_cap, d_slow,
-                                                                               slow_cap, d_ctr);
+                                                                               slow_cap, d_ctr, prefetch);
     }
     K_CHECK(stream, "sga_kernel");
     return BWT_OK;

@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define BWT_B200_ABI_VERSION 3   /* 3: packed reads in, compact hits out, bwt_index_info.fused, bwt_sample_reads_edits */
+#define BWT_B200_ABI_VERSION 4   /* 3: packed reads in, compact hits out, bwt_index_info.fused, bwt_sample_reads_edits; 4: bwt_fs_stats.settled */
 
 typedef enum bwt_status {
     BWT_OK = 0,
@@ -311,6 +311,8 @@ typedef struct bwt_fs_stats {
                                                                     stack spills to HBM */
     float ms_kernel;         /* CUDA-event time of fs_search_kernel (all passes) */
     uint32_t launches;
+    uint64_t settled;        /* queries answered by the pigeonhole front end (exact piece searches + window verification)
+                                without the depth-first search; `nodes` counts their verified candidate windows */
 } bwt_fs_stats;
 
 /* For every query Qsec: the list fs:find_seeds(Ref_Seq) returns after seeds:generate_fs(Qsec, Len, Defects), with
@@ -319,7 +321,8 @@ typedef struct bwt_fs_stats {
  * character dropped; seeds.erl:51-62); the walk takes the leftmost matching window, jumps Len ahead, repeats
  * (seeds.erl:23-43).  seeds[seed_offsets[r] .. seed_offsets[r+1]) = 1-based window starts N of query r in DESCENDING
  * order, exactly the accumulator the Erlang function returns.  The patterns are never materialised: one warp per
- * query walks the recursion on the FM index (inexact.cu).  The index text is over ACGT (the builder maps IUPAC codes
+ * query either finds the windows from exact searches of pattern pieces and verifies them (Defects <= 2), or walks the
+ * recursion on the FM index (inexact.cu).  The index text is over ACGT (the builder maps IUPAC codes
  * as fm_index.erl:131-135), so a query character outside ACGT can only be covered by a defect.
  * max_raw_hits (<= 0: 1024): per-query scratch for matching windows before the greedy walk; BWT_FS_LIMIT once more
  * than half of it is taken by distinct windows.

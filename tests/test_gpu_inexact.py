@@ -19,6 +19,47 @@ from bwt_b200.synth import random_reference            # noqa: E402
 from conftest import GOLDEN                            # noqa: E402
 
 
+@pytest.fixture(autouse=True, params=["pigeonhole", "search_only"])
+def fs_mode(request):
+    """Every test runs twice: with the pigeonhole front end (exact piece searches + window verification, Defects <= 2,
+    falling back to the depth-first search where it does not apply) and with BWT_FS_PIGEON=0 (the search alone)."""
+    if request.param == "search_only":
+        os.environ["BWT_FS_PIGEON"] = "0"
+    else:
+        os.environ.pop("BWT_FS_PIGEON", None)
+    yield request.param
+    os.environ.pop("BWT_FS_PIGEON", None)
+
+
+def test_front_end_settles_and_falls_back(gl_ref, fs_mode):
+    """unique loci are settled by the front end, a tandem repeat hands the query to the search; same answers"""
+    rng = random.Random(9)
+    with api.Index.build(gl_ref, shift=1) as ix:
+        qs = []
+        for _ in range(200):
+            s = rng.randrange(0, len(gl_ref) - 110)
+            q = bytearray(gl_ref[s:s + 104])
+            if rng.random() < 0.5:
+                q[rng.randrange(100)] = rng.choice(b"ACGT")
+            if rng.random() < 0.3:
+                del q[rng.randrange(90)]
+            qs.append(bytes(q[:102]))
+        st, so, sd, stats = ix.fs_find_seeds(qs, None, 98, 2, 4096)
+        assert (st == api.FS_OK).all()
+        for got, q in zip(_split(so, sd), qs):
+            assert got == c_fs_scan_dp(q, 98, 2, gl_ref), q
+        if fs_mode == "pigeonhole":
+            assert 100 <= stats.settled <= 200
+        else:
+            assert stats.settled == 0
+    ref = b"ACGGT" * 400 + random_reference(500, 3)
+    with api.Index.build(ref, shift=1) as ix:
+        q = (b"ACGGT" * 30)[:62]
+        st, so, sd, stats = ix.fs_find_seeds([q], None, 60, 2, 1 << 14)
+        assert st.tolist() == [api.FS_OK] and stats.settled == 0        # every piece occurs hundreds of times
+        assert _split(so, sd)[0] == c_fs_scan_dp(q, 60, 2, ref)
+
+
 def _split(so, sd):
     return [sd[so[r]:so[r + 1]].tolist() for r in range(len(so) - 1)]
 
@@ -127,7 +168,7 @@ def test_stack_spill_and_many_hits():
         st, so, sd, stats = ix.fs_find_seeds([q], None, 60, 4, 1 << 16)
         assert st.tolist() == [api.FS_OK] and len(sd) == 0
         print("dead-end walk: nodes %d lf %d spills %d" % (stats.nodes, stats.lf_steps, stats.spills))
-        assert stats.nodes > 10000
+        assert stats.nodes > 10000                             # Defects = 4: the front end does not apply
         os.environ["BWT_FS_STACK"] = "32"                       # tiny shared-memory stack: the HBM spill path must run
         try:
             st2, so2, sd2, stats2 = ix.fs_find_seeds([q, b"AC" * 40], None, 60, 4, 1 << 16)

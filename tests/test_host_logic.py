@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
     L = _lib.lib()                                   # raises if a symbol is missing
     for n in names:
         assert getattr(L, n) is not None
-    assert L.bwt_abi_version() == 3
+    assert L.bwt_abi_version() == 4
 
 
 def test_struct_layouts_match_header():

@@ -515,7 +515,10 @@ def run_config3(a, env, api, ix, build_s):
                                 "occ_gbs": round(64.0 * fss.lf_steps / (fss.ms_kernel * 1e-3) / 1e9, 1),
                                 "frac_of_random_gather": round(64.0 * fss.lf_steps / (fss.ms_kernel * 1e-3) / 1e9 / extra["gather_gbs"], 4),
                                 "seeds_per_query": len(fsd) / mq, "limit_status": int((fst == api.FS_LIMIT).sum()),
-                                "note": "fs_search_kernel: warp-per-query DFS over gen_pattern/5 (seeds.erl:51-62), 64 B per LF step"}
+                                "settled_by_front_end": fss.settled / mq,
+                                "note": "fs_search_kernel: per query one warp; pigeonhole front end (15 exact piece searches + bit-parallel "
+                                        "window verification) with the depth-first search over gen_pattern/5 (seeds.erl:51-62) as fallback; "
+                                        "states = piece searches + verified windows (front end) or search states (fallback); 64 B per LF step"}
 
     batch = api.Batch(ix, n, read_bytes)
     batch.upload(reads, offs)
@@ -646,7 +649,7 @@ def run_config5(a, env, api, steps, warmup):
     gather_out = None
     t_total = ms_run = ms_gather = build_s = 0.0
     link_bytes = 0
-    fs = {"queries": 0, "kernel_ms": 0.0, "seeds": 0, "lf_steps": 0, "limit": 0}
+    fs = {"queries": 0, "kernel_ms": 0.0, "seeds": 0, "lf_steps": 0, "limit": 0, "settled": 0}
     part_hits = []
     for j in range(rounds):
         pidx = j * world + rank
@@ -683,13 +686,13 @@ def run_config5(a, env, api, steps, warmup):
         if mq > 0 and have:
             fst, fso, fsd, fss = px.fs_find_seeds(reads[:offs[mq]], offs[:mq + 1], 244, 2, 1024)
             fs["queries"] += mq; fs["kernel_ms"] += fss.ms_kernel; fs["seeds"] += len(fsd); fs["lf_steps"] += fss.lf_steps
-            fs["limit"] += int((fst == api.FS_LIMIT).sum())
+            fs["limit"] += int((fst == api.FS_LIMIT).sum()); fs["settled"] += int(fss.settled)
         batch.close()
         px.close()
     os.environ.pop("BWT_FUSED", None)
     comm.close()
     t_all, t_run, t_g, fs_ms = env.max_over_ranks([t_total, ms_run, ms_gather, fs["kernel_ms"]])
-    fsq, fsl, fss_, fslim = env.sum_over_ranks([fs["queries"], fs["lf_steps"], fs["seeds"], fs["limit"]])
+    fsq, fsl, fss_, fslim, fsset = env.sum_over_ranks([fs["queries"], fs["lf_steps"], fs["seeds"], fs["limit"], fs["settled"]])
     if rank != 0:
         return None
     return {"workload": "BASELINE.json configs[4]: %.3f Gbp synthetic reference in %d _pJ partitions (fm_index.erl:113-124), %d per rank; %d synthetic "
@@ -703,7 +706,7 @@ def run_config5(a, env, api, steps, warmup):
             "index_build_s_per_rank": round(build_s, 1),
             "inexact": {"len": 244, "defects": 2, "queries_x_partitions": fsq, "kernel_ms_max_rank": fs_ms,
                         "query_partition_searches_per_s": fsq / (fs_ms * 1e-3) if fs_ms else None,
-                        "seeds": fss_, "lf_steps": fsl, "limit_status": fslim,
+                        "seeds": fss_, "lf_steps": fsl, "limit_status": fslim, "settled_by_front_end": fsset / max(1, fsq),
                         "note": "fs_search_kernel per partition (seeds.erl:11-62 semantics, parity unpinned in the reference); seeds stay per partition"}}
 
 

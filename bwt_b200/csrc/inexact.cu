@@ -124,50 +124,69 @@ __device__ uint32_t warp_sort_unique(uint32_t *v, uint32_t raw, int lane) {
 // ---------------------------------------------------------------------------------------------------
 constexpr uint32_t FS_PIG_WIDTH = 32;
 
-// one candidate window W = text[s0, s0+len) against the patterns of (Q, len, D); D <= 2.  Mirrors fs_search_kernel's
-// transitions with the text character known instead of searched for.
-__device__ bool fs_verify_window(const uint8_t *__restrict__ W, const uint8_t *__restrict__ Q, const int len, const int D) {
-    const int DD = D + 1, NDI = 2 * D + 1;
-    auto bit = [&](int di, int d, int m) { return 1ull << ((di * DD + d) * DD + m); };
+// One candidate window W = text[s0, s0+len) against the patterns of (Q, len, D), D = 1 or 2: the transitions of
+// fs_search_kernel with the text character known instead of searched for, all states of one pattern position in ONE
+// 64-bit word.  State (diff = q - p + D in 0..2D, d defects left, m matches made, capped at D) sits at bit
+// (diff * (D+1) + d) * (D+1) + m, so every transition is a mask and a shift:
+//   match      (q >= 1, Q[q-1] = t)    m -> min(m+1, D)           bits with m < D move up one place
+//   `_` for the query character (Q[q-1] != t), d -> d-1           >> (D+1)
+//   `_` inserted: p-1 with the same q, diff+1, d-1                << (D+1)^2 - (D+1)
+//   drop (p < Len, q >= 1): diff-1, d-1                           >> (D+1)^2 + (D+1), repeated D times
+// accept at p = 0:  q <= d  and  d - q <= m.
+template <int D>
+__device__ bool fs_verify_window_t(const uint8_t *__restrict__ W, const uint8_t *__restrict__ Q, const int len) {
+    constexpr int DD = D + 1, NDI = 2 * D + 1, GRP = DD * DD;          // bits per diff group
+    constexpr uint64_t ONE = 1ull;
+    // masks over the whole word
+    uint64_t M_LT = 0, M_DGE1 = 0, M_DIGE1 = 0, M_DILT = 0, M_ACC = 0;
+#pragma unroll
+    for (int di = 0; di < NDI; di++)
+#pragma unroll
+        for (int d = 0; d <= D; d++)
+#pragma unroll
+            for (int m = 0; m <= D; m++) {
+                const uint64_t b = ONE << ((di * DD + d) * DD + m);
+                if (m < D) M_LT |= b;
+                if (d >= 1) M_DGE1 |= b;
+                if (di >= 1) M_DIGE1 |= b;
+                if (di + 1 < NDI) M_DILT |= b;
+                const int q = di - D;
+                if (q >= 0 && q <= d && d - q <= m) M_ACC |= b;
+            }
+    constexpr uint64_t GMASK = (ONE << GRP) - 1;
     uint64_t S = 0;
+#pragma unroll
     for (int sft = 0; sft < NDI; sft++)
-        if (len - D + sft >= 0) S |= bit(sft, D, 0);                 // pattern ends after query character Len - D + sft
+        if (len - D + sft >= 0) S |= ONE << ((sft * DD + D) * DD);    // pattern ends after query character Len - D + sft; d = D, m = 0
     for (int p = len; p >= 1; p--) {
-        if (p < len) {                                              // drops (seeds.erl:60; not once the pattern is complete, guard :57)
-            for (int rep = 0; rep < D; rep++)
-                for (int di = 1; di < NDI; di++) {
-                    if (p + di - D < 1) continue;
-                    for (int d = 1; d <= D; d++)
-                        for (int m = 0; m <= D; m++)
-                            if (S & bit(di, d, m)) S |= bit(di - 1, d - 1, m);
-                }
-        }
+        // per diff group: does query character q = p + di - D exist, and does it equal the text character?
         const uint8_t t = W[p - 1];
-        uint64_t N = 0;
+        uint64_t HASQ = 0, EQ = 0;
+#pragma unroll
         for (int di = 0; di < NDI; di++) {
             const int q = p + di - D;
-            const bool hasq = q >= 1;
-            const uint8_t qch = hasq ? Q[q - 1] : (uint8_t)0;
-            const bool eq = hasq && qch == t && bwt_code(qch) >= 0;
-            for (int d = 0; d <= D; d++)
-                for (int m = 0; m <= D; m++) {
-                    if (!(S & bit(di, d, m))) continue;
-                    if (eq) N |= bit(di, d, m < D ? m + 1 : m);                       // match
-                    if (hasq && qch != t && d >= 1) N |= bit(di, d - 1, m);            // `_` in place of the query character
-                    if (d >= 1 && di + 1 < NDI) N |= bit(di + 1, d - 1, m);            // `_` inserted
-                }
+            if (q >= 1) {
+                HASQ |= GMASK << (di * GRP);
+                const uint8_t qch = Q[q - 1];
+                if (qch == t && bwt_code(qch) >= 0) EQ |= GMASK << (di * GRP);
+            }
         }
+        if (p < len) {
+#pragma unroll
+            for (int rep = 0; rep < D; rep++) S |= (S & M_DGE1 & M_DIGE1 & HASQ) >> (GRP + DD);
+        }
+        const uint64_t Sm = S & EQ;
+        uint64_t N = ((Sm & M_LT) << 1) | (Sm & ~M_LT);                 // match
+        N |= (S & HASQ & ~EQ & M_DGE1) >> DD;                           // `_` in place of the query character
+        N |= (S & M_DGE1 & M_DILT) << (GRP - DD);                       // `_` inserted
         S = N;
         if (!S) return false;
     }
-    for (int di = 0; di < NDI; di++) {
-        const int q = di - D;                                        // query characters left in front of the pattern
-        if (q < 0) continue;
-        for (int d = 0; d <= D; d++)
-            for (int m = 0; m <= D; m++)
-                if ((S & bit(di, d, m)) && q <= d && d - q <= m) return true;
-    }
-    return false;
+    return (S & M_ACC) != 0;
+}
+
+__device__ __forceinline__ bool fs_verify_window(const uint8_t *__restrict__ W, const uint8_t *__restrict__ Q, const int len, const int D) {
+    return D == 1 ? fs_verify_window_t<1>(W, Q, len) : fs_verify_window_t<2>(W, Q, len);
 }
 
 // -> true: my_hits[0, *raw_out) holds the matching window starts (1-based, ascending, distinct).  false: run the search.

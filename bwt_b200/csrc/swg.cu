@@ -15,6 +15,9 @@
 namespace {
 
 constexpr int GW_WARPS = 4;                 // warps (= pairs in flight) per block
+#ifndef GW_MIN_BLOCKS
+#define GW_MIN_BLOCKS 4                     // resident CTAs per SM the register allocation aims at
+#endif
 constexpr int GW_MAX_WC = 64;               // columns per lane at most: windows up to 2048 bases
 
 __device__ __forceinline__ double sigma_gw(uint8_t q, uint8_t r) {      // sw.erl:164-202, first clause wins
@@ -41,7 +44,7 @@ __host__ __device__ inline uint64_t gw_slot_words(int lq, int lr) {
     return (uint64_t)(lq + 32) * 32 * nw + (uint64_t)lq + lr + 4;
 }
 
-__global__ void __launch_bounds__(GW_WARPS * 32) sw_general_warp_kernel(DevReads R, const uint8_t *__restrict__ rbase,
+__global__ void __launch_bounds__(GW_WARPS * 32, GW_MIN_BLOCKS) sw_general_warp_kernel(DevReads R, const uint8_t *__restrict__ rbase,
                                                                         const SwDesc *__restrict__ desc, const uint32_t *__restrict__ list,
                                                                         uint32_t first, uint32_t *cursor, uint32_t *__restrict__ list_big,
                                                                         uint32_t *scratch, uint64_t slot_words, int wc_cap,
@@ -210,7 +213,7 @@ int sw_general_warp_plan(int max_lq, int sms, SwGwPlan *pl) {
     pl->wc_cap = (lr_cap + 31) / 32;
     pl->slot_words = (gw_slot_words(lq, pl->wc_cap * 32) + 31) & ~31ull;
     pl->smem = (size_t)GW_WARPS * pl->wc_cap * 32 * (sizeof(double) + 1);
-    pl->blocks = sms * 4;
+    pl->blocks = sms * GW_MIN_BLOCKS;
     pl->scratch_words = (uint64_t)pl->blocks * GW_WARPS * pl->slot_words;
     return BWT_OK;
 }

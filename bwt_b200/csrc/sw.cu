@@ -448,6 +448,23 @@ struct SwFastParams {
     int max_strips;
 };
 
+// (a & 0x00080008) | c in ONE LOP3: the instruction takes a single immediate, so c must sit in a register -- and the
+// compiler, which knows it is a constant, would rather spend a second LOP3 than a register; sw_opaque hides the value.
+// The DP loop is bound by the ALU pipe (77 % of its peak), where LOP3 / PRMT / VIADDMNMX / VIMNMX issue at half the rate
+// of the FMA pipe's IMAD: every LOP3 saved per cell is ~8 % of the kernel.
+__device__ __forceinline__ uint32_t sw_opaque(uint32_t v) { uint32_t r; asm volatile("mov.b32 %0, %1;" : "=r"(r) : "r"(v)); return r; }
+__device__ __forceinline__ uint32_t and8_or(uint32_t a, uint32_t c) {
+    uint32_t d;
+    asm("lop3.b32 %0, %1, 0x00080008, %2, 0xEA;" : "=r"(d) : "r"(a), "r"(c));
+    return d;
+}
+// a * b + c on the FMA pipe (mad.lo): the direction codes (K - m) << 3r are accumulated as K * 2^3r - m * 2^3r
+__device__ __forceinline__ uint32_t mad_lo(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t d;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+
 struct StripState {
     uint32_t mleft[SW_R];     // m(i, j-1) of both pairs
     uint32_t left15[SW_R];    // left candidate key for column j: m(i,j-1) + 8*[left] - 15
@@ -467,6 +484,7 @@ __device__ __forceinline__ void sw_cols(std::conditional_t<DELTA, uint16_t, uint
     const uint32_t live = CAPPED ? (((capv & 0xFFFFu) == 0x7FFFu ? 0xFFFFu : 0u) | ((capv >> 16) == 0x7FFFu ? 0xFFFF0000u : 0u)) : 0xFFFFFFFFu;
     uint32_t rwA = refw[(2 * ((j_from - 1) >> 4)) * B] >> (2 * ((j_from - 1) & 15));
     uint32_t rwB = refw[(2 * ((j_from - 1) >> 4) + 1) * B] >> (2 * ((j_from - 1) & 15));
+    const uint32_t c_up = sw_opaque(0xFFF2FFF2u), c_left = sw_opaque(0xFFF1FFF1u);
     for (int j = j_from; j <= j_to; j++) {
         if (((j - 1) & 15) == 0) { rwA = refw[(2 * ((j - 1) >> 4)) * B]; rwB = refw[(2 * ((j - 1) >> 4) + 1) * B]; }
         // PRMT selector: lane A = byte cA of profA sign-extended, lane B = byte cB of profB sign-extended
@@ -478,7 +496,7 @@ __device__ __forceinline__ void sw_cols(std::conditional_t<DELTA, uint16_t, uint
         const uint32_t mD_top = kt_prev & 0xFFF8FFF8u;                 // m(i0-1, j-1)
         kt_prev = kt;
         uint32_t mup = mT;
-        uint32_t tup = (((kt & 0x00020002u) * 4u)) | 0xFFF2FFF2u;      // 8*[up] - 14 per lane
+        uint32_t tup = and8_or(kt * 4u, c_up);                         // 8*[up] - 14 per lane
         uint32_t mdiag = mD_top;
         uint32_t acc_lo = 0, acc_hi = 0, K = 0;
 #pragma unroll
@@ -488,14 +506,15 @@ __device__ __forceinline__ void sw_cols(std::conditional_t<DELTA, uint16_t, uint
             K = __viaddmax_s16x2(mup, tup, x);                          // max(up, .)
             if (MASKED) K &= (r >= rminA ? 0x0000FFFFu : 0u) | (r >= rminB ? 0xFFFF0000u : 0u);
             mdiag = S.mleft[r];
-            const uint32_t t7 = K & 0x00070007u;
             const uint32_t m = K & 0xFFF8FFF8u;
             S.mleft[r] = m;
-            S.left15[r] = __vadd2(m, ((t7 * 8u) & 0x00080008u) | 0xFFF1FFF1u);
+            S.left15[r] = __vadd2(m, and8_or(K * 8u, c_left));          // m + 8*[left] - 15
             mup = m;
-            tup = ((t7 * 4u) & 0x00080008u) | 0xFFF2FFF2u;
+            tup = and8_or(K * 4u, c_up);
             S.mx[r] = __vmaxs2(S.mx[r], CAPPED ? __vmins2(K, capv) : K);
-            if (r < 5) acc_lo += t7 << (3 * r); else acc_hi += t7 << (3 * (r - 5));
+            // the cell's 3-bit direction code K - m at bits 3r of the strip's word
+            if (r < 5) { acc_lo = mad_lo(K, 1u << (3 * r), acc_lo); acc_lo = mad_lo(m, 0u - (1u << (3 * r)), acc_lo); }
+            else { acc_hi = mad_lo(K, 1u << (3 * (r - 5)), acc_hi); acc_hi = mad_lo(m, 0u - (1u << (3 * (r - 5))), acc_hi); }
         }
         if (DELTA) {
             const uint32_t dk = __vsub2(K, kl_prev);

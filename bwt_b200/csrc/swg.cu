@@ -16,7 +16,8 @@ namespace {
 
 constexpr int GW_WARPS = 4;                 // warps (= pairs in flight) per block
 #ifndef GW_MIN_BLOCKS
-#define GW_MIN_BLOCKS 4                     // resident CTAs per SM the register allocation aims at
+#define GW_MIN_BLOCKS 8                     // resident CTAs per SM the register allocation aims at: 64 registers, 32 pairs in flight per SM
+                                            // (the kernel is latency-bound: 0.093 -> 0.064 us per pair against 4 CTAs x 86 registers; 12 CTAs spill: 0.076)
 #endif
 constexpr int GW_MAX_WC = 64;               // columns per lane at most: windows up to 2048 bases
 

@@ -473,7 +473,8 @@ struct StripState {
 
 // columns j_from..j_to of one strip.  CAPPED: a pair whose window ended before this column keeps computing (its lane
 // is garbage from here on) but must not raise its row maxima: its keys are clamped to -32768 for the maximum.
-template <bool MASKED, bool CAPPED, bool DELTA>
+// TRACK = false: only the strip's last row keeps its running maximum (see the row-threshold note in sw_fast_kernel).
+template <bool MASKED, bool CAPPED, bool DELTA, bool TRACK>
 __device__ __forceinline__ void sw_cols(std::conditional_t<DELTA, uint16_t, uint32_t> *__restrict__ row, const uint32_t *__restrict__ refw,
                                         uint2 *__restrict__ dstrip, const int j_from, const int j_to, const int rminA, const int rminB,
                                         const uint32_t capv, const uint32_t (&profA)[SW_R], const uint32_t (&profB)[SW_R],
@@ -511,7 +512,7 @@ __device__ __forceinline__ void sw_cols(std::conditional_t<DELTA, uint16_t, uint
             S.left15[r] = __vadd2(m, and8_or(K * 8u, c_left));          // m + 8*[left] - 15
             mup = m;
             tup = and8_or(K * 4u, c_up);
-            S.mx[r] = __vmaxs2(S.mx[r], CAPPED ? __vmins2(K, capv) : K);
+            if (TRACK || r == SW_R - 1) S.mx[r] = __vmaxs2(S.mx[r], CAPPED ? __vmins2(K, capv) : K);
             // the cell's 3-bit direction code K - m at bits 3r of the strip's word
             if (r < 5) { acc_lo = mad_lo(K, 1u << (3 * r), acc_lo); acc_lo = mad_lo(m, 0u - (1u << (3 * r)), acc_lo); }
             else { acc_hi = mad_lo(K, 1u << (3 * (r - 5)), acc_hi); acc_hi = mad_lo(m, 0u - (1u << (3 * (r - 5))), acc_hi); }
@@ -532,7 +533,7 @@ __device__ __forceinline__ void sw_cols(std::conditional_t<DELTA, uint16_t, uint
 // The two pairs of a thread may have different query lengths: both are aligned at their LAST row, so lane X's row r of
 // this strip is query row i0X + r, and rows <= 0 (only in the first strips, more of them for the shorter query) act as
 // row 0 of the table.
-template <bool MASKED, bool DELTA>
+template <bool MASKED, bool DELTA, bool TRACK>
 __device__ __forceinline__ void sw_strip(std::conditional_t<DELTA, uint16_t, uint32_t> *__restrict__ row, const uint32_t *__restrict__ refw,
                                          uint2 *__restrict__ dstrip, const int lr_min, const int lr_max, const uint32_t capv,
                                          const int i0A, const int i0B, const uint32_t (&profA)[SW_R], const uint32_t (&profB)[SW_R],
@@ -549,8 +550,8 @@ __device__ __forceinline__ void sw_strip(std::conditional_t<DELTA, uint16_t, uin
     }
     uint32_t kt_prev = pack2(col0(i0A - 1), col0(i0B - 1));              // K(i0-1, 0): column 0 is known in closed form
     uint32_t kl_prev = pack2(col0(i0A + SW_R - 1), col0(i0B + SW_R - 1));    // K(last row of the strip, 0)
-    sw_cols<MASKED, false, DELTA>(row, refw, dstrip, 1, lr_min, rminA, rminB, 0u, profA, profB, S, kt_prev, kl_prev, ovf);
-    sw_cols<MASKED, true, DELTA>(row, refw, dstrip, lr_min + 1, lr_max, rminA, rminB, capv, profA, profB, S, kt_prev, kl_prev, ovf);
+    sw_cols<MASKED, false, DELTA, TRACK>(row, refw, dstrip, 1, lr_min, rminA, rminB, 0u, profA, profB, S, kt_prev, kl_prev, ovf);
+    sw_cols<MASKED, true, DELTA, TRACK>(row, refw, dstrip, lr_min + 1, lr_max, rminA, rminB, capv, profA, profB, S, kt_prev, kl_prev, ovf);
 }
 
 // traceback of one lane (sw.erl:116-160) + CIGAR text; returns false when the run buffer overflowed.
@@ -673,6 +674,7 @@ __global__ void __launch_bounds__(SW_BLOCK) sw_fast_kernel(SwFastParams p) {
         int rowsA = lqA, rowsB = lqB;
         bool failA = false, failB = false;
         StripState S;
+        int slackA = 0, slackB = 0;                                  // Vmax - threshold at the last row of the previous strip
         uint32_t ovf = 0;                                            // per lane: a boundary-row difference left int8
         for (int s = 0; s < nstr; s++) {
             const int i0A = ifA + s * R, i0B = ifB + s * R;
@@ -686,16 +688,27 @@ __global__ void __launch_bounds__(SW_BLOCK) sw_fast_kernel(SwFastParams p) {
                 profB[r] = 0xFCFCFCFCu ^ (0xE8u << (8 * qb));
             }
             uint2 *dstrip = dirs + (size_t)s * p.cap_cols * B;
-            if (i0A < 1 || i0B < 1) sw_strip<true, DELTA>(row, refw, dstrip, lr_min, lr_max, capv, i0A, i0B, profA, profB, S, ovf);
-            else sw_strip<false, DELTA>(row, refw, dstrip, lr_min, lr_max, capv, i0A, i0B, profA, profB, S, ovf);
-            // row threshold (sw.erl:69-71): Vmax of row i must reach thr0 + 2*i
+            // Row threshold (sw.erl:69-71): Vmax of row i must reach thr0 + 2*i.  A row's maximum is at most 2 below the
+            // maximum of the row above (the `up` candidate of the cell under the best cell costs -1 or -2, sw.erl:105-106)
+            // and the threshold rises by 2 per row, so the slack Vmax(i) - thr(i) falls by at most 4 per row: when both
+            // pairs left the previous strip with a slack of 4*R or more, no row of this strip can fail, and the ten
+            // VIMNMX per column that keep the rows' maxima shrink to the one of the strip's last row.
+            const bool light = i0A >= 1 && i0B >= 1 && slackA >= 4 * R && slackB >= 4 * R;
+            if (i0A < 1 || i0B < 1) sw_strip<true, DELTA, true>(row, refw, dstrip, lr_min, lr_max, capv, i0A, i0B, profA, profB, S, ovf);
+            else if (light) sw_strip<false, DELTA, false>(row, refw, dstrip, lr_min, lr_max, capv, i0A, i0B, profA, profB, S, ovf);
+            else sw_strip<false, DELTA, true>(row, refw, dstrip, lr_min, lr_max, capv, i0A, i0B, profA, profB, S, ovf);
+            if (!light) {
 #pragma unroll
-            for (int r = 0; r < R; r++) {
-                const int iA = i0A + r, iB = i0B + r;
-                if (iA >= 1 && !failA && (lane16(S.mx[r], 0) >> 3) < thrA + 2 * iA) { failA = true; rowsA = iA; }
-                if (iB >= 1 && !failB && (lane16(S.mx[r], 1) >> 3) < thrB + 2 * iB) { failB = true; rowsB = iB; }
+                for (int r = 0; r < R; r++) {
+                    const int iA = i0A + r, iB = i0B + r;
+                    if (iA >= 1 && !failA && (lane16(S.mx[r], 0) >> 3) < thrA + 2 * iA) { failA = true; rowsA = iA; }
+                    if (iB >= 1 && !failB && (lane16(S.mx[r], 1) >> 3) < thrB + 2 * iB) { failB = true; rowsB = iB; }
+                }
             }
             if (failA && failB) break;
+            // a failed pair keeps the other one going at full tracking cost or not at all: its own slack no longer matters
+            slackA = failA ? 0x7FFF : (lane16(S.mx[R - 1], 0) >> 3) - (thrA + 2 * (i0A + R - 1));
+            slackB = failB ? 0x7FFF : (lane16(S.mx[R - 1], 1) >> 3) - (thrB + 2 * (i0B + R - 1));
         }
         // a pair whose boundary row could not be difference-coded is redone with absolute rows (rare: it takes
         // a gap run of a dozen bases right next to a high-scoring path)

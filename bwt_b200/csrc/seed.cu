@@ -11,7 +11,9 @@ namespace {
 
 constexpr int SGA_BLOCK = 128;
 #ifndef SGA_MIN_BLOCKS
-#define SGA_MIN_BLOCKS 8       // resident CTAs per SM the register allocation aims at (8 x 128 threads x 64 registers)
+#define SGA_MIN_BLOCKS 10      // resident CTAs per SM the register allocation of the 16-lane kernel aims at: 51 registers, 40 warps per
+                               // SM (7.72 -> 7.21 ms per 10 M reads against 8 CTAs x 64 registers; 12 would spill: 7.49 ms).  The
+                               // 32-lane kernel's shared memory allows 8.
 #endif
 
 enum { CTR_SEARCHES = 0, CTR_LF, CTR_HBM_LF, CTR_LOCATED, CTR_CLUSTERS, CTR_N };
@@ -551,7 +553,7 @@ __device__ __forceinline__ void sga_prefetch_next(const DevIndex &ix, const DevR
 }
 
 template <int G, int MAXT>
-__global__ void __launch_bounds__(SGA_BLOCK, SGA_MIN_BLOCKS) sga_kernel(DevIndex ix, DevReads R, int64_t n_reads,
+__global__ void __launch_bounds__(SGA_BLOCK, G == 16 ? SGA_MIN_BLOCKS : 8) sga_kernel(DevIndex ix, DevReads R, int64_t n_reads,
                                                         int32_t *read_status, uint32_t *ncl, uint32_t *cl_base,
                                                         Cluster *clusters, uint32_t cl_cap, SlowRead *slow,
                                                         uint32_t slow_cap, SeedCounters *ctr, int prefetch) {

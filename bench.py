@@ -63,7 +63,7 @@ def parse():
     ap.add_argument("--no-side", action="store_true", help="skip the untimed peak / LF-walk side measurements")
     ap.add_argument("--no-legs", action="store_true", help="skip the config4 / config5 / config1 / n_reads legs")
     ap.add_argument("--chunk-reads", type=int, default=1 << 20, help="reads per pipelined chunk of the e2e leg")
-    ap.add_argument("--depth", type=int, default=3, help="chunks in flight in the e2e leg")
+    ap.add_argument("--depth", type=int, default=4, help="chunks in flight in the e2e leg (sweep in profiles/r2t_e2e_sweep.log: 4 beats 3 by ~4 %)")
     ap.add_argument("--inexact-queries", type=int, default=50_000, help="queries of the untimed bounded-edit side leg (0 = skip)")
     ap.add_argument("--c4-reads", type=int, default=80_000_000, help="config 4: reads in total (sharded over the ranks)")
     ap.add_argument("--c5-reads", type=int, default=2_000_000, help="config 5: reads (every partition sees all of them)")
@@ -459,7 +459,14 @@ def roofline_objects(a, K, t_ev, agg, read_bytes, cig_bytes, extra):
                 "algorithmic_bytes_per_launch": sga_bytes / K,
                 "traffic": tr_sga["dram_bytes_per_launch"] if tr_sga else None,
                 "random_gather_peak_gbs": extra.get("gather_gbs"),
-                "frac_of_random_gather": round(sga_gbs / extra["gather_gbs"], 4) if extra.get("gather_gbs") else None}
+                "frac_of_random_gather": round(sga_gbs / extra["gather_gbs"], 4) if extra.get("gather_gbs") else None,
+                # the ceiling that applies: random ACCESSES per second -- one per table lookup
+                "lookups_per_s": agg["searches"] / (agg["ms_sga"] * 1e-3) if agg["ms_sga"] else None,
+                "random_access_peak_per_s": extra["gather_gbs"] * 1e9 / 32 if extra.get("gather_gbs") else None,
+                "frac_of_random_access_peak": round(agg["searches"] / (agg["ms_sga"] * 1e-3) / (extra["gather_gbs"] * 1e9 / 32), 4)
+                if extra.get("gather_gbs") and agg["ms_sga"] else None,
+                "note": "random access on this part is bound by accesses in flight, not bytes: the peak is the measured rate of random "
+                        "32-byte sector reads (two 16-byte loads each, L2::64B, as the kernel issues them); the kernel also sorts and votes"}
     return roof, roof_alu, roof_sga, gcups
 
 
@@ -487,7 +494,7 @@ def run_config3(a, env, api, ix, build_s):
     # -- untimed side measurements on rank 0: roofline denominators measured on this device, and the FM walk alone
     extra = {}
     if rank == 0 and not a.no_side:
-        extra["gather_gbs"] = api.peak_gather_gbs(dev, 8 << 30)          # random 64-byte atoms over 8 GiB
+        extra["gather_gbs"] = api.peak_gather_gbs(dev, 8 << 30)          # random 32-byte sectors over 8 GiB (accesses/s x 32 B)
         extra["dpx_gops"] = api.peak_dpx_gops(dev)
         # LF steps/s of bwa:find_seeds alone: 15-mers cut from the reads, 4^8 table only (every later step reads two
         # Occ sectors), the walk the deep tables replace in the aligned-reads path
@@ -501,8 +508,12 @@ def run_config3(a, env, api, ix, build_s):
         extra["lf_walk"] = {"subsequences": m, "lf_steps_per_s": lf * 3 / (ms * 1e-3), "occ_steps_per_s": hbm_lf * 3 / (ms * 1e-3),
                             "achieved_gbs": round(gbs, 1), "frac_of_hbm_copy_peak": round(gbs / load_peaks()[0], 4),
                             "frac_of_random_gather": round(gbs / extra["gather_gbs"], 4), "kmer_depth": 8,
+                            "occ_sector_reads_per_s": 2 * hbm_lf * 3 / (ms * 1e-3),
+                            "frac_of_random_access_peak": round(2 * hbm_lf * 3 / (ms * 1e-3) / (extra["gather_gbs"] * 1e9 / 32), 4),
                             "note": "BASELINE's 'FM LF-steps/s vs HBM roofline': search_kernel on 15-mers with the 4^8 table only, "
-                                    "64 B (two Occ sectors) per step beyond it"}
+                                    "64 B (two Occ sectors) per step beyond it; the ratio to the random-access peak can exceed 1: the first "
+                                    "two levels below the table (16 + 64 MB of Occ blocks) are L2-resident and both bounds of a narrow "
+                                    "interval share a sector"}
         # the bounded-edit search of seeds.erl (row A9/F4) on the same index: Defects = 2 on a sample of the reads
         mq = min(n, a.inexact_queries)
         if mq > 0:

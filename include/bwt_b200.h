@@ -379,7 +379,8 @@ int bwt_sample_reads_edits(const bwt_index *h, const bwt_sample_opts *o, uint8_t
                            int64_t *offsets_out, int64_t *starts_out, int64_t *total_bytes);
 
 /* Microbenchmarks that give the roofline denominators measured on the device at hand:
- * random 32-byte-sector gather bandwidth (GB/s) and DPX (VIADDMNMX/VIMNMX3) issue rate (Gop/s). */
+ * random 32-byte-sector gather (two 16-byte loads per sector, L2::64B; GB/s = accesses/s x 32 B) and DPX
+ * (VIADDMNMX/VIMNMX3) issue rate (Gop/s). */
 int bwt_peak_gather_gbs(int device, uint64_t bytes, double *gbs);
 int bwt_peak_dpx_gops(int device, double *gops);
 

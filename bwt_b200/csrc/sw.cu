@@ -765,7 +765,7 @@ __global__ void __launch_bounds__(SW_BLOCK) sw_fast_kernel(SwFastParams p) {
 constexpr uint32_t SW_SORT_LR = 512;          // window lengths per query length (the fast tiers end at 384 columns)
 __device__ __forceinline__ uint32_t sw_shape_key(const SwDesc &d, uint32_t nbins) {
     const uint32_t k = (uint32_t)d.lq * SW_SORT_LR + min((uint32_t)d.lr, SW_SORT_LR - 1u);
-    return min(k, nbins - 1u);
+    return nbins - 1u - min(k, nbins - 1u);        // largest tables first: the kernel's last, partly filled wave is then made of the cheapest pairs
 }
 
 __global__ void __launch_bounds__(256) sw_shape_hist_kernel(const SwDesc *__restrict__ desc, const uint32_t *__restrict__ list,
@@ -959,8 +959,8 @@ int grow(T *&p, size_t &cap_items, size_t need_items) {
 int sw_stage_reserve(SwStage &st, uint32_t pairs) {
     if (pairs <= st.cap && st.d_desc) return BWT_OK;
     uint32_t want = pairs + pairs / 4 + 1024;
-    if (st.d_desc) { cudaFree(st.d_desc); cudaFree(st.d_out); cudaFree(st.d_list_fast); cudaFree(st.d_list_wide); cudaFree(st.d_list_gen); cudaFree(st.d_list_ovf); cudaFree(st.d_list_wfa); cudaFree(st.d_list_big); cudaFree(st.d_list_sorted); }
-    st.d_list_sorted = nullptr;
+    if (st.d_desc) { cudaFree(st.d_desc); cudaFree(st.d_out); cudaFree(st.d_list_fast); cudaFree(st.d_list_wide); cudaFree(st.d_list_gen); cudaFree(st.d_list_ovf); cudaFree(st.d_list_wfa); cudaFree(st.d_list_big); cudaFree(st.d_list_sorted); cudaFree(st.d_list_gen2); }
+    st.d_list_sorted = nullptr; st.d_list_gen2 = nullptr;
     st.d_desc = nullptr; st.d_out = nullptr; st.d_list_fast = nullptr; st.d_list_wide = nullptr; st.d_list_gen = nullptr; st.d_list_ovf = nullptr; st.d_list_wfa = nullptr; st.d_list_big = nullptr;
     st.cap = 0;
     CU_TRY(cudaMalloc(&st.d_desc, (size_t)want * sizeof(SwDesc)));
@@ -972,6 +972,7 @@ int sw_stage_reserve(SwStage &st, uint32_t pairs) {
     CU_TRY(cudaMalloc(&st.d_list_wfa, (size_t)want * sizeof(uint32_t)));
     CU_TRY(cudaMalloc(&st.d_list_big, (size_t)want * sizeof(uint32_t)));
     CU_TRY(cudaMalloc(&st.d_list_sorted, (size_t)want * sizeof(uint32_t)));
+    CU_TRY(cudaMalloc(&st.d_list_gen2, (size_t)want * sizeof(uint32_t)));
     if (!st.d_ctr) {
         CU_TRY(cudaMalloc(&st.d_ctr, sizeof(SwCounters)));
         CU_TRY(cudaMallocHost(&st.h_ctr, sizeof(SwCounters)));
@@ -990,7 +991,7 @@ int sw_stage_reserve(SwStage &st, uint32_t pairs) {
 
 void sw_stage_free(SwStage &st) {
     cudaFree(st.d_desc); cudaFree(st.d_out); cudaFree(st.d_list_fast); cudaFree(st.d_list_wide); cudaFree(st.d_list_gen); cudaFree(st.d_list_ovf);
-    cudaFree(st.d_list_wfa); cudaFree(st.d_list_big); cudaFree(st.d_list_sorted); cudaFree(st.d_sort_bins); cudaFree(st.d_gw_scratch);
+    cudaFree(st.d_list_wfa); cudaFree(st.d_list_big); cudaFree(st.d_list_sorted); cudaFree(st.d_sort_bins); cudaFree(st.d_list_gen2); cudaFree(st.d_swd_scratch); cudaFree(st.d_gw_scratch);
     cudaFree(st.d_ctr); if (st.h_ctr) cudaFreeHost(st.h_ctr);
     if (st.ev_k0) cudaEventDestroy(st.ev_k0);
     if (st.ev_k1) cudaEventDestroy(st.ev_k1);
@@ -1057,6 +1058,12 @@ int sw_small_limit() {
     return e && *e ? atoi(e) : 4096;
 }
 namespace {
+
+// BWT_SW_DOUBLE=0: every double-precision pair through the warp-per-pair kernel (A/B, tests of that kernel)
+bool sw_double_enabled() {
+    const char *e = getenv("BWT_SW_DOUBLE");
+    return !(e && *e && atoi(e) == 0);
+}
 
 int sw_use_shortcut() {
     // BWT_SW_SHORTCUT: 3 (default) quick test + wavefront rule, 2 the wavefront rule alone, 1 the quick test alone,
@@ -1127,7 +1134,19 @@ int sw_stage_enqueue(SwStage &st, const DevReads &R, const uint8_t *d_rbase, con
     SwGwPlan gw;
     BWT_TRY(sw_general_warp_plan(max_lq, st.cfg_sms, &gw));
     BWT_TRY(grow(st.d_gw_scratch, st.gw_scratch_words, (size_t)gw.scratch_words));
-    BWT_TRY(launch_sw_general_warp(gw, R, d_rbase, st.d_desc, st.d_list_gen, 0, &st.d_ctr->gen_cursor, st.d_list_big, st.d_gw_scratch,
+    const uint32_t *gen_list = st.d_list_gen, *gen_n = &st.d_ctr->n_general;
+    if (!st.small && sw_double_enabled()) {
+        // throughput path of the double-precision pairs: one thread per pair; what it cannot take (windows wider than its
+        // slices, bytes outside the IUPAC letters) goes on to the warp-per-pair kernel
+        SwdPlan dp;
+        BWT_TRY(sw_double_plan(max_lq, st.cfg_sms, n_cap, &dp));
+        BWT_TRY(grow(st.d_swd_scratch, st.swd_scratch_bytes, (size_t)dp.scratch_bytes));
+        BWT_TRY(launch_sw_double(dp, R, d_rbase, st.d_desc, st.d_list_gen, &st.d_ctr->n_general, st.d_list_gen2, &st.d_ctr->n_gen2,
+                                 st.d_swd_scratch, st.d_out, st.d_ctr, st.d_cig_tmp, st.cig_cap, stream));
+        st.launches += 1;
+        gen_list = st.d_list_gen2; gen_n = &st.d_ctr->n_gen2;
+    }
+    BWT_TRY(launch_sw_general_warp(gw, R, d_rbase, st.d_desc, gen_list, gen_n, 0, &st.d_ctr->gen_cursor, st.d_list_big, st.d_gw_scratch,
                                    st.d_out, st.d_ctr, st.d_cig_tmp, st.cig_cap, stream));
     st.launches += 1;
     return BWT_OK;
@@ -1174,7 +1193,7 @@ int sw_stage_finish(SwStage &st, const DevReads &R, const uint8_t *d_rbase, cons
         SwGwPlan gw;
         BWT_TRY(sw_general_warp_plan(max_lq, st.cfg_sms, &gw));
         CU_TRY(cudaMemsetAsync(&st.d_ctr->gen_cursor, 0, sizeof(uint32_t), stream));
-        BWT_TRY(launch_sw_general_warp(gw, R, d_rbase, st.d_desc, st.d_list_gen, done_general, &st.d_ctr->gen_cursor, st.d_list_big,
+        BWT_TRY(launch_sw_general_warp(gw, R, d_rbase, st.d_desc, st.d_list_gen, &st.d_ctr->n_general, done_general, &st.d_ctr->gen_cursor, st.d_list_big,
                                        st.d_gw_scratch, st.d_out, st.d_ctr, st.d_cig_tmp, st.cig_cap, stream));
         st.launches += 1;
         *redo_emit = true;

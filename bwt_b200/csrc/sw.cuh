@@ -21,7 +21,7 @@ struct SwCounters {
     unsigned long long sw_calls, cells;
     unsigned long long shortcut_calls, shortcut_cells;   // pairs settled by sw_classify_kernel without the DP (included above)
     uint32_t n_fast, n_wide, n_general, n_ovf;   // list cursors
-    uint32_t n_wfa, pad2;                        // pairs the quick test left to the wavefront rule
+    uint32_t n_wfa, n_gen2;                      // pairs the quick test left to the wavefront rule; pairs sw_double_kernel handed on to the warp kernel
     uint32_t n_big, gen_cursor;                  // general pairs too large for the warp kernel's slots; its work cursor
     uint32_t cig_used, cig_overflow; // temporary CIGAR arena
     uint32_t general_done, pad;
@@ -62,6 +62,9 @@ struct SwStage {
     uint2 *d_dirs = nullptr;          // direction scratch: one uint2 per (strip, column, thread)
     size_t dirs_words = 0;
     uint32_t *d_list_big = nullptr;
+    uint32_t *d_list_gen2 = nullptr;   // what sw_double_kernel leaves to the warp-per-pair kernel
+    uint8_t *d_swd_scratch = nullptr;  // slices of sw_double_kernel
+    size_t swd_scratch_bytes = 0;
     uint32_t *d_list_sorted = nullptr; // d_list_fast ordered by (Lq, Lr)
     uint32_t *d_sort_bins = nullptr;   // its counting-sort bins
     size_t sort_bins_cap = 0;
@@ -80,11 +83,18 @@ struct SwStage {
     float ms_fast_kernel = 0;
 };
 
+// thread-per-pair double-precision kernel (swd.cu): the throughput path of pairs with 'N' / IUPAC bytes
+struct SwdPlan { int cap_cols, max_strips, blocks; uint64_t off_bdir, off_dirs, scratch_bytes; };
+int sw_double_plan(int max_lq, int sms, uint32_t n_cap, SwdPlan *pl);
+int launch_sw_double(const SwdPlan &pl, const DevReads &R, const uint8_t *d_rbase, const SwDesc *d_desc, const uint32_t *d_list,
+                     const uint32_t *d_n_list, uint32_t *d_next, uint32_t *d_n_next, uint8_t *d_scratch, SwOut *d_out, SwCounters *d_ctr,
+                     char *d_cig, uint32_t cig_cap, cudaStream_t stream);
+
 // warp-per-pair general kernel (swg.cu)
 struct SwGwPlan { int wc_cap; uint64_t slot_words, scratch_words; size_t smem; int blocks; };
 int sw_general_warp_plan(int max_lq, int sms, SwGwPlan *pl);
 int launch_sw_general_warp(const SwGwPlan &pl, const DevReads &R, const uint8_t *d_rbase, const SwDesc *d_desc, const uint32_t *d_list,
-                           uint32_t first, uint32_t *d_cursor, uint32_t *d_list_big, uint32_t *d_scratch, SwOut *d_out, SwCounters *d_ctr,
+                           const uint32_t *d_n_list, uint32_t first, uint32_t *d_cursor, uint32_t *d_list_big, uint32_t *d_scratch, SwOut *d_out, SwCounters *d_ctr,
                            char *d_cig, uint32_t cig_cap, cudaStream_t stream);
 
 int sw_small_limit();

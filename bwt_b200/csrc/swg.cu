@@ -47,7 +47,7 @@ __host__ __device__ inline uint64_t gw_slot_words(int lq, int lr) {
 
 __global__ void __launch_bounds__(GW_WARPS * 32, GW_MIN_BLOCKS) sw_general_warp_kernel(DevReads R, const uint8_t *__restrict__ rbase,
                                                                         const SwDesc *__restrict__ desc, const uint32_t *__restrict__ list,
-                                                                        uint32_t first, uint32_t *cursor, uint32_t *__restrict__ list_big,
+                                                                        const uint32_t *__restrict__ n_list_ptr, uint32_t first, uint32_t *cursor, uint32_t *__restrict__ list_big,
                                                                         uint32_t *scratch, uint64_t slot_words, int wc_cap,
                                                                         SwOut *out, SwCounters *ctr, char *cig, uint32_t cig_cap) {
     extern __shared__ double gw_smem[];
@@ -56,7 +56,7 @@ __global__ void __launch_bounds__(GW_WARPS * 32, GW_MIN_BLOCKS) sw_general_warp_
     double *prev = gw_smem + (size_t)wib * wc_cap * 32;                                            // prev[c*32 + lane] = V(i-1, j)
     uint8_t *rch = reinterpret_cast<uint8_t *>(gw_smem + (size_t)GW_WARPS * wc_cap * 32) + (size_t)wib * wc_cap * 32;   // rch[c*32 + lane]
     uint32_t *slot = scratch + ((size_t)blockIdx.x * GW_WARPS + wib) * slot_words;
-    const uint32_t n_list = ctr->n_general;
+    const uint32_t n_list = *n_list_ptr;
     uint32_t n_done = 0;                                                    // this warp's work counters, flushed at the end
     unsigned long long n_cells = 0;
     for (;;) {
@@ -220,14 +220,14 @@ int sw_general_warp_plan(int max_lq, int sms, SwGwPlan *pl) {
 }
 
 int launch_sw_general_warp(const SwGwPlan &pl, const DevReads &R, const uint8_t *d_rbase, const SwDesc *d_desc, const uint32_t *d_list,
-                           uint32_t first, uint32_t *d_cursor, uint32_t *d_list_big, uint32_t *d_scratch, SwOut *d_out, SwCounters *d_ctr,
+                           const uint32_t *d_n_list, uint32_t first, uint32_t *d_cursor, uint32_t *d_list_big, uint32_t *d_scratch, SwOut *d_out, SwCounters *d_ctr,
                            char *d_cig, uint32_t cig_cap, cudaStream_t stream) {
     static bool attr_set = false;
     if (!attr_set || pl.smem > 48 * 1024) {
         CU_TRY(cudaFuncSetAttribute(sw_general_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(pl.smem, 48 * 1024)));
         attr_set = true;
     }
-    sw_general_warp_kernel<<<pl.blocks, GW_WARPS * 32, pl.smem, stream>>>(R, d_rbase, d_desc, d_list, first, d_cursor, d_list_big, d_scratch,
+    sw_general_warp_kernel<<<pl.blocks, GW_WARPS * 32, pl.smem, stream>>>(R, d_rbase, d_desc, d_list, d_n_list, first, d_cursor, d_list_big, d_scratch,
                                                                          pl.slot_words, pl.wc_cap, d_out, d_ctr, d_cig, cig_cap);
     K_CHECK(stream, "sw_general_warp_kernel");
     return BWT_OK;

@@ -711,20 +711,11 @@ int launch_sga(const DevIndex &ix, const DevReads &R, int64_t n_reads, int max_r
     // low bits: 0 off (default: measured 5-13 % slower with any of the modes), 1 prefetch.global.L2, 2 64-byte bulk prefetch, 3 discarded load
     static int prefetch = -1;
     if (prefetch < 0) { const char *e = getenv("BWT_SGA_PREFETCH"); prefetch = e && *e ? atoi(e) : 8; }
-    static int g16_maxlen = -1;   // BWT_SGA_G16_MAXLEN: longest read (bases) of a batch seeded with 16 lanes per read (default 200; 0 = 135)
-    if (g16_maxlen < 0) { const char *e = getenv("BWT_SGA_G16_MAXLEN"); g16_maxlen = e && *e ? atoi(e) : 200; if (g16_maxlen > BWT_MIN_LEN * 31 + BWT_MAX_LEN) g16_maxlen = BWT_MIN_LEN * 31 + BWT_MAX_LEN; }
     // 16 lanes per read while every read has at most 16 subsequences (<= 135 bases), else a full warp
     if (max_read_len <= BWT_MIN_LEN * 15 + BWT_MAX_LEN) {
         int64_t blocks = (n_reads + 7) / 8;
         if (blocks > 148 * 256) blocks = 148 * 256;
         sga_kernel<16, 16><<<(unsigned)blocks, SGA_BLOCK, 0, stream>>>(ix, R, n_reads, d_read_status, d_ncl,
-                                                                     d_cl_base, d_clusters, cl_cap, d_slow, slow_cap, d_ctr, prefetch);
-    } else if (max_read_len <= g16_maxlen) {
-        // up to 32 subsequences on 16 lanes (two rounds of look-ups): a full warp per read leaves 14 of its lanes idle on a
-        // 150-base read; the register sort takes 128 seed ends, ~4 per subsequence on a 3 Gbp reference
-        int64_t blocks = (n_reads + 7) / 8;
-        if (blocks > 148 * 256) blocks = 148 * 256;
-        sga_kernel<16, 32><<<(unsigned)blocks, SGA_BLOCK, 0, stream>>>(ix, R, n_reads, d_read_status, d_ncl,
                                                                      d_cl_base, d_clusters, cl_cap, d_slow, slow_cap, d_ctr, prefetch);
     } else {
         int64_t blocks = (n_reads + 3) / 4;

@@ -12,6 +12,8 @@
 // 256-entry constant table, the query character's row of 2-bit codes (-1 / 2 / 1.6 per class) is built once per strip.
 // A window byte outside those fourteen letters matches only itself, which no table of classes can say: such pairs, and
 // pairs beyond the slice's columns or strips, go on to the warp-per-pair kernel (list `next`).
+#include <type_traits>
+
 #include "sw.cuh"
 
 namespace {
@@ -113,6 +115,7 @@ __global__ void __launch_bounds__(SWD_BLOCK, SWD_MIN_BLOCKS) sw_double_kernel(Sw
         for (int j = 1; j <= lr; j++) { bval[(size_t)j * NT] = 0.0; bdir[(size_t)j * NT] = 3; }   // row 0: {0, undef} (sw.erl:61)
         const double thr0 = (double)(-2 * (lq / 2));                         // sw.erl:62
         int fail_row = -1;
+        double slack = 0.0;                                                  // row maximum - threshold at the last row of the previous strip
         for (int s = 0; s < nstr && fail_row < 0; s++) {
             const int i0 = i_first + s * R;
             uint32_t rowtab[R];
@@ -130,42 +133,55 @@ __global__ void __launch_bounds__(SWD_BLOCK, SWD_MIN_BLOCKS) sw_double_kernel(Sw
             }
             double top_prev = i0 - 1 >= 1 ? (double)(-i0) : 0.0;             // V(i0-1, 0)
             uint16_t *dstrip = dirs + (size_t)s * p.cap_cols * NT;
-            for (int j = 1; j <= lr; j++) {
-                const double top = bval[(size_t)j * NT];                     // V(i0-1, j)
-                int updir = (int)bdir[(size_t)j * NT];
-                const int sh = 2 * swd_class(w[j - 1]);
-                double diag = top_prev, up = top;
-                uint32_t nd = 0;
+            // A row's maximum is at most 2 below the maximum of the row above (the `up` candidate under the best cell) and
+            // the threshold rises by 2 per row: with a slack of more than 4 per row of this strip no row of it can fail
+            // (+1: a subtraction that crosses a binade may round in the last place), and only the strip's last row needs
+            // its maximum.  Rows <= 0 exist in the first strip only.
+            const bool masked = i0 < 1, light = !masked && slack >= 4.0 * R + 1.0;
+            auto columns = [&](auto MASKED, auto TRACK) {
+                for (int j = 1; j <= lr; j++) {
+                    const double top = bval[(size_t)j * NT];                 // V(i0-1, j)
+                    int updir = (int)bdir[(size_t)j * NT];
+                    const int sh = 2 * swd_class(w[j - 1]);
+                    double diag = top_prev, up = top;
+                    uint32_t nd = 0;
+#pragma unroll
+                    for (int r = 0; r < R; r++) {
+                        const uint32_t code = (rowtab[r] >> sh) & 3u;
+                        const double sg = code == 1u ? 2.0 : code == 2u ? 1.6 : -1.0;
+                        const double dg = __dadd_rn(diag, sg);               // sw.erl:90-94: one addition per candidate
+                        const double uc = __dadd_rn(up, updir == 1 ? -1.0 : -2.0);
+                        const double lc = __dadd_rn(vl[r], ((dl >> (2 * r)) & 3u) == 0u ? -1.0 : -2.0);
+                        const double v1 = fmax(dg, uc);                      // up_left > up > left among equal values
+                        int dir = uc > dg ? 1 : 2;
+                        double v = fmax(v1, lc);
+                        if (lc > v1) dir = 0;
+                        if (decltype(MASKED)::value && i0 + r < 1) { v = 0.0; dir = 3; }   // a row of the padding in front of the first strip
+                        diag = vl[r];
+                        vl[r] = v;
+                        if (decltype(TRACK)::value || r == R - 1) mx[r] = fmax(mx[r], v);
+                        nd |= (uint32_t)dir << (2 * r);
+                        up = v; updir = dir;
+                    }
+                    dl = nd;
+                    top_prev = top;
+                    bval[(size_t)j * NT] = up;                               // the strip's last row is the next strip's boundary
+                    bdir[(size_t)j * NT] = (uint8_t)updir;
+                    dstrip[(size_t)j * NT] = (uint16_t)nd;
+                }
+            };
+            if (masked) columns(std::true_type{}, std::true_type{});
+            else if (light) columns(std::false_type{}, std::false_type{});
+            else columns(std::false_type{}, std::true_type{});
+            // row threshold (sw.erl:69-71): the maximum of row i must reach thr0 + 2*i
+            if (!light) {
 #pragma unroll
                 for (int r = 0; r < R; r++) {
-                    const uint32_t code = (rowtab[r] >> sh) & 3u;
-                    const double sg = code == 1u ? 2.0 : code == 2u ? 1.6 : -1.0;
-                    const double dg = __dadd_rn(diag, sg);                   // sw.erl:90-94: one addition per candidate
-                    const double uc = __dadd_rn(up, updir == 1 ? -1.0 : -2.0);
-                    const double lc = __dadd_rn(vl[r], ((dl >> (2 * r)) & 3u) == 0u ? -1.0 : -2.0);
-                    const bool up_wins = uc > dg;                            // up_left > up > left among equal values
-                    double v = up_wins ? uc : dg;
-                    int dir = up_wins ? 1 : 2;
-                    if (lc > v) { v = lc; dir = 0; }
-                    if (i0 + r < 1) { v = 0.0; dir = 3; }                    // a row of the padding in front of the first strip
-                    diag = vl[r];
-                    vl[r] = v;
-                    if (v > mx[r]) mx[r] = v;
-                    nd |= (uint32_t)dir << (2 * r);
-                    up = v; updir = dir;
+                    const int i = i0 + r;
+                    if (i >= 1 && fail_row < 0 && mx[r] < thr0 + 2.0 * (double)i) fail_row = i;
                 }
-                dl = nd;
-                top_prev = top;
-                bval[(size_t)j * NT] = up;                                   // the strip's last row is the next strip's boundary
-                bdir[(size_t)j * NT] = (uint8_t)updir;
-                dstrip[(size_t)j * NT] = (uint16_t)nd;
             }
-            // row threshold (sw.erl:69-71): the maximum of row i must reach thr0 + 2*i
-#pragma unroll
-            for (int r = 0; r < R; r++) {
-                const int i = i0 + r;
-                if (i >= 1 && fail_row < 0 && mx[r] < thr0 + 2.0 * (double)i) fail_row = i;
-            }
+            slack = mx[R - 1] - (thr0 + 2.0 * (double)(i0 + R - 1));
             if (s == nstr - 1 && fail_row < 0) {
                 // leftmost column of the last row that holds its maximum (sw.erl:110-112); column 0 holds -(lq+1)
                 const double vmax = mx[R - 1];

@@ -99,7 +99,7 @@ __global__ void __launch_bounds__(SWD_BLOCK, SWD_MIN_BLOCKS) sw_double_kernel(Sw
         const int lq = d.lq, lr = d.lr;
         const uint8_t *w = p.rbase + d.r_off;
         const int nstr = (lq + R - 1) / R;
-        bool take = lq >= 1 && lr >= 1 && lr + 1 <= p.cap_cols && nstr <= p.max_strips && lq <= lr + 1;   // the CIGAR runs reuse the boundary row
+        bool take = lq >= 1 && lr >= 1 && lr + 1 <= p.cap_cols && nstr <= p.max_strips;
         if (take) {
             int other = 0;
             for (int j = 0; j < lr; j++) other |= swd_class(w[j]) == SWD_OTHER;
@@ -115,6 +115,7 @@ __global__ void __launch_bounds__(SWD_BLOCK, SWD_MIN_BLOCKS) sw_double_kernel(Sw
         for (int j = 1; j <= lr; j++) { bval[(size_t)j * NT] = 0.0; bdir[(size_t)j * NT] = 3; }   // row 0: {0, undef} (sw.erl:61)
         const double thr0 = (double)(-2 * (lq / 2));                         // sw.erl:62
         int fail_row = -1;
+        bool handed_on = false;
         double slack = 0.0;                                                  // row maximum - threshold at the last row of the previous strip
         for (int s = 0; s < nstr && fail_row < 0; s++) {
             const int i0 = i_first + s * R;
@@ -191,6 +192,7 @@ __global__ void __launch_bounds__(SWD_BLOCK, SWD_MIN_BLOCKS) sw_double_kernel(Sw
                 // traceback (sw.erl:116-160): up_left -> M, left -> D, up -> I; the runs go where the boundary row was
                 uint32_t *runs = reinterpret_cast<uint32_t *>(p.bval) + 2 * gt;        // runs[k * 2 * NT]: the low word of this thread's bval[k]
                 int i = lq, j = jbest, nr = 0, cur = -1, len = 0;
+                const int run_cap = p.cap_cols;                              // one run per boundary-row slot
                 while (i > 0) {
                     int op;                                                  // 0 = M, 1 = D, 2 = I
                     if (j == 0) op = 2;
@@ -200,10 +202,16 @@ __global__ void __launch_bounds__(SWD_BLOCK, SWD_MIN_BLOCKS) sw_double_kernel(Sw
                         op = c == 2u ? 0 : c == 1u ? 2 : 1;
                     }
                     if (op == cur) len++;
-                    else { if (cur >= 0) runs[(size_t)(nr++) * 2 * NT] = ((uint32_t)len << 2) | (uint32_t)cur; cur = op; len = 1; }
+                    else { if (cur >= 0) { if (nr < run_cap) runs[(size_t)nr * 2 * NT] = ((uint32_t)len << 2) | (uint32_t)cur; nr++; } cur = op; len = 1; }
                     if (op == 0) { i--; j--; } else if (op == 2) i--; else j--;
                 }
-                runs[(size_t)(nr++) * 2 * NT] = ((uint32_t)len << 2) | (uint32_t)cur;
+                if (nr < run_cap) runs[(size_t)nr * 2 * NT] = ((uint32_t)len << 2) | (uint32_t)cur;
+                nr++;
+                if (nr > run_cap) {                                          // more runs than slots (a path that alternates all the way): the warp kernel's
+                    p.next[atomicAdd(p.n_next, 1u)] = cand;
+                    handed_on = true;
+                    break;
+                }
                 int clen = 0;
                 for (int k = 0; k < nr; k++) {
                     uint32_t l = runs[(size_t)k * 2 * NT] >> 2;
@@ -231,6 +239,7 @@ __global__ void __launch_bounds__(SWD_BLOCK, SWD_MIN_BLOCKS) sw_double_kernel(Sw
                 p.out[cand] = o;
             }
         }
+        if (handed_on) continue;
         if (fail_row >= 0) {
             SwOut o;
             o.score = 0; o.status = BWT_HIT_NO_MATCH; o.cigar_len = 0; o.cigar_off = 0;

@@ -5,7 +5,13 @@ scripts/make_reference_golden.escript runs the UNMODIFIED reference (src/{fmi,bw
 from worker_bwt.erl:84-106) over it on any box with Erlang/OTP and writes tests/golden/reference_outputs.json.  The build
 image has no OTP, so that file may be absent; these tests then still run every input through the oracle (CPU) and
 through the CUDA path (GPU) and compare the two, and they compare BOTH with the reference's file the moment it is
-committed.  Until then DESIGN.md keeps saying "parity unpinned" for rows A2-A14.
+committed.
+
+Since the image has no BEAM, scripts/make_reference_golden_interpreted.py ALSO runs the same unmodified source files through
+oracle/mini_erl.py, a minimal generic Erlang evaluator (tree walker over the subset the four modules use; OTP's lists /
+erlang functions re-implemented from their documented semantics), and commits tests/golden/reference_outputs_interpreted.json:
+the oracle and the CUDA path are compared with it here.  That pins them to the reference's own source text -- clause
+order, guards, term order of lists:max/1 -- but not to a BEAM run (OTP's lists:sort/2 tie order stays unpinned).
 """
 import json
 import os
@@ -88,6 +94,56 @@ def reference_outputs():
     return items
 
 
+INTERPRETED = os.path.join(HERE, "golden", "reference_outputs_interpreted.json")
+
+
+def interpreted_outputs():
+    """{input index: output} of the reference's own source files run by oracle/mini_erl.py
+    (scripts/make_reference_golden_interpreted.py); None when the file is absent"""
+    if not os.path.exists(INTERPRETED):
+        return None
+    with open(INTERPRETED) as f:
+        doc = json.load(f)
+    out = {}
+    for it in doc["items"]:
+        out[it["index"]] = it["out"] if it["kind"] in ("S", "P") else {k: v for k, v in it.items() if k in ("sga", "cigars", "top")}
+    return out
+
+
+def test_oracle_equals_the_interpreted_reference(oracle_outputs):
+    """the hand-written oracle against the UNMODIFIED src/{fmi,bwa,sga,sw}.erl executed by a generic Erlang evaluator:
+    every committed input (bwa:find_seeds/6, sga:sga/6 + the worker's fold, sw:sw/2)"""
+    got = interpreted_outputs()
+    assert got is not None, "tests/golden/reference_outputs_interpreted.json is part of the repository"
+    items = load_inputs()
+    assert len(got) == len(items)
+    kinds = {"S": 0, "R": 0, "P": 0}
+    for k, want in got.items():
+        assert oracle_outputs[k] == want, (k, items[k])
+        kinds[items[k][0]] += 1
+    assert kinds["S"] >= 400 and kinds["R"] >= 700 and kinds["P"] >= 500
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/src/sw.erl"), reason="the reference tree only exists in the build container")
+def test_interpreted_file_is_what_the_evaluator_says_about_the_reference_sources():
+    """re-run a sample of the inputs through oracle/mini_erl.py on /root/reference's own files: the committed JSON is
+    reproducible here, not hand-edited"""
+    import subprocess
+    import sys
+    import tempfile
+    got = interpreted_outputs()
+    script = os.path.join(os.path.dirname(HERE), "scripts", "make_reference_golden_interpreted.py")
+    for first, last in ((0, 40), (407, 411), (1129, 1150)):
+        with tempfile.TemporaryDirectory() as tmp:
+            env = dict(os.environ, BWT_GOLDEN_OUT=os.path.join(tmp, "out.json"))
+            subprocess.check_call([sys.executable, script, "/root/reference", str(first), str(last)], env=env, stdout=subprocess.DEVNULL)
+            with open(os.path.join(tmp, "out.json")) as f:
+                doc = json.load(f)
+        for it in doc["items"]:
+            want = it["out"] if it["kind"] in ("S", "P") else {k: v for k, v in it.items() if k in ("sga", "cigars", "top")}
+            assert got[it["index"]] == want, it["index"]
+
+
 def test_inputs_cover_every_kind_and_edge():
     items = load_inputs()
     kinds = {k for k, _ in items}
@@ -165,7 +221,10 @@ def test_cuda_path_equals_oracle_and_reference(gl_fm, gl_ref, oracle_outputs):
     pst, sc, pc = api.sw_batch(q, qo, r, ro)
     for j, k in enumerate(p_idx):
         got[k] = "no_match" if pst[j] == api.HIT_NO_MATCH else [int(sc[j]), pc[j].decode()]
+    interp = interpreted_outputs()
     for k in range(len(items)):
         assert got[k] == oracle_outputs[k], (k, items[k])
         if ref is not None:
             assert got[k] == ref[k], (k, items[k])
+        if interp is not None and k in interp:
+            assert got[k] == interp[k], (k, items[k])

@@ -75,6 +75,17 @@ class ErlError(Exception):
     pass
 
 
+class Device:
+    """what file:open/2 returns here: io:format/3 appends to it (seeds:generate_fs/3 WRITES an Erlang module, seeds.erl:13-47)"""
+    __slots__ = ("name", "buf")
+
+    def __init__(self, name):
+        self.name, self.buf = name, []
+
+    def text(self) -> str:
+        return "".join(self.buf)
+
+
 def from_pylist(xs) -> Any:
     out = NIL
     for x in reversed(list(xs)):
@@ -107,7 +118,7 @@ def _rank(x) -> int:
         return 0
     if isinstance(x, Atom):
         return 1
-    if isinstance(x, Fun):
+    if isinstance(x, (Fun, Device)):
         return 3
     if isinstance(x, tuple):
         return 6
@@ -531,7 +542,12 @@ class Machine:
     def __init__(self, src_dir: str, inc_dir: str):
         self.src_dir, self.inc_dir = src_dir, inc_dir
         self.mods: Dict[str, Dict[Tuple[str, int], list]] = {}
+        self.devices: List[Device] = []
         self.steps = 0
+
+    def load_text(self, mod: str, text: str):
+        """a module from source text (the fs.erl that seeds:generate_fs/3 writes)"""
+        self.mods[mod] = Parser(tokenize(text), {"MODULE": [("atom", mod)]}).forms()
 
     def load(self, mod: str):
         if mod in self.mods:
@@ -882,6 +898,39 @@ class Machine:
                 return acc
             if name == "duplicate" and n == 2:
                 return from_pylist([args[1]] * args[0])
+        if mod == "file" and name == "open" and n == 2:
+            dev = Device(bytes(to_pylist(args[0])).decode())
+            self.devices.append(dev)
+            return (OK, dev)
+        if mod == "file" and name == "close" and n == 1:
+            return OK
+        if mod == "io" and name == "format" and n == 3 and isinstance(args[0], Device):
+            fmt, fargs, out, i = to_pylist(args[1]), to_pylist(args[2]), [], 0
+            while i < len(fmt):
+                c = fmt[i]
+                if c == 126 and i + 1 < len(fmt):                       # ~p ~s ~n ~~ ~b ~c: what seeds.erl uses (and a little more)
+                    d = chr(fmt[i + 1])
+                    i += 2
+                    if d == "n":
+                        out.append("\n")
+                    elif d == "~":
+                        out.append("~")
+                    elif d in ("p", "w", "b"):
+                        v = fargs.pop(0)
+                        if not isinstance(v, int):
+                            raise ErlError("io:format ~%s of a non-integer is outside the evaluated subset" % d)
+                        out.append(str(v))
+                    elif d == "s":
+                        out.append("".join(map(chr, to_pylist(fargs.pop(0)))))
+                    elif d == "c":
+                        out.append(chr(fargs.pop(0)))
+                    else:
+                        raise ErlError("io:format directive ~%s is outside the evaluated subset" % d)
+                else:
+                    out.append(chr(c))
+                    i += 1
+            args[0].buf.append("".join(out))
+            return OK
         if mod == "io" and name == "format":
             return OK
         raise ErlError("undef %s:%s/%d (not part of the evaluated subset)" % (mod, name, n))

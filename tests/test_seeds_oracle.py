@@ -86,3 +86,20 @@ def test_walk_semantics():
     assert S.fs_find_seeds(pats, 4, b"CAAAA") == [2]                  # seeds.erl:26-30: exactly Len left
     assert S.fs_find_seeds(pats, 4, b"AAA") == []
     assert c_fs_scan_dp(b"AAAA", 4, 0, b"AAAAAAAAAA") == [5, 1]
+
+
+def test_kats_equal_the_interpreted_reference():
+    """tests/golden/seeds_kat_interpreted.json: the UNMODIFIED src/seeds.erl run by oracle/mini_erl.py (generate_fs/3 writes
+    fs.erl, the evaluator loads that text and runs fs:find_seeds/1) on the KAT inputs.  The oracle's answers equal it."""
+    import json
+    import os
+    here = os.path.dirname(os.path.abspath(__file__))
+    with open(os.path.join(here, "golden", "seeds_kat.json")) as f:
+        kat = json.load(f)
+    with open(os.path.join(here, "golden", "seeds_kat_interpreted.json")) as f:
+        interp = json.load(f)
+    assert len(interp["cases"]) == len(kat["cases"]) == 60
+    for c, r in zip(kat["cases"], interp["cases"]):
+        assert (c["ref"], c["q"], c["len"], c["defects"]) == (r["ref"], r["q"], r["len"], r["defects"])
+        assert c["seeds"] == r["seeds"], (c["ref"], c["q"], c["len"], c["defects"])
+        assert c["n_patterns"] >= 1 and r["true_clauses"] >= 1

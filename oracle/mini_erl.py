@@ -75,6 +75,23 @@ class ErlError(Exception):
     pass
 
 
+class ReadDevice:
+    """a file opened with [read] in list mode: file:read_line/1 returns the next line with its newline, or eof"""
+    __slots__ = ("d", "p")
+
+    def __init__(self, data: bytes):
+        self.d, self.p = data, 0
+
+    def read_line(self):
+        if self.p >= len(self.d):
+            return None
+        k = self.d.find(b"\n", self.p)
+        k = len(self.d) if k < 0 else k + 1
+        ln = self.d[self.p:k]
+        self.p = k
+        return ln
+
+
 class Device:
     """what file:open/2 returns here: io:format/3 appends to it (seeds:generate_fs/3 WRITES an Erlang module, seeds.erl:13-47)"""
     __slots__ = ("name", "buf")
@@ -118,7 +135,7 @@ def _rank(x) -> int:
         return 0
     if isinstance(x, Atom):
         return 1
-    if isinstance(x, (Fun, Device)):
+    if isinstance(x, (Fun, Device, ReadDevice)):
         return 3
     if isinstance(x, tuple):
         return 6
@@ -896,6 +913,11 @@ class Machine:
                 for x in to_pylist(args[2]):
                     acc = self.apply_fun(args[0], [x, acc])
                 return acc
+            if name == "droplast" and n == 1:
+                xs = to_pylist(args[0])
+                if not xs:
+                    raise ErlError("function_clause lists:droplast([])")
+                return from_pylist(xs[:-1])
             if name == "duplicate" and n == 2:
                 return from_pylist([args[1]] * args[0])
         if mod == "file" and name == "open" and n == 2:
@@ -904,6 +926,9 @@ class Machine:
             return (OK, dev)
         if mod == "file" and name == "close" and n == 1:
             return OK
+        if mod == "file" and name == "read_line" and n == 1 and isinstance(args[0], ReadDevice):
+            ln = args[0].read_line()                                    # list mode: {ok, Line incl. its newline} | eof
+            return atom("eof") if ln is None else (OK, from_pylist(ln))
         if mod == "io" and name == "format" and n == 3 and isinstance(args[0], Device):
             fmt, fargs, out, i = to_pylist(args[1]), to_pylist(args[2]), [], 0
             while i < len(fmt):

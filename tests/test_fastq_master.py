@@ -87,3 +87,35 @@ def test_sink_filter_and_format():
     assert master.sink_line(msg, "21") == O.master_sink_line(msg, "21") == "\nread1 x      21      12345      150M      291      ACGT\n"
     assert master.sink_line(("cigar", b"r", (264, "1M"), 1, b"A"), "21") is None
     assert master.sink_line("no_cigar", "21") is None
+
+
+@pytest.mark.skipif(not __import__("os").path.exists("/root/reference/src/fastq.erl"), reason="the reference tree only exists in the build container")
+def test_oracle_equals_the_interpreted_fastq_erl():
+    """src/fastq.erl, unmodified, run by oracle/mini_erl.py (file:read_line/1 over an in-memory device): read_seqs/2 in
+    batches, every quirk of the record reader -- against the oracle's restatement"""
+    from oracle import mini_erl as E
+    m = E.Machine("/root/reference/src", "/root/reference/include")
+    m.load("fastq")
+
+    def conv(term):
+        if isinstance(term, E.Atom):
+            return str(term)
+        if isinstance(term, tuple) and term and isinstance(term[0], E.Atom) and str(term[0]) in ("ok", "eof"):
+            return (str(term[0]), [(bytes(E.to_pylist(a)), bytes(E.to_pylist(b))) for (a, b) in E.to_pylist(term[1])])
+        raise AssertionError(term)
+
+    rng = np.random.default_rng(9)
+    recs = [(b"r%d x" % k, bytes(rng.choice(list(b"ACGTN"), size=int(rng.integers(0, 40))).astype(np.uint8))) for k in range(23)]
+    texts = [_fastq(recs, 0, True), _fastq(recs, 4, True), _fastq(recs, 0, False), _fastq(recs[:7], 3, False), b"", b"junk\n\n",
+             b"@r1\nACGT", b"@r1\nACGT\n+", b"@\n\n"]
+    for text in texts:
+        for n in (1, 5, 200):
+            dev_e, dev_o = E.ReadDevice(text), O.LineDev(text)
+            while True:
+                got = conv(m.call("fastq", "read_seqs", [dev_e, n]))
+                want = O.fastq_read_seqs(dev_o, n)
+                assert got == want, (text[:40], n)
+                if got == "eof" or got[0] == "eof":
+                    break
+    with pytest.raises(E.ErlError):                                        # header as the last line: {ok,SeqData} = eof
+        m.call("fastq", "read_seqs", [E.ReadDevice(b"@r1\nACGT\n+\nIIII\n@r2\n"), 5])

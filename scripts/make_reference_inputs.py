@@ -77,6 +77,43 @@ for it in range(60):                                     # low complexity: many 
 for it in range(40):                                     # unrelated strings
     lines.append(b"P " + rnd(int(rng.integers(5, 90)), b"ACGT") + b" " + rnd(int(rng.integers(5, 120)), b"ACGT"))
 
+# -- appended in round 2 (indices of everything above stay as they were): pairs aimed at the tie rules of sw:sw/2 -- low-complexity
+#    and tandem-repeat strings (competing diagonals, deletions between matching flanks), slack 0..20, substitutions and
+#    indels next to each other; the generator of tests/test_gpu_parity.py::test_sw_shortcut_adversarial, shorter strings
+rng2 = np.random.default_rng(20261019)
+for it in range(600):
+    alpha = [b"ACGT", b"AC", b"ACGT", b"AAC", b"ACGT"][it % 5]
+    lq, dd = int(rng2.integers(4, 70)), int(rng2.integers(0, 21))
+    pick = lambda n: bytes(alpha[int(x)] for x in rng2.integers(0, len(alpha), n))   # noqa: E731
+    mode = rng2.random()
+    if mode < 0.55:
+        base = pick(lq + dd + 4)
+        s0 = int(rng2.integers(0, dd + 3))
+        q = bytearray(base[s0:s0 + lq]) + bytearray(pick(max(0, lq - len(base[s0:s0 + lq]))))
+        for _ in range(int(rng2.choice([0, 0, 1, 1, 1, 2, 3, 4, 5, 6]))):
+            u = rng2.random()
+            if u < 0.7:
+                q[int(rng2.integers(0, lq))] = alpha[int(rng2.integers(0, len(alpha)))]
+            elif u < 0.85 and len(q) > 5:
+                del q[int(rng2.integers(0, len(q)))]
+                q += pick(1)
+            else:
+                q.insert(int(rng2.integers(0, len(q))), alpha[int(rng2.integers(0, len(alpha)))])
+        lines.append(b"P " + bytes(q[:lq]) + b" " + base[:lq + dd])
+    elif mode < 0.85:
+        unit = pick(int(rng2.integers(1, 5)))
+        base = (unit * 400)[:lq + dd]
+        r = bytearray(base)
+        for _ in range(int(rng2.integers(0, 3))):
+            r[int(rng2.integers(0, len(r)))] = b"ACGT"[int(rng2.integers(0, 4))]
+        s0 = int(rng2.integers(0, dd + 1))
+        q = bytearray(base[s0:s0 + lq])
+        for _ in range(int(rng2.integers(0, 6))):
+            q[int(rng2.integers(0, lq))] = b"ACGT"[int(rng2.integers(0, 4))]
+        lines.append(b"P " + bytes(q) + b" " + bytes(r))
+    else:
+        lines.append(b"P " + pick(lq) + b" " + pick(lq + dd))
+
 out = os.path.join(ROOT, "tests", "golden", "reference_inputs.txt")
 with open(out, "wb") as f:
     f.write(b"\n".join(lines) + b"\n")

@@ -230,7 +230,7 @@ def sample(api, a, ix, n, read_len, seed, env, pinned=True, synth=None, n_rate=0
     return reads, offs, (rt, ot)
 
 
-AGG_KEYS = ("lf", "hbm_lf", "located", "searches", "clusters", "sw_calls", "cells", "general", "launches", "sc_calls", "sc_cells")
+AGG_KEYS = ("lf", "hbm_lf", "located", "searches", "clusters", "sw_calls", "cells", "general", "launches", "sc_calls", "sc_cells", "band_calls", "band_cells", "band_filled")
 
 
 def new_agg():
@@ -256,6 +256,7 @@ def resident_steps(batch, steps, warmup, env, clocks=None):
         agg["searches"] += s.searches; agg["clusters"] += s.clusters; agg["sw_calls"] += s.sw_calls
         agg["cells"] += s.sw_cells; agg["general"] += s.sw_general; agg["launches"] += s.launches
         agg["sc_calls"] += s.sw_shortcut; agg["sc_cells"] += s.sw_shortcut_cells
+        agg["band_calls"] += s.sw_band; agg["band_cells"] += s.sw_band_cells; agg["band_filled"] += s.sw_band_filled
         agg["ms_sga"] += s.ms_sga_kernel; agg["ms_sw"] += s.ms_sw_kernel
         agg["ms_seed"] += s.ms_seed; agg["ms_swstage"] += s.ms_sw; agg["ms_emit"] += s.ms_emit
     env.barrier()
@@ -428,7 +429,7 @@ def roofline_objects(a, K, t_ev, agg, read_bytes, cig_bytes, extra):
     #                instructions (8.5 per cell pair: PRMT, 2 VIADDMNMX, VIMNMX, VIADD.16x2, 3.5 LOP3 -- from SASS)
     sga_bytes = (64.0 * agg["hbm_lf"] + 8.0 * agg["searches"] + 4.0 * agg["located"] + float(read_bytes * K))
     sga_gbs = sga_bytes / (agg["ms_sga"] * 1e-3) / 1e9 if agg["ms_sga"] > 0 else 0.0
-    dp_calls, dp_cells = agg["sw_calls"] - agg["sc_calls"], agg["cells"] - agg["sc_cells"]
+    dp_calls, dp_cells = agg["sw_calls"] - agg["sc_calls"] - agg["band_calls"], agg["cells"] - agg["sc_cells"] - agg["band_cells"]
     sw_bytes = dp_calls * (2.0 * a.read_len + 16.0) + float(cig_bytes * K) * (dp_calls / max(1, agg["sw_calls"]))
     sw_gbs = sw_bytes / (agg["ms_sw"] * 1e-3) / 1e9 if agg["ms_sw"] > 0 else 0.0
     gcups = dp_cells / (agg["ms_sw"] * 1e-3) / 1e9 if agg["ms_sw"] else 0.0
@@ -477,6 +478,8 @@ def work_object(agg, n, K, gcups, n_hits):
             "sw_calls_per_read": agg["sw_calls"] / (n * K), "cells_per_read": agg["cells"] / (n * K),
             "sw_gcups": gcups,
             "sw_shortcut_pairs_frac": agg["sc_calls"] / max(1, agg["sw_calls"]),
+            "sw_band_pairs_frac": agg["band_calls"] / max(1, agg["sw_calls"]),
+            "sw_band_cells_filled_per_pair": agg["band_filled"] / max(1, agg["band_calls"]),
             "sw_cells_equivalent_gcups": agg["cells"] / (agg["ms_swstage"] * 1e-3) / 1e9 if agg["ms_swstage"] else None,
             "sw_general_pairs": agg["general"], "hits_per_step": n_hits,
             "ms_sw_fast_kernels": agg["ms_sw"] / K, "ms_sga_kernel": agg["ms_sga"] / K,

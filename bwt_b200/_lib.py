@@ -52,7 +52,8 @@ class BwtStats(C.Structure):
                 ("ms_total", C.c_float), ("ms_seed", C.c_float), ("ms_sw", C.c_float), ("ms_emit", C.c_float),
                 ("ms_h2d", C.c_float), ("ms_d2h", C.c_float), ("ms_sga_kernel", C.c_float), ("ms_sw_kernel", C.c_float),
                 ("launches", C.c_uint32), ("reserved", C.c_uint32),
-                ("sw_shortcut", C.c_uint64), ("sw_shortcut_cells", C.c_uint64)]
+                ("sw_shortcut", C.c_uint64), ("sw_shortcut_cells", C.c_uint64),
+                ("sw_band", C.c_uint64), ("sw_band_cells", C.c_uint64), ("sw_band_filled", C.c_uint64)]
 
 
 class BwtFsStats(C.Structure):
@@ -145,7 +146,7 @@ def lib():
             fn = getattr(L, name)          # AttributeError here = the .so does not export a declared symbol
             fn.restype = res
             fn.argtypes = args
-        if L.bwt_abi_version() != 4:
+        if L.bwt_abi_version() != 5:
             raise ImportError("bwt_b200: ABI version mismatch")
         _lib = L
     return _lib

@@ -665,6 +665,7 @@ static int run_core(bwt_batch *b, bool with_sw, bool compact) {
         s.clusters = ncl;
         s.sw_calls = b->sw.sw_calls; s.sw_cells = b->sw.cells; s.sw_general = b->sw.n_general;
         s.sw_shortcut = b->sw.shortcut_calls; s.sw_shortcut_cells = b->sw.shortcut_cells;
+        s.sw_band = b->sw.band_calls; s.sw_band_cells = b->sw.band_cells; s.sw_band_filled = b->sw.band_cells_filled;
         s.launches += b->sw.launches;
         cudaEventElapsedTime(&s.ms_sga_kernel, b->ev[6], b->ev[7]);
         cudaEventElapsedTime(&s.ms_seed, b->ev[0], b->ev[1]);
@@ -825,6 +826,7 @@ void stats_add(bwt_stats &t, const bwt_stats &s) {
     t.reads += s.reads; t.searches += s.searches; t.lf_steps += s.lf_steps; t.hbm_lf_steps += s.hbm_lf_steps;
     t.located_rows += s.located_rows; t.clusters += s.clusters; t.sw_calls += s.sw_calls; t.sw_cells += s.sw_cells;
     t.sw_shortcut += s.sw_shortcut; t.sw_shortcut_cells += s.sw_shortcut_cells;
+    t.sw_band += s.sw_band; t.sw_band_cells += s.sw_band_cells; t.sw_band_filled += s.sw_band_filled;
     t.sw_general += s.sw_general; t.ms_total += s.ms_total; t.ms_seed += s.ms_seed; t.ms_sw += s.ms_sw; t.ms_emit += s.ms_emit;
     t.ms_h2d += s.ms_h2d; t.ms_d2h += s.ms_d2h; t.ms_sga_kernel += s.ms_sga_kernel; t.ms_sw_kernel += s.ms_sw_kernel;
     t.launches += s.launches;

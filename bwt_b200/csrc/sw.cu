@@ -959,8 +959,8 @@ int grow(T *&p, size_t &cap_items, size_t need_items) {
 int sw_stage_reserve(SwStage &st, uint32_t pairs) {
     if (pairs <= st.cap && st.d_desc) return BWT_OK;
     uint32_t want = pairs + pairs / 4 + 1024;
-    if (st.d_desc) { cudaFree(st.d_desc); cudaFree(st.d_out); cudaFree(st.d_list_fast); cudaFree(st.d_list_wide); cudaFree(st.d_list_gen); cudaFree(st.d_list_ovf); cudaFree(st.d_list_wfa); cudaFree(st.d_list_big); cudaFree(st.d_list_sorted); cudaFree(st.d_list_gen2); }
-    st.d_list_sorted = nullptr; st.d_list_gen2 = nullptr;
+    if (st.d_desc) { cudaFree(st.d_desc); cudaFree(st.d_out); cudaFree(st.d_list_fast); cudaFree(st.d_list_wide); cudaFree(st.d_list_gen); cudaFree(st.d_list_ovf); cudaFree(st.d_list_wfa); cudaFree(st.d_list_big); cudaFree(st.d_list_sorted); cudaFree(st.d_list_gen2); cudaFree(st.d_list_fast2); }
+    st.d_list_sorted = nullptr; st.d_list_gen2 = nullptr; st.d_list_fast2 = nullptr;
     st.d_desc = nullptr; st.d_out = nullptr; st.d_list_fast = nullptr; st.d_list_wide = nullptr; st.d_list_gen = nullptr; st.d_list_ovf = nullptr; st.d_list_wfa = nullptr; st.d_list_big = nullptr;
     st.cap = 0;
     CU_TRY(cudaMalloc(&st.d_desc, (size_t)want * sizeof(SwDesc)));
@@ -973,6 +973,7 @@ int sw_stage_reserve(SwStage &st, uint32_t pairs) {
     CU_TRY(cudaMalloc(&st.d_list_big, (size_t)want * sizeof(uint32_t)));
     CU_TRY(cudaMalloc(&st.d_list_sorted, (size_t)want * sizeof(uint32_t)));
     CU_TRY(cudaMalloc(&st.d_list_gen2, (size_t)want * sizeof(uint32_t)));
+    CU_TRY(cudaMalloc(&st.d_list_fast2, (size_t)want * sizeof(uint32_t)));
     if (!st.d_ctr) {
         CU_TRY(cudaMalloc(&st.d_ctr, sizeof(SwCounters)));
         CU_TRY(cudaMallocHost(&st.h_ctr, sizeof(SwCounters)));
@@ -991,7 +992,7 @@ int sw_stage_reserve(SwStage &st, uint32_t pairs) {
 
 void sw_stage_free(SwStage &st) {
     cudaFree(st.d_desc); cudaFree(st.d_out); cudaFree(st.d_list_fast); cudaFree(st.d_list_wide); cudaFree(st.d_list_gen); cudaFree(st.d_list_ovf);
-    cudaFree(st.d_list_wfa); cudaFree(st.d_list_big); cudaFree(st.d_list_sorted); cudaFree(st.d_sort_bins); cudaFree(st.d_list_gen2); cudaFree(st.d_swd_scratch); cudaFree(st.d_gw_scratch);
+    cudaFree(st.d_list_wfa); cudaFree(st.d_list_big); cudaFree(st.d_list_sorted); cudaFree(st.d_sort_bins); cudaFree(st.d_list_gen2); cudaFree(st.d_swd_scratch); cudaFree(st.d_gw_scratch); cudaFree(st.d_list_fast2); cudaFree(st.d_band_scratch);
     cudaFree(st.d_ctr); if (st.h_ctr) cudaFreeHost(st.h_ctr);
     if (st.ev_k0) cudaEventDestroy(st.ev_k0);
     if (st.ev_k1) cudaEventDestroy(st.ev_k1);
@@ -1065,6 +1066,13 @@ bool sw_double_enabled() {
     return !(e && *e && atoi(e) == 0);
 }
 
+// BWT_SW_BAND=0: no banded table -- every pair the shortcut leaves open fills its whole table (A/B, parity tests of the
+// full-table kernels on gapped pairs)
+bool sw_band_enabled() {
+    const char *e = getenv("BWT_SW_BAND");
+    return !(e && *e && atoi(e) == 0);
+}
+
 int sw_use_shortcut() {
     // BWT_SW_SHORTCUT: 3 (default) quick test + wavefront rule, 2 the wavefront rule alone, 1 the quick test alone,
     // 0 every pair through the DP (A/B timing, and parity tests of the DP on easy pairs); read per run: tests flip it
@@ -1082,6 +1090,7 @@ int sw_stage_enqueue(SwStage &st, const DevReads &R, const uint8_t *d_rbase, con
                      const uint32_t *d_n, uint32_t n_cap, int max_lq, cudaStream_t stream) {
     (void)d_rbase;
     st.sw_calls = st.cells = st.n_general = st.shortcut_calls = st.shortcut_cells = 0;
+    st.band_calls = st.band_cells = st.band_cells_filled = 0;
     st.ms_fast_kernel = 0;
     if (n_cap > st.cap) { bwt_set_error("sw_stage: %u pairs exceed the reserved %u", n_cap, st.cap); return BWT_ERR_ARG; }
     SwPlan pl;
@@ -1107,23 +1116,33 @@ int sw_stage_enqueue(SwStage &st, const DevReads &R, const uint8_t *d_rbase, con
         st.launches += 1;
     }
     SwFastParams p = sw_params(st, R, d_ref2, pl);
-    // large batches: the DP list ordered by shape (see sw_shape_hist_kernel); small ones are not worth three launches
-    const uint32_t *fast_list = st.d_list_fast;
+    const uint32_t *fast_list = st.d_list_fast, *fast_n = &st.d_ctr->n_fast;
+    // gapped pairs: a band of the table plus a certificate (swb.cu); what it cannot certify goes on to the full table
+    if (!st.small && sw_band_enabled()) {
+        SwbPlan bp;
+        BWT_TRY(sw_band_plan(max_lq, st.cfg_sms, n_cap, &bp));
+        BWT_TRY(grow(st.d_band_scratch, st.band_scratch_words, (size_t)bp.scratch_words));
+        BWT_TRY(launch_sw_band(bp, R, d_ref2, st.d_desc, fast_list, fast_n, st.d_list_fast2, &st.d_ctr->n_fast2, st.d_band_scratch,
+                               st.d_out, st.d_ctr, st.d_cig_tmp, st.cig_cap, stream));
+        st.launches += 1;
+        fast_list = st.d_list_fast2; fast_n = &st.d_ctr->n_fast2;
+    }
+    // large batches: the full-table list ordered by shape (see sw_shape_hist_kernel); small ones are not worth three launches
     if (!st.small && sw_sort_min_pairs() >= 0 && n_cap >= (uint32_t)sw_sort_min_pairs()) {
         const uint32_t nbins = (uint32_t)(std::min(max_lq, SW_FAST_MAX_LQ) + 1) * SW_SORT_LR;
         BWT_TRY(grow(st.d_sort_bins, st.sort_bins_cap, (size_t)nbins));
         CU_TRY(cudaMemsetAsync(st.d_sort_bins, 0, (size_t)nbins * sizeof(uint32_t), stream));
         const unsigned sgrid = std::min(cgrid, 148u * 8u);
-        sw_shape_hist_kernel<<<sgrid, 256, 0, stream>>>(st.d_desc, st.d_list_fast, &st.d_ctr->n_fast, st.d_sort_bins, nbins);
+        sw_shape_hist_kernel<<<sgrid, 256, 0, stream>>>(st.d_desc, fast_list, fast_n, st.d_sort_bins, nbins);
         sw_shape_scan_kernel<<<1, 1024, 0, stream>>>(st.d_sort_bins, nbins);
-        sw_shape_scatter_kernel<<<sgrid, 256, 0, stream>>>(st.d_desc, st.d_list_fast, &st.d_ctr->n_fast, st.d_sort_bins, nbins, st.d_list_sorted);
+        sw_shape_scatter_kernel<<<sgrid, 256, 0, stream>>>(st.d_desc, fast_list, fast_n, st.d_sort_bins, nbins, st.d_list_sorted);
         K_CHECK(stream, "sw_shape_* kernels");
         st.launches += 3;
         fast_list = st.d_list_sorted;
     }
     CU_TRY(cudaEventRecord(st.ev_k0, stream));
     if (!st.small) {
-        p.list = fast_list; p.n_list = &st.d_ctr->n_fast; p.cap_cols = pl.cap_narrow;
+        p.list = fast_list; p.n_list = fast_n; p.cap_cols = pl.cap_narrow;
         sw_fast_kernel<true><<<pl.grid[0], SW_BLOCK, smem_of(pl.cap_narrow, true), stream>>>(p);
         K_CHECK(stream, "sw_fast_kernel (narrow)");
         st.launches += 1;
@@ -1244,6 +1263,7 @@ int sw_stage_finish(SwStage &st, const DevReads &R, const uint8_t *d_rbase, cons
         cudaEventElapsedTime(&st.ms_fast_kernel, st.ev_k0, st.ev_k1);
         st.sw_calls = st.h_ctr->sw_calls; st.cells = st.h_ctr->cells; st.n_general = st.h_ctr->n_general;
         st.shortcut_calls = st.h_ctr->shortcut_calls; st.shortcut_cells = st.h_ctr->shortcut_cells;
+        st.band_calls = st.h_ctr->band_calls; st.band_cells = st.h_ctr->band_cells; st.band_cells_filled = st.h_ctr->band_cells_filled;
         return BWT_OK;
     }
     // temporary CIGAR arena too small: grow to what this attempt asked for (and then some); the caller redoes the stage

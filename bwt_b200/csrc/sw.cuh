@@ -25,7 +25,9 @@ struct SwCounters {
     uint32_t n_big, gen_cursor;                  // general pairs too large for the warp kernel's slots; its work cursor
     uint32_t cig_used, cig_overflow; // temporary CIGAR arena
     uint32_t general_done, pad;
-    uint32_t pad3[8];
+    unsigned long long band_calls, band_cells;   // pairs settled by sw_band_kernel and the cells sw:sw/2 fills for them (both INCLUDED in sw_calls / cells)
+    unsigned long long band_cells_filled;        // cells of the bands it filled instead
+    uint32_t n_fast2, pad3;                      // cursor of the list sw_band_kernel leaves to sw_fast_kernel
     // The temporary CIGAR arena is handed out from SW_CIG_SHARDS regions, each with its cursor on its own 128-byte line
     // (chosen by block): millions of appends to ONE cursor serialise in a single L2 slice at ~1.75 ns each.
     uint32_t cig_sub[64 * 32];
@@ -66,6 +68,9 @@ struct SwStage {
     uint8_t *d_swd_scratch = nullptr;  // slices of sw_double_kernel
     size_t swd_scratch_bytes = 0;
     uint32_t *d_list_sorted = nullptr; // d_list_fast ordered by (Lq, Lr)
+    uint32_t *d_list_fast2 = nullptr;  // what sw_band_kernel leaves to sw_fast_kernel
+    uint32_t *d_band_scratch = nullptr; // direction words of sw_band_kernel
+    size_t band_scratch_words = 0;
     uint32_t *d_sort_bins = nullptr;   // its counting-sort bins
     size_t sort_bins_cap = 0;
     uint32_t *d_gw_scratch = nullptr; // slots of the warp-per-pair general kernel
@@ -78,6 +83,7 @@ struct SwStage {
     uint32_t launches = 0;
     bool small = false;               // worker-sized batch: DP pairs go to the warp-per-pair kernel, fast tiers not launched
     unsigned long long sw_calls = 0, cells = 0, n_general = 0, shortcut_calls = 0, shortcut_cells = 0;
+    unsigned long long band_calls = 0, band_cells = 0, band_cells_filled = 0;
     int cfg_max_lq = -1, cfg_sms = 0, cfg_per_sm[3] = {0, 0, 0};   // launch configuration of the last run (host queries are not free)
     cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr;   // around sw_fast_kernel
     float ms_fast_kernel = 0;
@@ -89,6 +95,13 @@ int sw_double_plan(int max_lq, int sms, uint32_t n_cap, SwdPlan *pl);
 int launch_sw_double(const SwdPlan &pl, const DevReads &R, const uint8_t *d_rbase, const SwDesc *d_desc, const uint32_t *d_list,
                      const uint32_t *d_n_list, uint32_t *d_next, uint32_t *d_n_next, uint8_t *d_scratch, SwOut *d_out, SwCounters *d_ctr,
                      char *d_cig, uint32_t cig_cap, cudaStream_t stream);
+
+// thread-per-pair banded table with a certificate (swb.cu): plain pairs whose best alignment has a gap
+struct SwbPlan { int rows_cap, blocks; uint64_t scratch_words; };
+int sw_band_plan(int max_lq, int sms, uint32_t n_cap, SwbPlan *pl);
+int launch_sw_band(const SwbPlan &pl, const DevReads &R, const uint32_t *d_ref2, const SwDesc *d_desc, const uint32_t *d_list,
+                   const uint32_t *d_n_list, uint32_t *d_next, uint32_t *d_n_next, uint32_t *d_scratch, SwOut *d_out,
+                   SwCounters *d_ctr, char *d_cig, uint32_t cig_cap, cudaStream_t stream);
 
 // warp-per-pair general kernel (swg.cu)
 struct SwGwPlan { int wc_cap; uint64_t slot_words, scratch_words; size_t smem; int blocks; };

@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define BWT_B200_ABI_VERSION 4   /* 3: packed reads in, compact hits out, bwt_index_info.fused, bwt_sample_reads_edits; 4: bwt_fs_stats.settled */
+#define BWT_B200_ABI_VERSION 5   /* 3: packed reads in, compact hits out, bwt_index_info.fused, bwt_sample_reads_edits; 4: bwt_fs_stats.settled; 5: bwt_stats.sw_band* */
 
 typedef enum bwt_status {
     BWT_OK = 0,
@@ -145,6 +145,9 @@ typedef struct bwt_stats {   /* work counters of the last run (definitions: DESI
     uint64_t sw_shortcut, sw_shortcut_cells; /* pairs (and their cells, both INCLUDED in sw_calls / sw_cells) whose sw:sw/2
                                                 result was proven without filling the table: a perfect or one-mismatch
                                                 diagonal with no competing deletion (sw.cu, sw_shortcut) */
+    uint64_t sw_band, sw_band_cells;         /* pairs (and the cells sw:sw/2 fills for them, both INCLUDED in sw_calls / sw_cells)
+                                                settled from a band of the table plus a certificate (swb.cu) */
+    uint64_t sw_band_filled;                 /* cells of the bands filled instead */
 } bwt_stats;
 
 const char *bwt_last_error(void);

@@ -141,10 +141,14 @@ def test_classification_stages_one_at_a_time(mode):
         os.environ.pop("BWT_SW_SHORTCUT", None)
 
 
-def test_dp_pairs_of_different_lengths():
-    """Every pair through the DP kernel (BWT_SW_SHORTCUT=0), neighbouring pairs of very different query lengths: the two
-    halves of a thread's packed registers then start their first real row in different strips."""
+@pytest.mark.parametrize("band", ["0", "1"])
+def test_dp_pairs_of_different_lengths(band):
+    """Every pair through the DP kernels (BWT_SW_SHORTCUT=0), neighbouring pairs of very different query lengths: the two
+    halves of a thread's packed registers then start their first real row in different strips (band 0: the full-table
+    kernel alone); with the banded table in front (band 1) the lanes of a warp run bands of different heights and the
+    full-table kernel gets what is left."""
     os.environ["BWT_SW_SHORTCUT"] = "0"
+    os.environ["BWT_SW_BAND"] = band
     try:
         rng = np.random.default_rng(77)
         pairs = []
@@ -165,6 +169,7 @@ def test_dp_pairs_of_different_lengths():
         assert _check_pairs(pairs) > 3500
     finally:
         os.environ.pop("BWT_SW_SHORTCUT", None)
+        os.environ.pop("BWT_SW_BAND", None)
 
 
 def test_indel_reads_sampler_and_depth_invariance(gl_index, gl_ref):

@@ -19,20 +19,27 @@ from test_oracle_golden import (KAT_2_CIGARS, KAT_2_SGA, READ_KAT_1, READ_KAT_2,
                                 _rand_query, _rand_seq)
 
 
-@pytest.fixture(autouse=True, params=["shortcut", "dp_only", "small"])
+@pytest.fixture(autouse=True, params=["shortcut", "dp_only", "small", "band_only"])
 def sw_mode(request):
-    """Every test of this file runs three times: with the no-DP shortcut of sw_classify_kernel / sw_wfa_kernel and the
-    packed-integer DP tiers behind it; with BWT_SW_SHORTCUT=0, which sends every pair through those DP kernels; and in
-    the routing of worker-sized batches (BWT_SW_SMALL: every pair that needs the table takes the warp-per-pair kernel
-    in doubles, the fast tiers are never launched), forced here for batches of any size."""
+    """Every test of this file runs four times: with the no-DP shortcut of sw_classify_kernel / sw_wfa_kernel, the banded
+    table of sw_band_kernel and the packed-integer full-table tiers behind them (the default routing); with
+    BWT_SW_SHORTCUT=0 BWT_SW_BAND=0, which sends every pair through the full-table kernels; in the routing of
+    worker-sized batches (BWT_SW_SMALL: every pair that needs the table takes the warp-per-pair kernel in doubles, the
+    fast tiers are never launched), forced here for batches of any size; and with BWT_SW_SHORTCUT=0 alone, which hands
+    every plain pair -- gapless ones too -- to the banded table first."""
     os.environ.pop("BWT_SW_SHORTCUT", None)
+    os.environ.pop("BWT_SW_BAND", None)
     os.environ["BWT_SW_SMALL"] = "0"
     if request.param == "dp_only":
         os.environ["BWT_SW_SHORTCUT"] = "0"
+        os.environ["BWT_SW_BAND"] = "0"
     elif request.param == "small":
         os.environ["BWT_SW_SMALL"] = "2000000000"
+    elif request.param == "band_only":
+        os.environ["BWT_SW_SHORTCUT"] = "0"
     yield request.param
     os.environ.pop("BWT_SW_SHORTCUT", None)
+    os.environ.pop("BWT_SW_BAND", None)
     os.environ.pop("BWT_SW_SMALL", None)
 
 
@@ -324,6 +331,13 @@ def test_shortcut_is_taken_and_counted(gl_index, gl_ref, sw_mode):
         assert 0.1 * s.sw_calls < s.sw_shortcut <= s.sw_calls and 0 < s.sw_shortcut_cells <= s.sw_cells
     else:
         assert s.sw_shortcut == 0 and s.sw_shortcut_cells == 0
+    # the banded table: reads with an indel in the default routing, nearly every pair when the shortcut is off
+    if sw_mode == "shortcut":
+        assert 0 < s.sw_band < 0.5 * s.sw_calls and s.sw_band_filled < s.sw_band_cells <= s.sw_cells
+    elif sw_mode == "band_only":
+        assert s.sw_band > 0.4 * s.sw_calls and s.sw_band_filled < 0.25 * s.sw_band_cells
+    else:
+        assert s.sw_band == 0 and s.sw_band_cells == 0 and s.sw_band_filled == 0
 
 
 def test_sw_parity_iupac_and_n():

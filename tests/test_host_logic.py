@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
     L = _lib.lib()                                   # raises if a symbol is missing
     for n in names:
         assert getattr(L, n) is not None
-    assert L.bwt_abi_version() == 4
+    assert L.bwt_abi_version() == 5
 
 
 def test_struct_layouts_match_header():
@@ -34,7 +34,7 @@ def test_struct_layouts_match_header():
     assert C.sizeof(_lib.BwtIndexInfo) == 72
     assert C.sizeof(_lib.BwtHit16) == 16 and api.HIT16_DTYPE.itemsize == 16
     assert C.sizeof(_lib.BwtPackedReads) == 88 and C.sizeof(_lib.BwtSampleOpts) == 72
-    assert C.sizeof(_lib.BwtStats) == 9 * 8 + 8 * 4 + 2 * 4 + 2 * 8
+    assert C.sizeof(_lib.BwtStats) == 9 * 8 + 8 * 4 + 2 * 4 + 5 * 8
 
 
 def test_no_cpu_fallback_without_device(tmp_path):

@@ -507,7 +507,7 @@ class Comm:
 class Aligner:
     """Pipelined ``bwt_align_batch``: persistent chunk buffers, copies overlapped with kernels (``bwt_aligner``)."""
 
-    def __init__(self, index: Index, chunk_reads: int = 1 << 20, chunk_bytes: int = 256 << 20, depth: int = 3):
+    def __init__(self, index: Index, chunk_reads: int = 1 << 20, chunk_bytes: int = 256 << 20, depth: int = 5):
         self.index = index
         self._a = C.c_void_p()
         check(lib().bwt_aligner_create(index.handle, int(chunk_reads), int(chunk_bytes), int(depth), C.byref(self._a)))

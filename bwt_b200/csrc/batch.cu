@@ -814,7 +814,9 @@ extern "C" int bwt_aligner_stats(bwt_aligner *a, bwt_stats *out) {
 namespace {
 struct PipeShared {
     std::mutex mu, compute_mu;
-    std::condition_variable cv;
+    std::condition_variable cv, compute_cv;
+    int64_t compute_next = 0;        // next chunk to enter its run (chunks enter in order)
+    int compute_in = 0;              // chunks inside their run
     int64_t next_chunk = 0;          // chunks [0, next_chunk) have published their totals
     int64_t hit_base = 0, cig_base = 0;
     bool space = true;
@@ -856,9 +858,21 @@ int aligner_run_io(bwt_aligner *a, const AlignIO &io) {
     std::vector<int64_t> wbase, wcount;                     // packed input: word base / count / longest read per chunk
     std::vector<int> wmax;
     if (io.packed) {
+        // chunk sizes: a quarter and a half chunk at either end -- the first chunk's upload and the last one's download are
+        // the part of a run nothing overlaps with (BWT_CHUNK_RAMP=0: equal chunks)
+        std::vector<int64_t> sizes;
+        const int64_t cr = a->chunk_reads;
+        const char *env_ramp = getenv("BWT_CHUNK_RAMP");
+        if ((!env_ramp || atoi(env_ramp) != 0) && cr >= 4096 && n >= 4 * cr) {
+            const int64_t q = cr / 4, h = cr / 2, mid = n - 2 * (q + h), k = (mid + cr - 1) / cr;
+            sizes.push_back(q); sizes.push_back(h);
+            for (int64_t t = 0; t < k; t++) sizes.push_back(mid / k + (t < mid % k ? 1 : 0));
+            sizes.push_back(h); sizes.push_back(q);
+        }
         int64_t wb = 0;
+        size_t si = 0;
         for (int64_t lo = 0; lo < n;) {
-            const int64_t hi = std::min(n, lo + a->chunk_reads);
+            const int64_t hi = std::min(n, lo + (si < sizes.size() ? sizes[si++] : cr));
             int64_t words; int mx;
             packed_geom(io.packed, lo, hi, &words, &mx);
             wbase.push_back(wb); wcount.push_back(words); wmax.push_back(mx);
@@ -880,7 +894,16 @@ int aligner_run_io(bwt_aligner *a, const AlignIO &io) {
     std::vector<bwt_stats> wstats((size_t)depth);
     const bool trace = getenv("BWT_TRACE") != nullptr;       // per-chunk host timeline on stderr (debug aid)
     const char *env_tok = getenv("BWT_COMPUTE_TOKEN");
-    const int token_mode = env_tok ? atoi(env_tok) : 0;      // 1: one chunk at a time inside a run (A/B against free overlap)
+    // Chunks inside their run (kernels enqueued or executing) at any time, entered in chunk order.  With free overlap the
+    // workers fall into lock step -- all `depth` chunks compute side by side, finish together, then all wait for their
+    // copies while the GPU idles (profiles/r2b3_e2e_timeline.md: 1.3 ms per round of four).  Three at a time keeps the next
+    // chunk's kernels queued behind the running ones' while the other workers' copies go on beside them (sweeps in
+    // profiles/r2b4_e2e_token_sweep.log, r2b6: three at a time with five chunks in flight).
+    // BWT_COMPUTE_TOKEN=0: free overlap; N > 0: at most N.
+    const int token_mode = env_tok && *env_tok ? atoi(env_tok) : 3;
+    cudaEvent_t ev_origin = nullptr;                         // trace: device-side times of every chunk against one origin
+    if (trace) { cudaSetDevice(a->batches[0]->ix->device); cudaEventCreate(&ev_origin); cudaEventRecord(ev_origin, a->batches[0]->stream); }
+    auto dev_ms = [&](cudaEvent_t e) { float ms = -1.f; if (ev_origin) cudaEventElapsedTime(&ms, ev_origin, e); return ms; };
     const auto t_start = std::chrono::steady_clock::now();
     auto now_ms = [&] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_start).count(); };
     auto worker = [&](int w) {
@@ -892,24 +915,43 @@ int aligner_run_io(bwt_aligner *a, const AlignIO &io) {
             bool skip;
             { std::lock_guard<std::mutex> g(sh.mu); skip = sh.status != BWT_OK; }
             double t0 = now_ms(), t1 = t0, t2 = t0, t3 = t0;
+            bool took_turn = false;
             if (!skip) {
                 if (b->dl_pending) {     // the previous chunk's results must have left before this run overwrites them
                     cudaError_t e = batch_wait(b, b->dl_stream, b->ev_block_dl, b->n > 65536);
                     b->dl_pending = false;
                     if (e != cudaSuccess) { bwt_set_error("aligner download: %s", cudaGetErrorString(e)); st = BWT_ERR_CUDA; }
-                    else { float ms = 0; cudaEventElapsedTime(&ms, b->ev_dl0, b->ev_dl1); wstats[(size_t)w].ms_d2h += ms; }
+                    else {
+                        float ms = 0; cudaEventElapsedTime(&ms, b->ev_dl0, b->ev_dl1); wstats[(size_t)w].ms_d2h += ms;
+                        if (trace) fprintf(stderr, "chunk %3lld w%d: device d2h %.2f-%.2f (collected at host %.2f)\n", (long long)(c - depth), w, dev_ms(b->ev_dl0), dev_ms(b->ev_dl1), now_ms());
+                    }
                 }
                 if (st == BWT_OK)
                     st = io.packed ? batch_upload_packed_range(b, io.packed, lo, lo + m, wbase[(size_t)c], wcount[(size_t)c], wmax[(size_t)c])
                                    : bwt_batch_upload(b, io.reads, io.offsets + lo, m);
                 t1 = now_ms();
                 if (st == BWT_OK) {
-                    std::unique_lock<std::mutex> run_token(sh.compute_mu, std::defer_lock);
-                    if (token_mode == 1) run_token.lock();
+                    if (token_mode > 0) {
+                        std::unique_lock<std::mutex> g(sh.compute_mu);
+                        sh.compute_cv.wait(g, [&] { return sh.compute_next == c && sh.compute_in < token_mode; });
+                        sh.compute_next = c + 1; sh.compute_in++;
+                        took_turn = true;
+                    }
+                    sh.compute_cv.notify_all();
                     st = run_core(b, true, io.compact);
+                    if (token_mode > 0) { std::lock_guard<std::mutex> g(sh.compute_mu); sh.compute_in--; }
+                    sh.compute_cv.notify_all();
                     if (st == BWT_OK) { float ms = 0; cudaEventElapsedTime(&ms, b->ev[4], b->ev[5]); b->stats.ms_h2d = ms; }
                 }
                 t2 = now_ms();
+            }
+            if (token_mode > 0 && !took_turn) {
+                // a chunk that does not run (an earlier failure, a failed upload) still takes its turn: the chunks behind it wait for it
+                std::unique_lock<std::mutex> g(sh.compute_mu);
+                sh.compute_cv.wait(g, [&] { return sh.compute_next == c; });
+                sh.compute_next = c + 1;
+                g.unlock();
+                sh.compute_cv.notify_all();
             }
             int64_t nh = (skip || st != BWT_OK) ? 0 : b->n_hits, nc = (skip || st != BWT_OK) ? 0 : b->cigar_bytes;
             int64_t hb, cb;
@@ -962,8 +1004,8 @@ int aligner_run_io(bwt_aligner *a, const AlignIO &io) {
             }
             stats_add(wstats[(size_t)w], b->stats);
             if (trace)
-                fprintf(stderr, "chunk %3lld w%d: upload %.2f-%.2f run -%.2f (seed %.2f sw %.2f emit %.2f) wait -%.2f download -%.2f\n", (long long)c, w,
-                        t0, t1, t2, b->stats.ms_seed, b->stats.ms_sw, b->stats.ms_emit, t3, now_ms());
+                fprintf(stderr, "chunk %3lld w%d: host upload %.2f-%.2f run -%.2f wait -%.2f download -%.2f | device h2d %.2f-%.2f seed %.2f sw %.2f emit %.2f-%.2f\n", (long long)c, w,
+                        t0, t1, t2, t3, now_ms(), dev_ms(b->ev[4]), dev_ms(b->ev[5]), dev_ms(b->ev[0]), dev_ms(b->ev[1]), dev_ms(b->ev[2]), dev_ms(b->ev[3]));
         }
     };
     auto worker_all = [&](int w) {
@@ -973,13 +1015,17 @@ int aligner_run_io(bwt_aligner *a, const AlignIO &io) {
             cudaError_t e = batch_wait(b, b->dl_stream, b->ev_block_dl, b->n > 65536);
             b->dl_pending = false;
             if (e != cudaSuccess) { std::lock_guard<std::mutex> g(sh.mu); if (sh.status == BWT_OK) { sh.status = BWT_ERR_CUDA; sh.error = cudaGetErrorString(e); } }
-            else { float ms = 0; cudaEventElapsedTime(&ms, b->ev_dl0, b->ev_dl1); wstats[(size_t)w].ms_d2h += ms; }
+            else {
+                float ms = 0; cudaEventElapsedTime(&ms, b->ev_dl0, b->ev_dl1); wstats[(size_t)w].ms_d2h += ms;
+                if (trace) fprintf(stderr, "last of   w%d: device d2h %.2f-%.2f (collected at host %.2f)\n", w, dev_ms(b->ev_dl0), dev_ms(b->ev_dl1), now_ms());
+            }
         }
     };
     std::vector<std::thread> th;
     for (int w = 1; w < depth; w++) th.emplace_back(worker_all, w);
     worker_all(0);
     for (auto &t : th) t.join();
+    if (ev_origin) cudaEventDestroy(ev_origin);
     for (int w = 0; w < depth; w++) stats_add(a->stats, wstats[(size_t)w]);
     *io.n_hits = sh.hit_base; *io.cigar_bytes = sh.cig_base;
     if (sh.status != BWT_OK) { bwt_set_error("%s", sh.error.c_str()); return sh.status; }
@@ -1036,7 +1082,7 @@ extern "C" int bwt_align_batch(bwt_index *h, const uint8_t *reads, const int64_t
     // sizes rounded up to powers of two: the aligner kept with the index then fits the next call as well
     const int64_t cr = std::min(round_up_pow2(std::max<int64_t>(1, n), 1024), CHUNK_READS);
     const int64_t cb = std::min(round_up_pow2(std::max<int64_t>(16, total_bytes), 1 << 17), CHUNK_BYTES);
-    const int depth = n > 2 * CHUNK_READS ? 3 : (n > CHUNK_READS ? 2 : 1);
+    const int depth = (int)std::min<int64_t>(5, std::max<int64_t>(1, (n + CHUNK_READS - 1) / CHUNK_READS));   // chunks in flight (profiles/r2b6: five, three of them inside their run)
     bwt_aligner *a = nullptr;
     bool temporary = false;
     if (h->tail_mu) {

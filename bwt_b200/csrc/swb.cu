@@ -49,11 +49,18 @@ __device__ __forceinline__ bool band_pair(const SwbParams &p, const SwDesc &d, u
     swb::Band<WB> s;
     swb::init<WB>(s, lo, lr);
     const int last_full = min(lq, lr - lo - WB + 1);
-    uint32_t qw = 0;
+    // strings by groups of 16 rows: the query word of the group, and the 32 window bases from the group's first cell on --
+    // row i = 16g + t + 1 looks at window bases i + lo - 1 + b = (16g + lo) + t + b, one funnel shift away
+    uint32_t qw = 0, w0 = 0, w1 = 0;
     auto neq_of = [&](int i) {
-        if (((i - 1) & 15) == 0) qw = read_fwd_word(pkr, lq, (i - 1) >> 4);
-        const uint32_t qb = (qw >> (2 * ((i - 1) & 15))) & 3u;
-        const uint32_t x = window_word(p.ref2, d.r_off, i + lo - 1) ^ (qb * 0x55555555u);   // cell b <-> window base i + lo - 1 + b
+        const int t = (i - 1) & 15;
+        if (t == 0) {
+            qw = read_fwd_word(pkr, lq, (i - 1) >> 4);
+            w0 = window_word(p.ref2, d.r_off, i - 1 + lo);
+            w1 = window_word(p.ref2, d.r_off, i - 1 + lo + 16);
+        }
+        const uint32_t qb = (qw >> (2 * t)) & 3u;
+        const uint32_t x = __funnelshift_r(w0, w1, 2 * t) ^ (qb * 0x55555555u);
         return (x | (x >> 1)) & 0x55555555u;
     };
     int i = 1;
@@ -63,7 +70,20 @@ __device__ __forceinline__ bool band_pair(const SwbParams &p, const SwDesc &d, u
     int score = 0, b_end = 0;
     if (!swb::finish<WB>(s, lq, lo, lr, &score, &b_end)) return false;
     uint16_t runs[swb::MAX_RUNS];
-    const int nr = swb::trace<WB>([&](int row) { return dirs[(size_t)(row - 1) * B]; }, lq, lo, b_end, runs);
+    // the walk reads the direction words eight rows at a time (independent loads; a walk mostly moves up one row per step)
+    uint32_t dw[8];
+    int dw_hi = 0;                                               // dw[k] = word of row dw_hi - k; nothing fetched yet
+    const int nr = swb::trace<WB>([&](int row) {
+        if (row > dw_hi || row <= dw_hi - 8) {
+            dw_hi = row;
+#pragma unroll
+            for (int k = 0; k < 8; k++) dw[k] = row - k >= 1 ? dirs[(size_t)(row - k - 1) * B] : 0u;
+        }
+        uint32_t v = dw[0];
+#pragma unroll
+        for (int k = 1; k < 8; k++) if (dw_hi - row == k) v = dw[k];
+        return v;
+    }, lq, lo, b_end, runs);
     if (nr < 0) return false;
     const int clen = swb::cigar_len(runs, nr);
     bool room;

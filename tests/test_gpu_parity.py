@@ -335,7 +335,7 @@ def test_shortcut_is_taken_and_counted(gl_index, gl_ref, sw_mode):
     if sw_mode == "shortcut":
         assert 0 < s.sw_band < 0.5 * s.sw_calls and s.sw_band_filled < s.sw_band_cells <= s.sw_cells
     elif sw_mode == "band_only":
-        assert s.sw_band > 0.4 * s.sw_calls and s.sw_band_filled < 0.25 * s.sw_band_cells
+        assert s.sw_band > 0.25 * s.sw_calls and s.sw_band_filled < 0.25 * s.sw_band_cells
     else:
         assert s.sw_band == 0 and s.sw_band_cells == 0 and s.sw_band_filled == 0
 

@@ -858,21 +858,9 @@ int aligner_run_io(bwt_aligner *a, const AlignIO &io) {
     std::vector<int64_t> wbase, wcount;                     // packed input: word base / count / longest read per chunk
     std::vector<int> wmax;
     if (io.packed) {
-        // chunk sizes: a quarter and a half chunk at either end -- the first chunk's upload and the last one's download are
-        // the part of a run nothing overlaps with (BWT_CHUNK_RAMP=0: equal chunks)
-        std::vector<int64_t> sizes;
-        const int64_t cr = a->chunk_reads;
-        const char *env_ramp = getenv("BWT_CHUNK_RAMP");
-        if ((!env_ramp || atoi(env_ramp) != 0) && cr >= 4096 && n >= 4 * cr) {
-            const int64_t q = cr / 4, h = cr / 2, mid = n - 2 * (q + h), k = (mid + cr - 1) / cr;
-            sizes.push_back(q); sizes.push_back(h);
-            for (int64_t t = 0; t < k; t++) sizes.push_back(mid / k + (t < mid % k ? 1 : 0));
-            sizes.push_back(h); sizes.push_back(q);
-        }
         int64_t wb = 0;
-        size_t si = 0;
         for (int64_t lo = 0; lo < n;) {
-            const int64_t hi = std::min(n, lo + (si < sizes.size() ? sizes[si++] : cr));
+            const int64_t hi = std::min(n, lo + a->chunk_reads);
             int64_t words; int mx;
             packed_geom(io.packed, lo, hi, &words, &mx);
             wbase.push_back(wb); wcount.push_back(words); wmax.push_back(mx);

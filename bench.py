@@ -63,17 +63,13 @@ def parse():
     ap.add_argument("--no-side", action="store_true", help="skip the untimed peak / LF-walk side measurements")
     ap.add_argument("--no-legs", action="store_true", help="skip the config4 / config5 / config1 / n_reads legs")
     ap.add_argument("--chunk-reads", type=int, default=1 << 20, help="reads per pipelined chunk of the e2e leg")
-    ap.add_argument("--depth", type=int, default=0, help="chunks in flight in the e2e leg; 0 = 5 on one GPU (sweeps in profiles/r2b4_e2e_token_sweep.log and r2b6_e2e_token_depth_chunk_sweep.log), fewer when N ranks share the host cores (every chunk in flight is a host thread)")
+    ap.add_argument("--depth", type=int, default=5, help="chunks in flight in the e2e leg (sweeps: profiles/r2b4_e2e_token_sweep.log, r2b6_e2e_token_depth_chunk_sweep.log; 8 ranks on 32 host cores: profiles/r2n8c_e2e_depth.log)")
     ap.add_argument("--inexact-queries", type=int, default=50_000, help="queries of the untimed bounded-edit side leg (0 = skip)")
     ap.add_argument("--c4-reads", type=int, default=80_000_000, help="config 4: reads in total (sharded over the ranks)")
     ap.add_argument("--c5-reads", type=int, default=2_000_000, help="config 5: reads (every partition sees all of them)")
     ap.add_argument("--c5-queries", type=int, default=20_000, help="config 5: queries of the bounded-edit search per partition")
     ap.add_argument("--partitions", type=int, default=8)
-    a = ap.parse_args()
-    if a.depth <= 0:
-        world = int(os.environ.get("WORLD_SIZE", "1"))
-        a.depth = 5 if world == 1 else max(2, min(5, (os.cpu_count() or 8) // world - 1))
-    return a
+    return ap.parse_args()
 
 
 def edits_text(a):

@@ -959,8 +959,8 @@ int grow(T *&p, size_t &cap_items, size_t need_items) {
 int sw_stage_reserve(SwStage &st, uint32_t pairs) {
     if (pairs <= st.cap && st.d_desc) return BWT_OK;
     uint32_t want = pairs + pairs / 4 + 1024;
-    if (st.d_desc) { cudaFree(st.d_desc); cudaFree(st.d_out); cudaFree(st.d_list_fast); cudaFree(st.d_list_wide); cudaFree(st.d_list_gen); cudaFree(st.d_list_ovf); cudaFree(st.d_list_wfa); cudaFree(st.d_list_big); cudaFree(st.d_list_sorted); cudaFree(st.d_list_gen2); cudaFree(st.d_list_fast2); }
-    st.d_list_sorted = nullptr; st.d_list_gen2 = nullptr; st.d_list_fast2 = nullptr;
+    if (st.d_desc) { cudaFree(st.d_desc); cudaFree(st.d_out); cudaFree(st.d_list_fast); cudaFree(st.d_list_wide); cudaFree(st.d_list_gen); cudaFree(st.d_list_ovf); cudaFree(st.d_list_wfa); cudaFree(st.d_list_big); cudaFree(st.d_list_sorted); cudaFree(st.d_list_gen2); cudaFree(st.d_list_fast2); cudaFree(st.d_list_fast3); }
+    st.d_list_sorted = nullptr; st.d_list_gen2 = nullptr; st.d_list_fast2 = nullptr; st.d_list_fast3 = nullptr;
     st.d_desc = nullptr; st.d_out = nullptr; st.d_list_fast = nullptr; st.d_list_wide = nullptr; st.d_list_gen = nullptr; st.d_list_ovf = nullptr; st.d_list_wfa = nullptr; st.d_list_big = nullptr;
     st.cap = 0;
     CU_TRY(cudaMalloc(&st.d_desc, (size_t)want * sizeof(SwDesc)));
@@ -974,6 +974,7 @@ int sw_stage_reserve(SwStage &st, uint32_t pairs) {
     CU_TRY(cudaMalloc(&st.d_list_sorted, (size_t)want * sizeof(uint32_t)));
     CU_TRY(cudaMalloc(&st.d_list_gen2, (size_t)want * sizeof(uint32_t)));
     CU_TRY(cudaMalloc(&st.d_list_fast2, (size_t)want * sizeof(uint32_t)));
+    CU_TRY(cudaMalloc(&st.d_list_fast3, (size_t)want * sizeof(uint32_t)));
     if (!st.d_ctr) {
         CU_TRY(cudaMalloc(&st.d_ctr, sizeof(SwCounters)));
         CU_TRY(cudaMallocHost(&st.h_ctr, sizeof(SwCounters)));
@@ -992,7 +993,7 @@ int sw_stage_reserve(SwStage &st, uint32_t pairs) {
 
 void sw_stage_free(SwStage &st) {
     cudaFree(st.d_desc); cudaFree(st.d_out); cudaFree(st.d_list_fast); cudaFree(st.d_list_wide); cudaFree(st.d_list_gen); cudaFree(st.d_list_ovf);
-    cudaFree(st.d_list_wfa); cudaFree(st.d_list_big); cudaFree(st.d_list_sorted); cudaFree(st.d_sort_bins); cudaFree(st.d_list_gen2); cudaFree(st.d_swd_scratch); cudaFree(st.d_gw_scratch); cudaFree(st.d_list_fast2); cudaFree(st.d_band_scratch);
+    cudaFree(st.d_list_wfa); cudaFree(st.d_list_big); cudaFree(st.d_list_sorted); cudaFree(st.d_sort_bins); cudaFree(st.d_list_gen2); cudaFree(st.d_swd_scratch); cudaFree(st.d_gw_scratch); cudaFree(st.d_list_fast2); cudaFree(st.d_list_fast3); cudaFree(st.d_band_scratch);
     cudaFree(st.d_ctr); if (st.h_ctr) cudaFreeHost(st.h_ctr);
     if (st.ev_k0) cudaEventDestroy(st.ev_k0);
     if (st.ev_k1) cudaEventDestroy(st.ev_k1);
@@ -1073,6 +1074,12 @@ bool sw_band_enabled() {
     return !(e && *e && atoi(e) == 0);
 }
 
+// BWT_SW_BAND_SORT=0: the list is ordered by shape behind the banded table (for sw_fast_kernel) instead of in front of it
+bool sw_band_sort_first() {
+    const char *e = getenv("BWT_SW_BAND_SORT");
+    return !(e && *e && atoi(e) == 0);
+}
+
 int sw_use_shortcut() {
     // BWT_SW_SHORTCUT: 3 (default) quick test + wavefront rule, 2 the wavefront rule alone, 1 the quick test alone,
     // 0 every pair through the DP (A/B timing, and parity tests of the DP on easy pairs); read per run: tests flip it
@@ -1117,18 +1124,13 @@ int sw_stage_enqueue(SwStage &st, const DevReads &R, const uint8_t *d_rbase, con
     }
     SwFastParams p = sw_params(st, R, d_ref2, pl);
     const uint32_t *fast_list = st.d_list_fast, *fast_n = &st.d_ctr->n_fast;
-    // gapped pairs: a band of the table plus a certificate (swb.cu); what it cannot certify goes on to the full table
-    if (!st.small && sw_band_enabled()) {
-        SwbPlan bp;
-        BWT_TRY(sw_band_plan(max_lq, st.cfg_sms, n_cap, &bp));
-        BWT_TRY(grow(st.d_band_scratch, st.band_scratch_words, (size_t)bp.scratch_words));
-        BWT_TRY(launch_sw_band(bp, R, d_ref2, st.d_desc, fast_list, fast_n, st.d_list_fast2, &st.d_ctr->n_fast2, st.d_band_scratch,
-                               st.d_out, st.d_ctr, st.d_cig_tmp, st.cig_cap, stream));
-        st.launches += 1;
-        fast_list = st.d_list_fast2; fast_n = &st.d_ctr->n_fast2;
-    }
-    // large batches: the full-table list ordered by shape (see sw_shape_hist_kernel); small ones are not worth three launches
-    if (!st.small && sw_sort_min_pairs() >= 0 && n_cap >= (uint32_t)sw_sort_min_pairs()) {
+    const bool band = !st.small && sw_band_enabled();
+    const bool sort = !st.small && sw_sort_min_pairs() >= 0 && n_cap >= (uint32_t)sw_sort_min_pairs();
+    const bool sort_first = sw_band_sort_first();
+    // large batches: the list ordered by shape (see sw_shape_hist_kernel); small ones are not worth three launches.
+    // In front of the banded table it keeps a warp's pairs at one band width and one height; what the band leaves comes
+    // out in nearly that order, so sw_fast_kernel's short list is not sorted again.
+    auto sort_list = [&]() -> int {
         const uint32_t nbins = (uint32_t)(std::min(max_lq, SW_FAST_MAX_LQ) + 1) * SW_SORT_LR;
         BWT_TRY(grow(st.d_sort_bins, st.sort_bins_cap, (size_t)nbins));
         CU_TRY(cudaMemsetAsync(st.d_sort_bins, 0, (size_t)nbins * sizeof(uint32_t), stream));
@@ -1139,6 +1141,27 @@ int sw_stage_enqueue(SwStage &st, const DevReads &R, const uint8_t *d_rbase, con
         K_CHECK(stream, "sw_shape_* kernels");
         st.launches += 3;
         fast_list = st.d_list_sorted;
+        return BWT_OK;
+    };
+    if (sort && (!band || sort_first)) BWT_TRY(sort_list());
+    // gapped pairs: a band of the table plus a certificate (swb.cu), tried with a small penalty budget (narrow band) first
+    // and with a larger one on what that left; what neither certifies goes on to the full table
+    if (band) {
+        SwbPlan bp;
+        BWT_TRY(sw_band_plan(max_lq, st.cfg_sms, n_cap, &bp));
+        BWT_TRY(grow(st.d_band_scratch, st.band_scratch_words, (size_t)bp.scratch_words));
+        BWT_TRY(launch_sw_band(bp, R, d_ref2, st.d_desc, fast_list, fast_n, st.d_list_fast2, &st.d_ctr->n_fast2, st.d_band_scratch,
+                               st.d_out, st.d_ctr, st.d_cig_tmp, st.cig_cap, stream));
+        st.launches += 1;
+        fast_list = st.d_list_fast2; fast_n = &st.d_ctr->n_fast2;
+        if (bp.p_second) {
+            bp.p_prev = bp.p_short; bp.p_short = bp.p_second;
+            BWT_TRY(launch_sw_band(bp, R, d_ref2, st.d_desc, fast_list, fast_n, st.d_list_fast3, &st.d_ctr->n_fast3, st.d_band_scratch,
+                                   st.d_out, st.d_ctr, st.d_cig_tmp, st.cig_cap, stream));
+            st.launches += 1;
+            fast_list = st.d_list_fast3; fast_n = &st.d_ctr->n_fast3;
+        }
+        if (sort && !sort_first) BWT_TRY(sort_list());
     }
     CU_TRY(cudaEventRecord(st.ev_k0, stream));
     if (!st.small) {

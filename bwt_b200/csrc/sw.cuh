@@ -27,7 +27,7 @@ struct SwCounters {
     uint32_t general_done, pad;
     unsigned long long band_calls, band_cells;   // pairs settled by sw_band_kernel and the cells sw:sw/2 fills for them (both INCLUDED in sw_calls / cells)
     unsigned long long band_cells_filled;        // cells of the bands it filled instead
-    uint32_t n_fast2, pad3;                      // cursor of the list sw_band_kernel leaves to sw_fast_kernel
+    uint32_t n_fast2, n_fast3;                   // cursors of the lists sw_band_kernel (first / second pass) leaves to sw_fast_kernel
     // The temporary CIGAR arena is handed out from SW_CIG_SHARDS regions, each with its cursor on its own 128-byte line
     // (chosen by block): millions of appends to ONE cursor serialise in a single L2 slice at ~1.75 ns each.
     uint32_t cig_sub[64 * 32];
@@ -68,7 +68,7 @@ struct SwStage {
     uint8_t *d_swd_scratch = nullptr;  // slices of sw_double_kernel
     size_t swd_scratch_bytes = 0;
     uint32_t *d_list_sorted = nullptr; // d_list_fast ordered by (Lq, Lr)
-    uint32_t *d_list_fast2 = nullptr;  // what sw_band_kernel leaves to sw_fast_kernel
+    uint32_t *d_list_fast2 = nullptr, *d_list_fast3 = nullptr;  // what sw_band_kernel's first / second pass leaves
     uint32_t *d_band_scratch = nullptr; // direction words of sw_band_kernel
     size_t band_scratch_words = 0;
     uint32_t *d_sort_bins = nullptr;   // its counting-sort bins
@@ -97,7 +97,7 @@ int launch_sw_double(const SwdPlan &pl, const DevReads &R, const uint8_t *d_rbas
                      char *d_cig, uint32_t cig_cap, cudaStream_t stream);
 
 // thread-per-pair banded table with a certificate (swb.cu): plain pairs whose best alignment has a gap
-struct SwbPlan { int rows_cap, blocks; uint64_t scratch_words; };
+struct SwbPlan { int rows_cap, blocks, p_short, p_second, p_prev; uint64_t scratch_words; };
 int sw_band_plan(int max_lq, int sms, uint32_t n_cap, SwbPlan *pl);
 int launch_sw_band(const SwbPlan &pl, const DevReads &R, const uint32_t *d_ref2, const SwDesc *d_desc, const uint32_t *d_list,
                    const uint32_t *d_n_list, uint32_t *d_next, uint32_t *d_n_next, uint32_t *d_scratch, SwOut *d_out,

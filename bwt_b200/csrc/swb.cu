@@ -6,9 +6,11 @@
 // gap, penalty beyond the budget, window slack beyond the widest band, reads beyond the scratch rows) are appended to
 // `next`, the list sw_fast_kernel fills the whole table for.
 //
-// Cost: Lq x WB cells of ~20 integer instructions against Lq x Lr cells of 7 in sw_fast_kernel -- 600 cells instead of
-// 10,100 for a 100 bp read with one indel.
+// Cost: Lq x WB cells of ~23 integer instructions against Lq x Lr cells of 7 in sw_fast_kernel -- 600 cells instead of
+// 10,100 for a 100 bp read with one indel.  Launched twice per batch: a small penalty budget (narrow band) on the list
+// ordered by shape, then a larger one on what the first pass left (sw.cu, sw_stage_enqueue).
 #include <algorithm>
+#include <cstdlib>
 
 #include "sw.cuh"
 #include "swb_core.cuh"
@@ -17,6 +19,8 @@ namespace {
 
 constexpr int SWB_BLOCK = 128;
 constexpr int SWB_MIN_BLOCKS = 5;
+constexpr int SWB_P_SHORT = 9;
+constexpr int SWB_P_SECOND = 15;
 
 struct SwbParams {
     DevReads R;
@@ -27,6 +31,8 @@ struct SwbParams {
     uint32_t *next, *n_next;
     uint32_t *dirs;               // per block: rows_cap x SWB_BLOCK words
     int rows_cap;
+    int p_short;                  // penalty budget of reads up to 128 bp (swb_core.cuh)
+    int p_prev;                   // second pass: the budget the pairs of this list were already tried with (0: first pass)
     SwCounters *ctr;
     char *cig;
     uint32_t cig_cap;
@@ -44,7 +50,7 @@ template <int WB>
 __device__ __forceinline__ bool band_pair(const SwbParams &p, const SwDesc &d, uint32_t k, uint32_t *__restrict__ dirs) {
     constexpr int B = SWB_BLOCK;
     const int lq = d.lq, lr = d.lr;
-    const int lo = -swb::kk_of(lq);
+    const int lo = -swb::kk_of(lq, p.p_short);
     const uint32_t *pkr = p.R.pk + __ldg(p.R.woff + d.read);
     swb::Band<WB> s;
     swb::init<WB>(s, lo, lr);
@@ -68,7 +74,7 @@ __device__ __forceinline__ bool band_pair(const SwbParams &p, const SwDesc &d, u
     for (; i <= last_full; i++) dirs[(size_t)(i - 1) * B] = swb::row<WB, false>(s, i, lo, lr, neq_of(i));
     for (; i <= lq; i++) dirs[(size_t)(i - 1) * B] = swb::row<WB, true>(s, i, lo, lr, neq_of(i));
     int score = 0, b_end = 0;
-    if (!swb::finish<WB>(s, lq, lo, lr, &score, &b_end)) return false;
+    if (!swb::finish<WB>(s, lq, lo, lr, p.p_short, &score, &b_end)) return false;
     uint16_t runs[swb::MAX_RUNS];
     // the walk reads the direction words eight rows at a time (independent loads; a walk mostly moves up one row per step)
     uint32_t dw[8];
@@ -111,7 +117,8 @@ __global__ void __launch_bounds__(SWB_BLOCK, SWB_MIN_BLOCKS) sw_band_kernel(SwbP
         int need = 0;
         if (todo) {
             k = p.list[e]; d = p.desc[k];
-            if (d.lq >= 4 && d.lq <= p.rows_cap && d.lr >= d.lq) { need = swb::need_of(d.lq, d.lr); if (need > 16) need = 0; }
+            if (d.lq >= 4 && d.lq <= p.rows_cap && d.lr >= d.lq) { need = swb::need_of(d.lq, d.lr, p.p_short); if (need > 16) need = 0; }
+            if (p.p_prev && swb::pmax_of(d.lq, p.p_short) <= swb::pmax_of(d.lq, p.p_prev)) need = 0;      // nothing new to try
         }
         // one instantiation per warp: the widest band any of its pairs needs (lists ordered by shape keep warps uniform)
         const int wneed = __reduce_max_sync(FULL, need);
@@ -152,6 +159,13 @@ __global__ void __launch_bounds__(SWB_BLOCK, SWB_MIN_BLOCKS) sw_band_kernel(SwbP
 
 int sw_band_plan(int max_lq, int sms, uint32_t n_cap, SwbPlan *pl) {
     pl->rows_cap = std::min(std::max(max_lq, 4), 256);
+    // BWT_SW_BAND_P: penalty budget of reads up to 128 bp in the first pass (9, 12 or 15), BWT_SW_BAND_P2: in a second pass
+    // over what the first one left (0 = no second pass); A/B in profiles/r2b8_band_budget.log, r2b9_band_passes.log
+    const char *e = getenv("BWT_SW_BAND_P"), *e2 = getenv("BWT_SW_BAND_P2");
+    const int pv = e && *e ? atoi(e) : SWB_P_SHORT, pv2 = e2 && *e2 ? atoi(e2) : SWB_P_SECOND;
+    pl->p_short = pv <= 9 ? 9 : pv <= 12 ? 12 : 15;
+    pl->p_second = pv2 <= pl->p_short ? 0 : pv2 <= 12 ? 12 : 15;
+    pl->p_prev = 0;
     const uint64_t want = ((uint64_t)n_cap + SWB_BLOCK - 1) / SWB_BLOCK;
     pl->blocks = (int)std::max<uint64_t>(1, std::min<uint64_t>(want, (uint64_t)sms * SWB_MIN_BLOCKS));
     pl->scratch_words = (uint64_t)pl->blocks * SWB_BLOCK * pl->rows_cap;
@@ -164,7 +178,7 @@ int launch_sw_band(const SwbPlan &pl, const DevReads &R, const uint32_t *d_ref2,
     SwbParams p;
     p.R = R; p.ref2 = d_ref2; p.desc = d_desc; p.out = d_out;
     p.list = d_list; p.n_list = d_n_list; p.next = d_next; p.n_next = d_n_next;
-    p.dirs = d_scratch; p.rows_cap = pl.rows_cap;
+    p.dirs = d_scratch; p.rows_cap = pl.rows_cap; p.p_short = pl.p_short; p.p_prev = pl.p_prev;
     p.ctr = d_ctr; p.cig = d_cig; p.cig_cap = cig_cap;
     sw_band_kernel<<<pl.blocks, SWB_BLOCK, 0, stream>>>(p);
     K_CHECK(stream, "sw_band_kernel");

@@ -49,11 +49,13 @@ constexpr int MAX_RUNS = 40;                 // CIGAR runs a certified path can 
 SWB_HD int imax(int a, int b) { return a > b ? a : b; }
 SWB_HD int imin(int a, int b) { return a < b ? a : b; }
 
-// penalty budget by read length (the band's half width grows with it) and the row-threshold limit 2*(Lq div 2)
-SWB_HD int pmax_of(int lq) { return imin(lq <= 128 ? 9 : lq <= 192 ? 12 : 15, 2 * (lq >> 1)); }
-SWB_HD int kk_of(int lq) { return imax(0, (pmax_of(lq) - 1) / 3); }
+// penalty budget by read length (the band's half width grows with it) and the row-threshold limit 2*(Lq div 2);
+// p_short = the budget of reads up to 128 bp (9: one indel and a substitution, band of Dd + 5 diagonals; 12: one indel and
+// two substitutions, Dd + 7) -- any budget is sound, it trades cells per pair against pairs left to the full table
+SWB_HD int pmax_of(int lq, int p_short) { return imin(lq <= 128 ? p_short : lq <= 192 ? imax(12, p_short) : 15, 2 * (lq >> 1)); }
+SWB_HD int kk_of(int lq, int p_short) { return imax(0, (pmax_of(lq, p_short) - 1) / 3); }
 // diagonals the band must hold: -k .. dd + k
-SWB_HD int need_of(int lq, int lr) { return (lr - lq) + 2 * kk_of(lq) + 1; }
+SWB_HD int need_of(int lq, int lr, int p_short) { return (lr - lq) + 2 * kk_of(lq, p_short) + 1; }
 
 template <int WB>
 struct Band {
@@ -112,7 +114,7 @@ SWB_UNROLL
 // after row Lq: the leftmost best end of the affine table; certified <=> within the budget, untainted, and the
 // reference-rule table agrees on the value (it must: kept as a guard)
 template <int WB>
-SWB_HD bool finish(const Band<WB> &s, int lq, int lo, int lr, int *score, int *b_end) {
+SWB_HD bool finish(const Band<WB> &s, int lq, int lo, int lr, int p_short, int *score, int *b_end) {
     int best = NEGK, bb = -1;
 SWB_UNROLL
     for (int b = 0; b < WB; b++) {
@@ -124,7 +126,7 @@ SWB_UNROLL
     int hk = NEGK, kk = NEGK;
 SWB_UNROLL
     for (int b = 0; b < WB; b++) if (b == bb) { hk = s.H[b]; kk = s.K[b]; }
-    if (2 * lq - best > pmax_of(lq)) return false;
+    if (2 * lq - best > pmax_of(lq, p_short)) return false;
     if (hk & 1) return false;
     if ((kk >> 2) != best) return false;
     *score = best; *b_end = bb;

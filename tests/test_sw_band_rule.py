@@ -34,12 +34,12 @@ def host():
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-I", os.path.join(ROOT, "bwt_b200", "csrc"),
                                src[0], "-o", so])
     lib = C.CDLL(so)
-    lib.swb_host.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_int, C.c_int, C.POINTER(C.c_int), C.c_char_p, C.c_int]
+    lib.swb_host.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.c_char_p, C.c_int]
 
-    def run(q, r, wb=0):
+    def run(q, r, wb=0, p_short=9):
         sc = C.c_int()
         buf = C.create_string_buffer(1024)
-        rc = lib.swb_host(q, len(q), r, len(r), wb, C.byref(sc), buf, 1024)
+        rc = lib.swb_host(q, len(q), r, len(r), wb, p_short, C.byref(sc), buf, 1024)
         assert rc >= 0
         return (sc.value, buf.value.decode()) if rc == 1 else None
     return run
@@ -92,12 +92,14 @@ def cases(rng, n, lmax=48):
             yield rs(lq, alpha), rs(lq + dd, alpha)
 
 
-@pytest.mark.parametrize("seed,n,lmax", [(9001, 60000, 48), (9002, 25000, 130), (9003, 6000, 256)])
-def test_band_agrees_with_sw_on_adversarial_pairs(host, seed, n, lmax):
+@pytest.mark.parametrize("seed,n,lmax,p_short", [(9001, 60000, 48, 9), (9002, 25000, 130, 9), (9003, 6000, 256, 9),
+                                                 (9004, 40000, 48, 12), (9005, 20000, 130, 12), (9006, 30000, 60, 15)])
+def test_band_agrees_with_sw_on_adversarial_pairs(host, seed, n, lmax, p_short):
+    """p_short = the penalty budget of reads up to 128 bp (BWT_SW_BAND_P of the kernel): every budget must be exact"""
     rng = random.Random(seed)
     settled = gapped = 0
     for q, r in cases(rng, n, lmax):
-        got = host(q, r)
+        got = host(q, r, 0, p_short)
         if got is None:
             continue
         want = c_sw(q, r)

